@@ -1,0 +1,113 @@
+"""ctypes binding of libdformer_b200.so (the C ABI declared in include/dfb200.h).
+
+There is deliberately NO fallback: if the shared library is missing the import raises, and every
+launcher raises on a non-zero return code (dfb200_last_error() text included)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdformer_b200.so")
+
+c_void_p, c_int, c_long, c_float, c_double = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_double
+
+
+class GemmArgs(ctypes.Structure):
+    _fields_ = [
+        ("A", c_void_p), ("B", c_void_p), ("C", c_void_p), ("bias", c_void_p),
+        ("lda", c_long), ("ldb", c_long), ("ldc", c_long),
+        ("strideA", c_long), ("strideB", c_long), ("strideC", c_long),
+        ("M", c_int), ("N", c_int), ("K", c_int), ("batch", c_int),
+        ("batch_inner", c_int),
+        ("strideA_in", c_long), ("strideB_in", c_long), ("strideC_in", c_long),
+        ("transA", c_int), ("transB", c_int),
+        ("a_dtype", c_int), ("b_dtype", c_int), ("out_dtype", c_int),
+        ("act", c_int), ("act_col_start", c_int),
+        ("accumulate", c_int), ("backend", c_int), ("splitk", c_int),
+        ("alpha", c_float),
+    ]
+
+
+class PackEntry(ctypes.Structure):
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("rows", c_int), ("cols", c_int), ("dst_ld", c_int), ("kind", c_int)]
+
+
+P, I, L, F, D = c_void_p, c_int, c_long, c_float, c_double
+# name -> argument ctypes (all return int unless noted)
+SIGNATURES = {
+    "dfb200_gemm": [ctypes.POINTER(GemmArgs), P],
+    "dfb200_colsum": [P, I, L, I, I, P, I, P],
+    "dfb200_pack_params": [P, I, I, I, P],
+    "dfb200_unpack_conv_grad": [P, I, I, I, P, P],
+    "dfb200_layernorm_fwd": [P, P, P, F, I, I, P, I, P, P, P],
+    "dfb200_layernorm_bwd": [P, I, P, P, P, P, I, I, P, I, P, P, P],
+    "dfb200_dwconv_fwd": [P, I, P, P, I, I, I, I, I, I, I, P, P],
+    "dfb200_dwconv_bwd": [P, P, I, P, P, I, I, I, I, I, I, I, P, P, P, P, P],
+    "dfb200_mul_fwd": [P, L, P, L, P, L, I, I, I, P],
+    "dfb200_mul_bwd": [P, L, P, L, P, L, P, L, P, L, I, I, I, P],
+    "dfb200_scale_residual_fwd": [P, P, I, P, P, I, I, I, P, P],
+    "dfb200_scale_residual_bwd": [P, P, I, P, P, I, I, I, P, P, P],
+    "dfb200_pool7_fwd": [P, I, P, I, I, I, I, I, P, P],
+    "dfb200_pool7_bwd": [P, I, I, I, I, I, I, P, P, P],
+    "dfb200_gaa_fwd": [P, P, I, I, I, I, I, P, P, P],
+    "dfb200_gaa_bwd": [P, P, P, P, I, I, I, I, I, P, P, P, P],
+    "dfb200_resize_fwd": [P, I, I, I, I, I, P, I, I, I, L, I, P],
+    "dfb200_resize_bwd": [P, I, L, I, I, I, I, I, I, I, P, I, I, P],
+    "dfb200_im2col3x3s2_fwd": [P, I, L, L, L, L, I, I, I, I, P, I, I, P],
+    "dfb200_im2col3x3s2_bwd": [P, I, I, I, I, I, I, P, I, P],
+    "dfb200_bn_stats": [P, I, I, I, P, P, P],
+    "dfb200_bn_finalize": [P, P, D, F, F, I, P, P, P, P, P],
+    "dfb200_bn_eval_stats": [P, P, F, I, P, P, P],
+    "dfb200_bn_apply": [P, I, P, P, P, P, P, I, P, I, I, I, P, I, P],
+    "dfb200_bn_bwd_reduce": [P, I, P, I, P, P, P, P, P, I, P, I, I, I, P, P, P, P],
+    "dfb200_bn_bwd_apply": [P, I, P, I, P, P, P, P, P, F, I, I, I, P, I, P],
+    "dfb200_normalize_cols": [P, I, I, I, P, P, P],
+    "dfb200_softmax_rows": [P, I, I, P, P],
+    "dfb200_softmax_rows_bwd": [P, P, I, I, P, P],
+    "dfb200_mu_update": [P, P, P, F, L, P, P],
+    "dfb200_mu_update_bwd": [P, P, P, P, F, L, P, I, P, P, P],
+    "dfb200_cast": [P, I, P, I, L, P],
+    "dfb200_axpy": [P, I, F, P, I, L, P],
+    "dfb200_upsample_ce_fwd": [P, I, I, I, I, I, I, I, P, I, P, P, P, P],
+    "dfb200_ce_finalize": [P, P, P],
+    "dfb200_upsample_ce_bwd": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, I, P],
+    "dfb200_adamw": [P, P, P, P, L, F, F, F, F, F, F, F, F, P],
+}
+
+
+class _Lib:
+    def __init__(self):
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"dformer_b200: CUDA extension {LIB_PATH} is missing -- build it with `make` "
+                "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
+        self.cdll = ctypes.CDLL(LIB_PATH)
+        self.cdll.dfb200_last_error.restype = ctypes.c_char_p
+        self.cdll.dfb200_version.restype = c_int
+        for name, args in SIGNATURES.items():
+            fn = getattr(self.cdll, name)
+            fn.argtypes = args
+            fn.restype = c_int
+            setattr(self, name[len("dfb200_"):], self._wrap(name, fn))
+
+    def _wrap(self, name, fn):
+        err = self.cdll.dfb200_last_error
+
+        def call(*a):
+            rc = fn(*a)
+            if rc != 0:
+                raise RuntimeError(f"{name} failed ({rc}): {err().decode()}")
+        call.__name__ = name
+        return call
+
+    def version(self):
+        return self.cdll.dfb200_version()
+
+
+_lib = None
+
+
+def lib() -> _Lib:
+    global _lib
+    if _lib is None:
+        _lib = _Lib()
+    return _lib

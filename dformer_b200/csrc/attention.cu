@@ -1,0 +1,299 @@
+// Global Awareness Attention pieces (DFormer.py:107-108,120-131):
+//   pool7      AdaptiveAvgPool2d((7,7)) of cat[LN(x), LN(x_e)] on channels-last tensors
+//   gaa        49 pooled queries attend over all H*W pixel keys/values (softmax over pixels)
+//   resize     bilinear align_corners=False resampling into a column slice of a wider buffer
+#include <string.h>
+
+#include "common.cuh"
+#include "dfb200_internal.h"
+
+namespace {
+
+__device__ __forceinline__ int win_start(int i, int n) { return (i * n) / 7; }
+__device__ __forceinline__ int win_end(int i, int n) { return ((i + 1) * n + 6) / 7; }
+
+template <typename T>
+__global__ void pool7_fwd_kernel(const T* __restrict__ xn, int C1, const T* __restrict__ en, int C2, int B, int H, int W, T* __restrict__ out) {
+  const int Ct = C1 + C2, nvec = Ct >> 3;
+  const long n = (long)B * 49 * nvec;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % nvec) * 8;
+    const int cell = (int)((i / nvec) % 49);
+    const int b = (int)(i / ((long)nvec * 49));
+    const int py = cell / 7, px = cell % 7;
+    const int y0 = win_start(py, H), y1 = win_end(py, H), x0 = win_start(px, W), x1 = win_end(px, W);
+    const T* src; int Cs, cc;
+    if (c < C1) { src = xn; Cs = C1; cc = c; } else { src = en; Cs = C2; cc = c - C1; }
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) {
+        float v[8];
+        Vec8<T>::load(src + (((long)b * H + y) * W + x) * Cs + cc, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+    const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    Vec8<T>::store(out + ((long)b * 49 + cell) * Ct + c, acc);
+  }
+}
+
+// gather form: each pixel belongs to <= 2 x 2 (overlapping) windows
+template <typename T>
+__global__ void pool7_bwd_kernel(const T* __restrict__ dout, int C1, int C2, int B, int H, int W, T* __restrict__ dxn, T* __restrict__ den) {
+  const int Ct = C1 + C2, nvec = Ct >> 3;
+  const long n = (long)B * H * W * nvec;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % nvec) * 8;
+    const long pix = i / nvec;
+    const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long)W * H));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int py = 0; py < 7; ++py) {
+      const int y0 = win_start(py, H), y1 = win_end(py, H);
+      if (y < y0 || y >= y1) continue;
+      for (int px = 0; px < 7; ++px) {
+        const int x0 = win_start(px, W), x1 = win_end(px, W);
+        if (x < x0 || x >= x1) continue;
+        float v[8];
+        Vec8<T>::load(dout + ((long)b * 49 + py * 7 + px) * Ct + c, v);
+        const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], inv, acc[j]);
+      }
+    }
+    if (c < C1) Vec8<T>::store(dxn + pix * C1 + c, acc);
+    else Vec8<T>::store(den + pix * C2 + (c - C1), acc);
+  }
+}
+
+// ------------------------------------------------------------------ bilinear resize
+struct Lerp { int i0, i1; float w1; };
+__device__ __forceinline__ Lerp lerp_coord(int o, int n_in, int n_out) {
+  Lerp l;
+  if (n_in == n_out) { l.i0 = o; l.i1 = o; l.w1 = 0.f; return l; }
+  const float scale = (float)n_in / (float)n_out;
+  float src = ((float)o + 0.5f) * scale - 0.5f;
+  if (src < 0.f) src = 0.f;
+  l.i0 = min((int)src, n_in - 1);
+  l.i1 = min(l.i0 + 1, n_in - 1);
+  l.w1 = src - (float)l.i0;
+  return l;
+}
+
+template <typename TI, typename TO>
+__global__ void resize_fwd_kernel(const TI* __restrict__ in, int B, int Hi, int Wi, int C, TO* __restrict__ out, int Ho, int Wo, long ldo, int col0) {
+  const int nvec = C >> 3;
+  const long n = (long)B * Ho * Wo * nvec;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % nvec) * 8;
+    const long pix = i / nvec;
+    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long)Wo * Ho));
+    const Lerp ly = lerp_coord(oy, Hi, Ho), lx = lerp_coord(ox, Wi, Wo);
+    const TI* base = in + (long)b * Hi * Wi * C + c;
+    float v00[8], v01[8], v10[8], v11[8], o[8];
+    Vec8<TI>::load(base + ((long)ly.i0 * Wi + lx.i0) * C, v00);
+    Vec8<TI>::load(base + ((long)ly.i0 * Wi + lx.i1) * C, v01);
+    Vec8<TI>::load(base + ((long)ly.i1 * Wi + lx.i0) * C, v10);
+    Vec8<TI>::load(base + ((long)ly.i1 * Wi + lx.i1) * C, v11);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float top = (1.f - lx.w1) * v00[j] + lx.w1 * v01[j];
+      const float bot = (1.f - lx.w1) * v10[j] + lx.w1 * v11[j];
+      o[j] = (1.f - ly.w1) * top + ly.w1 * bot;
+    }
+    Vec8<TO>::store(out + pix * ldo + col0 + c, o);
+  }
+}
+
+// gather form of the adjoint: each input pixel scans the output pixels that can reference it
+template <typename TO, typename TI>
+__global__ void resize_bwd_kernel(const TO* __restrict__ dout, long ldo, int col0, int B, int Hi, int Wi, int C, int Ho, int Wo, TI* __restrict__ din,
+                                  int accumulate) {
+  const int nvec = C >> 3;
+  const long n = (long)B * Hi * Wi * nvec;
+  const float ry = (float)Ho / (float)Hi, rx = (float)Wo / (float)Wi;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % nvec) * 8;
+    const long pix = i / nvec;
+    const int ix = (int)(pix % Wi), iy = (int)((pix / Wi) % Hi), b = (int)(pix / ((long)Wi * Hi));
+    int oy_lo = max(0, (int)floorf((iy - 1) * ry) - 1), oy_hi = min(Ho - 1, (int)ceilf((iy + 2) * ry) + 1);
+    int ox_lo = max(0, (int)floorf((ix - 1) * rx) - 1), ox_hi = min(Wo - 1, (int)ceilf((ix + 2) * rx) + 1);
+    if (iy == 0) oy_lo = 0;
+    if (iy == Hi - 1) oy_hi = Ho - 1;
+    if (ix == 0) ox_lo = 0;
+    if (ix == Wi - 1) ox_hi = Wo - 1;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      const Lerp ly = lerp_coord(oy, Hi, Ho);
+      const float wy = (ly.i0 == iy ? 1.f - ly.w1 : 0.f) + (ly.i1 == iy ? ly.w1 : 0.f);
+      if (wy == 0.f) continue;
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        const Lerp lx = lerp_coord(ox, Wi, Wo);
+        const float wx = (lx.i0 == ix ? 1.f - lx.w1 : 0.f) + (lx.i1 == ix ? lx.w1 : 0.f);
+        if (wx == 0.f) continue;
+        float g[8];
+        Vec8<TO>::load(dout + (((long)b * Ho + oy) * Wo + ox) * ldo + col0 + c, g);
+        const float w = wy * wx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, g[j], acc[j]);
+      }
+    }
+    TI* dst = din + pix * C + c;
+    if (accumulate) {
+      float old[8];
+      Vec8<TI>::load(dst, old);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += old[j];
+    }
+    Vec8<TI>::store(dst, acc);
+  }
+}
+
+inline int ew_grid(long n) {
+  long b = (n + 255) / 256;
+  if (b < 1) b = 1;
+  const long cap = 148L * 16;
+  return (int)(b > cap ? cap : b);
+}
+
+// dS = P * (dP - rowsum(dP * P)), in place on dP
+__global__ void softmax_bwd_inplace_kernel(float* __restrict__ dP, const float* __restrict__ P, int rows, int cols) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* g = dP + (long)row * cols;
+  const float* p = P + (long)row * cols;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s = fmaf(g[c], p[c], s);
+  s = warp_sum(s);
+  for (int c = lane; c < cols; c += 32) g[c] = p[c] * (g[c] - s);
+}
+
+}  // namespace
+
+#define ST reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" int dfb200_pool7_fwd(const void* xn, int C1, const void* en, int C2, int dtype, int B, int H, int W, void* out, void* stream) {
+  DFB_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0, "pool7: channels must be multiples of 8");
+  DFB_DISPATCH_DTYPE(dtype, T, {
+    pool7_fwd_kernel<T><<<ew_grid((long)B * 49 * (C1 + C2) / 8), 256, 0, ST>>>((const T*)xn, C1, (const T*)en, C2, B, H, W, (T*)out);
+  });
+  return dfb_check_launch("pool7_fwd");
+}
+extern "C" int dfb200_pool7_bwd(const void* dout, int C1, int C2, int dtype, int B, int H, int W, void* dxn, void* den, void* stream) {
+  DFB_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0, "pool7: channels must be multiples of 8");
+  DFB_DISPATCH_DTYPE(dtype, T, {
+    pool7_bwd_kernel<T><<<ew_grid((long)B * H * W * (C1 + C2) / 8), 256, 0, ST>>>((const T*)dout, C1, C2, B, H, W, (T*)dxn, (T*)den);
+  });
+  return dfb_check_launch("pool7_bwd");
+}
+
+extern "C" int dfb200_resize_fwd(const void* in, int in_dtype, int B, int Hi, int Wi, int C, void* out, int out_dtype, int Ho, int Wo, long ldo, int col0,
+                                 void* stream) {
+  DFB_REQUIRE(C % 8 == 0 && ldo % 8 == 0 && col0 % 8 == 0, "resize: C, ldo, col0 must be multiples of 8");
+  const int g = ew_grid((long)B * Ho * Wo * C / 8);
+#define L(TI, TO) resize_fwd_kernel<TI, TO><<<g, 256, 0, ST>>>((const TI*)in, B, Hi, Wi, C, (TO*)out, Ho, Wo, ldo, col0)
+  if (in_dtype == 0 && out_dtype == 0) L(float, float);
+  else if (in_dtype == 0 && out_dtype == 1) L(float, bf16);
+  else if (in_dtype == 1 && out_dtype == 1) L(bf16, bf16);
+  else if (in_dtype == 1 && out_dtype == 0) L(bf16, float);
+  else { dfb_set_error("resize: bad dtypes"); return DFB_ERR_ARG; }
+#undef L
+  return dfb_check_launch("resize_fwd");
+}
+extern "C" int dfb200_resize_bwd(const void* dout, int out_dtype, long ldo, int col0, int B, int Hi, int Wi, int C, int Ho, int Wo, void* din, int in_dtype,
+                                 int accumulate, void* stream) {
+  DFB_REQUIRE(C % 8 == 0 && ldo % 8 == 0 && col0 % 8 == 0, "resize: C, ldo, col0 must be multiples of 8");
+  const int g = ew_grid((long)B * Hi * Wi * C / 8);
+#define L(TO, TI) resize_bwd_kernel<TO, TI><<<g, 256, 0, ST>>>((const TO*)dout, ldo, col0, B, Hi, Wi, C, Ho, Wo, (TI*)din, accumulate)
+  if (in_dtype == 0 && out_dtype == 0) L(float, float);
+  else if (in_dtype == 0 && out_dtype == 1) L(bf16, float);
+  else if (in_dtype == 1 && out_dtype == 1) L(bf16, bf16);
+  else if (in_dtype == 1 && out_dtype == 0) L(float, bf16);
+  else { dfb_set_error("resize: bad dtypes"); return DFB_ERR_ARG; }
+#undef L
+  return dfb_check_launch("resize_bwd");
+}
+
+// ------------------------------------------------------------------ GAA (batched SIMT GEMMs + row softmax)
+static dfb200_gemm_args gaa_args(int B, int heads) {
+  dfb200_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.batch = B; g.batch_inner = heads;
+  g.backend = DFB200_BACKEND_SIMT; g.splitk = 1;
+  g.act_col_start = 0;
+  return g;
+}
+
+extern "C" int dfb200_gaa_fwd(const void* m, const void* kv, int dtype, int B, int HW, int heads, int d, float* out, float* probs, void* stream) {
+  const int Cp = heads * d;
+  const size_t es = dtype == 1 ? 2 : 4;
+  // S = scale * Q K^T   (per (b, head):  [49, d] x [HW, d]^T)
+  dfb200_gemm_args g = gaa_args(B, heads);
+  g.A = m; g.lda = Cp; g.strideA = 49L * Cp; g.strideA_in = d; g.a_dtype = dtype;
+  g.B = kv; g.ldb = 2L * Cp; g.strideB = (long)HW * 2 * Cp; g.strideB_in = d; g.b_dtype = dtype; g.transB = 1;
+  g.C = probs; g.ldc = HW; g.strideC = (long)heads * 49 * HW; g.strideC_in = 49L * HW; g.out_dtype = 0;
+  g.M = 49; g.N = HW; g.K = d; g.alpha = 1.0f / sqrtf((float)d);
+  int rc = dfb_gemm_simt(g, ST);
+  if (rc) return rc;
+  rc = dfb200_softmax_rows(probs, B * heads * 49, HW, probs, stream);
+  if (rc) return rc;
+  // O = P V  ([49, HW] x [HW, d]) -> out[b, :, head*d : (head+1)*d]
+  g = gaa_args(B, heads);
+  g.A = probs; g.lda = HW; g.strideA = (long)heads * 49 * HW; g.strideA_in = 49L * HW; g.a_dtype = 0;
+  g.B = (const char*)kv + (size_t)Cp * es; g.ldb = 2L * Cp; g.strideB = (long)HW * 2 * Cp; g.strideB_in = d; g.b_dtype = dtype; g.transB = 0;
+  g.C = out; g.ldc = Cp; g.strideC = 49L * Cp; g.strideC_in = d; g.out_dtype = 0;
+  g.M = 49; g.N = d; g.K = HW;
+  if (HW >= 1024) {   // long reduction, tiny output: split it and accumulate with fp32 atomics
+    cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * 49 * Cp, ST);
+    g.splitk = dfb_cdiv(HW, 256); g.accumulate = 1;
+  }
+  return dfb_gemm_simt(g, ST);
+}
+
+extern "C" int dfb200_gaa_bwd(const float* dout, const void* m, const void* kv, const float* probs, int dtype, int B, int HW, int heads, int d, float* dm,
+                              void* dkv, float* scratch, void* stream) {
+  const int Cp = heads * d;
+  const size_t es = dtype == 1 ? 2 : 4;
+  const float scale = 1.0f / sqrtf((float)d);
+  float* dP = scratch;
+  // dV = P^T dO  -> dkv[:, Cp + head*d ...]
+  dfb200_gemm_args g = gaa_args(B, heads);
+  g.A = probs; g.lda = HW; g.strideA = (long)heads * 49 * HW; g.strideA_in = 49L * HW; g.a_dtype = 0; g.transA = 1;
+  g.B = dout; g.ldb = Cp; g.strideB = 49L * Cp; g.strideB_in = d; g.b_dtype = 0; g.transB = 0;
+  g.C = (char*)dkv + (size_t)Cp * es; g.ldc = 2L * Cp; g.strideC = (long)HW * 2 * Cp; g.strideC_in = d; g.out_dtype = dtype;
+  g.M = HW; g.N = d; g.K = 49;
+  int rc = dfb_gemm_simt(g, ST);
+  if (rc) return rc;
+  // dP = dO V^T
+  g = gaa_args(B, heads);
+  g.A = dout; g.lda = Cp; g.strideA = 49L * Cp; g.strideA_in = d; g.a_dtype = 0;
+  g.B = (const char*)kv + (size_t)Cp * es; g.ldb = 2L * Cp; g.strideB = (long)HW * 2 * Cp; g.strideB_in = d; g.b_dtype = dtype; g.transB = 1;
+  g.C = dP; g.ldc = HW; g.strideC = (long)heads * 49 * HW; g.strideC_in = 49L * HW; g.out_dtype = 0;
+  g.M = 49; g.N = HW; g.K = d;
+  rc = dfb_gemm_simt(g, ST);
+  if (rc) return rc;
+  // dS = P * (dP - rowsum(dP*P))   (in place)
+  softmax_bwd_inplace_kernel<<<dfb_cdiv(B * heads * 49, 8), 256, 0, ST>>>(dP, probs, B * heads * 49, HW);
+  rc = dfb_check_launch("gaa softmax bwd");
+  if (rc) return rc;
+  // dQ = scale * dS K
+  g = gaa_args(B, heads);
+  g.A = dP; g.lda = HW; g.strideA = (long)heads * 49 * HW; g.strideA_in = 49L * HW; g.a_dtype = 0;
+  g.B = kv; g.ldb = 2L * Cp; g.strideB = (long)HW * 2 * Cp; g.strideB_in = d; g.b_dtype = dtype; g.transB = 0;
+  g.C = dm; g.ldc = Cp; g.strideC = 49L * Cp; g.strideC_in = d; g.out_dtype = 0;
+  g.M = 49; g.N = d; g.K = HW; g.alpha = scale;
+  if (HW >= 1024) {
+    cudaMemsetAsync(dm, 0, sizeof(float) * (size_t)B * 49 * Cp, ST);
+    g.splitk = dfb_cdiv(HW, 256); g.accumulate = 1;
+  }
+  rc = dfb_gemm_simt(g, ST);
+  if (rc) return rc;
+  // dK = scale * dS^T Q -> dkv[:, head*d ...]
+  g = gaa_args(B, heads);
+  g.A = dP; g.lda = HW; g.strideA = (long)heads * 49 * HW; g.strideA_in = 49L * HW; g.a_dtype = 0; g.transA = 1;
+  g.B = m; g.ldb = Cp; g.strideB = 49L * Cp; g.strideB_in = d; g.b_dtype = dtype; g.transB = 0;
+  g.C = dkv; g.ldc = 2L * Cp; g.strideC = (long)HW * 2 * Cp; g.strideC_in = d; g.out_dtype = dtype;
+  g.M = HW; g.N = d; g.K = 49; g.alpha = scale;
+  return dfb_gemm_simt(g, ST);
+}

@@ -1,0 +1,382 @@
+// HBM-bound element-wise / column-reduction kernels: parameter packing, gating, layer-scale residual,
+// NMF multiplicative updates, softmax rows, casts, AdamW.  All are single-pass, 16-byte vectorised
+// where the shape allows (C % 8 == 0), grid-stride, fp32 math.
+#include "common.cuh"
+#include "dfb200_internal.h"
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+inline int ew_grid(long n, int per_thread = 1) {
+  long b = (n + (long)EW_THREADS * per_thread - 1) / ((long)EW_THREADS * per_thread);
+  if (b < 1) b = 1;
+  const long cap = 148L * 16;
+  return (int)(b > cap ? cap : b);
+}
+
+// ------------------------------------------------------------------ column reductions
+// Flat mapping: active threads A = (T / nvec) * nvec so that thread t always owns channel-vector t % nvec
+// while consecutive threads touch consecutive 16/32-byte vectors (full coalescing across row boundaries).
+template <typename T, int NACC, typename F>
+__device__ __forceinline__ void colreduce_body(int M, int C, int rows_per_block, F f, float* const* outs, float* smem) {
+  const int nvec_all = C >> 3;
+  const int v0 = blockIdx.y * EW_THREADS;                         // channel-vector chunk
+  const int nvec = min(EW_THREADS, nvec_all - v0);
+  const int rl_count = EW_THREADS / nvec;
+  const int active = rl_count * nvec;
+  const int t = threadIdx.x;
+  float acc[NACC][8];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
+  const int cv = (t < active) ? (t % nvec) : 0;
+  const int rl = t / nvec;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  if (t < active) {
+    for (int r = r0 + rl; r < r1; r += rl_count) f(r, (v0 + cv) * 8, acc);
+  }
+  // reduce over rl through shared memory
+  float* s = smem;   // [NACC][EW_THREADS][8]
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[(a * EW_THREADS + t) * 8 + j] = acc[a][j];
+  __syncthreads();
+  for (int i = t; i < NACC * nvec * 8; i += EW_THREADS) {
+    const int a = i / (nvec * 8), rem = i % (nvec * 8), v = rem >> 3, j = rem & 7;
+    float sum = 0.f;
+    for (int q = 0; q < rl_count; ++q) sum += s[(a * EW_THREADS + q * nvec + v) * 8 + j];
+    atomicAdd(outs[a] + (v0 + v) * 8 + j, sum);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) colsum_kernel(const T* __restrict__ X, long ldx, int M, int N, float* out, int rows_per_block) {
+  extern __shared__ float smem[];
+  float* outs[1] = {out};
+  colreduce_body<T, 1>(M, N, rows_per_block,
+                       [&](int r, int c, float(*acc)[8]) {
+                         float v[8];
+                         Vec8<T>::load(X + (long)r * ldx + c, v);
+#pragma unroll
+                         for (int j = 0; j < 8; ++j) acc[0][j] += v[j];
+                       },
+                       outs, smem);
+}
+
+template <typename T>
+__global__ void colsum_scalar_kernel(const T* __restrict__ X, long ldx, int M, int N, float* out, int rows_per_block) {
+  const int n = blockIdx.y * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s += to_f(X[(long)r * ldx + n]);
+  atomicAdd(out + n, s);
+}
+
+inline int pick_rows_per_block(int M) {
+  int rpb = dfb_cdiv(M, 148 * 4);
+  if (rpb < 32) rpb = 32;
+  return rpb;
+}
+
+// ------------------------------------------------------------------ parameter packing
+template <typename T>
+__global__ void pack_params_kernel(const dfb200_pack_entry* __restrict__ table, int max_elems) {
+  const dfb200_pack_entry e = table[blockIdx.y];
+  T* dst = reinterpret_cast<T*>(e.dst);
+  if (e.kind == 0) {
+    const long n = (long)e.rows * e.cols;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+      const int r = (int)(i / e.cols), c = (int)(i % e.cols);
+      dst[(long)r * e.dst_ld + c] = from_f<T>(e.src[i]);
+    }
+  } else {  // conv weight [Cout, Cin, 3, 3] -> [Cout, (ky*3+kx)*Cin + ci]
+    const int cin = e.cols;
+    const long n = (long)e.rows * cin * 9;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+      const int co = (int)(i / (cin * 9)), rem = (int)(i % (cin * 9));
+      const int tap = rem / cin, ci = rem % cin;
+      dst[(long)co * e.dst_ld + rem] = from_f<T>(e.src[((long)co * cin + ci) * 9 + tap]);
+    }
+  }
+}
+
+__global__ void unpack_conv_grad_kernel(const float* __restrict__ dWp, int ld, int Cout, int Cin, float* __restrict__ dW) {
+  const long n = (long)Cout * Cin * 9;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int co = (int)(i / (Cin * 9)), rem = (int)(i % (Cin * 9));
+    const int ci = rem / 9, tap = rem % 9;
+    dW[i] = dWp[(long)co * ld + tap * Cin + ci];
+  }
+}
+
+// ------------------------------------------------------------------ gating multiply
+template <typename T>
+__global__ void mul_fwd_kernel(const T* __restrict__ a, long lda, const T* __restrict__ b, long ldb, T* __restrict__ o, long ldo, int M, int nvec) {
+  const long n = (long)M * nvec;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / nvec; const int c = (int)(i % nvec) * 8;
+    float x[8], y[8];
+    Vec8<T>::load(a + r * lda + c, x);
+    Vec8<T>::load(b + r * ldb + c, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] *= y[j];
+    Vec8<T>::store(o + r * ldo + c, x);
+  }
+}
+template <typename T>
+__global__ void mul_bwd_kernel(const T* __restrict__ dout, long ldo, const T* __restrict__ a, long lda, const T* __restrict__ b, long ldb,
+                               T* __restrict__ da, long ldda, T* __restrict__ db, long lddb, int M, int nvec) {
+  const long n = (long)M * nvec;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / nvec; const int c = (int)(i % nvec) * 8;
+    float g[8], x[8], y[8], ga[8], gb[8];
+    Vec8<T>::load(dout + r * ldo + c, g);
+    Vec8<T>::load(a + r * lda + c, x);
+    Vec8<T>::load(b + r * ldb + c, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ga[j] = g[j] * y[j]; gb[j] = g[j] * x[j]; }
+    Vec8<T>::store(da + r * ldda + c, ga);
+    Vec8<T>::store(db + r * lddb + c, gb);
+  }
+}
+
+// ------------------------------------------------------------------ layer-scale residual
+template <typename T>
+__global__ void scale_residual_fwd_kernel(const float* __restrict__ res, const T* __restrict__ y, const float* __restrict__ ls,
+                                          const float* __restrict__ scale_b, int M, int nvec, int rows_per_sample, float* __restrict__ out) {
+  const long n = (long)M * nvec;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / nvec; const int c = (int)(i % nvec) * 8;
+    const float sb = scale_b ? scale_b[r / rows_per_sample] : 1.f;
+    float rv[8], yv[8], lv[8];
+    Vec8<float>::load(res + i * 8, rv);
+    Vec8<T>::load(y + i * 8, yv);
+    Vec8<float>::load(ls + c, lv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rv[j] = fmaf(sb * lv[j], yv[j], rv[j]);
+    Vec8<float>::store(out + i * 8, rv);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) scale_residual_bwd_kernel(const float* __restrict__ dout, const T* __restrict__ y, const float* __restrict__ ls,
+                                                                        const float* __restrict__ scale_b, int M, int C, int rows_per_sample,
+                                                                        T* __restrict__ dy, float* dls, int rows_per_block) {
+  extern __shared__ float smem[];
+  float* outs[1] = {dls};
+  colreduce_body<T, 1>(M, C, rows_per_block,
+                       [&](int r, int c, float(*acc)[8]) {
+                         const float sb = scale_b ? scale_b[r / rows_per_sample] : 1.f;
+                         float g[8], yv[8], lv[8], o[8];
+                         Vec8<float>::load(dout + (long)r * C + c, g);
+                         Vec8<T>::load(y + (long)r * C + c, yv);
+                         Vec8<float>::load(ls + c, lv);
+#pragma unroll
+                         for (int j = 0; j < 8; ++j) { o[j] = g[j] * lv[j] * sb; acc[0][j] += g[j] * yv[j] * sb; }
+                         Vec8<T>::store(dy + (long)r * C + c, o);
+                       },
+                       outs, smem);
+}
+
+// ------------------------------------------------------------------ NMF helpers
+__global__ void normalize_cols_kernel(const float* __restrict__ in, int D, int R, float* __restrict__ out, float* __restrict__ norms) {
+  // one block per image b; thread r handles column r of the [D,R] matrix: out = in / max(||col||_2, 1e-12)
+  const int b = blockIdx.x;
+  const float* src = in + (long)b * D * R;
+  float* dst = out + (long)b * D * R;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) { const float v = src[(long)d * R + r]; s = fmaf(v, v, s); }
+    const float nrm = fmaxf(sqrtf(s), 1e-12f);
+    if (norms) norms[b * R + r] = nrm;
+    const float inv = 1.f / nrm;
+    for (int d = 0; d < D; ++d) dst[(long)d * R + r] = src[(long)d * R + r] * inv;
+  }
+}
+
+__global__ void softmax_rows_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out) {
+  // one warp per row
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* x = in + (long)row * cols;
+  float* y = out + (long)row * cols;
+  float m = -INFINITY;
+  for (int c = lane; c < cols; c += 32) m = fmaxf(m, x[c]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += __expf(x[c] - m);
+  s = warp_sum(s);
+  const float inv = 1.f / s;
+  for (int c = lane; c < cols; c += 32) y[c] = __expf(x[c] - m) * inv;
+}
+__global__ void softmax_rows_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, int rows, int cols, float* __restrict__ din) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* g = dout + (long)row * cols;
+  const float* p = out + (long)row * cols;
+  float* d = din + (long)row * cols;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s = fmaf(g[c], p[c], s);
+  s = warp_sum(s);
+  for (int c = lane; c < cols; c += 32) d[c] = p[c] * (g[c] - s);
+}
+
+__global__ void mu_update_kernel(const float* __restrict__ a, const float* __restrict__ num, const float* __restrict__ den, float eps, long n, float* __restrict__ out) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    out[i] = a[i] * num[i] / (den[i] + eps);
+}
+__global__ void mu_update_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ a, const float* __restrict__ num, const float* __restrict__ den,
+                                     float eps, long n, float* __restrict__ da, int acc_da, float* __restrict__ dnum, float* __restrict__ dden) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float inv = 1.f / (den[i] + eps), g = dout[i];
+    const float ga = g * num[i] * inv;
+    da[i] = acc_da ? da[i] + ga : ga;
+    dnum[i] = g * a[i] * inv;
+    dden[i] = -g * a[i] * num[i] * inv * inv;
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) out[i] = from_f<TO>(to_f(in[i]));
+}
+template <typename TI, typename TO>
+__global__ void axpy_kernel(const TI* __restrict__ x, float alpha, TO* __restrict__ y, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] = from_f<TO>(fmaf(alpha, to_f(x[i]), to_f(y[i])));
+}
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n, float lr, float b1,
+                             float b2, float eps, float wd, float c1, float c2, float gs) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gs;
+    float pi = p[i];
+    pi *= (1.f - lr * wd);                                  // decoupled weight decay (torch.optim.AdamW)
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(c2) + eps;
+    p[i] = pi - (lr / c1) * mi / denom;
+  }
+}
+
+}  // namespace
+
+#define ST reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" int dfb200_colsum(const void* X, int dtype, long ldx, int M, int N, float* out, int accumulate, void* stream) {
+  if (M <= 0 || N <= 0) return DFB_OK;
+  if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * N, ST);
+  const int rpb = pick_rows_per_block(M);
+  const bool vec = (N % 8 == 0) && (ldx % 8 == 0) && ((reinterpret_cast<uintptr_t>(X) & 31) == 0);
+  DFB_DISPATCH_DTYPE(dtype, T, {
+    if (vec) {
+      dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(N / 8, EW_THREADS));
+      colsum_kernel<T><<<grid, EW_THREADS, EW_THREADS * 8 * sizeof(float), ST>>>((const T*)X, ldx, M, N, out, rpb);
+    } else {
+      dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(N, 128));
+      colsum_scalar_kernel<T><<<grid, 128, 0, ST>>>((const T*)X, ldx, M, N, out, rpb);
+    }
+  });
+  return dfb_check_launch("colsum");
+}
+
+extern "C" int dfb200_pack_params(const dfb200_pack_entry* table_dev, int n_entries, int max_elems, int dst_dtype, void* stream) {
+  if (n_entries <= 0) return DFB_OK;
+  DFB_REQUIRE(n_entries <= 65535, "pack_params: too many entries (%d)", n_entries);
+  int gx = dfb_cdiv(max_elems, EW_THREADS * 4);
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  dim3 grid(gx, n_entries);
+  DFB_DISPATCH_DTYPE(dst_dtype, T, { pack_params_kernel<T><<<grid, EW_THREADS, 0, ST>>>(table_dev, max_elems); });
+  return dfb_check_launch("pack_params");
+}
+
+extern "C" int dfb200_unpack_conv_grad(const float* dWp, int ld, int Cout, int Cin, float* dW, void* stream) {
+  unpack_conv_grad_kernel<<<ew_grid((long)Cout * Cin * 9), EW_THREADS, 0, ST>>>(dWp, ld, Cout, Cin, dW);
+  return dfb_check_launch("unpack_conv_grad");
+}
+
+extern "C" int dfb200_mul_fwd(const void* a, long lda, const void* b, long ldb, void* out, long ldo, int dtype, int M, int N, void* stream) {
+  DFB_REQUIRE(N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 8 == 0, "mul: N and leading dims must be multiples of 8");
+  DFB_DISPATCH_DTYPE(dtype, T, { mul_fwd_kernel<T><<<ew_grid((long)M * N / 8), EW_THREADS, 0, ST>>>((const T*)a, lda, (const T*)b, ldb, (T*)out, ldo, M, N / 8); });
+  return dfb_check_launch("mul_fwd");
+}
+extern "C" int dfb200_mul_bwd(const void* dout, long ldo, const void* a, long lda, const void* b, long ldb, void* da, long ldda, void* db, long lddb,
+                              int dtype, int M, int N, void* stream) {
+  DFB_REQUIRE(N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 8 == 0 && ldda % 8 == 0 && lddb % 8 == 0, "mul_bwd: alignment");
+  DFB_DISPATCH_DTYPE(dtype, T, {
+    mul_bwd_kernel<T><<<ew_grid((long)M * N / 8), EW_THREADS, 0, ST>>>((const T*)dout, ldo, (const T*)a, lda, (const T*)b, ldb, (T*)da, ldda, (T*)db, lddb, M, N / 8);
+  });
+  return dfb_check_launch("mul_bwd");
+}
+
+extern "C" int dfb200_scale_residual_fwd(const float* res, const void* y, int dtype, const float* ls, const float* scale_b, int M, int C,
+                                         int rows_per_sample, float* out, void* stream) {
+  DFB_REQUIRE(C % 8 == 0, "scale_residual: C %% 8 != 0");
+  DFB_DISPATCH_DTYPE(dtype, T, {
+    scale_residual_fwd_kernel<T><<<ew_grid((long)M * C / 8), EW_THREADS, 0, ST>>>(res, (const T*)y, ls, scale_b, M, C / 8, rows_per_sample, out);
+  });
+  return dfb_check_launch("scale_residual_fwd");
+}
+extern "C" int dfb200_scale_residual_bwd(const float* dout, const void* y, int dtype, const float* ls, const float* scale_b, int M, int C,
+                                         int rows_per_sample, void* dy, float* dls, void* stream) {
+  DFB_REQUIRE(C % 8 == 0, "scale_residual: C %% 8 != 0");
+  const int rpb = pick_rows_per_block(M);
+  dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(C / 8, EW_THREADS));
+  DFB_DISPATCH_DTYPE(dtype, T, {
+    scale_residual_bwd_kernel<T><<<grid, EW_THREADS, EW_THREADS * 8 * sizeof(float), ST>>>(dout, (const T*)y, ls, scale_b, M, C, rows_per_sample, (T*)dy, dls, rpb);
+  });
+  return dfb_check_launch("scale_residual_bwd");
+}
+
+extern "C" int dfb200_normalize_cols(const float* in, int B, int D, int R, float* out, float* norms, void* stream) {
+  normalize_cols_kernel<<<B, 64, 0, ST>>>(in, D, R, out, norms);
+  return dfb_check_launch("normalize_cols");
+}
+extern "C" int dfb200_softmax_rows(const float* in, int rows, int cols, float* out, void* stream) {
+  if (rows <= 0) return DFB_OK;
+  softmax_rows_kernel<<<dfb_cdiv(rows, 8), 256, 0, ST>>>(in, rows, cols, out);
+  return dfb_check_launch("softmax_rows");
+}
+extern "C" int dfb200_softmax_rows_bwd(const float* dout, const float* out, int rows, int cols, float* din, void* stream) {
+  if (rows <= 0) return DFB_OK;
+  softmax_rows_bwd_kernel<<<dfb_cdiv(rows, 8), 256, 0, ST>>>(dout, out, rows, cols, din);
+  return dfb_check_launch("softmax_rows_bwd");
+}
+extern "C" int dfb200_mu_update(const float* a, const float* num, const float* den, float eps, long n, float* out, void* stream) {
+  mu_update_kernel<<<ew_grid(n), EW_THREADS, 0, ST>>>(a, num, den, eps, n, out);
+  return dfb_check_launch("mu_update");
+}
+extern "C" int dfb200_mu_update_bwd(const float* dout, const float* a, const float* num, const float* den, float eps, long n, float* da,
+                                    int accumulate_da, float* dnum, float* dden, void* stream) {
+  mu_update_bwd_kernel<<<ew_grid(n), EW_THREADS, 0, ST>>>(dout, a, num, den, eps, n, da, accumulate_da, dnum, dden);
+  return dfb_check_launch("mu_update_bwd");
+}
+
+extern "C" int dfb200_cast(const void* in, int in_dtype, void* out, int out_dtype, long n, void* stream) {
+  const int g = ew_grid(n, 4);
+  if (in_dtype == 0 && out_dtype == 0) cast_kernel<float, float><<<g, EW_THREADS, 0, ST>>>((const float*)in, (float*)out, n);
+  else if (in_dtype == 0 && out_dtype == 1) cast_kernel<float, bf16><<<g, EW_THREADS, 0, ST>>>((const float*)in, (bf16*)out, n);
+  else if (in_dtype == 1 && out_dtype == 0) cast_kernel<bf16, float><<<g, EW_THREADS, 0, ST>>>((const bf16*)in, (float*)out, n);
+  else if (in_dtype == 1 && out_dtype == 1) cast_kernel<bf16, bf16><<<g, EW_THREADS, 0, ST>>>((const bf16*)in, (bf16*)out, n);
+  else { dfb_set_error("cast: bad dtypes"); return DFB_ERR_ARG; }
+  return dfb_check_launch("cast");
+}
+extern "C" int dfb200_axpy(const void* x, int x_dtype, float alpha, void* y, int y_dtype, long n, void* stream) {
+  const int g = ew_grid(n, 4);
+  if (x_dtype == 0 && y_dtype == 0) axpy_kernel<float, float><<<g, EW_THREADS, 0, ST>>>((const float*)x, alpha, (float*)y, n);
+  else if (x_dtype == 0 && y_dtype == 1) axpy_kernel<float, bf16><<<g, EW_THREADS, 0, ST>>>((const float*)x, alpha, (bf16*)y, n);
+  else if (x_dtype == 1 && y_dtype == 0) axpy_kernel<bf16, float><<<g, EW_THREADS, 0, ST>>>((const bf16*)x, alpha, (float*)y, n);
+  else if (x_dtype == 1 && y_dtype == 1) axpy_kernel<bf16, bf16><<<g, EW_THREADS, 0, ST>>>((const bf16*)x, alpha, (bf16*)y, n);
+  else { dfb_set_error("axpy: bad dtypes"); return DFB_ERR_ARG; }
+  return dfb_check_launch("axpy");
+}
+
+extern "C" int dfb200_adamw(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps,
+                            float weight_decay, float bias_c1, float bias_c2, float grad_scale, void* stream) {
+  adamw_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2, grad_scale);
+  return dfb_check_launch("adamw");
+}

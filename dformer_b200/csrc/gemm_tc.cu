@@ -1,0 +1,436 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a (bf16 operands, fp32 accumulation in tensor memory).
+//
+//   C[M,N] = epi( opA(A) * opB(B) + bias ),   same operand conventions as gemm_simt.cu.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer  : cp.async.bulk.tensor tiles (128B swizzle) into a 4-stage smem ring
+//   warp 1      MMA issuer    : one thread issues tcgen05.mma (UMMA 128 x BN x 16), accumulators in TMEM,
+//                               double-buffered (2 x 256 columns) so the epilogue of tile i overlaps tile i+1
+//   warps 2..5  epilogue      : tcgen05.ld (32 lanes x 32 columns per warp) -> bias / activation -> global
+//
+// Both operands may be K-major (reduction dim contiguous) or MN-major (reduction dim strided), which is
+// what lets one kernel serve forward (A K-major, W K-major), dgrad (dY K-major, W MN-major) and wgrad
+// (dY MN-major, X MN-major) without any transposed copies in HBM.  The wgrad case reduces over the pixel
+// dimension, so the reduction can be split across CTAs (split-K) with fp32 red.global.add epilogues.
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <string.h>
+
+#include "common.cuh"
+#include "dfb200_internal.h"
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M (cta_group::1)
+constexpr int BK = 64;           // 64 bf16 = one 128-byte swizzle row
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16 KB
+constexpr int B_STAGE_BYTES = 256 * BK * 2;       // 32 KB (BN <= 256)
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int TMEM_COLS = 512;   // 2 accumulator stages x 256 fp32 columns
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TcParams {
+  int M, N, K;               // problem (K = reduction length)
+  int BN;                    // tile N (multiple of 16, <= 256)
+  int m_tiles, n_tiles, splits, kb_per_split, kb_total;
+  int a_mn_major, b_mn_major;
+  void* C; long ldc;
+  const float* bias;
+  int out_bf16, act, act_col_start, accumulate;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("dfb200 gemm_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), 128-byte swizzle:
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4   [32,46) stride byte offset >> 4
+//   [46,48) version = 1 (Blackwell)   [61,64) layout type = 2 (SWIZZLE_128B)
+// K-major : rows of 128 B, 8-row groups 1024 B apart           -> LBO (unused) = 1, SBO = 1024
+// MN-major: 64-element MN chunks are [64 k-rows x 128 B] boxes -> LBO = 8192 (next MN chunk), SBO = 1024 (next 8 k-rows)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, bool mn_major) {
+  const uint64_t lbo = mn_major ? (8192u >> 4) : 1u;
+  const uint64_t sbo = 1024u >> 4;
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int a_boxes = p.a_mn_major ? 2 : 1;                       // MN-major: one [64 k x 64 mn] box per 64 MN elements
+  const int b_boxes = p.b_mn_major ? (p.BN + 63) / 64 : 1;
+  const uint32_t stage_tx = (uint32_t)A_STAGE_BYTES + (uint32_t)(p.b_mn_major ? b_boxes * 8192 : p.BN * 128);
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.n_tiles, m_blk = (tile / p.n_tiles) % p.m_tiles, sp = tile / (p.n_tiles * p.m_tiles);
+        const int kb0 = sp * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], stage_tx);
+          if (p.a_mn_major) {
+            for (int i = 0; i < a_boxes; ++i) tma_load_2d(&tmA, &full_bar[stage], sa + i * 8192, m_blk * BM + i * 64, kb * BK);
+          } else {
+            tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m_blk * BM);
+          }
+          if (p.b_mn_major) {
+            for (int i = 0; i < b_boxes; ++i) tma_load_2d(&tmB, &full_bar[stage], sb + i * 8192, n_blk * p.BN + i * 64, kb * BK);
+          } else {
+            tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n_blk * p.BN);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      // Instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1,
+      // a_major bit 15, b_major bit 16, N>>3 at [17,23), M>>4 at [24,29).
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn_major << 15) |
+                             ((uint32_t)p.b_mn_major << 16) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t a_kstep = p.a_mn_major ? 2048u : 32u;   // bytes per UMMA_K = 16 reduction elements
+      const uint32_t b_kstep = p.b_mn_major ? 2048u : 32u;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int sp = tile / (p.n_tiles * p.m_tiles);
+        const int kb0 = sp * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = make_smem_desc(sa + k * a_kstep, p.a_mn_major);
+            const uint64_t bd = make_smem_desc(sb + k * b_kstep, p.b_mn_major);
+            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);          // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 2..5) ===============================
+    const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.n_tiles, m_blk = (tile / p.n_tiles) % p.m_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + quad * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * 256u;
+      const bool row_ok = row < p.M;
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + (uint32_t)c0, r);
+        tmem_ld_wait();
+        const int col0 = n_blk * p.BN + c0;
+        if (row_ok && col0 < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const int ncols = min(32, min(p.BN - c0, p.N - col0));
+          if (p.splits > 1) {
+            float* dst = reinterpret_cast<float*>(p.C) + (long)row * p.ldc + col0;
+            const bool add_bias = p.bias != nullptr && tile < p.m_tiles * p.n_tiles;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) atomicAdd(dst + j, v[j] + (add_bias ? p.bias[col0 + j] : 0.f));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < ncols) {
+                float x = v[j];
+                if (p.bias) x += __ldg(p.bias + col0 + j);
+                if (col0 + j >= p.act_col_start) {
+                  if (p.act == 1) x = gelu_f(x);
+                  else if (p.act == 2) x = fmaxf(x, 0.f);
+                }
+                v[j] = x;
+              }
+            }
+            if (p.out_bf16) {
+              bf16* dst = reinterpret_cast<bf16*>(p.C) + (long)row * p.ldc + col0;
+              if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) Vec8<bf16>::store(dst + j, v + j);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
+              }
+            } else {
+              float* dst = reinterpret_cast<float*>(p.C) + (long)row * p.ldc + col0;
+              if (p.accumulate) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncols) dst[j] += v[j];
+              } else if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncols) dst[j] = v[j];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; long inner, outer, ld; int box_inner, box_outer;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = 1469598103934665603ull;
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(&k);
+    for (size_t i = 0; i < sizeof(MapKey); ++i) h = (h ^ b[i]) * 1099511628211ull;
+    return h;
+  }
+};
+
+// 2-D bf16 tensor map over a row-major [outer, inner] matrix with leading dimension ld (elements).
+int make_map(CUtensorMap* out, const void* ptr, long inner, long outer, long ld, int box_inner, int box_outer) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.inner = inner; key.outer = outer; key.ld = ld; key.box_inner = box_inner; key.box_outer = box_outer;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return DFB_OK; }
+  }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { dfb_set_error("cuTensorMapEncodeTiled entry point not available"); return DFB_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    dfb_set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%ld outer=%ld ld=%ld box=%dx%d", (int)r, ptr, inner, outer, ld, box_inner, box_outer);
+    return DFB_ERR_CUDA;
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 65536) cache.clear();
+    cache.emplace(key, *out);
+  }
+  return DFB_OK;
+}
+
+int pick_bn(int N) {
+  if (N <= 256) return ((N + 15) / 16) * 16;
+  int best = 256; long best_cost = (long)dfb_cdiv(N, 256) * 256;
+  for (int bn = 240; bn >= 64; bn -= 16) {
+    const long cost = (long)dfb_cdiv(N, bn) * bn;
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+}  // namespace
+
+bool dfb_gemm_tc_supported(const dfb200_gemm_args& g) {
+  if (g.a_dtype != 1 || g.b_dtype != 1 || g.batch != 1 || g.batch_inner > 1) return false;
+  if (g.alpha != 0.f && g.alpha != 1.f) return false;
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return false;
+  if ((g.lda % 8) || (g.ldb % 8)) return false;
+  if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) return false;
+  if (g.accumulate && g.out_dtype != 0) return false;
+  return true;
+}
+
+int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
+  DFB_REQUIRE(dfb_gemm_tc_supported(g), "gemm_tc: unsupported arguments (dtype=%d/%d batch=%d lda=%ld ldb=%ld)", g.a_dtype, g.b_dtype, g.batch, g.lda, g.ldb);
+  static int num_sms = 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) { dfb_set_error("gemm_tc smem attr: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
+    attr_set = true;
+  }
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.BN = pick_bn(g.N);
+  p.m_tiles = dfb_cdiv(g.M, BM);
+  p.n_tiles = dfb_cdiv(g.N, p.BN);
+  p.kb_total = dfb_cdiv(g.K, BK);
+  p.a_mn_major = g.transA ? 1 : 0;   // A stored [K, M]  -> M contiguous
+  p.b_mn_major = g.transB ? 0 : 1;   // B stored [K, N]  -> N contiguous
+  p.C = g.C; p.ldc = g.ldc; p.bias = g.bias;
+  p.out_bf16 = g.out_dtype == 1; p.act = g.act; p.act_col_start = g.act_col_start; p.accumulate = g.accumulate;
+  // split-K when the output has too few tiles to fill the machine and the reduction is long (wgrad)
+  int splits = 1;
+  const long tiles = (long)p.m_tiles * p.n_tiles;
+  if (g.splitk > 1) splits = g.splitk;
+  else if (g.splitk == 0 && g.out_dtype == 0 && g.act == 0 && tiles * 2 <= num_sms && p.kb_total >= 16)
+    splits = (int)min((long)p.kb_total / 4, (long)(num_sms / tiles));
+  if (splits < 1) splits = 1;
+  if (splits > 1) DFB_REQUIRE(g.out_dtype == 0 && g.act == 0, "gemm_tc split-K needs fp32 output without activation");
+  p.kb_per_split = dfb_cdiv(p.kb_total, splits);
+  p.splits = dfb_cdiv(p.kb_total, p.kb_per_split);
+  if (p.splits > 1 && !g.accumulate) {
+    cudaError_t e = cudaMemset2DAsync(g.C, g.ldc * sizeof(float), 0, (size_t)g.N * sizeof(float), g.M, st);
+    if (e != cudaSuccess) { dfb_set_error("memset2d: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
+  }
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (g.transA) rc = make_map(&tmA, g.A, g.M, g.K, g.lda, 64, 64);          // stored [K, M]
+  else rc = make_map(&tmA, g.A, g.K, g.M, g.lda, 64, BM);                  // stored [M, K]
+  if (rc) return rc;
+  if (g.transB) rc = make_map(&tmB, g.B, g.K, g.N, g.ldb, 64, p.BN);        // stored [N, K]
+  else rc = make_map(&tmB, g.B, g.N, g.K, g.ldb, 64, 64);                  // stored [K, N]
+  if (rc) return rc;
+  const long total = tiles * p.splits;
+  const int grid = (int)min((long)num_sms, total);
+  gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
+  return dfb_check_launch("gemm_tc");
+}

@@ -1,0 +1,138 @@
+// Fused x8 bilinear upsample (align_corners=False) + cross-entropy with ignore_index
+// (models/builder.py:203,230).  Forward optionally materialises the NCHW fp32 logits the API returns;
+// backward is a deterministic gather over the hi-res pixels that reference each low-res logit.
+#include "common.cuh"
+#include "dfb200_internal.h"
+
+namespace {
+
+struct Lerp { int i0, i1; float w1; };
+__device__ __forceinline__ Lerp lerp_coord(int o, int n_in, int n_out) {
+  Lerp l;
+  if (n_in == n_out) { l.i0 = o; l.i1 = o; l.w1 = 0.f; return l; }
+  const float scale = (float)n_in / (float)n_out;
+  float src = ((float)o + 0.5f) * scale - 0.5f;
+  if (src < 0.f) src = 0.f;
+  l.i0 = min((int)src, n_in - 1);
+  l.i1 = min(l.i0 + 1, n_in - 1);
+  l.w1 = src - (float)l.i0;
+  return l;
+}
+
+template <typename T>
+__device__ __forceinline__ float interp_logit(const T* __restrict__ base, int w, int ncls, const Lerp& ly, const Lerp& lx, int c) {
+  const float v00 = to_f(base[((long)ly.i0 * w + lx.i0) * ncls + c]);
+  const float v01 = to_f(base[((long)ly.i0 * w + lx.i1) * ncls + c]);
+  const float v10 = to_f(base[((long)ly.i1 * w + lx.i0) * ncls + c]);
+  const float v11 = to_f(base[((long)ly.i1 * w + lx.i1) * ncls + c]);
+  const float top = (1.f - lx.w1) * v00 + lx.w1 * v01;
+  const float bot = (1.f - lx.w1) * v10 + lx.w1 * v11;
+  return (1.f - ly.w1) * top + ly.w1 * bot;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_ce_fwd_kernel(const T* __restrict__ small, int B, int h, int w, int ncls, int H, int W,
+                                                              const int64_t* __restrict__ label, int ignore, float* __restrict__ out,
+                                                              float* __restrict__ lse_out, float* loss_acc) {
+  __shared__ float red[32];
+  float loss = 0.f, cnt = 0.f;
+  const long n = (long)B * H * W;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H), b = (int)(i / ((long)W * H));
+    const Lerp ly = lerp_coord(y, h, H), lx = lerp_coord(x, w, W);
+    const T* base = small + (long)b * h * w * ncls;
+    const long lab = label ? label[i] : (long)ignore;
+    float m = -INFINITY, s = 0.f, picked = 0.f;
+    for (int c = 0; c < ncls; ++c) {
+      const float v = interp_logit(base, w, ncls, ly, lx, c);
+      if (out) out[((long)b * ncls + c) * H * W + (long)y * W + x] = v;
+      if (v > m) { s = s * __expf(m - v) + 1.f; m = v; } else { s += __expf(v - m); }
+      if ((long)c == lab) picked = v;
+    }
+    const float lse = m + __logf(s);
+    if (lse_out) lse_out[i] = lse;
+    if (label && lab != (long)ignore && lab >= 0 && lab < ncls) { loss += lse - picked; cnt += 1.f; }
+  }
+  if (loss_acc) {
+    loss = block_sum(loss, red);
+    cnt = block_sum(cnt, red);
+    if (threadIdx.x == 0) { atomicAdd(loss_acc, loss); atomicAdd(loss_acc + 1, cnt); }
+  }
+}
+
+__global__ void ce_finalize_kernel(const float* acc, float* loss) { loss[0] = acc[0] / acc[1]; }
+
+// thread = (low-res pixel, class); scans the hi-res pixels whose bilinear footprint includes the pixel
+template <typename T, typename TD>
+__global__ void upsample_ce_bwd_kernel(const T* __restrict__ small, int B, int h, int w, int ncls, int H, int W, const int64_t* __restrict__ label,
+                                       int ignore, const float* __restrict__ lse, const float* __restrict__ loss_acc, const float* __restrict__ dloss,
+                                       TD* __restrict__ dsmall) {
+  const long n = (long)B * h * w * ncls;
+  const float gscale = dloss[0] / loss_acc[1];
+  const float ry = (float)H / (float)h, rx = (float)W / (float)w;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ncls);
+    const long pix = i / ncls;
+    const int ix = (int)(pix % w), iy = (int)((pix / w) % h), b = (int)(pix / ((long)w * h));
+    int oy_lo = max(0, (int)floorf((iy - 1) * ry) - 1), oy_hi = min(H - 1, (int)ceilf((iy + 2) * ry) + 1);
+    int ox_lo = max(0, (int)floorf((ix - 1) * rx) - 1), ox_hi = min(W - 1, (int)ceilf((ix + 2) * rx) + 1);
+    if (iy == 0) oy_lo = 0;
+    if (iy == h - 1) oy_hi = H - 1;
+    if (ix == 0) ox_lo = 0;
+    if (ix == w - 1) ox_hi = W - 1;
+    const T* base = small + (long)b * h * w * ncls;
+    float acc = 0.f;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      const Lerp ly = lerp_coord(oy, h, H);
+      const float wy = (ly.i0 == iy ? 1.f - ly.w1 : 0.f) + (ly.i1 == iy ? ly.w1 : 0.f);
+      if (wy == 0.f) continue;
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        const Lerp lx = lerp_coord(ox, w, W);
+        const float wx = (lx.i0 == ix ? 1.f - lx.w1 : 0.f) + (lx.i1 == ix ? lx.w1 : 0.f);
+        if (wx == 0.f) continue;
+        const long hp = ((long)b * H + oy) * W + ox;
+        const long lab = label[hp];
+        if (lab == (long)ignore || lab < 0 || lab >= ncls) continue;
+        const float v = interp_logit(base, w, ncls, ly, lx, c);
+        float g = __expf(v - lse[hp]);
+        if ((long)c == lab) g -= 1.f;
+        acc = fmaf(wy * wx, g, acc);
+      }
+    }
+    dsmall[i] = from_f<TD>(acc * gscale);
+  }
+}
+
+}  // namespace
+
+#define ST reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" int dfb200_upsample_ce_fwd(const void* logits_small, int dtype, int B, int h, int w, int ncls, int H, int W, const int64_t* label, int ignore,
+                                      float* out_nchw, float* lse, float* loss_acc, void* stream) {
+  const long n = (long)B * H * W;
+  long g = (n + 255) / 256;
+  if (g > 148L * 16) g = 148L * 16;
+  if (g < 1) g = 1;
+  DFB_DISPATCH_DTYPE(dtype, T, {
+    upsample_ce_fwd_kernel<T><<<(int)g, 256, 0, ST>>>((const T*)logits_small, B, h, w, ncls, H, W, label, ignore, out_nchw, lse, loss_acc);
+  });
+  return dfb_check_launch("upsample_ce_fwd");
+}
+
+extern "C" int dfb200_ce_finalize(const float* loss_acc, float* loss, void* stream) {
+  ce_finalize_kernel<<<1, 1, 0, ST>>>(loss_acc, loss);
+  return dfb_check_launch("ce_finalize");
+}
+
+extern "C" int dfb200_upsample_ce_bwd(const void* logits_small, int dtype, int B, int h, int w, int ncls, int H, int W, const int64_t* label, int ignore,
+                                      const float* lse, const float* loss_acc, const float* dloss, void* dlogits_small, int dl_dtype, void* stream) {
+  const long n = (long)B * h * w * ncls;
+  long g = (n + 255) / 256;
+  if (g < 1) g = 1;
+#define L(T, TD) upsample_ce_bwd_kernel<T, TD><<<(int)g, 256, 0, ST>>>((const T*)logits_small, B, h, w, ncls, H, W, label, ignore, lse, loss_acc, dloss, (TD*)dlogits_small)
+  const int key = dtype * 2 + dl_dtype;
+  switch (key) { case 0: L(float, float); break; case 1: L(float, bf16); break; case 2: L(bf16, float); break; case 3: L(bf16, bf16); break;
+    default: dfb_set_error("upsample_ce_bwd: bad dtypes"); return DFB_ERR_ARG; }
+#undef L
+  return dfb_check_launch("upsample_ce_bwd");
+}

@@ -1,0 +1,365 @@
+// LayerNorm (channels-last, eps 1e-6) and BatchNorm2d kernels.  HBM-bound, one pass per tensor.
+#include "common.cuh"
+#include "dfb200_internal.h"
+
+namespace {
+
+constexpr int LN_MAX_PER_LANE = 32;   // C <= 1024
+
+// ------------------------------------------------------------------ LayerNorm forward: one warp per row
+template <typename T>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                     int M, int C, T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
+    const float* xr = x + (long)row * C;
+    float v[LN_MAX_PER_LANE];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+      const int c = lane + i * 32;
+      v[i] = (c < C) ? xr[c] : 0.f;
+      s += v[i];
+    }
+    const float mu = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+      const int c = lane + i * 32;
+      const float d = (c < C) ? v[i] - mu : 0.f;
+      q = fmaf(d, d, q);
+    }
+    const float rs = rsqrtf(warp_sum(q) / C + eps);
+    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+    T* yr = y + (long)row * C;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+      const int c = lane + i * 32;
+      if (c < C) yr[c] = from_f<T>((v[i] - mu) * rs * gamma[c] + beta[c]);
+    }
+  }
+}
+
+// LayerNorm backward: warp per row for dx; per-lane partial dgamma/dbeta accumulated over the block's rows.
+template <typename T>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd, int M, int C, float* __restrict__ dx,
+                                                     int acc_dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float sm[];   // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  float pg[LN_MAX_PER_LANE], pb[LN_MAX_PER_LANE];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) { pg[i] = 0.f; pb[i] = 0.f; }
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
+    const float* xr = x + (long)row * C;
+    const T* gr = dy + (long)row * C;
+    const float mu = mean[row], rs = rstd[row];
+    float xh[LN_MAX_PER_LANE], g[LN_MAX_PER_LANE];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+      const int c = lane + i * 32;
+      if (c < C) {
+        const float d = to_f(gr[c]);
+        xh[i] = (xr[c] - mu) * rs;
+        g[i] = d * gamma[c];
+        pg[i] = fmaf(d, xh[i], pg[i]);
+        pb[i] += d;
+        s1 += g[i];
+        s2 = fmaf(g[i], xh[i], s2);
+      } else { xh[i] = 0.f; g[i] = 0.f; }
+    }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+    float* dr = dx + (long)row * C;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+      const int c = lane + i * 32;
+      if (c < C) {
+        const float v = rs * (g[i] - s1 - xh[i] * s2);
+        dr[c] = acc_dx ? dr[c] + v : v;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < C) { atomicAdd(&sm[c], pg[i]); atomicAdd(&sm[C + c], pb[i]); }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { atomicAdd(dgamma + c, sm[c]); atomicAdd(dbeta + c, sm[C + c]); }
+}
+
+// ------------------------------------------------------------------ BatchNorm
+constexpr int BN_THREADS = 256;
+
+// Column sums in double (block-level partials in float over <= rows_per_block rows).
+template <typename T>
+__global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T* __restrict__ x, int M, int C, double* sum, double* sumsq, int rows_per_block) {
+  __shared__ float s1[BN_THREADS * 8];
+  __shared__ float s2[BN_THREADS * 8];
+  const int nvec_all = C >> 3;
+  const int v0 = blockIdx.y * BN_THREADS;
+  const int nvec = min(BN_THREADS, nvec_all - v0);
+  const int rl_count = BN_THREADS / nvec, active = rl_count * nvec;
+  const int t = threadIdx.x;
+  float a1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  if (t < active) {
+    const int cv = t % nvec, rl = t / nvec;
+    for (int r = r0 + rl; r < r1; r += rl_count) {
+      float v[8];
+      Vec8<T>::load(x + (long)r * C + (v0 + cv) * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a1[j] += v[j]; a2[j] = fmaf(v[j], v[j], a2[j]); }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[t * 8 + j] = a1[j]; s2[t * 8 + j] = a2[j]; }
+  __syncthreads();
+  for (int i = t; i < nvec * 8; i += BN_THREADS) {
+    const int v = i >> 3, j = i & 7;
+    double d1 = 0.0, d2 = 0.0;
+    for (int q = 0; q < rl_count; ++q) { d1 += s1[(q * nvec + v) * 8 + j]; d2 += s2[(q * nvec + v) * 8 + j]; }
+    atomicAdd(sum + (v0 + v) * 8 + j, d1);
+    atomicAdd(sumsq + (v0 + v) * 8 + j, d2);
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, double count, float eps, float momentum, int C,
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* running_mean, float* running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mu = sum[c] / count;
+  double var = sumsq[c] / count - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)mu;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+__global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, float eps, int C, float* mean, float* invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mean[c] = rm[c];
+  invstd[c] = rsqrtf(rv[c] + eps);
+}
+
+__device__ __forceinline__ float act_fwd(float z, int act) { return act == 1 ? gelu_f(z) : (act == 2 ? fmaxf(z, 0.f) : z); }
+__device__ __forceinline__ float act_bwd(float z, int act) { return act == 1 ? gelu_grad_f(z) : (act == 2 ? (z > 0.f ? 1.f : 0.f) : 1.f); }
+
+template <typename TX, typename TY>
+__global__ void bn_apply_kernel(const TX* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, const TY* __restrict__ residual, int act, const float* __restrict__ chan_scale,
+                                int rows_per_sample, int M, int C, TY* __restrict__ y) {
+  const int nvec = C >> 3;
+  const long n = (long)M * nvec;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / nvec; const int c = (int)(i % nvec) * 8;
+    float v[8], res[8];
+    Vec8<TX>::load(x + i * 8, v);
+    if (residual) Vec8<TY>::load(residual + i * 8, res);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float z = (v[j] - mean[c + j]) * invstd[c + j] * gamma[c + j] + beta[c + j];
+      if (residual) z += res[j];
+      z = act_fwd(z, act);
+      if (chan_scale) z *= chan_scale[(r / rows_per_sample) * C + c + j];
+      v[j] = z;
+    }
+    Vec8<TY>::store(y + i * 8, v);
+  }
+}
+
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ mean,
+                                                                   const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   const TY* __restrict__ residual, int act, const float* __restrict__ chan_scale, int rows_per_sample,
+                                                                   int M, int C, TY* __restrict__ gbuf, float* sum_g, float* sum_gx, int rows_per_block) {
+  __shared__ float s1[BN_THREADS * 8];
+  __shared__ float s2[BN_THREADS * 8];
+  const int nvec_all = C >> 3;
+  const int v0 = blockIdx.y * BN_THREADS;
+  const int nvec = min(BN_THREADS, nvec_all - v0);
+  const int rl_count = BN_THREADS / nvec, active = rl_count * nvec;
+  const int t = threadIdx.x;
+  float a1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  if (t < active) {
+    const int cv = t % nvec, rl = t / nvec, c = (v0 + cv) * 8;
+    float mu[8], is[8], ga[8], be[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { mu[j] = mean[c + j]; is[j] = invstd[c + j]; ga[j] = gamma[c + j]; be[j] = beta[c + j]; }
+    for (int r = r0 + rl; r < r1; r += rl_count) {
+      const long off = (long)r * C + c;
+      float xv[8], g[8], res[8];
+      Vec8<TX>::load(x + off, xv);
+      Vec8<TY>::load(dy + off, g);
+      if (residual) Vec8<TY>::load(residual + off, res);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xv[j] - mu[j]) * is[j];
+        float gj = g[j];
+        if (chan_scale) gj *= chan_scale[(r / rows_per_sample) * C + c + j];
+        if (act) {
+          float z = xh * ga[j] + be[j];
+          if (residual) z += res[j];
+          gj *= act_bwd(z, act);
+        }
+        g[j] = gj;
+        a1[j] += gj;
+        a2[j] = fmaf(gj, xh, a2[j]);
+      }
+      Vec8<TY>::store(gbuf + off, g);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[t * 8 + j] = a1[j]; s2[t * 8 + j] = a2[j]; }
+  __syncthreads();
+  for (int i = t; i < nvec * 8; i += BN_THREADS) {
+    const int v = i >> 3, j = i & 7;
+    float d1 = 0.f, d2 = 0.f;
+    for (int q = 0; q < rl_count; ++q) { d1 += s1[(q * nvec + v) * 8 + j]; d2 += s2[(q * nvec + v) * 8 + j]; }
+    atomicAdd(sum_g + (v0 + v) * 8 + j, d1);
+    atomicAdd(sum_gx + (v0 + v) * 8 + j, d2);
+  }
+}
+
+template <typename TX, typename TY, typename TD>
+__global__ void bn_bwd_apply_kernel(const TY* __restrict__ gbuf, const TX* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ sum_g, const float* __restrict__ sum_gx, float inv_count,
+                                    int training, int M, int C, TD* __restrict__ dx) {
+  const int nvec = C >> 3;
+  const long n = (long)M * nvec;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % nvec) * 8;
+    float g[8], xv[8];
+    Vec8<TY>::load(gbuf + i * 8, g);
+    Vec8<TX>::load(x + i * 8, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float k = gamma[c + j] * invstd[c + j];
+      if (training) {
+        const float xh = (xv[j] - mean[c + j]) * invstd[c + j];
+        g[j] = k * (g[j] - sum_g[c + j] * inv_count - xh * sum_gx[c + j] * inv_count);
+      } else {
+        g[j] = k * g[j];
+      }
+    }
+    Vec8<TD>::store(dx + i * 8, g);
+  }
+}
+
+inline int ew_grid(long n) {
+  long b = (n + 255) / 256;
+  if (b < 1) b = 1;
+  const long cap = 148L * 16;
+  return (int)(b > cap ? cap : b);
+}
+inline int rows_per_block(int M) { int r = dfb_cdiv(M, 148 * 4); return r < 32 ? 32 : r; }
+
+}  // namespace
+
+#define ST reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" int dfb200_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int M, int C, void* y, int y_dtype, float* mean,
+                                    float* rstd, void* stream) {
+  DFB_REQUIRE(C >= 1 && C <= 32 * LN_MAX_PER_LANE, "layernorm: C=%d out of range", C);
+  if (M <= 0) return DFB_OK;
+  const int grid = min(dfb_cdiv(M, 8), 148 * 8);
+  DFB_DISPATCH_DTYPE(y_dtype, T, { ln_fwd_kernel<T><<<grid, 256, 0, ST>>>(x, gamma, beta, eps, M, C, (T*)y, mean, rstd); });
+  return dfb_check_launch("layernorm_fwd");
+}
+
+extern "C" int dfb200_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean, const float* rstd, int M, int C,
+                                    float* dx, int accumulate_dx, float* dgamma, float* dbeta, void* stream) {
+  DFB_REQUIRE(C >= 1 && C <= 32 * LN_MAX_PER_LANE, "layernorm: C=%d out of range", C);
+  if (M <= 0) return DFB_OK;
+  const int grid = min(dfb_cdiv(M, 8), 148 * 2);
+  DFB_DISPATCH_DTYPE(dy_dtype, T, {
+    ln_bwd_kernel<T><<<grid, 256, 2 * C * sizeof(float), ST>>>((const T*)dy, x, gamma, mean, rstd, M, C, dx, accumulate_dx, dgamma, dbeta);
+  });
+  return dfb_check_launch("layernorm_bwd");
+}
+
+extern "C" int dfb200_bn_stats(const void* x, int dtype, int M, int C, double* sum, double* sumsq, void* stream) {
+  DFB_REQUIRE(C % 8 == 0, "bn_stats: C %% 8 != 0 (C=%d)", C);
+  cudaMemsetAsync(sum, 0, sizeof(double) * C, ST);
+  cudaMemsetAsync(sumsq, 0, sizeof(double) * C, ST);
+  if (M <= 0) return DFB_OK;
+  int rpb = dfb_cdiv(M, 148 * 4);
+  if (rpb < 32) rpb = 32;
+  if (rpb > 4096) rpb = 4096;          // bound the length of float partial sums
+  dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(C / 8, BN_THREADS));
+  DFB_DISPATCH_DTYPE(dtype, T, { bn_stats_kernel<T><<<grid, BN_THREADS, 0, ST>>>((const T*)x, M, C, sum, sumsq, rpb); });
+  return dfb_check_launch("bn_stats");
+}
+
+extern "C" int dfb200_bn_finalize(const double* sum, const double* sumsq, double count, float eps, float momentum, int C, float* mean, float* invstd,
+                                  float* running_mean, float* running_var, void* stream) {
+  bn_finalize_kernel<<<dfb_cdiv(C, 128), 128, 0, ST>>>(sum, sumsq, count, eps, momentum, C, mean, invstd, running_mean, running_var);
+  return dfb_check_launch("bn_finalize");
+}
+extern "C" int dfb200_bn_eval_stats(const float* running_mean, const float* running_var, float eps, int C, float* mean, float* invstd, void* stream) {
+  bn_eval_stats_kernel<<<dfb_cdiv(C, 128), 128, 0, ST>>>(running_mean, running_var, eps, C, mean, invstd);
+  return dfb_check_launch("bn_eval_stats");
+}
+
+extern "C" int dfb200_bn_apply(const void* x, int x_dtype, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                               const void* residual, int act, const float* chan_scale, int rows_per_sample, int M, int C, void* y, int y_dtype, void* stream) {
+  DFB_REQUIRE(C % 8 == 0, "bn_apply: C %% 8 != 0 (C=%d)", C);
+  const int grid = ew_grid((long)M * C / 8);
+#define L(TX, TY) bn_apply_kernel<TX, TY><<<grid, 256, 0, ST>>>((const TX*)x, mean, invstd, gamma, beta, (const TY*)residual, act, chan_scale, rows_per_sample, M, C, (TY*)y)
+  if (x_dtype == 0 && y_dtype == 0) L(float, float);
+  else if (x_dtype == 0 && y_dtype == 1) L(float, bf16);
+  else if (x_dtype == 1 && y_dtype == 1) L(bf16, bf16);
+  else if (x_dtype == 1 && y_dtype == 0) L(bf16, float);
+  else { dfb_set_error("bn_apply: bad dtypes"); return DFB_ERR_ARG; }
+#undef L
+  return dfb_check_launch("bn_apply");
+}
+
+extern "C" int dfb200_bn_bwd_reduce(const void* dy, int y_dtype, const void* x, int x_dtype, const float* mean, const float* invstd, const float* gamma,
+                                    const float* beta, const void* residual, int act, const float* chan_scale, int rows_per_sample, int M, int C,
+                                    void* gbuf, float* sum_g, float* sum_gx, void* stream) {
+  DFB_REQUIRE(C % 8 == 0, "bn_bwd_reduce: C %% 8 != 0 (C=%d)", C);
+  const int rpb = rows_per_block(M);
+  dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(C / 8, BN_THREADS));
+#define L(TX, TY) bn_bwd_reduce_kernel<TX, TY><<<grid, BN_THREADS, 0, ST>>>((const TY*)dy, (const TX*)x, mean, invstd, gamma, beta, (const TY*)residual, act, chan_scale, rows_per_sample, M, C, (TY*)gbuf, sum_g, sum_gx, rpb)
+  if (x_dtype == 0 && y_dtype == 0) L(float, float);
+  else if (x_dtype == 0 && y_dtype == 1) L(float, bf16);
+  else if (x_dtype == 1 && y_dtype == 1) L(bf16, bf16);
+  else if (x_dtype == 1 && y_dtype == 0) L(bf16, float);
+  else { dfb_set_error("bn_bwd_reduce: bad dtypes"); return DFB_ERR_ARG; }
+#undef L
+  return dfb_check_launch("bn_bwd_reduce");
+}
+
+extern "C" int dfb200_bn_bwd_apply(const void* gbuf, int y_dtype, const void* x, int x_dtype, const float* mean, const float* invstd, const float* gamma,
+                                   const float* sum_g, const float* sum_gx, float count, int training, int M, int C, void* dx, int dx_dtype, void* stream) {
+  DFB_REQUIRE(C % 8 == 0, "bn_bwd_apply: C %% 8 != 0 (C=%d)", C);
+  const int grid = ew_grid((long)M * C / 8);
+  const float inv = 1.f / count;
+#define L(TX, TY, TD) bn_bwd_apply_kernel<TX, TY, TD><<<grid, 256, 0, ST>>>((const TY*)gbuf, (const TX*)x, mean, invstd, gamma, sum_g, sum_gx, inv, training, M, C, (TD*)dx)
+  const int key = x_dtype * 4 + y_dtype * 2 + dx_dtype;
+  switch (key) {
+    case 0: L(float, float, float); break;
+    case 1: L(float, float, bf16); break;
+    case 2: L(float, bf16, float); break;
+    case 3: L(float, bf16, bf16); break;
+    case 4: L(bf16, float, float); break;
+    case 5: L(bf16, float, bf16); break;
+    case 6: L(bf16, bf16, float); break;
+    case 7: L(bf16, bf16, bf16); break;
+    default: dfb_set_error("bn_bwd_apply: bad dtypes"); return DFB_ERR_ARG;
+  }
+#undef L
+  return dfb_check_launch("bn_bwd_apply");
+}

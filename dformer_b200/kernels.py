@@ -1,0 +1,334 @@
+"""Thin torch-tensor front-ends for the C-ABI launchers (pointer / stride extraction only).
+
+PyTorch is used here for device memory and the current CUDA stream -- no torch compute.
+Every function launches asynchronously on ``torch.cuda.current_stream()``."""
+import ctypes
+
+import torch
+
+from ._lib import GemmArgs, PackEntry, lib
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+SIMT, TCGEN05, AUTO = 0, 1, 2
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+_TD = {F32: torch.float32, BF16: torch.bfloat16}
+
+
+def dt(t: torch.Tensor) -> int:
+    return _DT[t.dtype]
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t, name="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError(f"dformer_b200: {name} must be a CUDA tensor (there is no CPU path)")
+    return t
+
+
+def gemm(a, b, *, trans_a=False, trans_b=True, bias=None, out=None, out_dtype=None, act=ACT_NONE, act_col_start=0,
+         accumulate=False, backend=AUTO, splitk=0, alpha=0.0, M=None, N=None, K=None):
+    """out[M,N] = act(alpha * op(a) @ op(b) + bias).  a/b are 2-D with unit inner stride (row slices allowed)."""
+    _chk(a), _chk(b)
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    if M is None:
+        M = a.shape[1] if trans_a else a.shape[0]
+    if K is None:
+        K = a.shape[0] if trans_a else a.shape[1]
+    if N is None:
+        N = b.shape[0] if trans_b else b.shape[1]
+    kb = b.shape[1] if trans_b else b.shape[0]
+    assert kb >= K, (a.shape, b.shape, trans_a, trans_b)
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=out_dtype or a.dtype)
+    assert out.stride(1) == 1
+    g = GemmArgs()
+    g.A, g.B, g.C, g.bias = a.data_ptr(), b.data_ptr(), out.data_ptr(), _p(bias)
+    g.lda, g.ldb, g.ldc = a.stride(0), b.stride(0), out.stride(0)
+    g.M, g.N, g.K, g.batch, g.batch_inner = M, N, K, 1, 1
+    g.transA, g.transB = int(trans_a), int(trans_b)
+    g.a_dtype, g.b_dtype, g.out_dtype = dt(a), dt(b), dt(out)
+    g.act, g.act_col_start, g.accumulate, g.backend, g.splitk, g.alpha = act, act_col_start, int(accumulate), backend, splitk, alpha
+    lib().gemm(ctypes.byref(g), _s())
+    return out
+
+
+def bgemm(a, b, out, *, trans_a=False, trans_b=False, M, N, K, accumulate=False, alpha=0.0, splitk=1):
+    """Strided-batched GEMM over the leading dimension of 3-D tensors (SIMT backend)."""
+    assert a.dim() == 3 and b.dim() == 3 and out.dim() == 3 and a.stride(2) == 1 and b.stride(2) == 1 and out.stride(2) == 1
+    g = GemmArgs()
+    g.A, g.B, g.C, g.bias = a.data_ptr(), b.data_ptr(), out.data_ptr(), None
+    g.lda, g.ldb, g.ldc = a.stride(1), b.stride(1), out.stride(1)
+    g.strideA, g.strideB, g.strideC = a.stride(0), b.stride(0), out.stride(0)
+    g.M, g.N, g.K, g.batch, g.batch_inner = M, N, K, a.shape[0], 1
+    g.transA, g.transB = int(trans_a), int(trans_b)
+    g.a_dtype, g.b_dtype, g.out_dtype = dt(a), dt(b), dt(out)
+    g.accumulate, g.backend, g.splitk, g.alpha = int(accumulate), SIMT, splitk, alpha
+    lib().gemm(ctypes.byref(g), _s())
+    return out
+
+
+def colsum(x, out=None, accumulate=False):
+    M, N = x.shape
+    if out is None:
+        out = torch.empty(N, device=x.device, dtype=torch.float32)
+    lib().colsum(x.data_ptr(), dt(x), x.stride(0), M, N, out.data_ptr(), int(accumulate), _s())
+    return out
+
+
+def build_pack_table(entries, device):
+    """entries: list of (src_tensor, dst_tensor_view, rows, cols, dst_ld, kind) -> (device uint8 table, n, max_elems)"""
+    arr = (PackEntry * len(entries))()
+    mx = 1
+    for i, (src, dst, rows, cols, ld, kind) in enumerate(entries):
+        arr[i].src, arr[i].dst, arr[i].rows, arr[i].cols, arr[i].dst_ld, arr[i].kind = src.data_ptr(), dst.data_ptr(), rows, cols, ld, kind
+        mx = max(mx, rows * cols * (9 if kind == 1 else 1))
+    raw = bytes(arr)
+    host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+    return host.to(device), len(entries), mx
+
+
+def pack_params(table, n, max_elems, dst_dtype):
+    lib().pack_params(table.data_ptr(), n, max_elems, dst_dtype, _s())
+
+
+def unpack_conv_grad(dwp, cout, cin, out):
+    lib().unpack_conv_grad(dwp.data_ptr(), dwp.stride(0), cout, cin, out.data_ptr(), _s())
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, eps, out_dtype):
+    M, C = x.shape
+    y = torch.empty((M, C), device=x.device, dtype=out_dtype)
+    mean = torch.empty(M, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+    lib().layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, M, C, y.data_ptr(), dt(y), mean.data_ptr(), rstd.data_ptr(), _s())
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, accumulate_dx, dgamma, dbeta):
+    M, C = x.shape
+    lib().layernorm_bwd(dy.data_ptr(), dt(dy), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), M, C,
+                        dx.data_ptr(), int(accumulate_dx), dgamma.data_ptr(), dbeta.data_ptr(), _s())
+
+
+def dwconv_fwd(x, weight, bias, B, H, W, k, add_input=False, act=ACT_NONE):
+    C = x.shape[-1]
+    y = torch.empty_like(x)
+    lib().dwconv_fwd(x.data_ptr(), dt(x), weight.data_ptr(), _p(bias), B, H, W, C, k, int(add_input), act, y.data_ptr(), _s())
+    return y
+
+
+def dwconv_bwd(dy, x, weight, bias, B, H, W, k, add_input, act, dweight, dbias, need_dx=True):
+    C = x.shape[-1]
+    dz = torch.empty_like(dy) if act != ACT_NONE else None
+    dx = torch.empty_like(dy) if need_dx else None
+    lib().dwconv_bwd(dy.data_ptr(), x.data_ptr(), dt(x), weight.data_ptr(), _p(bias), B, H, W, C, k, int(add_input), act,
+                     _p(dz), _p(dx), dweight.data_ptr(), dbias.data_ptr(), _s())
+    return dx
+
+
+def mul_fwd(a, b, out):
+    M, N = a.shape
+    lib().mul_fwd(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0), dt(a), M, N, _s())
+    return out
+
+
+def mul_bwd(dout, a, b, da, db):
+    M, N = a.shape
+    lib().mul_bwd(dout.data_ptr(), dout.stride(0), a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), da.data_ptr(), da.stride(0),
+                  db.data_ptr(), db.stride(0), dt(a), M, N, _s())
+
+
+def scale_residual_fwd(res, y, ls, scale_b, rows_per_sample):
+    M, C = res.shape
+    out = torch.empty_like(res)
+    lib().scale_residual_fwd(res.data_ptr(), y.data_ptr(), dt(y), ls.data_ptr(), _p(scale_b), M, C, rows_per_sample, out.data_ptr(), _s())
+    return out
+
+
+def scale_residual_bwd(dout, y, ls, scale_b, rows_per_sample, dls):
+    M, C = dout.shape
+    dy = torch.empty_like(y)
+    lib().scale_residual_bwd(dout.data_ptr(), y.data_ptr(), dt(y), ls.data_ptr(), _p(scale_b), M, C, rows_per_sample, dy.data_ptr(), dls.data_ptr(), _s())
+    return dy
+
+
+def pool7_fwd(xn, en, B, H, W):
+    C1, C2 = xn.shape[-1], en.shape[-1]
+    out = torch.empty((B * 49, C1 + C2), device=xn.device, dtype=xn.dtype)
+    lib().pool7_fwd(xn.data_ptr(), C1, en.data_ptr(), C2, dt(xn), B, H, W, out.data_ptr(), _s())
+    return out
+
+
+def pool7_bwd(dout, C1, C2, B, H, W):
+    dxn = torch.empty((B * H * W, C1), device=dout.device, dtype=dout.dtype)
+    den = torch.empty((B * H * W, C2), device=dout.device, dtype=dout.dtype)
+    lib().pool7_bwd(dout.data_ptr(), C1, C2, dt(dout), B, H, W, dxn.data_ptr(), den.data_ptr(), _s())
+    return dxn, den
+
+
+def gaa_fwd(m, kv, B, HW, heads, d):
+    out = torch.empty((B * 49, heads * d), device=m.device, dtype=torch.float32)
+    probs = torch.empty((B, heads, 49, HW), device=m.device, dtype=torch.float32)
+    lib().gaa_fwd(m.data_ptr(), kv.data_ptr(), dt(m), B, HW, heads, d, out.data_ptr(), probs.data_ptr(), _s())
+    return out, probs
+
+
+def gaa_bwd(dout, m, kv, probs, B, HW, heads, d):
+    dm = torch.empty((B * 49, heads * d), device=m.device, dtype=torch.float32)
+    dkv = torch.empty_like(kv)
+    scratch = torch.empty((B, heads, 49, HW), device=m.device, dtype=torch.float32)
+    lib().gaa_bwd(dout.data_ptr(), m.data_ptr(), kv.data_ptr(), probs.data_ptr(), dt(m), B, HW, heads, d, dm.data_ptr(), dkv.data_ptr(),
+                  scratch.data_ptr(), _s())
+    return dm, dkv
+
+
+def resize_fwd(inp, B, Hi, Wi, out, Ho, Wo, col0=0):
+    C = inp.shape[-1]
+    lib().resize_fwd(inp.data_ptr(), dt(inp), B, Hi, Wi, C, out.data_ptr(), dt(out), Ho, Wo, out.stride(0), col0, _s())
+    return out
+
+
+def resize_bwd(dout, col0, B, Hi, Wi, C, Ho, Wo, din, accumulate=False):
+    lib().resize_bwd(dout.data_ptr(), dt(dout), dout.stride(0), col0, B, Hi, Wi, C, Ho, Wo, din.data_ptr(), dt(din), int(accumulate), _s())
+    return din
+
+
+def im2col_fwd(inp, strides, B, H, W, Cin, out_dtype, ld):
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    out = torch.empty((B * Ho * Wo, ld), device=inp.device, dtype=out_dtype)
+    sb, sy, sx, sc = strides
+    lib().im2col3x3s2_fwd(inp.data_ptr(), dt(inp), sb, sy, sx, sc, B, H, W, Cin, out.data_ptr(), dt(out), ld, _s())
+    return out
+
+
+def im2col_bwd(dcol, B, H, W, Cin, in_dtype):
+    din = torch.empty((B * H * W, Cin), device=dcol.device, dtype=in_dtype)
+    lib().im2col3x3s2_bwd(dcol.data_ptr(), dt(dcol), dcol.stride(0), B, H, W, Cin, din.data_ptr(), dt(din), _s())
+    return din
+
+
+def bn_stats(x):
+    M, C = x.shape
+    st = torch.empty((2, C), device=x.device, dtype=torch.float64)
+    lib().bn_stats(x.data_ptr(), dt(x), M, C, st[0].data_ptr(), st[1].data_ptr(), _s())
+    return st
+
+
+def bn_finalize(st, count, eps, momentum, running_mean, running_var):
+    C = st.shape[1]
+    ms = torch.empty((2, C), device=st.device, dtype=torch.float32)
+    lib().bn_finalize(st[0].data_ptr(), st[1].data_ptr(), float(count), eps, momentum, C, ms[0].data_ptr(), ms[1].data_ptr(),
+                      _p(running_mean), _p(running_var), _s())
+    return ms
+
+
+def bn_eval_stats(running_mean, running_var, eps):
+    C = running_mean.numel()
+    ms = torch.empty((2, C), device=running_mean.device, dtype=torch.float32)
+    lib().bn_eval_stats(running_mean.data_ptr(), running_var.data_ptr(), eps, C, ms[0].data_ptr(), ms[1].data_ptr(), _s())
+    return ms
+
+
+def bn_apply(x, ms, gamma, beta, out_dtype, residual=None, act=ACT_NONE, chan_scale=None, rows_per_sample=1):
+    M, C = x.shape
+    y = torch.empty((M, C), device=x.device, dtype=out_dtype)
+    lib().bn_apply(x.data_ptr(), dt(x), ms[0].data_ptr(), ms[1].data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(residual), act,
+                   _p(chan_scale), rows_per_sample, M, C, y.data_ptr(), dt(y), _s())
+    return y
+
+
+def bn_bwd_reduce(dy, x, ms, gamma, beta, residual, act, chan_scale, rows_per_sample):
+    M, C = x.shape
+    gbuf = torch.empty_like(dy)
+    sums = torch.zeros((2, C), device=x.device, dtype=torch.float32)
+    lib().bn_bwd_reduce(dy.data_ptr(), dt(dy), x.data_ptr(), dt(x), ms[0].data_ptr(), ms[1].data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                        _p(residual), act, _p(chan_scale), rows_per_sample, M, C, gbuf.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), _s())
+    return gbuf, sums
+
+
+def bn_bwd_apply(gbuf, x, ms, gamma, sums, count, training, dx_dtype):
+    M, C = x.shape
+    dx = torch.empty((M, C), device=x.device, dtype=dx_dtype)
+    lib().bn_bwd_apply(gbuf.data_ptr(), dt(gbuf), x.data_ptr(), dt(x), ms[0].data_ptr(), ms[1].data_ptr(), gamma.data_ptr(),
+                       sums[0].data_ptr(), sums[1].data_ptr(), float(count), int(training), M, C, dx.data_ptr(), dt(dx), _s())
+    return dx
+
+
+def normalize_cols(x):
+    B, D, R = x.shape
+    out = torch.empty_like(x)
+    norms = torch.empty((B, R), device=x.device, dtype=torch.float32)
+    lib().normalize_cols(x.data_ptr(), B, D, R, out.data_ptr(), norms.data_ptr(), _s())
+    return out, norms
+
+
+def softmax_rows(x):
+    out = torch.empty_like(x)
+    lib().softmax_rows(x.data_ptr(), x.numel() // x.shape[-1], x.shape[-1], out.data_ptr(), _s())
+    return out
+
+
+def softmax_rows_bwd(dout, out):
+    din = torch.empty_like(out)
+    lib().softmax_rows_bwd(dout.data_ptr(), out.data_ptr(), out.numel() // out.shape[-1], out.shape[-1], din.data_ptr(), _s())
+    return din
+
+
+def mu_update(a, num, den, eps=1e-6):
+    out = torch.empty_like(a)
+    lib().mu_update(a.data_ptr(), num.data_ptr(), den.data_ptr(), eps, a.numel(), out.data_ptr(), _s())
+    return out
+
+
+def mu_update_bwd(dout, a, num, den, da, accumulate_da, eps=1e-6):
+    dnum = torch.empty_like(a)
+    dden = torch.empty_like(a)
+    lib().mu_update_bwd(dout.data_ptr(), a.data_ptr(), num.data_ptr(), den.data_ptr(), eps, a.numel(), da.data_ptr(), int(accumulate_da),
+                        dnum.data_ptr(), dden.data_ptr(), _s())
+    return dnum, dden
+
+
+def cast(x, dtype):
+    out = torch.empty(x.shape, device=x.device, dtype=dtype)
+    lib().cast(x.data_ptr(), dt(x), out.data_ptr(), dt(out), x.numel(), _s())
+    return out
+
+
+def axpy(x, alpha, y):
+    lib().axpy(x.data_ptr(), dt(x), alpha, y.data_ptr(), dt(y), x.numel(), _s())
+    return y
+
+
+def upsample_ce_fwd(small, B, h, w, ncls, H, W, label, ignore, want_out=True, want_loss=True):
+    dev = small.device
+    out = torch.empty((B, ncls, H, W), device=dev, dtype=torch.float32) if want_out else None
+    lse = torch.empty((B, H, W), device=dev, dtype=torch.float32) if want_loss else None
+    acc = torch.zeros(2, device=dev, dtype=torch.float32) if want_loss else None
+    lib().upsample_ce_fwd(small.data_ptr(), dt(small), B, h, w, ncls, H, W, _p(label), ignore, _p(out), _p(lse), _p(acc), _s())
+    loss = None
+    if want_loss:
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        lib().ce_finalize(acc.data_ptr(), loss.data_ptr(), _s())
+    return out, lse, acc, loss
+
+
+def upsample_ce_bwd(small, B, h, w, ncls, H, W, label, ignore, lse, acc, dloss):
+    dsmall = torch.empty_like(small)
+    lib().upsample_ce_bwd(small.data_ptr(), dt(small), B, h, w, ncls, H, W, label.data_ptr(), ignore, lse.data_ptr(), acc.data_ptr(),
+                          dloss.data_ptr(), dsmall.data_ptr(), dt(dsmall), _s())
+    return dsmall
+
+
+def adamw(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0):
+    c1 = 1.0 - beta1 ** step
+    c2 = 1.0 - beta2 ** step
+    lib().adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps, wd, c1, c2, grad_scale, _s())

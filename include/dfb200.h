@@ -1,0 +1,198 @@
+/* dfb200.h -- C ABI of libdformer_b200.so: hand-written sm_100a kernels for the DFormer RGB-D
+ * forward/backward hot path (encoder Block/attention, LightHamHead/NMF2D, upsample + CE loss).
+ *
+ * The reference (Originofamonia/DFormer) is pure PyTorch and has NO native interface; every entry
+ * point below replaces a group of ATen/cuDNN/cuBLAS calls issued by the reference file:line cited at
+ * the declaration.  Conventions:
+ *   - plain pointers + sizes, no torch types; the CALLER owns all memory (outputs, workspaces);
+ *   - every launcher is asynchronous on the given `stream` (a cudaStream_t passed as void*),
+ *     never synchronises, never allocates device memory;
+ *   - returns 0 on success, a negative code otherwise; dfb200_last_error() gives the message;
+ *   - `dtype` codes: 0 = float32, 1 = bfloat16.  Activations are channels-last: [B, H, W, C]
+ *     (= row-major [M, C] with M = B*H*W).  Statistics, residual stream and parameters are float32.
+ */
+#ifndef DFB200_H_
+#define DFB200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFB200_F32 0
+#define DFB200_BF16 1
+#define DFB200_ACT_NONE 0
+#define DFB200_ACT_GELU 1
+#define DFB200_ACT_RELU 2
+#define DFB200_BACKEND_SIMT 0    /* CUDA-core fp32-accumulate GEMM (exact fp32 path)         */
+#define DFB200_BACKEND_TCGEN05 1 /* tcgen05/TMEM/TMA GEMM (bf16 operands, fp32 accumulation) */
+#define DFB200_BACKEND_AUTO 2
+
+const char* dfb200_last_error(void);
+int dfb200_version(void);
+
+/* ---- GEMM: nn.Linear / 1x1 conv / im2col conv forward, dgrad and wgrad --------------------------
+ * Replaces addmm/convolution/bmm of DFormer.py:60,65,110-121,125,133,141-143, ham_head.py:48,89,122-141,
+ * 174-177,234,238, decode_head.py:230 and their autograd backward.
+ *   C[M,N] = act( opA(A) * opB(B) + bias ),   opA(A) is M x K, opB(B) is K x N
+ *   transA = 0: A stored [M,K] (lda)    transA = 1: A stored [K,M]
+ *   transB = 0: B stored [K,N] (ldb)    transB = 1: B stored [N,K]   (nn.Linear weight layout)
+ * `act` is applied to columns >= act_col_start only (fused q|q_cut|l projection, DFormer.py:110-113).
+ * `accumulate` adds into an fp32 C.  `batch` > 1 runs strided-batched problems (SIMT backend only).
+ * The SIMT backend accepts any mix of fp32/bf16 A and B; tcgen05 needs both bf16. */
+typedef struct dfb200_gemm_args {
+  const void* A; const void* B; void* C;
+  const float* bias;
+  long lda, ldb, ldc;
+  long strideA, strideB, strideC;
+  int M, N, K, batch;
+  int batch_inner;       /* >1: two-level batch, z = zo*batch_inner + zi, offsets zo*stride + zi*stride_in */
+  long strideA_in, strideB_in, strideC_in;
+  int transA, transB;
+  int a_dtype, b_dtype, out_dtype;
+  int act, act_col_start;
+  int accumulate;
+  int backend;
+  int splitk;            /* 0 = auto, 1 = off, >1 = forced number of reduction splits */
+  float alpha;           /* scales the product before bias/activation (0 is treated as 1) */
+} dfb200_gemm_args;
+int dfb200_gemm(const dfb200_gemm_args* args, void* stream);
+
+/* column sums: out[n] (+)= sum_m X[m,n]  (bias gradients).  X is [M,N] with leading dimension ldx. */
+int dfb200_colsum(const void* X, int dtype, long ldx, int M, int N, float* out, int accumulate, void* stream);
+
+/* ---- parameter packing: fp32 parameters -> compute-dtype GEMM operands ---------------------------
+ * One launch converts a table of parameter tensors.  kind 0: row-major [rows, cols] copy into
+ * dst (leading dimension dst_ld, zero-padding cols..dst_ld-1 is the caller's job via memset);
+ * kind 1: conv weight [Cout, Cin, 3, 3] -> [Cout, 9*Cin (+pad)] with k = (ky*3+kx)*Cin + ci.
+ * The table lives in DEVICE memory (uploaded once by the caller). */
+typedef struct dfb200_pack_entry {
+  const float* src; void* dst;
+  int rows, cols, dst_ld, kind;   /* kind 1: cols = Cin */
+} dfb200_pack_entry;
+int dfb200_pack_params(const dfb200_pack_entry* table_dev, int n_entries, int max_elems, int dst_dtype, void* stream);
+/* inverse of kind 1 for gradients: dW[Cout,Cin,3,3] = gather(dWp[Cout, ld]) */
+int dfb200_unpack_conv_grad(const float* dWp, int ld, int Cout, int Cin, float* dW, void* stream);
+
+/* ---- LayerNorm over channels (DFormer.py:37-39, eps 1e-6) ---------------------------------------- */
+int dfb200_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int M, int C,
+                         void* y, int y_dtype, float* mean, float* rstd, void* stream);
+/* dx is fp32 [M,C]; if accumulate_dx != 0 the LN gradient is added to dx (residual-stream gradient).
+ * dgamma/dbeta are accumulated with atomics and must be zero-initialised by the caller. */
+int dfb200_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean,
+                         const float* rstd, int M, int C, float* dx, int accumulate_dx, float* dgamma, float* dbeta,
+                         void* stream);
+
+/* ---- depthwise k x k conv, stride 1, 'same' padding, channels-last (DFormer.py:54,62,80-81,115,133)
+ * y = act( dw(x) + bias [+ x if add_input] ).  weight is the nn.Conv2d tensor [C,1,k,k] (fp32), k in {3,7}. */
+int dfb200_dwconv_fwd(const void* x, int dtype, const float* weight, const float* bias, int B, int H, int W, int C,
+                      int k, int add_input, int act, void* y, void* stream);
+/* Backward.  Given dy and the forward input x:
+ *   dz = dy * act'(z) with z recomputed from x when act != 0;  dx = dw^T(dz) [+ dz];
+ *   dweight[C,1,k,k], dbias[C] accumulated with atomics (zero-initialised by the caller).
+ * `dz_buf` is a caller-provided scratch of the same shape/dtype as dy (only used when act != 0). */
+int dfb200_dwconv_bwd(const void* dy, const void* x, int dtype, const float* weight, const float* bias, int B, int H,
+                      int W, int C, int k, int add_input, int act, void* dz_buf, void* dx, float* dweight,
+                      float* dbias, void* stream);
+
+/* ---- elementwise glue of Block/Attention ---------------------------------------------------------
+ * mul:  out[m, n] = a[m, n] * b[m, n]  with independent leading dimensions (q*a, cut*e: DFormer.py:134-135;
+ *       `out` is a column slice of the concat buffer of :137-140). */
+int dfb200_mul_fwd(const void* a, long lda, const void* b, long ldb, void* out, long ldo, int dtype, int M, int N, void* stream);
+int dfb200_mul_bwd(const void* dout, long ldo, const void* a, long lda, const void* b, long ldb, void* da, long ldda,
+                   void* db, long lddb, int dtype, int M, int N, void* stream);
+/* layer-scale residual (DFormer.py:173-179): out[m,c] = res[m,c] + scale_b[b] * ls[c] * y[m,c]
+ * (scale_b = DropPath mask / keep_prob per sample, NULL = 1).  res/out fp32, y in `dtype`. rows_per_sample = H*W. */
+int dfb200_scale_residual_fwd(const float* res, const void* y, int dtype, const float* ls, const float* scale_b,
+                              int M, int C, int rows_per_sample, float* out, void* stream);
+/* dy = dout * ls * scale_b;  dls[c] += sum_m dout*y*scale_b (atomics; zero-init by caller). d(res) = dout (alias). */
+int dfb200_scale_residual_bwd(const float* dout, const void* y, int dtype, const float* ls, const float* scale_b,
+                              int M, int C, int rows_per_sample, void* dy, float* dls, void* stream);
+
+/* ---- Global Awareness Attention pieces (DFormer.py:107-108,120-131) ------------------------------
+ * pool: AdaptiveAvgPool2d(7,7) of cat[xn (C1 ch), en (C2 ch)] -> out [B,49,C1+C2] (compute dtype). */
+int dfb200_pool7_fwd(const void* xn, int C1, const void* en, int C2, int dtype, int B, int H, int W, void* out, void* stream);
+int dfb200_pool7_bwd(const void* dout, int C1, int C2, int dtype, int B, int H, int W, void* dxn, void* den, void* stream);
+/* attention: queries m [B,49,heads*d], keys/values kv [B,HW,2*heads*d] (k = cols [0,heads*d), v = rest,
+ * head-major), softmax over the HW pixels, scale d^-0.5.  out [B,49,heads*d].
+ * out is fp32 (it is tiny and feeds the 7x7 -> HxW resize). */
+int dfb200_gaa_fwd(const void* m, const void* kv, int dtype, int B, int HW, int heads, int d, float* out,
+                   float* probs /* [B,heads,49,HW] fp32, kept for backward */, void* stream);
+/* dout fp32 [B,49,heads*d]; dm fp32 [B,49,heads*d]; dkv [B,HW,2*heads*d] in `dtype`;
+ * scratch: 2 * B*heads*49*HW floats (dP / dS). */
+int dfb200_gaa_bwd(const float* dout, const void* m, const void* kv, const float* probs, int dtype, int B, int HW,
+                   int heads, int d, float* dm, void* dkv, float* scratch, void* stream);
+/* bilinear (align_corners=False) resize of a channels-last map into a column slice of a wider buffer:
+ * out[b, y, x, col0 + c] = interp(in[b, :, :, c]).  Used for 7x7 -> HxW (DFormer.py:131), the head's
+ * resize+concat (ham_head.py:226-233) with fp32 inputs. */
+int dfb200_resize_fwd(const void* in, int in_dtype, int B, int Hi, int Wi, int C, void* out, int out_dtype, int Ho,
+                      int Wo, long ldo, int col0, void* stream);
+/* din (+)= resize^T(dout slice); din has the input's dtype; accumulate only for fp32 din. */
+int dfb200_resize_bwd(const void* dout, int out_dtype, long ldo, int col0, int B, int Hi, int Wi, int C, int Ho, int Wo,
+                      void* din, int in_dtype, int accumulate, void* stream);
+
+/* ---- dense 3x3 stride-2 convs of the stems / downsample layers (DFormer.py:194-228,295-296) --------
+ * im2col gather into [B*Ho*Wo, ld] (k = (ky*3+kx)*Cin + ci, zero padded to ld) followed by dfb200_gemm.
+ * Input addressing is generic: element (b, y, x, c) at in[b*sb + y*sy + x*sx + c*sc] so that the NCHW
+ * network inputs (and the channel-0 slice of modal_x, DFormer.py:286) are read in place. */
+int dfb200_im2col3x3s2_fwd(const void* in, int in_dtype, long sb, long sy, long sx, long sc, int B, int H, int W,
+                           int Cin, void* out, int out_dtype, int ld, void* stream);
+int dfb200_im2col3x3s2_bwd(const void* dcol, int col_dtype, int ld, int B, int H, int W, int Cin, void* din,
+                           int in_dtype, void* stream);
+
+/* ---- BatchNorm2d on channels-last activations (DFormer.py:196,199,207,210,219,225; ham_head.py:170,209,219)
+ * stats: sum[c], sumsq[c] over M rows (fp32, written not accumulated).  Cross-rank SyncBN all-reduces them. */
+int dfb200_bn_stats(const void* x, int dtype, int M, int C, double* sum, double* sumsq, void* stream);
+/* finalize: mean/invstd from (sum, sumsq, count); updates running stats (momentum, unbiased var) if non-NULL. */
+int dfb200_bn_finalize(const double* sum, const double* sumsq, double count, float eps, float momentum, int C, float* mean,
+                       float* invstd, float* running_mean, float* running_var, void* stream);
+/* eval: mean/invstd from running statistics */
+int dfb200_bn_eval_stats(const float* running_mean, const float* running_var, float eps, int C, float* mean, float* invstd, void* stream);
+/* y = act( (x-mean)*invstd*gamma + beta [+ residual] ) [* chan_scale[b,c]] ; act: 0 none, 1 GELU, 2 ReLU */
+int dfb200_bn_apply(const void* x, int x_dtype, const float* mean, const float* invstd, const float* gamma,
+                    const float* beta, const void* residual, int act, const float* chan_scale, int rows_per_sample,
+                    int M, int C, void* y, int y_dtype, void* stream);
+/* backward, pass 1: g = dy [* chan_scale] * act'(.) ; writes g (dtype of y) into gbuf, accumulates
+ * sum_g[c], sum_gx[c] = sum g*xhat (zero-init by caller).  pass 2 (bn_bwd_apply):
+ *   dx = gamma*invstd*( g - sum_g/n - xhat*sum_gx/n )   (training)  or gamma*invstd*g (eval)          */
+int dfb200_bn_bwd_reduce(const void* dy, int y_dtype, const void* x, int x_dtype, const float* mean, const float* invstd,
+                         const float* gamma, const float* beta, const void* residual, int act, const float* chan_scale,
+                         int rows_per_sample, int M, int C, void* gbuf, float* sum_g, float* sum_gx, void* stream);
+int dfb200_bn_bwd_apply(const void* gbuf, int y_dtype, const void* x, int x_dtype, const float* mean, const float* invstd,
+                        const float* gamma, const float* sum_g, const float* sum_gx, float count, int training, int M,
+                        int C, void* dx, int dx_dtype, void* stream);
+
+/* ---- NMF2D element-wise steps (ham_head.py:49,115,126,133,143); the bmm's go through dfb200_gemm ---- */
+int dfb200_normalize_cols(const float* in, int B, int D, int R, float* out, float* norms, void* stream); /* F.normalize(dim=1) */
+int dfb200_softmax_rows(const float* in, int rows, int cols, float* out, void* stream);
+int dfb200_softmax_rows_bwd(const float* dout, const float* out, int rows, int cols, float* din, void* stream);
+/* out = a * num / (den + eps) */
+int dfb200_mu_update(const float* a, const float* num, const float* den, float eps, long n, float* out, void* stream);
+/* given dout: da (+)= dout*num/(den+eps); dnum = dout*a/(den+eps); dden = -dout*a*num/(den+eps)^2 */
+int dfb200_mu_update_bwd(const float* dout, const float* a, const float* num, const float* den, float eps, long n,
+                         float* da, int accumulate_da, float* dnum, float* dden, void* stream);
+int dfb200_cast(const void* in, int in_dtype, void* out, int out_dtype, long n, void* stream);
+int dfb200_axpy(const void* x, int x_dtype, float alpha, void* y, int y_dtype, long n, void* stream); /* y += alpha*x */
+
+/* ---- fused x8 bilinear upsample + cross entropy (builder.py:203,230) ------------------------------
+ * logits_small: channels-last [B, h, w, ncls] (compute dtype).  Writes (optionally) the NCHW fp32
+ * up-sampled logits `out` [B, ncls, H, W], and accumulates loss_sum / valid_count (2 floats, zero-init).
+ * label: int64 [B,H,W], `ignore` = 255.  loss = loss_sum / valid_count is finished by the caller or by
+ * dfb200_ce_finalize (device scalar, no host sync). */
+int dfb200_upsample_ce_fwd(const void* logits_small, int dtype, int B, int h, int w, int ncls, int H, int W,
+                           const int64_t* label, int ignore, float* out_nchw, float* lse /* [B,H,W] */, float* loss_acc,
+                           void* stream);
+int dfb200_ce_finalize(const float* loss_acc, float* loss, void* stream);
+/* dlogits_small [B,h,w,ncls] = resize^T( (softmax(up) - onehot) * dloss / valid )  (gather form, deterministic) */
+int dfb200_upsample_ce_bwd(const void* logits_small, int dtype, int B, int h, int w, int ncls, int H, int W,
+                           const int64_t* label, int ignore, const float* lse, const float* loss_acc, const float* dloss,
+                           void* dlogits_small, int dl_dtype, void* stream);
+
+/* ---- fused multi-tensor AdamW on flat fp32 buffers (utils/train.py:211,336; next-row N1) ------------ */
+int dfb200_adamw(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, float bias_c1, float bias_c2, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFB200_H_ */

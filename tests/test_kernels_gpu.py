@@ -1,0 +1,382 @@
+"""Kernel-level parity: every C-ABI launcher against the plain-PyTorch fp32 statement of the same op.
+
+fp32 kernels: tight tolerances.  bf16 kernels: inputs are rounded to bf16 first, the reference is
+computed in fp32 from the rounded inputs, and the tolerance covers one bf16 rounding of the output."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+
+
+def K():
+    from dformer_b200 import kernels
+    return kernels
+
+
+def tol(dtype):
+    return dict(rtol=2e-2, atol=2e-2) if dtype == torch.bfloat16 else dict(rtol=1e-4, atol=1e-4)
+
+
+def rnd(*shape, dtype=torch.float32, scale=1.0):
+    return (torch.randn(*shape, device=DEV) * scale).to(dtype)
+
+
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+# ----------------------------------------------------------------------------- GEMM (SIMT)
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K_", [(300, 96, 48), (49, 40, 130), (1000, 144, 288)])
+def test_gemm_simt(dtype, ta, tb, M, N, K_):
+    k = K()
+    a = rnd(K_, M, dtype=dtype) if ta else rnd(M, K_, dtype=dtype)
+    b = rnd(N, K_, dtype=dtype) if tb else rnd(K_, N, dtype=dtype)
+    bias = rnd(N)
+    out = k.gemm(a, b, trans_a=ta, trans_b=tb, bias=bias, backend=k.SIMT, act=k.ACT_GELU, act_col_start=N // 2)
+    A = (a.float().t() if ta else a.float())
+    Bm = (b.float().t() if tb else b.float())
+    ref = A @ Bm + bias
+    ref[:, N // 2:] = F.gelu(ref[:, N // 2:])
+    torch.testing.assert_close(out.float(), ref, **(dict(rtol=2e-2, atol=5e-2) if dtype == torch.bfloat16 else dict(rtol=1e-4, atol=1e-3)))
+
+
+def test_gemm_simt_splitk_and_accumulate():
+    k = K()
+    a, b = rnd(5000, 64), rnd(5000, 96)
+    out = k.gemm(a, b, trans_a=True, trans_b=False, backend=k.SIMT, splitk=8)
+    ref = a.t() @ b
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=5e-3)
+    out2 = k.gemm(a, b, trans_a=True, trans_b=False, backend=k.SIMT, splitk=1, out=ref.clone(), accumulate=True)
+    torch.testing.assert_close(out2, 2 * ref, rtol=1e-4, atol=1e-2)
+
+
+def test_bgemm_mixed_dtypes():
+    k = K()
+    a = rnd(3, 70, 33, dtype=torch.bfloat16)
+    b = rnd(3, 33, 20)
+    out = torch.empty(3, 70, 20, device=DEV)
+    k.bgemm(a, b, out, M=70, N=20, K=33, alpha=0.5)
+    torch.testing.assert_close(out, 0.5 * torch.bmm(a.float(), b), rtol=1e-4, atol=1e-3)
+
+
+def test_colsum():
+    k = K()
+    for dtype in DTYPES:
+        for N in (96, 40, 37, 2304):
+            x = rnd(1234, N, dtype=dtype)
+            torch.testing.assert_close(k.colsum(x), x.float().sum(0), rtol=1e-3, atol=1e-2)
+
+
+# ----------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C", [16, 48, 96, 288, 576])
+def test_layernorm(dtype, C):
+    k = K()
+    M = 777
+    x = rnd(M, C) * 2 + 0.5
+    g, b = 1 + 0.1 * rnd(C), 0.1 * rnd(C)
+    y, mean, rstd = k.layernorm_fwd(x, g, b, 1e-6, dtype)
+    xr = x.clone().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (C,), gr, br, 1e-6)
+    torch.testing.assert_close(y.float(), ref, **tol(dtype))
+    dy = rnd(M, C, dtype=dtype)
+    ref.backward(dy.float())
+    dx = torch.ones(M, C, device=DEV)
+    dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    k.layernorm_bwd(dy, x, g, mean, rstd, dx, True, dg, db)
+    torch.testing.assert_close(dx - 1, xr.grad, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(dg, gr.grad, rtol=1e-3, atol=2e-2)
+    torch.testing.assert_close(db, br.grad, rtol=1e-3, atol=2e-2)
+
+
+# ----------------------------------------------------------------------------- depthwise conv
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("k_,C,add,act", [(3, 256, True, 1), (7, 96, False, 0), (7, 48, False, 0), (3, 72, True, 1)])
+def test_dwconv(dtype, k_, C, add, act):
+    k = K()
+    B, H, W = 2, 15, 21
+    x = rnd(B, H, W, C, dtype=dtype)
+    w, b = rnd(C, 1, k_, k_, scale=0.2), rnd(C, scale=0.1)
+    y = k.dwconv_fwd(x.view(-1, C), w, b, B, H, W, k_, add, act)
+    xr = x.float().clone().requires_grad_(True)
+    wr, brr = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    z = F.conv2d(xr.permute(0, 3, 1, 2), wr, brr, padding=k_ // 2, groups=C).permute(0, 2, 3, 1)
+    if add:
+        z = z + xr
+    ref = F.gelu(z) if act == 1 else z
+    torch.testing.assert_close(y.view(B, H, W, C).float(), ref, **tol(dtype))
+    dy = rnd(B, H, W, C, dtype=dtype)
+    ref.backward(dy.float())
+    dw, dbias = torch.zeros_like(w), torch.zeros_like(b)
+    dx = k.dwconv_bwd(dy.view(-1, C), x.view(-1, C), w, b, B, H, W, k_, add, act, dw, dbias)
+    t = dict(rtol=3e-2, atol=5e-2) if dtype == torch.bfloat16 else dict(rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(dx.view(B, H, W, C).float(), xr.grad, **t)
+    torch.testing.assert_close(dw, wr.grad, rtol=3e-2 if dtype == torch.bfloat16 else 1e-3, atol=0.3 if dtype == torch.bfloat16 else 1e-2)
+    torch.testing.assert_close(dbias, brr.grad, rtol=3e-2 if dtype == torch.bfloat16 else 1e-3, atol=0.3 if dtype == torch.bfloat16 else 1e-2)
+
+
+# ----------------------------------------------------------------------------- gating / residual
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_mul_and_scale_residual(dtype):
+    k = K()
+    M, C = 600, 96
+    buf = rnd(M, 3 * C, dtype=dtype)
+    a, b = buf[:, :C], buf[:, C:2 * C]
+    cat = torch.zeros(M, 2 * C, device=DEV, dtype=dtype)
+    k.mul_fwd(a, b, cat[:, C:])
+    torch.testing.assert_close(cat[:, C:].float(), a.float() * b.float(), **tol(dtype))
+    assert cat[:, :C].abs().max() == 0
+    dout = rnd(M, 2 * C, dtype=dtype)
+    da, db = torch.empty(M, C, device=DEV, dtype=dtype), torch.empty(M, C, device=DEV, dtype=dtype)
+    k.mul_bwd(dout[:, C:], a, b, da, db)
+    torch.testing.assert_close(da.float(), dout[:, C:].float() * b.float(), **tol(dtype))
+    torch.testing.assert_close(db.float(), dout[:, C:].float() * a.float(), **tol(dtype))
+    # layer-scale residual with per-sample DropPath scale
+    B, hw = 3, 200
+    res, y, ls = rnd(M, C), rnd(M, C, dtype=dtype), rnd(C)
+    sb = torch.tensor([0.0, 1.25, 1.25], device=DEV)
+    out = k.scale_residual_fwd(res, y, ls, sb, hw)
+    ref = res + sb.repeat_interleave(hw)[:, None] * ls * y.float()
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+    g = rnd(M, C)
+    dls = torch.zeros(C, device=DEV)
+    dy = k.scale_residual_bwd(g, y, ls, sb, hw, dls)
+    torch.testing.assert_close(dy.float(), g * ls * sb.repeat_interleave(hw)[:, None], **tol(dtype))
+    torch.testing.assert_close(dls, (g * y.float() * sb.repeat_interleave(hw)[:, None]).sum(0), rtol=1e-3, atol=1e-2)
+
+
+# ----------------------------------------------------------------------------- pooling / attention / resize
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("H,W", [(60, 80), (15, 20), (2, 3), (9, 7)])
+def test_pool7(dtype, H, W):
+    k = K()
+    B, C1, C2 = 2, 64, 32
+    xn, en = rnd(B, H, W, C1, dtype=dtype), rnd(B, H, W, C2, dtype=dtype)
+    out = k.pool7_fwd(xn.view(-1, C1), en.view(-1, C2), B, H, W)
+    cat = torch.cat([xn, en], 3).float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.adaptive_avg_pool2d(cat, (7, 7))
+    torch.testing.assert_close(out.view(B, 7, 7, C1 + C2).float(), ref.permute(0, 2, 3, 1), **tol(dtype))
+    dout = rnd(B, 7, 7, C1 + C2, dtype=dtype)
+    ref.backward(dout.float().permute(0, 3, 1, 2))
+    dxn, den = k.pool7_bwd(dout.view(-1, C1 + C2), C1, C2, B, H, W)
+    gref = cat.grad.permute(0, 2, 3, 1)
+    torch.testing.assert_close(dxn.view(B, H, W, C1).float(), gref[..., :C1], **tol(dtype))
+    torch.testing.assert_close(den.view(B, H, W, C2).float(), gref[..., C1:], **tol(dtype))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("HW,heads,d", [(1200, 4, 36), (300, 8, 32), (4800, 2, 48), (6, 8, 16)])
+def test_gaa(dtype, HW, heads, d):
+    k = K()
+    B, Cp = 2, heads * d
+    m = rnd(B * 49, Cp, dtype=dtype)
+    kv = rnd(B * HW, 2 * Cp, dtype=dtype)
+    out, probs = k.gaa_fwd(m, kv, B, HW, heads, d)
+    mr = m.float().clone().requires_grad_(True)
+    kvr = kv.float().clone().requires_grad_(True)
+    q = mr.view(B, 49, heads, d).permute(0, 2, 1, 3)
+    kk, vv = kvr.view(B, HW, 2, heads, d).permute(2, 0, 3, 1, 4)
+    att = ((q * d ** -0.5) @ kk.transpose(-2, -1)).softmax(-1)
+    ref = (att @ vv).permute(0, 2, 1, 3).reshape(B * 49, Cp)
+    torch.testing.assert_close(out, ref, rtol=1e-3, atol=1e-3)
+    dout = rnd(B * 49, Cp)
+    ref.backward(dout)
+    dm, dkv = k.gaa_bwd(dout, m, kv, probs, B, HW, heads, d)
+    t = dict(rtol=3e-2, atol=3e-2) if dtype == torch.bfloat16 else dict(rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(dm, mr.grad, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(dkv.float(), kvr.grad, **t)
+
+
+@pytest.mark.parametrize("in_dtype,out_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("hi,wi,ho,wo", [(7, 7, 60, 80), (15, 20, 60, 80), (30, 40, 60, 80), (60, 80, 60, 80), (7, 7, 2, 3)])
+def test_resize(in_dtype, out_dtype, hi, wi, ho, wo):
+    k = K()
+    B, C = 2, 32
+    x = rnd(B, hi, wi, C, dtype=in_dtype)
+    out = torch.zeros(B * ho * wo, 3 * C, device=DEV, dtype=out_dtype)
+    k.resize_fwd(x.view(-1, C), B, hi, wi, out, ho, wo, col0=C)
+    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    ref = F.interpolate(xr, (ho, wo), mode="bilinear", align_corners=False)
+    torch.testing.assert_close(out.view(B, ho, wo, 3 * C)[..., C:2 * C].float(), ref.permute(0, 2, 3, 1), **tol(out_dtype))
+    assert out.view(B, ho, wo, 3 * C)[..., :C].abs().max() == 0
+    dout = rnd(B * ho * wo, 3 * C, dtype=out_dtype)
+    ref.backward(dout.view(B, ho, wo, 3 * C)[..., C:2 * C].float().permute(0, 3, 1, 2))
+    din = torch.ones(B * hi * wi, C, device=DEV, dtype=in_dtype)
+    k.resize_bwd(dout, C, B, hi, wi, C, ho, wo, din, accumulate=(in_dtype == torch.float32))
+    want = xr.grad.permute(0, 2, 3, 1).reshape(-1, C) + (1 if in_dtype == torch.float32 else 0)
+    t = dict(rtol=3e-2, atol=0.2) if torch.bfloat16 in (in_dtype, out_dtype) else dict(rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(din.float(), want, **t)
+
+
+# ----------------------------------------------------------------------------- im2col conv
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_im2col_conv3x3s2(dtype):
+    k = K()
+    B, H, W = 2, 30, 42
+    # NCHW fp32 network input with Cin = 3 (scalar path, K padded to 32)
+    x = rnd(B, 3, H, W)
+    col = k.im2col_fwd(x, (3 * H * W, W, 1, H * W), B, H, W, 3, dtype, 32)
+    w = rnd(16, 3, 3, 3, scale=0.3)
+    wp = torch.zeros(16, 32, device=DEV)
+    wp[:, :27] = w.permute(0, 2, 3, 1).reshape(16, 27)
+    out = col.float() @ wp.t()
+    ref = F.conv2d(x.to(dtype).float(), w, stride=2, padding=1).permute(0, 2, 3, 1).reshape(-1, 16)
+    torch.testing.assert_close(out, ref, rtol=1e-3, atol=1e-3)
+    # channel-0 slice of a 3-channel NCHW tensor with Cin = 1
+    col1 = k.im2col_fwd(x, (3 * H * W, W, 1, H * W), B, H, W, 1, dtype, 16)
+    w1 = rnd(8, 1, 3, 3)
+    wp1 = torch.zeros(8, 16, device=DEV)
+    wp1[:, :9] = w1.reshape(8, 9)
+    ref1 = F.conv2d(x[:, 0:1].to(dtype).float(), w1, stride=2, padding=1).permute(0, 2, 3, 1).reshape(-1, 8)
+    torch.testing.assert_close(col1.float() @ wp1.t(), ref1, rtol=1e-3, atol=1e-3)
+    # channels-last vector path (+ odd spatial size) and its adjoint
+    Cin, H2, W2 = 24, 15, 21
+    xc = rnd(B, H2, W2, Cin, dtype=dtype)
+    col2 = k.im2col_fwd(xc.view(-1, Cin), (H2 * W2 * Cin, W2 * Cin, Cin, 1), B, H2, W2, Cin, dtype, 9 * Cin)
+    w2 = rnd(40, Cin, 3, 3, scale=0.1)
+    xr = xc.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    ref2 = F.conv2d(xr, w2, stride=2, padding=1)
+    out2 = col2.float() @ w2.permute(0, 2, 3, 1).reshape(40, -1).t()
+    torch.testing.assert_close(out2, ref2.permute(0, 2, 3, 1).reshape(-1, 40), rtol=1e-3, atol=1e-3)
+    dy = rnd(*ref2.shape)
+    ref2.backward(dy)
+    dcol = (dy.permute(0, 2, 3, 1).reshape(-1, 40) @ w2.permute(0, 2, 3, 1).reshape(40, -1)).to(dtype)
+    din = k.im2col_bwd(dcol, B, H2, W2, Cin, dtype)
+    torch.testing.assert_close(din.float(), xr.grad.permute(0, 2, 3, 1).reshape(-1, Cin), **(dict(rtol=3e-2, atol=5e-2) if dtype == torch.bfloat16 else dict(rtol=1e-4, atol=1e-4)))
+    # pack / unpack of conv weights
+    from dformer_b200.kernels import build_pack_table, pack_params, unpack_conv_grad
+    dst = torch.zeros(40, 9 * Cin, device=DEV, dtype=dtype)
+    lin = rnd(10, 24)
+    dst2 = torch.zeros(12, 24, device=DEV, dtype=dtype)
+    table, n, mx = build_pack_table([(w2, dst, 40, Cin, 9 * Cin, 1), (lin, dst2[2:], 10, 24, 24, 0)], DEV)
+    pack_params(table, n, mx, k.dt(dst))
+    torch.testing.assert_close(dst.float(), w2.permute(0, 2, 3, 1).reshape(40, -1).to(dtype).float())
+    torch.testing.assert_close(dst2[2:].float(), lin.to(dtype).float())
+    back = unpack_conv_grad(w2.permute(0, 2, 3, 1).reshape(40, -1).contiguous(), 40, Cin, torch.empty_like(w2))
+    torch.testing.assert_close(back, w2)
+
+
+# ----------------------------------------------------------------------------- BatchNorm
+@pytest.mark.parametrize("x_dtype,y_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("act,use_res", [(0, False), (1, False), (2, False), (2, True)])
+def test_batchnorm_train(x_dtype, y_dtype, act, use_res):
+    k = K()
+    M, C, B = 2400, 48, 2
+    x = (rnd(M, C) * 1.5 + 0.7).to(x_dtype)
+    gamma, beta = 1 + 0.1 * rnd(C), 0.1 * rnd(C)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    res = rnd(M, C, dtype=y_dtype) if use_res else None
+    st = k.bn_stats(x)
+    ms = k.bn_finalize(st, M, 1e-5, 0.1, rm, rv)
+    y = k.bn_apply(x, ms, gamma, beta, y_dtype, residual=res, act=act)
+    xr = x.float().clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    z = F.batch_norm(xr, rm2, rv2, gr, br, True, 0.1, 1e-5)
+    rr = res.float().clone().requires_grad_(True) if use_res else None
+    if use_res:
+        z = z + rr
+    ref = F.gelu(z) if act == 1 else (F.relu(z) if act == 2 else z)
+    torch.testing.assert_close(y.float(), ref, **tol(y_dtype))
+    torch.testing.assert_close(rm, rm2, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(rv, rv2, rtol=1e-4, atol=1e-5)
+    dy = rnd(M, C, dtype=y_dtype)
+    ref.backward(dy.float())
+    gbuf, sums = k.bn_bwd_reduce(dy, x, ms, gamma, beta, res, act, None, M // B)
+    dx = k.bn_bwd_apply(gbuf, x, ms, gamma, sums, M, True, x_dtype)
+    t = dict(rtol=3e-2, atol=3e-2) if torch.bfloat16 in (x_dtype, y_dtype) else dict(rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(dx.float(), xr.grad, **t)
+    torch.testing.assert_close(sums[1], gr.grad, rtol=2e-2, atol=0.5 if y_dtype == torch.bfloat16 else 1e-2)   # dgamma
+    torch.testing.assert_close(sums[0], br.grad, rtol=2e-2, atol=0.5 if y_dtype == torch.bfloat16 else 1e-2)   # dbeta
+    if use_res:
+        torch.testing.assert_close(gbuf.float(), rr.grad, **t)
+
+
+def test_batchnorm_eval_and_channel_dropout():
+    k = K()
+    M, C, B = 960, 64, 2
+    x = rnd(M, C)
+    gamma, beta, rm, rv = 1 + 0.1 * rnd(C), 0.1 * rnd(C), 0.1 * rnd(C), 0.5 + torch.rand(C, device=DEV)
+    ms = k.bn_eval_stats(rm, rv, 1e-3)
+    mask = (torch.rand(B, C, device=DEV) > 0.3).float() / 0.7
+    y = k.bn_apply(x, ms, gamma, beta, torch.float32, act=2, chan_scale=mask, rows_per_sample=M // B)
+    ref = F.relu(F.batch_norm(x, rm, rv, gamma, beta, False, 0.1, 1e-3)) * mask.repeat_interleave(M // B, 0)
+    torch.testing.assert_close(y, ref, rtol=1e-4, atol=1e-5)
+
+
+# ----------------------------------------------------------------------------- NMF helpers
+def test_nmf_elementwise():
+    k = K()
+    b = torch.rand(2, 512, 64, device=DEV)
+    nb, norms = k.normalize_cols(b)
+    torch.testing.assert_close(nb, F.normalize(b, dim=1), rtol=1e-5, atol=1e-6)
+    x = rnd(300, 64)
+    sm = k.softmax_rows(x)
+    torch.testing.assert_close(sm, x.softmax(-1), rtol=1e-5, atol=1e-6)
+    g = rnd(300, 64)
+    xr = x.clone().requires_grad_(True)
+    xr.softmax(-1).backward(g)
+    torch.testing.assert_close(k.softmax_rows_bwd(g, sm), xr.grad, rtol=1e-4, atol=1e-6)
+    a, num, den = torch.rand(1000, device=DEV), torch.rand(1000, device=DEV), torch.rand(1000, device=DEV) + 0.1
+    ar, nr, dr = (t.clone().requires_grad_(True) for t in (a, num, den))
+    ref = ar * nr / (dr + 1e-6)
+    torch.testing.assert_close(k.mu_update(a, num, den), ref, rtol=1e-5, atol=1e-6)
+    ref.backward(g.flatten()[:1000])
+    da = torch.ones(1000, device=DEV)
+    dnum, dden = k.mu_update_bwd(g.flatten()[:1000].contiguous(), a, num, den, da, True)
+    torch.testing.assert_close(da - 1, ar.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dnum, nr.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dden, dr.grad, rtol=1e-4, atol=1e-4)
+    y = torch.ones(100, device=DEV, dtype=torch.bfloat16)
+    k.axpy(rnd(100), 2.0, y)
+    assert k.cast(y, torch.float32).dtype == torch.float32
+
+
+# ----------------------------------------------------------------------------- upsample + CE
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("ncls", [40, 37])
+def test_upsample_ce(dtype, ncls):
+    k = K()
+    B, h, w, H, W = 2, 12, 16, 96, 128
+    small = rnd(B, h, w, ncls, dtype=dtype)
+    label = torch.randint(0, ncls, (B, H, W), device=DEV)
+    label[torch.rand(B, H, W, device=DEV) < 0.1] = 255
+    out, lse, acc, loss = k.upsample_ce_fwd(small.view(-1, ncls), B, h, w, ncls, H, W, label, 255)
+    sr = small.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    up = F.interpolate(sr, (H, W), mode="bilinear", align_corners=False)
+    ref_loss = F.cross_entropy(up, label, reduction="none", ignore_index=255)[label != 255].mean()
+    torch.testing.assert_close(out, up, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(loss, ref_loss, rtol=1e-4, atol=1e-5)
+    (ref_loss * 3.0).backward()
+    dl = torch.full((), 3.0, device=DEV)
+    ds = k.upsample_ce_bwd(small.view(-1, ncls), B, h, w, ncls, H, W, label, 255, lse, acc, dl)
+    t = dict(rtol=3e-2, atol=1e-5) if dtype == torch.bfloat16 else dict(rtol=1e-3, atol=1e-7)
+    torch.testing.assert_close(ds.view(B, h, w, ncls).float(), sr.grad.permute(0, 2, 3, 1), **t)
+
+
+def test_adamw_matches_torch():
+    k = K()
+    p = rnd(1000)
+    g = rnd(1000)
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in (1, 2, 3):
+        pr.grad = g.clone()
+        opt.step()
+        k.adamw(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, 0.01, step)
+    torch.testing.assert_close(p, pr.detach(), rtol=1e-5, atol=1e-6)

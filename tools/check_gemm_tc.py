@@ -1,0 +1,91 @@
+"""Stand-alone parity check of the tcgen05 GEMM (run in its own process: a protocol bug traps the
+kernel and poisons the CUDA context).  Prints one line per case and exits non-zero on mismatch."""
+import sys
+import os
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dformer_b200 import kernels as k  # noqa: E402
+
+
+def main():
+    torch.manual_seed(0)
+    dev = "cuda"
+    ok = True
+    cases = []
+    # (M, N, K, trans_a, trans_b, out_dtype, act, splitk)
+    for M, N, K in [(128, 64, 64), (256, 96, 96), (300, 48, 48), (4800, 192, 192), (1000, 288, 1152), (19200, 768, 96),
+                    (777, 40, 512), (512, 2304, 576), (200, 144, 72), (4800, 512, 1056)]:
+        cases.append((M, N, K, False, True, torch.bfloat16, 1, 1))       # forward: A K-major, W K-major
+    for M, N, K in [(256, 64, 128), (300, 96, 240), (4800, 192, 480), (1000, 576, 288), (130, 48, 40)]:
+        cases.append((M, N, K, False, False, torch.bfloat16, 0, 1))      # dgrad: dY K-major, W MN-major
+    for M, N, K in [(64, 64, 512), (96, 96, 3000), (240, 96, 4800), (768, 96, 19200), (40, 512, 1234), (288, 1152, 2400)]:
+        cases.append((M, N, K, True, False, torch.float32, 0, 0))        # wgrad: both MN-major, split-K auto
+    cases.append((1000, 200, 320, False, True, torch.float32, 0, 1))
+    for (M, N, K, ta, tb, od, act, sk) in cases:
+        a = (torch.randn(K, M, device=dev) if ta else torch.randn(M, K, device=dev)).bfloat16()
+        b = (torch.randn(N, K, device=dev) if tb else torch.randn(K, N, device=dev)).bfloat16()
+        bias = torch.randn(N, device=dev)
+        out = k.gemm(a, b, trans_a=ta, trans_b=tb, bias=bias, backend=k.TCGEN05, out_dtype=od, act=act, act_col_start=N // 2 // 8 * 8, splitk=sk)
+        torch.cuda.synchronize()
+        A = a.float().t() if ta else a.float()
+        Bm = b.float().t() if tb else b.float()
+        ref = A @ Bm + bias
+        if act:
+            c0 = N // 2 // 8 * 8
+            ref[:, c0:] = torch.nn.functional.gelu(ref[:, c0:])
+        err = (out.float() - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        lim = (2e-2 if od == torch.bfloat16 else 2e-3) * max(scale, 1.0)
+        good = err <= lim and bool(torch.isfinite(out.float()).all())
+        ok &= good
+        print(f"{'OK ' if good else 'BAD'} M={M} N={N} K={K} ta={int(ta)} tb={int(tb)} out={od} act={act} err={err:.4g} lim={lim:.4g}", flush=True)
+    # strided C / A slices (column slice of a wider buffer), accumulate
+    buf = torch.randn(1000, 3 * 96, device=dev).bfloat16()
+    w = torch.randn(64, 96, device=dev).bfloat16()
+    outbuf = torch.zeros(1000, 256, device=dev, dtype=torch.bfloat16)
+    k.gemm(buf[:, 96:192], w, trans_b=True, backend=k.TCGEN05, out=outbuf[:, 64:128])
+    ref = buf[:, 96:192].float() @ w.float().t()
+    err = (outbuf[:, 64:128].float() - ref).abs().max().item()
+    good = err < 0.3 and outbuf[:, :64].abs().max().item() == 0 and outbuf[:, 128:].abs().max().item() == 0
+    ok &= good
+    print(f"{'OK ' if good else 'BAD'} strided slices err={err:.4g}")
+    acc = torch.ones(96, 64, device=dev)
+    x = torch.randn(5000, 64, device=dev).bfloat16()
+    dy = torch.randn(5000, 96, device=dev).bfloat16()
+    k.gemm(dy, x, trans_a=True, trans_b=False, backend=k.TCGEN05, out=acc, accumulate=True)
+    ref = dy.float().t() @ x.float() + 1
+    err = (acc - ref).abs().max().item()
+    good = err < 0.05
+    ok &= good
+    print(f"{'OK ' if good else 'BAD'} wgrad accumulate err={err:.4g}")
+    # timing of a few representative shapes
+    for (M, N, K) in [(153600, 768, 96), (153600, 96, 768), (38400, 1536, 192), (38400, 192, 1536), (9600, 1152, 288), (38400, 512, 1056), (8192, 8192, 8192)]:
+        a = torch.randn(M, K, device=dev).bfloat16()
+        b = torch.randn(N, K, device=dev).bfloat16()
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        for _ in range(3):
+            k.gemm(a, b, trans_b=True, backend=k.TCGEN05, out=out)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            k.gemm(a, b, trans_b=True, backend=k.TCGEN05, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(10):
+            torch.matmul(a, b.t(), out=out)
+        t1.record()
+        torch.cuda.synchronize()
+        ms_t = t0.elapsed_time(t1) / 10
+        fl = 2.0 * M * N * K
+        by = 2.0 * (M * K + N * K + M * N)
+        print(f"time M={M} N={N} K={K}: {ms:.4f} ms  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e6:.0f} GB/s | cuBLAS {ms_t:.4f} ms {fl / ms_t / 1e9:.1f} TFLOP/s")
+    print("ALL OK" if ok else "FAILED")
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
