@@ -143,9 +143,36 @@ __global__ void mul_bwd_kernel(const T* __restrict__ dout, long ldo, const T* __
   }
 }
 
+// ------------------------------------------------------------------ stand-alone activation
+template <typename T>
+__global__ void act_fwd_kernel(const T* __restrict__ in, long ldi, T* __restrict__ out, long ldo, int act, int M, int nvec) {
+  const long n = (long)M * nvec;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / nvec; const int c = (int)(i % nvec) * 8;
+    float v[8];
+    Vec8<T>::load(in + r * ldi + c, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = act == 1 ? gelu_f(v[j]) : fmaxf(v[j], 0.f);
+    Vec8<T>::store(out + r * ldo + c, v);
+  }
+}
+template <typename T>
+__global__ void act_bwd_kernel(const T* __restrict__ dout, long lddo, const T* __restrict__ z, long ldz, T* __restrict__ din, long lddi, int act, int M, int nvec) {
+  const long n = (long)M * nvec;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / nvec; const int c = (int)(i % nvec) * 8;
+    float g[8], zz[8];
+    Vec8<T>::load(dout + r * lddo + c, g);
+    Vec8<T>::load(z + r * ldz + c, zz);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= act == 1 ? gelu_grad_f(zz[j]) : (zz[j] > 0.f ? 1.f : 0.f);
+    Vec8<T>::store(din + r * lddi + c, g);
+  }
+}
+
 // ------------------------------------------------------------------ layer-scale residual
 template <typename T>
-__global__ void scale_residual_fwd_kernel(const float* __restrict__ res, const T* __restrict__ y, const float* __restrict__ ls,
+__global__ void scale_residual_fwd_kernel(const float* __restrict__ res, const T* __restrict__ y, long ldy, const float* __restrict__ ls,
                                           const float* __restrict__ scale_b, int M, int nvec, int rows_per_sample, float* __restrict__ out) {
   const long n = (long)M * nvec;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -153,7 +180,7 @@ __global__ void scale_residual_fwd_kernel(const float* __restrict__ res, const T
     const float sb = scale_b ? scale_b[r / rows_per_sample] : 1.f;
     float rv[8], yv[8], lv[8];
     Vec8<float>::load(res + i * 8, rv);
-    Vec8<T>::load(y + i * 8, yv);
+    Vec8<T>::load(y + r * ldy + c, yv);
     Vec8<float>::load(ls + c, lv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) rv[j] = fmaf(sb * lv[j], yv[j], rv[j]);
@@ -161,9 +188,9 @@ __global__ void scale_residual_fwd_kernel(const float* __restrict__ res, const T
   }
 }
 template <typename T>
-__global__ void __launch_bounds__(EW_THREADS) scale_residual_bwd_kernel(const float* __restrict__ dout, const T* __restrict__ y, const float* __restrict__ ls,
+__global__ void __launch_bounds__(EW_THREADS) scale_residual_bwd_kernel(const float* __restrict__ dout, const T* __restrict__ y, long ldy, const float* __restrict__ ls,
                                                                         const float* __restrict__ scale_b, int M, int C, int rows_per_sample,
-                                                                        T* __restrict__ dy, float* dls, int rows_per_block) {
+                                                                        T* __restrict__ dy, long lddy, float* dls, int rows_per_block) {
   extern __shared__ float smem[];
   float* outs[1] = {dls};
   colreduce_body<T, 1>(M, C, rows_per_block,
@@ -171,11 +198,11 @@ __global__ void __launch_bounds__(EW_THREADS) scale_residual_bwd_kernel(const fl
                          const float sb = scale_b ? scale_b[r / rows_per_sample] : 1.f;
                          float g[8], yv[8], lv[8], o[8];
                          Vec8<float>::load(dout + (long)r * C + c, g);
-                         Vec8<T>::load(y + (long)r * C + c, yv);
+                         Vec8<T>::load(y + (long)r * ldy + c, yv);
                          Vec8<float>::load(ls + c, lv);
 #pragma unroll
                          for (int j = 0; j < 8; ++j) { o[j] = g[j] * lv[j] * sb; acc[0][j] += g[j] * yv[j] * sb; }
-                         Vec8<T>::store(dy + (long)r * C + c, o);
+                         Vec8<T>::store(dy + (long)r * lddy + c, o);
                        },
                        outs, smem);
 }
@@ -313,21 +340,32 @@ extern "C" int dfb200_mul_bwd(const void* dout, long ldo, const void* a, long ld
   return dfb_check_launch("mul_bwd");
 }
 
-extern "C" int dfb200_scale_residual_fwd(const float* res, const void* y, int dtype, const float* ls, const float* scale_b, int M, int C,
+extern "C" int dfb200_act_fwd(const void* in, long ldi, void* out, long ldo, int dtype, int act, int M, int N, void* stream) {
+  DFB_REQUIRE(N % 8 == 0 && ldi % 8 == 0 && ldo % 8 == 0 && (act == 1 || act == 2), "act_fwd: bad arguments");
+  DFB_DISPATCH_DTYPE(dtype, T, { act_fwd_kernel<T><<<ew_grid((long)M * N / 8), EW_THREADS, 0, ST>>>((const T*)in, ldi, (T*)out, ldo, act, M, N / 8); });
+  return dfb_check_launch("act_fwd");
+}
+extern "C" int dfb200_act_bwd(const void* dout, long lddo, const void* z, long ldz, void* din, long lddi, int dtype, int act, int M, int N, void* stream) {
+  DFB_REQUIRE(N % 8 == 0 && lddo % 8 == 0 && ldz % 8 == 0 && lddi % 8 == 0 && (act == 1 || act == 2), "act_bwd: bad arguments");
+  DFB_DISPATCH_DTYPE(dtype, T, { act_bwd_kernel<T><<<ew_grid((long)M * N / 8), EW_THREADS, 0, ST>>>((const T*)dout, lddo, (const T*)z, ldz, (T*)din, lddi, act, M, N / 8); });
+  return dfb_check_launch("act_bwd");
+}
+
+extern "C" int dfb200_scale_residual_fwd(const float* res, const void* y, long ldy, int dtype, const float* ls, const float* scale_b, int M, int C,
                                          int rows_per_sample, float* out, void* stream) {
-  DFB_REQUIRE(C % 8 == 0, "scale_residual: C %% 8 != 0");
+  DFB_REQUIRE(C % 8 == 0 && ldy % 8 == 0, "scale_residual: C, ldy %% 8 != 0");
   DFB_DISPATCH_DTYPE(dtype, T, {
-    scale_residual_fwd_kernel<T><<<ew_grid((long)M * C / 8), EW_THREADS, 0, ST>>>(res, (const T*)y, ls, scale_b, M, C / 8, rows_per_sample, out);
+    scale_residual_fwd_kernel<T><<<ew_grid((long)M * C / 8), EW_THREADS, 0, ST>>>(res, (const T*)y, ldy, ls, scale_b, M, C / 8, rows_per_sample, out);
   });
   return dfb_check_launch("scale_residual_fwd");
 }
-extern "C" int dfb200_scale_residual_bwd(const float* dout, const void* y, int dtype, const float* ls, const float* scale_b, int M, int C,
-                                         int rows_per_sample, void* dy, float* dls, void* stream) {
-  DFB_REQUIRE(C % 8 == 0, "scale_residual: C %% 8 != 0");
+extern "C" int dfb200_scale_residual_bwd(const float* dout, const void* y, long ldy, int dtype, const float* ls, const float* scale_b, int M, int C,
+                                         int rows_per_sample, void* dy, long lddy, float* dls, void* stream) {
+  DFB_REQUIRE(C % 8 == 0 && ldy % 8 == 0 && lddy % 8 == 0, "scale_residual: C, ldy, lddy %% 8 != 0");
   const int rpb = pick_rows_per_block(M);
   dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(C / 8, EW_THREADS));
   DFB_DISPATCH_DTYPE(dtype, T, {
-    scale_residual_bwd_kernel<T><<<grid, EW_THREADS, EW_THREADS * 8 * sizeof(float), ST>>>(dout, (const T*)y, ls, scale_b, M, C, rows_per_sample, (T*)dy, dls, rpb);
+    scale_residual_bwd_kernel<T><<<grid, EW_THREADS, EW_THREADS * 8 * sizeof(float), ST>>>(dout, (const T*)y, ldy, ls, scale_b, M, C, rows_per_sample, (T*)dy, lddy, dls, rpb);
   });
   return dfb_check_launch("scale_residual_bwd");
 }

@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
 // LayerNorm backward: warp per row for dx; per-lane partial dgamma/dbeta accumulated over the block's rows.
 template <typename T>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
-                                                     const float* __restrict__ mean, const float* __restrict__ rstd, int M, int C, float* __restrict__ dx,
-                                                     int acc_dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd, int M, int C, const float* dx_in, float* dx,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
   extern __shared__ float sm[];   // [2][C]
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
@@ -76,12 +76,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
     s1 = warp_sum(s1) / C;
     s2 = warp_sum(s2) / C;
     float* dr = dx + (long)row * C;
+    const float* di = dx_in ? dx_in + (long)row * C : nullptr;
 #pragma unroll
     for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
       const int c = lane + i * 32;
       if (c < C) {
         const float v = rs * (g[i] - s1 - xh[i] * s2);
-        dr[c] = acc_dx ? dr[c] + v : v;
+        dr[c] = di ? di[c] + v : v;
       }
     }
   }
@@ -279,12 +280,12 @@ extern "C" int dfb200_layernorm_fwd(const float* x, const float* gamma, const fl
 }
 
 extern "C" int dfb200_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean, const float* rstd, int M, int C,
-                                    float* dx, int accumulate_dx, float* dgamma, float* dbeta, void* stream) {
+                                    const float* dx_in, float* dx, float* dgamma, float* dbeta, void* stream) {
   DFB_REQUIRE(C >= 1 && C <= 32 * LN_MAX_PER_LANE, "layernorm: C=%d out of range", C);
   if (M <= 0) return DFB_OK;
   const int grid = min(dfb_cdiv(M, 8), 148 * 2);
   DFB_DISPATCH_DTYPE(dy_dtype, T, {
-    ln_bwd_kernel<T><<<grid, 256, 2 * C * sizeof(float), ST>>>((const T*)dy, x, gamma, mean, rstd, M, C, dx, accumulate_dx, dgamma, dbeta);
+    ln_bwd_kernel<T><<<grid, 256, 2 * C * sizeof(float), ST>>>((const T*)dy, x, gamma, mean, rstd, M, C, dx_in, dx, dgamma, dbeta);
   });
   return dfb_check_launch("layernorm_bwd");
 }

@@ -113,10 +113,13 @@ def layernorm_fwd(x, gamma, beta, eps, out_dtype):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx, accumulate_dx, dgamma, dbeta):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dgamma, dbeta):
+    """returns dx = (dx_in or 0) + LN-gradient (fresh fp32 tensor); dgamma/dbeta accumulate."""
     M, C = x.shape
+    dx = torch.empty((M, C), device=x.device, dtype=torch.float32)
     lib().layernorm_bwd(dy.data_ptr(), dt(dy), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), M, C,
-                        dx.data_ptr(), int(accumulate_dx), dgamma.data_ptr(), dbeta.data_ptr(), _s())
+                        _p(dx_in), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _s())
+    return dx
 
 
 def dwconv_fwd(x, weight, bias, B, H, W, k, add_input=False, act=ACT_NONE):
@@ -150,15 +153,33 @@ def mul_bwd(dout, a, b, da, db):
 def scale_residual_fwd(res, y, ls, scale_b, rows_per_sample):
     M, C = res.shape
     out = torch.empty_like(res)
-    lib().scale_residual_fwd(res.data_ptr(), y.data_ptr(), dt(y), ls.data_ptr(), _p(scale_b), M, C, rows_per_sample, out.data_ptr(), _s())
+    lib().scale_residual_fwd(res.data_ptr(), y.data_ptr(), y.stride(0), dt(y), ls.data_ptr(), _p(scale_b), M, C, rows_per_sample, out.data_ptr(), _s())
     return out
 
 
-def scale_residual_bwd(dout, y, ls, scale_b, rows_per_sample, dls):
+def scale_residual_bwd(dout, y, ls, scale_b, rows_per_sample, dls, dy=None):
     M, C = dout.shape
-    dy = torch.empty_like(y)
-    lib().scale_residual_bwd(dout.data_ptr(), y.data_ptr(), dt(y), ls.data_ptr(), _p(scale_b), M, C, rows_per_sample, dy.data_ptr(), dls.data_ptr(), _s())
+    if dy is None:
+        dy = torch.empty((M, C), device=y.device, dtype=y.dtype)
+    lib().scale_residual_bwd(dout.data_ptr(), y.data_ptr(), y.stride(0), dt(y), ls.data_ptr(), _p(scale_b), M, C, rows_per_sample,
+                             dy.data_ptr(), dy.stride(0), dls.data_ptr(), _s())
     return dy
+
+
+def act_fwd(x, act, out=None):
+    M, N = x.shape
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=x.dtype)
+    lib().act_fwd(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), dt(x), act, M, N, _s())
+    return out
+
+
+def act_bwd(dout, z, act, out=None):
+    M, N = z.shape
+    if out is None:
+        out = torch.empty((M, N), device=z.device, dtype=z.dtype)
+    lib().act_bwd(dout.data_ptr(), dout.stride(0), z.data_ptr(), z.stride(0), out.data_ptr(), out.stride(0), dt(z), act, M, N, _s())
+    return out
 
 
 def pool7_fwd(xn, en, B, H, W):

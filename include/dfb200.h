@@ -77,10 +77,10 @@ int dfb200_unpack_conv_grad(const float* dWp, int ld, int Cout, int Cin, float* 
 /* ---- LayerNorm over channels (DFormer.py:37-39, eps 1e-6) ---------------------------------------- */
 int dfb200_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int M, int C,
                          void* y, int y_dtype, float* mean, float* rstd, void* stream);
-/* dx is fp32 [M,C]; if accumulate_dx != 0 the LN gradient is added to dx (residual-stream gradient).
+/* dx is fp32 [M,C]; dx = (dx_in ? dx_in : 0) + LN-gradient (dx_in = gradient of the residual branch; may alias dx).
  * dgamma/dbeta are accumulated with atomics and must be zero-initialised by the caller. */
 int dfb200_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean,
-                         const float* rstd, int M, int C, float* dx, int accumulate_dx, float* dgamma, float* dbeta,
+                         const float* rstd, int M, int C, const float* dx_in, float* dx, float* dgamma, float* dbeta,
                          void* stream);
 
 /* ---- depthwise k x k conv, stride 1, 'same' padding, channels-last (DFormer.py:54,62,80-81,115,133)
@@ -103,11 +103,16 @@ int dfb200_mul_bwd(const void* dout, long ldo, const void* a, long lda, const vo
                    void* db, long lddb, int dtype, int M, int N, void* stream);
 /* layer-scale residual (DFormer.py:173-179): out[m,c] = res[m,c] + scale_b[b] * ls[c] * y[m,c]
  * (scale_b = DropPath mask / keep_prob per sample, NULL = 1).  res/out fp32, y in `dtype`. rows_per_sample = H*W. */
-int dfb200_scale_residual_fwd(const float* res, const void* y, int dtype, const float* ls, const float* scale_b,
+int dfb200_scale_residual_fwd(const float* res, const void* y, long ldy, int dtype, const float* ls, const float* scale_b,
                               int M, int C, int rows_per_sample, float* out, void* stream);
 /* dy = dout * ls * scale_b;  dls[c] += sum_m dout*y*scale_b (atomics; zero-init by caller). d(res) = dout (alias). */
-int dfb200_scale_residual_bwd(const float* dout, const void* y, int dtype, const float* ls, const float* scale_b,
-                              int M, int C, int rows_per_sample, void* dy, float* dls, void* stream);
+int dfb200_scale_residual_bwd(const float* dout, const void* y, long ldy, int dtype, const float* ls, const float* scale_b,
+                              int M, int C, int rows_per_sample, void* dy, long lddy, float* dls, void* stream);
+/* stand-alone activation on a column slice: out = act(in);  din = dout * act'(z) (GELU: z = pre-activation;
+ * ReLU: z may be the forward output).  All operands have independent leading dimensions. */
+int dfb200_act_fwd(const void* in, long ldi, void* out, long ldo, int dtype, int act, int M, int N, void* stream);
+int dfb200_act_bwd(const void* dout, long lddo, const void* z, long ldz, void* din, long lddi, int dtype, int act, int M, int N,
+                   void* stream);
 
 /* ---- Global Awareness Attention pieces (DFormer.py:107-108,120-131) ------------------------------
  * pool: AdaptiveAvgPool2d(7,7) of cat[xn (C1 ch), en (C2 ch)] -> out [B,49,C1+C2] (compute dtype). */

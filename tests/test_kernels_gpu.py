@@ -95,9 +95,8 @@ def test_layernorm(dtype, C):
     torch.testing.assert_close(y.float(), ref, **tol(dtype))
     dy = rnd(M, C, dtype=dtype)
     ref.backward(dy.float())
-    dx = torch.ones(M, C, device=DEV)
     dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
-    k.layernorm_bwd(dy, x, g, mean, rstd, dx, True, dg, db)
+    dx = k.layernorm_bwd(dy, x, g, mean, rstd, torch.ones(M, C, device=DEV), dg, db)
     torch.testing.assert_close(dx - 1, xr.grad, rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(dg, gr.grad, rtol=1e-3, atol=2e-2)
     torch.testing.assert_close(db, br.grad, rtol=1e-3, atol=2e-2)
@@ -147,16 +146,25 @@ def test_mul_and_scale_residual(dtype):
     torch.testing.assert_close(db.float(), dout[:, C:].float() * a.float(), **tol(dtype))
     # layer-scale residual with per-sample DropPath scale
     B, hw = 3, 200
-    res, y, ls = rnd(M, C), rnd(M, C, dtype=dtype), rnd(C)
+    res, y, ls = rnd(M, C), rnd(M, 2 * C, dtype=dtype)[:, C:], rnd(C)
     sb = torch.tensor([0.0, 1.25, 1.25], device=DEV)
     out = k.scale_residual_fwd(res, y, ls, sb, hw)
     ref = res + sb.repeat_interleave(hw)[:, None] * ls * y.float()
     torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
     g = rnd(M, C)
     dls = torch.zeros(C, device=DEV)
-    dy = k.scale_residual_bwd(g, y, ls, sb, hw, dls)
+    dybuf = torch.zeros(M, 3 * C, device=DEV, dtype=dtype)
+    dy = k.scale_residual_bwd(g, y, ls, sb, hw, dls, dy=dybuf[:, C:2 * C])
     torch.testing.assert_close(dy.float(), g * ls * sb.repeat_interleave(hw)[:, None], **tol(dtype))
     torch.testing.assert_close(dls, (g * y.float() * sb.repeat_interleave(hw)[:, None]).sum(0), rtol=1e-3, atol=1e-2)
+    # stand-alone activation on column slices
+    z = rnd(M, 3 * C, dtype=dtype)
+    o = k.act_fwd(z[:, C:2 * C], k.ACT_GELU)
+    torch.testing.assert_close(o.float(), F.gelu(z[:, C:2 * C].float()), **tol(dtype))
+    zr = z[:, C:2 * C].float().clone().requires_grad_(True)
+    F.gelu(zr).backward(dout[:, :C].float())
+    dz = k.act_bwd(dout[:, :C], z[:, C:2 * C], k.ACT_GELU)
+    torch.testing.assert_close(dz.float(), zr.grad, **tol(dtype))
 
 
 # ----------------------------------------------------------------------------- pooling / attention / resize
