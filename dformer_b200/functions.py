@@ -1,0 +1,535 @@
+"""autograd.Functions with hand-scheduled forward AND backward for the DFormer hot path.
+
+Granularity follows the reference's modules -- one Function per stem / downsample layer / Block /
+LightHamHead / upsample+CE -- so the autograd graph has ~50 nodes instead of ~3500 ATen ops, fan-in
+gradients are accumulated inside our kernels, and parameter gradients are written straight into the
+flat GradArena.  Everything below is launch orchestration: pointers, shapes and kernel order; all
+arithmetic happens in libdformer_b200.so."""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import kernels as K
+from .runtime import GradArena, backend_for
+
+F32 = torch.float32
+
+
+# ============================================================================================ helpers
+def _lin(x, wb, T, act=K.ACT_NONE, act_col_start=0, out=None, out_dtype=None):
+    w, b = wb
+    return K.gemm(x, w, trans_b=True, bias=b, out=out, out_dtype=out_dtype or T, act=act, act_col_start=act_col_start,
+                  backend=backend_for(T), K=x.shape[1])
+
+
+def _lin_bwd(dy, x, w, dW, db, T, need_dx=True, dx_out=None):
+    """dW[N,K] = dy^T x (fp32, into the arena), db = colsum(dy), returns dx = dy @ W."""
+    be = backend_for(T)
+    K.gemm(dy, x, trans_a=True, trans_b=False, out=dW, backend=be)
+    if db is not None:
+        K.colsum(dy, out=db)
+    if not need_dx:
+        return None
+    return K.gemm(dy, w, trans_a=False, trans_b=False, out=dx_out, out_dtype=T, backend=be, N=w.shape[1])
+
+
+def _views(arena: GradArena, prefix: str, names):
+    return {n: arena.view(prefix + n) for n in names}
+
+
+class BNState:
+    """Plain container describing one BatchNorm layer for the kernels (parameters + buffers + mode)."""
+
+    def __init__(self, mod, prefix, training, sync_group=None):
+        self.weight, self.bias = mod.weight, mod.bias
+        self.running_mean, self.running_var, self.nbt = mod.running_mean, mod.running_var, mod.num_batches_tracked
+        self.eps, self.momentum = mod.eps, (mod.momentum if mod.momentum is not None else 0.1)
+        self.training = training or mod.running_mean is None
+        self.prefix = prefix
+        self.sync_group = sync_group if (training and dist.is_available() and dist.is_initialized() and sync_group is not False) else None
+        self.sync = self.sync_group is not None
+
+
+def _bn_fwd(x2d, bn: BNState, out_dtype, act=K.ACT_NONE, residual=None, chan_scale=None, rows_per_sample=1):
+    M, C = x2d.shape
+    if bn.training:
+        st = K.bn_stats(x2d)                                    # [2, C] fp64: sum, sum of squares
+        count = float(M)
+        if bn.sync:                                             # SyncBatchNorm: one all-reduce of (sum, sumsq); equal shards per rank
+            grp = bn.sync_group if bn.sync_group is not True else None
+            dist.all_reduce(st, group=grp)
+            count = float(M) * dist.get_world_size(grp)
+        ms = K.bn_finalize(st, count, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
+        if bn.nbt is not None:
+            bn.nbt.add_(1)
+    else:
+        ms = K.bn_eval_stats(bn.running_mean, bn.running_var, bn.eps)
+        count = float(M)
+    y = K.bn_apply(x2d, ms, bn.weight, bn.bias, out_dtype, residual=residual, act=act, chan_scale=chan_scale, rows_per_sample=rows_per_sample)
+    return y, ms, count
+
+
+def _bn_bwd(dy, x2d, ms, bn: BNState, count, dx_dtype, dgamma, dbeta, act=K.ACT_NONE, residual=None, chan_scale=None, rows_per_sample=1):
+    """returns (dx, g) with g = gradient w.r.t. the pre-activation (= gradient of the residual branch)."""
+    gbuf, sums = K.bn_bwd_reduce(dy, x2d, ms, bn.weight, bn.bias, residual, act, chan_scale, rows_per_sample)
+    K.axpy(sums[0], 1.0, dbeta)                                 # local parameter gradients (DP averages them later)
+    K.axpy(sums[1], 1.0, dgamma)
+    if bn.sync:
+        dist.all_reduce(sums, group=bn.sync_group if bn.sync_group is not True else None)
+    dx = K.bn_bwd_apply(gbuf, x2d, ms, bn.weight, sums, count, bn.training, dx_dtype)
+    return dx, gbuf
+
+
+# ============================================================================================ stem
+class StemFn(torch.autograd.Function):
+    """DFormer.py:194-211 -- conv3x3 s2 -> BN -> GELU -> conv3x3 s2 -> BN on an NCHW network input.
+    Output: channels-last fp32 residual stream [B*H/4*W/4, C0]."""
+
+    @staticmethod
+    def forward(ctx, inp, st, w1, b1, g1, be1, w2, b2, g2, be2):
+        T = st.dtype
+        B, H, W = inp.shape[0], inp.shape[2], inp.shape[3]
+        cin = st.cin
+        H1, W1, H2, W2 = (H + 1) // 2, (W + 1) // 2, ((H + 1) // 2 + 1) // 2, ((W + 1) // 2 + 1) // 2
+        pk1, pk2 = st.packed[st.g1], st.packed[st.g2]
+        col1 = K.im2col_fwd(inp, (inp.stride(0), inp.stride(2), inp.stride(3), inp.stride(1)), B, H, W, cin, T, pk1[0].shape[1])
+        c1 = _lin(col1, pk1, T)
+        a1, ms1, n1 = _bn_fwd(c1, st.bn1, T, act=K.ACT_GELU)
+        cm = a1.shape[1]
+        col2 = K.im2col_fwd(a1, (H1 * W1 * cm, W1 * cm, cm, 1), B, H1, W1, cm, T, pk2[0].shape[1])
+        c2 = _lin(col2, pk2, T)
+        x0, ms2, n2 = _bn_fwd(c2, st.bn2, F32)
+        ctx.st, ctx.dims = st, (B, H, W, H1, W1, H2, W2, cm)
+        ctx.n = (n1, n2)
+        ctx.save_for_backward(col1, c1, ms1, col2, c2, ms2)
+        return x0
+
+    @staticmethod
+    def backward(ctx, dx0):
+        st = ctx.st
+        T = st.dtype
+        col1, c1, ms1, col2, c2, ms2 = ctx.saved_tensors
+        B, H, W, H1, W1, H2, W2, cm = ctx.dims
+        n1, n2 = ctx.n
+        ar: GradArena = st.arena
+        p = st.prefix
+        dx0 = dx0.contiguous()
+        dc2, _ = _bn_bwd(dx0, c2, ms2, st.bn2, n2, T, ar.view(p + "4.weight"), ar.view(p + "4.bias"))
+        pk1, pk2 = st.packed[st.g1], st.packed[st.g2]
+        dW2p = torch.empty(pk2[0].shape, device=dx0.device, dtype=F32)
+        dcol2 = _lin_bwd(dc2, col2, pk2[0], dW2p, ar.view(p + "3.bias"), T)
+        K.unpack_conv_grad(dW2p, pk2[0].shape[0], cm, ar.view(p + "3.weight"))
+        da1 = K.im2col_bwd(dcol2, B, H1, W1, cm, T)
+        # a1 = GELU(BN1(c1)) is recomputed inside the BN backward (pre-activation from c1)
+        dc1, _ = _bn_bwd(da1, c1, ms1, st.bn1, n1, T, ar.view(p + "1.weight"), ar.view(p + "1.bias"), act=K.ACT_GELU)
+        dW1p = torch.empty(pk1[0].shape, device=dx0.device, dtype=F32)
+        _lin_bwd(dc1, col1, pk1[0], dW1p, ar.view(p + "0.bias"), T, need_dx=False)
+        K.unpack_conv_grad(dW1p, pk1[0].shape[0], st.cin, ar.view(p + "0.weight"))
+        ar.done(st.tag)
+        return (None, None, ar.view(p + "0.weight"), ar.view(p + "0.bias"), ar.view(p + "1.weight"), ar.view(p + "1.bias"),
+                ar.view(p + "3.weight"), ar.view(p + "3.bias"), ar.view(p + "4.weight"), ar.view(p + "4.bias"))
+
+
+# ============================================================================================ downsample
+class DownsampleFn(torch.autograd.Function):
+    """DFormer.py:216-228 -- BN -> conv3x3 s2 on the channels-last fp32 stage output [B*H*W, Cin]."""
+
+    @staticmethod
+    def forward(ctx, x, st, g, be, w, b):
+        T = st.dtype
+        B, H, W = st.B, st.H, st.W
+        cin = x.shape[1]
+        xb, ms, n = _bn_fwd(x, st.bn, T)
+        pk = st.packed[st.g]
+        col = K.im2col_fwd(xb, (H * W * cin, W * cin, cin, 1), B, H, W, cin, T, pk[0].shape[1])
+        y = _lin(col, pk, T, out_dtype=F32)
+        ctx.st, ctx.n = st, n
+        ctx.save_for_backward(x, ms, col)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        st = ctx.st
+        T = st.dtype
+        x, ms, col = ctx.saved_tensors
+        ar: GradArena = st.arena
+        p = st.prefix
+        cin = x.shape[1]
+        dyT = dy.contiguous() if T == F32 else K.cast(dy.contiguous(), T)
+        pk = st.packed[st.g]
+        dWp = torch.empty(pk[0].shape, device=dy.device, dtype=F32)
+        dcol = _lin_bwd(dyT, col, pk[0], dWp, ar.view(p + "1.bias"), T)
+        K.unpack_conv_grad(dWp, pk[0].shape[0], cin, ar.view(p + "1.weight"))
+        dxb = K.im2col_bwd(dcol, st.B, st.H, st.W, cin, T)
+        dx, _ = _bn_bwd(dxb, x, ms, st.bn, ctx.n, F32, ar.view(p + "0.weight"), ar.view(p + "0.bias"))
+        ar.done(st.tag)
+        return dx, None, ar.view(p + "0.weight"), ar.view(p + "0.bias"), ar.view(p + "1.weight"), ar.view(p + "1.bias")
+
+
+# ============================================================================================ Block
+BLOCK_PARAM_ORDER_DOC = "see models/encoders/DFormer.py: Block.param_names()"
+
+
+def _mlp_fwd(x, pfx, st, P, sv, scale_b):
+    """DFormer.py:58-67 + layer-scale residual :176/:179.  x fp32 [M,C] -> fp32 [M,C]."""
+    T = st.dtype
+    B, H, W = st.B, st.H, st.W
+    hn, mu, rs = K.layernorm_fwd(x, P[pfx + "norm.weight"], P[pfx + "norm.bias"], 1e-6, T)
+    h = _lin(hn, st.packed[st.key + pfx + "fc1"], T)
+    u = K.dwconv_fwd(h, P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, add_input=True, act=K.ACT_GELU)
+    f = _lin(u, st.packed[st.key + pfx + "fc2"], T)
+    ls = P["layer_scale_2" if pfx == "mlp." else "layer_scale_2_e"]
+    out = K.scale_residual_fwd(x, f, ls, scale_b, H * W)
+    sv.update({pfx + "x": x, pfx + "mu": mu, pfx + "rs": rs, pfx + "hn": hn, pfx + "h": h, pfx + "u": u, pfx + "f": f})
+    return out
+
+
+def _mlp_bwd(dout, pfx, st, P, sv, scale_b, G):
+    """returns d(input of the MLP residual branch) = dout + LN-path gradient (fp32)."""
+    T = st.dtype
+    B, H, W = st.B, st.H, st.W
+    lsn = "layer_scale_2" if pfx == "mlp." else "layer_scale_2_e"
+    df = K.scale_residual_bwd(dout, sv[pfx + "f"], P[lsn], scale_b, H * W, G[lsn])
+    w2 = st.packed[st.key + pfx + "fc2"][0]
+    du = _lin_bwd(df, sv[pfx + "u"], w2, G[pfx + "fc2.weight"], G[pfx + "fc2.bias"], T)
+    dh = K.dwconv_bwd(du, sv[pfx + "h"], P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, True, K.ACT_GELU,
+                      G[pfx + "pos.weight"], G[pfx + "pos.bias"])
+    w1 = st.packed[st.key + pfx + "fc1"][0]
+    dhn = _lin_bwd(dh, sv[pfx + "hn"], w1, G[pfx + "fc1.weight"], G[pfx + "fc1.bias"], T)
+    return K.layernorm_bwd(dhn, sv[pfx + "x"], P[pfx + "norm.weight"], sv[pfx + "mu"], sv[pfx + "rs"], dout,
+                           G[pfx + "norm.weight"], G[pfx + "norm.bias"])
+
+
+class BlockFn(torch.autograd.Function):
+    """DFormer.py:147-181 (Block) with Attention :102-145 and both MLPs :58-67; x, x_e are the fp32
+    channels-last residual streams [M, C], [M, C/2]."""
+
+    @staticmethod
+    def forward(ctx, x, x_e, st, *params):
+        T = st.dtype
+        P = dict(zip(st.names, params))
+        B, H, W, C = st.B, st.H, st.W, st.C
+        Ce, M, HW = C // 2, x.shape[0], st.H * st.W
+        win, dd = st.window != 0, st.drop_depth
+        pk = lambda n: st.packed[st.key + n]
+        sv = {}
+        # ---- Attention
+        xn, mu1, rs1 = K.layernorm_fwd(x, P["attn.norm.weight"], P["attn.norm.bias"], 1e-6, T)
+        en, mu2, rs2 = K.layernorm_fwd(x_e, P["attn.norm_e.weight"], P["attn.norm_e.bias"], 1e-6, T)
+        qcl = _lin(xn, pk("attn.qcl"), T)                                         # [M, 2.5C] = q | cut | z_l
+        l = K.act_fwd(qcl[:, C + Ce:], K.ACT_GELU)
+        cv = K.dwconv_fwd(l, P["attn.conv.weight"], P["attn.conv.bias"], B, H, W, 7)
+        a = _lin(cv, pk("attn.a"), T)
+        ycols = 2 * C if win else C + Ce
+        y = torch.empty((M, ycols), device=x.device, dtype=T)
+        K.mul_fwd(qcl[:, :C], a, y[:, :C])
+        if win:
+            kv = _lin(l, pk("attn.kv"), T)
+            pooled = K.pool7_fwd(xn, en, B, H, W)
+            m = _lin(pooled, pk("attn.short_cut_linear"), T)
+            o7, probs = K.gaa_fwd(m, kv, B, HW, st.heads, Ce // st.heads)
+            K.resize_fwd(o7, B, 7, 7, y, H, W, col0=C)
+            sv.update(kv=kv, pooled=pooled, m=m, probs=probs)
+        ef = _lin(en, pk("attn.e_fore"), T)
+        ec = K.dwconv_fwd(ef, P["attn.e_conv.weight"], P["attn.e_conv.bias"], B, H, W, 7)
+        e = _lin(ec, pk("attn.e_back"), T)
+        K.mul_fwd(qcl[:, C:C + Ce], e, y[:, ycols - Ce:])
+        pp = _lin(y, pk("attn.pp"), T)                                            # [M, C (+Ce)] = proj | proj_e
+        x1 = K.scale_residual_fwd(x, pp[:, :C], P["layer_scale_1"], st.dp[0], HW)
+        sv.update(x=x, x_e=x_e, mu1=mu1, rs1=rs1, mu2=mu2, rs2=rs2, xn=xn, en=en, qcl=qcl, l=l, cv=cv, a=a, y=y, ef=ef, ec=ec, e=e, pp=pp)
+        # ---- MLPs
+        x2 = _mlp_fwd(x1, "mlp.", st, P, sv, st.dp[1])
+        if not dd:
+            xe1 = K.scale_residual_fwd(x_e, pp[:, C:], P["layer_scale_1_e"], st.dp[2], HW)
+            xe2 = _mlp_fwd(xe1, "mlp_e2.", st, P, sv, st.dp[3])
+        else:
+            xe2 = x_e
+        ctx.st, ctx.sv, ctx.P = st, sv, P
+        return x2, xe2
+
+    @staticmethod
+    def backward(ctx, dx2, dxe2):
+        st, sv = ctx.st, ctx.sv
+        T = st.dtype
+        P = ctx.P
+        ar: GradArena = st.arena
+        G = {n: ar.view(st.prefix + n) for n in st.names}
+        B, H, W, C = st.B, st.H, st.W, st.C
+        Ce, HW = C // 2, st.H * st.W
+        M = sv["x"].shape[0]
+        win, dd = st.window != 0, st.drop_depth
+        pk = lambda n: st.packed[st.key + n]
+        dev = sv["x"].device
+        dx2 = dx2.contiguous()
+        # ---- MLPs (reverse)
+        dx1 = _mlp_bwd(dx2, "mlp.", st, P, sv, st.dp[1], G)
+        ppw = pk("attn.pp")[0]
+        dpp = torch.empty((M, ppw.shape[0]), device=dev, dtype=T)
+        K.scale_residual_bwd(dx1, sv["pp"][:, :C], P["layer_scale_1"], st.dp[0], HW, G["layer_scale_1"], dy=dpp[:, :C])
+        if not dd:
+            dxe2 = dxe2.contiguous() if dxe2 is not None else torch.zeros_like(sv["x_e"])
+            dxe1 = _mlp_bwd(dxe2, "mlp_e2.", st, P, sv, st.dp[3], G)
+            K.scale_residual_bwd(dxe1, sv["pp"][:, C:], P["layer_scale_1_e"], st.dp[2], HW, G["layer_scale_1_e"], dy=dpp[:, C:])
+        else:
+            dxe1 = None
+        # ---- proj | proj_e
+        if dd:
+            dWpp, dbpp = G["attn.proj.weight"], G["attn.proj.bias"]
+        else:
+            dWpp = ar.span(st.prefix + "attn.proj.weight", st.prefix + "attn.proj_e.weight", ppw.shape)
+            dbpp = ar.span(st.prefix + "attn.proj.bias", st.prefix + "attn.proj_e.bias", (ppw.shape[0],))
+        dy = _lin_bwd(dpp, sv["y"], ppw, dWpp, dbpp, T)
+        ycols = dy.shape[1]
+        qcl = sv["qcl"]
+        dqcl = torch.empty_like(qcl)
+        da = torch.empty((M, C), device=dev, dtype=T)
+        K.mul_bwd(dy[:, :C], qcl[:, :C], sv["a"], dqcl[:, :C], da)
+        de = torch.empty((M, Ce), device=dev, dtype=T)
+        K.mul_bwd(dy[:, ycols - Ce:], qcl[:, C:C + Ce], sv["e"], dqcl[:, C:C + Ce], de)
+        # ---- depth gate path: e = e_back(dw7(e_fore(en)))
+        dec = _lin_bwd(de, sv["ec"], pk("attn.e_back")[0], G["attn.e_back.weight"], G["attn.e_back.bias"], T)
+        def_ = K.dwconv_bwd(dec, sv["ef"], P["attn.e_conv.weight"], P["attn.e_conv.bias"], B, H, W, 7, False, K.ACT_NONE,
+                            G["attn.e_conv.weight"], G["attn.e_conv.bias"])
+        den = _lin_bwd(def_, sv["en"], pk("attn.e_fore")[0], G["attn.e_fore.weight"], G["attn.e_fore.bias"], T)
+        # ---- a = a(dw7(l))
+        dcv = _lin_bwd(da, sv["cv"], pk("attn.a")[0], G["attn.a.weight"], G["attn.a.bias"], T)
+        dl = K.dwconv_bwd(dcv, sv["l"], P["attn.conv.weight"], P["attn.conv.bias"], B, H, W, 7, False, K.ACT_NONE,
+                          G["attn.conv.weight"], G["attn.conv.bias"])
+        dxn_pool = None
+        if win:
+            do7 = torch.empty((B * 49, Ce), device=dev, dtype=F32)
+            K.resize_bwd(dy, C, B, 7, 7, Ce, H, W, do7)
+            dm, dkv = K.gaa_bwd(do7, sv["m"], sv["kv"], sv["probs"], B, HW, st.heads, Ce // st.heads)
+            dmT = dm if T == F32 else K.cast(dm, T)
+            dpooled = _lin_bwd(dmT, sv["pooled"], pk("attn.short_cut_linear")[0], G["attn.short_cut_linear.weight"],
+                               G["attn.short_cut_linear.bias"], T)
+            dxn_pool, den_pool = K.pool7_bwd(dpooled, C, Ce, B, H, W)
+            dl_kv = _lin_bwd(dkv, sv["l"], pk("attn.kv")[0], G["attn.kv.weight"], G["attn.kv.bias"], T)
+            K.axpy(dl_kv, 1.0, dl)
+            K.axpy(den_pool, 1.0, den)
+        K.act_bwd(dl, qcl[:, C + Ce:], K.ACT_GELU, out=dqcl[:, C + Ce:])
+        qclw = pk("attn.qcl")[0]
+        dWq = ar.span(st.prefix + "attn.q.weight", st.prefix + "attn.l.weight", qclw.shape)
+        dbq = ar.span(st.prefix + "attn.q.bias", st.prefix + "attn.l.bias", (qclw.shape[0],))
+        dxn = _lin_bwd(dqcl, sv["xn"], qclw, dWq, dbq, T)
+        if dxn_pool is not None:
+            K.axpy(dxn_pool, 1.0, dxn)
+        dx = K.layernorm_bwd(dxn, sv["x"], P["attn.norm.weight"], sv["mu1"], sv["rs1"], dx1, G["attn.norm.weight"], G["attn.norm.bias"])
+        dxe = K.layernorm_bwd(den, sv["x_e"], P["attn.norm_e.weight"], sv["mu2"], sv["rs2"], dxe1, G["attn.norm_e.weight"], G["attn.norm_e.bias"])
+        if dd and dxe2 is not None:
+            K.axpy(dxe2.contiguous(), 1.0, dxe)                                  # x_e passes through the last block unchanged
+        ctx.sv = ctx.P = None
+        ar.done(st.tag)
+        return (dx, dxe, None) + tuple(G[n] for n in st.names)
+
+
+# ============================================================================================ NMF2D
+def _nmf_fwd(x, bases_raw, steps, T):
+    """ham_head.py:60-100,109-145 on channels-last x [B, N, D] (compute dtype); bases_raw [B, D, R] fp32."""
+    B, N, D = x.shape
+    R = bases_raw.shape[2]
+    dev = x.device
+    f = lambda *s: torch.empty(s, device=dev, dtype=F32)
+    bases, _ = K.normalize_cols(bases_raw)
+    S = K.bgemm(x, bases, f(B, N, R), M=N, N=R, K=D)
+    coef = K.softmax_rows(S)
+    tape = []
+
+    def coef_update(coef, bases):
+        num = K.bgemm(x, bases, f(B, N, R), M=N, N=R, K=D)
+        btb = K.bgemm(bases, bases, f(B, R, R), trans_a=True, M=R, N=R, K=D)
+        den = K.bgemm(coef, btb, f(B, N, R), M=N, N=R, K=R)
+        return K.mu_update(coef, num, den), (coef, num, den, bases, btb)
+
+    for _ in range(steps):
+        coef_n, rec_c = coef_update(coef, bases)
+        num2 = K.bgemm(x, coef_n, f(B, D, R), trans_a=True, M=D, N=R, K=N, splitk=max(1, N // 512))
+        ctc = K.bgemm(coef_n, coef_n, f(B, R, R), trans_a=True, M=R, N=R, K=N, splitk=max(1, N // 512))
+        den2 = K.bgemm(bases, ctc, f(B, D, R), M=D, N=R, K=R)
+        bases_n = K.mu_update(bases, num2, den2)
+        tape.append((rec_c, (bases, num2, den2, coef_n, ctc)))
+        coef, bases = coef_n, bases_n
+    coef_f, rec_f = coef_update(coef, bases)
+    out = torch.empty((B, N, D), device=dev, dtype=T)
+    K.bgemm(coef_f, bases, out, trans_b=True, M=N, N=D, K=R)
+    return out, (tape, rec_f, coef_f, bases, coef, S)
+
+
+def _nmf_bwd(dout, x, saved):
+    """Back-propagation through every multiplicative update (the reference does not detach them, ham_head.py:45,119)."""
+    tape, rec_f, coef_f, bases_T, _, S = saved
+    B, N, D = x.shape
+    R = coef_f.shape[2]
+    dev = x.device
+    f = lambda *s: torch.empty(s, device=dev, dtype=F32)
+    dx = torch.zeros((B, N, D), device=dev, dtype=F32)
+    sk = max(1, N // 512)
+    # out = coef_f @ bases^T
+    dcoef = K.bgemm(dout, bases_T, f(B, N, R), M=N, N=R, K=D)
+    dbases = K.bgemm(dout, coef_f, f(B, D, R), trans_a=True, M=D, N=R, K=N, splitk=sk)
+
+    def coef_update_bwd(dcoef_new, rec, dbases):
+        coef, num, den, bases, btb = rec
+        dco = f(B, N, R)
+        dnum, dden = K.mu_update_bwd(dcoef_new, coef, num, den, dco, False)
+        K.bgemm(dnum, bases, dx, trans_b=True, M=N, N=D, K=R, accumulate=True)           # num = x @ bases
+        K.bgemm(x, dnum, dbases, trans_a=True, M=D, N=R, K=N, accumulate=True, splitk=sk)
+        K.bgemm(dden, btb, dco, M=N, N=R, K=R, accumulate=True)                          # den = coef @ BtB (BtB symmetric)
+        dbtb = K.bgemm(coef, dden, f(B, R, R), trans_a=True, M=R, N=R, K=N, splitk=sk)
+        K.bgemm(bases, dbtb, dbases, M=D, N=R, K=R, accumulate=True)                     # BtB = bases^T bases
+        K.bgemm(bases, dbtb, dbases, trans_b=True, M=D, N=R, K=R, accumulate=True)
+        return dco
+
+    def bases_update_bwd(dbases_new, rec, dcoef):
+        bases, num2, den2, coef, ctc = rec
+        dba = f(B, D, R)
+        dnum2, dden2 = K.mu_update_bwd(dbases_new, bases, num2, den2, dba, False)
+        K.bgemm(coef, dnum2, dx, trans_b=True, M=N, N=D, K=R, accumulate=True)           # num2 = x^T @ coef
+        K.bgemm(x, dnum2, dcoef, M=N, N=R, K=D, accumulate=True)
+        K.bgemm(dden2, ctc, dba, M=D, N=R, K=R, accumulate=True)                         # den2 = bases @ CtC
+        dctc = K.bgemm(bases, dden2, f(B, R, R), trans_a=True, M=R, N=R, K=D)
+        K.bgemm(coef, dctc, dcoef, M=N, N=R, K=R, accumulate=True)                       # CtC = coef^T coef
+        K.bgemm(coef, dctc, dcoef, trans_b=True, M=N, N=R, K=R, accumulate=True)
+        return dba
+
+    dcoef = coef_update_bwd(dcoef, rec_f, dbases)
+    for rec_c, rec_b in reversed(tape):
+        dbases = bases_update_bwd(dbases, rec_b, dcoef)
+        dcoef = coef_update_bwd(dcoef, rec_c, dbases)
+    # coef0 = softmax(x @ bases0)
+    coef0, bases0 = (tape[0][0][0], tape[0][0][3]) if tape else (rec_f[0], rec_f[3])
+    dS = K.softmax_rows_bwd(dcoef, coef0)
+    K.bgemm(dS, bases0, dx, trans_b=True, M=N, N=D, K=R, accumulate=True)
+    return dx
+
+
+# ============================================================================================ LightHamHead
+class HeadFn(torch.autograd.Function):
+    """ham_head.py:222-240 (LightHamHead.forward), :173-180 (Hamburger), decode_head.py:226-231 (cls_seg).
+    Inputs: the three channels-last fp32 stage outputs; output: channels-last logits [B*h*w, ncls]."""
+
+    @staticmethod
+    def forward(ctx, o1, o2, o3, bases_raw, st, *params):
+        T = st.dtype
+        P = dict(zip(st.names, params))
+        B = st.B
+        (h1, w1), (h2, w2), (h3, w3) = st.sizes
+        C1, C2, C3 = o1.shape[1], o2.shape[1], o3.shape[1]
+        M = o1.shape[0]
+        pk = lambda n: st.packed[n]
+        cat = torch.empty((M, C1 + C2 + C3), device=o1.device, dtype=T)
+        K.resize_fwd(o1, B, h1, w1, cat, h1, w1, col0=0)
+        K.resize_fwd(o2, B, h2, w2, cat, h1, w1, col0=C1)
+        K.resize_fwd(o3, B, h3, w3, cat, h1, w1, col0=C1 + C2)
+        s_pre = _lin(cat, pk("squeeze"), T)
+        s, ms_s, n_s = _bn_fwd(s_pre, st.bn_sq, T, act=K.ACT_RELU)
+        hin = _lin(s, pk("ham_in"), T, act=K.ACT_RELU)
+        D = hin.shape[1]
+        nmf, nmf_saved = _nmf_fwd(hin.view(B, h1 * w1, D), bases_raw, st.steps, T)
+        nmf2d = nmf.view(M, D)
+        ho_pre = _lin(nmf2d, pk("ham_out"), T)
+        hs, ms_o, n_o = _bn_fwd(ho_pre, st.bn_out, T, act=K.ACT_RELU, residual=s)
+        al_pre = _lin(hs, pk("align"), T)
+        al, ms_a, n_a = _bn_fwd(al_pre, st.bn_al, T, act=K.ACT_RELU, chan_scale=st.drop_mask, rows_per_sample=h1 * w1)
+        logits = _lin(al, pk("conv_seg"), T)
+        ctx.st = st
+        ctx.sv = dict(cat=cat, s_pre=s_pre, ms_s=ms_s, n_s=n_s, s=s, hin=hin, nmf_saved=nmf_saved, nmf=nmf2d, ho_pre=ho_pre, ms_o=ms_o,
+                      n_o=n_o, hs=hs, al_pre=al_pre, ms_a=ms_a, n_a=n_a, al=al, shapes=(C1, C2, C3, M, D))
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        st, sv = ctx.st, ctx.sv
+        T = st.dtype
+        ar: GradArena = st.arena
+        G = {n: ar.view(st.prefix + n) for n in st.names}
+        B = st.B
+        (h1, w1), (h2, w2), (h3, w3) = st.sizes
+        C1, C2, C3, M, D = sv["shapes"]
+        pk = lambda n: st.packed[n]
+        dev = dlogits.device
+        dlogits = dlogits.contiguous()
+        if dlogits.dtype != T:
+            dlogits = K.cast(dlogits, T)
+        dal = _lin_bwd(dlogits, sv["al"], pk("conv_seg")[0], G["conv_seg.weight"].view(pk("conv_seg")[0].shape), G["conv_seg.bias"], T)
+        dal_pre, _ = _bn_bwd(dal, sv["al_pre"], sv["ms_a"], st.bn_al, sv["n_a"], T, G["align.bn.weight"], G["align.bn.bias"], act=K.ACT_RELU,
+                             chan_scale=st.drop_mask, rows_per_sample=h1 * w1)
+        dhs = _lin_bwd(dal_pre, sv["hs"], pk("align")[0], G["align.conv.weight"].view(pk("align")[0].shape), None, T)
+        # hs = ReLU(s + BN(ho_pre)): g = gradient of the pre-activation = gradient of the residual s
+        dho_pre, ds_res = _bn_bwd(dhs, sv["ho_pre"], sv["ms_o"], st.bn_out, sv["n_o"], T, G["hamburger.ham_out.bn.weight"],
+                                  G["hamburger.ham_out.bn.bias"], act=K.ACT_RELU, residual=sv["s"])
+        dnmf = _lin_bwd(dho_pre, sv["nmf"], pk("ham_out")[0], G["hamburger.ham_out.conv.weight"].view(pk("ham_out")[0].shape), None, T)
+        hin = sv["hin"]
+        dhin32 = _nmf_bwd(dnmf.view(B, h1 * w1, D), hin.view(B, h1 * w1, D), sv["nmf_saved"]).view(M, D)
+        dhin = dhin32 if T == F32 else K.cast(dhin32, T)
+        dhin_pre = K.act_bwd(dhin, hin, K.ACT_RELU)
+        ds = _lin_bwd(dhin_pre, sv["s"], pk("ham_in")[0], G["hamburger.ham_in.conv.weight"].view(pk("ham_in")[0].shape),
+                      G["hamburger.ham_in.conv.bias"], T)
+        K.axpy(ds_res, 1.0, ds)
+        ds_pre, _ = _bn_bwd(ds, sv["s_pre"], sv["ms_s"], st.bn_sq, sv["n_s"], T, G["squeeze.bn.weight"], G["squeeze.bn.bias"], act=K.ACT_RELU)
+        dcat = _lin_bwd(ds_pre, sv["cat"], pk("squeeze")[0], G["squeeze.conv.weight"].view(pk("squeeze")[0].shape), None, T)
+        do1 = torch.empty((M, C1), device=dev, dtype=F32)
+        do2 = torch.empty((B * h2 * w2, C2), device=dev, dtype=F32)
+        do3 = torch.empty((B * h3 * w3, C3), device=dev, dtype=F32)
+        K.resize_bwd(dcat, 0, B, h1, w1, C1, h1, w1, do1)
+        K.resize_bwd(dcat, C1, B, h2, w2, C2, h1, w1, do2)
+        K.resize_bwd(dcat, C1 + C2, B, h3, w3, C3, h1, w1, do3)
+        ctx.sv = None
+        ar.done(st.tag)
+        return (do1, do2, do3, None, None) + tuple(G[n] for n in st.names)
+
+
+# ============================================================================================ upsample + CE
+class UpsampleCEFn(torch.autograd.Function):
+    """builder.py:203 (F.interpolate x8, bilinear, align_corners=False) + :230 (masked-mean CE).
+    Returns (loss, out_nchw); only the loss is differentiable."""
+
+    @staticmethod
+    def forward(ctx, small, label, meta):
+        B, h, w, ncls, H, W, ignore, want_out = meta
+        out, lse, acc, loss = K.upsample_ce_fwd(small, B, h, w, ncls, H, W, label, ignore, want_out=want_out, want_loss=label is not None)
+        ctx.meta = meta
+        if label is not None:
+            ctx.save_for_backward(small, label, lse, acc)
+        if out is None:
+            out = torch.empty(0, device=small.device)
+        if loss is None:
+            loss = torch.zeros((), device=small.device)
+        ctx.mark_non_differentiable(out)
+        return loss, out
+
+    @staticmethod
+    def backward(ctx, dloss, _dout):
+        B, h, w, ncls, H, W, ignore, _ = ctx.meta
+        small, label, lse, acc = ctx.saved_tensors
+        dl = dloss.contiguous().float()
+        ds = K.upsample_ce_bwd(small, B, h, w, ncls, H, W, label, ignore, lse, acc, dl)
+        return ds, None, None
+
+
+class UpsampleFn(torch.autograd.Function):
+    """Differentiable x8 upsample alone (eval / `decode` API): out NCHW fp32 from channels-last logits."""
+
+    @staticmethod
+    def forward(ctx, small, meta):
+        B, h, w, ncls, H, W = meta
+        out, _, _, _ = K.upsample_ce_fwd(small, B, h, w, ncls, H, W, None, 255, want_out=True, want_loss=False)
+        ctx.meta, ctx.dtype = meta, small.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, h, w, ncls, H, W = ctx.meta
+        # adjoint of the bilinear resize on an NCHW gradient: go through channels-last (layout plumbing only)
+        g = dout.permute(0, 2, 3, 1).contiguous().view(B * H * W, ncls)
+        pad = (8 - ncls % 8) % 8
+        if pad:
+            g = torch.nn.functional.pad(g, (0, pad))
+        din = torch.empty((B * h * w, ncls + pad), device=dout.device, dtype=F32)
+        K.resize_bwd(g, 0, B, h, w, ncls + pad, H, W, din)
+        din = din[:, :ncls].contiguous()
+        return (din if ctx.dtype == F32 else K.cast(din, ctx.dtype)), None

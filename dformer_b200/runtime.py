@@ -1,0 +1,189 @@
+"""Host-side runtime shared by the model mirrors: precision selection, parameter packing into
+compute-dtype GEMM operands (one launch per module forward) and the flat gradient arena that the
+backward kernels write into (and that the data-parallel engine all-reduces bucket by bucket)."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import kernels as K
+
+_PRECISION_DEFAULT = "fp32"
+
+
+def resolve_dtype(module_precision: Optional[str]) -> torch.dtype:
+    """bf16 when the module asks for it or when the caller runs under torch.autocast(bf16)
+    (the reference's AMP switch, utils/train.py:322); fp32 otherwise."""
+    if torch.is_autocast_enabled():
+        ad = torch.get_autocast_gpu_dtype()
+        if ad == torch.bfloat16:
+            return torch.bfloat16
+        raise RuntimeError("dformer_b200 supports fp32 and bf16 compute (autocast dtype %s requested)" % ad)
+    p = module_precision or _PRECISION_DEFAULT
+    if p in ("bf16", torch.bfloat16):
+        return torch.bfloat16
+    if p in ("fp32", torch.float32):
+        return torch.float32
+    raise ValueError(p)
+
+
+def backend_for(dtype: torch.dtype) -> int:
+    # bf16 -> tcgen05 whenever the shape qualifies; fp32 -> exact CUDA-core GEMM
+    return K.AUTO if dtype == torch.bfloat16 else K.SIMT
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("dformer_b200 runs on sm_100a CUDA devices only: got a %s tensor. "
+                               "There is no CPU fallback (use the oracle in oracle/ for CPU checks)." % t.device)
+
+
+# --------------------------------------------------------------------------------------------- layout
+@dataclass
+class Slot:
+    name: str
+    param: nn.Parameter
+    offset: int
+    numel: int
+
+
+class ParamLayout:
+    """Order + offsets of a module's parameters inside the flat fp32 gradient arena.  Members of a fused
+    GEMM group are adjacent (their concatenated weight gradient is ONE contiguous [sum N, K] matrix)."""
+
+    def __init__(self):
+        self.slots: Dict[str, Slot] = {}
+        self.order: List[str] = []
+        self.total = 0
+        self.marks: Dict[str, Tuple[int, int]] = {}     # named contiguous ranges (e.g. one Block) for DP buckets
+
+    def add(self, name: str, p: nn.Parameter):
+        off = (self.total + 7) // 8 * 8
+        self.slots[name] = Slot(name, p, off, p.numel())
+        self.order.append(name)
+        self.total = off + p.numel()
+
+    def begin_mark(self, tag: str):
+        self.marks[tag] = ((self.total + 7) // 8 * 8, -1)
+
+    def end_mark(self, tag: str):
+        self.marks[tag] = (self.marks[tag][0], self.total)
+
+
+class GradArena:
+    """One zero-initialised flat fp32 buffer per backward pass; kernels write parameter gradients straight
+    into views of it.  `on_range_done(lo, hi)` lets the DP engine launch a bucket all-reduce as soon as the
+    gradients of a contiguous range are final (reverse execution order)."""
+
+    def __init__(self, layout: ParamLayout, device, on_range_done: Optional[Callable] = None):
+        self.layout = layout
+        self.device = device
+        self.buf: Optional[torch.Tensor] = None
+        self.on_range_done = on_range_done
+
+    def flat(self) -> torch.Tensor:
+        if self.buf is None:
+            self.buf = torch.zeros(self.layout.total, device=self.device, dtype=torch.float32)
+        return self.buf
+
+    def view(self, name: str) -> torch.Tensor:
+        s = self.layout.slots[name]
+        return self.flat()[s.offset:s.offset + s.numel].view(s.param.shape)
+
+    def span(self, first: str, last: str, shape) -> torch.Tensor:
+        a, b = self.layout.slots[first], self.layout.slots[last]
+        return self.flat()[a.offset:b.offset + b.numel].view(shape)
+
+    def done(self, tag: str):
+        if self.on_range_done is not None:
+            lo, hi = self.layout.marks[tag]
+            self.on_range_done(self, lo, hi)
+
+
+# --------------------------------------------------------------------------------------------- packing
+@dataclass
+class GemmGroup:
+    """Row-concatenation of nn.Linear / conv weights that feed ONE GEMM (e.g. q|q_cut|l)."""
+    name: str
+    weights: List[str]                  # parameter names in concat order
+    biases: List[Optional[str]]
+    kind: int = 0                       # 0 linear / 1x1 conv, 1 dense 3x3 conv (im2col order)
+    n_rows: int = 0
+    k: int = 0                          # logical K
+    ld: int = 0                         # padded K (multiple of 8)
+    w_off: int = 0
+    b_off: int = -1
+
+
+class ParamPacker:
+    """Compute-dtype copies of every GEMM weight of a module, refreshed by a single pack_params launch
+    (table cached per (device, dtype)); fp32 concatenated biases by a second launch."""
+
+    def __init__(self, named_params: Dict[str, nn.Parameter]):
+        self.params = named_params
+        self.groups: Dict[str, GemmGroup] = {}
+        self.w_total = 0
+        self.b_total = 0
+        self._cache = {}
+
+    def add(self, name: str, weights: Sequence[str], biases: Sequence[Optional[str]], kind: int = 0) -> GemmGroup:
+        g = GemmGroup(name, list(weights), list(biases), kind)
+        rows = 0
+        for w in weights:
+            p = self.params[w]
+            rows += p.shape[0]
+            k = p.shape[1] * (9 if kind == 1 else 1)
+            assert g.k in (0, k)
+            g.k = k
+        g.n_rows = rows
+        g.ld = (g.k + 7) // 8 * 8
+        g.w_off = (self.w_total + 63) // 64 * 64
+        self.w_total = g.w_off + rows * g.ld
+        if any(b is not None for b in biases):
+            assert all(b is not None for b in biases)
+            g.b_off = (self.b_total + 7) // 8 * 8
+            self.b_total = g.b_off + rows
+        self.groups[name] = g
+        return g
+
+    def _build(self, device, dtype):
+        wbuf = torch.zeros(max(self.w_total, 1), device=device, dtype=dtype)       # zero padding columns stay zero
+        bbuf = torch.zeros(max(self.b_total, 1), device=device, dtype=torch.float32)
+        w_entries, b_entries = [], []
+        views = {}
+        for g in self.groups.values():
+            wv = wbuf[g.w_off:g.w_off + g.n_rows * g.ld].view(g.n_rows, g.ld)
+            bv = bbuf[g.b_off:g.b_off + g.n_rows] if g.b_off >= 0 else None
+            views[g.name] = (wv, bv)
+            r = 0
+            for wn, bn in zip(g.weights, g.biases):
+                p = self.params[wn]
+                n = p.shape[0]
+                if g.kind == 0:
+                    w_entries.append((p, wv[r:], n, g.k, g.ld, 0))
+                else:
+                    w_entries.append((p, wv[r:], n, p.shape[1], g.ld, 1))
+                if bn is not None:
+                    b_entries.append((self.params[bn], bv[r:], 1, n, n, 0))
+                r += n
+        wt = K.build_pack_table(w_entries, device)
+        bt = K.build_pack_table(b_entries, device) if b_entries else None
+        ptrs = tuple(p.data_ptr() for p in self.params.values())
+        return dict(wbuf=wbuf, bbuf=bbuf, views=views, wt=wt, bt=bt, ptrs=ptrs)
+
+    def pack(self, device, dtype) -> Dict[str, Tuple[torch.Tensor, Optional[torch.Tensor]]]:
+        key = (str(device), dtype)
+        c = self._cache.get(key)
+        if c is not None and c["ptrs"] != tuple(p.data_ptr() for p in self.params.values()):
+            c = None                                   # parameters were re-allocated (.to(), load with assign, ...)
+        if c is None:
+            c = self._build(device, dtype)
+            self._cache = {key: c}
+        K.pack_params(*c["wt"], K._DT[dtype])
+        if c["bt"] is not None:
+            K.pack_params(*c["bt"], K.F32)
+        return c["views"]

