@@ -72,7 +72,7 @@ SIGNATURES = {
     "dfb200_upsample_ce_fwd": [P, I, I, I, I, I, I, I, P, I, P, P, P, P],
     "dfb200_ce_finalize": [P, P, P],
     "dfb200_upsample_ce_bwd": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, I, P],
-    "dfb200_adamw": [P, P, P, P, L, F, F, F, F, F, F, F, F, P],
+    "dfb200_adamw": [P, P, P, P, L, F, F, F, F, F, F, F, F, P, P, P],
 }
 
 
@@ -85,6 +85,7 @@ class _Lib:
         self.cdll = ctypes.CDLL(LIB_PATH)
         self.cdll.dfb200_last_error.restype = ctypes.c_char_p
         self.cdll.dfb200_version.restype = c_int
+        self.cdll.dfb200_launch_count.restype = c_long
         for name, args in SIGNATURES.items():
             fn = getattr(self.cdll, name)
             fn.argtypes = args
@@ -103,6 +104,9 @@ class _Lib:
 
     def version(self):
         return self.cdll.dfb200_version()
+
+    def launch_count(self):
+        return self.cdll.dfb200_launch_count()
 
 
 _lib = None

@@ -14,7 +14,11 @@ void dfb_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static long g_launches = 0;
+extern "C" long dfb200_launch_count(void) { return g_launches; }
+
 int dfb_check_launch(const char* what) {
+  ++g_launches;
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     cudaGetLastError();

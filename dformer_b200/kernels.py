@@ -33,6 +33,9 @@ def _chk(t, name="tensor"):
     return t
 
 
+GEMM_PROFILE = None      # bench.py sets this to a list to time every GEMM launch with CUDA events
+
+
 def gemm(a, b, *, trans_a=False, trans_b=True, bias=None, out=None, out_dtype=None, act=ACT_NONE, act_col_start=0,
          accumulate=False, backend=AUTO, splitk=0, alpha=0.0, M=None, N=None, K=None):
     """out[M,N] = act(alpha * op(a) @ op(b) + bias).  a/b are 2-D with unit inner stride (row slices allowed)."""
@@ -56,6 +59,15 @@ def gemm(a, b, *, trans_a=False, trans_b=True, bias=None, out=None, out_dtype=No
     g.transA, g.transB = int(trans_a), int(trans_b)
     g.a_dtype, g.b_dtype, g.out_dtype = dt(a), dt(b), dt(out)
     g.act, g.act_col_start, g.accumulate, g.backend, g.splitk, g.alpha = act, act_col_start, int(accumulate), backend, splitk, alpha
+    if GEMM_PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lib().gemm(ctypes.byref(g), _s())
+        e1.record()
+        tc = backend != SIMT and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+        GEMM_PROFILE.append((e0, e1, 2.0 * M * N * K, a.element_size() * M * K + b.element_size() * N * K + out.element_size() * M * N, tc,
+                             (M, N, K, int(trans_a), int(trans_b))))
+        return out
     lib().gemm(ctypes.byref(g), _s())
     return out
 
@@ -349,7 +361,8 @@ def upsample_ce_bwd(small, B, h, w, ncls, H, W, label, ignore, lse, acc, dloss):
     return dsmall
 
 
-def adamw(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0):
+def adamw(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0, wd_arr=None, lr_arr=None):
     c1 = 1.0 - beta1 ** step
     c2 = 1.0 - beta2 ** step
-    lib().adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps, wd, c1, c2, grad_scale, _s())
+    lib().adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps, wd, c1, c2, grad_scale,
+                _p(wd_arr), _p(lr_arr), _s())

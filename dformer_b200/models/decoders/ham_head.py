@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 from ... import functions as Fn
-from ...runtime import GradArena, ParamLayout, ParamPacker, require_cuda, resolve_dtype
+from ...runtime import GradArena, ParamLayout, ParamPacker, flatten_parameters, is_flat, require_cuda, resolve_dtype
 from .decode_head import BaseDecodeHead
 
 
@@ -86,6 +86,7 @@ class LightHamHead(BaseDecodeHead):
         assert self.hamburger.ham.D == ham_channels, "NMF2D runs with S=1, D=ham_channels"
         self.sync_bn = dict(self.norm_cfg or {}).get("type") == "SyncBN"
         self._plan = None
+        self._last_arena = None
         self.grad_hook = None
         self.injected_bases = None       # tests / reproducibility: raw uniform bases (B, D, R) used instead of a fresh draw
 
@@ -105,8 +106,15 @@ class LightHamHead(BaseDecodeHead):
         packer.add("ham_out", ["hamburger.ham_out.conv.weight"], [None])
         packer.add("align", ["align.conv.weight"], [None])
         packer.add("conv_seg", ["conv_seg.weight"], ["conv_seg.bias"])
-        self._plan = SimpleNamespace(layout=layout, packer=packer, named=named)
+        self._plan = SimpleNamespace(layout=layout, packer=packer, named=named, flat=None)
         return self._plan
+
+    def flat_parameters(self):
+        """Flat fp32 buffer holding every hot-path parameter (arena layout); created on first use on the GPU."""
+        plan = self._plan or self._build_plan()
+        if not is_flat(plan.layout, plan.flat):
+            plan.flat = flatten_parameters(self, plan.layout)
+        return plan.flat
 
     def _apply(self, fn, *a, **k):
         self._plan = None
@@ -124,6 +132,7 @@ class LightHamHead(BaseDecodeHead):
         dev = flat[0].device
         packed = plan.packer.pack(dev, T)
         arena = GradArena(plan.layout, dev, self.grad_hook)
+        self._last_arena = arena
         training = self.training
         ham = self.hamburger.ham
         bases = self.injected_bases if self.injected_bases is not None else ham.draw_bases(B, ham.D, dev)

@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from ... import functions as Fn
-from ...runtime import GradArena, ParamLayout, ParamPacker, require_cuda, resolve_dtype
+from ...runtime import GradArena, ParamLayout, ParamPacker, flatten_parameters, is_flat, require_cuda, resolve_dtype
 
 
 def _norm_layer(norm_cfg, channels):
@@ -176,6 +176,7 @@ class DFormer(nn.Module):
                       mlp_ratio=mlp_ratios[i], drop_depth=((i == 3) and (j == depths[i] - 1))) for j in range(depths[i])]))
             cur += depths[i]
         self._plan = None
+        self._last_arena = None
         self.grad_hook = None           # set by the data-parallel engine: callable(arena, lo, hi)
 
     # ------------------------------------------------------------------ plan: arena layout + GEMM packing
@@ -207,8 +208,15 @@ class DFormer(nn.Module):
                 layout.end_mark(p)
                 for gname, members in blk.gemm_groups():
                     packer.add(p + gname, [p + m + ".weight" for m in members], [p + m + ".bias" for m in members])
-        self._plan = SimpleNamespace(layout=layout, packer=packer, named=named)
+        self._plan = SimpleNamespace(layout=layout, packer=packer, named=named, flat=None)
         return self._plan
+
+    def flat_parameters(self):
+        """Flat fp32 buffer holding every hot-path parameter (arena layout); created on first use on the GPU."""
+        plan = self._plan or self._build_plan()
+        if not is_flat(plan.layout, plan.flat):
+            plan.flat = flatten_parameters(self, plan.layout)
+        return plan.flat
 
     def _apply(self, fn, *a, **k):
         self._plan = None               # parameters may be re-allocated (.cuda(), .to(), ...)
@@ -243,6 +251,7 @@ class DFormer(nn.Module):
         dev = x.device
         packed = plan.packer.pack(dev, T)
         arena = GradArena(plan.layout, dev, self.grad_hook)
+        self._last_arena = arena
         named = plan.named
         B, H, W = x.shape[0], x.shape[2], x.shape[3]
         training = self.training

@@ -187,3 +187,28 @@ class ParamPacker:
         if c["bt"] is not None:
             K.pack_params(*c["bt"], K.F32)
         return c["views"]
+
+
+# --------------------------------------------------------------------------------------------- flat parameters
+def flatten_parameters(module, layout: ParamLayout):
+    """Re-home every parameter of `layout` into ONE flat fp32 device buffer laid out exactly like the gradient
+    arena (parameter i and its gradient share offsets), so the optimizer is a single fused launch over
+    (params, grads, m, v) and DP buckets are plain slices.  Values are preserved; state_dict keys/shapes are
+    untouched because each nn.Parameter keeps its identity and simply views into the buffer."""
+    dev = next(iter(layout.slots.values())).param.device
+    flat = torch.zeros(layout.total, device=dev, dtype=torch.float32)
+    with torch.no_grad():
+        for s in layout.slots.values():
+            v = flat[s.offset:s.offset + s.numel].view(s.param.shape)
+            v.copy_(s.param.data)
+            s.param.data = v
+    return flat
+
+
+def is_flat(layout: ParamLayout, flat: Optional[torch.Tensor]) -> bool:
+    if flat is None:
+        return False
+    first = layout.slots[layout.order[0]]
+    last = layout.slots[layout.order[-1]]
+    base = flat.data_ptr()
+    return (first.param.data_ptr() == base + 4 * first.offset) and (last.param.data_ptr() == base + 4 * last.offset)

@@ -194,8 +194,13 @@ int dfb200_upsample_ce_bwd(const void* logits_small, int dtype, int B, int h, in
                            void* dlogits_small, int dl_dtype, void* stream);
 
 /* ---- fused multi-tensor AdamW on flat fp32 buffers (utils/train.py:211,336; next-row N1) ------------ */
+/* per-element `wd_arr` (weight decay, NULL = weight_decay everywhere) and `lr_arr` (lr multiplier, 0 freezes an
+ * element; NULL = 1) reproduce the reference's parameter groups (utils/init_func.py:26-70) on one flat buffer. */
 int dfb200_adamw(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps,
-                 float weight_decay, float bias_c1, float bias_c2, float grad_scale, void* stream);
+                 float weight_decay, float bias_c1, float bias_c2, float grad_scale, const float* wd_arr,
+                 const float* lr_arr, void* stream);
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches evidence) */
+long dfb200_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -136,8 +136,8 @@ def bilinear_resize_nchw(x: Tensor, size: Sequence[int]) -> Tensor:
     Ho, Wo = int(size[0]), int(size[1])
     if (H, W) == (Ho, Wo):
         return x
-    y0, y1, wy = _bilinear_axis(H, Ho)
-    x0, x1, wx = _bilinear_axis(W, Wo)
+    y0, y1, wy = (t.to(x.device) for t in _bilinear_axis(H, Ho))
+    x0, x1, wx = (t.to(x.device) for t in _bilinear_axis(W, Wo))
     wy = wy.to(x.dtype)[:, None]
     wx = wx.to(x.dtype)[None, :]
     top = x[..., y0, :]
