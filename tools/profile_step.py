@@ -54,9 +54,7 @@ def main():
     for ev in prof.events():
         if ev.device_type == torch.autograd.DeviceType.CUDA:
             name = ev.name
-            for pre in ("void (anonymous namespace)::", "void "):
-                if name.startswith(pre):
-                    name = name[len(pre):]
+            name = name.replace("(anonymous namespace)::", "").replace("void ", "")
             name = name.split("(")[0][:90]
             agg[name][0] += ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
             agg[name][1] += 1
