@@ -6,7 +6,8 @@
 //   warp 0      TMA producer  : cp.async.bulk.tensor tiles (128B swizzle) into a 4-stage smem ring
 //   warp 1      MMA issuer    : one thread issues tcgen05.mma (UMMA 128 x BN x 16), accumulators in TMEM,
 //                               double-buffered (2 x 256 columns) so the epilogue of tile i overlaps tile i+1
-//   warps 2..5  epilogue      : tcgen05.ld (32 lanes x 32 columns per warp) -> bias / activation -> global
+//   warps 2..9  epilogue      : tcgen05.ld (32 lanes x 32 columns per warp) -> bias / activation -> global
+//                               (two warps per TMEM lane quadrant, each owning half of the tile's columns)
 //
 // Both operands may be K-major (reduction dim contiguous) or MN-major (reduction dim strided), which is
 // what lets one kernel serve forward (A K-major, W K-major), dgrad (dY K-major, W MN-major) and wgrad
@@ -29,7 +30,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16 KB
 constexpr int B_STAGE_BYTES = 256 * BK * 2;       // 32 KB (BN <= 256)
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int TMEM_COLS = 512;   // 2 accumulator stages x 256 fp32 columns
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;         // TMA warp + MMA warp + 8 epilogue warps
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct TcParams {
@@ -138,7 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -217,8 +218,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // =============================== epilogue (warps 2..5) ===============================
-    const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
+    // =============================== epilogue (warps 2..9) ===============================
+    // 8 warps: warp w reads TMEM lane quadrant (w & 3) (hardware rule: a warp may only touch lanes 32*(w%4)..+31)
+    // and the column half ((w - 2) >> 2) of the accumulator, so every SMSP has two epilogue warps in flight.
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int chunks = (p.BN + 31) >> 5;
+    const int c_begin = half == 0 ? 0 : (chunks + 1) >> 1, c_end = half == 0 ? (chunks + 1) >> 1 : chunks;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.n_tiles, m_blk = (tile / p.n_tiles) % p.m_tiles;
@@ -227,60 +233,89 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row = m_blk * BM + quad * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * 256u;
       const bool row_ok = row < p.M;
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      const bool first_split = tile < p.m_tiles * p.n_tiles;
+      for (int ch = c_begin; ch < c_end; ++ch) {
+        const int c0 = ch << 5;
         uint32_t r[32];
+        __syncwarp();                             // tcgen05.ld is warp-collective: reconverge after the per-row predicated stores
         tmem_ld32(t_row + (uint32_t)c0, r);
         tmem_ld_wait();
         const int col0 = n_blk * p.BN + c0;
-        if (row_ok && col0 < p.N) {
-          float v[32];
+        const int ncols = min(32, min(p.BN - c0, p.N - col0));
+        if (!row_ok || ncols <= 0) continue;
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          const int ncols = min(32, min(p.BN - c0, p.N - col0));
-          if (p.splits > 1) {
-            float* dst = reinterpret_cast<float*>(p.C) + (long)row * p.ldc + col0;
-            const bool add_bias = p.bias != nullptr && tile < p.m_tiles * p.n_tiles;
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const bool full = ncols == 32;
+        if (p.bias != nullptr && (p.splits == 1 || first_split)) {
+          const float* bp = p.bias + col0;
+          if (full && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) atomicAdd(dst + j, v[j] + (add_bias ? p.bias[col0 + j] : 0.f));
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < ncols) {
-                float x = v[j];
-                if (p.bias) x += __ldg(p.bias + col0 + j);
-                if (col0 + j >= p.act_col_start) {
-                  if (p.act == 1) x = gelu_f(x);
-                  else if (p.act == 2) x = fmaxf(x, 0.f);
-                }
-                v[j] = x;
-              }
-            }
-            if (p.out_bf16) {
-              bf16* dst = reinterpret_cast<bf16*>(p.C) + (long)row * p.ldc + col0;
-              if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) v[j] += __ldg(bp + j);
+          }
+        }
+        if (p.splits > 1) {                       // split-K partial sums: fp32 reductions into a zeroed / accumulating C
+          float* dst = reinterpret_cast<float*>(p.C) + (long)row * p.ldc + col0;
+          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) Vec8<bf16>::store(dst + j, v + j);
-              } else {
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+          } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) atomicAdd(dst + j, v[j]);
+          }
+          continue;
+        }
+        if (p.act != 0) {
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (col0 + j >= p.act_col_start) ? gelu_f(v[j]) : v[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (col0 + j >= p.act_col_start) ? fmaxf(v[j], 0.f) : v[j];
+          }
+        }
+        if (p.out_bf16) {
+          bf16* dst = reinterpret_cast<bf16*>(p.C) + (long)row * p.ldc + col0;
+          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) Vec8<bf16>::store(dst + j, v + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
+          }
+        } else {
+          float* dst = reinterpret_cast<float*>(p.C) + (long)row * p.ldc + col0;
+          const bool vec = full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+          if (p.accumulate) {
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 o = *reinterpret_cast<float4*>(dst + j);
+                o.x += v[j]; o.y += v[j + 1]; o.z += v[j + 2]; o.w += v[j + 3];
+                *reinterpret_cast<float4*>(dst + j) = o;
               }
             } else {
-              float* dst = reinterpret_cast<float*>(p.C) + (long)row * p.ldc + col0;
-              if (p.accumulate) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < ncols) dst[j] += v[j];
-              } else if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < ncols) dst[j] = v[j];
-              }
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) dst[j] += v[j];
             }
+          } else if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) dst[j] = v[j];
           }
         }
       }

@@ -6,43 +6,53 @@ namespace {
 
 constexpr int LN_MAX_PER_LANE = 32;   // C <= 1024
 
-// ------------------------------------------------------------------ LayerNorm forward: one warp per row
-template <typename T>
+// ------------------------------------------------------------------ LayerNorm: one warp per row, NPL values per lane
+// (NPL = ceil(C / 32) rounded up to a supported size; the row lives in registers between the two passes)
+template <typename T, int NPL>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                      int M, int C, T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
+  float gm[NPL], bt[NPL];
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int c = lane + i * 32;
+    gm[i] = c < C ? gamma[c] : 0.f;
+    bt[i] = c < C ? beta[c] : 0.f;
+  }
+  const float invC = 1.f / (float)C;
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
     const float* xr = x + (long)row * C;
-    float v[LN_MAX_PER_LANE];
+    float v[NPL];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    for (int i = 0; i < NPL; ++i) {
       const int c = lane + i * 32;
-      v[i] = (c < C) ? xr[c] : 0.f;
+      v[i] = (c < C) ? __ldg(xr + c) : 0.f;
       s += v[i];
     }
-    const float mu = warp_sum(s) / C;
+    const float mu = warp_sum(s) * invC;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    for (int i = 0; i < NPL; ++i) {
       const int c = lane + i * 32;
       const float d = (c < C) ? v[i] - mu : 0.f;
       q = fmaf(d, d, q);
     }
-    const float rs = rsqrtf(warp_sum(q) / C + eps);
+    const float rs = rsqrtf(warp_sum(q) * invC + eps);
     if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
     T* yr = y + (long)row * C;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    for (int i = 0; i < NPL; ++i) {
       const int c = lane + i * 32;
-      if (c < C) yr[c] = from_f<T>((v[i] - mu) * rs * gamma[c] + beta[c]);
+      if (c < C) yr[c] = from_f<T>((v[i] - mu) * rs * gm[i] + bt[i]);
     }
   }
 }
 
-// LayerNorm backward: warp per row for dx; per-lane partial dgamma/dbeta accumulated over the block's rows.
-template <typename T>
+// Backward: warp per row for dx; dgamma/dbeta partials stay in registers over the warp's rows, are combined across
+// the block's warps in shared memory and leave as one atomicAdd per channel per block.
+template <typename T, int NPL>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd, int M, int C, const float* dx_in, float* dx,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta) {
@@ -51,34 +61,39 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
-  float pg[LN_MAX_PER_LANE], pb[LN_MAX_PER_LANE];
+  float pg[NPL], pb[NPL], gm[NPL];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_PER_LANE; ++i) { pg[i] = 0.f; pb[i] = 0.f; }
+  for (int i = 0; i < NPL; ++i) {
+    pg[i] = 0.f; pb[i] = 0.f;
+    const int c = lane + i * 32;
+    gm[i] = c < C ? gamma[c] : 0.f;
+  }
+  const float invC = 1.f / (float)C;
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
     const float* xr = x + (long)row * C;
     const T* gr = dy + (long)row * C;
     const float mu = mean[row], rs = rstd[row];
-    float xh[LN_MAX_PER_LANE], g[LN_MAX_PER_LANE];
+    float xh[NPL], g[NPL];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    for (int i = 0; i < NPL; ++i) {
       const int c = lane + i * 32;
       if (c < C) {
         const float d = to_f(gr[c]);
-        xh[i] = (xr[c] - mu) * rs;
-        g[i] = d * gamma[c];
+        xh[i] = (__ldg(xr + c) - mu) * rs;
+        g[i] = d * gm[i];
         pg[i] = fmaf(d, xh[i], pg[i]);
         pb[i] += d;
         s1 += g[i];
         s2 = fmaf(g[i], xh[i], s2);
       } else { xh[i] = 0.f; g[i] = 0.f; }
     }
-    s1 = warp_sum(s1) / C;
-    s2 = warp_sum(s2) / C;
+    s1 = warp_sum(s1) * invC;
+    s2 = warp_sum(s2) * invC;
     float* dr = dx + (long)row * C;
     const float* di = dx_in ? dx_in + (long)row * C : nullptr;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    for (int i = 0; i < NPL; ++i) {
       const int c = lane + i * 32;
       if (c < C) {
         const float v = rs * (g[i] - s1 - xh[i] * s2);
@@ -87,13 +102,27 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
     }
   }
 #pragma unroll
-  for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+  for (int i = 0; i < NPL; ++i) {
     const int c = lane + i * 32;
     if (c < C) { atomicAdd(&sm[c], pg[i]); atomicAdd(&sm[C + c], pb[i]); }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) { atomicAdd(dgamma + c, sm[c]); atomicAdd(dbeta + c, sm[C + c]); }
 }
+
+#define LN_DISPATCH_NPL(C, ...)                                      \
+  do {                                                               \
+    const int npl_ = ((C) + 31) / 32;                                \
+    if (npl_ <= 1) { constexpr int NPL = 1; __VA_ARGS__ }            \
+    else if (npl_ <= 2) { constexpr int NPL = 2; __VA_ARGS__ }       \
+    else if (npl_ <= 3) { constexpr int NPL = 3; __VA_ARGS__ }       \
+    else if (npl_ <= 4) { constexpr int NPL = 4; __VA_ARGS__ }       \
+    else if (npl_ <= 6) { constexpr int NPL = 6; __VA_ARGS__ }       \
+    else if (npl_ <= 9) { constexpr int NPL = 9; __VA_ARGS__ }       \
+    else if (npl_ <= 16) { constexpr int NPL = 16; __VA_ARGS__ }     \
+    else if (npl_ <= 18) { constexpr int NPL = 18; __VA_ARGS__ }     \
+    else { constexpr int NPL = 32; __VA_ARGS__ }                     \
+  } while (0)
 
 // ------------------------------------------------------------------ BatchNorm
 constexpr int BN_THREADS = 256;
@@ -275,7 +304,7 @@ extern "C" int dfb200_layernorm_fwd(const float* x, const float* gamma, const fl
   DFB_REQUIRE(C >= 1 && C <= 32 * LN_MAX_PER_LANE, "layernorm: C=%d out of range", C);
   if (M <= 0) return DFB_OK;
   const int grid = min(dfb_cdiv(M, 8), 148 * 8);
-  DFB_DISPATCH_DTYPE(y_dtype, T, { ln_fwd_kernel<T><<<grid, 256, 0, ST>>>(x, gamma, beta, eps, M, C, (T*)y, mean, rstd); });
+  DFB_DISPATCH_DTYPE(y_dtype, T, { LN_DISPATCH_NPL(C, { ln_fwd_kernel<T, NPL><<<grid, 256, 0, ST>>>(x, gamma, beta, eps, M, C, (T*)y, mean, rstd); }); });
   return dfb_check_launch("layernorm_fwd");
 }
 
@@ -283,9 +312,9 @@ extern "C" int dfb200_layernorm_bwd(const void* dy, int dy_dtype, const float* x
                                     const float* dx_in, float* dx, float* dgamma, float* dbeta, void* stream) {
   DFB_REQUIRE(C >= 1 && C <= 32 * LN_MAX_PER_LANE, "layernorm: C=%d out of range", C);
   if (M <= 0) return DFB_OK;
-  const int grid = min(dfb_cdiv(M, 8), 148 * 2);
+  const int grid = min(dfb_cdiv(M, 8), 148 * 8);
   DFB_DISPATCH_DTYPE(dy_dtype, T, {
-    ln_bwd_kernel<T><<<grid, 256, 2 * C * sizeof(float), ST>>>((const T*)dy, x, gamma, mean, rstd, M, C, dx_in, dx, dgamma, dbeta);
+    LN_DISPATCH_NPL(C, { ln_bwd_kernel<T, NPL><<<grid, 256, 2 * C * sizeof(float), ST>>>((const T*)dy, x, gamma, mean, rstd, M, C, dx_in, dx, dgamma, dbeta); });
   });
   return dfb_check_launch("layernorm_bwd");
 }
