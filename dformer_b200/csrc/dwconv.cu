@@ -119,7 +119,38 @@ __global__ void __launch_bounds__(CB / 8 * STRIPS) dwconv_kernel(const T* __rest
 // tile of one 64-channel slab (16-byte vectors, coalesced 128-byte rows) in shared memory once, so vertical taps
 // are re-used on chip instead of being re-fetched from L2 by other CTAs; each thread then produces TH x TW output
 // pixels of one 8-channel vector with a register sliding window along W.
+// ---------------------------------------------------------------------------------------------------------
+// cp.async (LDGSTS) helpers: all 16-byte tile loads of a CTA are in flight at once (no register staging, no
+// per-iteration load->store dependency); out-of-image / out-of-slab vectors are zero-filled (src-size 0).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 constexpr int TL_TX = 32, TL_TY = 8, TL_TW = 4, TL_TH = 2;    // tile 8 x 32 pixels, thread 2 x 4 pixels -> 256 threads
+
+// halo tile [TY+K-1][TX+K-1][8 vectors] of the 64-channel slab starting at c_base
+template <int K>
+__device__ __forceinline__ void load_halo_tile_async(uint4* tile, const bf16* __restrict__ x, int b, int ty0, int tx0, int H, int W, int C,
+                                                     int c_base, int nv) {
+  constexpr int R = K / 2, SW = TL_TX + K - 1, SH = TL_TY + K - 1, N = SH * SW * 8;
+#pragma unroll
+  for (int it = 0; it < (N + 255) / 256; ++it) {
+    const int i = threadIdx.x + it * 256;
+    if (i < N) {
+      const int cv = i & 7, px = (i >> 3) % SW, py = (i >> 3) / SW;
+      const int gy = ty0 + py - R, gx = tx0 + px - R;
+      const bool ok = cv < nv && gy >= 0 && gy < H && gx >= 0 && gx < W;
+      const bf16* src = ok ? x + (((long)b * H + gy) * W + gx) * C + c_base + cv * 8 : x;
+      cp_async16(tile + i, src, ok);
+    }
+  }
+}
 
 template <int K, int MODE>
 __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ weight,
@@ -142,14 +173,8 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restric
   }
   if (threadIdx.x < 64) bsm[threadIdx.x] = (MODE != 2 && threadIdx.x < cb && bias) ? bias[c_base + threadIdx.x] : 0.f;
   const int nv = cb >> 3;
-  for (int i = threadIdx.x; i < SH * SW * 8; i += 256) {
-    const int cv = i & 7, px = (i >> 3) % SW, py = (i >> 3) / SW;
-    const int gy = ty0 + py - R, gx = tx0 + px - R;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (cv < nv && gy >= 0 && gy < H && gx >= 0 && gx < W)
-      v = __ldg(reinterpret_cast<const uint4*>(x + (((long)b * H + gy) * W + gx) * C + c_base + cv * 8));
-    tile[i] = v;
-  }
+  load_halo_tile_async<K>(tile, x, b, ty0, tx0, H, W, C, c_base, nv);
+  cp_async_wait_all();
   __syncthreads();
   const int cv = threadIdx.x & 7, sx = (threadIdx.x >> 3) & 7, sy = threadIdx.x >> 6;
   if (cv >= nv) return;
@@ -176,10 +201,8 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restric
 #pragma unroll
       for (int i = 0; i < TL_TW + K - 1; ++i) {
         const uint4 u = rowp[i * 8];
-        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
         float v[8];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(hh[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+        Vec8<bf16>::unpack(u, v);
 #pragma unroll
         for (int t = 0; t < TL_TW; ++t) {
           const int kx = i - t;
@@ -205,9 +228,10 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restric
       for (int j = 0; j < 8; ++j) o[j] = acc[r][t][j];
       if (add_input) {
         const uint4 u = tile[((ly + r + R) * SW + lx + t + R) * 8 + cv];
-        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+        float cval[8];
+        Vec8<bf16>::unpack(u, cval);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(hh[q]); o[2 * q] += f.x; o[2 * q + 1] += f.y; }
+        for (int j = 0; j < 8; ++j) o[j] += cval[j];
       }
       if (MODE == 0) {
         if (act == 1) {
@@ -351,6 +375,121 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const T* __restrict__
   }
 }
 
+// bf16 fast path of the weight gradient: a CTA walks a list of 8x32-pixel tiles of one 64-channel slab; per tile the
+// x halo tile and the dz tile are staged in shared memory with cp.async, and worker (cv, ky, part) slides a K-wide
+// register window along 8-pixel row segments: acc[kx] += dz[p] * x[p + (ky-R, kx-R)].  Partials live in registers
+// across all of the CTA's tiles and leave through shared-memory atomics + one global atomicAdd per (channel, tap).
+template <int K>
+__global__ void __launch_bounds__(256) dwconv_wgrad_tiled_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ x, int B, int H, int W, int C,
+                                                                float* __restrict__ dweight, float* __restrict__ dbias, int tiles_x, int tiles_y) {
+  constexpr int R = K / 2, SW = TL_TX + K - 1, SH = TL_TY + K - 1;
+  constexpr int P = 32 / K;                          // parts per kernel row (k=3: 10, k=7: 4)
+  constexpr int ITEMS = TL_TY * (TL_TX / 8);         // (row, 8-pixel segment) items per tile = 32
+  extern __shared__ __align__(16) uint8_t dsm[];
+  uint4* xt = reinterpret_cast<uint4*>(dsm);                                   // [SH][SW][8]
+  uint4* zt = xt + SH * SW * 8;                                                // [TY][TX][8]
+  float* red = reinterpret_cast<float*>(zt + TL_TY * TL_TX * 8);               // [K][8][K*8+8]
+  const int c_base = blockIdx.y * 64;
+  const int nv = min(64, C - c_base) >> 3;
+  const int cv = threadIdx.x & 7, wk = threadIdx.x >> 3;
+  const int ky = wk / P, part = wk % P;
+  const bool worker = wk < K * P && cv < nv;
+  for (int i = threadIdx.x; i < K * 8 * (K * 8 + 8); i += 256) red[i] = 0.f;
+  float acc[K][8], accb[8];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) accb[j] = 0.f;
+  const int n_tiles = B * tiles_x * tiles_y;
+  for (int tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
+    const int tx0 = (tile_id % tiles_x) * TL_TX, ty0 = ((tile_id / tiles_x) % tiles_y) * TL_TY, b = tile_id / (tiles_x * tiles_y);
+    __syncthreads();                                 // previous tile fully consumed
+    load_halo_tile_async<K>(xt, x, b, ty0, tx0, H, W, C, c_base, nv);
+#pragma unroll
+    for (int it = 0; it < TL_TY * TL_TX * 8 / 256; ++it) {
+      const int i = threadIdx.x + it * 256;
+      const int v = i & 7, px = (i >> 3) % TL_TX, py = (i >> 3) / TL_TX;
+      const int gy = ty0 + py, gx = tx0 + px;
+      const bool ok = v < nv && gy < H && gx < W;
+      const bf16* src = ok ? dz + (((long)b * H + gy) * W + gx) * C + c_base + v * 8 : dz;
+      cp_async16(zt + i, src, ok);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (worker) {
+      for (int item = part; item < ITEMS; item += P) {
+        const int row = item / (TL_TX / 8), xs = (item % (TL_TX / 8)) * 8;
+        const uint4* xrow = xt + ((row + ky) * SW + xs) * 8 + cv;          // x[row + ky - R][xs + i - R] at index i
+        const uint4* zrow = zt + (row * TL_TX + xs) * 8 + cv;
+        float win[K][8];
+#pragma unroll
+        for (int k = 1; k < K; ++k) Vec8<bf16>::unpack(xrow[(k - 1) * 8], win[k]);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+#pragma unroll
+          for (int k = 0; k < K - 1; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) win[k][j] = win[k + 1][j];
+          Vec8<bf16>::unpack(xrow[(t + K - 1) * 8], win[K - 1]);
+          float g[8];
+          Vec8<bf16>::unpack(zrow[t * 8], g);
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[k][j] = fmaf(g[j], win[k][j], acc[k][j]);
+          if (ky == R) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) accb[j] += g[j];
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (worker) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&red[(ky * 8 + cv) * (K * 8 + 8) + k * 8 + j], acc[k][j]);
+    if (ky == R) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&red[(ky * 8 + cv) * (K * 8 + 8) + K * 8 + j], accb[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * 8 * (K * 8 + 8); i += 256) {
+    const int e = i % (K * 8 + 8), rest = i / (K * 8 + 8);
+    const int v = rest % 8, kyy = rest / 8;
+    const int c = c_base + v * 8 + (e & 7);
+    if (c >= C) continue;
+    const float sum = red[i];
+    if (e < K * 8) atomicAdd(dweight + (long)c * K * K + kyy * K + (e >> 3), sum);
+    else if (kyy == R) atomicAdd(dbias + c, sum);
+  }
+}
+
+template <int K>
+int launch_wgrad_tiled(const bf16* dz, const bf16* x, int B, int H, int W, int C, float* dweight, float* dbias, cudaStream_t st) {
+  constexpr int SW = TL_TX + K - 1, SH = TL_TY + K - 1;
+  constexpr int smem = (SH * SW * 8 + TL_TY * TL_TX * 8) * 16 + K * 8 * (K * 8 + 8) * 4;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_wgrad_tiled_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { dfb_set_error("dwconv wgrad smem attr: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
+    attr = true;
+  }
+  const int tiles_x = dfb_cdiv(W, TL_TX), tiles_y = dfb_cdiv(H, TL_TY);
+  const int n_tiles = B * tiles_x * tiles_y, chunks = dfb_cdiv(C, 64);
+  int gx = dfb_cdiv(148 * 2, chunks);                 // ~2 CTAs per SM over all channel slabs
+  if (gx > n_tiles) gx = n_tiles;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, chunks);
+  dwconv_wgrad_tiled_kernel<K><<<grid, 256, smem, st>>>(dz, x, B, H, W, C, dweight, dbias, tiles_x, tiles_y);
+  return dfb_check_launch("dwconv_wgrad_tiled");
+}
+
 template <typename T, int K, int MODE>
 int launch_conv(const T* x, const T* dy, const float* w, const float* b, int B, int H, int W, int C, int add_input, int act, T* y, cudaStream_t st) {
   if constexpr (sizeof(T) == 2) {
@@ -407,6 +546,10 @@ extern "C" int dfb200_dwconv_bwd(const void* dy, const void* x, int dtype, const
       if (rc) return rc;
     }
     if (dweight) {
+      if constexpr (sizeof(T) == 2) {
+        return k == 3 ? launch_wgrad_tiled<3>((const bf16*)dz, (const bf16*)x, B, H, W, C, dweight, dbias, ST)
+                      : launch_wgrad_tiled<7>((const bf16*)dz, (const bf16*)x, B, H, W, C, dweight, dbias, ST);
+      }
       if (k == 3) dwconv_wgrad_kernel<T, 3><<<wgrid, 256, 0, ST>>>(dz, (const T*)x, B, H, W, C, dweight, dbias, ppb);
       else dwconv_wgrad_kernel<T, 7><<<wgrid, 256, 0, ST>>>(dz, (const T*)x, B, H, W, C, dweight, dbias, ppb);
       return dfb_check_launch("dwconv_wgrad");

@@ -38,6 +38,7 @@ struct TcParams {
   int BN;                    // tile N (multiple of 16, <= 256)
   int m_tiles, n_tiles, splits, kb_per_split, kb_total;
   int a_mn_major, b_mn_major;
+  int batch; long strideC;
   void* C; long ldc;
   const float* bias;
   int out_bf16, act, act_col_start, accumulate;
@@ -77,10 +78,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -133,7 +134,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+  const int total_tiles = tiles_mn * p.splits * p.batch;     // tile = ((batch * splits + split) * m_tiles + m) * n_tiles + n
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -161,7 +163,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_blk = tile % p.n_tiles, m_blk = (tile / p.n_tiles) % p.m_tiles, sp = tile / (p.n_tiles * p.m_tiles);
+        const int n_blk = tile % p.n_tiles, m_blk = (tile / p.n_tiles) % p.m_tiles;
+        const int sp = (tile / tiles_mn) % p.splits, bz = tile / (tiles_mn * p.splits);
         const int kb0 = sp * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -169,14 +172,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sb = sa + A_STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], stage_tx);
           if (p.a_mn_major) {
-            for (int i = 0; i < a_boxes; ++i) tma_load_2d(&tmA, &full_bar[stage], sa + i * 8192, m_blk * BM + i * 64, kb * BK);
+            for (int i = 0; i < a_boxes; ++i) tma_load_3d(&tmA, &full_bar[stage], sa + i * 8192, m_blk * BM + i * 64, kb * BK, bz);
           } else {
-            tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m_blk * BM);
+            tma_load_3d(&tmA, &full_bar[stage], sa, kb * BK, m_blk * BM, bz);
           }
           if (p.b_mn_major) {
-            for (int i = 0; i < b_boxes; ++i) tma_load_2d(&tmB, &full_bar[stage], sb + i * 8192, n_blk * p.BN + i * 64, kb * BK);
+            for (int i = 0; i < b_boxes; ++i) tma_load_3d(&tmB, &full_bar[stage], sb + i * 8192, n_blk * p.BN + i * 64, kb * BK, bz);
           } else {
-            tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n_blk * p.BN);
+            tma_load_3d(&tmB, &full_bar[stage], sb, kb * BK, n_blk * p.BN, bz);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -194,7 +197,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int sp = tile / (p.n_tiles * p.m_tiles);
+        const int sp = (tile / tiles_mn) % p.splits;
         const int kb0 = sp * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -233,7 +236,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row = m_blk * BM + quad * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * 256u;
       const bool row_ok = row < p.M;
-      const bool first_split = tile < p.m_tiles * p.n_tiles;
+      const bool first_split = ((tile / tiles_mn) % p.splits) == 0;
+      const long c_off = (long)(tile / (tiles_mn * p.splits)) * p.strideC;
       for (int ch = c_begin; ch < c_end; ++ch) {
         const int c0 = ch << 5;
         uint32_t r[32];
@@ -262,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if (p.splits > 1) {                       // split-K partial sums: fp32 reductions into a zeroed / accumulating C
-          float* dst = reinterpret_cast<float*>(p.C) + (long)row * p.ldc + col0;
+          float* dst = reinterpret_cast<float*>(p.C) + c_off + (long)row * p.ldc + col0;
           if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -284,7 +288,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if (p.out_bf16) {
-          bf16* dst = reinterpret_cast<bf16*>(p.C) + (long)row * p.ldc + col0;
+          bf16* dst = reinterpret_cast<bf16*>(p.C) + c_off + (long)row * p.ldc + col0;
           if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) Vec8<bf16>::store(dst + j, v + j);
@@ -294,7 +298,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
           }
         } else {
-          float* dst = reinterpret_cast<float*>(p.C) + (long)row * p.ldc + col0;
+          float* dst = reinterpret_cast<float*>(p.C) + c_off + (long)row * p.ldc + col0;
           const bool vec = full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
           if (p.accumulate) {
             if (vec) {
@@ -352,7 +356,7 @@ EncodeTiledFn get_encode() {
 }
 
 struct MapKey {
-  const void* ptr; long inner, outer, ld; int box_inner, box_outer;
+  const void* ptr; long inner, outer, ld, batch, bstride; int box_inner, box_outer;
   bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
 };
 struct MapKeyHash {
@@ -364,13 +368,14 @@ struct MapKeyHash {
   }
 };
 
-// 2-D bf16 tensor map over a row-major [outer, inner] matrix with leading dimension ld (elements).
-int make_map(CUtensorMap* out, const void* ptr, long inner, long outer, long ld, int box_inner, int box_outer) {
+// 3-D bf16 tensor map over `batch` row-major [outer, inner] matrices (leading dimension ld, batch stride bstride, elements).
+int make_map(CUtensorMap* out, const void* ptr, long inner, long outer, long ld, int box_inner, int box_outer, long batch, long bstride) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key;
   memset(&key, 0, sizeof(key));
   key.ptr = ptr; key.inner = inner; key.outer = outer; key.ld = ld; key.box_inner = box_inner; key.box_outer = box_outer;
+  key.batch = batch; key.bstride = bstride;
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -378,11 +383,11 @@ int make_map(CUtensorMap* out, const void* ptr, long inner, long outer, long ld,
   }
   EncodeTiledFn enc = get_encode();
   if (!enc) { dfb_set_error("cuTensorMapEncodeTiled entry point not available"); return DFB_ERR_CUDA; }
-  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)bstride * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -410,7 +415,8 @@ int pick_bn(int N) {
 }  // namespace
 
 bool dfb_gemm_tc_supported(const dfb200_gemm_args& g) {
-  if (g.a_dtype != 1 || g.b_dtype != 1 || g.batch != 1 || g.batch_inner > 1) return false;
+  if (g.a_dtype != 1 || g.b_dtype != 1 || g.batch < 1 || g.batch_inner > 1) return false;
+  if (g.batch > 1 && ((g.strideA % 8) || (g.strideB % 8) || g.bias != nullptr)) return false;
   if (g.alpha != 0.f && g.alpha != 1.f) return false;
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return false;
   if ((g.lda % 8) || (g.ldb % 8)) return false;
@@ -441,10 +447,11 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   p.a_mn_major = g.transA ? 1 : 0;   // A stored [K, M]  -> M contiguous
   p.b_mn_major = g.transB ? 0 : 1;   // B stored [K, N]  -> N contiguous
   p.C = g.C; p.ldc = g.ldc; p.bias = g.bias;
+  p.batch = g.batch; p.strideC = g.strideC;
   p.out_bf16 = g.out_dtype == 1; p.act = g.act; p.act_col_start = g.act_col_start; p.accumulate = g.accumulate;
   // split-K when the output has too few tiles to fill the machine and the reduction is long (wgrad)
   int splits = 1;
-  const long tiles = (long)p.m_tiles * p.n_tiles;
+  const long tiles = (long)p.m_tiles * p.n_tiles * g.batch;
   if (g.splitk > 1) splits = g.splitk;
   else if (g.splitk == 0 && g.out_dtype == 0 && g.act == 0 && tiles * 2 <= num_sms && p.kb_total >= 16)
     splits = (int)min((long)p.kb_total / 4, (long)(num_sms / tiles));
@@ -453,16 +460,20 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   p.kb_per_split = dfb_cdiv(p.kb_total, splits);
   p.splits = dfb_cdiv(p.kb_total, p.kb_per_split);
   if (p.splits > 1 && !g.accumulate) {
-    cudaError_t e = cudaMemset2DAsync(g.C, g.ldc * sizeof(float), 0, (size_t)g.N * sizeof(float), g.M, st);
-    if (e != cudaSuccess) { dfb_set_error("memset2d: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
+    for (int b = 0; b < g.batch; ++b) {
+      cudaError_t e = cudaMemset2DAsync((float*)g.C + (long)b * g.strideC, g.ldc * sizeof(float), 0, (size_t)g.N * sizeof(float), g.M, st);
+      if (e != cudaSuccess) { dfb_set_error("memset2d: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
+    }
   }
   CUtensorMap tmA, tmB;
   int rc;
-  if (g.transA) rc = make_map(&tmA, g.A, g.M, g.K, g.lda, 64, 64);          // stored [K, M]
-  else rc = make_map(&tmA, g.A, g.K, g.M, g.lda, 64, BM);                  // stored [M, K]
+  const long sA = g.batch > 1 ? g.strideA : (long)g.lda * (g.transA ? g.K : g.M);
+  const long sB = g.batch > 1 ? g.strideB : (long)g.ldb * (g.transB ? g.N : g.K);
+  if (g.transA) rc = make_map(&tmA, g.A, g.M, g.K, g.lda, 64, 64, g.batch, sA);          // stored [K, M]
+  else rc = make_map(&tmA, g.A, g.K, g.M, g.lda, 64, BM, g.batch, sA);                  // stored [M, K]
   if (rc) return rc;
-  if (g.transB) rc = make_map(&tmB, g.B, g.K, g.N, g.ldb, 64, p.BN);        // stored [N, K]
-  else rc = make_map(&tmB, g.B, g.N, g.K, g.ldb, 64, 64);                  // stored [K, N]
+  if (g.transB) rc = make_map(&tmB, g.B, g.K, g.N, g.ldb, 64, p.BN, g.batch, sB);        // stored [N, K]
+  else rc = make_map(&tmB, g.B, g.N, g.K, g.ldb, 64, 64, g.batch, sB);                  // stored [K, N]
   if (rc) return rc;
   const long total = tiles * p.splits;
   const int grid = (int)min((long)num_sms, total);

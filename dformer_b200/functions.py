@@ -329,71 +329,84 @@ class BlockFn(torch.autograd.Function):
 
 # ============================================================================================ NMF2D
 def _nmf_fwd(x, bases_raw, steps, T):
-    """ham_head.py:60-100,109-145 on channels-last x [B, N, D] (compute dtype); bases_raw [B, D, R] fp32."""
+    """ham_head.py:60-100,109-145 on channels-last x [B, N, D] (compute dtype); bases_raw [B, D, R] fp32.
+
+    The factor state (coef, bases) and every multiplicative update stay fp32; in bf16 mode the batched matrix
+    products run on the tcgen05 GEMM with bf16 copies of the factors (what the reference's autocast bmm does)."""
     B, N, D = x.shape
     R = bases_raw.shape[2]
     dev = x.device
     f = lambda *s: torch.empty(s, device=dev, dtype=F32)
+    lo = (lambda t: t) if T == F32 else (lambda t: K.cast(t, torch.bfloat16))
+    sk = max(1, N // 512)
     bases, _ = K.normalize_cols(bases_raw)
-    S = K.bgemm(x, bases, f(B, N, R), M=N, N=R, K=D)
+    bases_l = lo(bases)
+    S = K.bgemm(x, bases_l, f(B, N, R), M=N, N=R, K=D)
     coef = K.softmax_rows(S)
+    coef_l = lo(coef)
     tape = []
 
-    def coef_update(coef, bases):
-        num = K.bgemm(x, bases, f(B, N, R), M=N, N=R, K=D)
-        btb = K.bgemm(bases, bases, f(B, R, R), trans_a=True, M=R, N=R, K=D)
-        den = K.bgemm(coef, btb, f(B, N, R), M=N, N=R, K=R)
-        return K.mu_update(coef, num, den), (coef, num, den, bases, btb)
+    def coef_update(coef, coef_l, bases, bases_l):
+        num = K.bgemm(x, bases_l, f(B, N, R), M=N, N=R, K=D)
+        btb_l = lo(K.bgemm(bases_l, bases_l, f(B, R, R), trans_a=True, M=R, N=R, K=D))
+        den = K.bgemm(coef_l, btb_l, f(B, N, R), M=N, N=R, K=R)
+        return K.mu_update(coef, num, den), (coef, coef_l, num, den, bases_l, btb_l)
 
     for _ in range(steps):
-        coef_n, rec_c = coef_update(coef, bases)
-        num2 = K.bgemm(x, coef_n, f(B, D, R), trans_a=True, M=D, N=R, K=N, splitk=max(1, N // 512))
-        ctc = K.bgemm(coef_n, coef_n, f(B, R, R), trans_a=True, M=R, N=R, K=N, splitk=max(1, N // 512))
-        den2 = K.bgemm(bases, ctc, f(B, D, R), M=D, N=R, K=R)
+        coef_n, rec_c = coef_update(coef, coef_l, bases, bases_l)
+        coef_nl = lo(coef_n)
+        num2 = K.bgemm(x, coef_nl, f(B, D, R), trans_a=True, M=D, N=R, K=N, splitk=sk)
+        ctc_l = lo(K.bgemm(coef_nl, coef_nl, f(B, R, R), trans_a=True, M=R, N=R, K=N, splitk=sk))
+        den2 = K.bgemm(bases_l, ctc_l, f(B, D, R), M=D, N=R, K=R)
         bases_n = K.mu_update(bases, num2, den2)
-        tape.append((rec_c, (bases, num2, den2, coef_n, ctc)))
-        coef, bases = coef_n, bases_n
-    coef_f, rec_f = coef_update(coef, bases)
+        tape.append((rec_c, (bases, bases_l, num2, den2, coef_nl, ctc_l)))
+        coef, coef_l, bases = coef_n, coef_nl, bases_n
+        bases_l = lo(bases)
+    coef_f, rec_f = coef_update(coef, coef_l, bases, bases_l)
+    coef_fl = lo(coef_f)
     out = torch.empty((B, N, D), device=dev, dtype=T)
-    K.bgemm(coef_f, bases, out, trans_b=True, M=N, N=D, K=R)
-    return out, (tape, rec_f, coef_f, bases, coef, S)
+    K.bgemm(coef_fl, bases_l, out, trans_b=True, M=N, N=D, K=R)
+    return out, (tape, rec_f, coef_fl, bases_l)
 
 
-def _nmf_bwd(dout, x, saved):
+def _nmf_bwd(dout, x, saved, T):
     """Back-propagation through every multiplicative update (the reference does not detach them, ham_head.py:45,119)."""
-    tape, rec_f, coef_f, bases_T, _, S = saved
+    tape, rec_f, coef_fl, bases_Tl = saved
     B, N, D = x.shape
-    R = coef_f.shape[2]
+    R = coef_fl.shape[2]
     dev = x.device
     f = lambda *s: torch.empty(s, device=dev, dtype=F32)
+    lo = (lambda t: t) if T == F32 else (lambda t: K.cast(t, torch.bfloat16))
     dx = torch.zeros((B, N, D), device=dev, dtype=F32)
     sk = max(1, N // 512)
     # out = coef_f @ bases^T
-    dcoef = K.bgemm(dout, bases_T, f(B, N, R), M=N, N=R, K=D)
-    dbases = K.bgemm(dout, coef_f, f(B, D, R), trans_a=True, M=D, N=R, K=N, splitk=sk)
+    dcoef = K.bgemm(dout, bases_Tl, f(B, N, R), M=N, N=R, K=D)
+    dbases = K.bgemm(dout, coef_fl, f(B, D, R), trans_a=True, M=D, N=R, K=N, splitk=sk)
 
     def coef_update_bwd(dcoef_new, rec, dbases):
-        coef, num, den, bases, btb = rec
+        coef, coef_l, num, den, bases_l, btb_l = rec
         dco = f(B, N, R)
         dnum, dden = K.mu_update_bwd(dcoef_new, coef, num, den, dco, False)
-        K.bgemm(dnum, bases, dx, trans_b=True, M=N, N=D, K=R, accumulate=True)           # num = x @ bases
-        K.bgemm(x, dnum, dbases, trans_a=True, M=D, N=R, K=N, accumulate=True, splitk=sk)
-        K.bgemm(dden, btb, dco, M=N, N=R, K=R, accumulate=True)                          # den = coef @ BtB (BtB symmetric)
-        dbtb = K.bgemm(coef, dden, f(B, R, R), trans_a=True, M=R, N=R, K=N, splitk=sk)
-        K.bgemm(bases, dbtb, dbases, M=D, N=R, K=R, accumulate=True)                     # BtB = bases^T bases
-        K.bgemm(bases, dbtb, dbases, trans_b=True, M=D, N=R, K=R, accumulate=True)
+        dnum_l, dden_l = lo(dnum), lo(dden)
+        K.bgemm(dnum_l, bases_l, dx, trans_b=True, M=N, N=D, K=R, accumulate=True)          # num = x @ bases
+        K.bgemm(x, dnum_l, dbases, trans_a=True, M=D, N=R, K=N, accumulate=True, splitk=sk)
+        K.bgemm(dden_l, btb_l, dco, M=N, N=R, K=R, accumulate=True)                         # den = coef @ BtB (BtB symmetric)
+        dbtb_l = lo(K.bgemm(coef_l, dden_l, f(B, R, R), trans_a=True, M=R, N=R, K=N, splitk=sk))
+        K.bgemm(bases_l, dbtb_l, dbases, M=D, N=R, K=R, accumulate=True)                    # BtB = bases^T bases
+        K.bgemm(bases_l, dbtb_l, dbases, trans_b=True, M=D, N=R, K=R, accumulate=True)
         return dco
 
     def bases_update_bwd(dbases_new, rec, dcoef):
-        bases, num2, den2, coef, ctc = rec
+        bases, bases_l, num2, den2, coef_l, ctc_l = rec
         dba = f(B, D, R)
         dnum2, dden2 = K.mu_update_bwd(dbases_new, bases, num2, den2, dba, False)
-        K.bgemm(coef, dnum2, dx, trans_b=True, M=N, N=D, K=R, accumulate=True)           # num2 = x^T @ coef
-        K.bgemm(x, dnum2, dcoef, M=N, N=R, K=D, accumulate=True)
-        K.bgemm(dden2, ctc, dba, M=D, N=R, K=R, accumulate=True)                         # den2 = bases @ CtC
-        dctc = K.bgemm(bases, dden2, f(B, R, R), trans_a=True, M=R, N=R, K=D)
-        K.bgemm(coef, dctc, dcoef, M=N, N=R, K=R, accumulate=True)                       # CtC = coef^T coef
-        K.bgemm(coef, dctc, dcoef, trans_b=True, M=N, N=R, K=R, accumulate=True)
+        dnum2_l, dden2_l = lo(dnum2), lo(dden2)
+        K.bgemm(coef_l, dnum2_l, dx, trans_b=True, M=N, N=D, K=R, accumulate=True)          # num2 = x^T @ coef
+        K.bgemm(x, dnum2_l, dcoef, M=N, N=R, K=D, accumulate=True)
+        K.bgemm(dden2_l, ctc_l, dba, M=D, N=R, K=R, accumulate=True)                        # den2 = bases @ CtC
+        dctc_l = lo(K.bgemm(bases_l, dden2_l, f(B, R, R), trans_a=True, M=R, N=R, K=D))
+        K.bgemm(coef_l, dctc_l, dcoef, M=N, N=R, K=R, accumulate=True)                      # CtC = coef^T coef
+        K.bgemm(coef_l, dctc_l, dcoef, trans_b=True, M=N, N=R, K=R, accumulate=True)
         return dba
 
     dcoef = coef_update_bwd(dcoef, rec_f, dbases)
@@ -401,9 +414,10 @@ def _nmf_bwd(dout, x, saved):
         dbases = bases_update_bwd(dbases, rec_b, dcoef)
         dcoef = coef_update_bwd(dcoef, rec_c, dbases)
     # coef0 = softmax(x @ bases0)
-    coef0, bases0 = (tape[0][0][0], tape[0][0][3]) if tape else (rec_f[0], rec_f[3])
+    first = tape[0][0] if tape else rec_f
+    coef0, bases0_l = first[0], first[4]
     dS = K.softmax_rows_bwd(dcoef, coef0)
-    K.bgemm(dS, bases0, dx, trans_b=True, M=N, N=D, K=R, accumulate=True)
+    K.bgemm(lo(dS), bases0_l, dx, trans_b=True, M=N, N=D, K=R, accumulate=True)
     return dx
 
 
@@ -464,7 +478,7 @@ class HeadFn(torch.autograd.Function):
                                   G["hamburger.ham_out.bn.bias"], act=K.ACT_RELU, residual=sv["s"])
         dnmf = _lin_bwd(dho_pre, sv["nmf"], pk("ham_out")[0], G["hamburger.ham_out.conv.weight"].view(pk("ham_out")[0].shape), None, T)
         hin = sv["hin"]
-        dhin32 = _nmf_bwd(dnmf.view(B, h1 * w1, D), hin.view(B, h1 * w1, D), sv["nmf_saved"]).view(M, D)
+        dhin32 = _nmf_bwd(dnmf.view(B, h1 * w1, D), hin.view(B, h1 * w1, D), sv["nmf_saved"], T).view(M, D)
         dhin = dhin32 if T == F32 else K.cast(dhin32, T)
         dhin_pre = K.act_bwd(dhin, hin, K.ACT_RELU)
         ds = _lin_bwd(dhin_pre, sv["s"], pk("ham_in")[0], G["hamburger.ham_in.conv.weight"].view(pk("ham_in")[0].shape),

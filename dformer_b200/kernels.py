@@ -72,8 +72,9 @@ def gemm(a, b, *, trans_a=False, trans_b=True, bias=None, out=None, out_dtype=No
     return out
 
 
-def bgemm(a, b, out, *, trans_a=False, trans_b=False, M, N, K, accumulate=False, alpha=0.0, splitk=1):
-    """Strided-batched GEMM over the leading dimension of 3-D tensors (SIMT backend)."""
+def bgemm(a, b, out, *, trans_a=False, trans_b=False, M, N, K, accumulate=False, alpha=0.0, splitk=1, backend=AUTO):
+    """Strided-batched GEMM over the leading dimension of 3-D tensors: tcgen05 (3-D TMA maps) when both operands are
+    bf16, otherwise the CUDA-core kernel."""
     assert a.dim() == 3 and b.dim() == 3 and out.dim() == 3 and a.stride(2) == 1 and b.stride(2) == 1 and out.stride(2) == 1
     g = GemmArgs()
     g.A, g.B, g.C, g.bias = a.data_ptr(), b.data_ptr(), out.data_ptr(), None
@@ -82,7 +83,10 @@ def bgemm(a, b, out, *, trans_a=False, trans_b=False, M, N, K, accumulate=False,
     g.M, g.N, g.K, g.batch, g.batch_inner = M, N, K, a.shape[0], 1
     g.transA, g.transB = int(trans_a), int(trans_b)
     g.a_dtype, g.b_dtype, g.out_dtype = dt(a), dt(b), dt(out)
-    g.accumulate, g.backend, g.splitk, g.alpha = int(accumulate), SIMT, splitk, alpha
+    tc = (backend != SIMT and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and alpha in (0.0, 1.0)
+          and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0 and a.stride(1) % 8 == 0 and b.stride(1) % 8 == 0)
+    g.accumulate, g.backend, g.alpha = int(accumulate), (TCGEN05 if tc else SIMT), alpha
+    g.splitk = (0 if out.dtype == torch.float32 else 1) if tc else splitk
     lib().gemm(ctypes.byref(g), _s())
     return out
 
