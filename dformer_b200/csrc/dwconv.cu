@@ -20,7 +20,7 @@ constexpr int STRIPS = 32;       // strips per CTA -> 256 threads
 template <typename T, int K, int MODE>
 __global__ void __launch_bounds__(CB / 8 * STRIPS) dwconv_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ weight,
                                                                 const float* __restrict__ bias, int B, int H, int W, int C, int add_input, int act,
-                                                                T* __restrict__ y) {
+                                                                T* __restrict__ y, T* __restrict__ zout) {
   __shared__ float wsm[K * K][CB];
   __shared__ float bsm[CB];
   const int c_base = blockIdx.y * CB;
@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(CB / 8 * STRIPS) dwconv_kernel(const T* __rest
         o[j] = z;
       }
       if (MODE == 0) {
+        if (zout) Vec8<T>::store(zout + off, o);
         if (act == 1) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = gelu_f(o[j]);
@@ -155,7 +156,7 @@ __device__ __forceinline__ void load_halo_tile_async(uint4* tile, const bf16* __
 template <int K, int MODE>
 __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ weight,
                                                           const float* __restrict__ bias, int B, int H, int W, int C, int add_input, int act,
-                                                          bf16* __restrict__ y, int tiles_x, int tiles_y) {
+                                                          bf16* __restrict__ y, bf16* __restrict__ zout, int tiles_x, int tiles_y) {
   constexpr int R = K / 2, SW = TL_TX + K - 1, SH = TL_TY + K - 1;
   extern __shared__ __align__(16) uint8_t dsm[];
   uint4* tile = reinterpret_cast<uint4*>(dsm);                       // [SH][SW][8]
@@ -234,6 +235,7 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restric
         for (int j = 0; j < 8; ++j) o[j] += cval[j];
       }
       if (MODE == 0) {
+        if (zout) Vec8<bf16>::store(zout + off, o);
         if (act == 1) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = gelu_f(o[j]);
@@ -253,7 +255,8 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restric
 }
 
 template <int K, int MODE>
-int launch_tiled(const bf16* x, const bf16* dy, const float* w, const float* b, int B, int H, int W, int C, int add_input, int act, bf16* y, cudaStream_t st) {
+int launch_tiled(const bf16* x, const bf16* dy, const float* w, const float* b, int B, int H, int W, int C, int add_input, int act, bf16* y, bf16* zout,
+                 cudaStream_t st) {
   constexpr int SW = TL_TX + K - 1, SH = TL_TY + K - 1;
   constexpr int smem = SH * SW * 8 * 16 + (K * K * 64 + 64) * 4;
   static bool attr = false;
@@ -264,7 +267,7 @@ int launch_tiled(const bf16* x, const bf16* dy, const float* w, const float* b, 
   }
   const int tiles_x = dfb_cdiv(W, TL_TX), tiles_y = dfb_cdiv(H, TL_TY);
   dim3 grid((unsigned)((long)B * tiles_x * tiles_y), dfb_cdiv(C, 64));
-  dwconv_tiled_kernel<K, MODE><<<grid, 256, smem, st>>>(x, dy, w, b, B, H, W, C, add_input, act, y, tiles_x, tiles_y);
+  dwconv_tiled_kernel<K, MODE><<<grid, 256, smem, st>>>(x, dy, w, b, B, H, W, C, add_input, act, y, zout, tiles_x, tiles_y);
   return dfb_check_launch("dwconv_tiled");
 }
 
@@ -491,10 +494,11 @@ int launch_wgrad_tiled(const bf16* dz, const bf16* x, int B, int H, int W, int C
 }
 
 template <typename T, int K, int MODE>
-int launch_conv(const T* x, const T* dy, const float* w, const float* b, int B, int H, int W, int C, int add_input, int act, T* y, cudaStream_t st) {
+int launch_conv(const T* x, const T* dy, const float* w, const float* b, int B, int H, int W, int C, int add_input, int act, T* y, T* zout,
+                cudaStream_t st) {
   if constexpr (sizeof(T) == 2) {
     return launch_tiled<K, MODE>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), w, b, B, H, W, C, add_input, act,
-                                 reinterpret_cast<bf16*>(y), st);
+                                 reinterpret_cast<bf16*>(y), reinterpret_cast<bf16*>(zout), st);
   }
   const long strips = (long)B * H * ((W + TW - 1) / TW);
   long gx = (strips + STRIPS - 1) / STRIPS;
@@ -502,7 +506,7 @@ int launch_conv(const T* x, const T* dy, const float* w, const float* b, int B, 
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, dfb_cdiv(C, CB));
-  dwconv_kernel<T, K, MODE><<<grid, CB / 8 * STRIPS, 0, st>>>(x, dy, w, b, B, H, W, C, add_input, act, y);
+  dwconv_kernel<T, K, MODE><<<grid, CB / 8 * STRIPS, 0, st>>>(x, dy, w, b, B, H, W, C, add_input, act, y, zout);
   return dfb_check_launch("dwconv");
 }
 
@@ -511,17 +515,17 @@ int launch_conv(const T* x, const T* dy, const float* w, const float* b, int B, 
 #define ST reinterpret_cast<cudaStream_t>(stream)
 
 extern "C" int dfb200_dwconv_fwd(const void* x, int dtype, const float* weight, const float* bias, int B, int H, int W, int C, int k, int add_input,
-                                 int act, void* y, void* stream) {
+                                 int act, void* y, void* z_out, void* stream) {
   DFB_REQUIRE(C % 8 == 0, "dwconv: C %% 8 != 0 (C=%d)", C);
   DFB_REQUIRE(k == 3 || k == 7, "dwconv: k must be 3 or 7");
   DFB_DISPATCH_DTYPE(dtype, T, {
-    if (k == 3) return launch_conv<T, 3, 0>((const T*)x, nullptr, weight, bias, B, H, W, C, add_input, act, (T*)y, ST);
-    return launch_conv<T, 7, 0>((const T*)x, nullptr, weight, bias, B, H, W, C, add_input, act, (T*)y, ST);
+    if (k == 3) return launch_conv<T, 3, 0>((const T*)x, nullptr, weight, bias, B, H, W, C, add_input, act, (T*)y, (T*)z_out, ST);
+    return launch_conv<T, 7, 0>((const T*)x, nullptr, weight, bias, B, H, W, C, add_input, act, (T*)y, (T*)z_out, ST);
   });
 }
 
-extern "C" int dfb200_dwconv_bwd(const void* dy, const void* x, int dtype, const float* weight, const float* bias, int B, int H, int W, int C, int k,
-                                 int add_input, int act, void* dz_buf, void* dx, float* dweight, float* dbias, void* stream) {
+extern "C" int dfb200_dwconv_bwd(const void* dy, const void* x, const void* z, int dtype, const float* weight, const float* bias, int B, int H, int W,
+                                 int C, int k, int add_input, int act, void* dz_buf, void* dx, float* dweight, float* dbias, void* stream) {
   DFB_REQUIRE(C % 8 == 0, "dwconv: C %% 8 != 0 (C=%d)", C);
   DFB_REQUIRE(k == 3 || k == 7, "dwconv: k must be 3 or 7");
   DFB_REQUIRE(act == 0 || dz_buf != nullptr, "dwconv_bwd: dz_buf required when act != 0");
@@ -535,14 +539,18 @@ extern "C" int dfb200_dwconv_bwd(const void* dy, const void* x, int dtype, const
     const T* dz = (const T*)dy;
     int rc = DFB_OK;
     if (act != 0) {
-      rc = (k == 3) ? launch_conv<T, 3, 1>((const T*)x, (const T*)dy, weight, bias, B, H, W, C, add_input, act, (T*)dz_buf, ST)
-                    : launch_conv<T, 7, 1>((const T*)x, (const T*)dy, weight, bias, B, H, W, C, add_input, act, (T*)dz_buf, ST);
+      if (z != nullptr) {      // saved pre-activation: dz = dy * act'(z) is a single element-wise pass
+        rc = dfb200_act_bwd(dy, C, z, C, dz_buf, C, dtype, act, (int)((long)B * H * W), C, stream);
+      } else {
+        rc = (k == 3) ? launch_conv<T, 3, 1>((const T*)x, (const T*)dy, weight, bias, B, H, W, C, add_input, act, (T*)dz_buf, nullptr, ST)
+                      : launch_conv<T, 7, 1>((const T*)x, (const T*)dy, weight, bias, B, H, W, C, add_input, act, (T*)dz_buf, nullptr, ST);
+      }
       if (rc) return rc;
       dz = (const T*)dz_buf;
     }
     if (dx) {
-      rc = (k == 3) ? launch_conv<T, 3, 2>(dz, nullptr, weight, nullptr, B, H, W, C, add_input, 0, (T*)dx, ST)
-                    : launch_conv<T, 7, 2>(dz, nullptr, weight, nullptr, B, H, W, C, add_input, 0, (T*)dx, ST);
+      rc = (k == 3) ? launch_conv<T, 3, 2>(dz, nullptr, weight, nullptr, B, H, W, C, add_input, 0, (T*)dx, nullptr, ST)
+                    : launch_conv<T, 7, 2>(dz, nullptr, weight, nullptr, B, H, W, C, add_input, 0, (T*)dx, nullptr, ST);
       if (rc) return rc;
     }
     if (dweight) {

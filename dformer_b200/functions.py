@@ -29,7 +29,8 @@ def _lin(x, wb, T, act=K.ACT_NONE, act_col_start=0, out=None, out_dtype=None):
 def _lin_bwd(dy, x, w, dW, db, T, need_dx=True, dx_out=None):
     """dW[N,K] = dy^T x (fp32, into the arena), db = colsum(dy), returns dx = dy @ W."""
     be = backend_for(T)
-    K.gemm(dy, x, trans_a=True, trans_b=False, out=dW, backend=be)
+    # dW lives in the zero-initialised gradient arena (or a zeroed scratch): accumulate so that split-K needs no memset
+    K.gemm(dy, x, trans_a=True, trans_b=False, out=dW, backend=be, accumulate=True)
     if db is not None:
         K.colsum(dy, out=db)
     if not need_dx:
@@ -120,13 +121,13 @@ class StemFn(torch.autograd.Function):
         dx0 = dx0.contiguous()
         dc2, _ = _bn_bwd(dx0, c2, ms2, st.bn2, n2, T, ar.view(p + "4.weight"), ar.view(p + "4.bias"))
         pk1, pk2 = st.packed[st.g1], st.packed[st.g2]
-        dW2p = torch.empty(pk2[0].shape, device=dx0.device, dtype=F32)
+        dW2p = torch.zeros(pk2[0].shape, device=dx0.device, dtype=F32)
         dcol2 = _lin_bwd(dc2, col2, pk2[0], dW2p, ar.view(p + "3.bias"), T)
         K.unpack_conv_grad(dW2p, pk2[0].shape[0], cm, ar.view(p + "3.weight"))
         da1 = K.im2col_bwd(dcol2, B, H1, W1, cm, T)
         # a1 = GELU(BN1(c1)) is recomputed inside the BN backward (pre-activation from c1)
         dc1, _ = _bn_bwd(da1, c1, ms1, st.bn1, n1, T, ar.view(p + "1.weight"), ar.view(p + "1.bias"), act=K.ACT_GELU)
-        dW1p = torch.empty(pk1[0].shape, device=dx0.device, dtype=F32)
+        dW1p = torch.zeros(pk1[0].shape, device=dx0.device, dtype=F32)
         _lin_bwd(dc1, col1, pk1[0], dW1p, ar.view(p + "0.bias"), T, need_dx=False)
         K.unpack_conv_grad(dW1p, pk1[0].shape[0], st.cin, ar.view(p + "0.weight"))
         ar.done(st.tag)
@@ -161,7 +162,7 @@ class DownsampleFn(torch.autograd.Function):
         cin = x.shape[1]
         dyT = dy.contiguous() if T == F32 else K.cast(dy.contiguous(), T)
         pk = st.packed[st.g]
-        dWp = torch.empty(pk[0].shape, device=dy.device, dtype=F32)
+        dWp = torch.zeros(pk[0].shape, device=dy.device, dtype=F32)
         dcol = _lin_bwd(dyT, col, pk[0], dWp, ar.view(p + "1.bias"), T)
         K.unpack_conv_grad(dWp, pk[0].shape[0], cin, ar.view(p + "1.weight"))
         dxb = K.im2col_bwd(dcol, st.B, st.H, st.W, cin, T)
@@ -180,11 +181,11 @@ def _mlp_fwd(x, pfx, st, P, sv, scale_b):
     B, H, W = st.B, st.H, st.W
     hn, mu, rs = K.layernorm_fwd(x, P[pfx + "norm.weight"], P[pfx + "norm.bias"], 1e-6, T)
     h = _lin(hn, st.packed[st.key + pfx + "fc1"], T)
-    u = K.dwconv_fwd(h, P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, add_input=True, act=K.ACT_GELU)
+    u, z = K.dwconv_fwd(h, P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, add_input=True, act=K.ACT_GELU, save_z=True)
     f = _lin(u, st.packed[st.key + pfx + "fc2"], T)
     ls = P["layer_scale_2" if pfx == "mlp." else "layer_scale_2_e"]
     out = K.scale_residual_fwd(x, f, ls, scale_b, H * W)
-    sv.update({pfx + "x": x, pfx + "mu": mu, pfx + "rs": rs, pfx + "hn": hn, pfx + "h": h, pfx + "u": u, pfx + "f": f})
+    sv.update({pfx + "x": x, pfx + "mu": mu, pfx + "rs": rs, pfx + "hn": hn, pfx + "h": h, pfx + "u": u, pfx + "f": f, pfx + "z": z})
     return out
 
 
@@ -197,7 +198,7 @@ def _mlp_bwd(dout, pfx, st, P, sv, scale_b, G):
     w2 = st.packed[st.key + pfx + "fc2"][0]
     du = _lin_bwd(df, sv[pfx + "u"], w2, G[pfx + "fc2.weight"], G[pfx + "fc2.bias"], T)
     dh = K.dwconv_bwd(du, sv[pfx + "h"], P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, True, K.ACT_GELU,
-                      G[pfx + "pos.weight"], G[pfx + "pos.bias"])
+                      G[pfx + "pos.weight"], G[pfx + "pos.bias"], z=sv[pfx + "z"])
     w1 = st.packed[st.key + pfx + "fc1"][0]
     dhn = _lin_bwd(dh, sv[pfx + "hn"], w1, G[pfx + "fc1.weight"], G[pfx + "fc1.bias"], T)
     return K.layernorm_bwd(dhn, sv[pfx + "x"], P[pfx + "norm.weight"], sv[pfx + "mu"], sv[pfx + "rs"], dout,

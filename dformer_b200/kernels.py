@@ -138,18 +138,19 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dgamma, dbeta):
     return dx
 
 
-def dwconv_fwd(x, weight, bias, B, H, W, k, add_input=False, act=ACT_NONE):
+def dwconv_fwd(x, weight, bias, B, H, W, k, add_input=False, act=ACT_NONE, save_z=False):
     C = x.shape[-1]
     y = torch.empty_like(x)
-    lib().dwconv_fwd(x.data_ptr(), dt(x), weight.data_ptr(), _p(bias), B, H, W, C, k, int(add_input), act, y.data_ptr(), _s())
-    return y
+    z = torch.empty_like(x) if save_z else None
+    lib().dwconv_fwd(x.data_ptr(), dt(x), weight.data_ptr(), _p(bias), B, H, W, C, k, int(add_input), act, y.data_ptr(), _p(z), _s())
+    return (y, z) if save_z else y
 
 
-def dwconv_bwd(dy, x, weight, bias, B, H, W, k, add_input, act, dweight, dbias, need_dx=True):
+def dwconv_bwd(dy, x, weight, bias, B, H, W, k, add_input, act, dweight, dbias, need_dx=True, z=None):
     C = x.shape[-1]
     dz = torch.empty_like(dy) if act != ACT_NONE else None
     dx = torch.empty_like(dy) if need_dx else None
-    lib().dwconv_bwd(dy.data_ptr(), x.data_ptr(), dt(x), weight.data_ptr(), _p(bias), B, H, W, C, k, int(add_input), act,
+    lib().dwconv_bwd(dy.data_ptr(), x.data_ptr(), _p(z), dt(x), weight.data_ptr(), _p(bias), B, H, W, C, k, int(add_input), act,
                      _p(dz), _p(dx), dweight.data_ptr(), dbias.data_ptr(), _s())
     return dx
 

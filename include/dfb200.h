@@ -86,14 +86,15 @@ int dfb200_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const flo
 /* ---- depthwise k x k conv, stride 1, 'same' padding, channels-last (DFormer.py:54,62,80-81,115,133)
  * y = act( dw(x) + bias [+ x if add_input] ).  weight is the nn.Conv2d tensor [C,1,k,k] (fp32), k in {3,7}. */
 int dfb200_dwconv_fwd(const void* x, int dtype, const float* weight, const float* bias, int B, int H, int W, int C,
-                      int k, int add_input, int act, void* y, void* stream);
+                      int k, int add_input, int act, void* y, void* z_out /* optional: pre-activation, kept for backward */,
+                      void* stream);
 /* Backward.  Given dy and the forward input x:
- *   dz = dy * act'(z) with z recomputed from x when act != 0;  dx = dw^T(dz) [+ dz];
+ *   dz = dy * act'(z) with z taken from `z` when given, else recomputed from x (act != 0);  dx = dw^T(dz) [+ dz];
  *   dweight[C,1,k,k], dbias[C] accumulated with atomics (zero-initialised by the caller).
  * `dz_buf` is a caller-provided scratch of the same shape/dtype as dy (only used when act != 0). */
-int dfb200_dwconv_bwd(const void* dy, const void* x, int dtype, const float* weight, const float* bias, int B, int H,
-                      int W, int C, int k, int add_input, int act, void* dz_buf, void* dx, float* dweight,
-                      float* dbias, void* stream);
+int dfb200_dwconv_bwd(const void* dy, const void* x, const void* z /* optional saved pre-activation */, int dtype,
+                      const float* weight, const float* bias, int B, int H, int W, int C, int k, int add_input, int act,
+                      void* dz_buf, void* dx, float* dweight, float* dbias, void* stream);
 
 /* ---- elementwise glue of Block/Attention ---------------------------------------------------------
  * mul:  out[m, n] = a[m, n] * b[m, n]  with independent leading dimensions (q*a, cut*e: DFormer.py:134-135;

@@ -122,6 +122,13 @@ def test_dwconv(dtype, k_, C, add, act):
     ref.backward(dy.float())
     dw, dbias = torch.zeros_like(w), torch.zeros_like(b)
     dx = k.dwconv_bwd(dy.view(-1, C), x.view(-1, C), w, b, B, H, W, k_, add, act, dw, dbias)
+    if act:      # variant with the pre-activation saved by the forward kernel
+        y2, zsv = k.dwconv_fwd(x.view(-1, C), w, b, B, H, W, k_, add, act, save_z=True)
+        torch.testing.assert_close(y2, y)
+        torch.testing.assert_close(zsv.view(B, H, W, C).float(), z, **tol(dtype))
+        dw2, db2 = torch.zeros_like(w), torch.zeros_like(b)
+        dx2 = k.dwconv_bwd(dy.view(-1, C), x.view(-1, C), w, b, B, H, W, k_, add, act, dw2, db2, z=zsv)
+        torch.testing.assert_close(dx2.float(), dx.float(), **(dict(rtol=3e-2, atol=5e-2) if dtype == torch.bfloat16 else dict(rtol=1e-3, atol=1e-3)))
     t = dict(rtol=3e-2, atol=5e-2) if dtype == torch.bfloat16 else dict(rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(dx.view(B, H, W, C).float(), xr.grad, **t)
     torch.testing.assert_close(dw, wr.grad, rtol=3e-2 if dtype == torch.bfloat16 else 1e-3, atol=0.3 if dtype == torch.bfloat16 else 1e-2)

@@ -62,6 +62,21 @@ def main():
     print(f"total device kernel time {tot / 1e3:.2f} ms over {sum(v[1] for v in agg.values())} launches")
     for name, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
         print(f"{t / 1e3:9.3f} ms {100 * t / tot:5.1f}%  x{n:<5d} {name}")
+    # per-shape GEMM table (CUDA events around every launch)
+    from dformer_b200 import kernels as K
+    K.GEMM_PROFILE = []
+    step()
+    torch.cuda.synchronize()
+    prof, K.GEMM_PROFILE = K.GEMM_PROFILE, None
+    g = defaultdict(lambda: [0.0, 0, 0.0, 0.0])
+    for e0, e1, fl, by, tc, shape in prof:
+        a = g[(tc,) + shape]
+        a[0] += e0.elapsed_time(e1); a[1] += 1; a[2] += fl; a[3] += by
+    tt = sum(a[0] for a in g.values())
+    print(f"GEMM launches via gemm(): {len(prof)}, total {tt:.2f} ms (event-timed, includes launch gaps)")
+    print("   ms     n   TFLOP/s   GB/s   tc (M, N, K, ta, tb)")
+    for k, a in sorted(g.items(), key=lambda kv: -kv[1][0])[:45]:
+        print(f"{a[0]:7.3f} {a[1]:4d} {a[2] / a[0] / 1e9:8.1f} {a[3] / a[0] / 1e6:7.0f}   {int(k[0])} {k[1:]}")
 
 
 if __name__ == "__main__":
