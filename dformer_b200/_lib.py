@@ -72,7 +72,7 @@ SIGNATURES = {
     "dfb200_upsample_ce_fwd": [P, I, I, I, I, I, I, I, P, I, P, P, P, P],
     "dfb200_ce_finalize": [P, P, P],
     "dfb200_upsample_ce_bwd": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, I, P],
-    "dfb200_adamw": [P, P, P, P, L, F, F, F, F, F, F, F, F, P, P, P],
+    "dfb200_adamw": [P, P, P, P, L, F, F, F, F, F, F, F, F, P, P, P, P],
 }
 
 

@@ -277,7 +277,12 @@ __global__ void axpy_kernel(const TI* __restrict__ x, float alpha, TO* __restric
 
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n, float lr_s, float b1,
                              float b2, float eps, float wd_s, float c1, float c2, float gs, const float* __restrict__ wd_arr,
-                             const float* __restrict__ lr_arr) {
+                             const float* __restrict__ lr_arr, const float* __restrict__ dyn) {
+  if (dyn) {                                                // schedule state lives on the device (CUDA-graph replays)
+    lr_s = dyn[0];
+    c1 = 1.f - powf(b1, dyn[1]);
+    c2 = 1.f - powf(b2, dyn[1]);
+  }
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const float lrm = lr_arr ? lr_arr[i] : 1.f;
     if (lrm == 0.f) continue;                               // frozen element (parameter outside every optimizer group)
@@ -420,7 +425,7 @@ extern "C" int dfb200_axpy(const void* x, int x_dtype, float alpha, void* y, int
 
 extern "C" int dfb200_adamw(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps,
                             float weight_decay, float bias_c1, float bias_c2, float grad_scale, const float* wd_arr, const float* lr_arr,
-                            void* stream) {
-  adamw_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2, grad_scale, wd_arr, lr_arr);
+                            const float* dyn, void* stream) {
+  adamw_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2, grad_scale, wd_arr, lr_arr, dyn);
   return dfb_check_launch("adamw");
 }

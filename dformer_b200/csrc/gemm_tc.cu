@@ -17,6 +17,7 @@
 #include <mutex>
 #include <unordered_map>
 #include <string.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "dfb200_internal.h"
@@ -39,6 +40,7 @@ struct TcParams {
   int m_tiles, n_tiles, splits, kb_per_split, kb_total;
   int a_mn_major, b_mn_major;
   int batch; long strideC;
+  int stages;
   void* C; long ldc;
   const float* bias;
   int out_bf16, act, act_col_start, accumulate;
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
@@ -140,7 +142,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -181,7 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             tma_load_3d(&tmB, &full_bar[stage], sb, kb * BK, n_blk * p.BN, bz);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -214,7 +216,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);          // frees the smem slot once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -477,6 +479,12 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   if (rc) return rc;
   const long total = tiles * p.splits;
   const int grid = (int)min((long)num_sms, total);
-  gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
+  // pipeline depth: no deeper than the k-loop of one tile needs (smaller smem request for the many short-K GEMMs)
+  static int forced_stages = -1;
+  if (forced_stages < 0) { const char* e = getenv("DFB200_TC_STAGES"); forced_stages = e ? atoi(e) : 0; }
+  p.stages = forced_stages > 0 ? forced_stages : STAGES;
+  if (p.stages > STAGES) p.stages = STAGES;
+  const int smem_bytes = p.stages * STAGE_BYTES + 1024 + 256;
+  gemm_tc_kernel<<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmB, p);
   return dfb_check_launch("gemm_tc");
 }

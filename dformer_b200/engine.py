@@ -1,0 +1,60 @@
+"""CUDA-graph training step: forward + loss + backward (+ gradient all-reduce) + fused AdamW captured ONCE and
+replayed per iteration, so the ~2700 kernel launches of a DFormer-L step cost one graph launch on the host.
+
+Streams and graphs instead of a tracing compiler: the step is ordinary eager code (our autograd.Functions issuing
+C-ABI kernel launches on the current stream); `torch.cuda.graph` records it.  Inputs live in static device buffers
+that `step()` refreshes with asynchronous H2D copies; the NMF bases keep the reference's CPU `torch.rand` draw
+(ham_head.py:111), staged through pinned memory outside the graph."""
+import torch
+
+
+class GraphedTrainStep:
+    def __init__(self, model, optimizer, rgb, modal_x, label, grad_sync=None, warmup=3, use_graph=True):
+        self.model, self.opt, self.sync = model, optimizer, grad_sync
+        self.rgb, self.modal_x, self.label = rgb.clone(), modal_x.clone(), label.clone()
+        head = model.decode_head
+        ham = head.hamburger.ham
+        B = rgb.shape[0]
+        self._bases_host = torch.empty((B * ham.S, ham.D, ham.R), dtype=torch.float32).pin_memory()
+        self._bases_dev = torch.empty_like(self._bases_host, device=rgb.device)
+        head.injected_bases = self._bases_dev
+        self.loss = None
+        self.graph = None
+        self._draw_bases()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(max(1, warmup)):          # allocator / tensor-map cache / attribute warm-up on the side stream
+                self._eager()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = self._eager()
+
+    def _draw_bases(self):
+        torch.rand(self._bases_host.shape, out=self._bases_host)     # same CPU RNG stream as the reference
+        self._bases_dev.copy_(self._bases_host, non_blocking=True)
+
+    def _eager(self):
+        loss, _ = self.model(self.rgb, self.modal_x, self.label)
+        loss.backward()
+        if self.sync is not None:
+            self.sync.finish()
+        self.opt.step()
+        self.opt.zero_grad()
+        return loss.detach()
+
+    def step(self, rgb=None, modal_x=None, label=None):
+        """Copy the batch into the static buffers (async, works from pinned host memory) and run one step."""
+        if rgb is not None:
+            self.rgb.copy_(rgb, non_blocking=True)
+            self.modal_x.copy_(modal_x, non_blocking=True)
+            self.label.copy_(label, non_blocking=True)
+        self._draw_bases()
+        if self.graph is not None:
+            self.graph.replay()
+            return self.loss
+        self.loss = self._eager()
+        return self.loss

@@ -366,8 +366,8 @@ def upsample_ce_bwd(small, B, h, w, ncls, H, W, label, ignore, lse, acc, dloss):
     return dsmall
 
 
-def adamw(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0, wd_arr=None, lr_arr=None):
+def adamw(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0, wd_arr=None, lr_arr=None, dyn=None):
     c1 = 1.0 - beta1 ** step
     c2 = 1.0 - beta2 ** step
     lib().adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps, wd, c1, c2, grad_scale,
-                _p(wd_arr), _p(lr_arr), _s())
+                _p(wd_arr), _p(lr_arr), _p(dyn), _s())

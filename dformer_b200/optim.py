@@ -20,6 +20,7 @@ class FusedAdamW:
         self.model, self.lr, self.betas, self.eps, self.weight_decay = model, lr, betas, eps, weight_decay
         self.step_count = 0
         self.state = []
+        self._dyn = None          # device {lr, step}: the schedule state a captured CUDA graph reads at replay time
         for mod in _flat_modules(model):
             flat = mod.flat_parameters()
             layout = mod._plan.layout
@@ -43,6 +44,12 @@ class FusedAdamW:
                     lrm[sl] = 1.0
             self.state.append(dict(mod=mod, m=torch.zeros_like(flat), v=torch.zeros_like(flat), wd=wd, lrm=lrm))
 
+    def set_lr(self, lr):
+        """Update the learning rate read by (possibly graph-captured) optimizer launches."""
+        self.lr = lr
+        if self._dyn is not None:
+            self._dyn[0] = lr
+
     def zero_grad(self, set_to_none=True):
         for p in self.model.parameters():
             p.grad = None
@@ -52,6 +59,13 @@ class FusedAdamW:
         """Uses the gradient arenas written by the last backward pass (p.grad views alias them)."""
         self.step_count += 1
         lr = self.lr if lr is None else lr
+        dev = self.state[0]["m"].device if self.state else None
+        if self._dyn is None and dev is not None:
+            self._dyn = torch.tensor([lr, 0.0], device=dev, dtype=torch.float32)
+        if self._dyn is not None:
+            if not torch.cuda.is_current_stream_capturing() and lr != self.lr:
+                self._dyn[0] = lr
+            self._dyn[1:].add_(1.0)                   # device-side step counter (captured as a kernel)
         for st in self.state:
             mod = st["mod"]
             flat = mod.flat_parameters()
@@ -59,7 +73,7 @@ class FusedAdamW:
             if arena is None or arena.buf is None:        # no backward pass since the last step
                 continue
             K.adamw(flat, arena.buf, st["m"], st["v"], lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count,
-                    wd_arr=st["wd"], lr_arr=st["lrm"])
+                    wd_arr=st["wd"], lr_arr=st["lrm"], dyn=self._dyn)
 
 
 class WarmUpPolyLR:

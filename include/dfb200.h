@@ -199,7 +199,8 @@ int dfb200_upsample_ce_bwd(const void* logits_small, int dtype, int B, int h, in
  * element; NULL = 1) reproduce the reference's parameter groups (utils/init_func.py:26-70) on one flat buffer. */
 int dfb200_adamw(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps,
                  float weight_decay, float bias_c1, float bias_c2, float grad_scale, const float* wd_arr,
-                 const float* lr_arr, void* stream);
+                 const float* lr_arr, const float* dyn /* optional device {lr, step}: overrides lr and the bias corrections
+                 so a captured CUDA graph follows the schedule */, void* stream);
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches evidence) */
 long dfb200_launch_count(void);
 

@@ -395,3 +395,12 @@ def test_adamw_matches_torch():
         opt.step()
         k.adamw(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, 0.01, step)
     torch.testing.assert_close(p, pr.detach(), rtol=1e-5, atol=1e-6)
+    # device-side schedule state (CUDA-graph friendly) gives the same update
+    p2, m2, v2 = rnd(1000), torch.zeros(1000, device=DEV), torch.zeros(1000, device=DEV)
+    p3, m3, v3 = p2.clone(), m2.clone(), v2.clone()
+    dyn = torch.tensor([2e-3, 0.0], device=DEV)
+    for step in (1, 2):
+        dyn[1] += 1
+        k.adamw(p2, g, m2, v2, 123.0, 0.9, 0.999, 1e-8, 0.01, 77, dyn=dyn)
+        k.adamw(p3, g, m3, v3, 2e-3, 0.9, 0.999, 1e-8, 0.01, step)
+    torch.testing.assert_close(p2, p3, rtol=1e-5, atol=1e-6)

@@ -36,5 +36,33 @@ def main():
         print(f"M={M} N={N} K={K} ta={int(ta)} tb={int(tb)}: {ms * 1e3:.1f} us  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e6:.0f} GB/s", flush=True)
 
 
+def tiny(reps=200):
+    dev = "cuda"
+    for (M, N, K) in [(128, 64, 64), (144, 432, 392), (9600, 144, 144), (9600, 288, 288), (2400, 576, 576)]:
+        a = torch.randn(M, K, device=dev).bfloat16()
+        b = torch.randn(N, K, device=dev).bfloat16()
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        for _ in range(5):
+            k.gemm(a, b, trans_b=True, backend=k.TCGEN05, out=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g, stream=s):
+                for _ in range(reps):
+                    k.gemm(a, b, trans_b=True, backend=k.TCGEN05, out=out)
+        g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"tiny M={M} N={N} K={K}: {e0.elapsed_time(e1) / reps * 1e3:.2f} us per back-to-back launch (CUDA graph of {reps})", flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[2] == "tiny":
+        tiny()
+        sys.exit(0)
     main()
