@@ -260,7 +260,9 @@ class DFormer(nn.Module):
         rates = [blk.dropout_layer.drop_prob if isinstance(blk.dropout_layer, DropPathCfg) else 0.0 for st in self.stages for blk in st]
         dp = None
         if training and any(r > 0 for r in rates):
-            keep = 1.0 - torch.tensor(rates, device=dev, dtype=torch.float32).view(-1, 1, 1)
+            keep = getattr(plan, "dp_keep", None)
+            if keep is None or keep.device != dev:     # cached on the device: no H2D copy inside a captured step
+                keep = plan.dp_keep = (1.0 - torch.tensor(rates, dtype=torch.float32).view(-1, 1, 1)).to(dev)
             dp = torch.floor(keep + torch.rand(n_blocks, 4, B, device=dev)) / keep      # DropPath: mask / keep_prob per sample
 
         def stem(inp, sfx, cin):
