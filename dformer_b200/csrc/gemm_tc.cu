@@ -32,7 +32,8 @@ constexpr int B_STAGE_BYTES = 256 * BK * 2;       // 32 KB (BN <= 256)
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int TMEM_COLS = 512;   // 2 accumulator stages x 256 fp32 columns
 constexpr int NUM_THREADS = 320;         // TMA warp + MMA warp + 8 epilogue warps
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_STAGE_BYTES = 8 * 4096;         // per-epilogue-warp 32 x 128 B staging tile for coalesced stores
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct TcParams {
   int M, N, K;               // problem (K = reduction length)
@@ -129,7 +130,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * STAGE_BYTES);
+  uint8_t* epi_stage = smem + p.stages * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
@@ -238,6 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row = m_blk * BM + quad * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * 256u;
       const bool row_ok = row < p.M;
+      const bool rows_all_ok = (m_blk * BM + quad * 32 + 31) < p.M;     // warp-uniform: the whole 32-row slab is inside M
       const bool first_split = ((tile / tiles_mn) % p.splits) == 0;
       const long c_off = (long)(tile / (tiles_mn * p.splits)) * p.strideC;
       for (int ch = c_begin; ch < c_end; ++ch) {
@@ -291,7 +294,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (p.out_bf16) {
           bf16* dst = reinterpret_cast<bf16*>(p.C) + c_off + (long)row * p.ldc + col0;
-          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((p.ldc & 7) == 0) && rows_all_ok) {
+            // warp-private transpose through shared memory: lane r holds row r (32 columns); after the swizzled
+            // round trip 4 adjacent lanes write one row's 64 contiguous bytes -> every store instruction covers
+            // 8 fully-written 64-byte row segments instead of 32 scattered 16-byte pieces.
+            uint4* st = reinterpret_cast<uint4*>(epi_stage + (warp - 2) * 4096);
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              uint4 pk;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[u * 8 + 2 * q], v[u * 8 + 2 * q + 1]);
+              st[lane * 4 + (u ^ ((lane >> 1) & 3))] = pk;
+            }
+            __syncwarp();
+            bf16* base = reinterpret_cast<bf16*>(p.C) + c_off + (long)(m_blk * BM + quad * 32) * p.ldc + col0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = 8 * i + (lane >> 2), u = lane & 3;
+              const uint4 pk = st[rr * 4 + (u ^ ((rr >> 1) & 3))];
+              *reinterpret_cast<uint4*>(base + (long)rr * p.ldc + u * 8) = pk;
+            }
+          } else if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) Vec8<bf16>::store(dst + j, v + j);
           } else {
@@ -484,7 +509,7 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   if (forced_stages < 0) { const char* e = getenv("DFB200_TC_STAGES"); forced_stages = e ? atoi(e) : 0; }
   p.stages = forced_stages > 0 ? forced_stages : STAGES;
   if (p.stages > STAGES) p.stages = STAGES;
-  const int smem_bytes = p.stages * STAGE_BYTES + 1024 + 256;
+  const int smem_bytes = p.stages * STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 256;
   gemm_tc_kernel<<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmB, p);
   return dfb_check_launch("gemm_tc");
 }

@@ -207,7 +207,11 @@ def _mlp_bwd(dout, pfx, st, P, sv, scale_b, G):
 
 class BlockFn(torch.autograd.Function):
     """DFormer.py:147-181 (Block) with Attention :102-145 and both MLPs :58-67; x, x_e are the fp32
-    channels-last residual streams [M, C], [M, C/2]."""
+    channels-last residual streams [M, C], [M, C/2].
+
+    The depth-stream work that does not depend on the RGB stream (LN_e -> e_fore -> dw7x7 -> e_back, and the whole
+    depth MLP) is launched on a side CUDA stream: at stages 2-3 the kernels are too small to fill 148 SMs one at a
+    time, and under graph capture the two branches become parallel graph branches."""
 
     @staticmethod
     def forward(ctx, x, x_e, st, *params):
@@ -218,9 +222,20 @@ class BlockFn(torch.autograd.Function):
         win, dd = st.window != 0, st.drop_depth
         pk = lambda n: st.packed[st.key + n]
         sv = {}
-        # ---- Attention
+        side = st.side
+        main = torch.cuda.current_stream()
+        # ---- depth gate path on the side stream
+        K.fork(side)
+        with torch.cuda.stream(side):
+            en, mu2, rs2 = K.layernorm_fwd(x_e, P["attn.norm_e.weight"], P["attn.norm_e.bias"], 1e-6, T)
+            ev_en = K.signal(side)
+            ef = _lin(en, pk("attn.e_fore"), T)
+            ec = K.dwconv_fwd(ef, P["attn.e_conv.weight"], P["attn.e_conv.bias"], B, H, W, 7)
+            e = _lin(ec, pk("attn.e_back"), T)
+            ev_e = K.signal(side)
+        K.share(main, en, mu2, rs2, ef, ec, e)
+        # ---- RGB path
         xn, mu1, rs1 = K.layernorm_fwd(x, P["attn.norm.weight"], P["attn.norm.bias"], 1e-6, T)
-        en, mu2, rs2 = K.layernorm_fwd(x_e, P["attn.norm_e.weight"], P["attn.norm_e.bias"], 1e-6, T)
         qcl = _lin(xn, pk("attn.qcl"), T)                                         # [M, 2.5C] = q | cut | z_l
         l = K.act_fwd(qcl[:, C + Ce:], K.ACT_GELU)
         cv = K.dwconv_fwd(l, P["attn.conv.weight"], P["attn.conv.bias"], B, H, W, 7)
@@ -230,25 +245,29 @@ class BlockFn(torch.autograd.Function):
         K.mul_fwd(qcl[:, :C], a, y[:, :C])
         if win:
             kv = _lin(l, pk("attn.kv"), T)
+            main.wait_event(ev_en)
             pooled = K.pool7_fwd(xn, en, B, H, W)
             m = _lin(pooled, pk("attn.short_cut_linear"), T)
             o7, probs = K.gaa_fwd(m, kv, B, HW, st.heads, Ce // st.heads)
             K.resize_fwd(o7, B, 7, 7, y, H, W, col0=C)
             sv.update(kv=kv, pooled=pooled, m=m, probs=probs)
-        ef = _lin(en, pk("attn.e_fore"), T)
-        ec = K.dwconv_fwd(ef, P["attn.e_conv.weight"], P["attn.e_conv.bias"], B, H, W, 7)
-        e = _lin(ec, pk("attn.e_back"), T)
+        main.wait_event(ev_e)
         K.mul_fwd(qcl[:, C:C + Ce], e, y[:, ycols - Ce:])
         pp = _lin(y, pk("attn.pp"), T)                                            # [M, C (+Ce)] = proj | proj_e
-        x1 = K.scale_residual_fwd(x, pp[:, :C], P["layer_scale_1"], st.dp[0], HW)
         sv.update(x=x, x_e=x_e, mu1=mu1, rs1=rs1, mu2=mu2, rs2=rs2, xn=xn, en=en, qcl=qcl, l=l, cv=cv, a=a, y=y, ef=ef, ec=ec, e=e, pp=pp)
-        # ---- MLPs
-        x2 = _mlp_fwd(x1, "mlp.", st, P, sv, st.dp[1])
+        # ---- MLPs: depth stream on the side stream, RGB stream on the main stream
         if not dd:
-            xe1 = K.scale_residual_fwd(x_e, pp[:, C:], P["layer_scale_1_e"], st.dp[2], HW)
-            xe2 = _mlp_fwd(xe1, "mlp_e2.", st, P, sv, st.dp[3])
+            K.fork(side)
+            with torch.cuda.stream(side):
+                n_before = set(sv)
+                xe1 = K.scale_residual_fwd(x_e, pp[:, C:], P["layer_scale_1_e"], st.dp[2], HW)
+                xe2 = _mlp_fwd(xe1, "mlp_e2.", st, P, sv, st.dp[3])
+            K.share(main, xe1, xe2, *[sv[k] for k in sv if k not in n_before])
         else:
             xe2 = x_e
+        x1 = K.scale_residual_fwd(x, pp[:, :C], P["layer_scale_1"], st.dp[0], HW)
+        x2 = _mlp_fwd(x1, "mlp.", st, P, sv, st.dp[1])
+        K.join(side)
         ctx.st, ctx.sv, ctx.P = st, sv, P
         return x2, xe2
 
@@ -258,25 +277,32 @@ class BlockFn(torch.autograd.Function):
         T = st.dtype
         P = ctx.P
         ar: GradArena = st.arena
-        G = {n: ar.view(st.prefix + n) for n in st.names}
+        G = {n: ar.view(st.prefix + n) for n in st.names}           # allocates / zero-fills the arena on the main stream
         B, H, W, C = st.B, st.H, st.W, st.C
         Ce, HW = C // 2, st.H * st.W
         M = sv["x"].shape[0]
         win, dd = st.window != 0, st.drop_depth
         pk = lambda n: st.packed[st.key + n]
         dev = sv["x"].device
+        side = st.side
+        main = torch.cuda.current_stream()
         dx2 = dx2.contiguous()
-        # ---- MLPs (reverse)
-        dx1 = _mlp_bwd(dx2, "mlp.", st, P, sv, st.dp[1], G)
         ppw = pk("attn.pp")[0]
         dpp = torch.empty((M, ppw.shape[0]), device=dev, dtype=T)
-        K.scale_residual_bwd(dx1, sv["pp"][:, :C], P["layer_scale_1"], st.dp[0], HW, G["layer_scale_1"], dy=dpp[:, :C])
+        # ---- MLPs (reverse): depth stream on the side stream
+        dxe1 = None
         if not dd:
             dxe2 = dxe2.contiguous() if dxe2 is not None else torch.zeros_like(sv["x_e"])
-            dxe1 = _mlp_bwd(dxe2, "mlp_e2.", st, P, sv, st.dp[3], G)
-            K.scale_residual_bwd(dxe1, sv["pp"][:, C:], P["layer_scale_1_e"], st.dp[2], HW, G["layer_scale_1_e"], dy=dpp[:, C:])
-        else:
-            dxe1 = None
+            K.fork(side)
+            with torch.cuda.stream(side):
+                dxe1 = _mlp_bwd(dxe2, "mlp_e2.", st, P, sv, st.dp[3], G)
+                K.scale_residual_bwd(dxe1, sv["pp"][:, C:], P["layer_scale_1_e"], st.dp[2], HW, G["layer_scale_1_e"], dy=dpp[:, C:])
+                ev_e = K.signal(side)
+            K.share(main, dxe1)
+        dx1 = _mlp_bwd(dx2, "mlp.", st, P, sv, st.dp[1], G)
+        K.scale_residual_bwd(dx1, sv["pp"][:, :C], P["layer_scale_1"], st.dp[0], HW, G["layer_scale_1"], dy=dpp[:, :C])
+        if not dd:
+            main.wait_event(ev_e)
         # ---- proj | proj_e
         if dd:
             dWpp, dbpp = G["attn.proj.weight"], G["attn.proj.bias"]
@@ -288,19 +314,22 @@ class BlockFn(torch.autograd.Function):
         qcl = sv["qcl"]
         dqcl = torch.empty_like(qcl)
         da = torch.empty((M, C), device=dev, dtype=T)
-        K.mul_bwd(dy[:, :C], qcl[:, :C], sv["a"], dqcl[:, :C], da)
         de = torch.empty((M, Ce), device=dev, dtype=T)
         K.mul_bwd(dy[:, ycols - Ce:], qcl[:, C:C + Ce], sv["e"], dqcl[:, C:C + Ce], de)
-        # ---- depth gate path: e = e_back(dw7(e_fore(en)))
-        dec = _lin_bwd(de, sv["ec"], pk("attn.e_back")[0], G["attn.e_back.weight"], G["attn.e_back.bias"], T)
-        def_ = K.dwconv_bwd(dec, sv["ef"], P["attn.e_conv.weight"], P["attn.e_conv.bias"], B, H, W, 7, False, K.ACT_NONE,
-                            G["attn.e_conv.weight"], G["attn.e_conv.bias"])
-        den = _lin_bwd(def_, sv["en"], pk("attn.e_fore")[0], G["attn.e_fore.weight"], G["attn.e_fore.bias"], T)
-        # ---- a = a(dw7(l))
+        # ---- depth gate path e = e_back(dw7(e_fore(en))) on the side stream
+        K.fork(side)
+        with torch.cuda.stream(side):
+            dec = _lin_bwd(de, sv["ec"], pk("attn.e_back")[0], G["attn.e_back.weight"], G["attn.e_back.bias"], T)
+            def_ = K.dwconv_bwd(dec, sv["ef"], P["attn.e_conv.weight"], P["attn.e_conv.bias"], B, H, W, 7, False, K.ACT_NONE,
+                                G["attn.e_conv.weight"], G["attn.e_conv.bias"])
+            den = _lin_bwd(def_, sv["en"], pk("attn.e_fore")[0], G["attn.e_fore.weight"], G["attn.e_fore.bias"], T)
+        K.share(main, den)
+        # ---- RGB path: a = a(dw7(l)), kv, pooled queries
+        K.mul_bwd(dy[:, :C], qcl[:, :C], sv["a"], dqcl[:, :C], da)
         dcv = _lin_bwd(da, sv["cv"], pk("attn.a")[0], G["attn.a.weight"], G["attn.a.bias"], T)
         dl = K.dwconv_bwd(dcv, sv["l"], P["attn.conv.weight"], P["attn.conv.bias"], B, H, W, 7, False, K.ACT_NONE,
                           G["attn.conv.weight"], G["attn.conv.bias"])
-        dxn_pool = None
+        dxn_pool = den_pool = None
         if win:
             do7 = torch.empty((B * 49, Ce), device=dev, dtype=F32)
             K.resize_bwd(dy, C, B, 7, 7, Ce, H, W, do7)
@@ -311,7 +340,6 @@ class BlockFn(torch.autograd.Function):
             dxn_pool, den_pool = K.pool7_bwd(dpooled, C, Ce, B, H, W)
             dl_kv = _lin_bwd(dkv, sv["l"], pk("attn.kv")[0], G["attn.kv.weight"], G["attn.kv.bias"], T)
             K.axpy(dl_kv, 1.0, dl)
-            K.axpy(den_pool, 1.0, den)
         K.act_bwd(dl, qcl[:, C + Ce:], K.ACT_GELU, out=dqcl[:, C + Ce:])
         qclw = pk("attn.qcl")[0]
         dWq = ar.span(st.prefix + "attn.q.weight", st.prefix + "attn.l.weight", qclw.shape)
@@ -320,6 +348,9 @@ class BlockFn(torch.autograd.Function):
         if dxn_pool is not None:
             K.axpy(dxn_pool, 1.0, dxn)
         dx = K.layernorm_bwd(dxn, sv["x"], P["attn.norm.weight"], sv["mu1"], sv["rs1"], dx1, G["attn.norm.weight"], G["attn.norm.bias"])
+        K.join(side)
+        if den_pool is not None:
+            K.axpy(den_pool, 1.0, den)
         dxe = K.layernorm_bwd(den, sv["x_e"], P["attn.norm_e.weight"], sv["mu2"], sv["rs2"], dxe1, G["attn.norm_e.weight"], G["attn.norm_e.bias"])
         if dd and dxe2 is not None:
             K.axpy(dxe2.contiguous(), 1.0, dxe)                                  # x_e passes through the last block unchanged

@@ -23,6 +23,33 @@ def _s():
     return torch.cuda.current_stream().cuda_stream
 
 
+def fork(side):
+    """side stream waits for everything enqueued so far on the current stream"""
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    side.wait_event(ev)
+
+
+def join(side):
+    """current stream waits for everything enqueued so far on the side stream"""
+    ev = torch.cuda.Event()
+    ev.record(side)
+    torch.cuda.current_stream().wait_event(ev)
+
+
+def signal(stream=None):
+    ev = torch.cuda.Event()
+    ev.record(stream if stream is not None else torch.cuda.current_stream())
+    return ev
+
+
+def share(stream, *tensors):
+    """Tell the caching allocator that tensors created on another stream are also used on `stream`."""
+    for t in tensors:
+        if t is not None:
+            t.record_stream(stream)
+
+
 def _p(t):
     return None if t is None else t.data_ptr()
 

@@ -176,6 +176,7 @@ class DFormer(nn.Module):
                       mlp_ratio=mlp_ratios[i], drop_depth=((i == 3) and (j == depths[i] - 1))) for j in range(depths[i])]))
             cur += depths[i]
         self._plan = None
+        self._side_stream = None
         self._last_arena = None
         self.grad_hook = None           # set by the data-parallel engine: callable(arena, lo, hi)
 
@@ -280,6 +281,9 @@ class DFormer(nn.Module):
                                  bn=Fn.BNState(seq[0], p + "0", training, True if sync else False))
             return Fn.DownsampleFn.apply(xx, st, *[named[p + n] for n in ("0.weight", "0.bias", "1.weight", "1.bias")])
 
+        if self._side_stream is None or self._side_stream.device != dev:
+            self._side_stream = torch.cuda.Stream(device=dev)
+        side = self._side_stream
         outs = []
         h, w = H, W
         bi = 0
@@ -296,7 +300,7 @@ class DFormer(nn.Module):
                 p = f"stages.{i}.{j}."
                 names = blk.param_names()
                 st = SimpleNamespace(dtype=T, packed=packed, key=p, arena=arena, prefix=p, tag=p, names=names, B=B, H=h, W=w,
-                                     C=self.dims[i], heads=blk.num_head, window=blk.window, drop_depth=blk.drop_depth,
+                                     C=self.dims[i], heads=blk.num_head, window=blk.window, drop_depth=blk.drop_depth, side=side,
                                      dp=(tuple(dp[bi, k] if rates[bi] > 0 else None for k in range(4)) if dp is not None else (None,) * 4))
                 x, x_e = Fn.BlockFn.apply(x, x_e, st, *[named[p + n] for n in names])
                 bi += 1
