@@ -83,6 +83,22 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return r;
 }
 
+// Blackwell packed fp32 FMA: two independent FMAs per issue slot (SASS FFMA2).  acc += a * b on (x, y) pairs.
+__device__ __forceinline__ void ffma2(float2& acc, const float2& a, const float2& b) {
+  unsigned long long c = *reinterpret_cast<unsigned long long*>(&acc);
+  const unsigned long long aa = *reinterpret_cast<const unsigned long long*>(&a);
+  const unsigned long long bb = *reinterpret_cast<const unsigned long long*>(&b);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(aa), "l"(bb));
+  acc = *reinterpret_cast<float2*>(&c);
+}
+// 8 bf16 (one 16-byte vector) -> 4 fp32 pairs (channel 2q, 2q+1): one shift / one mask per value
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float2* v) {
+  v[0] = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u));
+  v[1] = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+  v[2] = make_float2(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u));
+  v[3] = make_float2(__uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u));
+}
+
 // 8-wide vector load/store of activations as floats (16B for bf16, 32B for fp32).
 template <typename T> struct Vec8;
 template <> struct Vec8<float> {
