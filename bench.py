@@ -221,9 +221,17 @@ def main():
         tms = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms, ms_e2e = tms.tolist()
-    if rank != 0:
+    def leave():
+        # NCCL communicators captured inside a CUDA graph can stall a graceful teardown: flush and leave directly
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        leave()
         return
     hbm, tf_burst, tf_sus, how = peaks()
     n = world
@@ -257,8 +265,7 @@ def main():
         except Exception as e:  # noqa: BLE001
             out["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": f"failed: {e}"}
     print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 if __name__ == "__main__":

@@ -49,6 +49,7 @@ class BNState:
         self.weight, self.bias = mod.weight, mod.bias
         self.running_mean, self.running_var, self.nbt = mod.running_mean, mod.running_var, mod.num_batches_tracked
         self.eps, self.momentum = mod.eps, (mod.momentum if mod.momentum is not None else 0.1)
+        training = bool(training and mod.training)             # honour a per-layer .eval() (frozen statistics) like nn.Module does
         self.training = training or mod.running_mean is None
         self.prefix = prefix
         self.sync_group = sync_group if (training and dist.is_available() and dist.is_initialized() and sync_group is not False) else None

@@ -23,6 +23,11 @@ def build(precision, syncbn):
     m.load_state_dict(make_state({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=3))
     m.cuda().train()
     m.decode_head.dropout = None
+    # The reference keeps the four stem BatchNorms as plain nn.BatchNorm2d even under SyncBN (DFormer.py:196-210), so with
+    # batch statistics they are per-rank by design; freeze them (running stats) to compare N ranks against one exactly.
+    for seq in (m.encoder_backbone.downsample_layers[0], m.encoder_backbone.downsample_layers_e[0]):
+        seq[1].eval()
+        seq[4].eval()
     return m
 
 
