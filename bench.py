@@ -153,7 +153,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
-    model = EncoderDecoder(cfg_for(args.precision, "cuda"), norm_layer=nn.BatchNorm2d, syncbn=(world > 1)).to(dev).train()
+    model = EncoderDecoder(cfg_for(args.precision, "cuda"), norm_layer=nn.SyncBatchNorm if world > 1 else nn.BatchNorm2d,
+                           syncbn=(world > 1)).to(dev).train()
     model.cfg.return_logits = False        # training consumes the loss only; the fused upsample+CE never materialises 98 MB/img of logits
     opt = FusedAdamW(model, lr=6e-5, weight_decay=0.01)
     sync = GradSync(model)

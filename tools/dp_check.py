@@ -19,7 +19,8 @@ from dformer_b200.parallel import GradSync  # noqa: E402
 def build(precision, syncbn):
     cfg = SimpleNamespace(backbone="DFormer-Tiny", decoder="ham", decoder_embed_dim=512, num_classes=40, drop_path_rate=0.0, aux_rate=0.0,
                           device="cuda", pretrained_model=None, bn_eps=1e-3, bn_momentum=0.1, background=255, precision=precision)
-    m = EncoderDecoder(cfg, norm_layer=nn.BatchNorm2d, syncbn=syncbn)
+    # utils/train.py:182-194: with --syncbn the reference passes norm_layer = nn.SyncBatchNorm (so init_weight sets the head's BN eps)
+    m = EncoderDecoder(cfg, norm_layer=nn.SyncBatchNorm if syncbn else nn.BatchNorm2d, syncbn=syncbn)
     m.load_state_dict(make_state({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=3))
     m.cuda().train()
     m.decode_head.dropout = None
@@ -56,12 +57,14 @@ def main():
             ref.decode_head.injected_bases = bases.cuda()
             l2, _ = ref(rgb.cuda(), hha.cuda(), label.cuda())
             l2.backward()
-            worst = 1.0
+            worst, worst_k = 1.0, None
             for k, p in ref.named_parameters():
                 if p.grad is None or p.grad.norm() < 1e-6:
                     continue
                 cos = torch.nn.functional.cosine_similarity(p.grad.flatten().float(), grads[k].flatten().float(), dim=0).item()
-                worst = min(worst, cos)
+                if cos < worst:
+                    worst, worst_k = cos, k
+            print(f"[dp_check] worst parameter: {worst_k} |ref grad| {dict(ref.named_parameters())[worst_k].grad.norm().item():.3e}", flush=True)
             rs = {k: v for k, v in ref.state_dict().items() if k.endswith("running_var")}
             stat_err = max((rs[k] - stats[k]).abs().max().item() for k in rs)
             good = worst >= (0.999999 if precision == "fp32" else 0.99) and stat_err < tol * 10
