@@ -26,13 +26,26 @@ def _lin(x, wb, T, act=K.ACT_NONE, act_col_start=0, out=None, out_dtype=None):
                   backend=backend_for(T), K=x.shape[1])
 
 
+_WGRAD_STREAM = None      # set by BlockFn.backward: weight/bias gradients are leaves of the backward graph
+
+
 def _lin_bwd(dy, x, w, dW, db, T, need_dx=True, dx_out=None):
-    """dW[N,K] = dy^T x (fp32, into the arena), db = colsum(dy), returns dx = dy @ W."""
+    """dW[N,K] = dy^T x (fp32, into the arena), db = colsum(dy), returns dx = dy @ W.
+    The parameter gradients go to the wgrad side stream when one is active (nothing downstream consumes them)."""
     be = backend_for(T)
-    # dW lives in the zero-initialised gradient arena (or a zeroed scratch): accumulate so that split-K needs no memset
-    K.gemm(dy, x, trans_a=True, trans_b=False, out=dW, backend=be, accumulate=True)
-    if db is not None:
-        K.colsum(dy, out=db)
+    ws = _WGRAD_STREAM
+    if ws is not None:
+        ws.wait_event(K.signal())
+        dy.record_stream(ws)
+        with torch.cuda.stream(ws):
+            K.gemm(dy, x, trans_a=True, trans_b=False, out=dW, backend=be, accumulate=True)
+            if db is not None:
+                K.colsum(dy, out=db)
+    else:
+        # dW lives in the zero-initialised gradient arena (or a zeroed scratch): accumulate so that split-K needs no memset
+        K.gemm(dy, x, trans_a=True, trans_b=False, out=dW, backend=be, accumulate=True)
+        if db is not None:
+            K.colsum(dy, out=db)
     if not need_dx:
         return None
     return K.gemm(dy, w, trans_a=False, trans_b=False, out=dx_out, out_dtype=T, backend=be, N=w.shape[1])
@@ -199,7 +212,7 @@ def _mlp_bwd(dout, pfx, st, P, sv, scale_b, G):
     w2 = st.packed[st.key + pfx + "fc2"][0]
     du = _lin_bwd(df, sv[pfx + "u"], w2, G[pfx + "fc2.weight"], G[pfx + "fc2.bias"], T)
     dh = K.dwconv_bwd(du, sv[pfx + "h"], P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, True, K.ACT_GELU,
-                      G[pfx + "pos.weight"], G[pfx + "pos.bias"], z=sv[pfx + "z"])
+                      G[pfx + "pos.weight"], G[pfx + "pos.bias"], z=sv[pfx + "z"], wgrad_stream=_WGRAD_STREAM)
     w1 = st.packed[st.key + pfx + "fc1"][0]
     dhn = _lin_bwd(dh, sv[pfx + "hn"], w1, G[pfx + "fc1.weight"], G[pfx + "fc1.bias"], T)
     return K.layernorm_bwd(dhn, sv[pfx + "x"], P[pfx + "norm.weight"], sv[pfx + "mu"], sv[pfx + "rs"], dout,
@@ -239,19 +252,25 @@ class BlockFn(torch.autograd.Function):
         xn, mu1, rs1 = K.layernorm_fwd(x, P["attn.norm.weight"], P["attn.norm.bias"], 1e-6, T)
         qcl = _lin(xn, pk("attn.qcl"), T)                                         # [M, 2.5C] = q | cut | z_l
         l = K.act_fwd(qcl[:, C + Ce:], K.ACT_GELU)
-        cv = K.dwconv_fwd(l, P["attn.conv.weight"], P["attn.conv.bias"], B, H, W, 7)
-        a = _lin(cv, pk("attn.a"), T)
         ycols = 2 * C if win else C + Ce
         y = torch.empty((M, ycols), device=x.device, dtype=T)
+        if win:                                                       # global-awareness branch on a second side stream
+            side2 = st.side2
+            K.fork(side2)
+            with torch.cuda.stream(side2):
+                kv = _lin(l, pk("attn.kv"), T)
+                side2.wait_event(ev_en)
+                pooled = K.pool7_fwd(xn, en, B, H, W)
+                m = _lin(pooled, pk("attn.short_cut_linear"), T)
+                o7, probs = K.gaa_fwd(m, kv, B, HW, st.heads, Ce // st.heads)
+                K.resize_fwd(o7, B, 7, 7, y, H, W, col0=C)
+            K.share(main, kv, pooled, m, probs, o7)
+            sv.update(kv=kv, pooled=pooled, m=m, probs=probs)
+        cv = K.dwconv_fwd(l, P["attn.conv.weight"], P["attn.conv.bias"], B, H, W, 7)
+        a = _lin(cv, pk("attn.a"), T)
         K.mul_fwd(qcl[:, :C], a, y[:, :C])
         if win:
-            kv = _lin(l, pk("attn.kv"), T)
-            main.wait_event(ev_en)
-            pooled = K.pool7_fwd(xn, en, B, H, W)
-            m = _lin(pooled, pk("attn.short_cut_linear"), T)
-            o7, probs = K.gaa_fwd(m, kv, B, HW, st.heads, Ce // st.heads)
-            K.resize_fwd(o7, B, 7, 7, y, H, W, col0=C)
-            sv.update(kv=kv, pooled=pooled, m=m, probs=probs)
+            K.join(side2)
         main.wait_event(ev_e)
         K.mul_fwd(qcl[:, C:C + Ce], e, y[:, ycols - Ce:])
         pp = _lin(y, pk("attn.pp"), T)                                            # [M, C (+Ce)] = proj | proj_e
@@ -285,8 +304,11 @@ class BlockFn(torch.autograd.Function):
         win, dd = st.window != 0, st.drop_depth
         pk = lambda n: st.packed[st.key + n]
         dev = sv["x"].device
-        side = st.side
+        side, side2, wstream = st.side, st.side2, st.wstream
         main = torch.cuda.current_stream()
+        global _WGRAD_STREAM
+        _WGRAD_STREAM = wstream
+        K.fork(wstream)                                             # wgrad stream starts after the arena memset / previous module
         dx2 = dx2.contiguous()
         ppw = pk("attn.pp")[0]
         dpp = torch.empty((M, ppw.shape[0]), device=dev, dtype=T)
@@ -322,24 +344,30 @@ class BlockFn(torch.autograd.Function):
         with torch.cuda.stream(side):
             dec = _lin_bwd(de, sv["ec"], pk("attn.e_back")[0], G["attn.e_back.weight"], G["attn.e_back.bias"], T)
             def_ = K.dwconv_bwd(dec, sv["ef"], P["attn.e_conv.weight"], P["attn.e_conv.bias"], B, H, W, 7, False, K.ACT_NONE,
-                                G["attn.e_conv.weight"], G["attn.e_conv.bias"])
+                                G["attn.e_conv.weight"], G["attn.e_conv.bias"], wgrad_stream=_WGRAD_STREAM)
             den = _lin_bwd(def_, sv["en"], pk("attn.e_fore")[0], G["attn.e_fore.weight"], G["attn.e_fore.bias"], T)
         K.share(main, den)
-        # ---- RGB path: a = a(dw7(l)), kv, pooled queries
+        # ---- global-awareness branch (resize^T -> attention -> pooled queries / kv) on a second side stream
+        dxn_pool = den_pool = dl_kv = None
+        if win:
+            K.fork(side2)
+            with torch.cuda.stream(side2):
+                do7 = torch.empty((B * 49, Ce), device=dev, dtype=F32)
+                K.resize_bwd(dy, C, B, 7, 7, Ce, H, W, do7)
+                dm, dkv = K.gaa_bwd(do7, sv["m"], sv["kv"], sv["probs"], B, HW, st.heads, Ce // st.heads)
+                dmT = dm if T == F32 else K.cast(dm, T)
+                dpooled = _lin_bwd(dmT, sv["pooled"], pk("attn.short_cut_linear")[0], G["attn.short_cut_linear.weight"],
+                                   G["attn.short_cut_linear.bias"], T)
+                dxn_pool, den_pool = K.pool7_bwd(dpooled, C, Ce, B, H, W)
+                dl_kv = _lin_bwd(dkv, sv["l"], pk("attn.kv")[0], G["attn.kv.weight"], G["attn.kv.bias"], T)
+            K.share(main, dxn_pool, den_pool, dl_kv)
+        # ---- RGB path: a = a(dw7(l))
         K.mul_bwd(dy[:, :C], qcl[:, :C], sv["a"], dqcl[:, :C], da)
         dcv = _lin_bwd(da, sv["cv"], pk("attn.a")[0], G["attn.a.weight"], G["attn.a.bias"], T)
         dl = K.dwconv_bwd(dcv, sv["l"], P["attn.conv.weight"], P["attn.conv.bias"], B, H, W, 7, False, K.ACT_NONE,
-                          G["attn.conv.weight"], G["attn.conv.bias"])
-        dxn_pool = den_pool = None
+                          G["attn.conv.weight"], G["attn.conv.bias"], wgrad_stream=_WGRAD_STREAM)
         if win:
-            do7 = torch.empty((B * 49, Ce), device=dev, dtype=F32)
-            K.resize_bwd(dy, C, B, 7, 7, Ce, H, W, do7)
-            dm, dkv = K.gaa_bwd(do7, sv["m"], sv["kv"], sv["probs"], B, HW, st.heads, Ce // st.heads)
-            dmT = dm if T == F32 else K.cast(dm, T)
-            dpooled = _lin_bwd(dmT, sv["pooled"], pk("attn.short_cut_linear")[0], G["attn.short_cut_linear.weight"],
-                               G["attn.short_cut_linear.bias"], T)
-            dxn_pool, den_pool = K.pool7_bwd(dpooled, C, Ce, B, H, W)
-            dl_kv = _lin_bwd(dkv, sv["l"], pk("attn.kv")[0], G["attn.kv.weight"], G["attn.kv.bias"], T)
+            K.join(side2)
             K.axpy(dl_kv, 1.0, dl)
         K.act_bwd(dl, qcl[:, C + Ce:], K.ACT_GELU, out=dqcl[:, C + Ce:])
         qclw = pk("attn.qcl")[0]
@@ -355,6 +383,8 @@ class BlockFn(torch.autograd.Function):
         dxe = K.layernorm_bwd(den, sv["x_e"], P["attn.norm_e.weight"], sv["mu2"], sv["rs2"], dxe1, G["attn.norm_e.weight"], G["attn.norm_e.bias"])
         if dd and dxe2 is not None:
             K.axpy(dxe2.contiguous(), 1.0, dxe)                                  # x_e passes through the last block unchanged
+        _WGRAD_STREAM = None
+        K.join(wstream)                                                          # all parameter gradients of this Block are final
         ctx.sv = ctx.P = None
         ar.done(st.tag)
         return (dx, dxe, None) + tuple(G[n] for n in st.names)

@@ -173,12 +173,24 @@ def dwconv_fwd(x, weight, bias, B, H, W, k, add_input=False, act=ACT_NONE, save_
     return (y, z) if save_z else y
 
 
-def dwconv_bwd(dy, x, weight, bias, B, H, W, k, add_input, act, dweight, dbias, need_dx=True, z=None):
+def dwconv_bwd(dy, x, weight, bias, B, H, W, k, add_input, act, dweight, dbias, need_dx=True, z=None, wgrad_stream=None):
+    """dx (and dz) on the current stream; the weight/bias gradient optionally on `wgrad_stream` (it is a leaf of the
+    backward graph: nothing downstream waits for it except the end-of-module join)."""
     C = x.shape[-1]
     dz = torch.empty_like(dy) if act != ACT_NONE else None
     dx = torch.empty_like(dy) if need_dx else None
+    if wgrad_stream is None:
+        lib().dwconv_bwd(dy.data_ptr(), x.data_ptr(), _p(z), dt(x), weight.data_ptr(), _p(bias), B, H, W, C, k, int(add_input), act,
+                         _p(dz), _p(dx), dweight.data_ptr(), dbias.data_ptr(), _s())
+        return dx
     lib().dwconv_bwd(dy.data_ptr(), x.data_ptr(), _p(z), dt(x), weight.data_ptr(), _p(bias), B, H, W, C, k, int(add_input), act,
-                     _p(dz), _p(dx), dweight.data_ptr(), dbias.data_ptr(), _s())
+                     _p(dz), _p(dx), None, None, _s())
+    g = dz if dz is not None else dy
+    wgrad_stream.wait_event(signal())
+    g.record_stream(wgrad_stream)
+    with torch.cuda.stream(wgrad_stream):
+        lib().dwconv_bwd(g.data_ptr(), x.data_ptr(), None, dt(x), weight.data_ptr(), _p(bias), B, H, W, C, k, int(add_input), ACT_NONE,
+                         None, None, dweight.data_ptr(), dbias.data_ptr(), _s())
     return dx
 
 

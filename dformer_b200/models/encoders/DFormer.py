@@ -281,9 +281,9 @@ class DFormer(nn.Module):
                                  bn=Fn.BNState(seq[0], p + "0", training, True if sync else False))
             return Fn.DownsampleFn.apply(xx, st, *[named[p + n] for n in ("0.weight", "0.bias", "1.weight", "1.bias")])
 
-        if self._side_stream is None or self._side_stream.device != dev:
-            self._side_stream = torch.cuda.Stream(device=dev)
-        side = self._side_stream
+        if self._side_stream is None or self._side_stream[0].device != dev:
+            self._side_stream = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
+        side, side2, wstream = self._side_stream
         outs = []
         h, w = H, W
         bi = 0
@@ -300,7 +300,7 @@ class DFormer(nn.Module):
                 p = f"stages.{i}.{j}."
                 names = blk.param_names()
                 st = SimpleNamespace(dtype=T, packed=packed, key=p, arena=arena, prefix=p, tag=p, names=names, B=B, H=h, W=w,
-                                     C=self.dims[i], heads=blk.num_head, window=blk.window, drop_depth=blk.drop_depth, side=side,
+                                     C=self.dims[i], heads=blk.num_head, window=blk.window, drop_depth=blk.drop_depth, side=side, side2=side2, wstream=wstream,
                                      dp=(tuple(dp[bi, k] if rates[bi] > 0 else None for k in range(4)) if dp is not None else (None,) * 4))
                 x, x_e = Fn.BlockFn.apply(x, x_e, st, *[named[p + n] for n in names])
                 bi += 1
