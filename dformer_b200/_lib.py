@@ -24,6 +24,8 @@ class GemmArgs(ctypes.Structure):
         ("act", c_int), ("act_col_start", c_int),
         ("accumulate", c_int), ("backend", c_int), ("splitk", c_int),
         ("alpha", c_float),
+        ("epi_mode", c_int), ("aux", c_void_p), ("ld_aux", c_long), ("out2", c_void_p), ("ld_out2", c_long),
+        ("ls", c_void_p), ("scale_b", c_void_p), ("rows_per_sample", c_int),
     ]
 
 

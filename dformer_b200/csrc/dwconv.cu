@@ -132,6 +132,9 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 constexpr int TL_TX = 32, TL_TY = 8, TL_TW = 4, TL_TH = 2;    // tile 8 x 32 pixels, thread 2 x 4 pixels -> 256 threads
 
@@ -382,16 +385,35 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const T* __restrict__
 // x halo tile and the dz tile are staged in shared memory with cp.async, and worker (cv, ky, part) slides a K-wide
 // register window along 8-pixel row segments: acc[kx] += dz[p] * x[p + (ky-R, kx-R)].  Partials live in registers
 // across all of the CTA's tiles and leave through shared-memory atomics + one global atomicAdd per (channel, tap).
-template <int K>
+template <int K, bool DB>
+__device__ __forceinline__ void wgrad_issue_tile(uint4* xt, uint4* zt, const bf16* __restrict__ dz, const bf16* __restrict__ x, int tile_id, int tiles_x,
+                                                 int tiles_y, int H, int W, int C, int c_base, int nv) {
+  const int tx0 = (tile_id % tiles_x) * TL_TX, ty0 = ((tile_id / tiles_x) % tiles_y) * TL_TY, b = tile_id / (tiles_x * tiles_y);
+  load_halo_tile_async<K>(xt, x, b, ty0, tx0, H, W, C, c_base, nv);
+#pragma unroll
+  for (int it = 0; it < TL_TY * TL_TX * 8 / 256; ++it) {
+    const int i = threadIdx.x + it * 256;
+    const int v = i & 7, px = (i >> 3) % TL_TX, py = (i >> 3) / TL_TX;
+    const int gy = ty0 + py, gx = tx0 + px;
+    const bool ok = v < nv && gy < H && gx < W;
+    const bf16* src = ok ? dz + (((long)b * H + gy) * W + gx) * C + c_base + v * 8 : dz;
+    cp_async16(zt + i, src, ok);
+  }
+  cp_async_commit();
+}
+
+// DB = true: the CTA double-buffers its tiles (prefetch of tile i+1 overlaps the FMAs of tile i); used where the
+// shared-memory footprint allows only one CTA per SM (7x7), otherwise two resident CTAs provide the overlap.
+template <int K, bool DB>
 __global__ void __launch_bounds__(256) dwconv_wgrad_tiled_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ x, int B, int H, int W, int C,
                                                                 float* __restrict__ dweight, float* __restrict__ dbias, int tiles_x, int tiles_y) {
   constexpr int R = K / 2, SW = TL_TX + K - 1, SH = TL_TY + K - 1;
   constexpr int P = 32 / K;                          // parts per kernel row (k=3: 10, k=7: 4)
   constexpr int ITEMS = TL_TY * (TL_TX / 8);         // (row, 8-pixel segment) items per tile = 32
+  constexpr int BUF_VECS = SH * SW * 8 + TL_TY * TL_TX * 8;
   extern __shared__ __align__(16) uint8_t dsm[];
-  uint4* xt = reinterpret_cast<uint4*>(dsm);                                   // [SH][SW][8]
-  uint4* zt = xt + SH * SW * 8;                                                // [TY][TX][8]
-  float* red = reinterpret_cast<float*>(zt + TL_TY * TL_TX * 8);               // [K][8][K*8+8]
+  uint4* buf0 = reinterpret_cast<uint4*>(dsm);                                 // per buffer: x halo [SH][SW][8] + dz [TY][TX][8]
+  float* red = reinterpret_cast<float*>(buf0 + (DB ? 2 : 1) * BUF_VECS);       // [K][8][K*8+8]
   const int c_base = blockIdx.y * 64;
   const int nv = min(64, C - c_base) >> 3;
   const int cv = threadIdx.x & 7, wk = threadIdx.x >> 3;
@@ -406,20 +428,25 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_tiled_kernel(const bf16* __r
 #pragma unroll
   for (int j = 0; j < 8; ++j) accb[j] = 0.f;
   const int n_tiles = B * tiles_x * tiles_y;
+  int cur = 0;
+  if (DB) wgrad_issue_tile<K, DB>(buf0, buf0 + SH * SW * 8, dz, x, blockIdx.x, tiles_x, tiles_y, H, W, C, c_base, nv);
   for (int tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
-    const int tx0 = (tile_id % tiles_x) * TL_TX, ty0 = ((tile_id / tiles_x) % tiles_y) * TL_TY, b = tile_id / (tiles_x * tiles_y);
-    __syncthreads();                                 // previous tile fully consumed
-    load_halo_tile_async<K>(xt, x, b, ty0, tx0, H, W, C, c_base, nv);
-#pragma unroll
-    for (int it = 0; it < TL_TY * TL_TX * 8 / 256; ++it) {
-      const int i = threadIdx.x + it * 256;
-      const int v = i & 7, px = (i >> 3) % TL_TX, py = (i >> 3) / TL_TX;
-      const int gy = ty0 + py, gx = tx0 + px;
-      const bool ok = v < nv && gy < H && gx < W;
-      const bf16* src = ok ? dz + (((long)b * H + gy) * W + gx) * C + c_base + v * 8 : dz;
-      cp_async16(zt + i, src, ok);
+    uint4* xt = buf0 + cur * BUF_VECS;
+    uint4* zt = xt + SH * SW * 8;
+    if (DB) {
+      const int next = tile_id + gridDim.x;
+      if (next < n_tiles) {
+        uint4* nx = buf0 + (cur ^ 1) * BUF_VECS;
+        wgrad_issue_tile<K, DB>(nx, nx + SH * SW * 8, dz, x, next, tiles_x, tiles_y, H, W, C, c_base, nv);
+        cp_async_wait_group<1>();                    // everything but the prefetch just issued has landed
+      } else {
+        cp_async_wait_group<0>();
+      }
+    } else {
+      __syncthreads();                               // previous tile fully consumed
+      wgrad_issue_tile<K, DB>(xt, zt, dz, x, tile_id, tiles_x, tiles_y, H, W, C, c_base, nv);
+      cp_async_wait_group<0>();
     }
-    cp_async_wait_all();
     __syncthreads();
     if (worker) {
       for (int item = part; item < ITEMS; item += P) {
@@ -449,6 +476,10 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_tiled_kernel(const bf16* __r
         }
       }
     }
+    if (DB) {
+      __syncthreads();                               // buffer `cur` is free again before the next prefetch overwrites it
+      cur ^= 1;
+    }
   }
   __syncthreads();
   if (worker) {
@@ -476,20 +507,21 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_tiled_kernel(const bf16* __r
 template <int K>
 int launch_wgrad_tiled(const bf16* dz, const bf16* x, int B, int H, int W, int C, float* dweight, float* dbias, cudaStream_t st) {
   constexpr int SW = TL_TX + K - 1, SH = TL_TY + K - 1;
-  constexpr int smem = (SH * SW * 8 + TL_TY * TL_TX * 8) * 16 + K * 8 * (K * 8 + 8) * 4;
+  constexpr bool DB = (K == 7);
+  constexpr int smem = (DB ? 2 : 1) * (SH * SW * 8 + TL_TY * TL_TX * 8) * 16 + K * 8 * (K * 8 + 8) * 4;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv_wgrad_tiled_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(dwconv_wgrad_tiled_kernel<K, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { dfb_set_error("dwconv wgrad smem attr: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
     attr = true;
   }
   const int tiles_x = dfb_cdiv(W, TL_TX), tiles_y = dfb_cdiv(H, TL_TY);
   const int n_tiles = B * tiles_x * tiles_y, chunks = dfb_cdiv(C, 64);
-  int gx = dfb_cdiv(148 * 2, chunks);                 // ~2 CTAs per SM over all channel slabs
+  int gx = dfb_cdiv(148 * (DB ? 1 : 2), chunks);      // one (double-buffered) or two CTAs per SM over all channel slabs
   if (gx > n_tiles) gx = n_tiles;
   if (gx < 1) gx = 1;
   dim3 grid(gx, chunks);
-  dwconv_wgrad_tiled_kernel<K><<<grid, 256, smem, st>>>(dz, x, B, H, W, C, dweight, dbias, tiles_x, tiles_y);
+  dwconv_wgrad_tiled_kernel<K, DB><<<grid, 256, smem, st>>>(dz, x, B, H, W, C, dweight, dbias, tiles_x, tiles_y);
   return dfb_check_launch("dwconv_wgrad_tiled");
 }
 

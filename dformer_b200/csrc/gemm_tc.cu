@@ -45,6 +45,7 @@ struct TcParams {
   void* C; long ldc;
   const float* bias;
   int out_bf16, act, act_col_start, accumulate;
+  int epi_mode; const void* aux; long ld_aux; void* out2; long ld_out2; const float* ls; const float* scale_b; int rows_per_sample;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -309,12 +310,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               st[lane * 4 + (u ^ ((lane >> 1) & 3))] = pk;
             }
             __syncwarp();
-            bf16* base = reinterpret_cast<bf16*>(p.C) + c_off + (long)(m_blk * BM + quad * 32) * p.ldc + col0;
+            const int row_base = m_blk * BM + quad * 32;
+            bf16* base = reinterpret_cast<bf16*>(p.C) + c_off + (long)row_base * p.ldc + col0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int rr = 8 * i + (lane >> 2), u = lane & 3;
-              const uint4 pk = st[rr * 4 + (u ^ ((rr >> 1) & 3))];
+              uint4 pk = st[rr * 4 + (u ^ ((rr >> 1) & 3))];
+              const long grow = row_base + rr;
+              const int gcol = col0 + u * 8;
+              if (p.epi_mode == 1) {              // dz = du * gelu'(z): the saved pre-activation is read in the coalesced store pattern
+                float f[8], z[8];
+                Vec8<bf16>::unpack(pk, f);
+                Vec8<bf16>::load(reinterpret_cast<const bf16*>(p.aux) + grow * p.ld_aux + gcol, z);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] *= gelu_grad_f(z[j]);
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+              }
               *reinterpret_cast<uint4*>(base + (long)rr * p.ldc + u * 8) = pk;
+              if (p.epi_mode == 2) {              // x_new = res + DropPath-scale * layer_scale * f  (fp32 residual stream)
+                float f[8], r8[8], l8[8];
+                Vec8<bf16>::unpack(pk, f);
+                Vec8<float>::load(reinterpret_cast<const float*>(p.aux) + grow * p.ld_aux + gcol, r8);
+                Vec8<float>::load(p.ls + gcol, l8);
+                const float sb = p.scale_b ? __ldg(p.scale_b + grow / p.rows_per_sample) : 1.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r8[j] = fmaf(sb * l8[j], f[j], r8[j]);
+                Vec8<float>::store(reinterpret_cast<float*>(p.out2) + grow * p.ld_out2 + gcol, r8);
+              }
+            }
+          } else if (p.epi_mode != 0) {           // tails of the fused epilogues: per element
+            const float sb = (p.epi_mode == 2 && p.scale_b) ? __ldg(p.scale_b + row / p.rows_per_sample) : 1.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < ncols) {
+                float f = __bfloat162float(__float2bfloat16_rn(v[j]));
+                if (p.epi_mode == 1) {
+                  f *= gelu_grad_f(__bfloat162float(reinterpret_cast<const bf16*>(p.aux)[(long)row * p.ld_aux + col0 + j]));
+                  dst[j] = __float2bfloat16_rn(f);
+                } else {
+                  dst[j] = __float2bfloat16_rn(f);
+                  const float r = reinterpret_cast<const float*>(p.aux)[(long)row * p.ld_aux + col0 + j];
+                  reinterpret_cast<float*>(p.out2)[(long)row * p.ld_out2 + col0 + j] = fmaf(sb * p.ls[col0 + j], f, r);
+                }
+              }
             }
           } else if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
@@ -449,6 +489,12 @@ bool dfb_gemm_tc_supported(const dfb200_gemm_args& g) {
   if ((g.lda % 8) || (g.ldb % 8)) return false;
   if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) return false;
   if (g.accumulate && g.out_dtype != 0) return false;
+  if (g.epi_mode != 0) {
+    if (g.out_dtype != 1 || g.batch != 1 || g.splitk > 1 || g.accumulate || g.act != 0 || g.aux == nullptr) return false;
+    if ((g.ld_aux % 8) || (reinterpret_cast<uintptr_t>(g.aux) & 15)) return false;
+    if (g.epi_mode == 2 && (g.out2 == nullptr || g.ls == nullptr || (g.ld_out2 % 8) || g.rows_per_sample <= 0)) return false;
+    if (g.epi_mode < 0 || g.epi_mode > 2) return false;
+  }
   return true;
 }
 
@@ -475,12 +521,14 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   p.b_mn_major = g.transB ? 0 : 1;   // B stored [K, N]  -> N contiguous
   p.C = g.C; p.ldc = g.ldc; p.bias = g.bias;
   p.batch = g.batch; p.strideC = g.strideC;
+  p.epi_mode = g.epi_mode; p.aux = g.aux; p.ld_aux = g.ld_aux; p.out2 = g.out2; p.ld_out2 = g.ld_out2;
+  p.ls = g.ls; p.scale_b = g.scale_b; p.rows_per_sample = g.rows_per_sample;
   p.out_bf16 = g.out_dtype == 1; p.act = g.act; p.act_col_start = g.act_col_start; p.accumulate = g.accumulate;
   // split-K when the output has too few tiles to fill the machine and the reduction is long (wgrad)
   int splits = 1;
   const long tiles = (long)p.m_tiles * p.n_tiles * g.batch;
   if (g.splitk > 1) splits = g.splitk;
-  else if (g.splitk == 0 && g.out_dtype == 0 && g.act == 0 && tiles * 2 <= num_sms && p.kb_total >= 16)
+  else if (g.splitk == 0 && g.out_dtype == 0 && g.act == 0 && g.epi_mode == 0 && tiles * 2 <= num_sms && p.kb_total >= 16)
     splits = (int)min((long)p.kb_total / 4, (long)(num_sms / tiles));
   if (splits < 1) splits = 1;
   if (splits > 1) DFB_REQUIRE(g.out_dtype == 0 && g.act == 0, "gemm_tc split-K needs fp32 output without activation");

@@ -29,7 +29,7 @@ def _lin(x, wb, T, act=K.ACT_NONE, act_col_start=0, out=None, out_dtype=None):
 _WGRAD_STREAM = None      # set by BlockFn.backward: weight/bias gradients are leaves of the backward graph
 
 
-def _lin_bwd(dy, x, w, dW, db, T, need_dx=True, dx_out=None):
+def _lin_bwd(dy, x, w, dW, db, T, need_dx=True, dx_out=None, dx_epi=None):
     """dW[N,K] = dy^T x (fp32, into the arena), db = colsum(dy), returns dx = dy @ W.
     The parameter gradients go to the wgrad side stream when one is active (nothing downstream consumes them)."""
     be = backend_for(T)
@@ -48,7 +48,7 @@ def _lin_bwd(dy, x, w, dW, db, T, need_dx=True, dx_out=None):
             K.colsum(dy, out=db)
     if not need_dx:
         return None
-    return K.gemm(dy, w, trans_a=False, trans_b=False, out=dx_out, out_dtype=T, backend=be, N=w.shape[1])
+    return K.gemm(dy, w, trans_a=False, trans_b=False, out=dx_out, out_dtype=T, backend=be, N=w.shape[1], epi=dx_epi)
 
 
 def _views(arena: GradArena, prefix: str, names):
@@ -196,9 +196,14 @@ def _mlp_fwd(x, pfx, st, P, sv, scale_b):
     hn, mu, rs = K.layernorm_fwd(x, P[pfx + "norm.weight"], P[pfx + "norm.bias"], 1e-6, T)
     h = _lin(hn, st.packed[st.key + pfx + "fc1"], T)
     u, z = K.dwconv_fwd(h, P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, add_input=True, act=K.ACT_GELU, save_z=True)
-    f = _lin(u, st.packed[st.key + pfx + "fc2"], T)
     ls = P["layer_scale_2" if pfx == "mlp." else "layer_scale_2_e"]
-    out = K.scale_residual_fwd(x, f, ls, scale_b, H * W)
+    if T == torch.bfloat16:      # fc2 + bias + layer-scale/DropPath residual in one tcgen05 epilogue (f kept for the dls gradient)
+        w2, b2 = st.packed[st.key + pfx + "fc2"]
+        out = torch.empty_like(x)
+        f = K.gemm(u, w2, trans_b=True, bias=b2, out_dtype=T, backend=K.TCGEN05, epi=("residual", x, out, ls, scale_b, H * W))
+    else:
+        f = _lin(u, st.packed[st.key + pfx + "fc2"], T)
+        out = K.scale_residual_fwd(x, f, ls, scale_b, H * W)
     sv.update({pfx + "x": x, pfx + "mu": mu, pfx + "rs": rs, pfx + "hn": hn, pfx + "h": h, pfx + "u": u, pfx + "f": f, pfx + "z": z})
     return out
 
@@ -210,9 +215,14 @@ def _mlp_bwd(dout, pfx, st, P, sv, scale_b, G):
     lsn = "layer_scale_2" if pfx == "mlp." else "layer_scale_2_e"
     df = K.scale_residual_bwd(dout, sv[pfx + "f"], P[lsn], scale_b, H * W, G[lsn])
     w2 = st.packed[st.key + pfx + "fc2"][0]
-    du = _lin_bwd(df, sv[pfx + "u"], w2, G[pfx + "fc2.weight"], G[pfx + "fc2.bias"], T)
-    dh = K.dwconv_bwd(du, sv[pfx + "h"], P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, True, K.ACT_GELU,
-                      G[pfx + "pos.weight"], G[pfx + "pos.bias"], z=sv[pfx + "z"], wgrad_stream=_WGRAD_STREAM)
+    if T == torch.bfloat16:      # dz = (df @ W2) * gelu'(z) in the dgrad GEMM's epilogue
+        dz = _lin_bwd(df, sv[pfx + "u"], w2, G[pfx + "fc2.weight"], G[pfx + "fc2.bias"], T, dx_epi=("gelu_grad", sv[pfx + "z"]))
+        dh = K.dwconv_bwd(dz, sv[pfx + "h"], P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, True, K.ACT_NONE,
+                          G[pfx + "pos.weight"], G[pfx + "pos.bias"], wgrad_stream=_WGRAD_STREAM)
+    else:
+        du = _lin_bwd(df, sv[pfx + "u"], w2, G[pfx + "fc2.weight"], G[pfx + "fc2.bias"], T)
+        dh = K.dwconv_bwd(du, sv[pfx + "h"], P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, True, K.ACT_GELU,
+                          G[pfx + "pos.weight"], G[pfx + "pos.bias"], z=sv[pfx + "z"], wgrad_stream=_WGRAD_STREAM)
     w1 = st.packed[st.key + pfx + "fc1"][0]
     dhn = _lin_bwd(dh, sv[pfx + "hn"], w1, G[pfx + "fc1.weight"], G[pfx + "fc1.bias"], T)
     return K.layernorm_bwd(dhn, sv[pfx + "x"], P[pfx + "norm.weight"], sv[pfx + "mu"], sv[pfx + "rs"], dout,

@@ -64,7 +64,8 @@ GEMM_PROFILE = None      # bench.py sets this to a list to time every GEMM launc
 
 
 def gemm(a, b, *, trans_a=False, trans_b=True, bias=None, out=None, out_dtype=None, act=ACT_NONE, act_col_start=0,
-         accumulate=False, backend=AUTO, splitk=0, alpha=0.0, M=None, N=None, K=None):
+         accumulate=False, backend=AUTO, splitk=0, alpha=0.0, M=None, N=None, K=None, epi=None):
+    # epi = ("gelu_grad", z) | ("residual", res_f32, out2_f32, ls, scale_b, rows_per_sample): fused tcgen05 epilogues
     """out[M,N] = act(alpha * op(a) @ op(b) + bias).  a/b are 2-D with unit inner stride (row slices allowed)."""
     _chk(a), _chk(b)
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
@@ -86,6 +87,13 @@ def gemm(a, b, *, trans_a=False, trans_b=True, bias=None, out=None, out_dtype=No
     g.transA, g.transB = int(trans_a), int(trans_b)
     g.a_dtype, g.b_dtype, g.out_dtype = dt(a), dt(b), dt(out)
     g.act, g.act_col_start, g.accumulate, g.backend, g.splitk, g.alpha = act, act_col_start, int(accumulate), backend, splitk, alpha
+    if epi is not None:
+        if epi[0] == "gelu_grad":
+            g.epi_mode, g.aux, g.ld_aux = 1, epi[1].data_ptr(), epi[1].stride(0)
+        else:
+            _, res, out2, ls, scale_b, rps = epi
+            g.epi_mode, g.aux, g.ld_aux, g.out2, g.ld_out2 = 2, res.data_ptr(), res.stride(0), out2.data_ptr(), out2.stride(0)
+            g.ls, g.scale_b, g.rows_per_sample = ls.data_ptr(), _p(scale_b), rps
     if GEMM_PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -55,6 +55,14 @@ typedef struct dfb200_gemm_args {
   int backend;
   int splitk;            /* 0 = auto, 1 = off, >1 = forced number of reduction splits */
   float alpha;           /* scales the product before bias/activation (0 is treated as 1) */
+  /* fused epilogues of the tcgen05 backend (bf16 output):
+   *   epi_mode 1: C = bf16(acc + bias) * gelu'(aux[m,n])              aux: bf16 pre-activation (MLP backward, DFormer.py:64)
+   *   epi_mode 2: C = f = bf16(acc + bias);  out2[m,n] = aux[m,n] + scale_b[m / rows_per_sample] * ls[n] * f
+   *               aux: fp32 residual, out2: fp32 new residual (layer-scale + DropPath residual, DFormer.py:173-179) */
+  int epi_mode;
+  const void* aux; long ld_aux;
+  void* out2; long ld_out2;
+  const float* ls; const float* scale_b; int rows_per_sample;
 } dfb200_gemm_args;
 int dfb200_gemm(const dfb200_gemm_args* args, void* stream);
 
