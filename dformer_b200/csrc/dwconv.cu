@@ -5,6 +5,8 @@
 // One thread = 8 channels (one 16-byte bf16 vector) x TW consecutive output pixels of a row, so each
 // input vector fetched from L1/L2 is reused for up to TW taps of the sliding window; weights for the
 // CTA's 64-channel slab sit in shared memory.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "dfb200_internal.h"
 
@@ -504,10 +506,9 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_tiled_kernel(const bf16* __r
   }
 }
 
-template <int K>
+template <int K, bool DB>
 int launch_wgrad_tiled(const bf16* dz, const bf16* x, int B, int H, int W, int C, float* dweight, float* dbias, cudaStream_t st) {
   constexpr int SW = TL_TX + K - 1, SH = TL_TY + K - 1;
-  constexpr bool DB = (K == 7);
   constexpr int smem = (DB ? 2 : 1) * (SH * SW * 8 + TL_TY * TL_TX * 8) * 16 + K * 8 * (K * 8 + 8) * 4;
   static bool attr = false;
   if (!attr) {
@@ -556,6 +557,12 @@ extern "C" int dfb200_dwconv_fwd(const void* x, int dtype, const float* weight, 
   });
 }
 
+static bool wgrad7_db() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DFB200_WGRAD7_DB"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+
 extern "C" int dfb200_dwconv_bwd(const void* dy, const void* x, const void* z, int dtype, const float* weight, const float* bias, int B, int H, int W,
                                  int C, int k, int add_input, int act, void* dz_buf, void* dx, float* dweight, float* dbias, void* stream) {
   DFB_REQUIRE(C % 8 == 0, "dwconv: C %% 8 != 0 (C=%d)", C);
@@ -587,8 +594,9 @@ extern "C" int dfb200_dwconv_bwd(const void* dy, const void* x, const void* z, i
     }
     if (dweight) {
       if constexpr (sizeof(T) == 2) {
-        return k == 3 ? launch_wgrad_tiled<3>((const bf16*)dz, (const bf16*)x, B, H, W, C, dweight, dbias, ST)
-                      : launch_wgrad_tiled<7>((const bf16*)dz, (const bf16*)x, B, H, W, C, dweight, dbias, ST);
+        if (k == 3) return launch_wgrad_tiled<3, false>((const bf16*)dz, (const bf16*)x, B, H, W, C, dweight, dbias, ST);
+        return wgrad7_db() ? launch_wgrad_tiled<7, true>((const bf16*)dz, (const bf16*)x, B, H, W, C, dweight, dbias, ST)
+                           : launch_wgrad_tiled<7, false>((const bf16*)dz, (const bf16*)x, B, H, W, C, dweight, dbias, ST);
       }
       if (k == 3) dwconv_wgrad_kernel<T, 3><<<wgrid, 256, 0, ST>>>(dz, (const T*)x, B, H, W, C, dweight, dbias, ppb);
       else dwconv_wgrad_kernel<T, 7><<<wgrid, 256, 0, ST>>>(dz, (const T*)x, B, H, W, C, dweight, dbias, ppb);

@@ -17,6 +17,11 @@ from . import kernels as K
 from .runtime import GradArena, backend_for
 
 F32 = torch.float32
+import os as _os
+# fused GEMM epilogues exist (gemm_tc.cu epi_mode 1/2) but measured slower on B200 for these wide-N / short-K GEMMs, whose
+# epilogue is already the critical resource (A/B in profiles/r01_ab_fused_epilogues.txt) -> off by default
+_FUSE_RES = _os.environ.get("DFB200_FUSE_RES", "0") == "1"
+_FUSE_GG = _os.environ.get("DFB200_FUSE_GG", "0") == "1"
 
 
 # ============================================================================================ helpers
@@ -197,7 +202,7 @@ def _mlp_fwd(x, pfx, st, P, sv, scale_b):
     h = _lin(hn, st.packed[st.key + pfx + "fc1"], T)
     u, z = K.dwconv_fwd(h, P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, add_input=True, act=K.ACT_GELU, save_z=True)
     ls = P["layer_scale_2" if pfx == "mlp." else "layer_scale_2_e"]
-    if T == torch.bfloat16:      # fc2 + bias + layer-scale/DropPath residual in one tcgen05 epilogue (f kept for the dls gradient)
+    if T == torch.bfloat16 and _FUSE_RES:      # fc2 + bias + layer-scale/DropPath residual in one tcgen05 epilogue (f kept for the dls gradient)
         w2, b2 = st.packed[st.key + pfx + "fc2"]
         out = torch.empty_like(x)
         f = K.gemm(u, w2, trans_b=True, bias=b2, out_dtype=T, backend=K.TCGEN05, epi=("residual", x, out, ls, scale_b, H * W))
@@ -215,7 +220,7 @@ def _mlp_bwd(dout, pfx, st, P, sv, scale_b, G):
     lsn = "layer_scale_2" if pfx == "mlp." else "layer_scale_2_e"
     df = K.scale_residual_bwd(dout, sv[pfx + "f"], P[lsn], scale_b, H * W, G[lsn])
     w2 = st.packed[st.key + pfx + "fc2"][0]
-    if T == torch.bfloat16:      # dz = (df @ W2) * gelu'(z) in the dgrad GEMM's epilogue
+    if T == torch.bfloat16 and _FUSE_GG:      # dz = (df @ W2) * gelu'(z) in the dgrad GEMM's epilogue
         dz = _lin_bwd(df, sv[pfx + "u"], w2, G[pfx + "fc2.weight"], G[pfx + "fc2.bias"], T, dx_epi=("gelu_grad", sv[pfx + "z"]))
         dh = K.dwconv_bwd(dz, sv[pfx + "h"], P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, True, K.ACT_NONE,
                           G[pfx + "pos.weight"], G[pfx + "pos.bias"], wgrad_stream=_WGRAD_STREAM)
