@@ -26,14 +26,13 @@ namespace {
 
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 64;           // 64 bf16 = one 128-byte swizzle row
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 8;                     // ring depth is chosen per launch: as deep as shared memory allows for this BN
 constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16 KB
-constexpr int B_STAGE_BYTES = 256 * BK * 2;       // 32 KB (BN <= 256)
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int MAX_SMEM = 227 * 1024;
 constexpr int TMEM_COLS = 512;   // 2 accumulator stages x 256 fp32 columns
 constexpr int NUM_THREADS = 320;         // TMA warp + MMA warp + 8 epilogue warps
 constexpr int EPI_STAGE_BYTES = 8 * 4096;         // per-epilogue-warp 32 x 128 B staging tile for coalesced stores
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = MAX_SMEM;
 
 struct TcParams {
   int M, N, K;               // problem (K = reduction length)
@@ -41,7 +40,7 @@ struct TcParams {
   int m_tiles, n_tiles, splits, kb_per_split, kb_total;
   int a_mn_major, b_mn_major;
   int batch; long strideC;
-  int stages;
+  int stages, stage_bytes;
   void* C; long ldc;
   const float* bias;
   int out_bf16, act, act_col_start, accumulate;
@@ -131,10 +130,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* epi_stage = smem + p.stages * STAGE_BYTES;
+  uint8_t* epi_stage = smem + p.stages * p.stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;     // [2]
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + MAX_STAGES;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -173,7 +172,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb0 = sp * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sa = smem + stage * p.stage_bytes;
           uint8_t* sb = sa + A_STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], stage_tx);
           if (p.a_mn_major) {
@@ -210,7 +209,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
           const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
@@ -555,9 +554,13 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   // pipeline depth: no deeper than the k-loop of one tile needs (smaller smem request for the many short-K GEMMs)
   static int forced_stages = -1;
   if (forced_stages < 0) { const char* e = getenv("DFB200_TC_STAGES"); forced_stages = e ? atoi(e) : 0; }
-  p.stages = forced_stages > 0 ? forced_stages : STAGES;
-  if (p.stages > STAGES) p.stages = STAGES;
-  const int smem_bytes = p.stages * STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 256;
+  const int b_bytes = p.b_mn_major ? ((p.BN + 63) / 64) * 8192 : ((p.BN * 128 + 1023) / 1024) * 1024;   // 1024-B aligned (swizzle atom)
+  p.stage_bytes = A_STAGE_BYTES + b_bytes;
+  const int fixed = EPI_STAGE_BYTES + 1024 + 512;
+  p.stages = (MAX_SMEM - fixed) / p.stage_bytes;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  if (forced_stages > 0 && forced_stages < p.stages) p.stages = forced_stages;
+  const int smem_bytes = p.stages * p.stage_bytes + fixed;
   gemm_tc_kernel<<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmB, p);
   return dfb_check_launch("gemm_tc");
 }

@@ -38,12 +38,17 @@ def main():
 
 def tiny(reps=200):
     dev = "cuda"
-    for (M, N, K) in [(128, 64, 64), (144, 432, 392), (9600, 144, 144), (9600, 288, 288), (2400, 576, 576)]:
-        a = torch.randn(M, K, device=dev).bfloat16()
-        b = torch.randn(N, K, device=dev).bfloat16()
-        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    cases = [(128, 64, 64, 0, 1), (128, 64, 448, 0, 1), (128, 64, 1792, 0, 1), (128, 64, 448, 1, 0), (144, 432, 392, 1, 0), (144, 432, 392, 0, 1),
+             (128, 256, 448, 0, 1), (9600, 144, 144, 0, 1), (9600, 288, 288, 0, 1), (2400, 576, 576, 0, 1)]
+    for (M, N, K, ta, tb) in cases:
+        a = (torch.randn(K, M, device=dev) if ta else torch.randn(M, K, device=dev)).bfloat16()
+        b = (torch.randn(N, K, device=dev) if tb else torch.randn(K, N, device=dev)).bfloat16()
+        out = torch.zeros(M, N, device=dev, dtype=torch.float32 if ta else torch.bfloat16)
+        _g = k.gemm
+        def gemm_call(a=a, b=b, out=out, ta=ta, tb=tb):
+            _g(a, b, trans_a=bool(ta), trans_b=bool(tb), backend=k.TCGEN05, out=out, accumulate=bool(ta))
         for _ in range(5):
-            k.gemm(a, b, trans_b=True, backend=k.TCGEN05, out=out)
+            gemm_call()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g = torch.cuda.CUDAGraph()
@@ -51,14 +56,14 @@ def tiny(reps=200):
         with torch.cuda.stream(s):
             with torch.cuda.graph(g, stream=s):
                 for _ in range(reps):
-                    k.gemm(a, b, trans_b=True, backend=k.TCGEN05, out=out)
+                    gemm_call()
         g.replay()
         torch.cuda.synchronize()
         e0.record()
         g.replay()
         e1.record()
         torch.cuda.synchronize()
-        print(f"tiny M={M} N={N} K={K}: {e0.elapsed_time(e1) / reps * 1e3:.2f} us per back-to-back launch (CUDA graph of {reps})", flush=True)
+        print(f"tiny M={M} N={N} K={K} ta={ta} tb={tb}: {e0.elapsed_time(e1) / reps * 1e3:.2f} us per back-to-back launch (CUDA graph of {reps})", flush=True)
 
 
 if __name__ == "__main__":
