@@ -150,6 +150,54 @@ __global__ void resize_bwd_kernel(const TO* __restrict__ dout, long ldo, int col
   }
 }
 
+// Adjoint for strong up-sampling (7x7 -> HxW): one warp per (input pixel, 8-channel vector); the lanes split the candidate
+// output window (hundreds of pixels) and combine with shuffles, instead of one thread walking the whole window.
+template <typename TO, typename TI>
+__global__ void __launch_bounds__(256) resize_bwd_warp_kernel(const TO* __restrict__ dout, long ldo, int col0, int B, int Hi, int Wi, int C, int Ho, int Wo,
+                                                             TI* __restrict__ din, int accumulate) {
+  const int nvec = C >> 3;
+  const long n = (long)B * Hi * Wi * nvec;
+  const float ry = (float)Ho / (float)Hi, rx = (float)Wo / (float)Wi;
+  const int lane = threadIdx.x & 31;
+  for (long i = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += (long)gridDim.x * (blockDim.x >> 5)) {
+    const int c = (int)(i % nvec) * 8;
+    const long pix = i / nvec;
+    const int ix = (int)(pix % Wi), iy = (int)((pix / Wi) % Hi), b = (int)(pix / ((long)Wi * Hi));
+    int oy_lo = max(0, (int)floorf((iy - 1) * ry) - 1), oy_hi = min(Ho - 1, (int)ceilf((iy + 2) * ry) + 1);
+    int ox_lo = max(0, (int)floorf((ix - 1) * rx) - 1), ox_hi = min(Wo - 1, (int)ceilf((ix + 2) * rx) + 1);
+    if (iy == 0) oy_lo = 0;
+    if (iy == Hi - 1) oy_hi = Ho - 1;
+    if (ix == 0) ox_lo = 0;
+    if (ix == Wi - 1) ox_hi = Wo - 1;
+    const int nx = ox_hi - ox_lo + 1, total = (oy_hi - oy_lo + 1) * nx;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = lane; t < total; t += 32) {
+      const int oy = oy_lo + t / nx, ox = ox_lo + t % nx;
+      const Lerp ly = lerp_coord(oy, Hi, Ho), lx = lerp_coord(ox, Wi, Wo);
+      const float wy = (ly.i0 == iy ? 1.f - ly.w1 : 0.f) + (ly.i1 == iy ? ly.w1 : 0.f);
+      const float wx = (lx.i0 == ix ? 1.f - lx.w1 : 0.f) + (lx.i1 == ix ? lx.w1 : 0.f);
+      const float w = wy * wx;
+      if (w == 0.f) continue;
+      float g[8];
+      Vec8<TO>::load(dout + (((long)b * Ho + oy) * Wo + ox) * ldo + col0 + c, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, g[j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) {
+      TI* dst = din + pix * C + c;
+      if (accumulate) {
+        float old[8];
+        Vec8<TI>::load(dst, old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += old[j];
+      }
+      Vec8<TI>::store(dst, acc);
+    }
+  }
+}
+
 inline int ew_grid(long n) {
   long b = (n + 255) / 256;
   if (b < 1) b = 1;
@@ -204,8 +252,14 @@ extern "C" int dfb200_resize_fwd(const void* in, int in_dtype, int B, int Hi, in
 extern "C" int dfb200_resize_bwd(const void* dout, int out_dtype, long ldo, int col0, int B, int Hi, int Wi, int C, int Ho, int Wo, void* din, int in_dtype,
                                  int accumulate, void* stream) {
   DFB_REQUIRE(C % 8 == 0 && ldo % 8 == 0 && col0 % 8 == 0, "resize: C, ldo, col0 must be multiples of 8");
-  const int g = ew_grid((long)B * Hi * Wi * C / 8);
-#define L(TO, TI) resize_bwd_kernel<TO, TI><<<g, 256, 0, ST>>>((const TO*)dout, ldo, col0, B, Hi, Wi, C, Ho, Wo, (TI*)din, accumulate)
+  const long work = (long)B * Hi * Wi * C / 8;
+  const bool coop = ((long)Ho * Wo >= 16L * Hi * Wi);              // >= 4x up-sampling per axis: hundreds of candidates per input pixel
+  const int g = coop ? (int)min(work / 8 + 1, 148L * 16) : ew_grid(work);
+#define L(TO, TI)                                                                                                                        \
+  do {                                                                                                                                   \
+    if (coop) resize_bwd_warp_kernel<TO, TI><<<g, 256, 0, ST>>>((const TO*)dout, ldo, col0, B, Hi, Wi, C, Ho, Wo, (TI*)din, accumulate); \
+    else resize_bwd_kernel<TO, TI><<<g, 256, 0, ST>>>((const TO*)dout, ldo, col0, B, Hi, Wi, C, Ho, Wo, (TI*)din, accumulate);           \
+  } while (0)
   if (in_dtype == 0 && out_dtype == 0) L(float, float);
   else if (in_dtype == 0 && out_dtype == 1) L(bf16, float);
   else if (in_dtype == 1 && out_dtype == 1) L(bf16, bf16);

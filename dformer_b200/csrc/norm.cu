@@ -110,6 +110,151 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
   for (int c = threadIdx.x; c < C; c += blockDim.x) { atomicAdd(dgamma + c, sm[c]); atomicAdd(dbeta + c, sm[C + c]); }
 }
 
+// ------------------------------------------------------------------ vectorised LayerNorm (C % 8 == 0)
+// L lanes cooperate on one row (L = 8, 16 or 32 so that small C still fills the warp with several rows); each lane owns
+// VPL 8-channel vectors -> every global access is a 16/32-byte vector and the row stays in registers.
+template <int L>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = L >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T, int L, int VPL>
+__global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                         int M, int C, T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+  constexpr int RPW = 32 / L;
+  const int lane = threadIdx.x & 31, sub = lane % L, rsel = lane / L;
+  const int nvec = C >> 3;
+  const int groups_per_block = (blockDim.x >> 5) * RPW;
+  float gm[VPL][8], bt[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = sub + i * L;
+    if (v < nvec) { Vec8<float>::load(gamma + v * 8, gm[i]); Vec8<float>::load(beta + v * 8, bt[i]); }
+  }
+  const float invC = 1.f / (float)C;
+  for (long row = (long)blockIdx.x * groups_per_block + (threadIdx.x >> 5) * RPW + rsel; row < M; row += (long)gridDim.x * groups_per_block) {
+    const float* xr = x + row * C;
+    float v[VPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vv = sub + i * L;
+      if (vv < nvec) {
+        Vec8<float>::load(xr + vv * 8, v[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i][j];
+      }
+    }
+    const float mu = group_sum<L>(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      if (sub + i * L < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mu; q = fmaf(d, d, q); }
+      }
+    }
+    const float rs = rsqrtf(group_sum<L>(q) * invC + eps);
+    if (sub == 0) { mean[row] = mu; rstd[row] = rs; }
+    T* yr = y + row * C;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vv = sub + i * L;
+      if (vv < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mu) * rs * gm[i][j] + bt[i][j];
+        Vec8<T>::store(yr + vv * 8, o);
+      }
+    }
+  }
+}
+
+template <typename T, int L, int VPL>
+__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ mean, const float* __restrict__ rstd, int M, int C, const float* dx_in,
+                                                         float* dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float sm[];   // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  constexpr int RPW = 32 / L;
+  const int lane = threadIdx.x & 31, sub = lane % L, rsel = lane / L;
+  const int nvec = C >> 3;
+  const int groups_per_block = (blockDim.x >> 5) * RPW;
+  float gm[VPL][8], pg[VPL][8], pb[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = sub + i * L;
+    if (v < nvec) Vec8<float>::load(gamma + v * 8, gm[i]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { pg[i][j] = 0.f; pb[i][j] = 0.f; }
+  }
+  const float invC = 1.f / (float)C;
+  for (long row = (long)blockIdx.x * groups_per_block + (threadIdx.x >> 5) * RPW + rsel; row < M; row += (long)gridDim.x * groups_per_block) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[VPL][8], g[VPL][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vv = sub + i * L;
+      if (vv < nvec) {
+        float d[8], xv[8];
+        Vec8<T>::load(dy + row * C + vv * 8, d);
+        Vec8<float>::load(x + row * C + vv * 8, xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (xv[j] - mu) * rs;
+          g[i][j] = d[j] * gm[i][j];
+          pg[i][j] = fmaf(d[j], xh[i][j], pg[i][j]);
+          pb[i][j] += d[j];
+          s1 += g[i][j];
+          s2 = fmaf(g[i][j], xh[i][j], s2);
+        }
+      }
+    }
+    s1 = group_sum<L>(s1) * invC;
+    s2 = group_sum<L>(s2) * invC;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vv = sub + i * L;
+      if (vv < nvec) {
+        float o[8];
+        if (dx_in) Vec8<float>::load(dx_in + row * C + vv * 8, o);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += rs * (g[i][j] - s1 - xh[i][j] * s2);
+        Vec8<float>::store(dx + row * C + vv * 8, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vv = sub + i * L;
+    if (vv < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { atomicAdd(&sm[vv * 8 + j], pg[i][j]); atomicAdd(&sm[C + vv * 8 + j], pb[i][j]); }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { atomicAdd(dgamma + c, sm[c]); atomicAdd(dbeta + c, sm[C + c]); }
+}
+
+#define LN_DISPATCH_VEC(C, ...)                                                            \
+  do {                                                                                     \
+    const int nvec_ = (C) >> 3;                                                            \
+    if (nvec_ <= 8) { constexpr int L = 8, VPL = 1; __VA_ARGS__ }                          \
+    else if (nvec_ <= 16) { constexpr int L = 16, VPL = 1; __VA_ARGS__ }                   \
+    else if (nvec_ <= 32) { constexpr int L = 32, VPL = 1; __VA_ARGS__ }                   \
+    else if (nvec_ <= 64) { constexpr int L = 32, VPL = 2; __VA_ARGS__ }                   \
+    else if (nvec_ <= 96) { constexpr int L = 32, VPL = 3; __VA_ARGS__ }                   \
+    else { constexpr int L = 32, VPL = 4; __VA_ARGS__ }                                    \
+  } while (0)
+
 #define LN_DISPATCH_NPL(C, ...)                                      \
   do {                                                               \
     const int npl_ = ((C) + 31) / 32;                                \
@@ -304,6 +449,10 @@ extern "C" int dfb200_layernorm_fwd(const float* x, const float* gamma, const fl
   DFB_REQUIRE(C >= 1 && C <= 32 * LN_MAX_PER_LANE, "layernorm: C=%d out of range", C);
   if (M <= 0) return DFB_OK;
   const int grid = min(dfb_cdiv(M, 8), 148 * 8);
+  if (C % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    DFB_DISPATCH_DTYPE(y_dtype, T, { LN_DISPATCH_VEC(C, { ln_fwd_vec_kernel<T, L, VPL><<<grid, 256, 0, ST>>>(x, gamma, beta, eps, M, C, (T*)y, mean, rstd); }); });
+    return dfb_check_launch("layernorm_fwd_vec");
+  }
   DFB_DISPATCH_DTYPE(y_dtype, T, { LN_DISPATCH_NPL(C, { ln_fwd_kernel<T, NPL><<<grid, 256, 0, ST>>>(x, gamma, beta, eps, M, C, (T*)y, mean, rstd); }); });
   return dfb_check_launch("layernorm_fwd");
 }
@@ -313,6 +462,12 @@ extern "C" int dfb200_layernorm_bwd(const void* dy, int dy_dtype, const float* x
   DFB_REQUIRE(C >= 1 && C <= 32 * LN_MAX_PER_LANE, "layernorm: C=%d out of range", C);
   if (M <= 0) return DFB_OK;
   const int grid = min(dfb_cdiv(M, 8), 148 * 8);
+  if (C % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dx_in)) & 15) == 0) {
+    DFB_DISPATCH_DTYPE(dy_dtype, T, {
+      LN_DISPATCH_VEC(C, { ln_bwd_vec_kernel<T, L, VPL><<<grid, 256, 2 * C * sizeof(float), ST>>>((const T*)dy, x, gamma, mean, rstd, M, C, dx_in, dx, dgamma, dbeta); });
+    });
+    return dfb_check_launch("layernorm_bwd_vec");
+  }
   DFB_DISPATCH_DTYPE(dy_dtype, T, {
     LN_DISPATCH_NPL(C, { ln_bwd_kernel<T, NPL><<<grid, 256, 2 * C * sizeof(float), ST>>>((const T*)dy, x, gamma, mean, rstd, M, C, dx_in, dx, dgamma, dbeta); });
   });
