@@ -134,8 +134,11 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict
     if (v < nvec) { Vec8<float>::load(gamma + v * 8, gm[i]); Vec8<float>::load(beta + v * 8, bt[i]); }
   }
   const float invC = 1.f / (float)C;
-  for (long row = (long)blockIdx.x * groups_per_block + (threadIdx.x >> 5) * RPW + rsel; row < M; row += (long)gridDim.x * groups_per_block) {
-    const float* xr = x + row * C;
+  // the trip count is warp-uniform (shuffles below use the full mask); rows past M are masked, not skipped
+  for (long row0 = (long)blockIdx.x * groups_per_block + (threadIdx.x >> 5) * RPW; row0 < M; row0 += (long)gridDim.x * groups_per_block) {
+    const long row = row0 + rsel;
+    const bool valid = row < M;
+    const float* xr = x + (valid ? row : 0) * C;
     float v[VPL][8];
     float s = 0.f;
 #pragma unroll
@@ -157,6 +160,7 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict
       }
     }
     const float rs = rsqrtf(group_sum<L>(q) * invC + eps);
+    if (!valid) continue;
     if (sub == 0) { mean[row] = mu; rstd[row] = rs; }
     T* yr = y + row * C;
 #pragma unroll
@@ -192,14 +196,16 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const T* __restrict__ d
     for (int j = 0; j < 8; ++j) { pg[i][j] = 0.f; pb[i][j] = 0.f; }
   }
   const float invC = 1.f / (float)C;
-  for (long row = (long)blockIdx.x * groups_per_block + (threadIdx.x >> 5) * RPW + rsel; row < M; row += (long)gridDim.x * groups_per_block) {
-    const float mu = mean[row], rs = rstd[row];
+  for (long row0 = (long)blockIdx.x * groups_per_block + (threadIdx.x >> 5) * RPW; row0 < M; row0 += (long)gridDim.x * groups_per_block) {
+    const long row = row0 + rsel;
+    const bool valid = row < M;                     // warp-uniform trip count; masked rows contribute zeros
+    const float mu = valid ? mean[row] : 0.f, rs = valid ? rstd[row] : 0.f;
     float xh[VPL][8], g[VPL][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int vv = sub + i * L;
-      if (vv < nvec) {
+      if (vv < nvec && valid) {
         float d[8], xv[8];
         Vec8<T>::load(dy + row * C + vv * 8, d);
         Vec8<float>::load(x + row * C + vv * 8, xv);
@@ -216,6 +222,7 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const T* __restrict__ d
     }
     s1 = group_sum<L>(s1) * invC;
     s2 = group_sum<L>(s2) * invC;
+    if (!valid) continue;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int vv = sub + i * L;
