@@ -33,7 +33,7 @@ __device__ __forceinline__ float interp_logit(const T* __restrict__ base, int w,
 template <typename T>
 __global__ void __launch_bounds__(256) upsample_ce_fwd_kernel(const T* __restrict__ small, int B, int h, int w, int ncls, int H, int W,
                                                               const int64_t* __restrict__ label, int ignore, float* __restrict__ out,
-                                                              float* __restrict__ lse_out, float* loss_acc) {
+                                                              float* __restrict__ lse_out, float* loss_acc, T* __restrict__ up_lowp) {
   __shared__ float red[32];
   float loss = 0.f, cnt = 0.f;
   const long n = (long)B * H * W;
@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) upsample_ce_fwd_kernel(const T* __restric
     for (int c = 0; c < ncls; ++c) {
       const float v = interp_logit(base, w, ncls, ly, lx, c);
       if (out) out[((long)b * ncls + c) * H * W + (long)y * W + x] = v;
+      if (up_lowp) up_lowp[((long)b * ncls + c) * H * W + (long)y * W + x] = from_f<T>(v);
       if (v > m) { s = s * __expf(m - v) + 1.f; m = v; } else { s += __expf(v - m); }
       if ((long)c == lab) picked = v;
     }
@@ -103,18 +104,72 @@ __global__ void upsample_ce_bwd_kernel(const T* __restrict__ small, int B, int h
   }
 }
 
+// ---- separable adjoint.  Pass 1 (rows): t[b,c,ly,ox] = sum_oy wy(ly,oy) * (softmax(up)[b,c,oy,ox] - onehot) * valid
+template <typename TU>
+__global__ void upsample_ce_bwd_rows_kernel(const TU* __restrict__ up, int B, int h, int ncls, int H, int W, const int64_t* __restrict__ label, int ignore,
+                                            const float* __restrict__ lse, float* __restrict__ t) {
+  const long n = (long)B * ncls * h * W;
+  const float ry = (float)H / (float)h;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % W);
+    const int ly = (int)((i / W) % h);
+    const int c = (int)((i / ((long)W * h)) % ncls);
+    const int b = (int)(i / ((long)W * h * ncls));
+    int oy_lo = max(0, (int)floorf((ly - 1) * ry) - 1), oy_hi = min(H - 1, (int)ceilf((ly + 2) * ry) + 1);
+    if (ly == 0) oy_lo = 0;
+    if (ly == h - 1) oy_hi = H - 1;
+    float acc = 0.f;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      const Lerp l = lerp_coord(oy, h, H);
+      const float wy = (l.i0 == ly ? 1.f - l.w1 : 0.f) + (l.i1 == ly ? l.w1 : 0.f);
+      if (wy == 0.f) continue;
+      const long hp = ((long)b * H + oy) * W + ox;
+      const long lab = label[hp];
+      if (lab == (long)ignore || lab < 0 || lab >= ncls) continue;
+      float g = __expf(to_f(up[((long)b * ncls + c) * H * W + (long)oy * W + ox]) - lse[hp]);
+      if ((long)c == lab) g -= 1.f;
+      acc = fmaf(wy, g, acc);
+    }
+    t[i] = acc;
+  }
+}
+// Pass 2 (columns): ds[b,ly,lx,c] = scale * sum_ox wx(lx,ox) * t[b,c,ly,ox]
+template <typename TD>
+__global__ void upsample_ce_bwd_cols_kernel(const float* __restrict__ t, int B, int h, int w, int ncls, int W, const float* __restrict__ loss_acc,
+                                            const float* __restrict__ dloss, TD* __restrict__ dsmall) {
+  const long n = (long)B * h * w * ncls;
+  const float gscale = dloss[0] / loss_acc[1];
+  const float rx = (float)W / (float)w;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ncls);
+    const long pix = i / ncls;
+    const int lx = (int)(pix % w), ly = (int)((pix / w) % h), b = (int)(pix / ((long)w * h));
+    int ox_lo = max(0, (int)floorf((lx - 1) * rx) - 1), ox_hi = min(W - 1, (int)ceilf((lx + 2) * rx) + 1);
+    if (lx == 0) ox_lo = 0;
+    if (lx == w - 1) ox_hi = W - 1;
+    const float* row = t + (((long)b * ncls + c) * h + ly) * W;
+    float acc = 0.f;
+    for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+      const Lerp l = lerp_coord(ox, w, W);
+      const float wx = (l.i0 == lx ? 1.f - l.w1 : 0.f) + (l.i1 == lx ? l.w1 : 0.f);
+      acc = fmaf(wx, row[ox], acc);
+    }
+    dsmall[i] = from_f<TD>(acc * gscale);
+  }
+}
+
 }  // namespace
 
 #define ST reinterpret_cast<cudaStream_t>(stream)
 
 extern "C" int dfb200_upsample_ce_fwd(const void* logits_small, int dtype, int B, int h, int w, int ncls, int H, int W, const int64_t* label, int ignore,
-                                      float* out_nchw, float* lse, float* loss_acc, void* stream) {
+                                      float* out_nchw, float* lse, float* loss_acc, void* up_lowp, void* stream) {
   const long n = (long)B * H * W;
   long g = (n + 255) / 256;
   if (g > 148L * 16) g = 148L * 16;
   if (g < 1) g = 1;
   DFB_DISPATCH_DTYPE(dtype, T, {
-    upsample_ce_fwd_kernel<T><<<(int)g, 256, 0, ST>>>((const T*)logits_small, B, h, w, ncls, H, W, label, ignore, out_nchw, lse, loss_acc);
+    upsample_ce_fwd_kernel<T><<<(int)g, 256, 0, ST>>>((const T*)logits_small, B, h, w, ncls, H, W, label, ignore, out_nchw, lse, loss_acc, (T*)up_lowp);
   });
   return dfb_check_launch("upsample_ce_fwd");
 }
@@ -122,6 +177,21 @@ extern "C" int dfb200_upsample_ce_fwd(const void* logits_small, int dtype, int B
 extern "C" int dfb200_ce_finalize(const float* loss_acc, float* loss, void* stream) {
   ce_finalize_kernel<<<1, 1, 0, ST>>>(loss_acc, loss);
   return dfb_check_launch("ce_finalize");
+}
+
+extern "C" int dfb200_upsample_ce_bwd_sep(const void* up, int up_dtype, int B, int h, int w, int ncls, int H, int W, const int64_t* label, int ignore,
+                                          const float* lse, const float* loss_acc, const float* dloss, float* scratch, void* dlogits_small, int dl_dtype,
+                                          void* stream) {
+  const long n1 = (long)B * ncls * h * W, n2 = (long)B * h * w * ncls;
+  long g1 = (n1 + 255) / 256, g2 = (n2 + 255) / 256;
+  if (g1 > 148L * 32) g1 = 148L * 32;
+  if (g1 < 1) g1 = 1;
+  if (g2 < 1) g2 = 1;
+  DFB_DISPATCH_DTYPE(up_dtype, TU, { upsample_ce_bwd_rows_kernel<TU><<<(int)g1, 256, 0, ST>>>((const TU*)up, B, h, ncls, H, W, label, ignore, lse, scratch); });
+  int rc = dfb_check_launch("upsample_ce_bwd_rows");
+  if (rc) return rc;
+  DFB_DISPATCH_DTYPE(dl_dtype, TD, { upsample_ce_bwd_cols_kernel<TD><<<(int)g2, 256, 0, ST>>>(scratch, B, h, w, ncls, W, loss_acc, dloss, (TD*)dlogits_small); });
+  return dfb_check_launch("upsample_ce_bwd_cols");
 }
 
 extern "C" int dfb200_upsample_ce_bwd(const void* logits_small, int dtype, int B, int h, int w, int ncls, int H, int W, const int64_t* label, int ignore,

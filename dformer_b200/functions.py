@@ -583,8 +583,10 @@ class UpsampleCEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, small, label, meta):
         B, h, w, ncls, H, W, ignore, want_out = meta
-        out, lse, acc, loss = K.upsample_ce_fwd(small, B, h, w, ncls, H, W, label, ignore, want_out=want_out, want_loss=label is not None)
+        out, lse, acc, loss, up = K.upsample_ce_fwd(small, B, h, w, ncls, H, W, label, ignore, want_out=want_out, want_loss=label is not None,
+                                                    keep_up=bool(ctx.needs_input_grad[0]))
         ctx.meta = meta
+        ctx.up = up
         if label is not None:
             ctx.save_for_backward(small, label, lse, acc)
         if out is None:
@@ -599,7 +601,11 @@ class UpsampleCEFn(torch.autograd.Function):
         B, h, w, ncls, H, W, ignore, _ = ctx.meta
         small, label, lse, acc = ctx.saved_tensors
         dl = dloss.contiguous().float()
-        ds = K.upsample_ce_bwd(small, B, h, w, ncls, H, W, label, ignore, lse, acc, dl)
+        if ctx.up is not None:
+            ds = K.upsample_ce_bwd_sep(ctx.up, small.dtype, B, h, w, ncls, H, W, label, ignore, lse, acc, dl)
+            ctx.up = None
+        else:
+            ds = K.upsample_ce_bwd(small, B, h, w, ncls, H, W, label, ignore, lse, acc, dl)
         return ds, None, None
 
 

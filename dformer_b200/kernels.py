@@ -393,17 +393,33 @@ def axpy(x, alpha, y):
     return y
 
 
-def upsample_ce_fwd(small, B, h, w, ncls, H, W, label, ignore, want_out=True, want_loss=True):
+def upsample_ce_fwd(small, B, h, w, ncls, H, W, label, ignore, want_out=True, want_loss=True, keep_up=False):
+    """keep_up: also keep the up-sampled logits in small's dtype for the separable backward (the fp32 `out` doubles as
+    that copy when small is fp32 and out is requested)."""
     dev = small.device
     out = torch.empty((B, ncls, H, W), device=dev, dtype=torch.float32) if want_out else None
     lse = torch.empty((B, H, W), device=dev, dtype=torch.float32) if want_loss else None
     acc = torch.zeros(2, device=dev, dtype=torch.float32) if want_loss else None
-    lib().upsample_ce_fwd(small.data_ptr(), dt(small), B, h, w, ncls, H, W, _p(label), ignore, _p(out), _p(lse), _p(acc), _s())
+    up = None
+    if keep_up and want_loss:
+        up = out if (out is not None and small.dtype == torch.float32) else torch.empty((B, ncls, H, W), device=dev, dtype=small.dtype)
+    lib().upsample_ce_fwd(small.data_ptr(), dt(small), B, h, w, ncls, H, W, _p(label), ignore, _p(out), _p(lse), _p(acc),
+                          _p(up) if up is not out else None, _s())
     loss = None
     if want_loss:
         loss = torch.empty((), device=dev, dtype=torch.float32)
         lib().ce_finalize(acc.data_ptr(), loss.data_ptr(), _s())
+    if keep_up:
+        return out, lse, acc, loss, up
     return out, lse, acc, loss
+
+
+def upsample_ce_bwd_sep(up, small_dtype, B, h, w, ncls, H, W, label, ignore, lse, acc, dloss):
+    dsmall = torch.empty((B * h * w, ncls), device=up.device, dtype=small_dtype)
+    scratch = torch.empty((B, ncls, h, W), device=up.device, dtype=torch.float32)
+    lib().upsample_ce_bwd_sep(up.data_ptr(), dt(up), B, h, w, ncls, H, W, label.data_ptr(), ignore, lse.data_ptr(), acc.data_ptr(),
+                              dloss.data_ptr(), scratch.data_ptr(), dsmall.data_ptr(), dt(dsmall), _s())
+    return dsmall
 
 
 def upsample_ce_bwd(small, B, h, w, ncls, H, W, label, ignore, lse, acc, dloss):

@@ -288,14 +288,18 @@ class DFormer(nn.Module):
         h, w = H, W
         bi = 0
         for i in range(4):
+            # the two modality streams are independent here: the depth stem / downsample runs on the side stream
+            main = torch.cuda.current_stream()
+            Fn.K.fork(side)
+            with torch.cuda.stream(side):
+                x_e = stem(x_e, "_e", 1) if i == 0 else down(x_e, "_e", i, h, w)
+            x_e.record_stream(main)
+            x = stem(x, "", 3) if i == 0 else down(x, "", i, h, w)
             if i == 0:
-                x = stem(x, "", 3)
-                x_e = stem(x_e, "_e", 1)
                 h, w = ((h + 1) // 2 + 1) // 2, ((w + 1) // 2 + 1) // 2
             else:
-                x = down(x, "", i, h, w)
-                x_e = down(x_e, "_e", i, h, w)
                 h, w = (h + 1) // 2, (w + 1) // 2
+            Fn.K.join(side)
             for j, blk in enumerate(self.stages[i]):
                 p = f"stages.{i}.{j}."
                 names = blk.param_names()

@@ -195,9 +195,16 @@ int dfb200_axpy(const void* x, int x_dtype, float alpha, void* y, int y_dtype, l
  * dfb200_ce_finalize (device scalar, no host sync). */
 int dfb200_upsample_ce_fwd(const void* logits_small, int dtype, int B, int h, int w, int ncls, int H, int W,
                            const int64_t* label, int ignore, float* out_nchw, float* lse /* [B,H,W] */, float* loss_acc,
+                           void* up_lowp /* optional [B,ncls,H,W] copy of the up-sampled logits in `dtype` (kept for backward) */,
                            void* stream);
 int dfb200_ce_finalize(const float* loss_acc, float* loss, void* stream);
 /* dlogits_small [B,h,w,ncls] = resize^T( (softmax(up) - onehot) * dloss / valid )  (gather form, deterministic) */
+/* Separable (rows, then columns) form of the same adjoint, fed by the up-sampled logits `up` [B,ncls,H,W] (dtype up_dtype)
+ * that the forward kernel can emit: each hi-res probability is evaluated once instead of once per overlapping footprint.
+ * scratch: B*ncls*h*W floats. */
+int dfb200_upsample_ce_bwd_sep(const void* up, int up_dtype, int B, int h, int w, int ncls, int H, int W, const int64_t* label,
+                               int ignore, const float* lse, const float* loss_acc, const float* dloss, float* scratch,
+                               void* dlogits_small, int dl_dtype, void* stream);
 int dfb200_upsample_ce_bwd(const void* logits_small, int dtype, int B, int h, int w, int ncls, int H, int W,
                            const int64_t* label, int ignore, const float* lse, const float* loss_acc, const float* dloss,
                            void* dlogits_small, int dl_dtype, void* stream);

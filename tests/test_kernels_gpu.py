@@ -381,6 +381,11 @@ def test_upsample_ce(dtype, ncls):
     ds = k.upsample_ce_bwd(small.view(-1, ncls), B, h, w, ncls, H, W, label, 255, lse, acc, dl)
     t = dict(rtol=3e-2, atol=1e-5) if dtype == torch.bfloat16 else dict(rtol=1e-3, atol=1e-7)
     torch.testing.assert_close(ds.view(B, h, w, ncls).float(), sr.grad.permute(0, 2, 3, 1), **t)
+    # separable form fed by the kept up-sampled logits
+    out2, lse2, acc2, loss2, up = k.upsample_ce_fwd(small.view(-1, ncls), B, h, w, ncls, H, W, label, 255, want_out=False, keep_up=True)
+    ds2 = k.upsample_ce_bwd_sep(up, dtype, B, h, w, ncls, H, W, label, 255, lse2, acc2, dl)
+    t2 = dict(rtol=5e-2, atol=2e-5) if dtype == torch.bfloat16 else dict(rtol=1e-3, atol=1e-7)
+    torch.testing.assert_close(ds2.view(B, h, w, ncls).float(), sr.grad.permute(0, 2, 3, 1), **t2)
 
 
 def test_adamw_matches_torch():
