@@ -615,7 +615,7 @@ class UpsampleFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, small, meta):
         B, h, w, ncls, H, W = meta
-        out, _, _, _ = K.upsample_ce_fwd(small, B, h, w, ncls, H, W, None, 255, want_out=True, want_loss=False)
+        out = K.upsample_ce_fwd(small, B, h, w, ncls, H, W, None, 255, want_out=True, want_loss=False)[0]
         ctx.meta, ctx.dtype = meta, small.dtype
         return out
 

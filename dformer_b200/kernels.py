@@ -409,9 +409,7 @@ def upsample_ce_fwd(small, B, h, w, ncls, H, W, label, ignore, want_out=True, wa
     if want_loss:
         loss = torch.empty((), device=dev, dtype=torch.float32)
         lib().ce_finalize(acc.data_ptr(), loss.data_ptr(), _s())
-    if keep_up:
-        return out, lse, acc, loss, up
-    return out, lse, acc, loss
+    return out, lse, acc, loss, up
 
 
 def upsample_ce_bwd_sep(up, small_dtype, B, h, w, ncls, H, W, label, ignore, lse, acc, dloss):

@@ -370,7 +370,7 @@ def test_upsample_ce(dtype, ncls):
     small = rnd(B, h, w, ncls, dtype=dtype)
     label = torch.randint(0, ncls, (B, H, W), device=DEV)
     label[torch.rand(B, H, W, device=DEV) < 0.1] = 255
-    out, lse, acc, loss = k.upsample_ce_fwd(small.view(-1, ncls), B, h, w, ncls, H, W, label, 255)
+    out, lse, acc, loss, _ = k.upsample_ce_fwd(small.view(-1, ncls), B, h, w, ncls, H, W, label, 255)
     sr = small.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
     up = F.interpolate(sr, (H, W), mode="bilinear", align_corners=False)
     ref_loss = F.cross_entropy(up, label, reduction="none", ignore_index=255)[label != 255].mean()
