@@ -105,20 +105,26 @@ __global__ void upsample_ce_bwd_kernel(const T* __restrict__ small, int B, int h
 }
 
 // ---- separable adjoint.  Pass 1 (rows): t[b,c,ly,ox] = sum_oy wy(ly,oy) * (softmax(up)[b,c,oy,ox] - onehot) * valid
-template <typename TU>
+// One thread owns (b, ly, ox) and a chunk of CH classes, so the label / log-sum-exp of each hi-res pixel is fetched once
+// per chunk instead of once per class; all loads are coalesced along ox.
+template <typename TU, int CH>
 __global__ void upsample_ce_bwd_rows_kernel(const TU* __restrict__ up, int B, int h, int ncls, int H, int W, const int64_t* __restrict__ label, int ignore,
                                             const float* __restrict__ lse, float* __restrict__ t) {
-  const long n = (long)B * ncls * h * W;
+  const int nchunk = (ncls + CH - 1) / CH;
+  const long n = (long)B * nchunk * h * W;
   const float ry = (float)H / (float)h;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const int ox = (int)(i % W);
     const int ly = (int)((i / W) % h);
-    const int c = (int)((i / ((long)W * h)) % ncls);
-    const int b = (int)(i / ((long)W * h * ncls));
+    const int ck = (int)((i / ((long)W * h)) % nchunk);
+    const int b = (int)(i / ((long)W * h * nchunk));
+    const int c0 = ck * CH;
     int oy_lo = max(0, (int)floorf((ly - 1) * ry) - 1), oy_hi = min(H - 1, (int)ceilf((ly + 2) * ry) + 1);
     if (ly == 0) oy_lo = 0;
     if (ly == h - 1) oy_hi = H - 1;
-    float acc = 0.f;
+    float acc[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) acc[j] = 0.f;
     for (int oy = oy_lo; oy <= oy_hi; ++oy) {
       const Lerp l = lerp_coord(oy, h, H);
       const float wy = (l.i0 == ly ? 1.f - l.w1 : 0.f) + (l.i1 == ly ? l.w1 : 0.f);
@@ -126,11 +132,20 @@ __global__ void upsample_ce_bwd_rows_kernel(const TU* __restrict__ up, int B, in
       const long hp = ((long)b * H + oy) * W + ox;
       const long lab = label[hp];
       if (lab == (long)ignore || lab < 0 || lab >= ncls) continue;
-      float g = __expf(to_f(up[((long)b * ncls + c) * H * W + (long)oy * W + ox]) - lse[hp]);
-      if ((long)c == lab) g -= 1.f;
-      acc = fmaf(wy, g, acc);
+      const float ls = lse[hp];
+      const TU* src = up + ((long)b * ncls + c0) * H * W + (long)oy * W + ox;
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        if (c0 + j < ncls) {
+          float g = __expf(to_f(src[(long)j * H * W]) - ls);
+          if ((long)(c0 + j) == lab) g -= 1.f;
+          acc[j] = fmaf(wy, g, acc[j]);
+        }
+      }
     }
-    t[i] = acc;
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (c0 + j < ncls) t[(((long)b * ncls + c0 + j) * h + ly) * W + ox] = acc[j];
   }
 }
 // Pass 2 (columns): ds[b,ly,lx,c] = scale * sum_ox wx(lx,ox) * t[b,c,ly,ox]
@@ -182,12 +197,13 @@ extern "C" int dfb200_ce_finalize(const float* loss_acc, float* loss, void* stre
 extern "C" int dfb200_upsample_ce_bwd_sep(const void* up, int up_dtype, int B, int h, int w, int ncls, int H, int W, const int64_t* label, int ignore,
                                           const float* lse, const float* loss_acc, const float* dloss, float* scratch, void* dlogits_small, int dl_dtype,
                                           void* stream) {
-  const long n1 = (long)B * ncls * h * W, n2 = (long)B * h * w * ncls;
+  constexpr int CH = 10;
+  const long n1 = (long)B * ((ncls + CH - 1) / CH) * h * W, n2 = (long)B * h * w * ncls;
   long g1 = (n1 + 255) / 256, g2 = (n2 + 255) / 256;
   if (g1 > 148L * 32) g1 = 148L * 32;
   if (g1 < 1) g1 = 1;
   if (g2 < 1) g2 = 1;
-  DFB_DISPATCH_DTYPE(up_dtype, TU, { upsample_ce_bwd_rows_kernel<TU><<<(int)g1, 256, 0, ST>>>((const TU*)up, B, h, ncls, H, W, label, ignore, lse, scratch); });
+  DFB_DISPATCH_DTYPE(up_dtype, TU, { upsample_ce_bwd_rows_kernel<TU, CH><<<(int)g1, 256, 0, ST>>>((const TU*)up, B, h, ncls, H, W, label, ignore, lse, scratch); });
   int rc = dfb_check_launch("upsample_ce_bwd_rows");
   if (rc) return rc;
   DFB_DISPATCH_DTYPE(dl_dtype, TD, { upsample_ce_bwd_cols_kernel<TD><<<(int)g2, 256, 0, ST>>>(scratch, B, h, w, ncls, W, loss_acc, dloss, (TD*)dlogits_small); });

@@ -42,6 +42,7 @@ def _lin_bwd(dy, x, w, dW, db, T, need_dx=True, dx_out=None, dx_epi=None):
     if ws is not None:
         ws.wait_event(K.signal())
         dy.record_stream(ws)
+        x.record_stream(ws)                         # saved activation: may be released before the trailing wgrad stream has read it
         with torch.cuda.stream(ws):
             K.gemm(dy, x, trans_a=True, trans_b=False, out=dW, backend=be, accumulate=True)
             if db is not None:
@@ -149,6 +150,8 @@ class StemFn(torch.autograd.Function):
         dW1p = torch.zeros(pk1[0].shape, device=dx0.device, dtype=F32)
         _lin_bwd(dc1, col1, pk1[0], dW1p, ar.view(p + "0.bias"), T, need_dx=False)
         K.unpack_conv_grad(dW1p, pk1[0].shape[0], st.cin, ar.view(p + "0.weight"))
+        if getattr(st, "wstream", None) is not None:
+            K.join(st.wstream)                        # every Block's parameter gradients (wgrad side stream) are final from here on
         ar.done(st.tag)
         return (None, None, ar.view(p + "0.weight"), ar.view(p + "0.bias"), ar.view(p + "1.weight"), ar.view(p + "1.bias"),
                 ar.view(p + "3.weight"), ar.view(p + "3.bias"), ar.view(p + "4.weight"), ar.view(p + "4.bias"))
@@ -399,9 +402,10 @@ class BlockFn(torch.autograd.Function):
         if dd and dxe2 is not None:
             K.axpy(dxe2.contiguous(), 1.0, dxe)                                  # x_e passes through the last block unchanged
         _WGRAD_STREAM = None
-        K.join(wstream)                                                          # all parameter gradients of this Block are final
         ctx.sv = ctx.P = None
-        ar.done(st.tag)
+        # the wgrad stream is NOT joined here (it may trail the dgrad chain across Blocks); the DP engine gets an event,
+        # and the stem's backward -- the last encoder node on the main stream -- performs the final join
+        ar.done(st.tag, K.signal(wstream))
         return (dx, dxe, None) + tuple(G[n] for n in st.names)
 
 

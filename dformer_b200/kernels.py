@@ -196,6 +196,7 @@ def dwconv_bwd(dy, x, weight, bias, B, H, W, k, add_input, act, dweight, dbias, 
     g = dz if dz is not None else dy
     wgrad_stream.wait_event(signal())
     g.record_stream(wgrad_stream)
+    x.record_stream(wgrad_stream)
     with torch.cuda.stream(wgrad_stream):
         lib().dwconv_bwd(g.data_ptr(), x.data_ptr(), None, dt(x), weight.data_ptr(), _p(bias), B, H, W, C, k, int(add_input), ACT_NONE,
                          None, None, dweight.data_ptr(), dbias.data_ptr(), _s())

@@ -266,10 +266,14 @@ class DFormer(nn.Module):
                 keep = plan.dp_keep = (1.0 - torch.tensor(rates, dtype=torch.float32).view(-1, 1, 1)).to(dev)
             dp = torch.floor(keep + torch.rand(n_blocks, 4, B, device=dev)) / keep      # DropPath: mask / keep_prob per sample
 
+        if self._side_stream is None or self._side_stream[0].device != dev:
+            self._side_stream = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
+        side, side2, wstream = self._side_stream
+
         def stem(inp, sfx, cin):
             p = f"downsample_layers{sfx}.0."
             seq = self.downsample_layers[0] if sfx == "" else self.downsample_layers_e[0]
-            st = SimpleNamespace(dtype=T, cin=cin, packed=packed, g1=p + "c1", g2=p + "c2", arena=arena, prefix=p, tag=p,
+            st = SimpleNamespace(dtype=T, cin=cin, packed=packed, g1=p + "c1", g2=p + "c2", arena=arena, prefix=p, tag=p, wstream=wstream,
                                  bn1=Fn.BNState(seq[1], p + "1", training, False), bn2=Fn.BNState(seq[4], p + "4", training, False))
             names = ("0.weight", "0.bias", "1.weight", "1.bias", "3.weight", "3.bias", "4.weight", "4.bias")
             return Fn.StemFn.apply(inp, st, *[named[p + n] for n in names])
@@ -281,9 +285,6 @@ class DFormer(nn.Module):
                                  bn=Fn.BNState(seq[0], p + "0", training, True if sync else False))
             return Fn.DownsampleFn.apply(xx, st, *[named[p + n] for n in ("0.weight", "0.bias", "1.weight", "1.bias")])
 
-        if self._side_stream is None or self._side_stream[0].device != dev:
-            self._side_stream = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
-        side, side2, wstream = self._side_stream
         outs = []
         h, w = H, W
         bi = 0

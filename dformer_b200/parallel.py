@@ -16,17 +16,19 @@ class GradSync:
         self.bucket_elems = int(bucket_mb * 1024 * 1024 / 4)
         self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.stream = torch.cuda.Stream() if (self.enabled and torch.cuda.is_available()) else None
-        self.pending = {}        # id(arena) -> [arena, lo, hi] contiguous finished-but-unsent range
+        self.pending = {}        # id(arena) -> [arena, lo, hi, events] contiguous finished-but-unsent range
         self.handles = []
         self.launched = 0
         for m in model.modules():
             if hasattr(m, "grad_hook") and hasattr(m, "_build_plan"):
                 m.grad_hook = self._on_range_done
 
-    def _fire(self, arena, lo, hi):
+    def _fire(self, arena, lo, hi, events=()):
         buf = arena.flat()[lo:hi]
         if self.stream is not None:
             self.stream.wait_stream(torch.cuda.current_stream())
+            for ev in events:                       # gradients written on the wgrad side stream
+                self.stream.wait_event(ev)
             with torch.cuda.stream(self.stream):
                 dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group)
             buf.record_stream(self.stream)
@@ -35,7 +37,7 @@ class GradSync:
             buf.div_(dist.get_world_size(self.group))
         self.launched += 1
 
-    def _on_range_done(self, arena, lo, hi):
+    def _on_range_done(self, arena, lo, hi, event=None):
         if not self.enabled:
             return
         key = id(arena)
@@ -47,8 +49,10 @@ class GradSync:
         else:
             if cur is not None:
                 self._fire(*cur)
-            cur = [arena, lo, hi]
+            cur = [arena, lo, hi, []]
             self.pending[key] = cur
+        if event is not None:
+            cur[3].append(event)
         if cur[2] - cur[1] >= self.bucket_elems:
             self._fire(*cur)
             del self.pending[key]

@@ -98,10 +98,11 @@ class GradArena:
         a, b = self.layout.slots[first], self.layout.slots[last]
         return self.flat()[a.offset:b.offset + b.numel].view(shape)
 
-    def done(self, tag: str):
+    def done(self, tag: str, event=None):
+        """`event`: CUDA event after which the range is final when its kernels ran on a side (wgrad) stream."""
         if self.on_range_done is not None:
             lo, hi = self.layout.marks[tag]
-            self.on_range_done(self, lo, hi)
+            self.on_range_done(self, lo, hi, event)
 
 
 # --------------------------------------------------------------------------------------------- packing

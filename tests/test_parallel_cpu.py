@@ -24,9 +24,9 @@ class _FakeArena:
     def flat(self):
         return self.buf
 
-    def done(self, tag):
+    def done(self, tag, event=None):
         lo, hi = self.layout.marks[tag]
-        self.on_range_done(self, lo, hi)
+        self.on_range_done(self, lo, hi, event)
 
 
 class _FakeModule(torch.nn.Module):
@@ -80,5 +80,5 @@ def test_gradsync_is_a_noop_without_process_group():
     model = torch.nn.Sequential(_FakeModule())
     sync = GradSync(model)
     assert not sync.enabled
-    model[0].grad_hook(None, 0, 10)
+    model[0].grad_hook(None, 0, 10, None)
     sync.finish()

@@ -35,6 +35,47 @@ from torch.profiler import ProfilerActivity, profile
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     run.step()
     torch.cuda.synchronize()
+# timeline analysis: busy union, idle gaps, concurrency
+iv = sorted((ev.time_range.start, ev.time_range.end, ev.name) for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA)
+t0, t1 = iv[0][0], max(e for _, e, _ in iv)
+busy, cur_s, cur_e = 0.0, iv[0][0], iv[0][1]
+gaps = []
+for s_, e_, n_ in iv[1:]:
+    if s_ > cur_e:
+        busy += cur_e - cur_s
+        gaps.append((s_ - cur_e, n_))
+        cur_s, cur_e = s_, e_
+    else:
+        cur_e = max(cur_e, e_)
+busy += cur_e - cur_s
+print(f"timeline: span {(t1 - t0) / 1e3:.2f} ms, busy (union) {busy / 1e3:.2f} ms, idle {(t1 - t0 - busy) / 1e3:.2f} ms in {len(gaps)} gaps")
+gaps.sort(reverse=True)
+print("largest gaps (us, next kernel):", [(round(g, 1), n.replace('(anonymous namespace)::', '').replace('void ', '')[:40]) for g, n in gaps[:8]])
+# time with exactly one kernel running
+pts = sorted([(s_, 1) for s_, e_, _ in iv] + [(e_, -1) for s_, e_, _ in iv])
+lvl, last, hist = 0, pts[0][0], defaultdict(float)
+for t_, d_ in pts:
+    hist[lvl] += t_ - last
+    last, lvl = t_, lvl + d_
+print("time by number of concurrently running kernels (ms):", {k: round(v / 1e3, 2) for k, v in sorted(hist.items())})
+# which kernels run ALONE (exclusive time per kernel name)
+import heapq
+ev2 = sorted([(s_, 0, i) for i, (s_, e_, _) in enumerate(iv)] + [(e_, 1, i) for i, (s_, e_, _) in enumerate(iv)])
+active, last_t, alone = set(), ev2[0][0], defaultdict(float)
+for t_, kind, i in ev2:
+    if len(active) == 1:
+        alone[iv[next(iter(active))][2]] += t_ - last_t
+    last_t = t_
+    if kind == 0:
+        active.add(i)
+    else:
+        active.discard(i)
+al = defaultdict(float)
+for n_, v_ in alone.items():
+    al[n_.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0][:60]] += v_
+print("exclusive (alone-on-GPU) time by kernel, ms:")
+for n_, v_ in sorted(al.items(), key=lambda kv: -kv[1])[:22]:
+    print(f"   {v_ / 1e3:7.3f}  {n_}")
 agg = defaultdict(lambda: [0.0, 0])
 tmin, tmax = 1e30, 0
 for ev in prof.events():
