@@ -215,7 +215,7 @@ def main():
     K.GEMM_PROFILE = None
     tc = [(a.elapsed_time(b), fl, by) for a, b, fl, by, is_tc, _ in prof if is_tc]
     simt = [(a.elapsed_time(b), fl, by) for a, b, fl, by, is_tc, _ in prof if not is_tc]
-    tc_ms, tc_fl = sum(t for t, _, _ in tc) / 2, sum(f for _, f, _ in tc) / 2
+    tc_ms, tc_fl, tc_by, tc_n = sum(t for t, _, _ in tc) / 2, sum(f for _, f, _ in tc) / 2, sum(b for _, _, b in tc) / 2, len(tc) // 2
     simt_ms = sum(t for t, _, _ in simt) / 2
 
     if world > 1:
@@ -240,6 +240,13 @@ def main():
     e2e = n * B / (ms_e2e * 1e-3)
     h2d = rgb_h.numel() * 4 + hha_h.numel() * 4 + lab_h.numel() * 8
     achieved = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    achieved_gbs = tc_by / (tc_ms * 1e-3) / 1e9 if tc_ms > 0 else 0.0
+    traffic = None
+    try:            # DRAM bytes per launch of the same kernel from the committed ncu capture (profiles/)
+        with open(os.path.join(ROOT, "profiles", "ncu_gemm_traffic.json")) as f:
+            traffic = json.load(f)["dram_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
     out = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
@@ -251,11 +258,17 @@ def main():
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "loss": host_loss},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM: all Linear/1x1/im2col conv fwd+dgrad+wgrad)",
-                     "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst, "traffic": None,
-                     "peak_source": how + " (MEASURED_PEAKS.json bf16_tflops, burst)",
-                     "kernel_ms_per_step": tc_ms, "kernel_share_of_step": tc_ms / ms, "simt_gemm_ms_per_step": simt_ms,
-                     "algorithmic_flops_per_step": tc_fl},
+        # DFormer's GEMMs have K = 48..288 for most layers (arithmetic intensity ~ K*N/(K+N) < the 246 FLOP/B ridge), so the
+        # dominant kernel is bounded by HBM, not by the tensor pipe; both views are reported.
+        "roofline": {"bound": "hbm", "kernel": "gemm_tc_kernel (tcgen05 GEMM: every Linear / 1x1 / im2col conv fwd + dgrad + wgrad)",
+                     "achieved": achieved_gbs, "peak": hbm, "unit": "GB/s", "frac": achieved_gbs / hbm, "traffic": traffic,
+                     "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)",
+                     "algorithmic_bytes_per_launch": tc_by / max(tc_n, 1), "launches_per_step": tc_n,
+                     "avg_launch_us": tc_ms * 1e3 / max(tc_n, 1), "kernel_ms_per_step": tc_ms, "kernel_share_of_step": tc_ms / ms,
+                     "timing": "CUDA events around every launch in an eager replay of the same step (includes inter-launch gaps)",
+                     "tensor_view": {"achieved_tflops": achieved, "peak_tflops": tf_burst, "frac": achieved / tf_burst,
+                                     "algorithmic_flops_per_step": tc_fl},
+                     "simt_gemm_ms_per_step": simt_ms},
         "step_roofline": {"achieved_tflops": value * FLOP_PER_IMG_TRAIN / n / 1e12, "frac_of_burst": value * FLOP_PER_IMG_TRAIN / n / 1e12 / tf_burst,
                           "frac_of_sustained": value * FLOP_PER_IMG_TRAIN / n / 1e12 / tf_sus, "flop_per_image": FLOP_PER_IMG_TRAIN},
     }

@@ -125,6 +125,140 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, bool mn_major
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
 }
 
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint32_t* w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
+  return r;
+}
+
+// Generic (rarely taken) epilogue: ragged chunks / row tails, activations, fp32 outputs, accumulate, scalar split-K.
+// Kept out of line so the hot loop stays small in the instruction cache.
+__device__ __noinline__ void epilogue_generic(const TcParams& p, float* v, int row, int col0, int ncols, long c_off, int m_blk, int quad, int lane,
+                                              int warp, uint8_t* epi_stage, bool rows_all_ok) {
+  const bool full = ncols == 32;
+        if (p.splits > 1) {                       // split-K partial sums: fp32 reductions into a zeroed / accumulating C
+          float* dst = reinterpret_cast<float*>(p.C) + c_off + (long)row * p.ldc + col0;
+          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) atomicAdd(dst + j, v[j]);
+          }
+          return;
+        }
+        if (p.act != 0) {
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (col0 + j >= p.act_col_start) ? gelu_f(v[j]) : v[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (col0 + j >= p.act_col_start) ? fmaxf(v[j], 0.f) : v[j];
+          }
+        }
+        if (p.out_bf16) {
+          bf16* dst = reinterpret_cast<bf16*>(p.C) + c_off + (long)row * p.ldc + col0;
+          if (false) {
+            // warp-private transpose through shared memory: lane r holds row r (32 columns); after the swizzled
+            // round trip 4 adjacent lanes write one row's 64 contiguous bytes -> every store instruction covers
+            // 8 fully-written 64-byte row segments instead of 32 scattered 16-byte pieces.
+            uint4* st = reinterpret_cast<uint4*>(epi_stage + (warp - 2) * 4096);
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              uint4 pk;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[u * 8 + 2 * q], v[u * 8 + 2 * q + 1]);
+              st[lane * 4 + (u ^ ((lane >> 1) & 3))] = pk;
+            }
+            __syncwarp();
+            const int row_base = m_blk * BM + quad * 32;
+            bf16* base = reinterpret_cast<bf16*>(p.C) + c_off + (long)row_base * p.ldc + col0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = 8 * i + (lane >> 2), u = lane & 3;
+              uint4 pk = st[rr * 4 + (u ^ ((rr >> 1) & 3))];
+              const long grow = row_base + rr;
+              const int gcol = col0 + u * 8;
+              if (p.epi_mode == 1) {              // dz = du * gelu'(z): the saved pre-activation is read in the coalesced store pattern
+                float f[8], z[8];
+                Vec8<bf16>::unpack(pk, f);
+                Vec8<bf16>::load(reinterpret_cast<const bf16*>(p.aux) + grow * p.ld_aux + gcol, z);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] *= gelu_grad_f(z[j]);
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+              }
+              *reinterpret_cast<uint4*>(base + (long)rr * p.ldc + u * 8) = pk;
+              if (p.epi_mode == 2) {              // x_new = res + DropPath-scale * layer_scale * f  (fp32 residual stream)
+                float f[8], r8[8], l8[8];
+                Vec8<bf16>::unpack(pk, f);
+                Vec8<float>::load(reinterpret_cast<const float*>(p.aux) + grow * p.ld_aux + gcol, r8);
+                Vec8<float>::load(p.ls + gcol, l8);
+                const float sb = p.scale_b ? __ldg(p.scale_b + grow / p.rows_per_sample) : 1.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r8[j] = fmaf(sb * l8[j], f[j], r8[j]);
+                Vec8<float>::store(reinterpret_cast<float*>(p.out2) + grow * p.ld_out2 + gcol, r8);
+              }
+            }
+          } else if (p.epi_mode != 0) {           // tails of the fused epilogues: per element
+            const float sb = (p.epi_mode == 2 && p.scale_b) ? __ldg(p.scale_b + row / p.rows_per_sample) : 1.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < ncols) {
+                float f = __bfloat162float(__float2bfloat16_rn(v[j]));
+                if (p.epi_mode == 1) {
+                  f *= gelu_grad_f(__bfloat162float(reinterpret_cast<const bf16*>(p.aux)[(long)row * p.ld_aux + col0 + j]));
+                  dst[j] = __float2bfloat16_rn(f);
+                } else {
+                  dst[j] = __float2bfloat16_rn(f);
+                  const float r = reinterpret_cast<const float*>(p.aux)[(long)row * p.ld_aux + col0 + j];
+                  reinterpret_cast<float*>(p.out2)[(long)row * p.ld_out2 + col0 + j] = fmaf(sb * p.ls[col0 + j], f, r);
+                }
+              }
+            }
+          } else if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) Vec8<bf16>::store(dst + j, v + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
+          }
+        } else {
+          float* dst = reinterpret_cast<float*>(p.C) + c_off + (long)row * p.ldc + col0;
+          const bool vec = full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+          if (p.accumulate) {
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 o = *reinterpret_cast<float4*>(dst + j);
+                o.x += v[j]; o.y += v[j + 1]; o.z += v[j + 2]; o.w += v[j + 3];
+                *reinterpret_cast<float4*>(dst + j) = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) dst[j] += v[j];
+            }
+          } else if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) dst[j] = v[j];
+          }
+        }
+}
+
 // ------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
@@ -270,124 +404,65 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (j < ncols) v[j] += __ldg(bp + j);
           }
         }
-        if (p.splits > 1) {                       // split-K partial sums: fp32 reductions into a zeroed / accumulating C
-          float* dst = reinterpret_cast<float*>(p.C) + c_off + (long)row * p.ldc + col0;
-          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        // ---- hot path 1: bf16 output, complete 32x32 chunk -> swizzled smem transpose -> coalesced 64-byte row segments
+        const bool aligned_c = ((p.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (((c_off + col0) & 7) == 0);
+        if (p.splits == 1 && p.out_bf16 && p.act == 0 && full && rows_all_ok && aligned_c) {
+          const uint32_t sbase = smem_u32(epi_stage + (warp - 2) * 4096);
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
-          } else {
+          for (int u = 0; u < 4; ++u) {
+            uint32_t w[4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) atomicAdd(dst + j, v[j]);
+            for (int q = 0; q < 4; ++q) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[u * 8 + 2 * q], v[u * 8 + 2 * q + 1]);
+              w[q] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            sts128(sbase + (uint32_t)(lane * 4 + (u ^ ((lane >> 1) & 3))) * 16u, w);
+          }
+          __syncwarp();
+          const int row_base = m_blk * BM + quad * 32;
+          bf16* base = reinterpret_cast<bf16*>(p.C) + c_off + (long)row_base * p.ldc + col0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = 8 * i + (lane >> 2), u = lane & 3;
+            uint4 pk = lds128(sbase + (uint32_t)(rr * 4 + (u ^ ((rr >> 1) & 3))) * 16u);
+            const long grow = row_base + rr;
+            const int gcol = col0 + u * 8;
+            if (p.epi_mode == 1) {              // dz = du * gelu'(z): the saved pre-activation is read in the coalesced store pattern
+              float f[8], z[8];
+              Vec8<bf16>::unpack(pk, f);
+              Vec8<bf16>::load(reinterpret_cast<const bf16*>(p.aux) + grow * p.ld_aux + gcol, z);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] *= gelu_grad_f(z[j]);
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+            }
+            *reinterpret_cast<uint4*>(base + (long)rr * p.ldc + u * 8) = pk;
+            if (p.epi_mode == 2) {              // x_new = res + DropPath-scale * layer_scale * f  (fp32 residual stream)
+              float f[8], r8[8], l8[8];
+              Vec8<bf16>::unpack(pk, f);
+              Vec8<float>::load(reinterpret_cast<const float*>(p.aux) + grow * p.ld_aux + gcol, r8);
+              Vec8<float>::load(p.ls + gcol, l8);
+              const float sb = p.scale_b ? __ldg(p.scale_b + grow / p.rows_per_sample) : 1.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) r8[j] = fmaf(sb * l8[j], f[j], r8[j]);
+              Vec8<float>::store(reinterpret_cast<float*>(p.out2) + grow * p.ld_out2 + gcol, r8);
+            }
           }
           continue;
         }
-        if (p.act != 0) {
-          if (p.act == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (col0 + j >= p.act_col_start) ? gelu_f(v[j]) : v[j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (col0 + j >= p.act_col_start) ? fmaxf(v[j], 0.f) : v[j];
-          }
-        }
-        if (p.out_bf16) {
-          bf16* dst = reinterpret_cast<bf16*>(p.C) + c_off + (long)row * p.ldc + col0;
-          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((p.ldc & 7) == 0) && rows_all_ok) {
-            // warp-private transpose through shared memory: lane r holds row r (32 columns); after the swizzled
-            // round trip 4 adjacent lanes write one row's 64 contiguous bytes -> every store instruction covers
-            // 8 fully-written 64-byte row segments instead of 32 scattered 16-byte pieces.
-            uint4* st = reinterpret_cast<uint4*>(epi_stage + (warp - 2) * 4096);
-            __syncwarp();
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              uint4 pk;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[u * 8 + 2 * q], v[u * 8 + 2 * q + 1]);
-              st[lane * 4 + (u ^ ((lane >> 1) & 3))] = pk;
-            }
-            __syncwarp();
-            const int row_base = m_blk * BM + quad * 32;
-            bf16* base = reinterpret_cast<bf16*>(p.C) + c_off + (long)row_base * p.ldc + col0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rr = 8 * i + (lane >> 2), u = lane & 3;
-              uint4 pk = st[rr * 4 + (u ^ ((rr >> 1) & 3))];
-              const long grow = row_base + rr;
-              const int gcol = col0 + u * 8;
-              if (p.epi_mode == 1) {              // dz = du * gelu'(z): the saved pre-activation is read in the coalesced store pattern
-                float f[8], z[8];
-                Vec8<bf16>::unpack(pk, f);
-                Vec8<bf16>::load(reinterpret_cast<const bf16*>(p.aux) + grow * p.ld_aux + gcol, z);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] *= gelu_grad_f(z[j]);
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
-              }
-              *reinterpret_cast<uint4*>(base + (long)rr * p.ldc + u * 8) = pk;
-              if (p.epi_mode == 2) {              // x_new = res + DropPath-scale * layer_scale * f  (fp32 residual stream)
-                float f[8], r8[8], l8[8];
-                Vec8<bf16>::unpack(pk, f);
-                Vec8<float>::load(reinterpret_cast<const float*>(p.aux) + grow * p.ld_aux + gcol, r8);
-                Vec8<float>::load(p.ls + gcol, l8);
-                const float sb = p.scale_b ? __ldg(p.scale_b + grow / p.rows_per_sample) : 1.f;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) r8[j] = fmaf(sb * l8[j], f[j], r8[j]);
-                Vec8<float>::store(reinterpret_cast<float*>(p.out2) + grow * p.ld_out2 + gcol, r8);
-              }
-            }
-          } else if (p.epi_mode != 0) {           // tails of the fused epilogues: per element
-            const float sb = (p.epi_mode == 2 && p.scale_b) ? __ldg(p.scale_b + row / p.rows_per_sample) : 1.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < ncols) {
-                float f = __bfloat162float(__float2bfloat16_rn(v[j]));
-                if (p.epi_mode == 1) {
-                  f *= gelu_grad_f(__bfloat162float(reinterpret_cast<const bf16*>(p.aux)[(long)row * p.ld_aux + col0 + j]));
-                  dst[j] = __float2bfloat16_rn(f);
-                } else {
-                  dst[j] = __float2bfloat16_rn(f);
-                  const float r = reinterpret_cast<const float*>(p.aux)[(long)row * p.ld_aux + col0 + j];
-                  reinterpret_cast<float*>(p.out2)[(long)row * p.ld_out2 + col0 + j] = fmaf(sb * p.ls[col0 + j], f, r);
-                }
-              }
-            }
-          } else if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) Vec8<bf16>::store(dst + j, v + j);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
-          }
-        } else {
+        // ---- hot path 2: split-K partial sums of a complete chunk -> vector reductions into the fp32 gradient
+        if (p.splits > 1 && full) {
           float* dst = reinterpret_cast<float*>(p.C) + c_off + (long)row * p.ldc + col0;
-          const bool vec = full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-          if (p.accumulate) {
-            if (vec) {
+          if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 o = *reinterpret_cast<float4*>(dst + j);
-                o.x += v[j]; o.y += v[j + 1]; o.z += v[j + 2]; o.w += v[j + 3];
-                *reinterpret_cast<float4*>(dst + j) = o;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) dst[j] += v[j];
-            }
-          } else if (vec) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) dst[j] = v[j];
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+            continue;
           }
         }
+        epilogue_generic(p, v, row, col0, ncols, c_off, m_blk, quad, lane, warp, epi_stage, rows_all_ok);
       }
       tc_fence_before();
       __syncwarp();
