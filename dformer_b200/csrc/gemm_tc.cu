@@ -452,17 +452,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           continue;
         }
-        // ---- hot path 2: split-K partial sums of a complete chunk -> vector reductions into the fp32 gradient
-        if (p.splits > 1 && full) {
+        // ---- hot path 1b: bf16 output, ragged chunk whose width is a multiple of 8 (BN = 48, 144, 240, ...): every lane
+        // writes whole 16-byte vectors of its own row (full 32-byte sectors, no staging needed for the short tail)
+        if (p.splits == 1 && p.out_bf16 && p.act == 0 && p.epi_mode == 0 && aligned_c && (ncols & 7) == 0) {
+          bf16* dst = reinterpret_cast<bf16*>(p.C) + c_off + (long)row * p.ldc + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            if (j < ncols) Vec8<bf16>::store(dst + j, v + j);
+          continue;
+        }
+        // ---- hot path 2: split-K partial sums -> vector reductions into the fp32 gradient
+        if (p.splits > 1 && (ncols & 3) == 0) {
           float* dst = reinterpret_cast<float*>(p.C) + c_off + (long)row * p.ldc + col0;
           if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+              if (j < ncols)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
             continue;
           }
         }
-        epilogue_generic(p, v, row, col0, ncols, c_off, m_blk, quad, lane, warp, epi_stage, rows_all_ok);
+        // ---- hot path 3: fp32 output without split-K (small wgrads accumulate into the arena; downsample convs write fp32)
+        if (p.splits == 1 && !p.out_bf16 && p.act == 0 && (ncols & 3) == 0) {
+          float* dst = reinterpret_cast<float*>(p.C) + c_off + (long)row * p.ldc + col0;
+          if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j < ncols) {
+                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (p.accumulate) {
+                  const float4 old = *reinterpret_cast<const float4*>(dst + j);
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                *reinterpret_cast<float4*>(dst + j) = o;
+              }
+            }
+            continue;
+          }
+        }
+        {
+          float vv[32];                            // address-taken copy: keeps v[] itself in registers for the hot paths
+#pragma unroll
+          for (int j = 0; j < 32; ++j) vv[j] = v[j];
+          epilogue_generic(p, vv, row, col0, ncols, c_off, m_blk, quad, lane, warp, epi_stage, rows_all_ok);
+        }
       }
       tc_fence_before();
       __syncwarp();
