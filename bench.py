@@ -209,8 +209,11 @@ def main():
     K.GEMM_PROFILE = []
     for _ in range(2):
         runner._draw_bases()
+        # park the GPU behind a ~150 ms spin so the host enqueues the whole eager step ahead of it: the events then bracket
+        # back-to-back device execution (true kernel durations) instead of host launch latency
+        torch.cuda._sleep(int(0.15 * 1.9e9))
         runner._eager()                                     # eager replay of the identical step, every GEMM bracketed by events
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
     prof = K.GEMM_PROFILE
     K.GEMM_PROFILE = None
     tc = [(a.elapsed_time(b), fl, by) for a, b, fl, by, is_tc, _ in prof if is_tc]
@@ -265,7 +268,8 @@ def main():
                      "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)",
                      "algorithmic_bytes_per_launch": tc_by / max(tc_n, 1), "launches_per_step": tc_n,
                      "avg_launch_us": tc_ms * 1e3 / max(tc_n, 1), "kernel_ms_per_step": tc_ms, "kernel_share_of_step": tc_ms / ms,
-                     "timing": "CUDA events around every launch in an eager replay of the same step (includes inter-launch gaps)",
+                     "timing": "CUDA events around every launch of an eager replay of the same step, GPU parked behind a spin kernel so "
+                               "launches are queued back-to-back (device durations, not host latency)",
                      "tensor_view": {"achieved_tflops": achieved, "peak_tflops": tf_burst, "frac": achieved / tf_burst,
                                      "algorithmic_flops_per_step": tc_fl},
                      "simt_gemm_ms_per_step": simt_ms},
