@@ -61,6 +61,7 @@ def _chk(t, name="tensor"):
 
 
 GEMM_PROFILE = None      # bench.py sets this to a list to time every GEMM launch with CUDA events
+GEMM_SHAPES_ONLY = False  # ... or just to collect the (shape, flops, bytes) census of a step
 
 
 def gemm(a, b, *, trans_a=False, trans_b=True, bias=None, out=None, out_dtype=None, act=ACT_NONE, act_col_start=0,
@@ -94,7 +95,11 @@ def gemm(a, b, *, trans_a=False, trans_b=True, bias=None, out=None, out_dtype=No
             _, res, out2, ls, scale_b, rps = epi
             g.epi_mode, g.aux, g.ld_aux, g.out2, g.ld_out2 = 2, res.data_ptr(), res.stride(0), out2.data_ptr(), out2.stride(0)
             g.ls, g.scale_b, g.rows_per_sample = ls.data_ptr(), _p(scale_b), rps
-    if GEMM_PROFILE is not None:
+    if GEMM_PROFILE is not None and GEMM_SHAPES_ONLY:
+        tc = backend != SIMT and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+        GEMM_PROFILE.append((None, None, 2.0 * M * N * K, a.element_size() * M * K + b.element_size() * N * K + out.element_size() * M * N, tc,
+                             (M, N, K, int(trans_a), int(trans_b), out.dtype == torch.float32, bias is not None, int(accumulate))))
+    elif GEMM_PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         lib().gemm(ctypes.byref(g), _s())
