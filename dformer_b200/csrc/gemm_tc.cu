@@ -576,12 +576,32 @@ int make_map(CUtensorMap* out, const void* ptr, long inner, long outer, long ld,
   return DFB_OK;
 }
 
-int pick_bn(int N) {
+// Tile width: minimise the estimated makespan of the static round-robin tile schedule,
+//   waves(BN) * bytes-moved-per-tile(BN)   with  waves = ceil(m_tiles * n_tiles * batch / #SM),
+// instead of only minimising padding: e.g. M = 9600, N = 288 gives 75 x 2 = 150 tiles with BN = 144 (two CTAs run two
+// tiles -> 2 waves of a 144-wide tile) but 225 tiles of width 96 (2 waves of a tile that is 1/3 cheaper).
+int pick_bn_padding(int N) {      // widest tile with the least padding (split-K problems: the reduction split fills the machine)
   if (N <= 256) return ((N + 15) / 16) * 16;
   int best = 256; long best_cost = (long)dfb_cdiv(N, 256) * 256;
   for (int bn = 240; bn >= 64; bn -= 16) {
     const long cost = (long)dfb_cdiv(N, bn) * bn;
     if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+int pick_bn(int N, int m_tiles, int kb, int batch, int num_sms, bool b_mn_major) {
+  const int n_max = N <= 256 ? ((N + 15) / 16) * 16 : 256;
+  int best = n_max;
+  double best_cost = 1e300;
+  for (int bn = n_max; bn >= 32; bn -= 16) {
+    if (b_mn_major && bn < 64 && N >= 64) continue;
+    const long n_tiles = (N + bn - 1) / bn;
+    const long tiles = (long)m_tiles * n_tiles * batch;
+    const long waves = (tiles + num_sms - 1) / num_sms;
+    const double per_tile = (double)kb * (16384.0 + 128.0 * bn) + 256.0 * bn + 24000.0;
+    const double cost = (double)waves * per_tile;
+    if (cost < best_cost * 0.97) { best_cost = cost; best = bn; }     // prefer wider tiles unless clearly (3 %) worse
   }
   return best;
 }
@@ -620,12 +640,17 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.M = g.M; p.N = g.N; p.K = g.K;
-  p.BN = pick_bn(g.N);
   p.m_tiles = dfb_cdiv(g.M, BM);
-  p.n_tiles = dfb_cdiv(g.N, p.BN);
   p.kb_total = dfb_cdiv(g.K, BK);
   p.a_mn_major = g.transA ? 1 : 0;   // A stored [K, M]  -> M contiguous
   p.b_mn_major = g.transB ? 0 : 1;   // B stored [K, N]  -> N contiguous
+  {
+    // wgrad-like problems will be split along K; their tile count is multiplied by the split factor later, so only
+    // the un-split (forward / dgrad) shapes are tuned for wave quantisation
+    const bool will_split = (g.splitk == 0 && g.out_dtype == 0 && g.act == 0 && p.kb_total >= 16) || g.splitk > 1;
+    p.BN = will_split ? pick_bn_padding(g.N) : pick_bn(g.N, p.m_tiles, p.kb_total, g.batch, num_sms, p.b_mn_major);
+  }
+  p.n_tiles = dfb_cdiv(g.N, p.BN);
   p.C = g.C; p.ldc = g.ldc; p.bias = g.bias;
   p.batch = g.batch; p.strideC = g.strideC;
   p.epi_mode = g.epi_mode; p.aux = g.aux; p.ld_aux = g.ld_aux; p.out2 = g.out2; p.ld_out2 = g.ld_out2;

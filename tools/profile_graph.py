@@ -13,6 +13,12 @@ from dformer_b200.engine import GraphedTrainStep  # noqa: E402
 from dformer_b200.optim import FusedAdamW  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+DEPTHS = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else None
+if DEPTHS:
+    from dformer_b200.models.encoders import DFormer as enc
+    enc.DFormer_Large = lambda pretrained=False, drop_path_rate=0.1, **kw: enc.DFormer(
+        dims=[96, 192, 288, 576], mlp_ratios=[8, 8, 4, 4], depths=DEPTHS, num_heads=[1, 2, 4, 8], windows=[0, 7, 7, 7],
+        drop_path_rate=drop_path_rate, **kw)
 cfg = SimpleNamespace(backbone="DFormer-Large", decoder="ham", decoder_embed_dim=512, num_classes=40, drop_path_rate=0.15, aux_rate=0.0,
                       device="cuda", pretrained_model=None, bn_eps=1e-3, bn_momentum=0.1, background=255, precision="bf16", return_logits=False)
 torch.manual_seed(0)
