@@ -22,6 +22,7 @@ import os as _os
 # epilogue is already the critical resource (A/B in profiles/r01_ab_fused_epilogues.txt) -> off by default
 _FUSE_RES = _os.environ.get("DFB200_FUSE_RES", "0") == "1"
 _FUSE_GG = _os.environ.get("DFB200_FUSE_GG", "0") == "1"
+_FUSE_DW = _os.environ.get("DFB200_FUSE_DW", "1") == "1"      # fused MLP middle (csrc/mlp_dw.cu); 0 = the unfused chain, kept for A/B runs
 
 
 # ============================================================================================ helpers
@@ -203,7 +204,10 @@ def _mlp_fwd(x, pfx, st, P, sv, scale_b):
     B, H, W = st.B, st.H, st.W
     hn, mu, rs = K.layernorm_fwd(x, P[pfx + "norm.weight"], P[pfx + "norm.bias"], 1e-6, T)
     h = _lin(hn, st.packed[st.key + pfx + "fc1"], T)
-    u, z = K.dwconv_fwd(h, P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, add_input=True, act=K.ACT_GELU, save_z=True)
+    if T == torch.bfloat16 and _FUSE_DW:       # TMA-fed fused kernel; the pre-activation is recomputed in the fused backward
+        u, z = K.mlp_dw_fwd(h, P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W), None
+    else:
+        u, z = K.dwconv_fwd(h, P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, add_input=True, act=K.ACT_GELU, save_z=True)
     ls = P["layer_scale_2" if pfx == "mlp." else "layer_scale_2_e"]
     if T == torch.bfloat16 and _FUSE_RES:      # fc2 + bias + layer-scale/DropPath residual in one tcgen05 epilogue (f kept for the dls gradient)
         w2, b2 = st.packed[st.key + pfx + "fc2"]
@@ -223,6 +227,13 @@ def _mlp_bwd(dout, pfx, st, P, sv, scale_b, G):
     lsn = "layer_scale_2" if pfx == "mlp." else "layer_scale_2_e"
     df = K.scale_residual_bwd(dout, sv[pfx + "f"], P[lsn], scale_b, H * W, G[lsn])
     w2 = st.packed[st.key + pfx + "fc2"][0]
+    if T == torch.bfloat16 and _FUSE_DW:      # GELU' . dw3x3^T . weight/bias gradients . fc1 bias gradient: one kernel, dz stays on chip
+        du = _lin_bwd(df, sv[pfx + "u"], w2, G[pfx + "fc2.weight"], G[pfx + "fc2.bias"], T)
+        dh = K.mlp_dw_bwd(du, sv[pfx + "h"], P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, G[pfx + "pos.weight"], G[pfx + "pos.bias"],
+                          G[pfx + "fc1.bias"])
+        dhn = _lin_bwd(dh, sv[pfx + "hn"], st.packed[st.key + pfx + "fc1"][0], G[pfx + "fc1.weight"], None, T)
+        return K.layernorm_bwd(dhn, sv[pfx + "x"], P[pfx + "norm.weight"], sv[pfx + "mu"], sv[pfx + "rs"], dout,
+                               G[pfx + "norm.weight"], G[pfx + "norm.bias"])
     if T == torch.bfloat16 and _FUSE_GG:      # dz = (df @ W2) * gelu'(z) in the dgrad GEMM's epilogue
         dz = _lin_bwd(df, sv[pfx + "u"], w2, G[pfx + "fc2.weight"], G[pfx + "fc2.bias"], T, dx_epi=("gelu_grad", sv[pfx + "z"]))
         dh = K.dwconv_bwd(dz, sv[pfx + "h"], P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, True, K.ACT_NONE,

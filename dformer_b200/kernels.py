@@ -208,6 +208,21 @@ def dwconv_bwd(dy, x, weight, bias, B, H, W, k, add_input, act, dweight, dbias, 
     return dx
 
 
+def mlp_dw_fwd(h, weight, bias, B, H, W):
+    """u = GELU(dw3x3(h) + bias + h) for bf16 channels-last h [B*H*W, C] (DFormer.py:62-64); nothing else is stored."""
+    u = torch.empty_like(h)
+    lib().mlp_dw_fwd(h.data_ptr(), dt(h), weight.data_ptr(), _p(bias), B, H, W, h.shape[-1], u.data_ptr(), _s())
+    return u
+
+
+def mlp_dw_bwd(du, h, weight, bias, B, H, W, dweight, dbias, dh_colsum=None):
+    """Fused backward of mlp_dw_fwd: returns dh; accumulates dweight, dbias and (optionally) colsum(dh) in place."""
+    dh = torch.empty_like(du)
+    lib().mlp_dw_bwd(du.data_ptr(), h.data_ptr(), dt(h), weight.data_ptr(), _p(bias), B, H, W, h.shape[-1], dh.data_ptr(),
+                     dweight.data_ptr(), _p(dbias), _p(dh_colsum), _s())
+    return dh
+
+
 def mul_fwd(a, b, out):
     M, N = a.shape
     lib().mul_fwd(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0), dt(a), M, N, _s())

@@ -104,6 +104,17 @@ int dfb200_dwconv_bwd(const void* dy, const void* x, const void* z /* optional s
                       const float* weight, const float* bias, int B, int H, int W, int C, int k, int add_input, int act,
                       void* dz_buf, void* dx, float* dweight, float* dbias, void* stream);
 
+/* ---- fused middle of the MLP (DFormer.py:62-64), bf16 channels-last activations only (dtype must be 1) ------
+ * forward:  u = GELU(dw3x3(h) + bias + h); the pre-activation is not stored.
+ * backward: dz = du * GELU'(dw3x3(h) + bias + h) (recomputed, kept on chip), dh = dz + dw3x3^T(dz),
+ *           dweight[C,1,3,3] += dz (*) h, dbias[C] += colsum(dz), dh_colsum[C] += colsum(dh) (= fc1 bias gradient;
+ *           optional).  The three accumulators are zero-initialised by the caller (fp32, atomics).
+ * TMA-fed persistent kernels: one pass over h (+ du) and one over the output. */
+int dfb200_mlp_dw_fwd(const void* h, int dtype, const float* weight, const float* bias, int B, int H, int W, int C,
+                      void* u, void* stream);
+int dfb200_mlp_dw_bwd(const void* du, const void* h, int dtype, const float* weight, const float* bias, int B, int H,
+                      int W, int C, void* dh, float* dweight, float* dbias, float* dh_colsum, void* stream);
+
 /* ---- elementwise glue of Block/Attention ---------------------------------------------------------
  * mul:  out[m, n] = a[m, n] * b[m, n]  with independent leading dimensions (q*a, cut*e: DFormer.py:134-135;
  *       `out` is a column slice of the concat buffer of :137-140). */

@@ -135,6 +135,37 @@ def test_dwconv(dtype, k_, C, add, act):
     torch.testing.assert_close(dbias, brr.grad, rtol=3e-2 if dtype == torch.bfloat16 else 1e-3, atol=0.3 if dtype == torch.bfloat16 else 1e-2)
 
 
+@pytest.mark.parametrize("B,H,W,C", [(2, 15, 21, 256), (1, 30, 40, 64), (2, 17, 70, 72), (1, 8, 32, 128), (3, 60, 80, 192), (1, 1, 1, 8)])
+def test_mlp_dw_fused(B, H, W, C):
+    """TMA-fed fused MLP middle (bf16): u = GELU(dw3x3(h)+b+h) and its whole backward (dh, dW, db, colsum(dh)) against
+    PyTorch autograd in fp32 on the bf16-rounded inputs; also against the unfused kernels it replaces."""
+    k = K()
+    dtype = torch.bfloat16
+    h = rnd(B, H, W, C, dtype=dtype)
+    w, b = rnd(C, 1, 3, 3, scale=0.2), rnd(C, scale=0.1)
+    u = k.mlp_dw_fwd(h.view(-1, C), w, b, B, H, W)
+    hr = h.float().clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    z = F.conv2d(hr.permute(0, 3, 1, 2), wr, br, padding=1, groups=C).permute(0, 2, 3, 1) + hr
+    ref = F.gelu(z)
+    torch.testing.assert_close(u.view(B, H, W, C).float(), ref, **tol(dtype))
+    torch.testing.assert_close(u, k.dwconv_fwd(h.view(-1, C), w, b, B, H, W, 3, True, 1), rtol=1e-2, atol=1e-2)
+    du = rnd(B, H, W, C, dtype=dtype)
+    ref.backward(du.float())
+    dw, db, dc = torch.zeros_like(w), torch.zeros_like(b), torch.zeros(C, device=DEV)
+    dh = k.mlp_dw_bwd(du.view(-1, C), h.view(-1, C), w, b, B, H, W, dw, db, dc)
+    t = dict(rtol=3e-2, atol=5e-2)
+    torch.testing.assert_close(dh.view(B, H, W, C).float(), hr.grad, **t)
+    n = math.sqrt(B * H * W)
+    torch.testing.assert_close(dw, wr.grad, rtol=3e-2, atol=0.03 * n)
+    torch.testing.assert_close(db, br.grad, rtol=3e-2, atol=0.03 * n)
+    torch.testing.assert_close(dc, dh.float().sum(0), rtol=1e-3, atol=1e-2 * n)
+    torch.testing.assert_close(dc, hr.grad.reshape(-1, C).sum(0), rtol=3e-2, atol=0.03 * n)
+    # accumulation semantics: a second call adds onto the same buffers
+    k.mlp_dw_bwd(du.view(-1, C), h.view(-1, C), w, b, B, H, W, dw, db, None)
+    torch.testing.assert_close(dw, 2 * wr.grad, rtol=3e-2, atol=0.06 * n)
+
+
 # ----------------------------------------------------------------------------- gating / residual
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_mul_and_scale_residual(dtype):
