@@ -39,25 +39,83 @@ template <> __device__ __forceinline__ float from_f<float>(float v) { return v; 
 template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
 
 // Exact-erf GELU (nn.GELU() default) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, below fp32 GEMM
-// round-off) so that one MUFU.EX2 + one MUFU.RCP replace the ~25-instruction erff; the same exp(-x^2/2) serves the
-// Gaussian pdf term of the derivative.
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& e) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  e = __expf(-z * z);
-  const float poly = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
-  const float erf_abs = 1.0f - poly * e;
-  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+// round-off): one MUFU.EX2 + one MUFU.RCP (approx forms: no IEEE fix-up subroutine) replace the ~25-instruction erff,
+// and the same exp(-x^2/2) serves the Gaussian pdf term of the derivative.
+//   q(x) = 0.5 * erfc(|x|/sqrt2) = t (a1/2 + t (a2/2 + ...)) exp(-x^2/2),  t = 1 / (1 + p |x| / sqrt2)
+//   Phi(x) = x >= 0 ? 1 - q : q          GELU(x) = max(x, 0) - |x| q          GELU'(x) = Phi(x) + x exp(-x^2/2) / sqrt(2 pi)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void gelu_q(float x, float& q, float& e) {
+  const float ax = fabsf(x);
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f));
+  e = ex2_approx(x * x * -0.72134752044448170368f);                     // exp(-x^2 / 2)
+  const float poly = fmaf(fmaf(fmaf(fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f), t, 0.5f * 1.421413741f), t, 0.5f * -0.284496736f), t,
+                          0.5f * 0.254829592f) * t;
+  q = poly * e;
 }
 __device__ __forceinline__ float gelu_f(float x) {
-  float cdf, e;
-  gelu_parts(x, cdf, e);
-  return x * cdf;
+  float q, e;
+  gelu_q(x, q, e);
+  return fmaf(-fabsf(x), q, fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  float cdf, e;
-  gelu_parts(x, cdf, e);
+  float q, e;
+  gelu_q(x, q, e);
+  const float cdf = x >= 0.f ? 1.0f - q : q;
   return fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+
+// Packed-pair (FFMA2 / FMUL2) forms of the same functions: the polynomial runs on two values per issue slot.
+__device__ __forceinline__ float2 fma2(const float2& a, const float2& b, const float2& c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(r)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 mul2(const float2& a, const float2& b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 add2(const float2& a, const float2& b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ void gelu_q2(const float2& x, float2& q, float2& e, float2& ax) {
+  ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 d = fma2(splat2(0.3275911f * 0.70710678118654752440f), ax, splat2(1.0f));
+  const float2 t = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+  const float2 a = mul2(mul2(x, x), splat2(-0.72134752044448170368f));
+  e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+  float2 p = fma2(splat2(0.5f * 1.061405429f), t, splat2(0.5f * -1.453152027f));
+  p = fma2(p, t, splat2(0.5f * 1.421413741f));
+  p = fma2(p, t, splat2(0.5f * -0.284496736f));
+  p = fma2(p, t, splat2(0.5f * 0.254829592f));
+  q = mul2(mul2(p, t), e);
+}
+__device__ __forceinline__ float2 gelu2(const float2& x) {
+  float2 q, e, ax;
+  gelu_q2(x, q, e, ax);
+  const float2 r = make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f));
+  return fma2(make_float2(-ax.x, -ax.y), q, r);
+}
+__device__ __forceinline__ float2 gelu_grad2(const float2& x) {
+  float2 q, e, ax;
+  gelu_q2(x, q, e, ax);
+  const float2 cdf = make_float2(x.x >= 0.f ? 1.0f - q.x : q.x, x.y >= 0.f ? 1.0f - q.y : q.y);
+  return fma2(mul2(x, splat2(0.39894228040143267794f)), e, cdf);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

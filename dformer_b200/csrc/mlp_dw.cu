@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(NT, 2) mlp_dw_fwd_kernel(const __grid_constant
   const int c_base = blockIdx.y * 64;
   const int c0 = c_base + cq * 4;
   const int n_tiles = B * tiles_x * tiles_y;
+  const long row_stride = (long)W * C;
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
@@ -169,19 +170,14 @@ __global__ void __launch_bounds__(NT, 2) mlp_dw_fwd_kernel(const __grid_constant
 #pragma unroll
         for (int t = 0; t < 4; ++t) { acc[r][t][0] = bq[0]; acc[r][t][1] = bq[1]; }
       conv3x3_block<2, 4, false>(hT, PW, r0, x0, cq, w, acc);
-      if (c0 < C) {
+      const int oy0 = ty0 + r0, ox0 = tx0 + x0;
+      bf16* up = u + (((long)b * H + oy0) * W + ox0) * C + c0;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int oy = ty0 + r0 + r;
-          if (oy >= H) continue;
+      for (int r = 0; r < 2; ++r) {
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int ox = tx0 + x0 + t;
-            if (ox >= W) continue;
-            float2 lo = acc[r][t][0], hi = acc[r][t][1];
-            lo.x = gelu_f(lo.x); lo.y = gelu_f(lo.y); hi.x = gelu_f(hi.x); hi.y = gelu_f(hi.y);
-            *reinterpret_cast<uint2*>(u + (((long)b * H + oy) * W + ox) * C + c0) = pack4(lo, hi);
-          }
+        for (int t = 0; t < 4; ++t) {
+          const uint2 o = pack4(gelu2(acc[r][t][0]), gelu2(acc[r][t][1]));
+          if (c0 < C && oy0 + r < H && ox0 + t < W) *reinterpret_cast<uint2*>(up + (long)r * row_stride + t * C) = o;
         }
       }
     }
@@ -222,6 +218,7 @@ __global__ void __launch_bounds__(NT, 2) mlp_dw_bwd_kernel(const __grid_constant
   const int c_base = blockIdx.y * 64;
   const int c0 = c_base + cq * 4;
   const int n_tiles = B * tiles_x * tiles_y;
+  const long row_stride = (long)W * C;
   if (tid == 0) {
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -258,9 +255,7 @@ __global__ void __launch_bounds__(NT, 2) mlp_dw_bwd_kernel(const __grid_constant
         if (col0 + t < ZP) {
           float2 lo, hi;
           unpack4(zp[t * NQ], lo, hi);
-          lo.x *= gelu_grad_f(acc[0][t][0].x); lo.y *= gelu_grad_f(acc[0][t][0].y);
-          hi.x *= gelu_grad_f(acc[0][t][1].x); hi.y *= gelu_grad_f(acc[0][t][1].y);
-          zp[t * NQ] = pack4(lo, hi);
+          zp[t * NQ] = pack4(mul2(lo, gelu_grad2(acc[0][t][0])), mul2(hi, gelu_grad2(acc[0][t][1])));
         }
       }
     }
@@ -274,20 +269,19 @@ __global__ void __launch_bounds__(NT, 2) mlp_dw_bwd_kernel(const __grid_constant
 #pragma unroll
         for (int t = 0; t < 4; ++t) acc[r][t][0] = acc[r][t][1] = make_float2(0.f, 0.f);
       conv3x3_block<2, 4, true>(zT, ZP, r0, x0, cq, w, acc);
-      if (c0 < C) {
+      const int oy0 = ty0 + r0, ox0 = tx0 + x0;
+      bf16* dp = dh + (((long)b * H + oy0) * W + ox0) * C + c0;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int oy = ty0 + r0 + r;
-          if (oy >= H) continue;
+      for (int r = 0; r < 2; ++r) {
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int ox = tx0 + x0 + t;
-            if (ox >= W) continue;
-            const uint2 o = pack4(acc[r][t][0], acc[r][t][1]);
-            *reinterpret_cast<uint2*>(dh + (((long)b * H + oy) * W + ox) * C + c0) = o;
+        for (int t = 0; t < 4; ++t) {
+          const uint2 o = pack4(acc[r][t][0], acc[r][t][1]);
+          if (c0 < C && oy0 + r < H && ox0 + t < W) {
+            *reinterpret_cast<uint2*>(dp + (long)r * row_stride + t * C) = o;
             float2 lo, hi;
             unpack4(o, lo, hi);                        // the bias gradient sums the values fc1's weight gradient will read
-            gc[0].x += lo.x; gc[0].y += lo.y; gc[1].x += hi.x; gc[1].y += hi.y;
+            gc[0] = add2(gc[0], lo);
+            gc[1] = add2(gc[1], hi);
           }
         }
       }
@@ -313,7 +307,7 @@ __global__ void __launch_bounds__(NT, 2) mlp_dw_bwd_kernel(const __grid_constant
             ffma2(gw[k][0], glo, win[k][0]);
             ffma2(gw[k][1], ghi, win[k][1]);
           }
-          if (ky == 1) { gb[0].x += glo.x; gb[0].y += glo.y; gb[1].x += ghi.x; gb[1].y += ghi.y; }
+          if (ky == 1) { gb[0] = add2(gb[0], glo); gb[1] = add2(gb[1], ghi); }
         }
       }
     }

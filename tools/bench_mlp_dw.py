@@ -30,7 +30,10 @@ def timeit(fn, reps=20):
 def main():
     tot = {"fwd_old": 0.0, "fwd_new": 0.0, "bwd_old": 0.0, "bwd_new": 0.0}
     counts = {0: 3, 1: 3, 2: 3, 3: 3, 4: 12, 5: 12, 6: 2, 7: 1}
+    only = int(sys.argv[1]) if len(sys.argv) > 1 else None       # profile mode: one shape, new kernels only
     for i, (B, H, W, C) in enumerate(SHAPES):
+        if only is not None and i != only:
+            continue
         M = B * H * W
         h = torch.randn(M, C, device="cuda").bfloat16()
         du = torch.randn(M, C, device="cuda").bfloat16()
@@ -45,13 +48,19 @@ def main():
             K.mlp_dw_fwd(h, w, b, B, H, W)
 
         fwd_old()
-
         def bwd_old():
             K.dwconv_bwd(du, h, w, b, B, H, W, 3, True, K.ACT_GELU, dw, db, z=zs["z"])
             K.colsum(du, out=dc)
 
         def bwd_new():
             K.mlp_dw_bwd(du, h, w, b, B, H, W, dw, db, dc)
+
+        if only is not None:
+            for _ in range(2):
+                fwd_new()
+                bwd_new()
+            torch.cuda.synchronize()
+            return
 
         t = {n: timeit(f) for n, f in (("fwd_old", fwd_old), ("fwd_new", fwd_new), ("bwd_old", bwd_old), ("bwd_new", bwd_new))}
         by = M * C * 2
