@@ -72,10 +72,12 @@ SIGNATURES = {
     "dfb200_mu_update": [P, P, P, F, L, P, P],
     "dfb200_mu_update_bwd": [P, P, P, P, F, L, P, I, P, P, P],
     "dfb200_cast": [P, I, P, I, L, P],
+    "dfb200_cast2d": [P, I, L, P, I, L, L, I, P],
     "dfb200_axpy": [P, I, F, P, I, L, P],
     "dfb200_upsample_ce_fwd": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, P],
     "dfb200_upsample_ce_bwd_sep": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, P, I, P],
     "dfb200_ce_finalize": [P, P, P],
+    "dfb200_upsample_ce_bwd_fused": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, P, I, P],
     "dfb200_upsample_ce_bwd": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, I, P],
     "dfb200_adamw": [P, P, P, P, L, F, F, F, F, F, F, F, F, P, P, P, P],
 }

@@ -269,6 +269,17 @@ template <typename TI, typename TO>
 __global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, long n) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) out[i] = from_f<TO>(to_f(in[i]));
 }
+// strided 2-D copy/convert: out[r, c] = in[r, c] with independent leading dimensions (writes into column slices of a
+// concatenated operand buffer)
+template <typename TI, typename TO>
+__global__ void cast2d_kernel(const TI* __restrict__ in, long ld_in, TO* __restrict__ out, long ld_out, long rows, int cols) {
+  const long n = rows * cols;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / cols;
+    const int c = (int)(i - r * cols);
+    out[r * ld_out + c] = from_f<TO>(to_f(in[r * ld_in + c]));
+  }
+}
 template <typename TI, typename TO>
 __global__ void axpy_kernel(const TI* __restrict__ x, float alpha, TO* __restrict__ y, long n) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
@@ -412,6 +423,17 @@ extern "C" int dfb200_cast(const void* in, int in_dtype, void* out, int out_dtyp
   else if (in_dtype == 1 && out_dtype == 1) cast_kernel<bf16, bf16><<<g, EW_THREADS, 0, ST>>>((const bf16*)in, (bf16*)out, n);
   else { dfb_set_error("cast: bad dtypes"); return DFB_ERR_ARG; }
   return dfb_check_launch("cast");
+}
+extern "C" int dfb200_cast2d(const void* in, int in_dtype, long ld_in, void* out, int out_dtype, long ld_out, long rows, int cols, void* stream) {
+  const long n = rows * cols;
+  if (n <= 0) return DFB_OK;
+  const int g = ew_grid(n, 4);
+  if (in_dtype == 0 && out_dtype == 0) cast2d_kernel<float, float><<<g, EW_THREADS, 0, ST>>>((const float*)in, ld_in, (float*)out, ld_out, rows, cols);
+  else if (in_dtype == 0 && out_dtype == 1) cast2d_kernel<float, bf16><<<g, EW_THREADS, 0, ST>>>((const float*)in, ld_in, (bf16*)out, ld_out, rows, cols);
+  else if (in_dtype == 1 && out_dtype == 0) cast2d_kernel<bf16, float><<<g, EW_THREADS, 0, ST>>>((const bf16*)in, ld_in, (float*)out, ld_out, rows, cols);
+  else if (in_dtype == 1 && out_dtype == 1) cast2d_kernel<bf16, bf16><<<g, EW_THREADS, 0, ST>>>((const bf16*)in, ld_in, (bf16*)out, ld_out, rows, cols);
+  else { dfb_set_error("cast2d: bad dtypes"); return DFB_ERR_ARG; }
+  return dfb_check_launch("cast2d");
 }
 extern "C" int dfb200_axpy(const void* x, int x_dtype, float alpha, void* y, int y_dtype, long n, void* stream) {
   const int g = ew_grid(n, 4);

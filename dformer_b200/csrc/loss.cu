@@ -173,6 +173,105 @@ __global__ void upsample_ce_bwd_cols_kernel(const float* __restrict__ t, int B, 
   }
 }
 
+// ---- separable adjoint, recompute form (no hi-res copy of the logits is kept by the forward pass).
+// Pass 1 (rows): thread = (b, source row ly0, hi-res column ox, chunk of CH classes).  All hi-res rows whose bilinear
+// source row i0 equals ly0 share the two horizontally interpolated low-res rows top = lerp_x(small[ly0]) and
+// bot = lerp_x(small[min(ly0+1, h-1)]), so a hi-res logit costs one lerp; g = softmax - onehot is evaluated exactly once
+// per hi-res pixel and class and split between the two source rows:
+//   tA[b, ly0, ox, c] = sum (1 - wy) g        (belongs to low-res row ly0)
+//   tB[b, ly0, ox, c] = sum wy g              (belongs to low-res row min(ly0 + 1, h - 1))
+__device__ __forceinline__ int first_row_of(int ly0, int h, int H) {      // first hi-res row whose source row i0 is >= ly0
+  if (ly0 <= 0) return 0;
+  if (ly0 >= h) return H;
+  int o = (int)ceilf(((float)ly0 + 0.5f) * (float)H / (float)h - 0.5f);
+  o = max(0, min(o, H));
+  while (o > 0 && lerp_coord(o - 1, h, H).i0 >= ly0) --o;
+  while (o < H && lerp_coord(o, h, H).i0 < ly0) ++o;
+  return o;
+}
+
+template <typename T, int CH>
+__global__ void __launch_bounds__(256) upsample_ce_bwd_rows_fused_kernel(const T* __restrict__ small, int B, int h, int w, int ncls, int H, int W,
+                                                                         const int64_t* __restrict__ label, int ignore, const float* __restrict__ lse,
+                                                                         float* __restrict__ tA, float* __restrict__ tB) {
+  const int nchunk = (ncls + CH - 1) / CH;
+  const long n = (long)B * h * nchunk * W;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % W);
+    const int ck = (int)((i / W) % nchunk);
+    const int ly0 = (int)((i / ((long)W * nchunk)) % h);
+    const int b = (int)(i / ((long)W * nchunk * h));
+    const int c0 = ck * CH;
+    const Lerp lx = lerp_coord(ox, w, W);
+    const int i1 = min(ly0 + 1, h - 1);
+    const T* r0 = small + (((long)b * h + ly0) * w) * ncls + c0;
+    const T* r1 = small + (((long)b * h + i1) * w) * ncls + c0;
+    float top[CH], bot[CH], a[CH], bb[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      a[j] = bb[j] = top[j] = bot[j] = 0.f;
+      if (c0 + j < ncls) {
+        const float v00 = to_f(r0[(long)lx.i0 * ncls + j]), v01 = to_f(r0[(long)lx.i1 * ncls + j]);
+        const float v10 = to_f(r1[(long)lx.i0 * ncls + j]), v11 = to_f(r1[(long)lx.i1 * ncls + j]);
+        top[j] = (1.f - lx.w1) * v00 + lx.w1 * v01;
+        bot[j] = (1.f - lx.w1) * v10 + lx.w1 * v11;
+      }
+    }
+    const int o_lo = first_row_of(ly0, h, H), o_hi = first_row_of(ly0 + 1, h, H);
+    for (int oy = o_lo; oy < o_hi; ++oy) {
+      const long hp = ((long)b * H + oy) * W + ox;
+      const long lab = label[hp];
+      if (lab == (long)ignore || lab < 0 || lab >= ncls) continue;
+      const float ls = lse[hp];
+      const float wy = lerp_coord(oy, h, H).w1;
+      const int lj = (int)lab - c0;
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        const float v = (1.f - wy) * top[j] + wy * bot[j];
+        float g = __expf(v - ls);
+        if (j == lj) g -= 1.f;
+        a[j] += g;
+        bb[j] = fmaf(wy, g, bb[j]);
+      }
+    }
+    const long o = (((long)b * h + ly0) * W + ox) * ncls + c0;
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (c0 + j < ncls) { tA[o + j] = a[j] - bb[j]; tB[o + j] = bb[j]; }
+  }
+}
+// Pass 2 (columns): ds[b,ly,lx,c] = scale * sum_ox wx(lx,ox) * (tA[ly] + tB[ly-1] (+ tB[h-1] on the last row))[ox, c]
+template <typename TD>
+__global__ void __launch_bounds__(256) upsample_ce_bwd_cols_fused_kernel(const float* __restrict__ tA, const float* __restrict__ tB, int B, int h, int w,
+                                                                         int ncls, int W, const float* __restrict__ loss_acc,
+                                                                         const float* __restrict__ dloss, TD* __restrict__ dsmall) {
+  const long n = (long)B * h * w * ncls;
+  const float gscale = dloss[0] / loss_acc[1];
+  const float rx = (float)W / (float)w;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ncls);
+    const long pix = i / ncls;
+    const int lx = (int)(pix % w), ly = (int)((pix / w) % h), b = (int)(pix / ((long)w * h));
+    int ox_lo = max(0, (int)floorf((lx - 1) * rx) - 1), ox_hi = min(W - 1, (int)ceilf((lx + 2) * rx) + 1);
+    if (lx == 0) ox_lo = 0;
+    if (lx == w - 1) ox_hi = W - 1;
+    const float* ra = tA + (((long)b * h + ly) * W) * ncls + c;
+    const float* rb = ly > 0 ? tB + (((long)b * h + ly - 1) * W) * ncls + c : nullptr;
+    const float* rl = ly == h - 1 ? tB + (((long)b * h + ly) * W) * ncls + c : nullptr;
+    float acc = 0.f;
+    for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+      const Lerp l = lerp_coord(ox, w, W);
+      const float wx = (l.i0 == lx ? 1.f - l.w1 : 0.f) + (l.i1 == lx ? l.w1 : 0.f);
+      if (wx == 0.f) continue;
+      float v = ra[(long)ox * ncls];
+      if (rb) v += rb[(long)ox * ncls];
+      if (rl) v += rl[(long)ox * ncls];
+      acc = fmaf(wx, v, acc);
+    }
+    dsmall[i] = from_f<TD>(acc * gscale);
+  }
+}
+
 }  // namespace
 
 #define ST reinterpret_cast<cudaStream_t>(stream)
@@ -221,4 +320,26 @@ extern "C" int dfb200_upsample_ce_bwd(const void* logits_small, int dtype, int B
     default: dfb_set_error("upsample_ce_bwd: bad dtypes"); return DFB_ERR_ARG; }
 #undef L
   return dfb_check_launch("upsample_ce_bwd");
+}
+
+extern "C" int dfb200_upsample_ce_bwd_fused(const void* logits_small, int dtype, int B, int h, int w, int ncls, int H, int W, const int64_t* label,
+                                            int ignore, const float* lse, const float* loss_acc, const float* dloss, float* scratch,
+                                            void* dlogits_small, int dl_dtype, void* stream) {
+  constexpr int CH = 10;
+  const long per = (long)B * h * W * ncls;
+  float* tA = scratch;
+  float* tB = scratch + per;
+  const long n1 = (long)B * h * ((ncls + CH - 1) / CH) * W, n2 = (long)B * h * w * ncls;
+  long g1 = (n1 + 255) / 256, g2 = (n2 + 255) / 256;
+  if (g1 < 1) g1 = 1;
+  if (g2 < 1) g2 = 1;
+  DFB_DISPATCH_DTYPE(dtype, T, {
+    upsample_ce_bwd_rows_fused_kernel<T, CH><<<(unsigned)g1, 256, 0, ST>>>((const T*)logits_small, B, h, w, ncls, H, W, label, ignore, lse, tA, tB);
+  });
+  int rc = dfb_check_launch("upsample_ce_bwd_rows_fused");
+  if (rc) return rc;
+  DFB_DISPATCH_DTYPE(dl_dtype, TD, {
+    upsample_ce_bwd_cols_fused_kernel<TD><<<(unsigned)g2, 256, 0, ST>>>(tA, tB, B, h, w, ncls, W, loss_acc, dloss, (TD*)dlogits_small);
+  });
+  return dfb_check_launch("upsample_ce_bwd_cols_fused");
 }

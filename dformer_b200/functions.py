@@ -463,14 +463,32 @@ def _nmf_fwd(x, bases_raw, steps, T):
 
 
 def _nmf_bwd(dout, x, saved, T):
-    """Back-propagation through every multiplicative update (the reference does not detach them, ham_head.py:45,119)."""
+    """Back-propagation through every multiplicative update (the reference does not detach them, ham_head.py:45,119).
+
+    The gradient w.r.t. x is a sum of 2*steps + 2 rank-R products (one per use of x in a numerator, plus the initial
+    softmax).  Their factors are gathered side by side along the reduction dimension -- A_cat [B, N, slots*R],
+    B_cat [B, D, slots*R] -- and contracted by ONE GEMM with K = slots*R that writes dx once, instead of `slots`
+    read-modify-write passes over an fp32 [B, N, D] accumulator."""
     tape, rec_f, coef_fl, bases_Tl = saved
     B, N, D = x.shape
     R = coef_fl.shape[2]
     dev = x.device
     f = lambda *s: torch.empty(s, device=dev, dtype=F32)
     lo = (lambda t: t) if T == F32 else (lambda t: K.cast(t, torch.bfloat16))
-    dx = torch.zeros((B, N, D), device=dev, dtype=F32)
+    slots = 2 * len(tape) + 2
+    a_cat = torch.empty((B, N, slots * R), device=dev, dtype=T)
+    b_cat = torch.empty((B, D, slots * R), device=dev, dtype=T)
+    slot = [0]
+
+    def push(a_src, b_src):
+        """register one product  dx += a_src[B,N,R] @ b_src[B,D,R]^T ; returns the compute-dtype views of both factors"""
+        k0 = slot[0] * R
+        slot[0] += 1
+        av, bv = a_cat[:, :, k0:k0 + R], b_cat[:, :, k0:k0 + R]
+        K.cast_into(a_src, av)
+        K.cast_into(b_src, bv)
+        return av, bv
+
     sk = max(1, N // 512)
     # out = coef_f @ bases^T
     dcoef = K.bgemm(dout, bases_Tl, f(B, N, R), M=N, N=R, K=D)
@@ -480,8 +498,8 @@ def _nmf_bwd(dout, x, saved, T):
         coef, coef_l, num, den, bases_l, btb_l = rec
         dco = f(B, N, R)
         dnum, dden = K.mu_update_bwd(dcoef_new, coef, num, den, dco, False)
-        dnum_l, dden_l = lo(dnum), lo(dden)
-        K.bgemm(dnum_l, bases_l, dx, trans_b=True, M=N, N=D, K=R, accumulate=True)          # num = x @ bases
+        dnum_l, _ = push(dnum, bases_l)                                                     # num = x @ bases
+        dden_l = lo(dden)
         K.bgemm(x, dnum_l, dbases, trans_a=True, M=D, N=R, K=N, accumulate=True, splitk=sk)
         K.bgemm(dden_l, btb_l, dco, M=N, N=R, K=R, accumulate=True)                         # den = coef @ BtB (BtB symmetric)
         dbtb_l = lo(K.bgemm(coef_l, dden_l, f(B, R, R), trans_a=True, M=R, N=R, K=N, splitk=sk))
@@ -493,8 +511,8 @@ def _nmf_bwd(dout, x, saved, T):
         bases, bases_l, num2, den2, coef_l, ctc_l = rec
         dba = f(B, D, R)
         dnum2, dden2 = K.mu_update_bwd(dbases_new, bases, num2, den2, dba, False)
-        dnum2_l, dden2_l = lo(dnum2), lo(dden2)
-        K.bgemm(coef_l, dnum2_l, dx, trans_b=True, M=N, N=D, K=R, accumulate=True)          # num2 = x^T @ coef
+        _, dnum2_l = push(coef_l, dnum2)                                                    # num2 = x^T @ coef
+        dden2_l = lo(dden2)
         K.bgemm(x, dnum2_l, dcoef, M=N, N=R, K=D, accumulate=True)
         K.bgemm(dden2_l, ctc_l, dba, M=D, N=R, K=R, accumulate=True)                        # den2 = bases @ CtC
         dctc_l = lo(K.bgemm(bases_l, dden2_l, f(B, R, R), trans_a=True, M=R, N=R, K=D))
@@ -510,7 +528,10 @@ def _nmf_bwd(dout, x, saved, T):
     first = tape[0][0] if tape else rec_f
     coef0, bases0_l = first[0], first[4]
     dS = K.softmax_rows_bwd(dcoef, coef0)
-    K.bgemm(lo(dS), bases0_l, dx, trans_b=True, M=N, N=D, K=R, accumulate=True)
+    push(dS, bases0_l)
+    assert slot[0] == slots
+    dx = torch.empty((B, N, D), device=dev, dtype=T)
+    K.bgemm(a_cat, b_cat, dx, trans_b=True, M=N, N=D, K=slots * R)
     return dx
 
 
@@ -571,8 +592,7 @@ class HeadFn(torch.autograd.Function):
                                   G["hamburger.ham_out.bn.bias"], act=K.ACT_RELU, residual=sv["s"])
         dnmf = _lin_bwd(dho_pre, sv["nmf"], pk("ham_out")[0], G["hamburger.ham_out.conv.weight"].view(pk("ham_out")[0].shape), None, T)
         hin = sv["hin"]
-        dhin32 = _nmf_bwd(dnmf.view(B, h1 * w1, D), hin.view(B, h1 * w1, D), sv["nmf_saved"], T).view(M, D)
-        dhin = dhin32 if T == F32 else K.cast(dhin32, T)
+        dhin = _nmf_bwd(dnmf.view(B, h1 * w1, D), hin.view(B, h1 * w1, D), sv["nmf_saved"], T).view(M, D)
         dhin_pre = K.act_bwd(dhin, hin, K.ACT_RELU)
         ds = _lin_bwd(dhin_pre, sv["s"], pk("ham_in")[0], G["hamburger.ham_in.conv.weight"].view(pk("ham_in")[0].shape),
                       G["hamburger.ham_in.conv.bias"], T)
@@ -598,10 +618,8 @@ class UpsampleCEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, small, label, meta):
         B, h, w, ncls, H, W, ignore, want_out = meta
-        out, lse, acc, loss, up = K.upsample_ce_fwd(small, B, h, w, ncls, H, W, label, ignore, want_out=want_out, want_loss=label is not None,
-                                                    keep_up=bool(ctx.needs_input_grad[0]))
+        out, lse, acc, loss, _ = K.upsample_ce_fwd(small, B, h, w, ncls, H, W, label, ignore, want_out=want_out, want_loss=label is not None)
         ctx.meta = meta
-        ctx.up = up
         if label is not None:
             ctx.save_for_backward(small, label, lse, acc)
         if out is None:
@@ -616,11 +634,7 @@ class UpsampleCEFn(torch.autograd.Function):
         B, h, w, ncls, H, W, ignore, _ = ctx.meta
         small, label, lse, acc = ctx.saved_tensors
         dl = dloss.contiguous().float()
-        if ctx.up is not None:
-            ds = K.upsample_ce_bwd_sep(ctx.up, small.dtype, B, h, w, ncls, H, W, label, ignore, lse, acc, dl)
-            ctx.up = None
-        else:
-            ds = K.upsample_ce_bwd(small, B, h, w, ncls, H, W, label, ignore, lse, acc, dl)
+        ds = K.upsample_ce_bwd_fused(small, B, h, w, ncls, H, W, label, ignore, lse, acc, dl)
         return ds, None, None
 
 

@@ -409,6 +409,16 @@ def cast(x, dtype):
     return out
 
 
+def cast_into(x, dst):
+    """dst[..., :] = x converted to dst.dtype; x, dst are [..., cols] with unit inner stride and uniform row strides
+    (dst is typically a column slice of a concatenated operand buffer)."""
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    assert x.stride(-1) == 1 and dst.stride(-1) == 1 and dst.shape == x.shape
+    lib().cast2d(x.data_ptr(), dt(x), x.stride(-2), dst.data_ptr(), dt(dst), dst.stride(-2), rows, cols, _s())
+    return dst
+
+
 def axpy(x, alpha, y):
     lib().axpy(x.data_ptr(), dt(x), alpha, y.data_ptr(), dt(y), x.numel(), _s())
     return y
@@ -438,6 +448,15 @@ def upsample_ce_bwd_sep(up, small_dtype, B, h, w, ncls, H, W, label, ignore, lse
     scratch = torch.empty((B, ncls, h, W), device=up.device, dtype=torch.float32)
     lib().upsample_ce_bwd_sep(up.data_ptr(), dt(up), B, h, w, ncls, H, W, label.data_ptr(), ignore, lse.data_ptr(), acc.data_ptr(),
                               dloss.data_ptr(), scratch.data_ptr(), dsmall.data_ptr(), dt(dsmall), _s())
+    return dsmall
+
+
+def upsample_ce_bwd_fused(small, B, h, w, ncls, H, W, label, ignore, lse, acc, dloss):
+    """Separable adjoint of upsample+CE recomputed from the low-res logits (no hi-res copy kept by the forward pass)."""
+    dsmall = torch.empty_like(small)
+    scratch = torch.empty((2, B, h, W, ncls), device=small.device, dtype=torch.float32)
+    lib().upsample_ce_bwd_fused(small.data_ptr(), dt(small), B, h, w, ncls, H, W, label.data_ptr(), ignore, lse.data_ptr(), acc.data_ptr(),
+                                dloss.data_ptr(), scratch.data_ptr(), dsmall.data_ptr(), dt(dsmall), _s())
     return dsmall
 
 

@@ -197,6 +197,9 @@ int dfb200_mu_update(const float* a, const float* num, const float* den, float e
 int dfb200_mu_update_bwd(const float* dout, const float* a, const float* num, const float* den, float eps, long n,
                          float* da, int accumulate_da, float* dnum, float* dden, void* stream);
 int dfb200_cast(const void* in, int in_dtype, void* out, int out_dtype, long n, void* stream);
+/* strided 2-D convert/copy: out[r*ld_out + c] = in[r*ld_in + c], r < rows, c < cols (column slices of concatenated operands) */
+int dfb200_cast2d(const void* in, int in_dtype, long ld_in, void* out, int out_dtype, long ld_out, long rows, int cols,
+                  void* stream);
 int dfb200_axpy(const void* x, int x_dtype, float alpha, void* y, int y_dtype, long n, void* stream); /* y += alpha*x */
 
 /* ---- fused x8 bilinear upsample + cross entropy (builder.py:203,230) ------------------------------
@@ -216,6 +219,12 @@ int dfb200_ce_finalize(const float* loss_acc, float* loss, void* stream);
 int dfb200_upsample_ce_bwd_sep(const void* up, int up_dtype, int B, int h, int w, int ncls, int H, int W, const int64_t* label,
                                int ignore, const float* lse, const float* loss_acc, const float* dloss, float* scratch,
                                void* dlogits_small, int dl_dtype, void* stream);
+/* Separable adjoint that recomputes the hi-res logits from logits_small (nothing but lse is kept by the forward pass):
+ * rows pass (one softmax evaluation per hi-res pixel and class, split between its two source rows) then columns pass.
+ * scratch: 2*B*h*W*ncls floats. */
+int dfb200_upsample_ce_bwd_fused(const void* logits_small, int dtype, int B, int h, int w, int ncls, int H, int W,
+                                 const int64_t* label, int ignore, const float* lse, const float* loss_acc,
+                                 const float* dloss, float* scratch, void* dlogits_small, int dl_dtype, void* stream);
 int dfb200_upsample_ce_bwd(const void* logits_small, int dtype, int B, int h, int w, int ncls, int H, int W,
                            const int64_t* label, int ignore, const float* lse, const float* loss_acc, const float* dloss,
                            void* dlogits_small, int dl_dtype, void* stream);

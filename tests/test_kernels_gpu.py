@@ -417,6 +417,27 @@ def test_upsample_ce(dtype, ncls):
     ds2 = k.upsample_ce_bwd_sep(up, dtype, B, h, w, ncls, H, W, label, 255, lse2, acc2, dl)
     t2 = dict(rtol=5e-2, atol=2e-5) if dtype == torch.bfloat16 else dict(rtol=1e-3, atol=1e-7)
     torch.testing.assert_close(ds2.view(B, h, w, ncls).float(), sr.grad.permute(0, 2, 3, 1), **t2)
+    # recompute form (what training uses): nothing but lse kept by the forward pass
+    ds3 = k.upsample_ce_bwd_fused(small.view(-1, ncls), B, h, w, ncls, H, W, label, 255, lse, acc, dl)
+    torch.testing.assert_close(ds3.view(B, h, w, ncls).float(), sr.grad.permute(0, 2, 3, 1), **t)
+
+
+@pytest.mark.parametrize("h,w,H,W", [(12, 16, 96, 128), (7, 9, 30, 40), (5, 6, 5, 6), (1, 3, 8, 9), (15, 20, 33, 47), (6, 8, 6, 64)])
+def test_upsample_ce_bwd_fused_general_scales(h, w, H, W):
+    """Integer, fractional, identity and degenerate scale factors of the separable recompute-form adjoint."""
+    k = K()
+    B, ncls = 2, 13
+    small = rnd(B, h, w, ncls)
+    label = torch.randint(0, ncls, (B, H, W), device=DEV)
+    label[torch.rand(B, H, W, device=DEV) < 0.2] = 255
+    out, lse, acc, loss, _ = k.upsample_ce_fwd(small.view(-1, ncls), B, h, w, ncls, H, W, label, 255, want_out=False)
+    sr = small.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    up = F.interpolate(sr, (H, W), mode="bilinear", align_corners=False)
+    ref_loss = F.cross_entropy(up, label, reduction="none", ignore_index=255)[label != 255].mean()
+    torch.testing.assert_close(loss, ref_loss, rtol=1e-4, atol=1e-5)
+    ref_loss.backward()
+    ds = k.upsample_ce_bwd_fused(small.view(-1, ncls), B, h, w, ncls, H, W, label, 255, lse, acc, torch.ones((), device=DEV))
+    torch.testing.assert_close(ds.view(B, h, w, ncls), sr.grad.permute(0, 2, 3, 1), rtol=1e-3, atol=1e-6)
 
 
 def test_adamw_matches_torch():
