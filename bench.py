@@ -121,6 +121,7 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
+    ap.add_argument("--quick", action="store_true", help="profiling aid: print only the device-timed ms/step and exit (not a bench line)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -193,6 +194,12 @@ def main():
     barrier()
     launches = (launches_per_step * args.steps) if graphed else (lib().launch_count() - launches0)
     ms = e0.elapsed_time(e1) / args.steps
+    if args.quick:
+        sampler.stop_flag = True
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms, "skip": os.environ.get("DFB200_PROFILE_SKIP", "")}))
+        sys.stdout.flush()
+        os._exit(0)
     # ---- end-to-end: pinned host inputs -> H2D, step, loss -> D2H, every step
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -1,0 +1,339 @@
+// Global Awareness Attention core (DFormer.py:122-130) as ONE kernel per direction.
+//
+// The 49 pooled query tokens of an image attend over all H*W pixel keys/values, softmax over the pixels:
+//   S = scale * Q K^T  [49, HW]      P = softmax_HW(S)      O = P V  [49, d]             per (image, head)
+// The unfused form ran three CUDA-core GEMM launches plus a row softmax (five launches backward) and kept the
+// [B, heads, 49, HW] probabilities for the backward pass.  Here a CTA owns 128 pixels of one (image, head):
+//
+//   forward   scores for its pixels -> local row max / sum -> unnormalised partial context, written next to (max, sum);
+//             the last CTA of an (image, head) to finish (atomic ticket) merges the partials flash-decoding style and
+//             stores O and the row log-sum-exp.  Nothing of size 49 x HW reaches HBM.
+//   backward  P is recomputed from Q, K and the saved log-sum-exp; dV and dK of the CTA's pixels are complete in
+//             registers, dQ partial sums go out as one fp32 atomic per element (dm is zeroed by the launcher).
+//             rowsum(dP o P) = rowsum(dO o O), so no second pass over the pixels is needed.
+//
+// Thread pair (lanes 2i, 2i+1) = one pixel; each lane keeps half of the pixel's k, v (and dk, dv) rows in registers and
+// the two halves of every dot product meet through one shuffle.  Q / dO rows are broadcast reads from shared memory.
+#include <string.h>
+
+#include "common.cuh"
+#include "dfb200_internal.h"
+
+namespace {
+
+constexpr int NQ = 49;             // pooled query tokens (7 x 7)
+constexpr int PC = 128;            // pixels per CTA
+constexpr int SP = PC + 4;         // row pitch of the [49][PC] score tile (float4-aligned)
+constexpr int NT = 256;
+
+template <typename T>
+__device__ __forceinline__ void load_half_row(const T* __restrict__ src, float* dst, int n, bool valid) {
+#pragma unroll
+  for (int j = 0; j < n; ++j) dst[j] = valid ? to_f(src[j]) : 0.f;
+}
+
+template <int D>
+struct Geo {
+  static constexpr int DH = D / 2;
+  static constexpr int G = NT / D;                        // row groups of the [49, D] output phase
+  static constexpr int RPG = (NQ + G - 1) / G;            // rows per group
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(NT) gaa_fused_fwd_kernel(const T* __restrict__ m, const T* __restrict__ kv, int HW, int heads, float scale, int nchunks,
+                                                          float* __restrict__ out, float* __restrict__ lse, float* __restrict__ part, int* __restrict__ counters) {
+  constexpr int DH = Geo<D>::DH, G = Geo<D>::G, RPG = Geo<D>::RPG, PS = D + 4;
+  extern __shared__ __align__(16) float smf[];
+  float* Qs = smf;                       // [49][D]
+  float* Vs = Qs + NQ * D;               // [PC][D]
+  float* Ss = Vs + PC * D;               // [49][SP]
+  float* ms = Ss + NQ * SP;              // [49] local row max
+  float* ls = ms + NQ;                   // [49] local row sum
+  __shared__ int s_last;
+  const int tid = threadIdx.x, bh = blockIdx.y, b = bh / heads, head = bh % heads, c = blockIdx.x;
+  const int Cp = heads * D;
+  for (int i = tid; i < NQ * D; i += NT) Qs[i] = to_f(m[((long)b * NQ + i / D) * Cp + head * D + i % D]);
+  const int p = tid >> 1, half = tid & 1;
+  const int pix = c * PC + p;
+  const bool valid = pix < HW;
+  float kreg[DH];
+  {
+    const T* row = kv + ((long)b * HW + (valid ? pix : 0)) * 2 * Cp + head * D + half * DH;
+    load_half_row(row, kreg, DH, valid);
+    float vreg[DH];
+    load_half_row(row + Cp, vreg, DH, valid);
+#pragma unroll
+    for (int j = 0; j < DH; ++j) Vs[p * D + half * DH + j] = vreg[j];
+  }
+  __syncthreads();
+  // ---- scores of this CTA's pixels
+  float2 k2[DH / 2];
+#pragma unroll
+  for (int j = 0; j < DH / 2; ++j) k2[j] = make_float2(kreg[2 * j], kreg[2 * j + 1]);
+#pragma unroll 7
+  for (int r = 0; r < NQ; ++r) {
+    const float2* q = reinterpret_cast<const float2*>(Qs + r * D + half * DH);      // 8-byte aligned: D and DH are even
+    float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < DH / 2; ++j) ffma2(s2, q[j], k2[j]);
+    float s = s2.x + s2.y;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (half == (r & 1)) Ss[r * SP + p] = valid ? s * scale : -INFINITY;
+  }
+  __syncthreads();
+  // ---- local softmax statistics, P~ = exp(S - local max) in place
+  for (int r = tid >> 5; r < NQ; r += NT / 32) {
+    const int lane = tid & 31;
+    float v[PC / 32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < PC / 32; ++i) { v[i] = Ss[r * SP + lane + 32 * i]; mx = fmaxf(mx, v[i]); }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < PC / 32; ++i) {
+      const float e = __expf(v[i] - mx);                  // exp(-inf) = 0 for the padded tail (pixel 0 of a chunk is always real)
+      Ss[r * SP + lane + 32 * i] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) { ms[r] = mx; ls[r] = sum; }
+  }
+  __syncthreads();
+  // ---- unnormalised partial context O~[r][j] = sum_p P~[r][p] V[p][j]
+  {
+    const int j = tid % D, g = tid / D;
+    if (g < G) {
+      float acc[RPG];
+#pragma unroll
+      for (int i = 0; i < RPG; ++i) acc[i] = 0.f;
+      for (int p4 = 0; p4 < PC; p4 += 4) {
+        const float v0 = Vs[(p4 + 0) * D + j], v1 = Vs[(p4 + 1) * D + j], v2 = Vs[(p4 + 2) * D + j], v3 = Vs[(p4 + 3) * D + j];
+#pragma unroll
+        for (int i = 0; i < RPG; ++i) {
+          const int r = g + i * G;
+          if (r < NQ) {
+            const float4 pr = *reinterpret_cast<const float4*>(Ss + r * SP + p4);
+            acc[i] = fmaf(pr.x, v0, fmaf(pr.y, v1, fmaf(pr.z, v2, fmaf(pr.w, v3, acc[i]))));
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < RPG; ++i) {
+        const int r = g + i * G;
+        if (r < NQ) {
+          float* dst = part + (((long)bh * nchunks + c) * NQ + r) * PS;
+          dst[j] = acc[i];
+          if (j == 0) { dst[D] = ms[r]; dst[D + 1] = ls[r]; }
+        }
+      }
+    }
+  }
+  // ---- the last CTA of this (image, head) merges all partials
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&counters[bh], 1) == nchunks - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // (1) all (max, sum) pairs of this (image, head) -> shared memory, independent loads
+  float* pm = ls + NQ;                   // [nchunks][49] chunk maxima -> weights exp(m_c - M)   (tail of the dynamic allocation)
+  float* pl = pm + nchunks * NQ;         // [nchunks][49] chunk sums
+  const float* base = part + (long)bh * nchunks * NQ * PS;
+  for (int i = tid; i < nchunks * NQ; i += NT) {
+    const float2 ml = __ldcg(reinterpret_cast<const float2*>(base + (long)i * PS + D));
+    pm[i] = ml.x;
+    pl[i] = ml.y;
+  }
+  __syncthreads();
+  // (2) per row: global max, total sum, per-chunk weights
+  for (int r = tid >> 5; r < NQ; r += NT / 32) {
+    const int lane = tid & 31;
+    float M = -INFINITY;
+    for (int cc = lane; cc < nchunks; cc += 32) M = fmaxf(M, pm[cc * NQ + r]);
+    M = warp_max(M);
+    float L = 0.f;
+    for (int cc = lane; cc < nchunks; cc += 32) {
+      const float w = __expf(pm[cc * NQ + r] - M);
+      L = fmaf(pl[cc * NQ + r], w, L);
+      pm[cc * NQ + r] = w;
+    }
+    L = warp_sum(L);
+    if (lane == 0) { ms[r] = 1.0f / L; lse[(long)bh * NQ + r] = M + __logf(L); }
+  }
+  __syncthreads();
+  // (3) O[r][j..j+3] = sum_c w[c][r] * O~_c[r][j..j+3] / L   (float4 loads, 4 chunks in flight per thread)
+  constexpr int D4 = D / 4;
+  for (int idx = tid; idx < NQ * D4; idx += NT) {
+    const int r = idx / D4, j = (idx % D4) * 4;
+    const float* src = base + (long)r * PS + j;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int cc = 0; cc < nchunks; ++cc) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (long)cc * NQ * PS));
+      const float w = pm[cc * NQ + r];
+      o.x = fmaf(v.x, w, o.x); o.y = fmaf(v.y, w, o.y); o.z = fmaf(v.z, w, o.z); o.w = fmaf(v.w, w, o.w);
+    }
+    const float inv = ms[r];
+    *reinterpret_cast<float4*>(out + ((long)b * NQ + r) * Cp + head * D + j) = make_float4(o.x * inv, o.y * inv, o.z * inv, o.w * inv);
+  }
+  if (tid == 0) counters[bh] = 0;                        // self-resetting ticket: the buffer is reusable by the next launch
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(NT) gaa_fused_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ lse,
+                                                          const T* __restrict__ m, const T* __restrict__ kv, int HW, int heads, float scale,
+                                                          float* __restrict__ dm, T* __restrict__ dkv) {
+  constexpr int DH = Geo<D>::DH, G = Geo<D>::G, RPG = Geo<D>::RPG;
+  extern __shared__ __align__(16) float smf[];
+  float* Qs = smf;                       // [49][D]
+  float* dOs = Qs + NQ * D;              // [49][D]
+  float* Ks = dOs + NQ * D;              // [PC][D]
+  float* dSs = Ks + PC * D;              // [49][SP]
+  float* lses = dSs + NQ * SP;           // [49]
+  float* Dr = lses + NQ;                 // [49] rowsum(dO o O) = rowsum(dP o P)
+  const int tid = threadIdx.x, bh = blockIdx.y, b = bh / heads, head = bh % heads, c = blockIdx.x;
+  const int Cp = heads * D;
+  for (int i = tid; i < NQ * D; i += NT) {
+    const long g = ((long)b * NQ + i / D) * Cp + head * D + i % D;
+    Qs[i] = to_f(m[g]);
+    dOs[i] = dout[g];
+  }
+  for (int r = tid >> 5; r < NQ; r += NT / 32) {
+    const long g = ((long)b * NQ + r) * Cp + head * D;
+    float s = 0.f;
+    for (int j = tid & 31; j < D; j += 32) s = fmaf(dout[g + j], out[g + j], s);
+    s = warp_sum(s);
+    if ((tid & 31) == 0) { Dr[r] = s; lses[r] = lse[(long)bh * NQ + r]; }
+  }
+  const int p = tid >> 1, half = tid & 1;
+  const int pix = c * PC + p;
+  const bool valid = pix < HW;
+  float2 k2[DH / 2], v2[DH / 2], dk2[DH / 2], dv2[DH / 2];
+  const long rowoff = ((long)b * HW + (valid ? pix : 0)) * 2 * Cp + head * D + half * DH;
+  {
+    float kreg[DH], vreg[DH];
+    load_half_row(kv + rowoff, kreg, DH, valid);
+    load_half_row(kv + rowoff + Cp, vreg, DH, valid);
+#pragma unroll
+    for (int j = 0; j < DH; ++j) Ks[p * D + half * DH + j] = kreg[j];
+#pragma unroll
+    for (int j = 0; j < DH / 2; ++j) {
+      k2[j] = make_float2(kreg[2 * j], kreg[2 * j + 1]);
+      v2[j] = make_float2(vreg[2 * j], vreg[2 * j + 1]);
+      dk2[j] = dv2[j] = make_float2(0.f, 0.f);
+    }
+  }
+  __syncthreads();
+#pragma unroll 2
+  for (int r = 0; r < NQ; ++r) {
+    const float2* q = reinterpret_cast<const float2*>(Qs + r * D + half * DH);
+    const float2* go = reinterpret_cast<const float2*>(dOs + r * D + half * DH);
+    float2 s2 = make_float2(0.f, 0.f), dp2 = make_float2(0.f, 0.f);
+    float2 qv[DH / 2], gv[DH / 2];
+#pragma unroll
+    for (int j = 0; j < DH / 2; ++j) { qv[j] = q[j]; gv[j] = go[j]; ffma2(s2, qv[j], k2[j]); ffma2(dp2, gv[j], v2[j]); }
+    float sd = s2.x + s2.y, dp = dp2.x + dp2.y;
+    sd += __shfl_xor_sync(0xffffffffu, sd, 1);
+    dp += __shfl_xor_sync(0xffffffffu, dp, 1);
+    const float P = valid ? __expf(fmaf(sd, scale, -lses[r])) : 0.f;
+    const float ds = P * (dp - Dr[r]);
+    const float2 P2 = make_float2(P, P), ds2 = make_float2(ds, ds);
+#pragma unroll
+    for (int j = 0; j < DH / 2; ++j) { ffma2(dv2[j], P2, gv[j]); ffma2(dk2[j], ds2, qv[j]); }
+    if (half == (r & 1)) dSs[r * SP + p] = ds;
+  }
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < DH / 2; ++j) {
+      dkv[rowoff + 2 * j] = from_f<T>(dk2[j].x * scale);
+      dkv[rowoff + 2 * j + 1] = from_f<T>(dk2[j].y * scale);
+      dkv[rowoff + Cp + 2 * j] = from_f<T>(dv2[j].x);
+      dkv[rowoff + Cp + 2 * j + 1] = from_f<T>(dv2[j].y);
+    }
+  }
+  __syncthreads();
+  // ---- dQ[r][j] += scale * sum_p dS[r][p] K[p][j]   (partial over this CTA's pixels)
+  const int j = tid % D, g = tid / D;
+  if (g < G) {
+    float acc[RPG];
+#pragma unroll
+    for (int i = 0; i < RPG; ++i) acc[i] = 0.f;
+    for (int p4 = 0; p4 < PC; p4 += 4) {
+      const float k0 = Ks[(p4 + 0) * D + j], k1 = Ks[(p4 + 1) * D + j], k2 = Ks[(p4 + 2) * D + j], k3 = Ks[(p4 + 3) * D + j];
+#pragma unroll
+      for (int i = 0; i < RPG; ++i) {
+        const int r = g + i * G;
+        if (r < NQ) {
+          const float4 d4 = *reinterpret_cast<const float4*>(dSs + r * SP + p4);
+          acc[i] = fmaf(d4.x, k0, fmaf(d4.y, k1, fmaf(d4.z, k2, fmaf(d4.w, k3, acc[i]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RPG; ++i) {
+      const int r = g + i * G;
+      if (r < NQ) atomicAdd(dm + ((long)b * NQ + r) * Cp + head * D + j, acc[i] * scale);
+    }
+  }
+}
+
+template <int D> constexpr int fwd_smem() { return (NQ * D + PC * D + NQ * SP + 2 * NQ) * 4; }
+template <int D> constexpr int bwd_smem() { return (2 * NQ * D + PC * D + NQ * SP + 2 * NQ) * 4; }
+
+template <typename T, int D>
+int launch_fwd(const void* m, const void* kv, int B, int HW, int heads, float* out, float* lse, float* part, int* counters, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gaa_fused_fwd_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) { dfb_set_error("gaa_fused_fwd smem attr: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
+    attr = true;
+  }
+  const int nchunks = dfb_cdiv(HW, PC);
+  const int smem = fwd_smem<D>() + 2 * nchunks * NQ * 4;            // + merge staging of the (max, sum) pairs
+  if (smem > 200 * 1024) { dfb_set_error("gaa_fused_fwd: HW=%d too large for the one-launch merge", HW); return DFB_ERR_UNSUPPORTED; }
+  dim3 grid(nchunks, B * heads);
+  gaa_fused_fwd_kernel<T, D><<<grid, NT, smem, st>>>((const T*)m, (const T*)kv, HW, heads, 1.0f / sqrtf((float)D), nchunks, out, lse, part, counters);
+  return dfb_check_launch("gaa_fused_fwd");
+}
+
+template <typename T, int D>
+int launch_bwd(const float* dout, const float* out, const float* lse, const void* m, const void* kv, int B, int HW, int heads, float* dm, void* dkv,
+               cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gaa_fused_bwd_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<D>());
+    if (e != cudaSuccess) { dfb_set_error("gaa_fused_bwd smem attr: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
+    attr = true;
+  }
+  cudaMemsetAsync(dm, 0, sizeof(float) * (size_t)B * NQ * heads * D, st);
+  dim3 grid(dfb_cdiv(HW, PC), B * heads);
+  gaa_fused_bwd_kernel<T, D><<<grid, NT, bwd_smem<D>(), st>>>(dout, out, lse, (const T*)m, (const T*)kv, HW, heads, 1.0f / sqrtf((float)D), dm, (T*)dkv);
+  return dfb_check_launch("gaa_fused_bwd");
+}
+
+}  // namespace
+
+#define ST reinterpret_cast<cudaStream_t>(stream)
+#define GAA_DISPATCH_D(d, ...)                                        \
+  switch (d) {                                                        \
+    case 16: { constexpr int D = 16; __VA_ARGS__ } break;             \
+    case 32: { constexpr int D = 32; __VA_ARGS__ } break;             \
+    case 36: { constexpr int D = 36; __VA_ARGS__ } break;             \
+    case 48: { constexpr int D = 48; __VA_ARGS__ } break;             \
+    default: dfb_set_error("gaa_fused: head dim %d not instantiated (16, 32, 36, 48)", d); return DFB_ERR_UNSUPPORTED; \
+  }
+
+extern "C" int dfb200_gaa_fused_fwd(const void* m, const void* kv, int dtype, int B, int HW, int heads, int d, float* out, float* lse, float* scratch,
+                                    int* counters, void* stream) {
+  DFB_REQUIRE(B > 0 && HW > 0 && heads > 0, "gaa_fused_fwd: empty problem");
+  DFB_DISPATCH_DTYPE(dtype, T, { GAA_DISPATCH_D(d, { return launch_fwd<T, D>(m, kv, B, HW, heads, out, lse, scratch, counters, ST); }) });
+  return DFB_OK;
+}
+
+extern "C" int dfb200_gaa_fused_bwd(const float* dout, const float* out, const float* lse, const void* m, const void* kv, int dtype, int B, int HW,
+                                    int heads, int d, float* dm, void* dkv, void* stream) {
+  DFB_REQUIRE(B > 0 && HW > 0 && heads > 0, "gaa_fused_bwd: empty problem");
+  DFB_DISPATCH_DTYPE(dtype, T, { GAA_DISPATCH_D(d, { return launch_bwd<T, D>(dout, out, lse, m, kv, B, HW, heads, dm, dkv, ST); }) });
+  return DFB_OK;
+}

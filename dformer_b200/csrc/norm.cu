@@ -337,26 +337,43 @@ __global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* 
 __device__ __forceinline__ float act_fwd(float z, int act) { return act == 1 ? gelu_f(z) : (act == 2 ? fmaxf(z, 0.f) : z); }
 __device__ __forceinline__ float act_bwd(float z, int act) { return act == 1 ? gelu_grad_f(z) : (act == 2 ? (z > 0.f ? 1.f : 0.f) : 1.f); }
 
+// Thread = one fixed 8-channel vector x a lane of rows (same decomposition as bn_stats): the per-channel affine
+// z = x * (gamma * invstd) + (beta - mean * gamma * invstd) sits in 16 registers for the thread's whole row range, so the
+// streaming loop is one 16-byte load, 8 FMAs (+ activation) and one 16-byte store.
 template <typename TX, typename TY>
-__global__ void bn_apply_kernel(const TX* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, const TY* __restrict__ residual, int act, const float* __restrict__ chan_scale,
-                                int rows_per_sample, int M, int C, TY* __restrict__ y) {
-  const int nvec = C >> 3;
-  const long n = (long)M * nvec;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const long r = i / nvec; const int c = (int)(i % nvec) * 8;
+__global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const TX* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              const TY* __restrict__ residual, int act, const float* __restrict__ chan_scale,
+                                                              int rows_per_sample, int M, int C, TY* __restrict__ y, int rows_per_block) {
+  const int nvec_all = C >> 3;
+  const int v0 = blockIdx.y * BN_THREADS;
+  const int nvec = min(BN_THREADS, nvec_all - v0);
+  const int rl_count = BN_THREADS / nvec, active = rl_count * nvec;
+  const int t = threadIdx.x;
+  if (t >= active) return;
+  const int cv = t % nvec, rl = t / nvec, c = (v0 + cv) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = gamma[c + j] * invstd[c + j];
+    sh[j] = fmaf(-mean[c + j], sc[j], beta[c + j]);
+  }
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  for (int r = r0 + rl; r < r1; r += rl_count) {
+    const long off = (long)r * C + c;
     float v[8], res[8];
-    Vec8<TX>::load(x + i * 8, v);
-    if (residual) Vec8<TY>::load(residual + i * 8, res);
+    Vec8<TX>::load(x + off, v);
+    if (residual) Vec8<TY>::load(residual + off, res);
+    const float* cs = chan_scale ? chan_scale + (long)(r / rows_per_sample) * C + c : nullptr;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float z = (v[j] - mean[c + j]) * invstd[c + j] * gamma[c + j] + beta[c + j];
+      float z = fmaf(v[j], sc[j], sh[j]);
       if (residual) z += res[j];
       z = act_fwd(z, act);
-      if (chan_scale) z *= chan_scale[(r / rows_per_sample) * C + c + j];
+      if (cs) z *= cs[j];
       v[j] = z;
     }
-    Vec8<TY>::store(y + i * 8, v);
+    Vec8<TY>::store(y + off, v);
   }
 }
 
@@ -414,37 +431,55 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const TY* __r
   }
 }
 
+// dx = gamma*invstd * (g - mean(g) - xhat * mean(g*xhat)) = p*g + q*x + r with per-channel p, q, r in registers
+// (same thread decomposition as bn_apply): two FMAs per element.
 template <typename TX, typename TY, typename TD>
-__global__ void bn_bwd_apply_kernel(const TY* __restrict__ gbuf, const TX* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ gamma, const float* __restrict__ sum_g, const float* __restrict__ sum_gx, float inv_count,
-                                    int training, int M, int C, TD* __restrict__ dx) {
-  const int nvec = C >> 3;
-  const long n = (long)M * nvec;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % nvec) * 8;
-    float g[8], xv[8];
-    Vec8<TY>::load(gbuf + i * 8, g);
-    Vec8<TX>::load(x + i * 8, xv);
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const TY* __restrict__ gbuf, const TX* __restrict__ x, const float* __restrict__ mean,
+                                                                  const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ sum_g, const float* __restrict__ sum_gx, float inv_count,
+                                                                  int training, int M, int C, TD* __restrict__ dx, int rows_per_block) {
+  const int nvec_all = C >> 3;
+  const int v0 = blockIdx.y * BN_THREADS;
+  const int nvec = min(BN_THREADS, nvec_all - v0);
+  const int rl_count = BN_THREADS / nvec, active = rl_count * nvec;
+  const int t = threadIdx.x;
+  if (t >= active) return;
+  const int cv = t % nvec, rl = t / nvec, c = (v0 + cv) * 8;
+  float p[8], q[8], rr[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float k = gamma[c + j] * invstd[c + j];
-      if (training) {
-        const float xh = (xv[j] - mean[c + j]) * invstd[c + j];
-        g[j] = k * (g[j] - sum_g[c + j] * inv_count - xh * sum_gx[c + j] * inv_count);
-      } else {
-        g[j] = k * g[j];
-      }
+  for (int j = 0; j < 8; ++j) {
+    const float is = invstd[c + j], k = gamma[c + j] * is;
+    p[j] = k;
+    if (training) {
+      const float a = sum_g[c + j] * inv_count, b = sum_gx[c + j] * inv_count * is;     // xhat * mean(g xhat) = (x - mu) * b
+      q[j] = -k * b;
+      rr[j] = k * (b * mean[c + j] - a);
+    } else {
+      q[j] = 0.f;
+      rr[j] = 0.f;
     }
-    Vec8<TD>::store(dx + i * 8, g);
+  }
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  for (int r = r0 + rl; r < r1; r += rl_count) {
+    const long off = (long)r * C + c;
+    float g[8], xv[8];
+    Vec8<TY>::load(gbuf + off, g);
+    Vec8<TX>::load(x + off, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = fmaf(p[j], g[j], fmaf(q[j], xv[j], rr[j]));
+    Vec8<TD>::store(dx + off, g);
   }
 }
 
-inline int ew_grid(long n) {
-  long b = (n + 255) / 256;
-  if (b < 1) b = 1;
-  const long cap = 148L * 16;
-  return (int)(b > cap ? cap : b);
+// rows per CTA of the streaming BN kernels: ~8 resident CTAs per SM, each thread walking >= 4 rows
+inline int bn_stream_rows(int M, int C) {
+  const int nvec = C / 8 < BN_THREADS ? C / 8 : BN_THREADS;
+  const int lanes = BN_THREADS / nvec;
+  int rpb = dfb_cdiv(M, 148 * 8);
+  if (rpb < 4 * lanes) rpb = 4 * lanes;
+  return rpb;
 }
+
 inline int rows_per_block(int M) { int r = dfb_cdiv(M, 148 * 4); return r < 32 ? 32 : r; }
 
 }  // namespace
@@ -468,7 +503,9 @@ extern "C" int dfb200_layernorm_bwd(const void* dy, int dy_dtype, const float* x
                                     const float* dx_in, float* dx, float* dgamma, float* dbeta, void* stream) {
   DFB_REQUIRE(C >= 1 && C <= 32 * LN_MAX_PER_LANE, "layernorm: C=%d out of range", C);
   if (M <= 0) return DFB_OK;
-  const int grid = min(dfb_cdiv(M, 8), 148 * 8);
+  // every CTA ends with 2*C global atomics (dgamma, dbeta): >= 32 rows per CTA keeps that tail below the streaming work
+  // at the small-M stages (M = 9600: 300 CTAs instead of 1184 contending for the same 2*C addresses)
+  const int grid = min(dfb_cdiv(M, 32), 148 * 8);
   if (C % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dx_in)) & 15) == 0) {
     DFB_DISPATCH_DTYPE(dy_dtype, T, {
       LN_DISPATCH_VEC(C, { ln_bwd_vec_kernel<T, L, VPL><<<grid, 256, 2 * C * sizeof(float), ST>>>((const T*)dy, x, gamma, mean, rstd, M, C, dx_in, dx, dgamma, dbeta); });
@@ -507,8 +544,10 @@ extern "C" int dfb200_bn_eval_stats(const float* running_mean, const float* runn
 extern "C" int dfb200_bn_apply(const void* x, int x_dtype, const float* mean, const float* invstd, const float* gamma, const float* beta,
                                const void* residual, int act, const float* chan_scale, int rows_per_sample, int M, int C, void* y, int y_dtype, void* stream) {
   DFB_REQUIRE(C % 8 == 0, "bn_apply: C %% 8 != 0 (C=%d)", C);
-  const int grid = ew_grid((long)M * C / 8);
-#define L(TX, TY) bn_apply_kernel<TX, TY><<<grid, 256, 0, ST>>>((const TX*)x, mean, invstd, gamma, beta, (const TY*)residual, act, chan_scale, rows_per_sample, M, C, (TY*)y)
+  if (M <= 0) return DFB_OK;
+  const int rpb = bn_stream_rows(M, C);
+  dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(C / 8, BN_THREADS));
+#define L(TX, TY) bn_apply_kernel<TX, TY><<<grid, BN_THREADS, 0, ST>>>((const TX*)x, mean, invstd, gamma, beta, (const TY*)residual, act, chan_scale, rows_per_sample, M, C, (TY*)y, rpb)
   if (x_dtype == 0 && y_dtype == 0) L(float, float);
   else if (x_dtype == 0 && y_dtype == 1) L(float, bf16);
   else if (x_dtype == 1 && y_dtype == 1) L(bf16, bf16);
@@ -537,9 +576,11 @@ extern "C" int dfb200_bn_bwd_reduce(const void* dy, int y_dtype, const void* x, 
 extern "C" int dfb200_bn_bwd_apply(const void* gbuf, int y_dtype, const void* x, int x_dtype, const float* mean, const float* invstd, const float* gamma,
                                    const float* sum_g, const float* sum_gx, float count, int training, int M, int C, void* dx, int dx_dtype, void* stream) {
   DFB_REQUIRE(C % 8 == 0, "bn_bwd_apply: C %% 8 != 0 (C=%d)", C);
-  const int grid = ew_grid((long)M * C / 8);
+  if (M <= 0) return DFB_OK;
   const float inv = 1.f / count;
-#define L(TX, TY, TD) bn_bwd_apply_kernel<TX, TY, TD><<<grid, 256, 0, ST>>>((const TY*)gbuf, (const TX*)x, mean, invstd, gamma, sum_g, sum_gx, inv, training, M, C, (TD*)dx)
+  const int rpb = bn_stream_rows(M, C);
+  dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(C / 8, BN_THREADS));
+#define L(TX, TY, TD) bn_bwd_apply_kernel<TX, TY, TD><<<grid, BN_THREADS, 0, ST>>>((const TY*)gbuf, (const TX*)x, mean, invstd, gamma, sum_g, sum_gx, inv, training, M, C, (TD*)dx, rpb)
   const int key = x_dtype * 4 + y_dtype * 2 + dx_dtype;
   switch (key) {
     case 0: L(float, float, float); break;

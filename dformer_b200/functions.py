@@ -22,6 +22,7 @@ import os as _os
 # epilogue is already the critical resource (A/B in profiles/r01_ab_fused_epilogues.txt) -> off by default
 _FUSE_RES = _os.environ.get("DFB200_FUSE_RES", "0") == "1"
 _FUSE_GG = _os.environ.get("DFB200_FUSE_GG", "0") == "1"
+_FUSE_GAA = _os.environ.get("DFB200_FUSE_GAA", "1") == "1"    # one-launch attention core (csrc/gaa_fused.cu); 0 = GEMM + softmax chain
 _FUSE_DW = _os.environ.get("DFB200_FUSE_DW", "1") == "1"      # fused MLP middle (csrc/mlp_dw.cu); 0 = the unfused chain, kept for A/B runs
 
 
@@ -291,10 +292,16 @@ class BlockFn(torch.autograd.Function):
                 side2.wait_event(ev_en)
                 pooled = K.pool7_fwd(xn, en, B, H, W)
                 m = _lin(pooled, pk("attn.short_cut_linear"), T)
-                o7, probs = K.gaa_fwd(m, kv, B, HW, st.heads, Ce // st.heads)
+                dh_ = Ce // st.heads
+                if _FUSE_GAA and dh_ in K.GAA_FUSED_DIMS:           # one launch; keeps only the row log-sum-exp
+                    o7, lse7 = K.gaa_fused_fwd(m, kv, B, HW, st.heads, dh_)
+                    probs = None
+                else:
+                    o7, probs = K.gaa_fwd(m, kv, B, HW, st.heads, dh_)
+                    lse7 = None
                 K.resize_fwd(o7, B, 7, 7, y, H, W, col0=C)
-            K.share(main, kv, pooled, m, probs, o7)
-            sv.update(kv=kv, pooled=pooled, m=m, probs=probs)
+            K.share(main, kv, pooled, m, probs, o7, lse7)
+            sv.update(kv=kv, pooled=pooled, m=m, probs=probs, o7=o7, lse7=lse7)
         cv = K.dwconv_fwd(l, P["attn.conv.weight"], P["attn.conv.bias"], B, H, W, 7)
         a = _lin(cv, pk("attn.a"), T)
         K.mul_fwd(qcl[:, :C], a, y[:, :C])
@@ -383,7 +390,10 @@ class BlockFn(torch.autograd.Function):
             with torch.cuda.stream(side2):
                 do7 = torch.empty((B * 49, Ce), device=dev, dtype=F32)
                 K.resize_bwd(dy, C, B, 7, 7, Ce, H, W, do7)
-                dm, dkv = K.gaa_bwd(do7, sv["m"], sv["kv"], sv["probs"], B, HW, st.heads, Ce // st.heads)
+                if sv["probs"] is None:
+                    dm, dkv = K.gaa_fused_bwd(do7, sv["o7"], sv["lse7"], sv["m"], sv["kv"], B, HW, st.heads, Ce // st.heads)
+                else:
+                    dm, dkv = K.gaa_bwd(do7, sv["m"], sv["kv"], sv["probs"], B, HW, st.heads, Ce // st.heads)
                 dmT = dm if T == F32 else K.cast(dm, T)
                 dpooled = _lin_bwd(dmT, sv["pooled"], pk("attn.short_cut_linear")[0], G["attn.short_cut_linear.weight"],
                                    G["attn.short_cut_linear.bias"], T)

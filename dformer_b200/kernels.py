@@ -297,6 +297,32 @@ def gaa_bwd(dout, m, kv, probs, B, HW, heads, d):
     return dm, dkv
 
 
+GAA_FUSED_DIMS = (16, 32, 36, 48)
+_GAA_COUNTERS = {}
+
+
+def gaa_fused_fwd(m, kv, B, HW, heads, d):
+    """One-launch attention core: returns (out [B*49, heads*d] fp32, lse [B*heads*49] fp32)."""
+    dev = m.device
+    out = torch.empty((B * 49, heads * d), device=dev, dtype=torch.float32)
+    lse = torch.empty((B * heads * 49,), device=dev, dtype=torch.float32)
+    scratch = torch.empty((B * heads * ((HW + 127) // 128) * 49 * (d + 4),), device=dev, dtype=torch.float32)
+    key = (dev, torch.cuda.current_stream().cuda_stream)
+    cnt = _GAA_COUNTERS.get(key)                      # self-resetting tickets: one persistent zeroed buffer per (device, stream)
+    if cnt is None or cnt.numel() < B * heads:
+        cnt = _GAA_COUNTERS[key] = torch.zeros(max(B * heads, 1024), device=dev, dtype=torch.int32)
+    lib().gaa_fused_fwd(m.data_ptr(), kv.data_ptr(), dt(m), B, HW, heads, d, out.data_ptr(), lse.data_ptr(), scratch.data_ptr(), cnt.data_ptr(), _s())
+    return out, lse
+
+
+def gaa_fused_bwd(dout, out, lse, m, kv, B, HW, heads, d):
+    dm = torch.empty((B * 49, heads * d), device=m.device, dtype=torch.float32)
+    dkv = torch.empty_like(kv)
+    lib().gaa_fused_bwd(dout.data_ptr(), out.data_ptr(), lse.data_ptr(), m.data_ptr(), kv.data_ptr(), dt(m), B, HW, heads, d, dm.data_ptr(),
+                        dkv.data_ptr(), _s())
+    return dm, dkv
+
+
 def resize_fwd(inp, B, Hi, Wi, out, Ho, Wo, col0=0):
     C = inp.shape[-1]
     lib().resize_fwd(inp.data_ptr(), dt(inp), B, Hi, Wi, C, out.data_ptr(), dt(out), Ho, Wo, out.stride(0), col0, _s())

@@ -147,6 +147,15 @@ int dfb200_gaa_fwd(const void* m, const void* kv, int dtype, int B, int HW, int 
  * scratch: 2 * B*heads*49*HW floats (dP / dS). */
 int dfb200_gaa_bwd(const float* dout, const void* m, const void* kv, const float* probs, int dtype, int B, int HW,
                    int heads, int d, float* dm, void* dkv, float* scratch, void* stream);
+
+/* Fused form of the same attention core (one launch per direction, nothing of size 49 x HW in HBM; head dim d in
+ * {16, 32, 36, 48}).  forward: out [B*49, heads*d] fp32, lse [B*heads*49] (row log-sum-exp kept for backward);
+ * scratch: B*heads*ceil(HW/128)*49*(d+4) floats of partials; counters: B*heads ints, zero before the first call
+ * (self-resetting).  backward: recomputes the probabilities from (m, kv, lse); dm is zero-filled by the launcher. */
+int dfb200_gaa_fused_fwd(const void* m, const void* kv, int dtype, int B, int HW, int heads, int d, float* out, float* lse,
+                         float* scratch, int* counters, void* stream);
+int dfb200_gaa_fused_bwd(const float* dout, const float* out, const float* lse, const void* m, const void* kv, int dtype,
+                         int B, int HW, int heads, int d, float* dm, void* dkv, void* stream);
 /* bilinear (align_corners=False) resize of a channels-last map into a column slice of a wider buffer:
  * out[b, y, x, col0 + c] = interp(in[b, :, :, c]).  Used for 7x7 -> HxW (DFormer.py:131), the head's
  * resize+concat (ham_head.py:226-233) with fp32 inputs. */

@@ -225,7 +225,7 @@ def test_pool7(dtype, H, W):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("HW,heads,d", [(1200, 4, 36), (300, 8, 32), (4800, 2, 48), (6, 8, 16)])
+@pytest.mark.parametrize("HW,heads,d", [(1200, 4, 36), (300, 8, 32), (4800, 2, 48), (6, 8, 16), (129, 1, 48), (256, 3, 16)])
 def test_gaa(dtype, HW, heads, d):
     k = K()
     B, Cp = 2, heads * d
@@ -245,6 +245,15 @@ def test_gaa(dtype, HW, heads, d):
     t = dict(rtol=3e-2, atol=3e-2) if dtype == torch.bfloat16 else dict(rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(dm, mr.grad, rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(dkv.float(), kvr.grad, **t)
+    # one-launch fused form (keeps only the row log-sum-exp); run twice: the ticket counters must reset themselves
+    for _ in range(2):
+        out2, lse = k.gaa_fused_fwd(m, kv, B, HW, heads, d)
+        torch.testing.assert_close(out2, ref, rtol=1e-3, atol=1e-3)
+        ref_lse = torch.logsumexp((q * d ** -0.5) @ kk.transpose(-2, -1), dim=-1).reshape(-1)
+        torch.testing.assert_close(lse, ref_lse.detach(), rtol=1e-3, atol=1e-3)
+        dm2, dkv2 = k.gaa_fused_bwd(dout, out2, lse, m, kv, B, HW, heads, d)
+        torch.testing.assert_close(dm2, mr.grad, rtol=1e-3, atol=1e-3)
+        torch.testing.assert_close(dkv2.float(), kvr.grad, **t)
 
 
 @pytest.mark.parametrize("in_dtype,out_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16)])
