@@ -8,7 +8,7 @@ LIB := dformer_b200/libdformer_b200.so
 
 all: $(LIB)
 
-build/%.o: dformer_b200/csrc/%.cu dformer_b200/csrc/common.cuh dformer_b200/csrc/dfb200_internal.h include/dfb200.h
+build/%.o: dformer_b200/csrc/%.cu dformer_b200/csrc/common.cuh dformer_b200/csrc/tile_common.cuh dformer_b200/csrc/dfb200_internal.h include/dfb200.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

@@ -5,3 +5,7 @@
 int dfb_gemm_simt(const dfb200_gemm_args& g, cudaStream_t st);
 int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st);
 bool dfb_gemm_tc_supported(const dfb200_gemm_args& g);
+
+// TMA-fed bf16 depthwise 7x7 (dw7.cu): y = dw7x7(x) + bias (flip = 0) or the data gradient dw7x7^T (flip = 1); weight/bias gradient
+int dfb_dw7_conv(const void* x, const float* weight, const float* bias, int B, int H, int W, int C, int flip, void* y, cudaStream_t st);
+int dfb_dw7_wgrad(const void* dz, const void* x, int B, int H, int W, int C, float* dweight, float* dbias, cudaStream_t st);

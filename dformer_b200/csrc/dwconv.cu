@@ -547,10 +547,17 @@ int launch_conv(const T* x, const T* dy, const float* w, const float* b, int B, 
 
 #define ST reinterpret_cast<cudaStream_t>(stream)
 
+static bool dw7_tma() {      // DFB200_DW7_TMA=0 selects the older cp.async kernels of this file (A/B runs)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DFB200_DW7_TMA"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+
 extern "C" int dfb200_dwconv_fwd(const void* x, int dtype, const float* weight, const float* bias, int B, int H, int W, int C, int k, int add_input,
                                  int act, void* y, void* z_out, void* stream) {
   DFB_REQUIRE(C % 8 == 0, "dwconv: C %% 8 != 0 (C=%d)", C);
   DFB_REQUIRE(k == 3 || k == 7, "dwconv: k must be 3 or 7");
+  if (k == 7 && dtype == 1 && !add_input && act == 0 && z_out == nullptr && dw7_tma()) return dfb_dw7_conv(x, weight, bias, B, H, W, C, 0, y, ST);
   DFB_DISPATCH_DTYPE(dtype, T, {
     if (k == 3) return launch_conv<T, 3, 0>((const T*)x, nullptr, weight, bias, B, H, W, C, add_input, act, (T*)y, (T*)z_out, ST);
     return launch_conv<T, 7, 0>((const T*)x, nullptr, weight, bias, B, H, W, C, add_input, act, (T*)y, (T*)z_out, ST);
@@ -568,6 +575,13 @@ extern "C" int dfb200_dwconv_bwd(const void* dy, const void* x, const void* z, i
   DFB_REQUIRE(C % 8 == 0, "dwconv: C %% 8 != 0 (C=%d)", C);
   DFB_REQUIRE(k == 3 || k == 7, "dwconv: k must be 3 or 7");
   DFB_REQUIRE(act == 0 || dz_buf != nullptr, "dwconv_bwd: dz_buf required when act != 0");
+  if (k == 7 && dtype == 1 && !add_input && act == 0 && dw7_tma()) {
+    if (dx) {
+      const int rc = dfb_dw7_conv(dy, weight, nullptr, B, H, W, C, 1, dx, ST);
+      if (rc) return rc;
+    }
+    return dweight ? dfb_dw7_wgrad(dy, x, B, H, W, C, dweight, dbias, ST) : DFB_OK;
+  }
   const long total_strips = (long)B * H * ((W + WG_TW - 1) / WG_TW);
   const int cchunks = dfb_cdiv(C, 64);
   int spb = dfb_cdiv(total_strips, dfb_cdiv(148 * 6, cchunks));     // ~6 CTAs per SM overall

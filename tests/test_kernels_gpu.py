@@ -135,6 +135,29 @@ def test_dwconv(dtype, k_, C, add, act):
     torch.testing.assert_close(dbias, brr.grad, rtol=3e-2 if dtype == torch.bfloat16 else 1e-3, atol=0.3 if dtype == torch.bfloat16 else 1e-2)
 
 
+@pytest.mark.parametrize("B,H,W,C", [(2, 30, 40, 144), (1, 17, 70, 64), (2, 60, 80, 96), (1, 9, 45, 48), (3, 15, 20, 288), (1, 5, 3, 40), (1, 33, 50, 192)])
+def test_dw7_tma(B, H, W, C):
+    """TMA-fed depthwise 7x7 (bf16): forward, data gradient and weight/bias gradient for both slab widths (48 / 64 channels),
+    both tile heights, partial slabs and partial tiles."""
+    k = K()
+    dtype = torch.bfloat16
+    x = rnd(B, H, W, C, dtype=dtype)
+    w, b = rnd(C, 1, 7, 7, scale=0.1), rnd(C, scale=0.1)
+    y = k.dwconv_fwd(x.view(-1, C), w, b, B, H, W, 7)
+    xr = x.float().clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.conv2d(xr.permute(0, 3, 1, 2), wr, br, padding=3, groups=C).permute(0, 2, 3, 1)
+    torch.testing.assert_close(y.view(B, H, W, C).float(), ref, **tol(dtype))
+    dy = rnd(B, H, W, C, dtype=dtype)
+    ref.backward(dy.float())
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    dx = k.dwconv_bwd(dy.view(-1, C), x.view(-1, C), w, b, B, H, W, 7, False, 0, dw, db)
+    torch.testing.assert_close(dx.view(B, H, W, C).float(), xr.grad, rtol=3e-2, atol=5e-2)
+    n = math.sqrt(B * H * W)
+    torch.testing.assert_close(dw, wr.grad, rtol=3e-2, atol=0.03 * n)
+    torch.testing.assert_close(db, br.grad, rtol=3e-2, atol=0.03 * n)
+
+
 @pytest.mark.parametrize("B,H,W,C", [(2, 15, 21, 256), (1, 30, 40, 64), (2, 17, 70, 72), (1, 8, 32, 128), (3, 60, 80, 192), (1, 1, 1, 8)])
 def test_mlp_dw_fused(B, H, W, C):
     """TMA-fed fused MLP middle (bf16): u = GELU(dw3x3(h)+b+h) and its whole backward (dh, dW, db, colsum(dh)) against
