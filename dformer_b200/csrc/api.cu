@@ -1,5 +1,6 @@
 // C-ABI glue: error reporting, version, GEMM backend dispatch.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -12,6 +13,12 @@ void dfb_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool dfb_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DFB200_PDL"); v = e ? atoi(e) : 1; }
+  return v != 0;
 }
 
 static long g_launches = 0;

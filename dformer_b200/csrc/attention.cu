@@ -14,6 +14,7 @@ __device__ __forceinline__ int win_end(int i, int n) { return ((i + 1) * n + 6) 
 
 template <typename T>
 __global__ void pool7_fwd_kernel(const T* __restrict__ xn, int C1, const T* __restrict__ en, int C2, int B, int H, int W, T* __restrict__ out) {
+  pdl_sync();
   const int Ct = C1 + C2, nvec = Ct >> 3;
   const long n = (long)B * 49 * nvec;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -42,6 +43,7 @@ __global__ void pool7_fwd_kernel(const T* __restrict__ xn, int C1, const T* __re
 // gather form: each pixel belongs to <= 2 x 2 (overlapping) windows
 template <typename T>
 __global__ void pool7_bwd_kernel(const T* __restrict__ dout, int C1, int C2, int B, int H, int W, T* __restrict__ dxn, T* __restrict__ den) {
+  pdl_sync();
   const int Ct = C1 + C2, nvec = Ct >> 3;
   const long n = (long)B * H * W * nvec;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -83,6 +85,7 @@ __device__ __forceinline__ Lerp lerp_coord(int o, int n_in, int n_out) {
 
 template <typename TI, typename TO>
 __global__ void resize_fwd_kernel(const TI* __restrict__ in, int B, int Hi, int Wi, int C, TO* __restrict__ out, int Ho, int Wo, long ldo, int col0) {
+  pdl_sync();
   const int nvec = C >> 3;
   const long n = (long)B * Ho * Wo * nvec;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -110,6 +113,7 @@ __global__ void resize_fwd_kernel(const TI* __restrict__ in, int B, int Hi, int 
 template <typename TO, typename TI>
 __global__ void resize_bwd_kernel(const TO* __restrict__ dout, long ldo, int col0, int B, int Hi, int Wi, int C, int Ho, int Wo, TI* __restrict__ din,
                                   int accumulate) {
+  pdl_sync();
   const int nvec = C >> 3;
   const long n = (long)B * Hi * Wi * nvec;
   const float ry = (float)Ho / (float)Hi, rx = (float)Wo / (float)Wi;
@@ -155,6 +159,7 @@ __global__ void resize_bwd_kernel(const TO* __restrict__ dout, long ldo, int col
 template <typename TO, typename TI>
 __global__ void __launch_bounds__(256) resize_bwd_warp_kernel(const TO* __restrict__ dout, long ldo, int col0, int B, int Hi, int Wi, int C, int Ho, int Wo,
                                                              TI* __restrict__ din, int accumulate) {
+  pdl_sync();
   const int nvec = C >> 3;
   const long n = (long)B * Hi * Wi * nvec;
   const float ry = (float)Ho / (float)Hi, rx = (float)Wo / (float)Wi;
@@ -207,6 +212,7 @@ inline int ew_grid(long n) {
 
 // dS = P * (dP - rowsum(dP * P)), in place on dP
 __global__ void softmax_bwd_inplace_kernel(float* __restrict__ dP, const float* __restrict__ P, int rows, int cols) {
+  pdl_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   float* g = dP + (long)row * cols;
@@ -224,14 +230,14 @@ __global__ void softmax_bwd_inplace_kernel(float* __restrict__ dP, const float* 
 extern "C" int dfb200_pool7_fwd(const void* xn, int C1, const void* en, int C2, int dtype, int B, int H, int W, void* out, void* stream) {
   DFB_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0, "pool7: channels must be multiples of 8");
   DFB_DISPATCH_DTYPE(dtype, T, {
-    pool7_fwd_kernel<T><<<ew_grid((long)B * 49 * (C1 + C2) / 8), 256, 0, ST>>>((const T*)xn, C1, (const T*)en, C2, B, H, W, (T*)out);
+    dfb_launch(pool7_fwd_kernel<T>, ew_grid((long)B * 49 * (C1 + C2) / 8), 256, 0, ST, (const T*)xn, C1, (const T*)en, C2, B, H, W, (T*)out);
   });
   return dfb_check_launch("pool7_fwd");
 }
 extern "C" int dfb200_pool7_bwd(const void* dout, int C1, int C2, int dtype, int B, int H, int W, void* dxn, void* den, void* stream) {
   DFB_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0, "pool7: channels must be multiples of 8");
   DFB_DISPATCH_DTYPE(dtype, T, {
-    pool7_bwd_kernel<T><<<ew_grid((long)B * H * W * (C1 + C2) / 8), 256, 0, ST>>>((const T*)dout, C1, C2, B, H, W, (T*)dxn, (T*)den);
+    dfb_launch(pool7_bwd_kernel<T>, ew_grid((long)B * H * W * (C1 + C2) / 8), 256, 0, ST, (const T*)dout, C1, C2, B, H, W, (T*)dxn, (T*)den);
   });
   return dfb_check_launch("pool7_bwd");
 }
@@ -240,7 +246,7 @@ extern "C" int dfb200_resize_fwd(const void* in, int in_dtype, int B, int Hi, in
                                  void* stream) {
   DFB_REQUIRE(C % 8 == 0 && ldo % 8 == 0 && col0 % 8 == 0, "resize: C, ldo, col0 must be multiples of 8");
   const int g = ew_grid((long)B * Ho * Wo * C / 8);
-#define L(TI, TO) resize_fwd_kernel<TI, TO><<<g, 256, 0, ST>>>((const TI*)in, B, Hi, Wi, C, (TO*)out, Ho, Wo, ldo, col0)
+#define L(TI, TO) dfb_launch(resize_fwd_kernel<TI, TO>, g, 256, 0, ST, (const TI*)in, B, Hi, Wi, C, (TO*)out, Ho, Wo, ldo, col0)
   if (in_dtype == 0 && out_dtype == 0) L(float, float);
   else if (in_dtype == 0 && out_dtype == 1) L(float, bf16);
   else if (in_dtype == 1 && out_dtype == 1) L(bf16, bf16);
@@ -257,8 +263,8 @@ extern "C" int dfb200_resize_bwd(const void* dout, int out_dtype, long ldo, int 
   const int g = coop ? (int)min(work / 8 + 1, 148L * 16) : ew_grid(work);
 #define L(TO, TI)                                                                                                                        \
   do {                                                                                                                                   \
-    if (coop) resize_bwd_warp_kernel<TO, TI><<<g, 256, 0, ST>>>((const TO*)dout, ldo, col0, B, Hi, Wi, C, Ho, Wo, (TI*)din, accumulate); \
-    else resize_bwd_kernel<TO, TI><<<g, 256, 0, ST>>>((const TO*)dout, ldo, col0, B, Hi, Wi, C, Ho, Wo, (TI*)din, accumulate);           \
+    if (coop) dfb_launch(resize_bwd_warp_kernel<TO, TI>, g, 256, 0, ST, (const TO*)dout, ldo, col0, B, Hi, Wi, C, Ho, Wo, (TI*)din, accumulate); \
+    else dfb_launch(resize_bwd_kernel<TO, TI>, g, 256, 0, ST, (const TO*)dout, ldo, col0, B, Hi, Wi, C, Ho, Wo, (TI*)din, accumulate);           \
   } while (0)
   if (in_dtype == 0 && out_dtype == 0) L(float, float);
   else if (in_dtype == 0 && out_dtype == 1) L(bf16, float);
@@ -328,7 +334,7 @@ extern "C" int dfb200_gaa_bwd(const float* dout, const void* m, const void* kv, 
   rc = dfb_gemm_simt(g, ST);
   if (rc) return rc;
   // dS = P * (dP - rowsum(dP*P))   (in place)
-  softmax_bwd_inplace_kernel<<<dfb_cdiv(B * heads * 49, 8), 256, 0, ST>>>(dP, probs, B * heads * 49, HW);
+  dfb_launch(softmax_bwd_inplace_kernel, dfb_cdiv(B * heads * 49, 8), 256, 0, ST, dP, probs, B * heads * 49, HW);
   rc = dfb_check_launch("gaa softmax bwd");
   if (rc) return rc;
   // dQ = scale * dS K

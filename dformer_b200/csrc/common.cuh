@@ -32,6 +32,36 @@ int dfb_check_launch(const char* what);
 
 static inline int dfb_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL).  Every kernel of this library is launched with the programmatic-stream-serialization
+// attribute (DFB200_PDL=0 turns it off) and begins with pdl_sync() = griddepcontrol.wait: the kernel may be scheduled while the
+// previous kernel of the stream drains, and blocks there until that kernel has completed and its memory is visible.  All
+// global-memory accesses of a kernel come after its pdl_sync(), so what overlaps is launch latency / CTA scheduling (and, in
+// the tcgen05 GEMM, the barrier / tensor-memory prologue).  Inside a captured CUDA graph the same-stream kernel->kernel edges
+// become programmatic edges.  Measured on the DFormer-L step: 28.72 -> 28.44 ms.  An early griddepcontrol.launch_dependents at
+// kernel entry (-DDFB_PDL_EARLY_TRIGGER) was measured SLOWER (29.42 ms): the waiting CTAs of the next kernel take SM slots
+// from the kernels of the three other streams of the step.
+__device__ __forceinline__ void pdl_sync() {
+#ifdef DFB_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool dfb_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void dfb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = dfb_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface through dfb_check_launch (cudaPeekAtLastError)
+}
+
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f(float v);

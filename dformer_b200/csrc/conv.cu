@@ -10,6 +10,7 @@ namespace {
 template <typename TI, typename TO>
 __global__ void im2col_scalar_kernel(const TI* __restrict__ in, long sb, long sy, long sx, long sc, int B, int H, int W, int Cin, TO* __restrict__ out,
                                      int ld) {
+  pdl_sync();
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const long n = (long)B * Ho * Wo * ld;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -29,6 +30,7 @@ __global__ void im2col_scalar_kernel(const TI* __restrict__ in, long sb, long sy
 // channels-last, Cin % 8 == 0, ld == 9*Cin: one thread moves one 8-channel vector of one tap
 template <typename TI, typename TO>
 __global__ void im2col_vec_kernel(const TI* __restrict__ in, int B, int H, int W, int Cin, TO* __restrict__ out) {
+  pdl_sync();
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const int nvec = Cin >> 3;
   const long n = (long)B * Ho * Wo * 9 * nvec;
@@ -47,6 +49,7 @@ __global__ void im2col_vec_kernel(const TI* __restrict__ in, int B, int H, int W
 // col2im (gather): input pixel (y, x) is referenced by <= 2 x 2 (output pixel, tap) pairs
 template <typename TC, typename TI>
 __global__ void col2im_kernel(const TC* __restrict__ dcol, int ld, int B, int H, int W, int Cin, TI* __restrict__ din) {
+  pdl_sync();
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const int nvec = Cin >> 3;
   const long n = (long)B * H * W * nvec;
@@ -94,8 +97,8 @@ extern "C" int dfb200_im2col3x3s2_fwd(const void* in, int in_dtype, long sb, lon
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const bool cl = (sc == 1 && sx == Cin && sy == (long)W * Cin && sb == (long)H * W * Cin);
   const bool vec = cl && (Cin % 8 == 0) && ld == 9 * Cin;
-#define LV(TI, TO) im2col_vec_kernel<TI, TO><<<ew_grid((long)B * Ho * Wo * 9 * Cin / 8), 256, 0, ST>>>((const TI*)in, B, H, W, Cin, (TO*)out)
-#define LS(TI, TO) im2col_scalar_kernel<TI, TO><<<ew_grid((long)B * Ho * Wo * ld), 256, 0, ST>>>((const TI*)in, sb, sy, sx, sc, B, H, W, Cin, (TO*)out, ld)
+#define LV(TI, TO) dfb_launch(im2col_vec_kernel<TI, TO>, ew_grid((long)B * Ho * Wo * 9 * Cin / 8), 256, 0, ST, (const TI*)in, B, H, W, Cin, (TO*)out)
+#define LS(TI, TO) dfb_launch(im2col_scalar_kernel<TI, TO>, ew_grid((long)B * Ho * Wo * ld), 256, 0, ST, (const TI*)in, sb, sy, sx, sc, B, H, W, Cin, (TO*)out, ld)
   const int key = in_dtype * 2 + out_dtype;
   if (vec) {
     switch (key) { case 0: LV(float, float); break; case 1: LV(float, bf16); break; case 2: LV(bf16, float); break; case 3: LV(bf16, bf16); break;
@@ -112,7 +115,7 @@ extern "C" int dfb200_im2col3x3s2_fwd(const void* in, int in_dtype, long sb, lon
 extern "C" int dfb200_im2col3x3s2_bwd(const void* dcol, int col_dtype, int ld, int B, int H, int W, int Cin, void* din, int in_dtype, void* stream) {
   DFB_REQUIRE(Cin % 8 == 0 && ld % 8 == 0, "col2im: Cin and ld must be multiples of 8");
   const int g = ew_grid((long)B * H * W * Cin / 8);
-#define L(TC, TI) col2im_kernel<TC, TI><<<g, 256, 0, ST>>>((const TC*)dcol, ld, B, H, W, Cin, (TI*)din)
+#define L(TC, TI) dfb_launch(col2im_kernel<TC, TI>, g, 256, 0, ST, (const TC*)dcol, ld, B, H, W, Cin, (TI*)din)
   const int key = col_dtype * 2 + in_dtype;
   switch (key) { case 0: L(float, float); break; case 1: L(float, bf16); break; case 2: L(bf16, float); break; case 3: L(bf16, bf16); break;
     default: dfb_set_error("col2im: bad dtypes"); return DFB_ERR_ARG; }

@@ -29,6 +29,7 @@ template <int SW, int TY, bool FLIP>
 __global__ void __launch_bounds__(NT, 3) dw7_conv_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ weight,
                                                         const float* __restrict__ bias, bf16* __restrict__ y, int B, int H, int W, int C, int tiles_x,
                                                         int tiles_y) {
+  pdl_sync();
   constexpr int NQ = Slab<SW>::NQ, NPG = Slab<SW>::NPG, TX = Slab<SW>::TX;
   constexpr int PW = TX + 6, PH = TY + 6, TILE_BYTES = PH * PW * SW * 2;
   constexpr int SEGS = TX / 8, NBLK = TY * SEGS;
@@ -110,6 +111,7 @@ template <int SW, int TY>
 __global__ void __launch_bounds__(NT, 2) dw7_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDZ,
                                                          float* __restrict__ dweight, float* __restrict__ dbias, int B, int H, int W, int C, int tiles_x,
                                                          int tiles_y) {
+  pdl_sync();
   constexpr int NQ = Slab<SW>::NQ, NPG = Slab<SW>::NPG, TX = Slab<SW>::TX;
   constexpr int PW = TX + 6, PH = TY + 6, X_BYTES = PH * PW * SW * 2, Z_BYTES = TY * TX * SW * 2;
   constexpr int SEGS = TX / 8, ITEMS = TY * SEGS, PARTS = NPG / 7;
@@ -221,7 +223,7 @@ int launch_conv(const bf16* x, const float* weight, const float* bias, int B, in
   if (rc) return rc;
   const int tiles_x = dfb_cdiv(W, TX), tiles_y = dfb_cdiv(H, TY), n_tiles = B * tiles_x * tiles_y;
   dim3 grid(gx_max < n_tiles ? gx_max : n_tiles, dfb_cdiv(C, SW));
-  dw7_conv_kernel<SW, TY, FLIP><<<grid, NT, smem, st>>>(tm, weight, bias, y, B, H, W, C, tiles_x, tiles_y);
+  dfb_launch(dw7_conv_kernel<SW, TY, FLIP>, grid, NT, smem, st, tm, weight, bias, y, B, H, W, C, tiles_x, tiles_y);
   return dfb_check_launch("dw7_conv");
 }
 
@@ -242,7 +244,7 @@ int launch_wgrad(const bf16* dz, const bf16* x, int B, int H, int W, int C, floa
   if (rc) return rc;
   const int tiles_x = dfb_cdiv(W, TX), tiles_y = dfb_cdiv(H, TY), n_tiles = B * tiles_x * tiles_y;
   dim3 grid(gx_max < n_tiles ? gx_max : n_tiles, dfb_cdiv(C, SW));
-  dw7_wgrad_kernel<SW, TY><<<grid, NT, smem, st>>>(tmX, tmZ, dweight, dbias, B, H, W, C, tiles_x, tiles_y);
+  dfb_launch(dw7_wgrad_kernel<SW, TY>, grid, NT, smem, st, tmX, tmZ, dweight, dbias, B, H, W, C, tiles_x, tiles_y);
   return dfb_check_launch("dw7_wgrad");
 }
 

@@ -23,6 +23,7 @@ template <typename T, int K, int MODE>
 __global__ void __launch_bounds__(CB / 8 * STRIPS) dwconv_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ weight,
                                                                 const float* __restrict__ bias, int B, int H, int W, int C, int add_input, int act,
                                                                 T* __restrict__ y, T* __restrict__ zout) {
+  pdl_sync();
   __shared__ float wsm[K * K][CB];
   __shared__ float bsm[CB];
   const int c_base = blockIdx.y * CB;
@@ -162,6 +163,7 @@ template <int K, int MODE>
 __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ weight,
                                                           const float* __restrict__ bias, int B, int H, int W, int C, int add_input, int act,
                                                           bf16* __restrict__ y, bf16* __restrict__ zout, int tiles_x, int tiles_y) {
+  pdl_sync();
   constexpr int R = K / 2, SW = TL_TX + K - 1, SH = TL_TY + K - 1;
   extern __shared__ __align__(16) uint8_t dsm[];
   uint4* tile = reinterpret_cast<uint4*>(dsm);                       // [SH][SW][8]
@@ -272,7 +274,7 @@ int launch_tiled(const bf16* x, const bf16* dy, const float* w, const float* b, 
   }
   const int tiles_x = dfb_cdiv(W, TL_TX), tiles_y = dfb_cdiv(H, TL_TY);
   dim3 grid((unsigned)((long)B * tiles_x * tiles_y), dfb_cdiv(C, 64));
-  dwconv_tiled_kernel<K, MODE><<<grid, 256, smem, st>>>(x, dy, w, b, B, H, W, C, add_input, act, y, zout, tiles_x, tiles_y);
+  dfb_launch(dwconv_tiled_kernel<K, MODE>, grid, 256, smem, st, x, dy, w, b, B, H, W, C, add_input, act, y, zout, tiles_x, tiles_y);
   return dfb_check_launch("dwconv_tiled");
 }
 
@@ -286,6 +288,7 @@ constexpr int WG_TW = 8;
 template <typename T, int K>
 __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const T* __restrict__ dz, const T* __restrict__ x, int B, int H, int W, int C,
                                                           float* __restrict__ dweight, float* __restrict__ dbias, int strips_per_block) {
+  pdl_sync();
   constexpr int R = K / 2;
   constexpr int LANES = 256 / (8 * K);             // strip lanes per CTA (k=3: 10, k=7: 4)
   __shared__ float red[K][8][K * 8 + 8];           // [ky][cv][kx*8 + j] (+8: bias partial), strip lanes combined by smem atomics
@@ -409,6 +412,7 @@ __device__ __forceinline__ void wgrad_issue_tile(uint4* xt, uint4* zt, const bf1
 template <int K, bool DB>
 __global__ void __launch_bounds__(256) dwconv_wgrad_tiled_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ x, int B, int H, int W, int C,
                                                                 float* __restrict__ dweight, float* __restrict__ dbias, int tiles_x, int tiles_y) {
+  pdl_sync();
   constexpr int R = K / 2, SW = TL_TX + K - 1, SH = TL_TY + K - 1;
   constexpr int P = 32 / K;                          // parts per kernel row (k=3: 10, k=7: 4)
   constexpr int ITEMS = TL_TY * (TL_TX / 8);         // (row, 8-pixel segment) items per tile = 32
@@ -522,7 +526,7 @@ int launch_wgrad_tiled(const bf16* dz, const bf16* x, int B, int H, int W, int C
   if (gx > n_tiles) gx = n_tiles;
   if (gx < 1) gx = 1;
   dim3 grid(gx, chunks);
-  dwconv_wgrad_tiled_kernel<K, DB><<<grid, 256, smem, st>>>(dz, x, B, H, W, C, dweight, dbias, tiles_x, tiles_y);
+  dfb_launch(dwconv_wgrad_tiled_kernel<K, DB>, grid, 256, smem, st, dz, x, B, H, W, C, dweight, dbias, tiles_x, tiles_y);
   return dfb_check_launch("dwconv_wgrad_tiled");
 }
 
@@ -539,7 +543,7 @@ int launch_conv(const T* x, const T* dy, const float* w, const float* b, int B, 
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, dfb_cdiv(C, CB));
-  dwconv_kernel<T, K, MODE><<<grid, CB / 8 * STRIPS, 0, st>>>(x, dy, w, b, B, H, W, C, add_input, act, y, zout);
+  dfb_launch(dwconv_kernel<T, K, MODE>, grid, CB / 8 * STRIPS, 0, st, x, dy, w, b, B, H, W, C, add_input, act, y, zout);
   return dfb_check_launch("dwconv");
 }
 
@@ -612,8 +616,8 @@ extern "C" int dfb200_dwconv_bwd(const void* dy, const void* x, const void* z, i
         return wgrad7_db() ? launch_wgrad_tiled<7, true>((const bf16*)dz, (const bf16*)x, B, H, W, C, dweight, dbias, ST)
                            : launch_wgrad_tiled<7, false>((const bf16*)dz, (const bf16*)x, B, H, W, C, dweight, dbias, ST);
       }
-      if (k == 3) dwconv_wgrad_kernel<T, 3><<<wgrid, 256, 0, ST>>>(dz, (const T*)x, B, H, W, C, dweight, dbias, ppb);
-      else dwconv_wgrad_kernel<T, 7><<<wgrid, 256, 0, ST>>>(dz, (const T*)x, B, H, W, C, dweight, dbias, ppb);
+      if (k == 3) dfb_launch(dwconv_wgrad_kernel<T, 3>, wgrid, 256, 0, ST, dz, (const T*)x, B, H, W, C, dweight, dbias, ppb);
+      else dfb_launch(dwconv_wgrad_kernel<T, 7>, wgrid, 256, 0, ST, dz, (const T*)x, B, H, W, C, dweight, dbias, ppb);
       return dfb_check_launch("dwconv_wgrad");
     }
     return DFB_OK;

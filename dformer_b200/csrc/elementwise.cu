@@ -53,6 +53,7 @@ __device__ __forceinline__ void colreduce_body(int M, int C, int rows_per_block,
 
 template <typename T>
 __global__ void __launch_bounds__(EW_THREADS) colsum_kernel(const T* __restrict__ X, long ldx, int M, int N, float* out, int rows_per_block) {
+  pdl_sync();
   extern __shared__ float smem[];
   float* outs[1] = {out};
   colreduce_body<T, 1>(M, N, rows_per_block,
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(EW_THREADS) colsum_kernel(const T* __restrict_
 
 template <typename T>
 __global__ void colsum_scalar_kernel(const T* __restrict__ X, long ldx, int M, int N, float* out, int rows_per_block) {
+  pdl_sync();
   const int n = blockIdx.y * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
@@ -84,6 +86,7 @@ inline int pick_rows_per_block(int M) {
 // ------------------------------------------------------------------ parameter packing
 template <typename T>
 __global__ void pack_params_kernel(const dfb200_pack_entry* __restrict__ table, int max_elems) {
+  pdl_sync();
   const dfb200_pack_entry e = table[blockIdx.y];
   T* dst = reinterpret_cast<T*>(e.dst);
   if (e.kind == 0) {
@@ -104,6 +107,7 @@ __global__ void pack_params_kernel(const dfb200_pack_entry* __restrict__ table, 
 }
 
 __global__ void unpack_conv_grad_kernel(const float* __restrict__ dWp, int ld, int Cout, int Cin, float* __restrict__ dW) {
+  pdl_sync();
   const long n = (long)Cout * Cin * 9;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const int co = (int)(i / (Cin * 9)), rem = (int)(i % (Cin * 9));
@@ -115,6 +119,7 @@ __global__ void unpack_conv_grad_kernel(const float* __restrict__ dWp, int ld, i
 // ------------------------------------------------------------------ gating multiply
 template <typename T>
 __global__ void mul_fwd_kernel(const T* __restrict__ a, long lda, const T* __restrict__ b, long ldb, T* __restrict__ o, long ldo, int M, int nvec) {
+  pdl_sync();
   const long n = (long)M * nvec;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const long r = i / nvec; const int c = (int)(i % nvec) * 8;
@@ -129,6 +134,7 @@ __global__ void mul_fwd_kernel(const T* __restrict__ a, long lda, const T* __res
 template <typename T>
 __global__ void mul_bwd_kernel(const T* __restrict__ dout, long ldo, const T* __restrict__ a, long lda, const T* __restrict__ b, long ldb,
                                T* __restrict__ da, long ldda, T* __restrict__ db, long lddb, int M, int nvec) {
+  pdl_sync();
   const long n = (long)M * nvec;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const long r = i / nvec; const int c = (int)(i % nvec) * 8;
@@ -146,6 +152,7 @@ __global__ void mul_bwd_kernel(const T* __restrict__ dout, long ldo, const T* __
 // ------------------------------------------------------------------ stand-alone activation
 template <typename T>
 __global__ void act_fwd_kernel(const T* __restrict__ in, long ldi, T* __restrict__ out, long ldo, int act, int M, int nvec) {
+  pdl_sync();
   const long n = (long)M * nvec;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const long r = i / nvec; const int c = (int)(i % nvec) * 8;
@@ -158,6 +165,7 @@ __global__ void act_fwd_kernel(const T* __restrict__ in, long ldi, T* __restrict
 }
 template <typename T>
 __global__ void act_bwd_kernel(const T* __restrict__ dout, long lddo, const T* __restrict__ z, long ldz, T* __restrict__ din, long lddi, int act, int M, int nvec) {
+  pdl_sync();
   const long n = (long)M * nvec;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const long r = i / nvec; const int c = (int)(i % nvec) * 8;
@@ -174,6 +182,7 @@ __global__ void act_bwd_kernel(const T* __restrict__ dout, long lddo, const T* _
 template <typename T>
 __global__ void scale_residual_fwd_kernel(const float* __restrict__ res, const T* __restrict__ y, long ldy, const float* __restrict__ ls,
                                           const float* __restrict__ scale_b, int M, int nvec, int rows_per_sample, float* __restrict__ out) {
+  pdl_sync();
   const long n = (long)M * nvec;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const long r = i / nvec; const int c = (int)(i % nvec) * 8;
@@ -191,6 +200,7 @@ template <typename T>
 __global__ void __launch_bounds__(EW_THREADS) scale_residual_bwd_kernel(const float* __restrict__ dout, const T* __restrict__ y, long ldy, const float* __restrict__ ls,
                                                                         const float* __restrict__ scale_b, int M, int C, int rows_per_sample,
                                                                         T* __restrict__ dy, long lddy, float* dls, int rows_per_block) {
+  pdl_sync();
   extern __shared__ float smem[];
   float* outs[1] = {dls};
   colreduce_body<T, 1>(M, C, rows_per_block,
@@ -209,6 +219,7 @@ __global__ void __launch_bounds__(EW_THREADS) scale_residual_bwd_kernel(const fl
 
 // ------------------------------------------------------------------ NMF helpers
 __global__ void normalize_cols_kernel(const float* __restrict__ in, int D, int R, float* __restrict__ out, float* __restrict__ norms) {
+  pdl_sync();
   // one block per image b; thread r handles column r of the [D,R] matrix: out = in / max(||col||_2, 1e-12)
   const int b = blockIdx.x;
   const float* src = in + (long)b * D * R;
@@ -224,6 +235,7 @@ __global__ void normalize_cols_kernel(const float* __restrict__ in, int D, int R
 }
 
 __global__ void softmax_rows_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out) {
+  pdl_sync();
   // one warp per row
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -239,6 +251,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ in, int rows, int 
   for (int c = lane; c < cols; c += 32) y[c] = __expf(x[c] - m) * inv;
 }
 __global__ void softmax_rows_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, int rows, int cols, float* __restrict__ din) {
+  pdl_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float* g = dout + (long)row * cols;
@@ -251,11 +264,13 @@ __global__ void softmax_rows_bwd_kernel(const float* __restrict__ dout, const fl
 }
 
 __global__ void mu_update_kernel(const float* __restrict__ a, const float* __restrict__ num, const float* __restrict__ den, float eps, long n, float* __restrict__ out) {
+  pdl_sync();
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     out[i] = a[i] * num[i] / (den[i] + eps);
 }
 __global__ void mu_update_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ a, const float* __restrict__ num, const float* __restrict__ den,
                                      float eps, long n, float* __restrict__ da, int acc_da, float* __restrict__ dnum, float* __restrict__ dden) {
+  pdl_sync();
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const float inv = 1.f / (den[i] + eps), g = dout[i];
     const float ga = g * num[i] * inv;
@@ -267,12 +282,14 @@ __global__ void mu_update_bwd_kernel(const float* __restrict__ dout, const float
 
 template <typename TI, typename TO>
 __global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, long n) {
+  pdl_sync();
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) out[i] = from_f<TO>(to_f(in[i]));
 }
 // strided 2-D copy/convert: out[r, c] = in[r, c] with independent leading dimensions (writes into column slices of a
 // concatenated operand buffer)
 template <typename TI, typename TO>
 __global__ void cast2d_kernel(const TI* __restrict__ in, long ld_in, TO* __restrict__ out, long ld_out, long rows, int cols) {
+  pdl_sync();
   const long n = rows * cols;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const long r = i / cols;
@@ -282,6 +299,7 @@ __global__ void cast2d_kernel(const TI* __restrict__ in, long ld_in, TO* __restr
 }
 template <typename TI, typename TO>
 __global__ void axpy_kernel(const TI* __restrict__ x, float alpha, TO* __restrict__ y, long n) {
+  pdl_sync();
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     y[i] = from_f<TO>(fmaf(alpha, to_f(x[i]), to_f(y[i])));
 }
@@ -289,6 +307,7 @@ __global__ void axpy_kernel(const TI* __restrict__ x, float alpha, TO* __restric
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n, float lr_s, float b1,
                              float b2, float eps, float wd_s, float c1, float c2, float gs, const float* __restrict__ wd_arr,
                              const float* __restrict__ lr_arr, const float* __restrict__ dyn) {
+  pdl_sync();
   if (dyn) {                                                // schedule state lives on the device (CUDA-graph replays)
     lr_s = dyn[0];
     c1 = 1.f - powf(b1, dyn[1]);
@@ -322,10 +341,10 @@ extern "C" int dfb200_colsum(const void* X, int dtype, long ldx, int M, int N, f
   DFB_DISPATCH_DTYPE(dtype, T, {
     if (vec) {
       dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(N / 8, EW_THREADS));
-      colsum_kernel<T><<<grid, EW_THREADS, EW_THREADS * 8 * sizeof(float), ST>>>((const T*)X, ldx, M, N, out, rpb);
+      dfb_launch(colsum_kernel<T>, grid, EW_THREADS, EW_THREADS * 8 * sizeof(float), ST, (const T*)X, ldx, M, N, out, rpb);
     } else {
       dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(N, 128));
-      colsum_scalar_kernel<T><<<grid, 128, 0, ST>>>((const T*)X, ldx, M, N, out, rpb);
+      dfb_launch(colsum_scalar_kernel<T>, grid, 128, 0, ST, (const T*)X, ldx, M, N, out, rpb);
     }
   });
   return dfb_check_launch("colsum");
@@ -338,37 +357,37 @@ extern "C" int dfb200_pack_params(const dfb200_pack_entry* table_dev, int n_entr
   if (gx < 1) gx = 1;
   if (gx > 64) gx = 64;
   dim3 grid(gx, n_entries);
-  DFB_DISPATCH_DTYPE(dst_dtype, T, { pack_params_kernel<T><<<grid, EW_THREADS, 0, ST>>>(table_dev, max_elems); });
+  DFB_DISPATCH_DTYPE(dst_dtype, T, { dfb_launch(pack_params_kernel<T>, grid, EW_THREADS, 0, ST, table_dev, max_elems); });
   return dfb_check_launch("pack_params");
 }
 
 extern "C" int dfb200_unpack_conv_grad(const float* dWp, int ld, int Cout, int Cin, float* dW, void* stream) {
-  unpack_conv_grad_kernel<<<ew_grid((long)Cout * Cin * 9), EW_THREADS, 0, ST>>>(dWp, ld, Cout, Cin, dW);
+  dfb_launch(unpack_conv_grad_kernel, ew_grid((long)Cout * Cin * 9), EW_THREADS, 0, ST, dWp, ld, Cout, Cin, dW);
   return dfb_check_launch("unpack_conv_grad");
 }
 
 extern "C" int dfb200_mul_fwd(const void* a, long lda, const void* b, long ldb, void* out, long ldo, int dtype, int M, int N, void* stream) {
   DFB_REQUIRE(N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 8 == 0, "mul: N and leading dims must be multiples of 8");
-  DFB_DISPATCH_DTYPE(dtype, T, { mul_fwd_kernel<T><<<ew_grid((long)M * N / 8), EW_THREADS, 0, ST>>>((const T*)a, lda, (const T*)b, ldb, (T*)out, ldo, M, N / 8); });
+  DFB_DISPATCH_DTYPE(dtype, T, { dfb_launch(mul_fwd_kernel<T>, ew_grid((long)M * N / 8), EW_THREADS, 0, ST, (const T*)a, lda, (const T*)b, ldb, (T*)out, ldo, M, N / 8); });
   return dfb_check_launch("mul_fwd");
 }
 extern "C" int dfb200_mul_bwd(const void* dout, long ldo, const void* a, long lda, const void* b, long ldb, void* da, long ldda, void* db, long lddb,
                               int dtype, int M, int N, void* stream) {
   DFB_REQUIRE(N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 8 == 0 && ldda % 8 == 0 && lddb % 8 == 0, "mul_bwd: alignment");
   DFB_DISPATCH_DTYPE(dtype, T, {
-    mul_bwd_kernel<T><<<ew_grid((long)M * N / 8), EW_THREADS, 0, ST>>>((const T*)dout, ldo, (const T*)a, lda, (const T*)b, ldb, (T*)da, ldda, (T*)db, lddb, M, N / 8);
+    dfb_launch(mul_bwd_kernel<T>, ew_grid((long)M * N / 8), EW_THREADS, 0, ST, (const T*)dout, ldo, (const T*)a, lda, (const T*)b, ldb, (T*)da, ldda, (T*)db, lddb, M, N / 8);
   });
   return dfb_check_launch("mul_bwd");
 }
 
 extern "C" int dfb200_act_fwd(const void* in, long ldi, void* out, long ldo, int dtype, int act, int M, int N, void* stream) {
   DFB_REQUIRE(N % 8 == 0 && ldi % 8 == 0 && ldo % 8 == 0 && (act == 1 || act == 2), "act_fwd: bad arguments");
-  DFB_DISPATCH_DTYPE(dtype, T, { act_fwd_kernel<T><<<ew_grid((long)M * N / 8), EW_THREADS, 0, ST>>>((const T*)in, ldi, (T*)out, ldo, act, M, N / 8); });
+  DFB_DISPATCH_DTYPE(dtype, T, { dfb_launch(act_fwd_kernel<T>, ew_grid((long)M * N / 8), EW_THREADS, 0, ST, (const T*)in, ldi, (T*)out, ldo, act, M, N / 8); });
   return dfb_check_launch("act_fwd");
 }
 extern "C" int dfb200_act_bwd(const void* dout, long lddo, const void* z, long ldz, void* din, long lddi, int dtype, int act, int M, int N, void* stream) {
   DFB_REQUIRE(N % 8 == 0 && lddo % 8 == 0 && ldz % 8 == 0 && lddi % 8 == 0 && (act == 1 || act == 2), "act_bwd: bad arguments");
-  DFB_DISPATCH_DTYPE(dtype, T, { act_bwd_kernel<T><<<ew_grid((long)M * N / 8), EW_THREADS, 0, ST>>>((const T*)dout, lddo, (const T*)z, ldz, (T*)din, lddi, act, M, N / 8); });
+  DFB_DISPATCH_DTYPE(dtype, T, { dfb_launch(act_bwd_kernel<T>, ew_grid((long)M * N / 8), EW_THREADS, 0, ST, (const T*)dout, lddo, (const T*)z, ldz, (T*)din, lddi, act, M, N / 8); });
   return dfb_check_launch("act_bwd");
 }
 
@@ -376,7 +395,7 @@ extern "C" int dfb200_scale_residual_fwd(const float* res, const void* y, long l
                                          int rows_per_sample, float* out, void* stream) {
   DFB_REQUIRE(C % 8 == 0 && ldy % 8 == 0, "scale_residual: C, ldy %% 8 != 0");
   DFB_DISPATCH_DTYPE(dtype, T, {
-    scale_residual_fwd_kernel<T><<<ew_grid((long)M * C / 8), EW_THREADS, 0, ST>>>(res, (const T*)y, ldy, ls, scale_b, M, C / 8, rows_per_sample, out);
+    dfb_launch(scale_residual_fwd_kernel<T>, ew_grid((long)M * C / 8), EW_THREADS, 0, ST, res, (const T*)y, ldy, ls, scale_b, M, C / 8, rows_per_sample, out);
   });
   return dfb_check_launch("scale_residual_fwd");
 }
@@ -386,41 +405,41 @@ extern "C" int dfb200_scale_residual_bwd(const float* dout, const void* y, long 
   const int rpb = pick_rows_per_block(M);
   dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(C / 8, EW_THREADS));
   DFB_DISPATCH_DTYPE(dtype, T, {
-    scale_residual_bwd_kernel<T><<<grid, EW_THREADS, EW_THREADS * 8 * sizeof(float), ST>>>(dout, (const T*)y, ldy, ls, scale_b, M, C, rows_per_sample, (T*)dy, lddy, dls, rpb);
+    dfb_launch(scale_residual_bwd_kernel<T>, grid, EW_THREADS, EW_THREADS * 8 * sizeof(float), ST, dout, (const T*)y, ldy, ls, scale_b, M, C, rows_per_sample, (T*)dy, lddy, dls, rpb);
   });
   return dfb_check_launch("scale_residual_bwd");
 }
 
 extern "C" int dfb200_normalize_cols(const float* in, int B, int D, int R, float* out, float* norms, void* stream) {
-  normalize_cols_kernel<<<B, 64, 0, ST>>>(in, D, R, out, norms);
+  dfb_launch(normalize_cols_kernel, B, 64, 0, ST, in, D, R, out, norms);
   return dfb_check_launch("normalize_cols");
 }
 extern "C" int dfb200_softmax_rows(const float* in, int rows, int cols, float* out, void* stream) {
   if (rows <= 0) return DFB_OK;
-  softmax_rows_kernel<<<dfb_cdiv(rows, 8), 256, 0, ST>>>(in, rows, cols, out);
+  dfb_launch(softmax_rows_kernel, dfb_cdiv(rows, 8), 256, 0, ST, in, rows, cols, out);
   return dfb_check_launch("softmax_rows");
 }
 extern "C" int dfb200_softmax_rows_bwd(const float* dout, const float* out, int rows, int cols, float* din, void* stream) {
   if (rows <= 0) return DFB_OK;
-  softmax_rows_bwd_kernel<<<dfb_cdiv(rows, 8), 256, 0, ST>>>(dout, out, rows, cols, din);
+  dfb_launch(softmax_rows_bwd_kernel, dfb_cdiv(rows, 8), 256, 0, ST, dout, out, rows, cols, din);
   return dfb_check_launch("softmax_rows_bwd");
 }
 extern "C" int dfb200_mu_update(const float* a, const float* num, const float* den, float eps, long n, float* out, void* stream) {
-  mu_update_kernel<<<ew_grid(n), EW_THREADS, 0, ST>>>(a, num, den, eps, n, out);
+  dfb_launch(mu_update_kernel, ew_grid(n), EW_THREADS, 0, ST, a, num, den, eps, n, out);
   return dfb_check_launch("mu_update");
 }
 extern "C" int dfb200_mu_update_bwd(const float* dout, const float* a, const float* num, const float* den, float eps, long n, float* da,
                                     int accumulate_da, float* dnum, float* dden, void* stream) {
-  mu_update_bwd_kernel<<<ew_grid(n), EW_THREADS, 0, ST>>>(dout, a, num, den, eps, n, da, accumulate_da, dnum, dden);
+  dfb_launch(mu_update_bwd_kernel, ew_grid(n), EW_THREADS, 0, ST, dout, a, num, den, eps, n, da, accumulate_da, dnum, dden);
   return dfb_check_launch("mu_update_bwd");
 }
 
 extern "C" int dfb200_cast(const void* in, int in_dtype, void* out, int out_dtype, long n, void* stream) {
   const int g = ew_grid(n, 4);
-  if (in_dtype == 0 && out_dtype == 0) cast_kernel<float, float><<<g, EW_THREADS, 0, ST>>>((const float*)in, (float*)out, n);
-  else if (in_dtype == 0 && out_dtype == 1) cast_kernel<float, bf16><<<g, EW_THREADS, 0, ST>>>((const float*)in, (bf16*)out, n);
-  else if (in_dtype == 1 && out_dtype == 0) cast_kernel<bf16, float><<<g, EW_THREADS, 0, ST>>>((const bf16*)in, (float*)out, n);
-  else if (in_dtype == 1 && out_dtype == 1) cast_kernel<bf16, bf16><<<g, EW_THREADS, 0, ST>>>((const bf16*)in, (bf16*)out, n);
+  if (in_dtype == 0 && out_dtype == 0) dfb_launch(cast_kernel<float, float>, g, EW_THREADS, 0, ST, (const float*)in, (float*)out, n);
+  else if (in_dtype == 0 && out_dtype == 1) dfb_launch(cast_kernel<float, bf16>, g, EW_THREADS, 0, ST, (const float*)in, (bf16*)out, n);
+  else if (in_dtype == 1 && out_dtype == 0) dfb_launch(cast_kernel<bf16, float>, g, EW_THREADS, 0, ST, (const bf16*)in, (float*)out, n);
+  else if (in_dtype == 1 && out_dtype == 1) dfb_launch(cast_kernel<bf16, bf16>, g, EW_THREADS, 0, ST, (const bf16*)in, (bf16*)out, n);
   else { dfb_set_error("cast: bad dtypes"); return DFB_ERR_ARG; }
   return dfb_check_launch("cast");
 }
@@ -428,19 +447,19 @@ extern "C" int dfb200_cast2d(const void* in, int in_dtype, long ld_in, void* out
   const long n = rows * cols;
   if (n <= 0) return DFB_OK;
   const int g = ew_grid(n, 4);
-  if (in_dtype == 0 && out_dtype == 0) cast2d_kernel<float, float><<<g, EW_THREADS, 0, ST>>>((const float*)in, ld_in, (float*)out, ld_out, rows, cols);
-  else if (in_dtype == 0 && out_dtype == 1) cast2d_kernel<float, bf16><<<g, EW_THREADS, 0, ST>>>((const float*)in, ld_in, (bf16*)out, ld_out, rows, cols);
-  else if (in_dtype == 1 && out_dtype == 0) cast2d_kernel<bf16, float><<<g, EW_THREADS, 0, ST>>>((const bf16*)in, ld_in, (float*)out, ld_out, rows, cols);
-  else if (in_dtype == 1 && out_dtype == 1) cast2d_kernel<bf16, bf16><<<g, EW_THREADS, 0, ST>>>((const bf16*)in, ld_in, (bf16*)out, ld_out, rows, cols);
+  if (in_dtype == 0 && out_dtype == 0) dfb_launch(cast2d_kernel<float, float>, g, EW_THREADS, 0, ST, (const float*)in, ld_in, (float*)out, ld_out, rows, cols);
+  else if (in_dtype == 0 && out_dtype == 1) dfb_launch(cast2d_kernel<float, bf16>, g, EW_THREADS, 0, ST, (const float*)in, ld_in, (bf16*)out, ld_out, rows, cols);
+  else if (in_dtype == 1 && out_dtype == 0) dfb_launch(cast2d_kernel<bf16, float>, g, EW_THREADS, 0, ST, (const bf16*)in, ld_in, (float*)out, ld_out, rows, cols);
+  else if (in_dtype == 1 && out_dtype == 1) dfb_launch(cast2d_kernel<bf16, bf16>, g, EW_THREADS, 0, ST, (const bf16*)in, ld_in, (bf16*)out, ld_out, rows, cols);
   else { dfb_set_error("cast2d: bad dtypes"); return DFB_ERR_ARG; }
   return dfb_check_launch("cast2d");
 }
 extern "C" int dfb200_axpy(const void* x, int x_dtype, float alpha, void* y, int y_dtype, long n, void* stream) {
   const int g = ew_grid(n, 4);
-  if (x_dtype == 0 && y_dtype == 0) axpy_kernel<float, float><<<g, EW_THREADS, 0, ST>>>((const float*)x, alpha, (float*)y, n);
-  else if (x_dtype == 0 && y_dtype == 1) axpy_kernel<float, bf16><<<g, EW_THREADS, 0, ST>>>((const float*)x, alpha, (bf16*)y, n);
-  else if (x_dtype == 1 && y_dtype == 0) axpy_kernel<bf16, float><<<g, EW_THREADS, 0, ST>>>((const bf16*)x, alpha, (float*)y, n);
-  else if (x_dtype == 1 && y_dtype == 1) axpy_kernel<bf16, bf16><<<g, EW_THREADS, 0, ST>>>((const bf16*)x, alpha, (bf16*)y, n);
+  if (x_dtype == 0 && y_dtype == 0) dfb_launch(axpy_kernel<float, float>, g, EW_THREADS, 0, ST, (const float*)x, alpha, (float*)y, n);
+  else if (x_dtype == 0 && y_dtype == 1) dfb_launch(axpy_kernel<float, bf16>, g, EW_THREADS, 0, ST, (const float*)x, alpha, (bf16*)y, n);
+  else if (x_dtype == 1 && y_dtype == 0) dfb_launch(axpy_kernel<bf16, float>, g, EW_THREADS, 0, ST, (const bf16*)x, alpha, (float*)y, n);
+  else if (x_dtype == 1 && y_dtype == 1) dfb_launch(axpy_kernel<bf16, bf16>, g, EW_THREADS, 0, ST, (const bf16*)x, alpha, (bf16*)y, n);
   else { dfb_set_error("axpy: bad dtypes"); return DFB_ERR_ARG; }
   return dfb_check_launch("axpy");
 }
@@ -448,6 +467,6 @@ extern "C" int dfb200_axpy(const void* x, int x_dtype, float alpha, void* y, int
 extern "C" int dfb200_adamw(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps,
                             float weight_decay, float bias_c1, float bias_c2, float grad_scale, const float* wd_arr, const float* lr_arr,
                             const float* dyn, void* stream) {
-  adamw_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2, grad_scale, wd_arr, lr_arr, dyn);
+  dfb_launch(adamw_kernel, ew_grid(n, 4), EW_THREADS, 0, ST, p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2, grad_scale, wd_arr, lr_arr, dyn);
   return dfb_check_launch("adamw");
 }

@@ -42,6 +42,7 @@ struct Geo {
 template <typename T, int D>
 __global__ void __launch_bounds__(NT) gaa_fused_fwd_kernel(const T* __restrict__ m, const T* __restrict__ kv, int HW, int heads, float scale, int nchunks,
                                                           float* __restrict__ out, float* __restrict__ lse, float* __restrict__ part, int* __restrict__ counters) {
+  pdl_sync();
   constexpr int DH = Geo<D>::DH, G = Geo<D>::G, RPG = Geo<D>::RPG, PS = D + 4;
   extern __shared__ __align__(16) float smf[];
   float* Qs = smf;                       // [49][D]
@@ -184,6 +185,7 @@ template <typename T, int D>
 __global__ void __launch_bounds__(NT) gaa_fused_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ lse,
                                                           const T* __restrict__ m, const T* __restrict__ kv, int HW, int heads, float scale,
                                                           float* __restrict__ dm, T* __restrict__ dkv) {
+  pdl_sync();
   constexpr int DH = Geo<D>::DH, G = Geo<D>::G, RPG = Geo<D>::RPG;
   extern __shared__ __align__(16) float smf[];
   float* Qs = smf;                       // [49][D]
@@ -293,7 +295,7 @@ int launch_fwd(const void* m, const void* kv, int B, int HW, int heads, float* o
   const int smem = fwd_smem<D>() + 2 * nchunks * NQ * 4;            // + merge staging of the (max, sum) pairs
   if (smem > 200 * 1024) { dfb_set_error("gaa_fused_fwd: HW=%d too large for the one-launch merge", HW); return DFB_ERR_UNSUPPORTED; }
   dim3 grid(nchunks, B * heads);
-  gaa_fused_fwd_kernel<T, D><<<grid, NT, smem, st>>>((const T*)m, (const T*)kv, HW, heads, 1.0f / sqrtf((float)D), nchunks, out, lse, part, counters);
+  dfb_launch(gaa_fused_fwd_kernel<T, D>, grid, NT, smem, st, (const T*)m, (const T*)kv, HW, heads, 1.0f / sqrtf((float)D), nchunks, out, lse, part, counters);
   return dfb_check_launch("gaa_fused_fwd");
 }
 
@@ -308,7 +310,7 @@ int launch_bwd(const float* dout, const float* out, const float* lse, const void
   }
   cudaMemsetAsync(dm, 0, sizeof(float) * (size_t)B * NQ * heads * D, st);
   dim3 grid(dfb_cdiv(HW, PC), B * heads);
-  gaa_fused_bwd_kernel<T, D><<<grid, NT, bwd_smem<D>(), st>>>(dout, out, lse, (const T*)m, (const T*)kv, HW, heads, 1.0f / sqrtf((float)D), dm, (T*)dkv);
+  dfb_launch(gaa_fused_bwd_kernel<T, D>, grid, NT, bwd_smem<D>(), st, dout, out, lse, (const T*)m, (const T*)kv, HW, heads, 1.0f / sqrtf((float)D), dm, (T*)dkv);
   return dfb_check_launch("gaa_fused_bwd");
 }
 

@@ -11,6 +11,7 @@ constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
 
 template <typename TAe, typename TBe, typename TO, bool TA, bool TB>
 __global__ void __launch_bounds__(NT) gemm_simt_kernel(dfb200_gemm_args g, int splits, int kchunk) {
+  pdl_sync();
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int zb = blockIdx.z / splits, zs = blockIdx.z % splits;
@@ -107,7 +108,7 @@ int launch(const dfb200_gemm_args& g, cudaStream_t st) {
   if (kchunk == 0) kchunk = BK;
   dim3 grid(dfb_cdiv(g.N, BN), dfb_cdiv(g.M, BM), nbatch * splits);
   DFB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm_simt grid too large (M=%d batch=%d)", g.M, g.batch);
-#define L(TA, TB) gemm_simt_kernel<TAe, TBe, TO, TA, TB><<<grid, NT, 0, st>>>(g, splits, kchunk)
+#define L(TA, TB) dfb_launch(gemm_simt_kernel<TAe, TBe, TO, TA, TB>, grid, NT, 0, st, g, splits, kchunk)
   if (g.transA) { if (g.transB) L(true, true); else L(true, false); }
   else { if (g.transB) L(false, true); else L(false, false); }
 #undef L

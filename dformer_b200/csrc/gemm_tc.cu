@@ -291,6 +291,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  // barrier init / tensor-memory allocation above touch no global memory: under programmatic dependent launch they overlap the
+  // tail of the previous kernel of the stream; everything below (TMA loads, bias / aux reads, stores) waits for it
+  pdl_sync();
 
   const int a_boxes = p.a_mn_major ? 2 : 1;                       // MN-major: one [64 k x 64 mn] box per 64 MN elements
   const int b_boxes = p.b_mn_major ? (p.BN + 63) / 64 : 1;
@@ -694,6 +697,6 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   if (forced_stages > 0 && forced_stages < p.stages) p.stages = forced_stages;
   const int smem_bytes = p.stages * p.stage_bytes + fixed;
-  gemm_tc_kernel<<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmB, p);
+  dfb_launch(gemm_tc_kernel, grid, NUM_THREADS, smem_bytes, st, tmA, tmB, p);
   return dfb_check_launch("gemm_tc");
 }

@@ -34,6 +34,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) upsample_ce_fwd_kernel(const T* __restrict__ small, int B, int h, int w, int ncls, int H, int W,
                                                               const int64_t* __restrict__ label, int ignore, float* __restrict__ out,
                                                               float* __restrict__ lse_out, float* loss_acc, T* __restrict__ up_lowp) {
+  pdl_sync();
   __shared__ float red[32];
   float loss = 0.f, cnt = 0.f;
   const long n = (long)B * H * W;
@@ -61,13 +62,15 @@ __global__ void __launch_bounds__(256) upsample_ce_fwd_kernel(const T* __restric
   }
 }
 
-__global__ void ce_finalize_kernel(const float* acc, float* loss) { loss[0] = acc[0] / acc[1]; }
+__global__ void ce_finalize_kernel(const float* acc, float* loss) {
+  pdl_sync(); loss[0] = acc[0] / acc[1]; }
 
 // thread = (low-res pixel, class); scans the hi-res pixels whose bilinear footprint includes the pixel
 template <typename T, typename TD>
 __global__ void upsample_ce_bwd_kernel(const T* __restrict__ small, int B, int h, int w, int ncls, int H, int W, const int64_t* __restrict__ label,
                                        int ignore, const float* __restrict__ lse, const float* __restrict__ loss_acc, const float* __restrict__ dloss,
                                        TD* __restrict__ dsmall) {
+  pdl_sync();
   const long n = (long)B * h * w * ncls;
   const float gscale = dloss[0] / loss_acc[1];
   const float ry = (float)H / (float)h, rx = (float)W / (float)w;
@@ -110,6 +113,7 @@ __global__ void upsample_ce_bwd_kernel(const T* __restrict__ small, int B, int h
 template <typename TU, int CH>
 __global__ void upsample_ce_bwd_rows_kernel(const TU* __restrict__ up, int B, int h, int ncls, int H, int W, const int64_t* __restrict__ label, int ignore,
                                             const float* __restrict__ lse, float* __restrict__ t) {
+  pdl_sync();
   const int nchunk = (ncls + CH - 1) / CH;
   const long n = (long)B * nchunk * h * W;
   const float ry = (float)H / (float)h;
@@ -152,6 +156,7 @@ __global__ void upsample_ce_bwd_rows_kernel(const TU* __restrict__ up, int B, in
 template <typename TD>
 __global__ void upsample_ce_bwd_cols_kernel(const float* __restrict__ t, int B, int h, int w, int ncls, int W, const float* __restrict__ loss_acc,
                                             const float* __restrict__ dloss, TD* __restrict__ dsmall) {
+  pdl_sync();
   const long n = (long)B * h * w * ncls;
   const float gscale = dloss[0] / loss_acc[1];
   const float rx = (float)W / (float)w;
@@ -194,6 +199,7 @@ template <typename T, int CH>
 __global__ void __launch_bounds__(256) upsample_ce_bwd_rows_fused_kernel(const T* __restrict__ small, int B, int h, int w, int ncls, int H, int W,
                                                                          const int64_t* __restrict__ label, int ignore, const float* __restrict__ lse,
                                                                          float* __restrict__ tA, float* __restrict__ tB) {
+  pdl_sync();
   const int nchunk = (ncls + CH - 1) / CH;
   const long n = (long)B * h * nchunk * W;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -245,6 +251,7 @@ template <typename TD>
 __global__ void __launch_bounds__(256) upsample_ce_bwd_cols_fused_kernel(const float* __restrict__ tA, const float* __restrict__ tB, int B, int h, int w,
                                                                          int ncls, int W, const float* __restrict__ loss_acc,
                                                                          const float* __restrict__ dloss, TD* __restrict__ dsmall) {
+  pdl_sync();
   const long n = (long)B * h * w * ncls;
   const float gscale = dloss[0] / loss_acc[1];
   const float rx = (float)W / (float)w;
@@ -283,13 +290,13 @@ extern "C" int dfb200_upsample_ce_fwd(const void* logits_small, int dtype, int B
   if (g > 148L * 16) g = 148L * 16;
   if (g < 1) g = 1;
   DFB_DISPATCH_DTYPE(dtype, T, {
-    upsample_ce_fwd_kernel<T><<<(int)g, 256, 0, ST>>>((const T*)logits_small, B, h, w, ncls, H, W, label, ignore, out_nchw, lse, loss_acc, (T*)up_lowp);
+    dfb_launch(upsample_ce_fwd_kernel<T>, (int)g, 256, 0, ST, (const T*)logits_small, B, h, w, ncls, H, W, label, ignore, out_nchw, lse, loss_acc, (T*)up_lowp);
   });
   return dfb_check_launch("upsample_ce_fwd");
 }
 
 extern "C" int dfb200_ce_finalize(const float* loss_acc, float* loss, void* stream) {
-  ce_finalize_kernel<<<1, 1, 0, ST>>>(loss_acc, loss);
+  dfb_launch(ce_finalize_kernel, 1, 1, 0, ST, loss_acc, loss);
   return dfb_check_launch("ce_finalize");
 }
 
@@ -302,10 +309,10 @@ extern "C" int dfb200_upsample_ce_bwd_sep(const void* up, int up_dtype, int B, i
   if (g1 > 148L * 32) g1 = 148L * 32;
   if (g1 < 1) g1 = 1;
   if (g2 < 1) g2 = 1;
-  DFB_DISPATCH_DTYPE(up_dtype, TU, { upsample_ce_bwd_rows_kernel<TU, CH><<<(int)g1, 256, 0, ST>>>((const TU*)up, B, h, ncls, H, W, label, ignore, lse, scratch); });
+  DFB_DISPATCH_DTYPE(up_dtype, TU, { dfb_launch(upsample_ce_bwd_rows_kernel<TU, CH>, (int)g1, 256, 0, ST, (const TU*)up, B, h, ncls, H, W, label, ignore, lse, scratch); });
   int rc = dfb_check_launch("upsample_ce_bwd_rows");
   if (rc) return rc;
-  DFB_DISPATCH_DTYPE(dl_dtype, TD, { upsample_ce_bwd_cols_kernel<TD><<<(int)g2, 256, 0, ST>>>(scratch, B, h, w, ncls, W, loss_acc, dloss, (TD*)dlogits_small); });
+  DFB_DISPATCH_DTYPE(dl_dtype, TD, { dfb_launch(upsample_ce_bwd_cols_kernel<TD>, (int)g2, 256, 0, ST, scratch, B, h, w, ncls, W, loss_acc, dloss, (TD*)dlogits_small); });
   return dfb_check_launch("upsample_ce_bwd_cols");
 }
 
@@ -314,7 +321,7 @@ extern "C" int dfb200_upsample_ce_bwd(const void* logits_small, int dtype, int B
   const long n = (long)B * h * w * ncls;
   long g = (n + 255) / 256;
   if (g < 1) g = 1;
-#define L(T, TD) upsample_ce_bwd_kernel<T, TD><<<(int)g, 256, 0, ST>>>((const T*)logits_small, B, h, w, ncls, H, W, label, ignore, lse, loss_acc, dloss, (TD*)dlogits_small)
+#define L(T, TD) dfb_launch(upsample_ce_bwd_kernel<T, TD>, (int)g, 256, 0, ST, (const T*)logits_small, B, h, w, ncls, H, W, label, ignore, lse, loss_acc, dloss, (TD*)dlogits_small)
   const int key = dtype * 2 + dl_dtype;
   switch (key) { case 0: L(float, float); break; case 1: L(float, bf16); break; case 2: L(bf16, float); break; case 3: L(bf16, bf16); break;
     default: dfb_set_error("upsample_ce_bwd: bad dtypes"); return DFB_ERR_ARG; }
@@ -334,12 +341,12 @@ extern "C" int dfb200_upsample_ce_bwd_fused(const void* logits_small, int dtype,
   if (g1 < 1) g1 = 1;
   if (g2 < 1) g2 = 1;
   DFB_DISPATCH_DTYPE(dtype, T, {
-    upsample_ce_bwd_rows_fused_kernel<T, CH><<<(unsigned)g1, 256, 0, ST>>>((const T*)logits_small, B, h, w, ncls, H, W, label, ignore, lse, tA, tB);
+    dfb_launch(upsample_ce_bwd_rows_fused_kernel<T, CH>, (unsigned)g1, 256, 0, ST, (const T*)logits_small, B, h, w, ncls, H, W, label, ignore, lse, tA, tB);
   });
   int rc = dfb_check_launch("upsample_ce_bwd_rows_fused");
   if (rc) return rc;
   DFB_DISPATCH_DTYPE(dl_dtype, TD, {
-    upsample_ce_bwd_cols_fused_kernel<TD><<<(unsigned)g2, 256, 0, ST>>>(tA, tB, B, h, w, ncls, W, loss_acc, dloss, (TD*)dlogits_small);
+    dfb_launch(upsample_ce_bwd_cols_fused_kernel<TD>, (unsigned)g2, 256, 0, ST, tA, tB, B, h, w, ncls, W, loss_acc, dloss, (TD*)dlogits_small);
   });
   return dfb_check_launch("upsample_ce_bwd_cols_fused");
 }

@@ -81,6 +81,7 @@ template <int TX, int TY>
 __global__ void __launch_bounds__(NT, 2) mlp_dw_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const float* __restrict__ weight,
                                                           const float* __restrict__ bias, bf16* __restrict__ u, int B, int H, int W, int C, int tiles_x,
                                                           int tiles_y) {
+  pdl_sync();
   constexpr int PW = TX + 2, PH = TY + 2, STAGE_BYTES = PH * PW * PIX_BYTES;
   constexpr int BR = TY / 2, BC = TX / 4;
   extern __shared__ uint8_t dsm_raw[];
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(NT, 2) mlp_dw_bwd_kernel(const __grid_constant
                                                           const float* __restrict__ weight, const float* __restrict__ bias, bf16* __restrict__ dh,
                                                           float* __restrict__ dweight, float* __restrict__ dbias, float* __restrict__ dh_colsum, int B,
                                                           int H, int W, int C, int tiles_x, int tiles_y) {
+  pdl_sync();
   using G = BwdGeom<TX, TY>;
   constexpr int HP = G::HP, ZP = G::ZP, ZR = G::ZR;
   constexpr int SEGA = (ZP + 3) / 4;                  // 4-pixel segments per dz row (the last one is partly padding)
@@ -322,7 +324,7 @@ int launch_fwd(const void* h, const float* weight, const float* bias, int B, int
   if (rc) return rc;
   const int tiles_x = dfb_cdiv(W, TX), tiles_y = dfb_cdiv(H, TY), nslab = dfb_cdiv(C, 64);
   dim3 grid(grid_x(B * tiles_x * tiles_y, nslab), nslab);
-  mlp_dw_fwd_kernel<TX, TY><<<grid, NT, smem, st>>>(tm, weight, bias, (bf16*)u, B, H, W, C, tiles_x, tiles_y);
+  dfb_launch(mlp_dw_fwd_kernel<TX, TY>, grid, NT, smem, st, tm, weight, bias, (bf16*)u, B, H, W, C, tiles_x, tiles_y);
   return dfb_check_launch("mlp_dw_fwd");
 }
 
@@ -343,7 +345,7 @@ int launch_bwd(const void* du, const void* h, const float* weight, const float* 
   if (rc) return rc;
   const int tiles_x = dfb_cdiv(W, TX), tiles_y = dfb_cdiv(H, TY), nslab = dfb_cdiv(C, 64);
   dim3 grid(grid_x(B * tiles_x * tiles_y, nslab), nslab);
-  mlp_dw_bwd_kernel<TX, TY><<<grid, NT, G::SMEM, st>>>(tmH, tmDU, weight, bias, (bf16*)dh, dweight, dbias, dh_colsum, B, H, W, C, tiles_x, tiles_y);
+  dfb_launch(mlp_dw_bwd_kernel<TX, TY>, grid, NT, G::SMEM, st, tmH, tmDU, weight, bias, (bf16*)dh, dweight, dbias, dh_colsum, B, H, W, C, tiles_x, tiles_y);
   return dfb_check_launch("mlp_dw_bwd");
 }
 

@@ -11,6 +11,7 @@ constexpr int LN_MAX_PER_LANE = 32;   // C <= 1024
 template <typename T, int NPL>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                      int M, int C, T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   float gm[NPL], bt[NPL];
@@ -56,6 +57,7 @@ template <typename T, int NPL>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd, int M, int C, const float* dx_in, float* dx,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_sync();
   extern __shared__ float sm[];   // [2][C]
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
@@ -123,6 +125,7 @@ __device__ __forceinline__ float group_sum(float v) {
 template <typename T, int L, int VPL>
 __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                          int M, int C, T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+  pdl_sync();
   constexpr int RPW = 32 / L;
   const int lane = threadIdx.x & 31, sub = lane % L, rsel = lane / L;
   const int nvec = C >> 3;
@@ -180,6 +183,7 @@ template <typename T, int L, int VPL>
 __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                                                          const float* __restrict__ mean, const float* __restrict__ rstd, int M, int C, const float* dx_in,
                                                          float* dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_sync();
   extern __shared__ float sm[];   // [2][C]
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
@@ -282,6 +286,7 @@ constexpr int BN_THREADS = 256;
 // Column sums in double (block-level partials in float over <= rows_per_block rows).
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T* __restrict__ x, int M, int C, double* sum, double* sumsq, int rows_per_block) {
+  pdl_sync();
   __shared__ float s1[BN_THREADS * 8];
   __shared__ float s2[BN_THREADS * 8];
   const int nvec_all = C >> 3;
@@ -314,6 +319,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T* __restric
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, double count, float eps, float momentum, int C,
                                    float* __restrict__ mean, float* __restrict__ invstd, float* running_mean, float* running_var) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mu = sum[c] / count;
@@ -328,6 +334,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
   }
 }
 __global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, float eps, int C, float* mean, float* invstd) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   mean[c] = rm[c];
@@ -345,6 +352,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const TX* __restri
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               const TY* __restrict__ residual, int act, const float* __restrict__ chan_scale,
                                                               int rows_per_sample, int M, int C, TY* __restrict__ y, int rows_per_block) {
+  pdl_sync();
   const int nvec_all = C >> 3;
   const int v0 = blockIdx.y * BN_THREADS;
   const int nvec = min(BN_THREADS, nvec_all - v0);
@@ -382,6 +390,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const TY* __r
                                                                    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                    const TY* __restrict__ residual, int act, const float* __restrict__ chan_scale, int rows_per_sample,
                                                                    int M, int C, TY* __restrict__ gbuf, float* sum_g, float* sum_gx, int rows_per_block) {
+  pdl_sync();
   __shared__ float s1[BN_THREADS * 8];
   __shared__ float s2[BN_THREADS * 8];
   const int nvec_all = C >> 3;
@@ -438,6 +447,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const TY* __re
                                                                   const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                                   const float* __restrict__ sum_g, const float* __restrict__ sum_gx, float inv_count,
                                                                   int training, int M, int C, TD* __restrict__ dx, int rows_per_block) {
+  pdl_sync();
   const int nvec_all = C >> 3;
   const int v0 = blockIdx.y * BN_THREADS;
   const int nvec = min(BN_THREADS, nvec_all - v0);
@@ -492,10 +502,10 @@ extern "C" int dfb200_layernorm_fwd(const float* x, const float* gamma, const fl
   if (M <= 0) return DFB_OK;
   const int grid = min(dfb_cdiv(M, 8), 148 * 8);
   if (C % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
-    DFB_DISPATCH_DTYPE(y_dtype, T, { LN_DISPATCH_VEC(C, { ln_fwd_vec_kernel<T, L, VPL><<<grid, 256, 0, ST>>>(x, gamma, beta, eps, M, C, (T*)y, mean, rstd); }); });
+    DFB_DISPATCH_DTYPE(y_dtype, T, { LN_DISPATCH_VEC(C, { dfb_launch(ln_fwd_vec_kernel<T, L, VPL>, grid, 256, 0, ST, x, gamma, beta, eps, M, C, (T*)y, mean, rstd); }); });
     return dfb_check_launch("layernorm_fwd_vec");
   }
-  DFB_DISPATCH_DTYPE(y_dtype, T, { LN_DISPATCH_NPL(C, { ln_fwd_kernel<T, NPL><<<grid, 256, 0, ST>>>(x, gamma, beta, eps, M, C, (T*)y, mean, rstd); }); });
+  DFB_DISPATCH_DTYPE(y_dtype, T, { LN_DISPATCH_NPL(C, { dfb_launch(ln_fwd_kernel<T, NPL>, grid, 256, 0, ST, x, gamma, beta, eps, M, C, (T*)y, mean, rstd); }); });
   return dfb_check_launch("layernorm_fwd");
 }
 
@@ -508,12 +518,12 @@ extern "C" int dfb200_layernorm_bwd(const void* dy, int dy_dtype, const float* x
   const int grid = min(dfb_cdiv(M, 32), 148 * 8);
   if (C % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dx_in)) & 15) == 0) {
     DFB_DISPATCH_DTYPE(dy_dtype, T, {
-      LN_DISPATCH_VEC(C, { ln_bwd_vec_kernel<T, L, VPL><<<grid, 256, 2 * C * sizeof(float), ST>>>((const T*)dy, x, gamma, mean, rstd, M, C, dx_in, dx, dgamma, dbeta); });
+      LN_DISPATCH_VEC(C, { dfb_launch(ln_bwd_vec_kernel<T, L, VPL>, grid, 256, 2 * C * sizeof(float), ST, (const T*)dy, x, gamma, mean, rstd, M, C, dx_in, dx, dgamma, dbeta); });
     });
     return dfb_check_launch("layernorm_bwd_vec");
   }
   DFB_DISPATCH_DTYPE(dy_dtype, T, {
-    LN_DISPATCH_NPL(C, { ln_bwd_kernel<T, NPL><<<grid, 256, 2 * C * sizeof(float), ST>>>((const T*)dy, x, gamma, mean, rstd, M, C, dx_in, dx, dgamma, dbeta); });
+    LN_DISPATCH_NPL(C, { dfb_launch(ln_bwd_kernel<T, NPL>, grid, 256, 2 * C * sizeof(float), ST, (const T*)dy, x, gamma, mean, rstd, M, C, dx_in, dx, dgamma, dbeta); });
   });
   return dfb_check_launch("layernorm_bwd");
 }
@@ -527,17 +537,17 @@ extern "C" int dfb200_bn_stats(const void* x, int dtype, int M, int C, double* s
   if (rpb < 32) rpb = 32;
   if (rpb > 4096) rpb = 4096;          // bound the length of float partial sums
   dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(C / 8, BN_THREADS));
-  DFB_DISPATCH_DTYPE(dtype, T, { bn_stats_kernel<T><<<grid, BN_THREADS, 0, ST>>>((const T*)x, M, C, sum, sumsq, rpb); });
+  DFB_DISPATCH_DTYPE(dtype, T, { dfb_launch(bn_stats_kernel<T>, grid, BN_THREADS, 0, ST, (const T*)x, M, C, sum, sumsq, rpb); });
   return dfb_check_launch("bn_stats");
 }
 
 extern "C" int dfb200_bn_finalize(const double* sum, const double* sumsq, double count, float eps, float momentum, int C, float* mean, float* invstd,
                                   float* running_mean, float* running_var, void* stream) {
-  bn_finalize_kernel<<<dfb_cdiv(C, 128), 128, 0, ST>>>(sum, sumsq, count, eps, momentum, C, mean, invstd, running_mean, running_var);
+  dfb_launch(bn_finalize_kernel, dfb_cdiv(C, 128), 128, 0, ST, sum, sumsq, count, eps, momentum, C, mean, invstd, running_mean, running_var);
   return dfb_check_launch("bn_finalize");
 }
 extern "C" int dfb200_bn_eval_stats(const float* running_mean, const float* running_var, float eps, int C, float* mean, float* invstd, void* stream) {
-  bn_eval_stats_kernel<<<dfb_cdiv(C, 128), 128, 0, ST>>>(running_mean, running_var, eps, C, mean, invstd);
+  dfb_launch(bn_eval_stats_kernel, dfb_cdiv(C, 128), 128, 0, ST, running_mean, running_var, eps, C, mean, invstd);
   return dfb_check_launch("bn_eval_stats");
 }
 
@@ -547,7 +557,7 @@ extern "C" int dfb200_bn_apply(const void* x, int x_dtype, const float* mean, co
   if (M <= 0) return DFB_OK;
   const int rpb = bn_stream_rows(M, C);
   dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(C / 8, BN_THREADS));
-#define L(TX, TY) bn_apply_kernel<TX, TY><<<grid, BN_THREADS, 0, ST>>>((const TX*)x, mean, invstd, gamma, beta, (const TY*)residual, act, chan_scale, rows_per_sample, M, C, (TY*)y, rpb)
+#define L(TX, TY) dfb_launch(bn_apply_kernel<TX, TY>, grid, BN_THREADS, 0, ST, (const TX*)x, mean, invstd, gamma, beta, (const TY*)residual, act, chan_scale, rows_per_sample, M, C, (TY*)y, rpb)
   if (x_dtype == 0 && y_dtype == 0) L(float, float);
   else if (x_dtype == 0 && y_dtype == 1) L(float, bf16);
   else if (x_dtype == 1 && y_dtype == 1) L(bf16, bf16);
@@ -563,7 +573,7 @@ extern "C" int dfb200_bn_bwd_reduce(const void* dy, int y_dtype, const void* x, 
   DFB_REQUIRE(C % 8 == 0, "bn_bwd_reduce: C %% 8 != 0 (C=%d)", C);
   const int rpb = rows_per_block(M);
   dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(C / 8, BN_THREADS));
-#define L(TX, TY) bn_bwd_reduce_kernel<TX, TY><<<grid, BN_THREADS, 0, ST>>>((const TY*)dy, (const TX*)x, mean, invstd, gamma, beta, (const TY*)residual, act, chan_scale, rows_per_sample, M, C, (TY*)gbuf, sum_g, sum_gx, rpb)
+#define L(TX, TY) dfb_launch(bn_bwd_reduce_kernel<TX, TY>, grid, BN_THREADS, 0, ST, (const TY*)dy, (const TX*)x, mean, invstd, gamma, beta, (const TY*)residual, act, chan_scale, rows_per_sample, M, C, (TY*)gbuf, sum_g, sum_gx, rpb)
   if (x_dtype == 0 && y_dtype == 0) L(float, float);
   else if (x_dtype == 0 && y_dtype == 1) L(float, bf16);
   else if (x_dtype == 1 && y_dtype == 1) L(bf16, bf16);
@@ -580,7 +590,7 @@ extern "C" int dfb200_bn_bwd_apply(const void* gbuf, int y_dtype, const void* x,
   const float inv = 1.f / count;
   const int rpb = bn_stream_rows(M, C);
   dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(C / 8, BN_THREADS));
-#define L(TX, TY, TD) bn_bwd_apply_kernel<TX, TY, TD><<<grid, BN_THREADS, 0, ST>>>((const TY*)gbuf, (const TX*)x, mean, invstd, gamma, sum_g, sum_gx, inv, training, M, C, (TD*)dx, rpb)
+#define L(TX, TY, TD) dfb_launch(bn_bwd_apply_kernel<TX, TY, TD>, grid, BN_THREADS, 0, ST, (const TY*)gbuf, (const TX*)x, mean, invstd, gamma, sum_g, sum_gx, inv, training, M, C, (TD*)dx, rpb)
   const int key = x_dtype * 4 + y_dtype * 2 + dx_dtype;
   switch (key) {
     case 0: L(float, float, float); break;
