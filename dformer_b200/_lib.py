@@ -41,7 +41,8 @@ SIGNATURES = {
     "dfb200_pack_params": [P, I, I, I, P],
     "dfb200_unpack_conv_grad": [P, I, I, I, P, P],
     "dfb200_layernorm_fwd": [P, P, P, F, I, I, P, I, P, P, P],
-    "dfb200_layernorm_bwd": [P, I, P, P, P, P, I, I, P, P, P, P, P],
+    "dfb200_scale_residual_layernorm_fwd": [P, P, L, I, P, P, I, I, I, P, P, P, F, P, P, P, P],
+    "dfb200_layernorm_bwd": [P, P, I, P, P, P, P, I, I, P, P, P, P, P],
     "dfb200_dwconv_fwd": [P, I, P, P, I, I, I, I, I, I, I, P, P, P],
     "dfb200_dwconv_bwd": [P, P, P, I, P, P, I, I, I, I, I, I, I, P, P, P, P, P],
     "dfb200_mlp_dw_fwd": [P, I, P, P, I, I, I, I, P, P],
@@ -51,7 +52,7 @@ SIGNATURES = {
     "dfb200_scale_residual_fwd": [P, P, L, I, P, P, I, I, I, P, P],
     "dfb200_scale_residual_bwd": [P, P, L, I, P, P, I, I, I, P, L, P, P],
     "dfb200_act_fwd": [P, L, P, L, I, I, I, I, P],
-    "dfb200_act_bwd": [P, L, P, L, P, L, I, I, I, I, P],
+    "dfb200_act_bwd": [P, L, P, L, P, L, P, L, I, I, I, I, P],
     "dfb200_pool7_fwd": [P, I, P, I, I, I, I, I, P, P],
     "dfb200_pool7_bwd": [P, I, I, I, I, I, I, P, P, P],
     "dfb200_gaa_fwd": [P, P, I, I, I, I, I, P, P, P],

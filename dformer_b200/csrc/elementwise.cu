@@ -164,13 +164,20 @@ __global__ void act_fwd_kernel(const T* __restrict__ in, long ldi, T* __restrict
   }
 }
 template <typename T>
-__global__ void act_bwd_kernel(const T* __restrict__ dout, long lddo, const T* __restrict__ z, long ldz, T* __restrict__ din, long lddi, int act, int M, int nvec) {
+__global__ void act_bwd_kernel(const T* __restrict__ dout, long lddo, const T* __restrict__ dout2, long lddo2, const T* __restrict__ z, long ldz,
+                               T* __restrict__ din, long lddi, int act, int M, int nvec) {
   pdl_sync();
   const long n = (long)M * nvec;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const long r = i / nvec; const int c = (int)(i % nvec) * 8;
     float g[8], zz[8];
     Vec8<T>::load(dout + r * lddo + c, g);
+    if (dout2) {                                     // fused gradient fan-in (sum rounded to T like the separate axpy pass did)
+      float g2[8];
+      Vec8<T>::load(dout2 + r * lddo2 + c, g2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = to_f(from_f<T>(g[j] + g2[j]));
+    }
     Vec8<T>::load(z + r * ldz + c, zz);
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[j] *= act == 1 ? gelu_grad_f(zz[j]) : (zz[j] > 0.f ? 1.f : 0.f);
@@ -385,9 +392,12 @@ extern "C" int dfb200_act_fwd(const void* in, long ldi, void* out, long ldo, int
   DFB_DISPATCH_DTYPE(dtype, T, { dfb_launch(act_fwd_kernel<T>, ew_grid((long)M * N / 8), EW_THREADS, 0, ST, (const T*)in, ldi, (T*)out, ldo, act, M, N / 8); });
   return dfb_check_launch("act_fwd");
 }
-extern "C" int dfb200_act_bwd(const void* dout, long lddo, const void* z, long ldz, void* din, long lddi, int dtype, int act, int M, int N, void* stream) {
-  DFB_REQUIRE(N % 8 == 0 && lddo % 8 == 0 && ldz % 8 == 0 && lddi % 8 == 0 && (act == 1 || act == 2), "act_bwd: bad arguments");
-  DFB_DISPATCH_DTYPE(dtype, T, { dfb_launch(act_bwd_kernel<T>, ew_grid((long)M * N / 8), EW_THREADS, 0, ST, (const T*)dout, lddo, (const T*)z, ldz, (T*)din, lddi, act, M, N / 8); });
+extern "C" int dfb200_act_bwd(const void* dout, long lddo, const void* dout2, long lddo2, const void* z, long ldz, void* din, long lddi, int dtype, int act,
+                              int M, int N, void* stream) {
+  DFB_REQUIRE(N % 8 == 0 && lddo % 8 == 0 && ldz % 8 == 0 && lddi % 8 == 0 && (!dout2 || lddo2 % 8 == 0) && (act == 1 || act == 2), "act_bwd: bad arguments");
+  DFB_DISPATCH_DTYPE(dtype, T, {
+    dfb_launch(act_bwd_kernel<T>, ew_grid((long)M * N / 8), EW_THREADS, 0, ST, (const T*)dout, lddo, (const T*)dout2, lddo2, (const T*)z, ldz, (T*)din, lddi, act, M, N / 8);
+  });
   return dfb_check_launch("act_bwd");
 }
 

@@ -8,9 +8,15 @@ constexpr int LN_MAX_PER_LANE = 32;   // C <= 1024
 
 // ------------------------------------------------------------------ LayerNorm: one warp per row, NPL values per lane
 // (NPL = ceil(C / 32) rounded up to a supported size; the row lives in registers between the two passes)
+// Optional fused layer-scale residual in front of the LayerNorm (DFormer.py:173-179 followed by :59/:104):
+//   x_out[m, c] = x[m, c] + scale_b[sample(m)] * ls[c] * y[m, c]   is written once and normalised in the same pass.
+struct LnResidual {
+  const void* y; long ldy; const float* ls; const float* scale_b; int rows_per_sample; float* x_out;
+};
+
 template <typename T, int NPL>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                                     int M, int C, T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+                                                     int M, int C, T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, const LnResidual rp) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
@@ -30,6 +36,11 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
     for (int i = 0; i < NPL; ++i) {
       const int c = lane + i * 32;
       v[i] = (c < C) ? __ldg(xr + c) : 0.f;
+      if (rp.y && c < C) {
+        const float sb = rp.scale_b ? rp.scale_b[row / rp.rows_per_sample] : 1.f;
+        v[i] = fmaf(sb * rp.ls[c], to_f(reinterpret_cast<const T*>(rp.y)[(long)row * rp.ldy + c]), v[i]);
+        rp.x_out[(long)row * C + c] = v[i];
+      }
       s += v[i];
     }
     const float mu = warp_sum(s) * invC;
@@ -54,9 +65,9 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
 // Backward: warp per row for dx; dgamma/dbeta partials stay in registers over the warp's rows, are combined across
 // the block's warps in shared memory and leave as one atomicAdd per channel per block.
 template <typename T, int NPL>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
-                                                     const float* __restrict__ mean, const float* __restrict__ rstd, int M, int C, const float* dx_in, float* dx,
-                                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy2, const float* __restrict__ x,
+                                                     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd, int M,
+                                                     int C, const float* dx_in, float* dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   pdl_sync();
   extern __shared__ float sm[];   // [2][C]
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
@@ -74,6 +85,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
     const float* xr = x + (long)row * C;
     const T* gr = dy + (long)row * C;
+    const T* gr2 = dy2 ? dy2 + (long)row * C : nullptr;
     const float mu = mean[row], rs = rstd[row];
     float xh[NPL], g[NPL];
     float s1 = 0.f, s2 = 0.f;
@@ -81,7 +93,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
     for (int i = 0; i < NPL; ++i) {
       const int c = lane + i * 32;
       if (c < C) {
-        const float d = to_f(gr[c]);
+        const float d = gr2 ? to_f(from_f<T>(to_f(gr[c]) + to_f(gr2[c]))) : to_f(gr[c]);      // the sum is rounded like the separate axpy pass was
         xh[i] = (__ldg(xr + c) - mu) * rs;
         g[i] = d * gm[i];
         pg[i] = fmaf(d, xh[i], pg[i]);
@@ -124,7 +136,8 @@ __device__ __forceinline__ float group_sum(float v) {
 
 template <typename T, int L, int VPL>
 __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                                         int M, int C, T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+                                                         int M, int C, T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd,
+                                                         const LnResidual rp) {
   pdl_sync();
   constexpr int RPW = 32 / L;
   const int lane = threadIdx.x & 31, sub = lane % L, rsel = lane / L;
@@ -149,6 +162,15 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict
       const int vv = sub + i * L;
       if (vv < nvec) {
         Vec8<float>::load(xr + vv * 8, v[i]);
+        if (rp.y && valid) {
+          const float sb = rp.scale_b ? rp.scale_b[row / rp.rows_per_sample] : 1.f;
+          float yv[8], lv[8];
+          Vec8<T>::load(reinterpret_cast<const T*>(rp.y) + row * rp.ldy + vv * 8, yv);
+          Vec8<float>::load(rp.ls + vv * 8, lv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] = fmaf(sb * lv[j], yv[j], v[i][j]);
+          Vec8<float>::store(rp.x_out + row * C + vv * 8, v[i]);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += v[i][j];
       }
@@ -180,13 +202,12 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict
 }
 
 template <typename T, int L, int VPL>
-__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
-                                                         const float* __restrict__ mean, const float* __restrict__ rstd, int M, int C, const float* dx_in,
-                                                         float* dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const T* __restrict__ dy, const T* __restrict__ dy2, const float* __restrict__ x,
+                                                         const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                         int M, int C, const float* dx_in, float* dx, float* __restrict__ dgamma,
+                                                         float* __restrict__ dbeta) {
   pdl_sync();
-  extern __shared__ float sm[];   // [2][C]
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
+  extern __shared__ float sm[];   // [8 warps][2][C] per-warp partial column sums
   constexpr int RPW = 32 / L;
   const int lane = threadIdx.x & 31, sub = lane % L, rsel = lane / L;
   const int nvec = C >> 3;
@@ -212,6 +233,12 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const T* __restrict__ d
       if (vv < nvec && valid) {
         float d[8], xv[8];
         Vec8<T>::load(dy + row * C + vv * 8, d);
+        if (dy2) {                                  // fused gradient fan-in (was a separate axpy pass): sum rounded to T like that pass did
+          float d2[8];
+          Vec8<T>::load(dy2 + row * C + vv * 8, d2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] = to_f(from_f<T>(d[j] + d2[j]));
+        }
         Vec8<float>::load(x + row * C + vv * 8, xv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -243,16 +270,28 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const T* __restrict__ d
       }
     }
   }
+  // column sums: lanes of a warp that own the same channels (different rows) meet through shuffles, every warp stores its
+  // partial row to its own shared-memory slab (no atomics), then one thread per channel adds the 8 slabs and issues the
+  // single global atomic of this CTA for that channel
+  float* slab = sm + (threadIdx.x >> 5) * 2 * C;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int vv = sub + i * L;
-    if (vv < nvec) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { atomicAdd(&sm[vv * 8 + j], pg[i][j]); atomicAdd(&sm[C + vv * 8 + j], pb[i][j]); }
+    for (int j = 0; j < 8; ++j) {
+      float a = pg[i][j], b = pb[i][j];
+#pragma unroll
+      for (int o = L; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+      if (rsel == 0 && vv < nvec) { slab[vv * 8 + j] = a; slab[C + vv * 8 + j] = b; }
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) { atomicAdd(dgamma + c, sm[c]); atomicAdd(dbeta + c, sm[C + c]); }
+  const int nwarp = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    float v = 0.f;
+    for (int w = 0; w < nwarp; ++w) v += sm[w * 2 * C + c];
+    atomicAdd((c < C ? dgamma : dbeta - C) + c, v);
+  }
 }
 
 #define LN_DISPATCH_VEC(C, ...)                                                            \
@@ -496,34 +535,53 @@ inline int rows_per_block(int M) { int r = dfb_cdiv(M, 148 * 4); return r < 32 ?
 
 #define ST reinterpret_cast<cudaStream_t>(stream)
 
+static int ln_fwd_launch(const float* x, const float* gamma, const float* beta, float eps, int M, int C, void* y, int y_dtype, float* mean, float* rstd,
+                         const LnResidual& rp, cudaStream_t st) {
+  const int grid = min(dfb_cdiv(M, 8), 148 * 8);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(rp.y) |
+                       reinterpret_cast<uintptr_t>(rp.x_out) | reinterpret_cast<uintptr_t>(rp.ls);
+  if (C % 8 == 0 && (al & 15) == 0 && (rp.y == nullptr || rp.ldy % 8 == 0)) {
+    DFB_DISPATCH_DTYPE(y_dtype, T, { LN_DISPATCH_VEC(C, { dfb_launch(ln_fwd_vec_kernel<T, L, VPL>, grid, 256, 0, st, x, gamma, beta, eps, M, C, (T*)y, mean, rstd, rp); }); });
+    return dfb_check_launch("layernorm_fwd_vec");
+  }
+  DFB_DISPATCH_DTYPE(y_dtype, T, { LN_DISPATCH_NPL(C, { dfb_launch(ln_fwd_kernel<T, NPL>, grid, 256, 0, st, x, gamma, beta, eps, M, C, (T*)y, mean, rstd, rp); }); });
+  return dfb_check_launch("layernorm_fwd");
+}
+
 extern "C" int dfb200_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int M, int C, void* y, int y_dtype, float* mean,
                                     float* rstd, void* stream) {
   DFB_REQUIRE(C >= 1 && C <= 32 * LN_MAX_PER_LANE, "layernorm: C=%d out of range", C);
   if (M <= 0) return DFB_OK;
-  const int grid = min(dfb_cdiv(M, 8), 148 * 8);
-  if (C % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
-    DFB_DISPATCH_DTYPE(y_dtype, T, { LN_DISPATCH_VEC(C, { dfb_launch(ln_fwd_vec_kernel<T, L, VPL>, grid, 256, 0, ST, x, gamma, beta, eps, M, C, (T*)y, mean, rstd); }); });
-    return dfb_check_launch("layernorm_fwd_vec");
-  }
-  DFB_DISPATCH_DTYPE(y_dtype, T, { LN_DISPATCH_NPL(C, { dfb_launch(ln_fwd_kernel<T, NPL>, grid, 256, 0, ST, x, gamma, beta, eps, M, C, (T*)y, mean, rstd); }); });
-  return dfb_check_launch("layernorm_fwd");
+  const LnResidual none = {nullptr, 0, nullptr, nullptr, 1, nullptr};
+  return ln_fwd_launch(x, gamma, beta, eps, M, C, y, y_dtype, mean, rstd, none, ST);
 }
 
-extern "C" int dfb200_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean, const float* rstd, int M, int C,
+// x_out = res + scale_b * ls * branch (fp32), y = LayerNorm(x_out) -- one pass (branch and y share `dtype`)
+extern "C" int dfb200_scale_residual_layernorm_fwd(const float* res, const void* branch, long ld_branch, int dtype, const float* ls, const float* scale_b,
+                                                   int rows_per_sample, int M, int C, float* x_out, const float* gamma, const float* beta, float eps,
+                                                   void* y, float* mean, float* rstd, void* stream) {
+  DFB_REQUIRE(C >= 1 && C <= 32 * LN_MAX_PER_LANE, "layernorm: C=%d out of range", C);
+  DFB_REQUIRE(branch && ls && x_out && rows_per_sample > 0, "scale_residual_layernorm_fwd: missing operand");
+  if (M <= 0) return DFB_OK;
+  const LnResidual rp = {branch, ld_branch, ls, scale_b, rows_per_sample, x_out};
+  return ln_fwd_launch(res, gamma, beta, eps, M, C, y, dtype, mean, rstd, rp, ST);
+}
+
+extern "C" int dfb200_layernorm_bwd(const void* dy, const void* dy2, int dy_dtype, const float* x, const float* gamma, const float* mean, const float* rstd, int M, int C,
                                     const float* dx_in, float* dx, float* dgamma, float* dbeta, void* stream) {
   DFB_REQUIRE(C >= 1 && C <= 32 * LN_MAX_PER_LANE, "layernorm: C=%d out of range", C);
   if (M <= 0) return DFB_OK;
   // every CTA ends with 2*C global atomics (dgamma, dbeta): >= 32 rows per CTA keeps that tail below the streaming work
   // at the small-M stages (M = 9600: 300 CTAs instead of 1184 contending for the same 2*C addresses)
   const int grid = min(dfb_cdiv(M, 32), 148 * 8);
-  if (C % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dx_in)) & 15) == 0) {
+  if (C % 8 == 0 && C <= 704 /* 8 per-warp slabs of 2*C floats in 48 KB */ && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dy2) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dx_in)) & 15) == 0) {
     DFB_DISPATCH_DTYPE(dy_dtype, T, {
-      LN_DISPATCH_VEC(C, { dfb_launch(ln_bwd_vec_kernel<T, L, VPL>, grid, 256, 2 * C * sizeof(float), ST, (const T*)dy, x, gamma, mean, rstd, M, C, dx_in, dx, dgamma, dbeta); });
+      LN_DISPATCH_VEC(C, { dfb_launch(ln_bwd_vec_kernel<T, L, VPL>, grid, 256, 16 * C * sizeof(float), ST, (const T*)dy, (const T*)dy2, x, gamma, mean, rstd, M, C, dx_in, dx, dgamma, dbeta); });
     });
     return dfb_check_launch("layernorm_bwd_vec");
   }
   DFB_DISPATCH_DTYPE(dy_dtype, T, {
-    LN_DISPATCH_NPL(C, { dfb_launch(ln_bwd_kernel<T, NPL>, grid, 256, 2 * C * sizeof(float), ST, (const T*)dy, x, gamma, mean, rstd, M, C, dx_in, dx, dgamma, dbeta); });
+    LN_DISPATCH_NPL(C, { dfb_launch(ln_bwd_kernel<T, NPL>, grid, 256, 2 * C * sizeof(float), ST, (const T*)dy, (const T*)dy2, x, gamma, mean, rstd, M, C, dx_in, dx, dgamma, dbeta); });
   });
   return dfb_check_launch("layernorm_bwd");
 }

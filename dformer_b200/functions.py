@@ -199,11 +199,16 @@ class DownsampleFn(torch.autograd.Function):
 BLOCK_PARAM_ORDER_DOC = "see models/encoders/DFormer.py: Block.param_names()"
 
 
-def _mlp_fwd(x, pfx, st, P, sv, scale_b):
-    """DFormer.py:58-67 + layer-scale residual :176/:179.  x fp32 [M,C] -> fp32 [M,C]."""
+def _mlp_fwd(x, pfx, st, P, sv, scale_b, pre=None):
+    """DFormer.py:58-67 + layer-scale residual :176/:179.  x fp32 [M,C] -> fp32 [M,C].
+    pre = (branch, layer_scale, drop_path_scale): the attention branch's residual x + dp * ls * branch (:173-175) is applied
+    in the same pass as this MLP's LayerNorm."""
     T = st.dtype
     B, H, W = st.B, st.H, st.W
-    hn, mu, rs = K.layernorm_fwd(x, P[pfx + "norm.weight"], P[pfx + "norm.bias"], 1e-6, T)
+    if pre is not None:
+        x, hn, mu, rs = K.scale_residual_layernorm_fwd(x, pre[0], pre[1], pre[2], H * W, P[pfx + "norm.weight"], P[pfx + "norm.bias"], 1e-6)
+    else:
+        hn, mu, rs = K.layernorm_fwd(x, P[pfx + "norm.weight"], P[pfx + "norm.bias"], 1e-6, T)
     h = _lin(hn, st.packed[st.key + pfx + "fc1"], T)
     if T == torch.bfloat16 and _FUSE_DW:       # TMA-fed fused kernel; the pre-activation is recomputed in the fused backward
         u, z = K.mlp_dw_fwd(h, P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W), None
@@ -316,13 +321,11 @@ class BlockFn(torch.autograd.Function):
             K.fork(side)
             with torch.cuda.stream(side):
                 n_before = set(sv)
-                xe1 = K.scale_residual_fwd(x_e, pp[:, C:], P["layer_scale_1_e"], st.dp[2], HW)
-                xe2 = _mlp_fwd(xe1, "mlp_e2.", st, P, sv, st.dp[3])
-            K.share(main, xe1, xe2, *[sv[k] for k in sv if k not in n_before])
+                xe2 = _mlp_fwd(x_e, "mlp_e2.", st, P, sv, st.dp[3], pre=(pp[:, C:], P["layer_scale_1_e"], st.dp[2]))
+            K.share(main, xe2, *[sv[k] for k in sv if k not in n_before])
         else:
             xe2 = x_e
-        x1 = K.scale_residual_fwd(x, pp[:, :C], P["layer_scale_1"], st.dp[0], HW)
-        x2 = _mlp_fwd(x1, "mlp.", st, P, sv, st.dp[1])
+        x2 = _mlp_fwd(x, "mlp.", st, P, sv, st.dp[1], pre=(pp[:, :C], P["layer_scale_1"], st.dp[0]))
         K.join(side)
         ctx.st, ctx.sv, ctx.P = st, sv, P
         return x2, xe2
@@ -407,19 +410,17 @@ class BlockFn(torch.autograd.Function):
                           G["attn.conv.weight"], G["attn.conv.bias"], wgrad_stream=_WGRAD_STREAM)
         if win:
             K.join(side2)
-            K.axpy(dl_kv, 1.0, dl)
-        K.act_bwd(dl, qcl[:, C + Ce:], K.ACT_GELU, out=dqcl[:, C + Ce:])
+        K.act_bwd(dl, qcl[:, C + Ce:], K.ACT_GELU, out=dqcl[:, C + Ce:], dout2=dl_kv)      # kv branch's gradient of l joins here
         qclw = pk("attn.qcl")[0]
         dWq = ar.span(st.prefix + "attn.q.weight", st.prefix + "attn.l.weight", qclw.shape)
         dbq = ar.span(st.prefix + "attn.q.bias", st.prefix + "attn.l.bias", (qclw.shape[0],))
         dxn = _lin_bwd(dqcl, sv["xn"], qclw, dWq, dbq, T)
-        if dxn_pool is not None:
-            K.axpy(dxn_pool, 1.0, dxn)
-        dx = K.layernorm_bwd(dxn, sv["x"], P["attn.norm.weight"], sv["mu1"], sv["rs1"], dx1, G["attn.norm.weight"], G["attn.norm.bias"])
+        # the pooled-query branch's gradient joins inside the LayerNorm backward kernels (dy2)
+        dx = K.layernorm_bwd(dxn, sv["x"], P["attn.norm.weight"], sv["mu1"], sv["rs1"], dx1, G["attn.norm.weight"], G["attn.norm.bias"],
+                             dy2=dxn_pool)
         K.join(side)
-        if den_pool is not None:
-            K.axpy(den_pool, 1.0, den)
-        dxe = K.layernorm_bwd(den, sv["x_e"], P["attn.norm_e.weight"], sv["mu2"], sv["rs2"], dxe1, G["attn.norm_e.weight"], G["attn.norm_e.bias"])
+        dxe = K.layernorm_bwd(den, sv["x_e"], P["attn.norm_e.weight"], sv["mu2"], sv["rs2"], dxe1, G["attn.norm_e.weight"], G["attn.norm_e.bias"],
+                              dy2=den_pool)
         if dd and dxe2 is not None:
             K.axpy(dxe2.contiguous(), 1.0, dxe)                                  # x_e passes through the last block unchanged
         _WGRAD_STREAM = None

@@ -169,11 +169,24 @@ def layernorm_fwd(x, gamma, beta, eps, out_dtype):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dgamma, dbeta):
-    """returns dx = (dx_in or 0) + LN-gradient (fresh fp32 tensor); dgamma/dbeta accumulate."""
+def scale_residual_layernorm_fwd(res, branch, ls, scale_b, rows_per_sample, gamma, beta, eps):
+    """x1 = res + scale_b * ls * branch (fp32) and LN(x1) in branch.dtype in one pass: returns (x1, y, mean, rstd)."""
+    M, C = res.shape
+    x1 = torch.empty_like(res)
+    y = torch.empty((M, C), device=res.device, dtype=branch.dtype)
+    mean = torch.empty(M, device=res.device, dtype=torch.float32)
+    rstd = torch.empty(M, device=res.device, dtype=torch.float32)
+    lib().scale_residual_layernorm_fwd(res.data_ptr(), branch.data_ptr(), branch.stride(0), dt(branch), ls.data_ptr(), _p(scale_b), rows_per_sample,
+                                       M, C, x1.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _s())
+    return x1, y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dgamma, dbeta, dy2=None):
+    """returns dx = (dx_in or 0) + LN-gradient of (dy [+ dy2]) (fresh fp32 tensor); dgamma/dbeta accumulate."""
     M, C = x.shape
     dx = torch.empty((M, C), device=x.device, dtype=torch.float32)
-    lib().layernorm_bwd(dy.data_ptr(), dt(dy), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), M, C,
+    assert dy2 is None or (dy2.dtype == dy.dtype and dy2.shape == dy.shape and dy2.is_contiguous())
+    lib().layernorm_bwd(dy.data_ptr(), _p(dy2), dt(dy), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), M, C,
                         _p(dx_in), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _s())
     return dx
 
@@ -259,11 +272,13 @@ def act_fwd(x, act, out=None):
     return out
 
 
-def act_bwd(dout, z, act, out=None):
+def act_bwd(dout, z, act, out=None, dout2=None):
+    """out = (dout [+ dout2]) * act'(z)"""
     M, N = z.shape
     if out is None:
         out = torch.empty((M, N), device=z.device, dtype=z.dtype)
-    lib().act_bwd(dout.data_ptr(), dout.stride(0), z.data_ptr(), z.stride(0), out.data_ptr(), out.stride(0), dt(z), act, M, N, _s())
+    lib().act_bwd(dout.data_ptr(), dout.stride(0), _p(dout2), dout2.stride(0) if dout2 is not None else 0, z.data_ptr(), z.stride(0),
+                  out.data_ptr(), out.stride(0), dt(z), act, M, N, _s())
     return out
 
 

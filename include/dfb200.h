@@ -87,7 +87,13 @@ int dfb200_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
                          void* y, int y_dtype, float* mean, float* rstd, void* stream);
 /* dx is fp32 [M,C]; dx = (dx_in ? dx_in : 0) + LN-gradient (dx_in = gradient of the residual branch; may alias dx).
  * dgamma/dbeta are accumulated with atomics and must be zero-initialised by the caller. */
-int dfb200_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* mean,
+/* Fused layer-scale residual + LayerNorm (DFormer.py:173-179 then :59): x_out = res + scale_b[sample] * ls * branch (fp32,
+ * written once), y = LN(x_out) in `dtype` (= dtype of branch), mean / rstd kept for backward. */
+int dfb200_scale_residual_layernorm_fwd(const float* res, const void* branch, long ld_branch, int dtype, const float* ls,
+                                        const float* scale_b, int rows_per_sample, int M, int C, float* x_out,
+                                        const float* gamma, const float* beta, float eps, void* y, float* mean, float* rstd,
+                                        void* stream);
+int dfb200_layernorm_bwd(const void* dy, const void* dy2 /* optional second gradient, added to dy (fan-in) */, int dy_dtype, const float* x, const float* gamma, const float* mean,
                          const float* rstd, int M, int C, const float* dx_in, float* dx, float* dgamma, float* dbeta,
                          void* stream);
 
@@ -131,8 +137,8 @@ int dfb200_scale_residual_bwd(const float* dout, const void* y, long ldy, int dt
 /* stand-alone activation on a column slice: out = act(in);  din = dout * act'(z) (GELU: z = pre-activation;
  * ReLU: z may be the forward output).  All operands have independent leading dimensions. */
 int dfb200_act_fwd(const void* in, long ldi, void* out, long ldo, int dtype, int act, int M, int N, void* stream);
-int dfb200_act_bwd(const void* dout, long lddo, const void* z, long ldz, void* din, long lddi, int dtype, int act, int M, int N,
-                   void* stream);
+int dfb200_act_bwd(const void* dout, long lddo, const void* dout2 /* optional second gradient added to dout */, long lddo2,
+                   const void* z, long ldz, void* din, long lddi, int dtype, int act, int M, int N, void* stream);
 
 /* ---- Global Awareness Attention pieces (DFormer.py:107-108,120-131) ------------------------------
  * pool: AdaptiveAvgPool2d(7,7) of cat[xn (C1 ch), en (C2 ch)] -> out [B,49,C1+C2] (compute dtype). */

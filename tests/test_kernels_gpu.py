@@ -97,9 +97,42 @@ def test_layernorm(dtype, C):
     ref.backward(dy.float())
     dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
     dx = k.layernorm_bwd(dy, x, g, mean, rstd, torch.ones(M, C, device=DEV), dg, db)
+    # fused fan-in: LN_bwd(dy_a + dy_b) in one kernel
+    dya = rnd(M, C, dtype=dtype)
+    dyb = (dy.float() - dya.float()).to(dtype)
+    dg2, db2 = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    dx2 = k.layernorm_bwd(dya, x, g, mean, rstd, torch.ones(M, C, device=DEV), dg2, db2, dy2=dyb)
+    t2 = dict(rtol=2e-2, atol=5e-2) if dtype == torch.bfloat16 else dict(rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dx2, dx, **t2)
+    torch.testing.assert_close(dg2, dg, rtol=2e-2, atol=0.5 if dtype == torch.bfloat16 else 1e-3)
     torch.testing.assert_close(dx - 1, xr.grad, rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(dg, gr.grad, rtol=1e-3, atol=2e-2)
     torch.testing.assert_close(db, br.grad, rtol=1e-3, atol=2e-2)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C", [96, 288, 52])
+def test_scale_residual_layernorm_fused(dtype, C):
+    """x1 = res + dp * ls * branch and LN(x1) in one pass == the two separate kernels."""
+    k = K()
+    B, rows = 3, 50
+    M = B * rows
+    res = rnd(M, C) * 2
+    wide = rnd(M, C + 24, dtype=dtype)
+    branch = wide[:, 8:8 + C] if C % 8 == 0 else rnd(M, C, dtype=dtype)
+    ls, dp = rnd(C) * 0.3, torch.tensor([1.2, 0.0, 1.2], device=DEV)
+    g, b = 1 + 0.1 * rnd(C), 0.1 * rnd(C)
+    x1, y, mean, rstd = k.scale_residual_layernorm_fwd(res, branch, ls, dp, rows, g, b, 1e-6)
+    x1_ref = res + dp.repeat_interleave(rows)[:, None] * ls * branch.float()
+    torch.testing.assert_close(x1, x1_ref, rtol=1e-5, atol=1e-5)
+    ref = F.layer_norm(x1_ref, (C,), g, b, 1e-6)
+    torch.testing.assert_close(y.float(), ref, **tol(dtype))
+    torch.testing.assert_close(mean, x1_ref.mean(1), rtol=1e-4, atol=1e-4)
+    if C % 8 == 0:
+        x1b = k.scale_residual_fwd(res, branch, ls, dp, rows)
+        yb, mb, rb = k.layernorm_fwd(x1b, g, b, 1e-6, dtype)
+        torch.testing.assert_close(x1, x1b)
+        torch.testing.assert_close(y, yb)
 
 
 # ----------------------------------------------------------------------------- depthwise conv
