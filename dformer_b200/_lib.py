@@ -45,8 +45,8 @@ SIGNATURES = {
     "dfb200_layernorm_bwd": [P, P, I, P, P, P, P, I, I, P, P, P, P, P],
     "dfb200_dwconv_fwd": [P, I, P, P, I, I, I, I, I, I, I, P, P, P],
     "dfb200_dwconv_bwd": [P, P, P, I, P, P, I, I, I, I, I, I, I, P, P, P, P, P],
-    "dfb200_mlp_dw_fwd": [P, I, P, P, I, I, I, I, P, P],
-    "dfb200_mlp_dw_bwd": [P, P, I, P, P, I, I, I, I, P, P, P, P, P],
+    "dfb200_mlp_dw_fwd": [P, I, P, P, I, I, I, I, P, P, P],
+    "dfb200_mlp_dw_bwd": [P, P, P, I, P, P, I, I, I, I, P, P, P, P, P],
     "dfb200_mul_fwd": [P, L, P, L, P, L, I, I, I, P],
     "dfb200_mul_bwd": [P, L, P, L, P, L, P, L, P, L, I, I, I, P],
     "dfb200_scale_residual_fwd": [P, P, L, I, P, P, I, I, I, P, P],

@@ -141,6 +141,14 @@ __device__ __forceinline__ float2 gelu2(const float2& x) {
   const float2 r = make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f));
   return fma2(make_float2(-ax.x, -ax.y), q, r);
 }
+// GELU and its derivative from one evaluation of (q, e)
+__device__ __forceinline__ void gelu_both2(const float2& x, float2& g, float2& dg) {
+  float2 q, e, ax;
+  gelu_q2(x, q, e, ax);
+  g = fma2(make_float2(-ax.x, -ax.y), q, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
+  const float2 cdf = make_float2(x.x >= 0.f ? 1.0f - q.x : q.x, x.y >= 0.f ? 1.0f - q.y : q.y);
+  dg = fma2(mul2(x, splat2(0.39894228040143267794f)), e, cdf);
+}
 __device__ __forceinline__ float2 gelu_grad2(const float2& x) {
   float2 q, e, ax;
   gelu_q2(x, q, e, ax);

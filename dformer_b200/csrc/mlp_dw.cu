@@ -79,8 +79,8 @@ __device__ __forceinline__ void load_taps(const float* __restrict__ weight, cons
 // ------------------------------------------------------------------------------------------------ forward
 template <int TX, int TY>
 __global__ void __launch_bounds__(NT, 2) mlp_dw_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const float* __restrict__ weight,
-                                                          const float* __restrict__ bias, bf16* __restrict__ u, int B, int H, int W, int C, int tiles_x,
-                                                          int tiles_y) {
+                                                          const float* __restrict__ bias, bf16* __restrict__ u, bf16* __restrict__ gp, int B, int H, int W,
+                                                          int C, int tiles_x, int tiles_y) {
   pdl_sync();
   constexpr int PW = TX + 2, PH = TY + 2, STAGE_BYTES = PH * PW * PIX_BYTES;
   constexpr int BR = TY / 2, BC = TX / 4;
@@ -122,13 +122,29 @@ __global__ void __launch_bounds__(NT, 2) mlp_dw_fwd_kernel(const __grid_constant
         for (int t = 0; t < 4; ++t) { acc[r][t][0] = bq[0]; acc[r][t][1] = bq[1]; }
       conv3x3_block<2, 4, false>(hT, PW, r0, x0, cq, w, acc);
       const int oy0 = ty0 + r0, ox0 = tx0 + x0;
-      bf16* up = u + (((long)b * H + oy0) * W + ox0) * C + c0;
+      const long off0 = (((long)b * H + oy0) * W + ox0) * C + c0;
+      if (gp) {                                        // training: GELU'(z) is kept (bf16) so that the backward pass is a pure stream
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < 2; ++r) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const uint2 o = pack4(gelu2(acc[r][t][0]), gelu2(acc[r][t][1]));
-          if (c0 < C && oy0 + r < H && ox0 + t < W) *reinterpret_cast<uint2*>(up + (long)r * row_stride + t * C) = o;
+          for (int t = 0; t < 4; ++t) {
+            float2 g0, g1, d0, d1;
+            gelu_both2(acc[r][t][0], g0, d0);
+            gelu_both2(acc[r][t][1], g1, d1);
+            if (c0 < C && oy0 + r < H && ox0 + t < W) {
+              *reinterpret_cast<uint2*>(u + off0 + (long)r * row_stride + t * C) = pack4(g0, g1);
+              *reinterpret_cast<uint2*>(gp + off0 + (long)r * row_stride + t * C) = pack4(d0, d1);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint2 o = pack4(gelu2(acc[r][t][0]), gelu2(acc[r][t][1]));
+            if (c0 < C && oy0 + r < H && ox0 + t < W) *reinterpret_cast<uint2*>(u + off0 + (long)r * row_stride + t * C) = o;
+          }
         }
       }
     }
@@ -296,6 +312,154 @@ __global__ void __launch_bounds__(NT, 2) mlp_dw_bwd_kernel(const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------------ backward, GELU'(z) kept by forward
+// Same outputs as mlp_dw_bwd_kernel, but dz = du * gp is a two-load product (no convolution / GELU' recompute, no second halo
+// ring of h).  Two (TY+2) x (TX+2) buffers: [du -> dz in place] and [gp, then h]: the h tile is fetched by a second TMA into
+// the buffer gp has just vacated while phase B (the transposed convolution, which only reads dz) runs.
+template <int TX, int TY>
+__global__ void __launch_bounds__(NT, 2) mlp_dw_bwd_saved_kernel(const __grid_constant__ CUtensorMap tmDU, const __grid_constant__ CUtensorMap tmGP,
+                                                                const __grid_constant__ CUtensorMap tmH, const float* __restrict__ weight,
+                                                                bf16* __restrict__ dh, float* __restrict__ dweight, float* __restrict__ dbias,
+                                                                float* __restrict__ dh_colsum, int B, int H, int W, int C, int tiles_x, int tiles_y) {
+  pdl_sync();
+  constexpr int ZP = TX + 2, ZR = TY + 2, BUF_BYTES = ZR * ZP * PIX_BYTES;
+  constexpr int BR = TY / 2, BC = TX / 4;
+  constexpr int PARTS = NPG / 3;
+  constexpr int ITEMS = TY * (TX / 8);
+  extern __shared__ uint8_t dsm_raw[];
+  __shared__ __align__(8) uint64_t bar[2];
+  uint8_t* dsm = align128(dsm_raw);
+  uint2* zT = reinterpret_cast<uint2*>(dsm);                         // du, then dz
+  uint2* hT = reinterpret_cast<uint2*>(dsm + BUF_BYTES);             // gp, then h      (both with origin (ty0-1, tx0-1))
+  float* red_w = reinterpret_cast<float*>(dsm + 2 * BUF_BYTES);      // [64][9]
+  float* red_b = red_w + 64 * 9;
+  float* red_c = red_b + 64;
+  const int tid = threadIdx.x, cq = tid & (NQ - 1), pg = tid >> 4;
+  const int c_base = blockIdx.y * 64;
+  const int c0 = c_base + cq * 4;
+  const int n_tiles = B * tiles_x * tiles_y;
+  const long row_stride = (long)W * C;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 64 * 9 + 128; i += NT) red_w[i] = 0.f;
+  float2 w[9][2], bq[2];
+  load_taps(weight, nullptr, c0, C, w, bq);
+  const int ky = pg / PARTS, part = pg % PARTS;
+  const bool wg_worker = pg < 3 * PARTS;
+  float2 gw[3][2], gb[2], gc[2];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) gw[k][0] = gw[k][1] = make_float2(0.f, 0.f);
+  gb[0] = gb[1] = gc[0] = gc[1] = make_float2(0.f, 0.f);
+  __syncthreads();
+  int it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int tx0 = (tile % tiles_x) * TX, ty0 = ((tile / tiles_x) % tiles_y) * TY, b = tile / (tiles_x * tiles_y);
+    if (tid == 0) {
+      mbar_expect_tx(&bar[0], 2 * BUF_BYTES);
+      tma_load_4d(&tmDU, &bar[0], zT, c_base, tx0 - 1, ty0 - 1, b);
+      tma_load_4d(&tmGP, &bar[0], hT, c_base, tx0 - 1, ty0 - 1, b);
+    }
+    mbar_wait(&bar[0], it & 1);
+    // ---- phase A: dz = du * GELU'(z) on the tile plus its one-pixel ring (zero outside the image: du is zero-filled there)
+    for (int i = tid; i < ZR * ZP * NQ; i += NT) {
+      float2 dlo, dhi, glo, ghi;
+      unpack4(zT[i], dlo, dhi);
+      unpack4(hT[i], glo, ghi);
+      zT[i] = pack4(mul2(dlo, glo), mul2(dhi, ghi));
+    }
+    fence_proxy_async();                               // gp has been consumed (generic proxy) before the TMA refill below
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&bar[1], BUF_BYTES);
+      tma_load_4d(&tmH, &bar[1], hT, c_base, tx0 - 1, ty0 - 1, b);
+    }
+    // ---- phase B: dh = dz + conv^T(dz), running column sum of dh (fc1 bias gradient); overlaps the h fetch
+    for (int blk = pg; blk < BR * BC; blk += NPG) {
+      const int r0 = (blk / BC) * 2, x0 = (blk % BC) * 4;
+      float2 acc[2][4][2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc[r][t][0] = acc[r][t][1] = make_float2(0.f, 0.f);
+      conv3x3_block<2, 4, true>(zT, ZP, r0, x0, cq, w, acc);
+      const int oy0 = ty0 + r0, ox0 = tx0 + x0;
+      bf16* dp = dh + (((long)b * H + oy0) * W + ox0) * C + c0;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint2 o = pack4(acc[r][t][0], acc[r][t][1]);
+          if (c0 < C && oy0 + r < H && ox0 + t < W) {
+            *reinterpret_cast<uint2*>(dp + (long)r * row_stride + t * C) = o;
+            float2 lo, hi;
+            unpack4(o, lo, hi);
+            gc[0] = add2(gc[0], lo);
+            gc[1] = add2(gc[1], hi);
+          }
+        }
+      }
+    }
+    // ---- phase C: dW[ky][kx] += dz[p] * h[p + (ky-1, kx-1)]
+    mbar_wait(&bar[1], it & 1);
+    if (wg_worker) {
+      for (int item = part; item < ITEMS; item += PARTS) {
+        const int r = item / (TX / 8), xs = (item % (TX / 8)) * 8;
+        const uint2* xrow = hT + ((r + ky) * ZP + xs) * NQ + cq;           // h[r + ky - 1][xs + i - 1] at index i  (origin -1)
+        const uint2* zrow = zT + ((r + 1) * ZP + xs + 1) * NQ + cq;
+        float2 win[3][2];
+        unpack4(xrow[0], win[1][0], win[1][1]);
+        unpack4(xrow[NQ], win[2][0], win[2][1]);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          win[0][0] = win[1][0]; win[0][1] = win[1][1];
+          win[1][0] = win[2][0]; win[1][1] = win[2][1];
+          unpack4(xrow[(t + 2) * NQ], win[2][0], win[2][1]);
+          float2 glo, ghi;
+          unpack4(zrow[t * NQ], glo, ghi);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            ffma2(gw[k][0], glo, win[k][0]);
+            ffma2(gw[k][1], ghi, win[k][1]);
+          }
+          if (ky == 1) { gb[0] = add2(gb[0], glo); gb[1] = add2(gb[1], ghi); }
+        }
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+  }
+  {
+    const float gcv[4] = {gc[0].x, gc[0].y, gc[1].x, gc[1].y};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(&red_c[cq * 4 + j], gcv[j]);
+    if (wg_worker) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float v[4] = {gw[k][0].x, gw[k][0].y, gw[k][1].x, gw[k][1].y};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(&red_w[(cq * 4 + j) * 9 + ky * 3 + k], v[j]);
+      }
+      if (ky == 1) {
+        const float v[4] = {gb[0].x, gb[0].y, gb[1].x, gb[1].y};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(&red_b[cq * 4 + j], v[j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 64 * 9; i += NT) {
+    const int c = c_base + i / 9;
+    if (c < C) atomicAdd(dweight + (long)c * 9 + i % 9, red_w[i]);
+  }
+  if (tid < 64 && c_base + tid < C) {
+    if (dbias) atomicAdd(dbias + c_base + tid, red_b[tid]);
+    if (dh_colsum) atomicAdd(dh_colsum + c_base + tid, red_c[tid]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host
 // tile geometry: 8 x 32 pixels unless 6 x 40 wastes less of the image on partial tiles
 bool wide_tile(int H, int W) {
@@ -311,7 +475,7 @@ int grid_x(int n_tiles, int nslab) {
 }
 
 template <int TX, int TY>
-int launch_fwd(const void* h, const float* weight, const float* bias, int B, int H, int W, int C, void* u, cudaStream_t st) {
+int launch_fwd(const void* h, const float* weight, const float* bias, int B, int H, int W, int C, void* u, void* gp, cudaStream_t st) {
   constexpr int smem = 2 * (TY + 2) * (TX + 2) * PIX_BYTES + 128;
   static bool attr = false;
   if (!attr) {
@@ -324,7 +488,7 @@ int launch_fwd(const void* h, const float* weight, const float* bias, int B, int
   if (rc) return rc;
   const int tiles_x = dfb_cdiv(W, TX), tiles_y = dfb_cdiv(H, TY), nslab = dfb_cdiv(C, 64);
   dim3 grid(grid_x(B * tiles_x * tiles_y, nslab), nslab);
-  dfb_launch(mlp_dw_fwd_kernel<TX, TY>, grid, NT, smem, st, tm, weight, bias, (bf16*)u, B, H, W, C, tiles_x, tiles_y);
+  dfb_launch(mlp_dw_fwd_kernel<TX, TY>, grid, NT, smem, st, tm, weight, bias, (bf16*)u, (bf16*)gp, B, H, W, C, tiles_x, tiles_y);
   return dfb_check_launch("mlp_dw_fwd");
 }
 
@@ -349,23 +513,50 @@ int launch_bwd(const void* du, const void* h, const float* weight, const float* 
   return dfb_check_launch("mlp_dw_bwd");
 }
 
+template <int TX, int TY>
+int launch_bwd_saved(const void* du, const void* gp, const void* h, const float* weight, int B, int H, int W, int C, void* dh, float* dweight, float* dbias,
+                     float* dh_colsum, cudaStream_t st) {
+  constexpr int smem = 2 * (TY + 2) * (TX + 2) * PIX_BYTES + (64 * 9 + 128) * 4 + 128;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_dw_bwd_saved_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { dfb_set_error("mlp_dw_bwd smem attr: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
+    attr = true;
+  }
+  CUtensorMap tmDU, tmGP, tmH;
+  int rc = make_map_nhwc(&tmDU, du, B, H, W, C, TX + 2, TY + 2);
+  if (rc) return rc;
+  rc = make_map_nhwc(&tmGP, gp, B, H, W, C, TX + 2, TY + 2);
+  if (rc) return rc;
+  rc = make_map_nhwc(&tmH, h, B, H, W, C, TX + 2, TY + 2);
+  if (rc) return rc;
+  const int tiles_x = dfb_cdiv(W, TX), tiles_y = dfb_cdiv(H, TY), nslab = dfb_cdiv(C, 64);
+  dim3 grid(grid_x(B * tiles_x * tiles_y, nslab), nslab);
+  dfb_launch(mlp_dw_bwd_saved_kernel<TX, TY>, grid, NT, smem, st, tmDU, tmGP, tmH, weight, (bf16*)dh, dweight, dbias, dh_colsum, B, H, W, C, tiles_x, tiles_y);
+  return dfb_check_launch("mlp_dw_bwd_saved");
+}
+
 }  // namespace
 
 #define ST reinterpret_cast<cudaStream_t>(stream)
 
-extern "C" int dfb200_mlp_dw_fwd(const void* h, int dtype, const float* weight, const float* bias, int B, int H, int W, int C, void* u, void* stream) {
+extern "C" int dfb200_mlp_dw_fwd(const void* h, int dtype, const float* weight, const float* bias, int B, int H, int W, int C, void* u, void* gp,
+                                 void* stream) {
   DFB_REQUIRE(dtype == 1, "mlp_dw_fwd: bf16 activations only (use dfb200_dwconv_fwd for fp32)");
   DFB_REQUIRE(C % 8 == 0, "mlp_dw_fwd: C %% 8 != 0 (C=%d)", C);
   DFB_REQUIRE(B > 0 && H > 0 && W > 0, "mlp_dw_fwd: empty input");
-  return wide_tile(H, W) ? launch_fwd<40, 6>(h, weight, bias, B, H, W, C, u, ST) : launch_fwd<32, 8>(h, weight, bias, B, H, W, C, u, ST);
+  return wide_tile(H, W) ? launch_fwd<40, 6>(h, weight, bias, B, H, W, C, u, gp, ST) : launch_fwd<32, 8>(h, weight, bias, B, H, W, C, u, gp, ST);
 }
 
-extern "C" int dfb200_mlp_dw_bwd(const void* du, const void* h, int dtype, const float* weight, const float* bias, int B, int H, int W, int C, void* dh,
-                                 float* dweight, float* dbias, float* dh_colsum, void* stream) {
+extern "C" int dfb200_mlp_dw_bwd(const void* du, const void* gp, const void* h, int dtype, const float* weight, const float* bias, int B, int H, int W, int C,
+                                 void* dh, float* dweight, float* dbias, float* dh_colsum, void* stream) {
   DFB_REQUIRE(dtype == 1, "mlp_dw_bwd: bf16 activations only (use dfb200_dwconv_bwd for fp32)");
   DFB_REQUIRE(C % 8 == 0, "mlp_dw_bwd: C %% 8 != 0 (C=%d)", C);
   DFB_REQUIRE(B > 0 && H > 0 && W > 0, "mlp_dw_bwd: empty input");
   DFB_REQUIRE(dweight != nullptr && dh != nullptr, "mlp_dw_bwd: dh and dweight are required");
+  if (gp)
+    return wide_tile(H, W) ? launch_bwd_saved<40, 6>(du, gp, h, weight, B, H, W, C, dh, dweight, dbias, dh_colsum, ST)
+                           : launch_bwd_saved<32, 8>(du, gp, h, weight, B, H, W, C, dh, dweight, dbias, dh_colsum, ST);
   return wide_tile(H, W) ? launch_bwd<40, 6>(du, h, weight, bias, B, H, W, C, dh, dweight, dbias, dh_colsum, ST)
                          : launch_bwd<32, 8>(du, h, weight, bias, B, H, W, C, dh, dweight, dbias, dh_colsum, ST);
 }

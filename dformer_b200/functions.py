@@ -21,8 +21,10 @@ import os as _os
 # fused GEMM epilogues exist (gemm_tc.cu epi_mode 1/2) but measured slower on B200 for these wide-N / short-K GEMMs, whose
 # epilogue is already the critical resource (A/B in profiles/r01_ab_fused_epilogues.txt) -> off by default
 _FUSE_RES = _os.environ.get("DFB200_FUSE_RES", "0") == "1"
+_FUSE_RES_MAXM = int(_os.environ.get("DFB200_FUSE_RES_MAXM", "0"))     # ... but always for GEMMs with at most this many rows (latency-bound stages)
 _FUSE_GG = _os.environ.get("DFB200_FUSE_GG", "0") == "1"
 _FUSE_GAA = _os.environ.get("DFB200_FUSE_GAA", "1") == "1"    # one-launch attention core (csrc/gaa_fused.cu); 0 = GEMM + softmax chain
+_SAVE_GP = _os.environ.get("DFB200_MLP_SAVE_GP", "1") == "1"    # fused MLP middle keeps GELU'(z) (bf16) instead of recomputing it in backward
 _FUSE_DW = _os.environ.get("DFB200_FUSE_DW", "1") == "1"      # fused MLP middle (csrc/mlp_dw.cu); 0 = the unfused chain, kept for A/B runs
 
 
@@ -211,11 +213,14 @@ def _mlp_fwd(x, pfx, st, P, sv, scale_b, pre=None):
         hn, mu, rs = K.layernorm_fwd(x, P[pfx + "norm.weight"], P[pfx + "norm.bias"], 1e-6, T)
     h = _lin(hn, st.packed[st.key + pfx + "fc1"], T)
     if T == torch.bfloat16 and _FUSE_DW:       # TMA-fed fused kernel; the pre-activation is recomputed in the fused backward
-        u, z = K.mlp_dw_fwd(h, P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W), None
+        if _SAVE_GP and sv.get("_bwd", True):
+            u, z = K.mlp_dw_fwd(h, P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, save_gp=True)      # z slot holds GELU'(z)
+        else:
+            u, z = K.mlp_dw_fwd(h, P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W), None
     else:
         u, z = K.dwconv_fwd(h, P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, add_input=True, act=K.ACT_GELU, save_z=True)
     ls = P["layer_scale_2" if pfx == "mlp." else "layer_scale_2_e"]
-    if T == torch.bfloat16 and _FUSE_RES:      # fc2 + bias + layer-scale/DropPath residual in one tcgen05 epilogue (f kept for the dls gradient)
+    if T == torch.bfloat16 and (_FUSE_RES or x.shape[0] <= _FUSE_RES_MAXM):      # fc2 + bias + layer-scale/DropPath residual in one tcgen05 epilogue (f kept for the dls gradient)
         w2, b2 = st.packed[st.key + pfx + "fc2"]
         out = torch.empty_like(x)
         f = K.gemm(u, w2, trans_b=True, bias=b2, out_dtype=T, backend=K.TCGEN05, epi=("residual", x, out, ls, scale_b, H * W))
@@ -236,7 +241,7 @@ def _mlp_bwd(dout, pfx, st, P, sv, scale_b, G):
     if T == torch.bfloat16 and _FUSE_DW:      # GELU' . dw3x3^T . weight/bias gradients . fc1 bias gradient: one kernel, dz stays on chip
         du = _lin_bwd(df, sv[pfx + "u"], w2, G[pfx + "fc2.weight"], G[pfx + "fc2.bias"], T)
         dh = K.mlp_dw_bwd(du, sv[pfx + "h"], P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, G[pfx + "pos.weight"], G[pfx + "pos.bias"],
-                          G[pfx + "fc1.bias"])
+                          G[pfx + "fc1.bias"], gp=sv[pfx + "z"])
         dhn = _lin_bwd(dh, sv[pfx + "hn"], st.packed[st.key + pfx + "fc1"][0], G[pfx + "fc1.weight"], None, T)
         return K.layernorm_bwd(dhn, sv[pfx + "x"], P[pfx + "norm.weight"], sv[pfx + "mu"], sv[pfx + "rs"], dout,
                                G[pfx + "norm.weight"], G[pfx + "norm.bias"])
@@ -270,7 +275,7 @@ class BlockFn(torch.autograd.Function):
         Ce, M, HW = C // 2, x.shape[0], st.H * st.W
         win, dd = st.window != 0, st.drop_depth
         pk = lambda n: st.packed[st.key + n]
-        sv = {}
+        sv = {"_bwd": any(ctx.needs_input_grad)}          # inference: nothing is kept for a backward pass
         side = st.side
         main = torch.cuda.current_stream()
         # ---- depth gate path on the side stream

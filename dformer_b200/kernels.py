@@ -221,17 +221,20 @@ def dwconv_bwd(dy, x, weight, bias, B, H, W, k, add_input, act, dweight, dbias, 
     return dx
 
 
-def mlp_dw_fwd(h, weight, bias, B, H, W):
-    """u = GELU(dw3x3(h) + bias + h) for bf16 channels-last h [B*H*W, C] (DFormer.py:62-64); nothing else is stored."""
+def mlp_dw_fwd(h, weight, bias, B, H, W, save_gp=False):
+    """u = GELU(dw3x3(h) + bias + h) for bf16 channels-last h [B*H*W, C] (DFormer.py:62-64).  save_gp: also return
+    GELU'(pre-activation) (bf16), which turns the backward kernel into a pure stream."""
     u = torch.empty_like(h)
-    lib().mlp_dw_fwd(h.data_ptr(), dt(h), weight.data_ptr(), _p(bias), B, H, W, h.shape[-1], u.data_ptr(), _s())
-    return u
+    gp = torch.empty_like(h) if save_gp else None
+    lib().mlp_dw_fwd(h.data_ptr(), dt(h), weight.data_ptr(), _p(bias), B, H, W, h.shape[-1], u.data_ptr(), _p(gp), _s())
+    return (u, gp) if save_gp else u
 
 
-def mlp_dw_bwd(du, h, weight, bias, B, H, W, dweight, dbias, dh_colsum=None):
-    """Fused backward of mlp_dw_fwd: returns dh; accumulates dweight, dbias and (optionally) colsum(dh) in place."""
+def mlp_dw_bwd(du, h, weight, bias, B, H, W, dweight, dbias, dh_colsum=None, gp=None):
+    """Fused backward of mlp_dw_fwd: returns dh; accumulates dweight, dbias and (optionally) colsum(dh) in place.
+    gp = GELU'(pre-activation) kept by the forward pass, or None to recompute it from h."""
     dh = torch.empty_like(du)
-    lib().mlp_dw_bwd(du.data_ptr(), h.data_ptr(), dt(h), weight.data_ptr(), _p(bias), B, H, W, h.shape[-1], dh.data_ptr(),
+    lib().mlp_dw_bwd(du.data_ptr(), _p(gp), h.data_ptr(), dt(h), weight.data_ptr(), _p(bias), B, H, W, h.shape[-1], dh.data_ptr(),
                      dweight.data_ptr(), _p(dbias), _p(dh_colsum), _s())
     return dh
 

@@ -117,9 +117,10 @@ int dfb200_dwconv_bwd(const void* dy, const void* x, const void* z /* optional s
  *           optional).  The three accumulators are zero-initialised by the caller (fp32, atomics).
  * TMA-fed persistent kernels: one pass over h (+ du) and one over the output. */
 int dfb200_mlp_dw_fwd(const void* h, int dtype, const float* weight, const float* bias, int B, int H, int W, int C,
-                      void* u, void* stream);
-int dfb200_mlp_dw_bwd(const void* du, const void* h, int dtype, const float* weight, const float* bias, int B, int H,
-                      int W, int C, void* dh, float* dweight, float* dbias, float* dh_colsum, void* stream);
+                      void* u, void* gp /* optional: GELU'(pre-activation) in bf16, kept for the backward pass */, void* stream);
+/* gp given: dz = du * gp (pure stream, 4 passes); gp NULL: GELU'(dw3x3(h) + bias + h) is recomputed (3 passes, more math) */
+int dfb200_mlp_dw_bwd(const void* du, const void* gp, const void* h, int dtype, const float* weight, const float* bias,
+                      int B, int H, int W, int C, void* dh, float* dweight, float* dbias, float* dh_colsum, void* stream);
 
 /* ---- elementwise glue of Block/Attention ---------------------------------------------------------
  * mul:  out[m, n] = a[m, n] * b[m, n]  with independent leading dimensions (q*a, cut*e: DFormer.py:134-135;

@@ -220,6 +220,18 @@ def test_mlp_dw_fused(B, H, W, C):
     # accumulation semantics: a second call adds onto the same buffers
     k.mlp_dw_bwd(du.view(-1, C), h.view(-1, C), w, b, B, H, W, dw, db, None)
     torch.testing.assert_close(dw, 2 * wr.grad, rtol=3e-2, atol=0.06 * n)
+    # training form: forward keeps GELU'(z), backward is a pure stream (no recompute)
+    u2, gp = k.mlp_dw_fwd(h.view(-1, C), w, b, B, H, W, save_gp=True)
+    torch.testing.assert_close(u2, u)
+    zd = z.detach()
+    gp_ref = 0.5 * (1 + torch.erf(zd / math.sqrt(2))) + zd * torch.exp(-0.5 * zd * zd) / math.sqrt(2 * math.pi)
+    torch.testing.assert_close(gp.view(B, H, W, C).float(), gp_ref, **tol(dtype))
+    dw3, db3, dc3 = torch.zeros_like(w), torch.zeros_like(b), torch.zeros(C, device=DEV)
+    dh3 = k.mlp_dw_bwd(du.view(-1, C), h.view(-1, C), w, b, B, H, W, dw3, db3, dc3, gp=gp)
+    torch.testing.assert_close(dh3.view(B, H, W, C).float(), hr.grad, **t)
+    torch.testing.assert_close(dw3, wr.grad, rtol=3e-2, atol=0.03 * n)
+    torch.testing.assert_close(db3, br.grad, rtol=3e-2, atol=0.03 * n)
+    torch.testing.assert_close(dc3, dh3.float().sum(0), rtol=1e-3, atol=1e-2 * n)
 
 
 # ----------------------------------------------------------------------------- gating / residual

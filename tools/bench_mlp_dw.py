@@ -28,7 +28,7 @@ def timeit(fn, reps=20):
 
 
 def main():
-    tot = {"fwd_old": 0.0, "fwd_new": 0.0, "bwd_old": 0.0, "bwd_new": 0.0}
+    tot = {"fwd_old": 0.0, "fwd_new": 0.0, "bwd_old": 0.0, "bwd_new": 0.0, "fwd_gp": 0.0, "bwd_gp": 0.0}
     counts = {0: 3, 1: 3, 2: 3, 3: 3, 4: 12, 5: 12, 6: 2, 7: 1}
     only = int(sys.argv[1]) if len(sys.argv) > 1 else None       # profile mode: one shape, new kernels only
     for i, (B, H, W, C) in enumerate(SHAPES):
@@ -55,6 +55,14 @@ def main():
         def bwd_new():
             K.mlp_dw_bwd(du, h, w, b, B, H, W, dw, db, dc)
 
+        _, gp = K.mlp_dw_fwd(h, w, b, B, H, W, save_gp=True)
+
+        def fwd_gp():
+            K.mlp_dw_fwd(h, w, b, B, H, W, save_gp=True)
+
+        def bwd_gp():
+            K.mlp_dw_bwd(du, h, w, b, B, H, W, dw, db, dc, gp=gp)
+
         if only is not None:
             for _ in range(2):
                 fwd_new()
@@ -62,10 +70,12 @@ def main():
             torch.cuda.synchronize()
             return
 
-        t = {n: timeit(f) for n, f in (("fwd_old", fwd_old), ("fwd_new", fwd_new), ("bwd_old", bwd_old), ("bwd_new", bwd_new))}
+        t = {n: timeit(f) for n, f in (("fwd_old", fwd_old), ("fwd_new", fwd_new), ("bwd_old", bwd_old), ("bwd_new", bwd_new), ("fwd_gp", fwd_gp),
+                                       ("bwd_gp", bwd_gp))}
         by = M * C * 2
         print(f"B{B} {H}x{W} C={C}: fwd {t['fwd_old']:7.1f} -> {t['fwd_new']:7.1f} us ({2 * by / t['fwd_new'] / 1e3:5.0f} GB/s)   "
-              f"bwd {t['bwd_old']:7.1f} -> {t['bwd_new']:7.1f} us ({3 * by / t['bwd_new'] / 1e3:5.0f} GB/s)", flush=True)
+              f"bwd {t['bwd_old']:7.1f} -> {t['bwd_new']:7.1f} us ({3 * by / t['bwd_new'] / 1e3:5.0f} GB/s)   "
+              f"keep GELU': fwd {t['fwd_gp']:7.1f} us ({3 * by / t['fwd_gp'] / 1e3:5.0f} GB/s) bwd {t['bwd_gp']:7.1f} us ({4 * by / t['bwd_gp'] / 1e3:5.0f} GB/s)", flush=True)
         for n in tot:
             tot[n] += t[n] * counts[i]
     print("per DFormer-L step (us): " + "  ".join(f"{n} {v:8.0f}" for n, v in tot.items()))
