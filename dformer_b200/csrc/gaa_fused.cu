@@ -26,10 +26,33 @@ constexpr int PC = 128;            // pixels per CTA
 constexpr int SP = PC + 4;         // row pitch of the [49][PC] score tile (float4-aligned)
 constexpr int NT = 256;
 
+// Cooperative, coalesced staging of a [PC pixels][D] slice of kv (row pitch `pitch` elements) into shared memory as fp32:
+// consecutive threads fetch consecutive 32-bit words of a pixel row (per-lane row loads would touch one sector per lane).
+template <typename T, int D>
+__device__ __forceinline__ void stage_rows(const T* __restrict__ src, long pitch, int nvalid, float* __restrict__ dst) {
+  constexpr int WPR = D / 2;
+  for (int i = threadIdx.x; i < PC * WPR; i += NT) {
+    const int p = i / WPR, w = i % WPR;
+    float2 f = make_float2(0.f, 0.f);
+    if (p < nvalid) {
+      if constexpr (sizeof(T) == 2) {
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(src + (long)p * pitch + 2 * w);
+        f = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+      } else {
+        f = *reinterpret_cast<const float2*>(src + (long)p * pitch + 2 * w);
+      }
+    }
+    *reinterpret_cast<float2*>(dst + p * D + 2 * w) = f;
+  }
+}
 template <typename T>
-__device__ __forceinline__ void load_half_row(const T* __restrict__ src, float* dst, int n, bool valid) {
-#pragma unroll
-  for (int j = 0; j < n; ++j) dst[j] = valid ? to_f(src[j]) : 0.f;
+__device__ __forceinline__ void store_pair(T* dst, float a, float b) {
+  if constexpr (sizeof(T) == 2) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(&h);
+  } else {
+    *reinterpret_cast<float2*>(dst) = make_float2(a, b);
+  }
 }
 
 template <int D>
@@ -57,20 +80,18 @@ __global__ void __launch_bounds__(NT) gaa_fused_fwd_kernel(const T* __restrict__
   const int p = tid >> 1, half = tid & 1;
   const int pix = c * PC + p;
   const bool valid = pix < HW;
-  float kreg[DH];
   {
-    const T* row = kv + ((long)b * HW + (valid ? pix : 0)) * 2 * Cp + head * D + half * DH;
-    load_half_row(row, kreg, DH, valid);
-    float vreg[DH];
-    load_half_row(row + Cp, vreg, DH, valid);
-#pragma unroll
-    for (int j = 0; j < DH; ++j) Vs[p * D + half * DH + j] = vreg[j];
+    const T* rows = kv + ((long)b * HW + (long)c * PC) * 2 * Cp + head * D;
+    const int nvalid = min(PC, HW - c * PC);
+    stage_rows<T, D>(rows, 2L * Cp, nvalid, Ss);            // K chunk, parked in the (not yet used) score tile
+    stage_rows<T, D>(rows + Cp, 2L * Cp, nvalid, Vs);       // V chunk
   }
   __syncthreads();
   // ---- scores of this CTA's pixels
   float2 k2[DH / 2];
 #pragma unroll
-  for (int j = 0; j < DH / 2; ++j) k2[j] = make_float2(kreg[2 * j], kreg[2 * j + 1]);
+  for (int j = 0; j < DH / 2; ++j) k2[j] = *reinterpret_cast<const float2*>(Ss + p * D + half * DH + 2 * j);
+  __syncthreads();                                          // every thread holds its k half-row before scores overwrite the tile
 #pragma unroll 7
   for (int r = 0; r < NQ; ++r) {
     const float2* q = reinterpret_cast<const float2*>(Qs + r * D + half * DH);      // 8-byte aligned: D and DH are even
@@ -214,19 +235,19 @@ __global__ void __launch_bounds__(NT) gaa_fused_bwd_kernel(const float* __restri
   float2 k2[DH / 2], v2[DH / 2], dk2[DH / 2], dv2[DH / 2];
   const long rowoff = ((long)b * HW + (valid ? pix : 0)) * 2 * Cp + head * D + half * DH;
   {
-    float kreg[DH], vreg[DH];
-    load_half_row(kv + rowoff, kreg, DH, valid);
-    load_half_row(kv + rowoff + Cp, vreg, DH, valid);
-#pragma unroll
-    for (int j = 0; j < DH; ++j) Ks[p * D + half * DH + j] = kreg[j];
-#pragma unroll
-    for (int j = 0; j < DH / 2; ++j) {
-      k2[j] = make_float2(kreg[2 * j], kreg[2 * j + 1]);
-      v2[j] = make_float2(vreg[2 * j], vreg[2 * j + 1]);
-      dk2[j] = dv2[j] = make_float2(0.f, 0.f);
-    }
+    const T* rows = kv + ((long)b * HW + (long)c * PC) * 2 * Cp + head * D;
+    const int nvalid = min(PC, HW - c * PC);
+    stage_rows<T, D>(rows, 2L * Cp, nvalid, Ks);            // K chunk (kept: phase 2 reads it column-wise)
+    stage_rows<T, D>(rows + Cp, 2L * Cp, nvalid, dSs);      // V chunk, parked in the (not yet used) dS tile
   }
   __syncthreads();
+#pragma unroll
+  for (int j = 0; j < DH / 2; ++j) {
+    k2[j] = *reinterpret_cast<const float2*>(Ks + p * D + half * DH + 2 * j);
+    v2[j] = *reinterpret_cast<const float2*>(dSs + p * D + half * DH + 2 * j);
+    dk2[j] = dv2[j] = make_float2(0.f, 0.f);
+  }
+  __syncthreads();                                          // v half-rows are in registers before dS overwrites the tile
 #pragma unroll 2
   for (int r = 0; r < NQ; ++r) {
     const float2* q = reinterpret_cast<const float2*>(Qs + r * D + half * DH);
@@ -248,10 +269,8 @@ __global__ void __launch_bounds__(NT) gaa_fused_bwd_kernel(const float* __restri
   if (valid) {
 #pragma unroll
     for (int j = 0; j < DH / 2; ++j) {
-      dkv[rowoff + 2 * j] = from_f<T>(dk2[j].x * scale);
-      dkv[rowoff + 2 * j + 1] = from_f<T>(dk2[j].y * scale);
-      dkv[rowoff + Cp + 2 * j] = from_f<T>(dv2[j].x);
-      dkv[rowoff + Cp + 2 * j + 1] = from_f<T>(dv2[j].y);
+      store_pair<T>(dkv + rowoff + 2 * j, dk2[j].x * scale, dk2[j].y * scale);
+      store_pair<T>(dkv + rowoff + Cp + 2 * j, dv2[j].x, dv2[j].y);
     }
   }
   __syncthreads();

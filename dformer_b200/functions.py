@@ -290,18 +290,21 @@ class BlockFn(torch.autograd.Function):
         K.share(main, en, mu2, rs2, ef, ec, e)
         # ---- RGB path
         xn, mu1, rs1 = K.layernorm_fwd(x, P["attn.norm.weight"], P["attn.norm.bias"], 1e-6, T)
+        if win:                                                       # global-awareness branch on a second side stream:
+            side2 = st.side2                                          # the pooled queries only need the two LayerNorm outputs, so they
+            K.fork(side2)                                             # are computed while the main stream runs the q|cut|l GEMM
+            with torch.cuda.stream(side2):
+                side2.wait_event(ev_en)
+                pooled = K.pool7_fwd(xn, en, B, H, W)
+                m = _lin(pooled, pk("attn.short_cut_linear"), T)
         qcl = _lin(xn, pk("attn.qcl"), T)                                         # [M, 2.5C] = q | cut | z_l
         l = K.act_fwd(qcl[:, C + Ce:], K.ACT_GELU)
         ycols = 2 * C if win else C + Ce
         y = torch.empty((M, ycols), device=x.device, dtype=T)
-        if win:                                                       # global-awareness branch on a second side stream
-            side2 = st.side2
+        if win:
             K.fork(side2)
             with torch.cuda.stream(side2):
                 kv = _lin(l, pk("attn.kv"), T)
-                side2.wait_event(ev_en)
-                pooled = K.pool7_fwd(xn, en, B, H, W)
-                m = _lin(pooled, pk("attn.short_cut_linear"), T)
                 dh_ = Ce // st.heads
                 if _FUSE_GAA and dh_ in K.GAA_FUSED_DIMS:           # one launch; keeps only the row log-sum-exp
                     o7, lse7 = K.gaa_fused_fwd(m, kv, B, HW, st.heads, dh_)
@@ -402,11 +405,12 @@ class BlockFn(torch.autograd.Function):
                     dm, dkv = K.gaa_fused_bwd(do7, sv["o7"], sv["lse7"], sv["m"], sv["kv"], B, HW, st.heads, Ce // st.heads)
                 else:
                     dm, dkv = K.gaa_bwd(do7, sv["m"], sv["kv"], sv["probs"], B, HW, st.heads, Ce // st.heads)
-                dmT = dm if T == F32 else K.cast(dm, T)
+                dl_kv = _lin_bwd(dkv, sv["l"], pk("attn.kv")[0], G["attn.kv.weight"], G["attn.kv.bias"], T)
+                ev_dlkv = K.signal(side2)                 # the main stream needs dl_kv early (GELU' of l); the pooled-query
+                dmT = dm if T == F32 else K.cast(dm, T)   # gradients below are only consumed by the final LayerNorm backward
                 dpooled = _lin_bwd(dmT, sv["pooled"], pk("attn.short_cut_linear")[0], G["attn.short_cut_linear.weight"],
                                    G["attn.short_cut_linear.bias"], T)
                 dxn_pool, den_pool = K.pool7_bwd(dpooled, C, Ce, B, H, W)
-                dl_kv = _lin_bwd(dkv, sv["l"], pk("attn.kv")[0], G["attn.kv.weight"], G["attn.kv.bias"], T)
             K.share(main, dxn_pool, den_pool, dl_kv)
         # ---- RGB path: a = a(dw7(l))
         K.mul_bwd(dy[:, :C], qcl[:, :C], sv["a"], dqcl[:, :C], da)
@@ -414,13 +418,15 @@ class BlockFn(torch.autograd.Function):
         dl = K.dwconv_bwd(dcv, sv["l"], P["attn.conv.weight"], P["attn.conv.bias"], B, H, W, 7, False, K.ACT_NONE,
                           G["attn.conv.weight"], G["attn.conv.bias"], wgrad_stream=_WGRAD_STREAM)
         if win:
-            K.join(side2)
+            main.wait_event(ev_dlkv)
         K.act_bwd(dl, qcl[:, C + Ce:], K.ACT_GELU, out=dqcl[:, C + Ce:], dout2=dl_kv)      # kv branch's gradient of l joins here
         qclw = pk("attn.qcl")[0]
         dWq = ar.span(st.prefix + "attn.q.weight", st.prefix + "attn.l.weight", qclw.shape)
         dbq = ar.span(st.prefix + "attn.q.bias", st.prefix + "attn.l.bias", (qclw.shape[0],))
         dxn = _lin_bwd(dqcl, sv["xn"], qclw, dWq, dbq, T)
         # the pooled-query branch's gradient joins inside the LayerNorm backward kernels (dy2)
+        if win:
+            K.join(side2)
         dx = K.layernorm_bwd(dxn, sv["x"], P["attn.norm.weight"], sv["mu1"], sv["rs1"], dx1, G["attn.norm.weight"], G["attn.norm.bias"],
                              dy2=dxn_pool)
         K.join(side)
