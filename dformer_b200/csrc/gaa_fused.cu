@@ -31,7 +31,8 @@ constexpr int NT = 256;
 template <typename T, int D>
 __device__ __forceinline__ void stage_rows(const T* __restrict__ src, long pitch, int nvalid, float* __restrict__ dst) {
   constexpr int WPR = D / 2;
-  for (int i = threadIdx.x; i < PC * WPR; i += NT) {
+#pragma unroll
+  for (int i = threadIdx.x; i < PC * WPR; i += NT) {        // fully unrolled: all loads of a thread are in flight together
     const int p = i / WPR, w = i % WPR;
     float2 f = make_float2(0.f, 0.f);
     if (p < nvalid) {
@@ -76,7 +77,16 @@ __global__ void __launch_bounds__(NT) gaa_fused_fwd_kernel(const T* __restrict__
   __shared__ int s_last;
   const int tid = threadIdx.x, bh = blockIdx.y, b = bh / heads, head = bh % heads, c = blockIdx.x;
   const int Cp = heads * D;
+#ifdef GAA_TIMING
+  long long tt[8]; int ti = 0;
+#define TICK() do { __syncthreads(); tt[ti++] = clock64(); } while (0)
+#else
+#define TICK() do {} while (0)
+#endif
+  TICK();
+#pragma unroll
   for (int i = tid; i < NQ * D; i += NT) Qs[i] = to_f(m[((long)b * NQ + i / D) * Cp + head * D + i % D]);
+  TICK();
   const int p = tid >> 1, half = tid & 1;
   const int pix = c * PC + p;
   const bool valid = pix < HW;
@@ -87,6 +97,7 @@ __global__ void __launch_bounds__(NT) gaa_fused_fwd_kernel(const T* __restrict__
     stage_rows<T, D>(rows + Cp, 2L * Cp, nvalid, Vs);       // V chunk
   }
   __syncthreads();
+  TICK();
   // ---- scores of this CTA's pixels
   float2 k2[DH / 2];
 #pragma unroll
@@ -103,6 +114,7 @@ __global__ void __launch_bounds__(NT) gaa_fused_fwd_kernel(const T* __restrict__
     if (half == (r & 1)) Ss[r * SP + p] = valid ? s * scale : -INFINITY;
   }
   __syncthreads();
+  TICK();
   // ---- local softmax statistics, P~ = exp(S - local max) in place
   for (int r = tid >> 5; r < NQ; r += NT / 32) {
     const int lane = tid & 31;
@@ -122,21 +134,23 @@ __global__ void __launch_bounds__(NT) gaa_fused_fwd_kernel(const T* __restrict__
     if (lane == 0) { ms[r] = mx; ls[r] = sum; }
   }
   __syncthreads();
+  TICK();
   // ---- unnormalised partial context O~[r][j] = sum_p P~[r][p] V[p][j]
   {
     const int j = tid % D, g = tid / D;
     if (g < G) {
-      float acc[RPG];
+      float2 acc[RPG];
 #pragma unroll
-      for (int i = 0; i < RPG; ++i) acc[i] = 0.f;
+      for (int i = 0; i < RPG; ++i) acc[i] = make_float2(0.f, 0.f);
       for (int p4 = 0; p4 < PC; p4 += 4) {
-        const float v0 = Vs[(p4 + 0) * D + j], v1 = Vs[(p4 + 1) * D + j], v2 = Vs[(p4 + 2) * D + j], v3 = Vs[(p4 + 3) * D + j];
+        const float2 v01 = make_float2(Vs[(p4 + 0) * D + j], Vs[(p4 + 1) * D + j]), v23 = make_float2(Vs[(p4 + 2) * D + j], Vs[(p4 + 3) * D + j]);
 #pragma unroll
         for (int i = 0; i < RPG; ++i) {
           const int r = g + i * G;
-          if (r < NQ) {
+          if (r < NQ) {                                   // even / odd pixels accumulate in the two halves of a packed FFMA2
             const float4 pr = *reinterpret_cast<const float4*>(Ss + r * SP + p4);
-            acc[i] = fmaf(pr.x, v0, fmaf(pr.y, v1, fmaf(pr.z, v2, fmaf(pr.w, v3, acc[i]))));
+            ffma2(acc[i], make_float2(pr.x, pr.y), v01);
+            ffma2(acc[i], make_float2(pr.z, pr.w), v23);
           }
         }
       }
@@ -145,17 +159,22 @@ __global__ void __launch_bounds__(NT) gaa_fused_fwd_kernel(const T* __restrict__
         const int r = g + i * G;
         if (r < NQ) {
           float* dst = part + (((long)bh * nchunks + c) * NQ + r) * PS;
-          dst[j] = acc[i];
+          dst[j] = acc[i].x + acc[i].y;
           if (j == 0) { dst[D] = ms[r]; dst[D + 1] = ls[r]; }
         }
       }
     }
   }
   // ---- the last CTA of this (image, head) merges all partials
+  TICK();
   __threadfence();
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(&counters[bh], 1) == nchunks - 1);
   __syncthreads();
+  TICK();
+#ifdef GAA_TIMING
+  if (tid == 0 && blockIdx.x == 1 && blockIdx.y == 3) printf("gaa fwd phases (cycles): Q %lld  KV %lld  score %lld  stats %lld  PV %lld  fence+ticket %lld\n", tt[1]-tt[0], tt[2]-tt[1], tt[3]-tt[2], tt[4]-tt[3], tt[5]-tt[4], tt[6]-tt[5]);
+#endif
   if (!s_last) return;
   __threadfence();
   // (1) all (max, sum) pairs of this (image, head) -> shared memory, independent loads
@@ -217,18 +236,32 @@ __global__ void __launch_bounds__(NT) gaa_fused_bwd_kernel(const float* __restri
   float* Dr = lses + NQ;                 // [49] rowsum(dO o O) = rowsum(dP o P)
   const int tid = threadIdx.x, bh = blockIdx.y, b = bh / heads, head = bh % heads, c = blockIdx.x;
   const int Cp = heads * D;
-  for (int i = tid; i < NQ * D; i += NT) {
-    const long g = ((long)b * NQ + i / D) * Cp + head * D + i % D;
-    Qs[i] = to_f(m[g]);
-    dOs[i] = dout[g];
+#ifdef GAA_TIMING
+  long long tt[8]; int ti = 0;
+#endif
+  TICK();
+  {
+    // every thread's loads (Q, dO, O) are issued before any is consumed; Dr[r] = sum_j dO[r][j] O[r][j] is then reduced from
+    // shared memory (dO) and a staged copy of O parked in the (not yet used) dS tile
+    float* Os = dSs;
+#pragma unroll
+    for (int i = tid; i < NQ * D; i += NT) {
+      const long g = ((long)b * NQ + i / D) * Cp + head * D + i % D;
+      Qs[i] = to_f(m[g]);
+      dOs[i] = dout[g];
+      Os[i] = out[g];
+    }
+    if (tid < NQ) lses[tid] = lse[(long)bh * NQ + tid];
+    __syncthreads();
+    for (int r = tid >> 5; r < NQ; r += NT / 32) {
+      float s = 0.f;
+      for (int j = tid & 31; j < D; j += 32) s = fmaf(dOs[r * D + j], Os[r * D + j], s);
+      s = warp_sum(s);
+      if ((tid & 31) == 0) Dr[r] = s;
+    }
+    __syncthreads();                                        // Os (in the dS tile) is dead before V is staged there
   }
-  for (int r = tid >> 5; r < NQ; r += NT / 32) {
-    const long g = ((long)b * NQ + r) * Cp + head * D;
-    float s = 0.f;
-    for (int j = tid & 31; j < D; j += 32) s = fmaf(dout[g + j], out[g + j], s);
-    s = warp_sum(s);
-    if ((tid & 31) == 0) { Dr[r] = s; lses[r] = lse[(long)bh * NQ + r]; }
-  }
+  TICK();
   const int p = tid >> 1, half = tid & 1;
   const int pix = c * PC + p;
   const bool valid = pix < HW;
@@ -248,6 +281,7 @@ __global__ void __launch_bounds__(NT) gaa_fused_bwd_kernel(const float* __restri
     dk2[j] = dv2[j] = make_float2(0.f, 0.f);
   }
   __syncthreads();                                          // v half-rows are in registers before dS overwrites the tile
+  TICK();
 #pragma unroll 2
   for (int r = 0; r < NQ; ++r) {
     const float2* q = reinterpret_cast<const float2*>(Qs + r * D + half * DH);
@@ -266,6 +300,7 @@ __global__ void __launch_bounds__(NT) gaa_fused_bwd_kernel(const float* __restri
     for (int j = 0; j < DH / 2; ++j) { ffma2(dv2[j], P2, gv[j]); ffma2(dk2[j], ds2, qv[j]); }
     if (half == (r & 1)) dSs[r * SP + p] = ds;
   }
+  TICK();
   if (valid) {
 #pragma unroll
     for (int j = 0; j < DH / 2; ++j) {
@@ -274,29 +309,35 @@ __global__ void __launch_bounds__(NT) gaa_fused_bwd_kernel(const float* __restri
     }
   }
   __syncthreads();
+  TICK();
   // ---- dQ[r][j] += scale * sum_p dS[r][p] K[p][j]   (partial over this CTA's pixels)
   const int j = tid % D, g = tid / D;
   if (g < G) {
-    float acc[RPG];
+    float2 acc[RPG];
 #pragma unroll
-    for (int i = 0; i < RPG; ++i) acc[i] = 0.f;
+    for (int i = 0; i < RPG; ++i) acc[i] = make_float2(0.f, 0.f);
     for (int p4 = 0; p4 < PC; p4 += 4) {
-      const float k0 = Ks[(p4 + 0) * D + j], k1 = Ks[(p4 + 1) * D + j], k2 = Ks[(p4 + 2) * D + j], k3 = Ks[(p4 + 3) * D + j];
+      const float2 k01 = make_float2(Ks[(p4 + 0) * D + j], Ks[(p4 + 1) * D + j]), k23 = make_float2(Ks[(p4 + 2) * D + j], Ks[(p4 + 3) * D + j]);
 #pragma unroll
       for (int i = 0; i < RPG; ++i) {
         const int r = g + i * G;
         if (r < NQ) {
           const float4 d4 = *reinterpret_cast<const float4*>(dSs + r * SP + p4);
-          acc[i] = fmaf(d4.x, k0, fmaf(d4.y, k1, fmaf(d4.z, k2, fmaf(d4.w, k3, acc[i]))));
+          ffma2(acc[i], make_float2(d4.x, d4.y), k01);
+          ffma2(acc[i], make_float2(d4.z, d4.w), k23);
         }
       }
     }
 #pragma unroll
     for (int i = 0; i < RPG; ++i) {
       const int r = g + i * G;
-      if (r < NQ) atomicAdd(dm + ((long)b * NQ + r) * Cp + head * D + j, acc[i] * scale);
+      if (r < NQ) atomicAdd(dm + ((long)b * NQ + r) * Cp + head * D + j, (acc[i].x + acc[i].y) * scale);
     }
   }
+  TICK();
+#ifdef GAA_TIMING
+  if (tid == 0 && blockIdx.x == 1 && blockIdx.y == 3) printf("gaa bwd phases (cycles): QdO+Dr %lld  KV %lld  rloop %lld  store %lld  dQ+atomics %lld\n", tt[1]-tt[0], tt[2]-tt[1], tt[3]-tt[2], tt[4]-tt[3], tt[5]-tt[4]);
+#endif
 }
 
 template <int D> constexpr int fwd_smem() { return (NQ * D + PC * D + NQ * SP + 2 * NQ) * 4; }
