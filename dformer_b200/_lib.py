@@ -72,8 +72,8 @@ SIGNATURES = {
     "dfb200_normalize_cols": [P, I, I, I, P, P, P],
     "dfb200_softmax_rows": [P, I, I, P, P],
     "dfb200_softmax_rows_bwd": [P, P, I, I, P, P],
-    "dfb200_mu_update": [P, P, P, F, L, P, P],
-    "dfb200_mu_update_bwd": [P, P, P, P, F, L, P, I, P, P, P],
+    "dfb200_mu_update": [P, P, P, F, L, P, P, I, P],
+    "dfb200_mu_update_bwd": [P, P, P, P, F, L, P, I, P, L, I, P, I, P],
     "dfb200_cast": [P, I, P, I, L, P],
     "dfb200_cast2d": [P, I, L, P, I, L, L, I, P],
     "dfb200_axpy": [P, I, F, P, I, L, P],

@@ -270,20 +270,32 @@ __global__ void softmax_rows_bwd_kernel(const float* __restrict__ dout, const fl
   for (int c = lane; c < cols; c += 32) d[c] = p[c] * (g[c] - s);
 }
 
-__global__ void mu_update_kernel(const float* __restrict__ a, const float* __restrict__ num, const float* __restrict__ den, float eps, long n, float* __restrict__ out) {
+// Multiplicative update of NMF2D (ham_head.py:126,133) with an optional second copy of the result in the compute dtype
+// (bf16 operand of the next batched GEMM), written in the same pass.
+template <typename TL>
+__global__ void mu_update_kernel(const float* __restrict__ a, const float* __restrict__ num, const float* __restrict__ den, float eps, long n,
+                                 float* __restrict__ out, TL* __restrict__ out_lo) {
   pdl_sync();
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-    out[i] = a[i] * num[i] / (den[i] + eps);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float v = a[i] * num[i] / (den[i] + eps);
+    out[i] = v;
+    if (out_lo) out_lo[i] = from_f<TL>(v);
+  }
 }
+// Backward.  dnum / dden are only ever consumed as GEMM operands, so they are written straight in the compute dtype: dnum with a
+// row length `cols` and leading dimension `ld_dnum` (it lands in a column slice of a K-concatenated operand), dden contiguous.
+template <typename TL>
 __global__ void mu_update_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ a, const float* __restrict__ num, const float* __restrict__ den,
-                                     float eps, long n, float* __restrict__ da, int acc_da, float* __restrict__ dnum, float* __restrict__ dden) {
+                                     float eps, long n, float* __restrict__ da, int acc_da, TL* __restrict__ dnum, long ld_dnum, int cols,
+                                     TL* __restrict__ dden) {
   pdl_sync();
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const float inv = 1.f / (den[i] + eps), g = dout[i];
     const float ga = g * num[i] * inv;
     da[i] = acc_da ? da[i] + ga : ga;
-    dnum[i] = g * a[i] * inv;
-    dden[i] = -g * a[i] * num[i] * inv * inv;
+    const long r = i / cols;
+    dnum[r * ld_dnum + (i - r * cols)] = from_f<TL>(g * a[i] * inv);
+    dden[i] = from_f<TL>(-g * a[i] * num[i] * inv * inv);
   }
 }
 
@@ -434,13 +446,16 @@ extern "C" int dfb200_softmax_rows_bwd(const float* dout, const float* out, int 
   dfb_launch(softmax_rows_bwd_kernel, dfb_cdiv(rows, 8), 256, 0, ST, dout, out, rows, cols, din);
   return dfb_check_launch("softmax_rows_bwd");
 }
-extern "C" int dfb200_mu_update(const float* a, const float* num, const float* den, float eps, long n, float* out, void* stream) {
-  dfb_launch(mu_update_kernel, ew_grid(n), EW_THREADS, 0, ST, a, num, den, eps, n, out);
+extern "C" int dfb200_mu_update(const float* a, const float* num, const float* den, float eps, long n, float* out, void* out_lo, int lo_dtype, void* stream) {
+  DFB_DISPATCH_DTYPE(lo_dtype, TL, { dfb_launch(mu_update_kernel<TL>, ew_grid(n), EW_THREADS, 0, ST, a, num, den, eps, n, out, (TL*)out_lo); });
   return dfb_check_launch("mu_update");
 }
 extern "C" int dfb200_mu_update_bwd(const float* dout, const float* a, const float* num, const float* den, float eps, long n, float* da,
-                                    int accumulate_da, float* dnum, float* dden, void* stream) {
-  dfb_launch(mu_update_bwd_kernel, ew_grid(n), EW_THREADS, 0, ST, dout, a, num, den, eps, n, da, accumulate_da, dnum, dden);
+                                    int accumulate_da, void* dnum, long ld_dnum, int cols, void* dden, int lo_dtype, void* stream) {
+  DFB_REQUIRE(cols > 0 && ld_dnum >= cols && dnum && dden, "mu_update_bwd: bad arguments");
+  DFB_DISPATCH_DTYPE(lo_dtype, TL, {
+    dfb_launch(mu_update_bwd_kernel<TL>, ew_grid(n), EW_THREADS, 0, ST, dout, a, num, den, eps, n, da, accumulate_da, (TL*)dnum, ld_dnum, cols, (TL*)dden);
+  });
   return dfb_check_launch("mu_update_bwd");
 }
 

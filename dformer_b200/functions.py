@@ -461,24 +461,24 @@ def _nmf_fwd(x, bases_raw, steps, T):
     coef_l = lo(coef)
     tape = []
 
+    lo_out = lambda *s: torch.empty(s, device=dev, dtype=T)     # short-K products land directly in the compute dtype (no split-K, no cast)
+
     def coef_update(coef, coef_l, bases, bases_l):
         num = K.bgemm(x, bases_l, f(B, N, R), M=N, N=R, K=D)
-        btb_l = lo(K.bgemm(bases_l, bases_l, f(B, R, R), trans_a=True, M=R, N=R, K=D))
+        btb_l = K.bgemm(bases_l, bases_l, lo_out(B, R, R), trans_a=True, M=R, N=R, K=D)
         den = K.bgemm(coef_l, btb_l, f(B, N, R), M=N, N=R, K=R)
-        return K.mu_update(coef, num, den), (coef, coef_l, num, den, bases_l, btb_l)
+        coef_n, coef_nl = K.mu_update(coef, num, den, lo_dtype=T)          # fp32 state + compute-dtype operand from one launch
+        return coef_n, coef_nl, (coef, coef_l, num, den, bases_l, btb_l)
 
     for _ in range(steps):
-        coef_n, rec_c = coef_update(coef, coef_l, bases, bases_l)
-        coef_nl = lo(coef_n)
+        coef_n, coef_nl, rec_c = coef_update(coef, coef_l, bases, bases_l)
         num2 = K.bgemm(x, coef_nl, f(B, D, R), trans_a=True, M=D, N=R, K=N, splitk=sk)
         ctc_l = lo(K.bgemm(coef_nl, coef_nl, f(B, R, R), trans_a=True, M=R, N=R, K=N, splitk=sk))
         den2 = K.bgemm(bases_l, ctc_l, f(B, D, R), M=D, N=R, K=R)
-        bases_n = K.mu_update(bases, num2, den2)
+        bases_n, bases_nl = K.mu_update(bases, num2, den2, lo_dtype=T)
         tape.append((rec_c, (bases, bases_l, num2, den2, coef_nl, ctc_l)))
-        coef, coef_l, bases = coef_n, coef_nl, bases_n
-        bases_l = lo(bases)
-    coef_f, rec_f = coef_update(coef, coef_l, bases, bases_l)
-    coef_fl = lo(coef_f)
+        coef, coef_l, bases, bases_l = coef_n, coef_nl, bases_n, bases_nl
+    coef_f, coef_fl, rec_f = coef_update(coef, coef_l, bases, bases_l)
     out = torch.empty((B, N, D), device=dev, dtype=T)
     K.bgemm(coef_fl, bases_l, out, trans_b=True, M=N, N=D, K=R)
     return out, (tape, rec_f, coef_fl, bases_l)
@@ -503,12 +503,15 @@ def _nmf_bwd(dout, x, saved, T):
     slot = [0]
 
     def push(a_src, b_src):
-        """register one product  dx += a_src[B,N,R] @ b_src[B,D,R]^T ; returns the compute-dtype views of both factors"""
+        """register one product  dx += a[B,N,R] @ b[B,D,R]^T : returns the two column slices of the concatenated operands; a source
+        given as None is written into its slice by the caller (mu_update_bwd emits dnum straight into it)"""
         k0 = slot[0] * R
         slot[0] += 1
         av, bv = a_cat[:, :, k0:k0 + R], b_cat[:, :, k0:k0 + R]
-        K.cast_into(a_src, av)
-        K.cast_into(b_src, bv)
+        if a_src is not None:
+            K.cast_into(a_src, av)
+        if b_src is not None:
+            K.cast_into(b_src, bv)
         return av, bv
 
     sk = max(1, N // 512)
@@ -519,9 +522,8 @@ def _nmf_bwd(dout, x, saved, T):
     def coef_update_bwd(dcoef_new, rec, dbases):
         coef, coef_l, num, den, bases_l, btb_l = rec
         dco = f(B, N, R)
-        dnum, dden = K.mu_update_bwd(dcoef_new, coef, num, den, dco, False)
-        dnum_l, _ = push(dnum, bases_l)                                                     # num = x @ bases
-        dden_l = lo(dden)
+        dnum_l, _ = push(None, bases_l)                                                     # num = x @ bases
+        dden_l = K.mu_update_bwd(dcoef_new, coef, num, den, dco, False, dnum_l, T)
         K.bgemm(x, dnum_l, dbases, trans_a=True, M=D, N=R, K=N, accumulate=True, splitk=sk)
         K.bgemm(dden_l, btb_l, dco, M=N, N=R, K=R, accumulate=True)                         # den = coef @ BtB (BtB symmetric)
         dbtb_l = lo(K.bgemm(coef_l, dden_l, f(B, R, R), trans_a=True, M=R, N=R, K=N, splitk=sk))
@@ -532,12 +534,11 @@ def _nmf_bwd(dout, x, saved, T):
     def bases_update_bwd(dbases_new, rec, dcoef):
         bases, bases_l, num2, den2, coef_l, ctc_l = rec
         dba = f(B, D, R)
-        dnum2, dden2 = K.mu_update_bwd(dbases_new, bases, num2, den2, dba, False)
-        _, dnum2_l = push(coef_l, dnum2)                                                    # num2 = x^T @ coef
-        dden2_l = lo(dden2)
+        _, dnum2_l = push(coef_l, None)                                                     # num2 = x^T @ coef
+        dden2_l = K.mu_update_bwd(dbases_new, bases, num2, den2, dba, False, dnum2_l, T)
         K.bgemm(x, dnum2_l, dcoef, M=N, N=R, K=D, accumulate=True)
         K.bgemm(dden2_l, ctc_l, dba, M=D, N=R, K=R, accumulate=True)                        # den2 = bases @ CtC
-        dctc_l = lo(K.bgemm(bases_l, dden2_l, f(B, R, R), trans_a=True, M=R, N=R, K=D))
+        dctc_l = K.bgemm(bases_l, dden2_l, torch.empty((B, R, R), device=dev, dtype=T), trans_a=True, M=R, N=R, K=D)
         K.bgemm(coef_l, dctc_l, dcoef, M=N, N=R, K=R, accumulate=True)                      # CtC = coef^T coef
         K.bgemm(coef_l, dctc_l, dcoef, trans_b=True, M=N, N=R, K=R, accumulate=True)
         return dba
@@ -597,6 +598,12 @@ class HeadFn(torch.autograd.Function):
         T = st.dtype
         ar: GradArena = st.arena
         G = {n: ar.view(st.prefix + n) for n in st.names}
+        # the five weight gradients of the head are leaves: they run on a side stream under the long, latency-bound NMF chain
+        global _WGRAD_STREAM
+        ws = getattr(st, "wstream", None)
+        if ws is not None:
+            K.fork(ws)
+            _WGRAD_STREAM = ws
         B = st.B
         (h1, w1), (h2, w2), (h3, w3) = st.sizes
         C1, C2, C3, M, D = sv["shapes"]
@@ -628,6 +635,9 @@ class HeadFn(torch.autograd.Function):
         K.resize_bwd(dcat, C1, B, h2, w2, C2, h1, w1, do2)
         K.resize_bwd(dcat, C1 + C2, B, h3, w3, C3, h1, w1, do3)
         ctx.sv = None
+        _WGRAD_STREAM = None
+        if ws is not None:
+            K.join(ws)
         ar.done(st.tag)
         return (do1, do2, do3, None, None) + tuple(G[n] for n in st.names)
 

@@ -433,18 +433,25 @@ def softmax_rows_bwd(dout, out):
     return din
 
 
-def mu_update(a, num, den, eps=1e-6):
+def mu_update(a, num, den, eps=1e-6, lo_dtype=None):
+    """a * num / (den + eps); with lo_dtype also returns a copy in that dtype written by the same launch."""
     out = torch.empty_like(a)
-    lib().mu_update(a.data_ptr(), num.data_ptr(), den.data_ptr(), eps, a.numel(), out.data_ptr(), _s())
-    return out
+    lo = torch.empty(a.shape, device=a.device, dtype=lo_dtype) if lo_dtype is not None and lo_dtype != a.dtype else None
+    lib().mu_update(a.data_ptr(), num.data_ptr(), den.data_ptr(), eps, a.numel(), out.data_ptr(), _p(lo), _DT[lo_dtype] if lo is not None else 0, _s())
+    if lo_dtype is None:
+        return out
+    return out, (lo if lo is not None else out)
 
 
-def mu_update_bwd(dout, a, num, den, da, accumulate_da, eps=1e-6):
-    dnum = torch.empty_like(a)
-    dden = torch.empty_like(a)
+def mu_update_bwd(dout, a, num, den, da, accumulate_da, dnum_out, dden_dtype, eps=1e-6):
+    """da (fp32) in place; dnum written into `dnum_out` (a [..., cols] view with uniform row stride, e.g. a column slice of a
+    K-concatenated GEMM operand) and dden returned contiguous, both in the GEMM compute dtype."""
+    cols = a.shape[-1]
+    assert dnum_out.shape == a.shape and dnum_out.stride(-1) == 1 and dnum_out.dtype == dden_dtype
+    dden = torch.empty(a.shape, device=a.device, dtype=dden_dtype)
     lib().mu_update_bwd(dout.data_ptr(), a.data_ptr(), num.data_ptr(), den.data_ptr(), eps, a.numel(), da.data_ptr(), int(accumulate_da),
-                        dnum.data_ptr(), dden.data_ptr(), _s())
-    return dnum, dden
+                        dnum_out.data_ptr(), dnum_out.stride(-2), cols, dden.data_ptr(), _DT[dden_dtype], _s())
+    return dden
 
 
 def cast(x, dtype):

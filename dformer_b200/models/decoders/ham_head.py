@@ -142,7 +142,10 @@ class LightHamHead(BaseDecodeHead):
             keep = 1.0 - self.dropout.p
             drop_mask = (torch.rand(B, self.channels, device=dev) < keep).float() / keep             # Dropout2d: whole channels per sample
         sync = True if (self.sync_bn and training) else False
-        st = SimpleNamespace(dtype=T, packed=packed, arena=arena, prefix="", tag="head", names=self.PARAMS, B=B, sizes=sizes,
+        ws = getattr(self, "_wstream", None)
+        if ws is None or ws.device != dev:
+            ws = self._wstream = torch.cuda.Stream(device=dev)
+        st = SimpleNamespace(dtype=T, packed=packed, arena=arena, prefix="", tag="head", names=self.PARAMS, B=B, sizes=sizes, wstream=ws,
                              steps=ham.train_steps if training else ham.eval_steps, drop_mask=drop_mask,
                              bn_sq=Fn.BNState(self.squeeze.bn, "squeeze.bn", training, sync),
                              bn_out=Fn.BNState(self.hamburger.ham_out.bn, "hamburger.ham_out.bn", training, sync),

@@ -208,10 +208,12 @@ int dfb200_normalize_cols(const float* in, int B, int D, int R, float* out, floa
 int dfb200_softmax_rows(const float* in, int rows, int cols, float* out, void* stream);
 int dfb200_softmax_rows_bwd(const float* dout, const float* out, int rows, int cols, float* din, void* stream);
 /* out = a * num / (den + eps) */
-int dfb200_mu_update(const float* a, const float* num, const float* den, float eps, long n, float* out, void* stream);
-/* given dout: da (+)= dout*num/(den+eps); dnum = dout*a/(den+eps); dden = -dout*a*num/(den+eps)^2 */
+int dfb200_mu_update(const float* a, const float* num, const float* den, float eps, long n, float* out,
+                     void* out_lo /* optional copy of out in lo_dtype (operand of the next GEMM) */, int lo_dtype, void* stream);
+/* da (fp32, optionally accumulated); dnum [n/cols rows x cols, leading dimension ld_dnum] and dden [n] in lo_dtype */
 int dfb200_mu_update_bwd(const float* dout, const float* a, const float* num, const float* den, float eps, long n,
-                         float* da, int accumulate_da, float* dnum, float* dden, void* stream);
+                         float* da, int accumulate_da, void* dnum, long ld_dnum, int cols, void* dden, int lo_dtype,
+                         void* stream);
 int dfb200_cast(const void* in, int in_dtype, void* out, int out_dtype, long n, void* stream);
 /* strided 2-D convert/copy: out[r*ld_out + c] = in[r*ld_in + c], r < rows, c < cols (column slices of concatenated operands) */
 int dfb200_cast2d(const void* in, int in_dtype, long ld_in, void* out, int out_dtype, long ld_out, long rows, int cols,

@@ -460,10 +460,20 @@ def test_nmf_elementwise():
     torch.testing.assert_close(k.mu_update(a, num, den), ref, rtol=1e-5, atol=1e-6)
     ref.backward(g.flatten()[:1000])
     da = torch.ones(1000, device=DEV)
-    dnum, dden = k.mu_update_bwd(g.flatten()[:1000].contiguous(), a, num, den, da, True)
-    torch.testing.assert_close(da - 1, ar.grad, rtol=1e-4, atol=1e-5)
-    torch.testing.assert_close(dnum, nr.grad, rtol=1e-4, atol=1e-5)
-    torch.testing.assert_close(dden, dr.grad, rtol=1e-4, atol=1e-4)
+    out32, out_lo = k.mu_update(a, num, den, lo_dtype=torch.bfloat16)          # fp32 state + bf16 operand from one launch
+    torch.testing.assert_close(out32, ref.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out_lo, ref.detach().bfloat16())
+    # dnum goes into a column slice of a wider operand buffer (rows of 50 values, leading dimension 120), dden contiguous
+    a2, n2, d2, g2 = (t.view(20, 50) for t in (a, num, den, g.flatten()[:1000].contiguous()))
+    for dt_ in (torch.float32, torch.bfloat16):
+        da = torch.ones(20, 50, device=DEV)
+        wide = torch.zeros(20, 120, device=DEV, dtype=dt_)
+        dden = k.mu_update_bwd(g2, a2, n2, d2, da, True, wide[:, 40:90], dt_)
+        t_ = dict(rtol=1e-4, atol=1e-4) if dt_ == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+        torch.testing.assert_close(da.flatten() - 1, ar.grad, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(wide[:, 40:90].float().flatten(), nr.grad, **t_)
+        torch.testing.assert_close(dden.float().flatten(), dr.grad, **t_)
+        assert wide[:, :40].abs().max() == 0 and wide[:, 90:].abs().max() == 0
     y = torch.ones(100, device=DEV, dtype=torch.bfloat16)
     k.axpy(rnd(100), 2.0, y)
     assert k.cast(y, torch.float32).dtype == torch.float32
