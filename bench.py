@@ -254,6 +254,50 @@ def main():
         tc_n += cnt
         del g_, a_, b_, o_
     simt_ms = float(n_simt)
+    # ---- the HBM-streaming kernels next in line (fused MLP middle, depthwise 7x7), stage-0 shapes, timed stand-alone the same way
+    def _time_graph(fn, reps=10):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        g_ = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(cap_stream):
+            with torch.cuda.graph(g_, stream=cap_stream):
+                for _ in range(reps):
+                    fn()
+        g_.replay()
+        torch.cuda.synchronize()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        g_.replay()
+        q1.record()
+        torch.cuda.synchronize()
+        return q0.elapsed_time(q1) / reps * 1e-3
+
+    other = []
+    try:
+        Hs, Ws, Ch = H // 4, W // 4, 768
+        hh = torch.randn(B * Hs * Ws, Ch, device=dev).bfloat16()
+        du = torch.randn_like(hh)
+        w3, b3 = torch.randn(Ch, 1, 3, 3, device=dev) * 0.2, torch.randn(Ch, device=dev) * 0.1
+        dw3, db3, dc3 = torch.zeros_like(w3), torch.zeros_like(b3), torch.zeros(Ch, device=dev)
+        _, gp = K.mlp_dw_fwd(hh, w3, b3, B, Hs, Ws, save_gp=True)
+        by = hh.numel() * 2
+        t_f = _time_graph(lambda: K.mlp_dw_fwd(hh, w3, b3, B, Hs, Ws, save_gp=True))
+        t_b = _time_graph(lambda: K.mlp_dw_bwd(du, hh, w3, b3, B, Hs, Ws, dw3, db3, dc3, gp=gp))
+        other.append({"kernel": "mlp_dw_fwd_kernel (dw3x3 + residual + GELU, keeps GELU')", "shape": [B, Hs, Ws, Ch], "bound": "hbm",
+                      "algorithmic_bytes": 3 * by, "us": t_f * 1e6, "achieved": 3 * by / t_f / 1e9, "unit": "GB/s"})
+        other.append({"kernel": "mlp_dw_bwd_saved_kernel (dz, dh, dW, db, fc1 bias grad)", "shape": [B, Hs, Ws, Ch], "bound": "hbm",
+                      "algorithmic_bytes": 4 * by, "us": t_b * 1e6, "achieved": 4 * by / t_b / 1e9, "unit": "GB/s"})
+        C7 = 96
+        x7 = torch.randn(B * Hs * Ws, C7, device=dev).bfloat16()
+        w7, b7 = torch.randn(C7, 1, 7, 7, device=dev) * 0.1, torch.randn(C7, device=dev) * 0.1
+        t_7 = _time_graph(lambda: K.dwconv_fwd(x7, w7, b7, B, Hs, Ws, 7))
+        fl7 = 2.0 * 49 * x7.numel()
+        other.append({"kernel": "dw7_conv_kernel (depthwise 7x7)", "shape": [B, Hs, Ws, C7], "bound": "fp32 FMA", "algorithmic_flops": fl7,
+                      "us": t_7 * 1e6, "achieved": fl7 / t_7 / 1e12, "unit": "TFLOP/s", "peak": 148 * 128 * 2 * 1.965e9 / 1e12})
+        del hh, du, gp, x7
+    except Exception as e:  # noqa: BLE001
+        other.append({"error": f"{type(e).__name__}: {e}"})
 
     if world > 1:
         tms = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -307,6 +351,7 @@ def main():
                      "tensor_view": {"achieved_tflops": achieved, "peak_tflops": tf_burst, "frac": achieved / tf_burst,
                                      "algorithmic_flops_per_step": tc_fl},
                      "cuda_core_gemm_launches_per_step": int(simt_ms)},
+        "other_kernels": [dict(o, peak=o.get("peak", hbm), frac=(o["achieved"] / o.get("peak", hbm))) if "achieved" in o else o for o in other],
         "step_roofline": {"achieved_tflops": value * FLOP_PER_IMG_TRAIN / n / 1e12, "frac_of_burst": value * FLOP_PER_IMG_TRAIN / n / 1e12 / tf_burst,
                           "frac_of_sustained": value * FLOP_PER_IMG_TRAIN / n / 1e12 / tf_sus, "flop_per_image": FLOP_PER_IMG_TRAIN},
     }

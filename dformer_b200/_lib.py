@@ -82,6 +82,9 @@ SIGNATURES = {
     "dfb200_ce_finalize": [P, P, P],
     "dfb200_upsample_ce_bwd_fused": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, P, I, P],
     "dfb200_upsample_ce_bwd": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, I, P],
+    "dfb200_resize_nchw_ac": [P, I, I, I, I, P, I, I, I, P],
+    "dfb200_ms_softmax_accum": [P, I, I, I, I, P, I, I, I, P],
+    "dfb200_argmax_confusion": [P, P, I, I, L, I, P, P, P],
     "dfb200_adamw": [P, P, P, P, L, F, F, F, F, F, F, F, F, P, P, P, P],
 }
 

@@ -518,6 +518,38 @@ def upsample_ce_bwd(small, B, h, w, ncls, H, W, label, ignore, lse, acc, dloss):
     return dsmall
 
 
+def resize_nchw_ac(x, Ho, Wo, flip=False):
+    """F.interpolate(x, (Ho, Wo), mode='bilinear', align_corners=True) [then torch.flip(dims=(3,))] for NCHW fp32."""
+    _chk(x, "x")
+    B, C, Hi, Wi = x.shape
+    x = x.contiguous().float()
+    out = torch.empty((B, C, Ho, Wo), device=x.device, dtype=torch.float32)
+    lib().resize_nchw_ac(x.data_ptr(), B, C, Hi, Wi, out.data_ptr(), Ho, Wo, int(flip), _s())
+    return out
+
+
+def ms_softmax_accum(logits, acc, flip=False):
+    """acc += softmax(F.interpolate(flip_W(logits) if flip else logits, acc.shape[2:], bilinear, align_corners=True), dim=1)"""
+    B, C, h, w = logits.shape
+    assert acc.shape[:2] == (B, C) and acc.dtype == torch.float32 and acc.is_contiguous()
+    logits = logits.contiguous().float()
+    lib().ms_softmax_accum(logits.data_ptr(), B, C, h, w, acc.data_ptr(), acc.shape[2], acc.shape[3], int(flip), _s())
+    return acc
+
+
+def argmax_confusion(score, target, ignore, hist=None, want_pred=False):
+    """pred = score.argmax(1); hist[target * C + pred] += 1 over target != ignore.  Returns pred (or None)."""
+    B, C = score.shape[:2]
+    HW = score[0, 0].numel()
+    assert score.dtype == torch.float32 and score.is_contiguous()
+    pred = torch.empty((B,) + tuple(score.shape[2:]), device=score.device, dtype=torch.int64) if want_pred else None
+    if target is not None:
+        target = target.contiguous()
+        assert target.dtype == torch.int64 and target.numel() == B * HW
+    lib().argmax_confusion(score.data_ptr(), _p(target), B, C, HW, ignore, _p(hist), _p(pred), _s())
+    return pred
+
+
 def adamw(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0, wd_arr=None, lr_arr=None, dyn=None):
     c1 = 1.0 - beta1 ** step
     c2 = 1.0 - beta2 ** step

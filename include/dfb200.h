@@ -247,6 +247,17 @@ int dfb200_upsample_ce_bwd(const void* logits_small, int dtype, int B, int h, in
                            const int64_t* label, int ignore, const float* lse, const float* loss_acc, const float* dloss,
                            void* dlogits_small, int dl_dtype, void* stream);
 
+/* ---- multi-scale + flip evaluation and the mIoU confusion matrix (utils/val_mm.py:257-470, utils/metrics_new.py:6-47) ----
+ * resize_nchw_ac:   out[B,C,Ho,Wo] = bilinear(in[B,C,Hi,Wi], align_corners=True), optionally mirrored along W afterwards
+ *                   (val_mm.py:366-368,378-380: F.interpolate(..., align_corners=True) then torch.flip(dims=(3,))).
+ * ms_softmax_accum: acc[B,C,H,W] += softmax_C( bilinear_ac( flip ? mirror_W(logits) : logits ) )   (val_mm.py:385-399).
+ * argmax_confusion: pred = argmax_C score; hist[target * C + pred] += 1 where target != ignore (metrics_new.py:18-22);
+ *                   hist [C*C] fp32 accumulated, pred [B*HW] optional, target may be NULL (prediction only). */
+int dfb200_resize_nchw_ac(const float* in, int B, int C, int Hi, int Wi, float* out, int Ho, int Wo, int flip, void* stream);
+int dfb200_ms_softmax_accum(const float* logits, int B, int C, int h, int w, float* acc, int H, int W, int flip, void* stream);
+int dfb200_argmax_confusion(const float* score, const int64_t* target, int B, int C, long HW, int ignore, float* hist,
+                            int64_t* pred, void* stream);
+
 /* ---- fused multi-tensor AdamW on flat fp32 buffers (utils/train.py:211,336; next-row N1) ------------ */
 /* per-element `wd_arr` (weight decay, NULL = weight_decay everywhere) and `lr_arr` (lr multiplier, 0 freezes an
  * element; NULL = 1) reproduce the reference's parameter groups (utils/init_func.py:26-70) on one flat buffer. */

@@ -548,3 +548,62 @@ def test_adamw_matches_torch():
         k.adamw(p2, g, m2, v2, 123.0, 0.9, 0.999, 1e-8, 0.01, 77, dyn=dyn)
         k.adamw(p3, g, m3, v3, 2e-3, 0.9, 0.999, 1e-8, 0.01, step)
     torch.testing.assert_close(p2, p3, rtol=1e-5, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------- multi-scale evaluation + metrics (row N3)
+@pytest.mark.parametrize("Hi,Wi,Ho,Wo", [(48, 64, 96, 128), (48, 64, 64, 96), (60, 80, 32, 32), (5, 7, 5, 7), (9, 1, 4, 3)])
+@pytest.mark.parametrize("flip", [False, True])
+def test_resize_nchw_align_corners(Hi, Wi, Ho, Wo, flip):
+    k = K()
+    x = rnd(2, 3, Hi, Wi)
+    ref = F.interpolate(x, size=(Ho, Wo), mode="bilinear", align_corners=True)
+    if flip:
+        ref = torch.flip(ref, dims=(3,))
+    torch.testing.assert_close(k.resize_nchw_ac(x, Ho, Wo, flip=flip), ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("ncls,h,w,H,W", [(40, 24, 32, 48, 64), (37, 32, 32, 30, 45), (5, 7, 9, 7, 9)])
+def test_ms_softmax_accum_and_confusion(ncls, h, w, H, W):
+    k = K()
+    B = 2
+    acc = torch.zeros(B, ncls, H, W, device=DEV)
+    ref = torch.zeros_like(acc)
+    for flip in (False, True, False):
+        logits = rnd(B, ncls, h, w) * 3
+        k.ms_softmax_accum(logits, acc, flip=flip)
+        lr = torch.flip(logits, dims=(3,)) if flip else logits
+        ref += F.interpolate(lr, size=(H, W), mode="bilinear", align_corners=True).softmax(dim=1)
+    torch.testing.assert_close(acc, ref, rtol=1e-4, atol=1e-5)
+    target = torch.randint(0, ncls, (B, H, W), device=DEV)
+    target[torch.rand(B, H, W, device=DEV) < 0.15] = 255
+    hist = torch.zeros(ncls, ncls, device=DEV)
+    pred = k.argmax_confusion(acc, target, 255, hist=hist, want_pred=True)
+    pr = ref.argmax(dim=1)
+    assert (pred == pr).float().mean() > 0.999
+    keep = target != 255
+    href = torch.bincount(target[keep] * ncls + pred[keep], minlength=ncls ** 2).view(ncls, ncls).float()
+    torch.testing.assert_close(hist, href)
+    k.argmax_confusion(acc, target, 255, hist=hist)              # accumulates
+    torch.testing.assert_close(hist, 2 * href)
+
+
+def test_metrics_match_reference_formulas():
+    from dformer_b200.evaluation import Metrics, scaled_size
+    ncls = 7
+    pred = rnd(3, ncls, 20, 30)
+    target = torch.randint(0, ncls, (3, 20, 30), device=DEV)
+    target[:, :3] = 255
+    m = Metrics(ncls, 255, DEV)
+    m.update(pred, target)
+    m.update(pred, target)
+    keep = target != 255
+    hist = 2 * torch.bincount(target[keep] * ncls + pred.argmax(1)[keep], minlength=ncls ** 2).view(ncls, ncls).float()
+    ious = hist.diag() / (hist.sum(0) + hist.sum(1) - hist.diag())
+    ious[ious.isnan()] = 0.0
+    got, miou = m.compute_iou()
+    assert got == (ious * 100).cpu().numpy().round(2).tolist() and miou == round(ious.mean().item() * 100, 2)
+    f1 = 2 * hist.diag() / (hist.sum(0) + hist.sum(1))
+    assert m.compute_f1()[1] == round(f1.mean().item() * 100, 2)
+    acc = hist.diag() / hist.sum(1)
+    assert m.compute_pixel_acc()[1] == round(acc.mean().item() * 100, 2)
+    assert scaled_size(480, 640, 0.75) == (384, 480) and scaled_size(480, 640, 1.25) == (608, 800)

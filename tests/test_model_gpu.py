@@ -172,3 +172,38 @@ def test_cpu_tensors_are_rejected_loudly():
     m, _ = build("DFormer-Tiny", 40, "fp32", 1, False)
     with pytest.raises(RuntimeError, match="no CPU"):
         m(torch.randn(1, 3, 64, 64), torch.randn(1, 3, 64, 64))
+
+
+def test_multi_scale_flip_evaluation_matches_the_reference_loop():
+    """dformer_b200.evaluation (fused resize / flip / softmax-accumulate / argmax-confusion kernels) against the reference's
+    evaluate_msf loop (utils/val_mm.py:357-399) written with torch ops around the SAME model, and its Metrics."""
+    import torch.nn.functional as F
+
+    from dformer_b200.evaluation import Metrics, evaluate, multi_scale_predict, scaled_size
+    ncls = 40
+    m, _ = build("DFormer-Tiny", ncls, "fp32", 5, train=False)
+    B, H, W = 2, 64, 96
+    rgb, hha, label, _ = make_inputs(B, H, W, ncls, seed=5)
+    rgb, hha, label = rgb.cuda(), hha.cuda(), label.cuda()
+    bases = torch.rand(B, 512, 64, generator=torch.Generator().manual_seed(1)).cuda()
+    m.decode_head.injected_bases = bases
+    scales = (0.75, 1.0, 1.5)
+    acc = multi_scale_predict(m, rgb, hha, scales, flip=True)
+    ref = torch.zeros(B, ncls, H, W, device=DEV)
+    with torch.no_grad():
+        for s in scales:
+            nh, nw = scaled_size(H, W, s)
+            imgs = [F.interpolate(t, size=(nh, nw), mode="bilinear", align_corners=True) for t in (rgb, hha)]
+            ref += F.interpolate(m(imgs[0], imgs[1]), size=(H, W), mode="bilinear", align_corners=True).softmax(dim=1)
+            imgs = [torch.flip(t, dims=(3,)) for t in imgs]
+            lg = torch.flip(m(imgs[0], imgs[1]), dims=(3,))
+            ref += F.interpolate(lg, size=(H, W), mode="bilinear", align_corners=True).softmax(dim=1)
+    torch.testing.assert_close(acc, ref, rtol=1e-3, atol=1e-4)
+    met = evaluate(m, [{"rgb": rgb, "modal_x": hha, "gt": label}], ncls, 255, scales, flip=True)
+    keep = label != 255
+    hist = torch.bincount(label[keep] * ncls + ref.argmax(1)[keep], minlength=ncls ** 2).view(ncls, ncls).float()
+    assert (met.hist - hist).abs().sum() <= 2          # at most one pixel whose top-2 scores tie within round-off
+    refm = Metrics(ncls, 255, DEV)
+    refm.update_hist(hist)
+    assert abs(met.compute_iou()[1] - refm.compute_iou()[1]) < 0.05
+    assert not m.training
