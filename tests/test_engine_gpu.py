@@ -39,3 +39,31 @@ def test_graphed_step_matches_eager_step():
     assert losses["graph"][-1] < losses["graph"][0] + 0.5 and losses["eager"][-1] < losses["eager"][0] + 0.5
     assert (finals["graph"] - finals["eager"]).abs().max() < 0.05          # same weights up to one extra AdamW step at lr 1e-3
     assert run.graph is not None
+
+
+def test_staged_input_prefetch_feeds_the_same_step():
+    """stage() + step() (H2D on the copy stream into staging buffers, consumed by the next step) trains on exactly the batch
+    that step(batch) would: with lr = 0 the weights stay put, so equal losses mean equal inputs reached the graph."""
+    from dformer_b200.engine import GraphedTrainStep
+    from dformer_b200.optim import FusedAdamW
+    g = torch.Generator().manual_seed(3)
+    batches = [(torch.randn(2, 3, 96, 128, generator=g).pin_memory(), torch.randn(2, 3, 96, 128, generator=g).pin_memory(),
+                torch.randint(0, 40, (2, 96, 128), generator=g).pin_memory()) for _ in range(3)]
+    m = _build(0)
+    opt = FusedAdamW(m, lr=0.0, weight_decay=0.0, reference_groups=False)
+    b0 = tuple(t.cuda() for t in batches[0])
+    run = GraphedTrainStep(m, opt, *b0, warmup=1, use_graph=True)
+    direct, staged = [], []
+    for b in batches:
+        torch.manual_seed(7)                                 # same NMF bases draw for both variants
+        direct.append(run.step(*b).item())
+    torch.manual_seed(7)                                     # the staged variant draws the bases inside stage()
+    run.stage(*batches[0])
+    for i in range(len(batches)):
+        loss = run.step()
+        if i + 1 < len(batches):
+            torch.manual_seed(7)
+            run.stage(*batches[i + 1])                       # overlaps the step just launched
+        staged.append(loss.item())
+    assert staged == pytest.approx(direct, rel=1e-5, abs=1e-6)      # (the loss sum uses fp32 atomics: last-bit differences)
+    assert len({round(v, 4) for v in direct}) == len(direct)     # the three batches really differ
