@@ -64,9 +64,14 @@ def main():
             K.mlp_dw_bwd(du, h, w, b, B, H, W, dw, db, dc, gp=gp)
 
         if only is not None:
+            x7 = torch.randn(M, 96, device="cuda").bfloat16()
+            w7, b7 = torch.randn(96, 1, 7, 7, device="cuda") * 0.1, torch.randn(96, device="cuda") * 0.1
+            dw7, db7 = torch.zeros_like(w7), torch.zeros_like(b7)
             for _ in range(2):
-                fwd_new()
-                bwd_new()
+                fwd_gp()
+                bwd_gp()
+                K.dwconv_fwd(x7, w7, b7, B, H, W, 7)
+                K.dwconv_bwd(x7, x7, w7, b7, B, H, W, 7, False, 0, dw7, db7)
             torch.cuda.synchronize()
             return
 

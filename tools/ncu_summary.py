@@ -30,6 +30,11 @@ def short(k):
 
 def main():
     data = load(sys.argv[1])
+    if "--step" in sys.argv:                 # drop model construction / optimizer set-up: keep launches from the first pack_params on
+        sys.argv.remove("--step")
+        keys = list(data)
+        first = next(i for i, k in enumerate(keys) if "pack_params" in data[k]["k"])
+        data = collections.OrderedDict((k, data[k]) for k in keys[first:])
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
     agg = collections.defaultdict(lambda: [0.0, 0, 0.0, 0.0])
     for d in data.values():
