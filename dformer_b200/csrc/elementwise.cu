@@ -203,25 +203,29 @@ __global__ void scale_residual_fwd_kernel(const float* __restrict__ res, const T
     Vec8<float>::store(out + i * 8, rv);
   }
 }
-template <typename T>
+template <typename T, int NOUT>
 __global__ void __launch_bounds__(EW_THREADS) scale_residual_bwd_kernel(const float* __restrict__ dout, const T* __restrict__ y, long ldy, const float* __restrict__ ls,
                                                                         const float* __restrict__ scale_b, int M, int C, int rows_per_sample,
-                                                                        T* __restrict__ dy, long lddy, float* dls, int rows_per_block) {
+                                                                        T* __restrict__ dy, long lddy, float* dls, float* dy_colsum, int rows_per_block) {
   pdl_sync();
   extern __shared__ float smem[];
-  float* outs[1] = {dls};
-  colreduce_body<T, 1>(M, C, rows_per_block,
-                       [&](int r, int c, float(*acc)[8]) {
-                         const float sb = scale_b ? scale_b[r / rows_per_sample] : 1.f;
-                         float g[8], yv[8], lv[8], o[8];
-                         Vec8<float>::load(dout + (long)r * C + c, g);
-                         Vec8<T>::load(y + (long)r * ldy + c, yv);
-                         Vec8<float>::load(ls + c, lv);
+  float* outs[2] = {dls, dy_colsum};      // NOUT == 2: also the column sum of dy (= bias gradient of the Linear that produced y)
+  colreduce_body<T, NOUT>(M, C, rows_per_block,
+                          [&](int r, int c, float(*acc)[8]) {
+                            const float sb = scale_b ? scale_b[r / rows_per_sample] : 1.f;
+                            float g[8], yv[8], lv[8], o[8];
+                            Vec8<float>::load(dout + (long)r * C + c, g);
+                            Vec8<T>::load(y + (long)r * ldy + c, yv);
+                            Vec8<float>::load(ls + c, lv);
 #pragma unroll
-                         for (int j = 0; j < 8; ++j) { o[j] = g[j] * lv[j] * sb; acc[0][j] += g[j] * yv[j] * sb; }
-                         Vec8<T>::store(dy + (long)r * lddy + c, o);
-                       },
-                       outs, smem);
+                            for (int j = 0; j < 8; ++j) {
+                              o[j] = g[j] * lv[j] * sb;
+                              acc[0][j] += g[j] * yv[j] * sb;
+                              if (NOUT == 2) acc[1][j] += to_f(from_f<T>(o[j]));      // sums the values the weight-gradient GEMM will read
+                            }
+                            Vec8<T>::store(dy + (long)r * lddy + c, o);
+                          },
+                          outs, smem);
 }
 
 // ------------------------------------------------------------------ NMF helpers
@@ -422,12 +426,17 @@ extern "C" int dfb200_scale_residual_fwd(const float* res, const void* y, long l
   return dfb_check_launch("scale_residual_fwd");
 }
 extern "C" int dfb200_scale_residual_bwd(const float* dout, const void* y, long ldy, int dtype, const float* ls, const float* scale_b, int M, int C,
-                                         int rows_per_sample, void* dy, long lddy, float* dls, void* stream) {
+                                         int rows_per_sample, void* dy, long lddy, float* dls, float* dy_colsum, void* stream) {
   DFB_REQUIRE(C % 8 == 0 && ldy % 8 == 0 && lddy % 8 == 0, "scale_residual: C, ldy, lddy %% 8 != 0");
   const int rpb = pick_rows_per_block(M);
   dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(C / 8, EW_THREADS));
   DFB_DISPATCH_DTYPE(dtype, T, {
-    dfb_launch(scale_residual_bwd_kernel<T>, grid, EW_THREADS, EW_THREADS * 8 * sizeof(float), ST, dout, (const T*)y, ldy, ls, scale_b, M, C, rows_per_sample, (T*)dy, lddy, dls, rpb);
+    if (dy_colsum)
+      dfb_launch(scale_residual_bwd_kernel<T, 2>, grid, EW_THREADS, 2 * EW_THREADS * 8 * sizeof(float), ST, dout, (const T*)y, ldy, ls, scale_b, M, C,
+                 rows_per_sample, (T*)dy, lddy, dls, dy_colsum, rpb);
+    else
+      dfb_launch(scale_residual_bwd_kernel<T, 1>, grid, EW_THREADS, EW_THREADS * 8 * sizeof(float), ST, dout, (const T*)y, ldy, ls, scale_b, M, C,
+                 rows_per_sample, (T*)dy, lddy, dls, dy_colsum, rpb);
   });
   return dfb_check_launch("scale_residual_bwd");
 }

@@ -236,10 +236,11 @@ def _mlp_bwd(dout, pfx, st, P, sv, scale_b, G):
     T = st.dtype
     B, H, W = st.B, st.H, st.W
     lsn = "layer_scale_2" if pfx == "mlp." else "layer_scale_2_e"
-    df = K.scale_residual_bwd(dout, sv[pfx + "f"], P[lsn], scale_b, H * W, G[lsn])
+    fused = T == torch.bfloat16 and _FUSE_DW
+    df = K.scale_residual_bwd(dout, sv[pfx + "f"], P[lsn], scale_b, H * W, G[lsn], dy_colsum=G[pfx + "fc2.bias"] if fused else None)
     w2 = st.packed[st.key + pfx + "fc2"][0]
-    if T == torch.bfloat16 and _FUSE_DW:      # GELU' . dw3x3^T . weight/bias gradients . fc1 bias gradient: one kernel, dz stays on chip
-        du = _lin_bwd(df, sv[pfx + "u"], w2, G[pfx + "fc2.weight"], G[pfx + "fc2.bias"], T)
+    if fused:                                 # GELU' . dw3x3^T . weight/bias gradients . fc1 bias gradient: one kernel, dz stays on chip
+        du = _lin_bwd(df, sv[pfx + "u"], w2, G[pfx + "fc2.weight"], None, T)                # fc2 bias gradient came with df above
         dh = K.mlp_dw_bwd(du, sv[pfx + "h"], P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, G[pfx + "pos.weight"], G[pfx + "pos.bias"],
                           G[pfx + "fc1.bias"], gp=sv[pfx + "z"])
         dhn = _lin_bwd(dh, sv[pfx + "hn"], st.packed[st.key + pfx + "fc1"][0], G[pfx + "fc1.weight"], None, T)
@@ -366,20 +367,21 @@ class BlockFn(torch.autograd.Function):
             K.fork(side)
             with torch.cuda.stream(side):
                 dxe1 = _mlp_bwd(dxe2, "mlp_e2.", st, P, sv, st.dp[3], G)
-                K.scale_residual_bwd(dxe1, sv["pp"][:, C:], P["layer_scale_1_e"], st.dp[2], HW, G["layer_scale_1_e"], dy=dpp[:, C:])
+                K.scale_residual_bwd(dxe1, sv["pp"][:, C:], P["layer_scale_1_e"], st.dp[2], HW, G["layer_scale_1_e"], dy=dpp[:, C:],
+                                     dy_colsum=G["attn.proj_e.bias"])                       # proj_e bias gradient in the same pass
                 ev_e = K.signal(side)
             K.share(main, dxe1)
         dx1 = _mlp_bwd(dx2, "mlp.", st, P, sv, st.dp[1], G)
-        K.scale_residual_bwd(dx1, sv["pp"][:, :C], P["layer_scale_1"], st.dp[0], HW, G["layer_scale_1"], dy=dpp[:, :C])
+        K.scale_residual_bwd(dx1, sv["pp"][:, :C], P["layer_scale_1"], st.dp[0], HW, G["layer_scale_1"], dy=dpp[:, :C],
+                             dy_colsum=G["attn.proj.bias"])                                 # proj bias gradient in the same pass
         if not dd:
             main.wait_event(ev_e)
         # ---- proj | proj_e
         if dd:
-            dWpp, dbpp = G["attn.proj.weight"], G["attn.proj.bias"]
+            dWpp = G["attn.proj.weight"]
         else:
             dWpp = ar.span(st.prefix + "attn.proj.weight", st.prefix + "attn.proj_e.weight", ppw.shape)
-            dbpp = ar.span(st.prefix + "attn.proj.bias", st.prefix + "attn.proj_e.bias", (ppw.shape[0],))
-        dy = _lin_bwd(dpp, sv["y"], ppw, dWpp, dbpp, T)
+        dy = _lin_bwd(dpp, sv["y"], ppw, dWpp, None, T)
         ycols = dy.shape[1]
         qcl = sv["qcl"]
         dqcl = torch.empty_like(qcl)

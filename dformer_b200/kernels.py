@@ -258,12 +258,14 @@ def scale_residual_fwd(res, y, ls, scale_b, rows_per_sample):
     return out
 
 
-def scale_residual_bwd(dout, y, ls, scale_b, rows_per_sample, dls, dy=None):
+def scale_residual_bwd(dout, y, ls, scale_b, rows_per_sample, dls, dy=None, dy_colsum=None):
+    """dy = dout * ls * scale_b; dls += colsum(dout * y * scale_b); optionally dy_colsum += colsum(dy) (the bias gradient of the
+    Linear that produced y), from the same pass."""
     M, C = dout.shape
     if dy is None:
         dy = torch.empty((M, C), device=y.device, dtype=y.dtype)
     lib().scale_residual_bwd(dout.data_ptr(), y.data_ptr(), y.stride(0), dt(y), ls.data_ptr(), _p(scale_b), M, C, rows_per_sample,
-                             dy.data_ptr(), dy.stride(0), dls.data_ptr(), _s())
+                             dy.data_ptr(), dy.stride(0), dls.data_ptr(), _p(dy_colsum), _s())
     return dy
 
 

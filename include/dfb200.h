@@ -134,7 +134,9 @@ int dfb200_scale_residual_fwd(const float* res, const void* y, long ldy, int dty
                               int M, int C, int rows_per_sample, float* out, void* stream);
 /* dy = dout * ls * scale_b;  dls[c] += sum_m dout*y*scale_b (atomics; zero-init by caller). d(res) = dout (alias). */
 int dfb200_scale_residual_bwd(const float* dout, const void* y, long ldy, int dtype, const float* ls, const float* scale_b,
-                              int M, int C, int rows_per_sample, void* dy, long lddy, float* dls, void* stream);
+                              int M, int C, int rows_per_sample, void* dy, long lddy, float* dls,
+                              float* dy_colsum /* optional: += column sums of dy (bias gradient of the layer that produced y) */,
+                              void* stream);
 /* stand-alone activation on a column slice: out = act(in);  din = dout * act'(z) (GELU: z = pre-activation;
  * ReLU: z may be the forward output).  All operands have independent leading dimensions. */
 int dfb200_act_fwd(const void* in, long ldi, void* out, long ldo, int dtype, int act, int M, int N, void* stream);

@@ -263,6 +263,12 @@ def test_mul_and_scale_residual(dtype):
     dy = k.scale_residual_bwd(g, y, ls, sb, hw, dls, dy=dybuf[:, C:2 * C])
     torch.testing.assert_close(dy.float(), g * ls * sb.repeat_interleave(hw)[:, None], **tol(dtype))
     torch.testing.assert_close(dls, (g * y.float() * sb.repeat_interleave(hw)[:, None]).sum(0), rtol=1e-3, atol=1e-2)
+    # same pass also emits the bias gradient of the layer that produced y (column sums of dy), accumulated
+    dls2, dbias = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    dy2 = k.scale_residual_bwd(g, y, ls, sb, hw, dls2, dy_colsum=dbias)
+    torch.testing.assert_close(dy2, dy)
+    torch.testing.assert_close(dls2, dls)
+    torch.testing.assert_close(dbias - 1, dy2.float().sum(0), rtol=1e-3, atol=1e-2)
     # stand-alone activation on column slices
     z = rnd(M, 3 * C, dtype=dtype)
     o = k.act_fwd(z[:, C:2 * C], k.ACT_GELU)
