@@ -48,11 +48,11 @@ SIGNATURES = {
     "dfb200_mlp_dw_fwd": [P, I, P, P, I, I, I, I, P, P, P],
     "dfb200_mlp_dw_bwd": [P, P, P, I, P, P, I, I, I, I, P, P, P, P, P],
     "dfb200_mul_fwd": [P, L, P, L, P, L, I, I, I, P],
-    "dfb200_mul_bwd": [P, L, P, L, P, L, P, L, P, L, I, I, I, P],
+    "dfb200_mul_bwd": [P, L, P, L, P, L, P, L, P, L, I, I, I, P, P, P],
     "dfb200_scale_residual_fwd": [P, P, L, I, P, P, I, I, I, P, P],
     "dfb200_scale_residual_bwd": [P, P, L, I, P, P, I, I, I, P, L, P, P, P],
     "dfb200_act_fwd": [P, L, P, L, I, I, I, I, P],
-    "dfb200_act_bwd": [P, L, P, L, P, L, P, L, I, I, I, I, P],
+    "dfb200_act_bwd": [P, L, P, L, P, L, P, L, I, I, I, I, P, P],
     "dfb200_pool7_fwd": [P, I, P, I, I, I, I, I, P, P],
     "dfb200_pool7_bwd": [P, I, I, I, I, I, I, P, P, P],
     "dfb200_gaa_fwd": [P, P, I, I, I, I, I, P, P, P],

@@ -597,7 +597,7 @@ extern "C" int dfb200_dwconv_bwd(const void* dy, const void* x, const void* z, i
     int rc = DFB_OK;
     if (act != 0) {
       if (z != nullptr) {      // saved pre-activation: dz = dy * act'(z) is a single element-wise pass
-        rc = dfb200_act_bwd(dy, C, nullptr, 0, z, C, dz_buf, C, dtype, act, (int)((long)B * H * W), C, stream);
+        rc = dfb200_act_bwd(dy, C, nullptr, 0, z, C, dz_buf, C, dtype, act, (int)((long)B * H * W), C, nullptr, stream);
       } else {
         rc = (k == 3) ? launch_conv<T, 3, 1>((const T*)x, (const T*)dy, weight, bias, B, H, W, C, add_input, act, (T*)dz_buf, nullptr, ST)
                       : launch_conv<T, 7, 1>((const T*)x, (const T*)dy, weight, bias, B, H, W, C, add_input, act, (T*)dz_buf, nullptr, ST);

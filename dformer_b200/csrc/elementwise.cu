@@ -185,6 +185,61 @@ __global__ void act_bwd_kernel(const T* __restrict__ dout, long lddo, const T* _
   }
 }
 
+// Column-summing forms of the two kernels above: the element-wise gradient and the bias gradient (column sums of that gradient
+// as the weight-gradient GEMM will read it, i.e. after rounding to T) of the Linear layers behind them leave in one pass.
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) mul_bwd_colsum_kernel(const T* __restrict__ dout, long ldo, const T* __restrict__ a, long lda,
+                                                                    const T* __restrict__ b, long ldb, T* __restrict__ da, long ldda, T* __restrict__ db,
+                                                                    long lddb, int M, int N, float* da_colsum, float* db_colsum, int rows_per_block) {
+  pdl_sync();
+  extern __shared__ float smem[];
+  float* outs[2] = {da_colsum, db_colsum};
+  colreduce_body<T, 2>(M, N, rows_per_block,
+                       [&](int r, int c, float(*acc)[8]) {
+                         float g[8], x[8], y[8], ga[8], gb[8];
+                         Vec8<T>::load(dout + (long)r * ldo + c, g);
+                         Vec8<T>::load(a + (long)r * lda + c, x);
+                         Vec8<T>::load(b + (long)r * ldb + c, y);
+#pragma unroll
+                         for (int j = 0; j < 8; ++j) {
+                           ga[j] = g[j] * y[j];
+                           gb[j] = g[j] * x[j];
+                           acc[0][j] += to_f(from_f<T>(ga[j]));
+                           acc[1][j] += to_f(from_f<T>(gb[j]));
+                         }
+                         Vec8<T>::store(da + (long)r * ldda + c, ga);
+                         Vec8<T>::store(db + (long)r * lddb + c, gb);
+                       },
+                       outs, smem);
+}
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) act_bwd_colsum_kernel(const T* __restrict__ dout, long lddo, const T* __restrict__ dout2, long lddo2,
+                                                                    const T* __restrict__ z, long ldz, T* __restrict__ din, long lddi, int act, int M, int N,
+                                                                    float* colsum, int rows_per_block) {
+  pdl_sync();
+  extern __shared__ float smem[];
+  float* outs[1] = {colsum};
+  colreduce_body<T, 1>(M, N, rows_per_block,
+                       [&](int r, int c, float(*acc)[8]) {
+                         float g[8], zz[8];
+                         Vec8<T>::load(dout + (long)r * lddo + c, g);
+                         if (dout2) {
+                           float g2[8];
+                           Vec8<T>::load(dout2 + (long)r * lddo2 + c, g2);
+#pragma unroll
+                           for (int j = 0; j < 8; ++j) g[j] = to_f(from_f<T>(g[j] + g2[j]));
+                         }
+                         Vec8<T>::load(z + (long)r * ldz + c, zz);
+#pragma unroll
+                         for (int j = 0; j < 8; ++j) {
+                           g[j] *= act == 1 ? gelu_grad_f(zz[j]) : (zz[j] > 0.f ? 1.f : 0.f);
+                           acc[0][j] += to_f(from_f<T>(g[j]));
+                         }
+                         Vec8<T>::store(din + (long)r * lddi + c, g);
+                       },
+                       outs, smem);
+}
+
 // ------------------------------------------------------------------ layer-scale residual
 template <typename T>
 __global__ void scale_residual_fwd_kernel(const float* __restrict__ res, const T* __restrict__ y, long ldy, const float* __restrict__ ls,
@@ -395,8 +450,18 @@ extern "C" int dfb200_mul_fwd(const void* a, long lda, const void* b, long ldb, 
   return dfb_check_launch("mul_fwd");
 }
 extern "C" int dfb200_mul_bwd(const void* dout, long ldo, const void* a, long lda, const void* b, long ldb, void* da, long ldda, void* db, long lddb,
-                              int dtype, int M, int N, void* stream) {
+                              int dtype, int M, int N, float* da_colsum, float* db_colsum, void* stream) {
   DFB_REQUIRE(N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 8 == 0 && ldda % 8 == 0 && lddb % 8 == 0, "mul_bwd: alignment");
+  DFB_REQUIRE((da_colsum == nullptr) == (db_colsum == nullptr), "mul_bwd: give both column-sum outputs or neither");
+  if (da_colsum) {
+    const int rpb = pick_rows_per_block(M);
+    dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(N / 8, EW_THREADS));
+    DFB_DISPATCH_DTYPE(dtype, T, {
+      dfb_launch(mul_bwd_colsum_kernel<T>, grid, EW_THREADS, 2 * EW_THREADS * 8 * sizeof(float), ST, (const T*)dout, ldo, (const T*)a, lda, (const T*)b, ldb,
+                 (T*)da, ldda, (T*)db, lddb, M, N, da_colsum, db_colsum, rpb);
+    });
+    return dfb_check_launch("mul_bwd_colsum");
+  }
   DFB_DISPATCH_DTYPE(dtype, T, {
     dfb_launch(mul_bwd_kernel<T>, ew_grid((long)M * N / 8), EW_THREADS, 0, ST, (const T*)dout, ldo, (const T*)a, lda, (const T*)b, ldb, (T*)da, ldda, (T*)db, lddb, M, N / 8);
   });
@@ -409,8 +474,17 @@ extern "C" int dfb200_act_fwd(const void* in, long ldi, void* out, long ldo, int
   return dfb_check_launch("act_fwd");
 }
 extern "C" int dfb200_act_bwd(const void* dout, long lddo, const void* dout2, long lddo2, const void* z, long ldz, void* din, long lddi, int dtype, int act,
-                              int M, int N, void* stream) {
+                              int M, int N, float* colsum, void* stream) {
   DFB_REQUIRE(N % 8 == 0 && lddo % 8 == 0 && ldz % 8 == 0 && lddi % 8 == 0 && (!dout2 || lddo2 % 8 == 0) && (act == 1 || act == 2), "act_bwd: bad arguments");
+  if (colsum) {
+    const int rpb = pick_rows_per_block(M);
+    dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(N / 8, EW_THREADS));
+    DFB_DISPATCH_DTYPE(dtype, T, {
+      dfb_launch(act_bwd_colsum_kernel<T>, grid, EW_THREADS, EW_THREADS * 8 * sizeof(float), ST, (const T*)dout, lddo, (const T*)dout2, lddo2, (const T*)z, ldz,
+                 (T*)din, lddi, act, M, N, colsum, rpb);
+    });
+    return dfb_check_launch("act_bwd_colsum");
+  }
   DFB_DISPATCH_DTYPE(dtype, T, {
     dfb_launch(act_bwd_kernel<T>, ew_grid((long)M * N / 8), EW_THREADS, 0, ST, (const T*)dout, lddo, (const T*)dout2, lddo2, (const T*)z, ldz, (T*)din, lddi, act, M, N / 8);
   });

@@ -387,11 +387,12 @@ class BlockFn(torch.autograd.Function):
         dqcl = torch.empty_like(qcl)
         da = torch.empty((M, C), device=dev, dtype=T)
         de = torch.empty((M, Ce), device=dev, dtype=T)
-        K.mul_bwd(dy[:, ycols - Ce:], qcl[:, C:C + Ce], sv["e"], dqcl[:, C:C + Ce], de)
+        # the element-wise gradient kernels below also emit the bias gradients of q | q_cut | l, a and e_back (column sums of what they write)
+        K.mul_bwd(dy[:, ycols - Ce:], qcl[:, C:C + Ce], sv["e"], dqcl[:, C:C + Ce], de, G["attn.q_cut.bias"], G["attn.e_back.bias"])
         # ---- depth gate path e = e_back(dw7(e_fore(en))) on the side stream
         K.fork(side)
         with torch.cuda.stream(side):
-            dec = _lin_bwd(de, sv["ec"], pk("attn.e_back")[0], G["attn.e_back.weight"], G["attn.e_back.bias"], T)
+            dec = _lin_bwd(de, sv["ec"], pk("attn.e_back")[0], G["attn.e_back.weight"], None, T)
             def_ = K.dwconv_bwd(dec, sv["ef"], P["attn.e_conv.weight"], P["attn.e_conv.bias"], B, H, W, 7, False, K.ACT_NONE,
                                 G["attn.e_conv.weight"], G["attn.e_conv.bias"], wgrad_stream=_WGRAD_STREAM)
             den = _lin_bwd(def_, sv["en"], pk("attn.e_fore")[0], G["attn.e_fore.weight"], G["attn.e_fore.bias"], T)
@@ -415,17 +416,16 @@ class BlockFn(torch.autograd.Function):
                 dxn_pool, den_pool = K.pool7_bwd(dpooled, C, Ce, B, H, W)
             K.share(main, dxn_pool, den_pool, dl_kv)
         # ---- RGB path: a = a(dw7(l))
-        K.mul_bwd(dy[:, :C], qcl[:, :C], sv["a"], dqcl[:, :C], da)
-        dcv = _lin_bwd(da, sv["cv"], pk("attn.a")[0], G["attn.a.weight"], G["attn.a.bias"], T)
+        K.mul_bwd(dy[:, :C], qcl[:, :C], sv["a"], dqcl[:, :C], da, G["attn.q.bias"], G["attn.a.bias"])
+        dcv = _lin_bwd(da, sv["cv"], pk("attn.a")[0], G["attn.a.weight"], None, T)
         dl = K.dwconv_bwd(dcv, sv["l"], P["attn.conv.weight"], P["attn.conv.bias"], B, H, W, 7, False, K.ACT_NONE,
                           G["attn.conv.weight"], G["attn.conv.bias"], wgrad_stream=_WGRAD_STREAM)
         if win:
             main.wait_event(ev_dlkv)
-        K.act_bwd(dl, qcl[:, C + Ce:], K.ACT_GELU, out=dqcl[:, C + Ce:], dout2=dl_kv)      # kv branch's gradient of l joins here
+        K.act_bwd(dl, qcl[:, C + Ce:], K.ACT_GELU, out=dqcl[:, C + Ce:], dout2=dl_kv, colsum=G["attn.l.bias"])      # kv branch's gradient of l joins here
         qclw = pk("attn.qcl")[0]
         dWq = ar.span(st.prefix + "attn.q.weight", st.prefix + "attn.l.weight", qclw.shape)
-        dbq = ar.span(st.prefix + "attn.q.bias", st.prefix + "attn.l.bias", (qclw.shape[0],))
-        dxn = _lin_bwd(dqcl, sv["xn"], qclw, dWq, dbq, T)
+        dxn = _lin_bwd(dqcl, sv["xn"], qclw, dWq, None, T)
         # the pooled-query branch's gradient joins inside the LayerNorm backward kernels (dy2)
         if win:
             K.join(side2)

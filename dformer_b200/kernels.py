@@ -245,10 +245,11 @@ def mul_fwd(a, b, out):
     return out
 
 
-def mul_bwd(dout, a, b, da, db):
+def mul_bwd(dout, a, b, da, db, da_colsum=None, db_colsum=None):
+    """da = dout * b, db = dout * a; with the colsum pair also accumulates the column sums of both (bias gradients)."""
     M, N = a.shape
     lib().mul_bwd(dout.data_ptr(), dout.stride(0), a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), da.data_ptr(), da.stride(0),
-                  db.data_ptr(), db.stride(0), dt(a), M, N, _s())
+                  db.data_ptr(), db.stride(0), dt(a), M, N, _p(da_colsum), _p(db_colsum), _s())
 
 
 def scale_residual_fwd(res, y, ls, scale_b, rows_per_sample):
@@ -277,13 +278,13 @@ def act_fwd(x, act, out=None):
     return out
 
 
-def act_bwd(dout, z, act, out=None, dout2=None):
-    """out = (dout [+ dout2]) * act'(z)"""
+def act_bwd(dout, z, act, out=None, dout2=None, colsum=None):
+    """out = (dout [+ dout2]) * act'(z); colsum (optional) += column sums of out"""
     M, N = z.shape
     if out is None:
         out = torch.empty((M, N), device=z.device, dtype=z.dtype)
     lib().act_bwd(dout.data_ptr(), dout.stride(0), _p(dout2), dout2.stride(0) if dout2 is not None else 0, z.data_ptr(), z.stride(0),
-                  out.data_ptr(), out.stride(0), dt(z), act, M, N, _s())
+                  out.data_ptr(), out.stride(0), dt(z), act, M, N, _p(colsum), _s())
     return out
 
 

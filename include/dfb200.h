@@ -127,7 +127,8 @@ int dfb200_mlp_dw_bwd(const void* du, const void* gp, const void* h, int dtype, 
  *       `out` is a column slice of the concat buffer of :137-140). */
 int dfb200_mul_fwd(const void* a, long lda, const void* b, long ldb, void* out, long ldo, int dtype, int M, int N, void* stream);
 int dfb200_mul_bwd(const void* dout, long ldo, const void* a, long lda, const void* b, long ldb, void* da, long ldda,
-                   void* db, long lddb, int dtype, int M, int N, void* stream);
+                   void* db, long lddb, int dtype, int M, int N,
+                   float* da_colsum, float* db_colsum /* optional pair: += column sums of da / db (bias gradients) */, void* stream);
 /* layer-scale residual (DFormer.py:173-179): out[m,c] = res[m,c] + scale_b[b] * ls[c] * y[m,c]
  * (scale_b = DropPath mask / keep_prob per sample, NULL = 1).  res/out fp32, y in `dtype`. rows_per_sample = H*W. */
 int dfb200_scale_residual_fwd(const float* res, const void* y, long ldy, int dtype, const float* ls, const float* scale_b,
@@ -141,7 +142,8 @@ int dfb200_scale_residual_bwd(const float* dout, const void* y, long ldy, int dt
  * ReLU: z may be the forward output).  All operands have independent leading dimensions. */
 int dfb200_act_fwd(const void* in, long ldi, void* out, long ldo, int dtype, int act, int M, int N, void* stream);
 int dfb200_act_bwd(const void* dout, long lddo, const void* dout2 /* optional second gradient added to dout */, long lddo2,
-                   const void* z, long ldz, void* din, long lddi, int dtype, int act, int M, int N, void* stream);
+                   const void* z, long ldz, void* din, long lddi, int dtype, int act, int M, int N,
+                   float* din_colsum /* optional: += column sums of din */, void* stream);
 
 /* ---- Global Awareness Attention pieces (DFormer.py:107-108,120-131) ------------------------------
  * pool: AdaptiveAvgPool2d(7,7) of cat[xn (C1 ch), en (C2 ch)] -> out [B,49,C1+C2] (compute dtype). */

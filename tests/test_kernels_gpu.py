@@ -250,6 +250,14 @@ def test_mul_and_scale_residual(dtype):
     k.mul_bwd(dout[:, C:], a, b, da, db)
     torch.testing.assert_close(da.float(), dout[:, C:].float() * b.float(), **tol(dtype))
     torch.testing.assert_close(db.float(), dout[:, C:].float() * a.float(), **tol(dtype))
+    # column-summing form: same element-wise results + bias gradients (column sums of what was written), accumulated
+    da2, db2 = torch.empty_like(da), torch.empty_like(db)
+    ca, cb = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+    k.mul_bwd(dout[:, C:], a, b, da2, db2, ca, cb)
+    torch.testing.assert_close(da2, da)
+    torch.testing.assert_close(db2, db)
+    torch.testing.assert_close(ca - 1, da.float().sum(0), rtol=1e-3, atol=2e-2)
+    torch.testing.assert_close(cb, db.float().sum(0), rtol=1e-3, atol=2e-2)
     # layer-scale residual with per-sample DropPath scale
     B, hw = 3, 200
     res, y, ls = rnd(M, C), rnd(M, 2 * C, dtype=dtype)[:, C:], rnd(C)
@@ -276,6 +284,10 @@ def test_mul_and_scale_residual(dtype):
     zr = z[:, C:2 * C].float().clone().requires_grad_(True)
     F.gelu(zr).backward(dout[:, :C].float())
     dz = k.act_bwd(dout[:, :C], z[:, C:2 * C], k.ACT_GELU)
+    cz = torch.zeros(C, device=DEV)
+    dz_b = k.act_bwd(dout[:, :C], z[:, C:2 * C], k.ACT_GELU, colsum=cz)
+    torch.testing.assert_close(dz_b, dz)
+    torch.testing.assert_close(cz, dz.float().sum(0), rtol=1e-3, atol=2e-2)
     torch.testing.assert_close(dz.float(), zr.grad, **tol(dtype))
 
 
