@@ -652,6 +652,10 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
     // the un-split (forward / dgrad) shapes are tuned for wave quantisation
     const bool will_split = (g.splitk == 0 && g.out_dtype == 0 && g.act == 0 && p.kb_total >= 16) || g.splitk > 1;
     p.BN = will_split ? pick_bn_padding(g.N) : pick_bn(g.N, p.m_tiles, p.kb_total, g.batch, num_sms, p.b_mn_major);
+    if (const char* e = getenv("DFB200_TC_BN")) {          // tuning aid (tools/gemm_bn_sweep.py): force the tile width
+      const int bn = atoi(e);
+      if (bn >= 16 && bn <= 256 && bn % 16 == 0 && !(p.b_mn_major && bn < 64 && g.N >= 64)) p.BN = bn;
+    }
   }
   p.n_tiles = dfb_cdiv(g.N, p.BN);
   p.C = g.C; p.ldc = g.ldc; p.bias = g.bias;
