@@ -82,6 +82,7 @@ SIGNATURES = {
     "dfb200_ce_finalize": [P, P, P],
     "dfb200_upsample_ce_bwd_fused": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, P, I, P],
     "dfb200_upsample_ce_bwd": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, I, P],
+    "dfb200_train_pre": [P, P, P, I, I, I, P, P, P, I, I, P, P, P, P],
     "dfb200_resize_nchw_ac": [P, I, I, I, I, P, I, I, I, P],
     "dfb200_ms_softmax_accum": [P, I, I, I, I, P, I, I, I, P],
     "dfb200_argmax_confusion": [P, P, I, I, L, I, P, P, P],

@@ -251,6 +251,15 @@ int dfb200_upsample_ce_bwd(const void* logits_small, int dtype, int B, int h, in
                            const int64_t* label, int ignore, const float* lse, const float* loss_acc, const float* dloss,
                            void* dlogits_small, int dl_dtype, void* stream);
 
+/* ---- training input pipeline (utils/dataloader/dataloader.py:20-73 TrainPre; row N2) --------------------------------------
+ * rgb / modal [B,H,W,3] uint8, label [B,H,W] uint8 on the device; params [B][5] int32 = {mirror, scaled_h, scaled_w, crop_y,
+ * crop_x} (the reference's random draws, made on the host in its order); lut_* [3][256] fp32 = ((v/255 - mean)/std) built in
+ * float64.  Outputs: rgb / modal [B,3,crop_h,crop_w] fp32 (padding 0), label [B,crop_h,crop_w] int64 (padding 255).
+ * Bit-exact with cv2.flip / cv2.resize(INTER_LINEAR | INTER_NEAREST) / copyMakeBorder on uint8 + numpy normalisation. */
+int dfb200_train_pre(const void* rgb, const void* modal, const void* label, int B, int H, int W, const int* params,
+                     const float* lut_rgb, const float* lut_modal, int crop_h, int crop_w, float* out_rgb, float* out_modal,
+                     int64_t* out_label, void* stream);
+
 /* ---- multi-scale + flip evaluation and the mIoU confusion matrix (utils/val_mm.py:257-470, utils/metrics_new.py:6-47) ----
  * resize_nchw_ac:   out[B,C,Ho,Wo] = bilinear(in[B,C,Hi,Wi], align_corners=True), optionally mirrored along W afterwards
  *                   (val_mm.py:366-368,378-380: F.interpolate(..., align_corners=True) then torch.flip(dims=(3,))).

@@ -101,3 +101,21 @@ def test_oracle_against_live_reference_small_variant():
         r = O.forward(P, rgb, hha, bases, v["dims"], v["depths"], label=label, return_all=True)
     torch.testing.assert_close(r["out"], out, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(r["loss"], loss, rtol=1e-5, atol=1e-5)
+
+
+def test_trainpre_oracle_matches_reference_golden():
+    """oracle/trainpre_oracle.py (numpy restatement of TrainPre incl. OpenCV's fixed-point resize) is pinned bit-exactly to the
+    outputs of the unmodified reference preprocessing run with real cv2 (oracle/make_golden_trainpre.py)."""
+    import random
+
+    import numpy as np
+
+    from oracle import trainpre_oracle as T
+    g = torch.load(os.path.join(G, "trainpre.pt"))
+    assert len(g["cases"]) >= 12
+    for c in g["cases"]:
+        random.seed(c["seed"])
+        r, l, m = T.train_pre(c["rgb"].numpy(), c["gt"].numpy(), c["modal"].numpy(), g["mean"], g["std"], c["scales"], c["crop"], c["sign"])
+        assert torch.from_numpy(np.ascontiguousarray(r)).float().equal(c["out_rgb"]), c["seed"]
+        assert torch.from_numpy(np.ascontiguousarray(l)).equal(c["out_gt"]), c["seed"]
+        assert torch.from_numpy(np.ascontiguousarray(m)).float().equal(c["out_modal"]), c["seed"]
