@@ -22,13 +22,15 @@
 namespace {
 
 constexpr int NQ = 49;             // pooled query tokens (7 x 7)
-constexpr int PC = 128;            // pixels per CTA
-constexpr int SP = PC + 4;         // row pitch of the [49][PC] score tile (float4-aligned)
-constexpr int NT = 256;
+// Threads per CTA (NT) and threads per pixel (TPP) are template parameters.  Forward: NT = 256, thread pair per pixel (128-pixel
+// chunks keep the number of partials to merge small).  Backward: NT = 128, thread pair per pixel (64-pixel chunks, 3-4 CTAs per SM).
+// Measured on B200 (stage 1 / 2 / 3 shapes of DFormer-L, batch 8, us): NT 256 TPP 2: 136 / 56 / 37;  NT 128 TPP 2: 114 / 57 / 37;
+// NT 256 TPP 4 (two thread pairs per pixel splitting the 49 query rows): 188 / 61 / 42.
+constexpr int NT_FWD = 256, NT_BWD = 128, TPP_BWD = 2;
 
 // Cooperative, coalesced staging of a [PC pixels][D] slice of kv (row pitch `pitch` elements) into shared memory as fp32:
 // consecutive threads fetch consecutive 32-bit words of a pixel row (per-lane row loads would touch one sector per lane).
-template <typename T, int D>
+template <typename T, int D, int NT, int PC>
 __device__ __forceinline__ void stage_rows(const T* __restrict__ src, long pitch, int nvalid, float* __restrict__ dst) {
   constexpr int WPR = D / 2;
 #pragma unroll
@@ -56,18 +58,19 @@ __device__ __forceinline__ void store_pair(T* dst, float a, float b) {
   }
 }
 
-template <int D>
+template <int D, int NT>
 struct Geo {
   static constexpr int DH = D / 2;
   static constexpr int G = NT / D;                        // row groups of the [49, D] output phase
   static constexpr int RPG = (NQ + G - 1) / G;            // rows per group
 };
 
-template <typename T, int D>
+template <typename T, int D, int NT>
 __global__ void __launch_bounds__(NT) gaa_fused_fwd_kernel(const T* __restrict__ m, const T* __restrict__ kv, int HW, int heads, float scale, int nchunks,
                                                           float* __restrict__ out, float* __restrict__ lse, float* __restrict__ part, int* __restrict__ counters) {
   pdl_sync();
-  constexpr int DH = Geo<D>::DH, G = Geo<D>::G, RPG = Geo<D>::RPG, PS = D + 4;
+  constexpr int PC = NT / 2, SP = PC + 4;
+  constexpr int DH = Geo<D, NT>::DH, G = Geo<D, NT>::G, RPG = Geo<D, NT>::RPG, PS = D + 4;
   extern __shared__ __align__(16) float smf[];
   float* Qs = smf;                       // [49][D]
   float* Vs = Qs + NQ * D;               // [PC][D]
@@ -93,8 +96,8 @@ __global__ void __launch_bounds__(NT) gaa_fused_fwd_kernel(const T* __restrict__
   {
     const T* rows = kv + ((long)b * HW + (long)c * PC) * 2 * Cp + head * D;
     const int nvalid = min(PC, HW - c * PC);
-    stage_rows<T, D>(rows, 2L * Cp, nvalid, Ss);            // K chunk, parked in the (not yet used) score tile
-    stage_rows<T, D>(rows + Cp, 2L * Cp, nvalid, Vs);       // V chunk
+    stage_rows<T, D, NT, PC>(rows, 2L * Cp, nvalid, Ss);            // K chunk, parked in the (not yet used) score tile
+    stage_rows<T, D, NT, PC>(rows + Cp, 2L * Cp, nvalid, Vs);       // V chunk
   }
   __syncthreads();
   TICK();
@@ -221,12 +224,15 @@ __global__ void __launch_bounds__(NT) gaa_fused_fwd_kernel(const T* __restrict__
   if (tid == 0) counters[bh] = 0;                        // self-resetting ticket: the buffer is reusable by the next launch
 }
 
-template <typename T, int D>
+// TPP threads per pixel: 2 = (half-row, half-row); 4 = two such pairs that split the 49 query rows between them (even / odd), which
+// halves the serial row loop -- the latency that bounds this kernel -- and meet again through one shuffle per accumulator at the end.
+template <typename T, int D, int NT, int TPP>
 __global__ void __launch_bounds__(NT) gaa_fused_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ lse,
                                                           const T* __restrict__ m, const T* __restrict__ kv, int HW, int heads, float scale,
                                                           float* __restrict__ dm, T* __restrict__ dkv) {
   pdl_sync();
-  constexpr int DH = Geo<D>::DH, G = Geo<D>::G, RPG = Geo<D>::RPG;
+  constexpr int PC = NT / TPP, SP = PC + 4, RGS = TPP / 2;
+  constexpr int DH = Geo<D, NT>::DH, G = Geo<D, NT>::G, RPG = Geo<D, NT>::RPG;
   extern __shared__ __align__(16) float smf[];
   float* Qs = smf;                       // [49][D]
   float* dOs = Qs + NQ * D;              // [49][D]
@@ -262,7 +268,7 @@ __global__ void __launch_bounds__(NT) gaa_fused_bwd_kernel(const float* __restri
     __syncthreads();                                        // Os (in the dS tile) is dead before V is staged there
   }
   TICK();
-  const int p = tid >> 1, half = tid & 1;
+  const int p = tid / TPP, half = tid & 1, rg = (tid >> 1) & (RGS - 1);
   const int pix = c * PC + p;
   const bool valid = pix < HW;
   float2 k2[DH / 2], v2[DH / 2], dk2[DH / 2], dv2[DH / 2];
@@ -270,8 +276,8 @@ __global__ void __launch_bounds__(NT) gaa_fused_bwd_kernel(const float* __restri
   {
     const T* rows = kv + ((long)b * HW + (long)c * PC) * 2 * Cp + head * D;
     const int nvalid = min(PC, HW - c * PC);
-    stage_rows<T, D>(rows, 2L * Cp, nvalid, Ks);            // K chunk (kept: phase 2 reads it column-wise)
-    stage_rows<T, D>(rows + Cp, 2L * Cp, nvalid, dSs);      // V chunk, parked in the (not yet used) dS tile
+    stage_rows<T, D, NT, PC>(rows, 2L * Cp, nvalid, Ks);        // K chunk (kept: phase 2 reads it column-wise)
+    stage_rows<T, D, NT, PC>(rows + Cp, 2L * Cp, nvalid, dSs);  // V chunk, parked in the (not yet used) dS tile
   }
   __syncthreads();
 #pragma unroll
@@ -282,8 +288,12 @@ __global__ void __launch_bounds__(NT) gaa_fused_bwd_kernel(const float* __restri
   }
   __syncthreads();                                          // v half-rows are in registers before dS overwrites the tile
   TICK();
+  constexpr int ROW_ITERS = (NQ + RGS - 1) / RGS;             // warp-uniform trip count (the shuffles below use the full mask)
 #pragma unroll 2
-  for (int r = 0; r < NQ; ++r) {
+  for (int it = 0; it < ROW_ITERS; ++it) {
+    const int r_raw = rg + it * RGS;
+    const bool row_ok = r_raw < NQ;
+    const int r = row_ok ? r_raw : NQ - 1;
     const float2* q = reinterpret_cast<const float2*>(Qs + r * D + half * DH);
     const float2* go = reinterpret_cast<const float2*>(dOs + r * D + half * DH);
     float2 s2 = make_float2(0.f, 0.f), dp2 = make_float2(0.f, 0.f);
@@ -293,19 +303,26 @@ __global__ void __launch_bounds__(NT) gaa_fused_bwd_kernel(const float* __restri
     float sd = s2.x + s2.y, dp = dp2.x + dp2.y;
     sd += __shfl_xor_sync(0xffffffffu, sd, 1);
     dp += __shfl_xor_sync(0xffffffffu, dp, 1);
-    const float P = valid ? __expf(fmaf(sd, scale, -lses[r])) : 0.f;
+    const float P = (valid && row_ok) ? __expf(fmaf(sd, scale, -lses[r])) : 0.f;
     const float ds = P * (dp - Dr[r]);
     const float2 P2 = make_float2(P, P), ds2 = make_float2(ds, ds);
 #pragma unroll
     for (int j = 0; j < DH / 2; ++j) { ffma2(dv2[j], P2, gv[j]); ffma2(dk2[j], ds2, qv[j]); }
-    if (half == (r & 1)) dSs[r * SP + p] = ds;
+    if (row_ok && half == (RGS == 1 ? (r & 1) : 0)) dSs[r * SP + p] = ds;
   }
   TICK();
+  if (RGS == 2) {                                             // the two row groups of a pixel add up their partial dK / dV
+#pragma unroll
+    for (int j = 0; j < DH / 2; ++j) {
+      dk2[j].x += __shfl_xor_sync(0xffffffffu, dk2[j].x, 2); dk2[j].y += __shfl_xor_sync(0xffffffffu, dk2[j].y, 2);
+      dv2[j].x += __shfl_xor_sync(0xffffffffu, dv2[j].x, 2); dv2[j].y += __shfl_xor_sync(0xffffffffu, dv2[j].y, 2);
+    }
+  }
   if (valid) {
 #pragma unroll
     for (int j = 0; j < DH / 2; ++j) {
-      store_pair<T>(dkv + rowoff + 2 * j, dk2[j].x * scale, dk2[j].y * scale);
-      store_pair<T>(dkv + rowoff + Cp + 2 * j, dv2[j].x, dv2[j].y);
+      if (RGS == 1 || rg == 0) store_pair<T>(dkv + rowoff + 2 * j, dk2[j].x * scale, dk2[j].y * scale);
+      if (RGS == 1 || rg == 1) store_pair<T>(dkv + rowoff + Cp + 2 * j, dv2[j].x, dv2[j].y);
     }
   }
   __syncthreads();
@@ -340,22 +357,22 @@ __global__ void __launch_bounds__(NT) gaa_fused_bwd_kernel(const float* __restri
 #endif
 }
 
-template <int D> constexpr int fwd_smem() { return (NQ * D + PC * D + NQ * SP + 2 * NQ) * 4; }
-template <int D> constexpr int bwd_smem() { return (2 * NQ * D + PC * D + NQ * SP + 2 * NQ) * 4; }
+template <int D, int NT> constexpr int fwd_smem() { return (NQ * D + (NT / 2) * D + NQ * (NT / 2 + 4) + 2 * NQ) * 4; }
+template <int D, int PC> constexpr int bwd_smem() { return (2 * NQ * D + PC * D + NQ * (PC + 4) + 2 * NQ) * 4; }
 
 template <typename T, int D>
 int launch_fwd(const void* m, const void* kv, int B, int HW, int heads, float* out, float* lse, float* part, int* counters, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gaa_fused_fwd_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gaa_fused_fwd_kernel<T, D, NT_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) { dfb_set_error("gaa_fused_fwd smem attr: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
     attr = true;
   }
-  const int nchunks = dfb_cdiv(HW, PC);
-  const int smem = fwd_smem<D>() + 2 * nchunks * NQ * 4;            // + merge staging of the (max, sum) pairs
+  const int nchunks = dfb_cdiv(HW, NT_FWD / 2);
+  const int smem = fwd_smem<D, NT_FWD>() + 2 * nchunks * NQ * 4;            // + merge staging of the (max, sum) pairs
   if (smem > 200 * 1024) { dfb_set_error("gaa_fused_fwd: HW=%d too large for the one-launch merge", HW); return DFB_ERR_UNSUPPORTED; }
   dim3 grid(nchunks, B * heads);
-  dfb_launch(gaa_fused_fwd_kernel<T, D>, grid, NT, smem, st, (const T*)m, (const T*)kv, HW, heads, 1.0f / sqrtf((float)D), nchunks, out, lse, part, counters);
+  dfb_launch(gaa_fused_fwd_kernel<T, D, NT_FWD>, grid, NT_FWD, smem, st, (const T*)m, (const T*)kv, HW, heads, 1.0f / sqrtf((float)D), nchunks, out, lse, part, counters);
   return dfb_check_launch("gaa_fused_fwd");
 }
 
@@ -364,13 +381,13 @@ int launch_bwd(const float* dout, const float* out, const float* lse, const void
                cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gaa_fused_bwd_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<D>());
+    cudaError_t e = cudaFuncSetAttribute(gaa_fused_bwd_kernel<T, D, NT_BWD, TPP_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<D, NT_BWD / TPP_BWD>());
     if (e != cudaSuccess) { dfb_set_error("gaa_fused_bwd smem attr: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
     attr = true;
   }
   cudaMemsetAsync(dm, 0, sizeof(float) * (size_t)B * NQ * heads * D, st);
-  dim3 grid(dfb_cdiv(HW, PC), B * heads);
-  dfb_launch(gaa_fused_bwd_kernel<T, D>, grid, NT, bwd_smem<D>(), st, dout, out, lse, (const T*)m, (const T*)kv, HW, heads, 1.0f / sqrtf((float)D), dm, (T*)dkv);
+  dim3 grid(dfb_cdiv(HW, NT_BWD / TPP_BWD), B * heads);
+  dfb_launch(gaa_fused_bwd_kernel<T, D, NT_BWD, TPP_BWD>, grid, NT_BWD, bwd_smem<D, NT_BWD / TPP_BWD>(), st, dout, out, lse, (const T*)m, (const T*)kv, HW, heads, 1.0f / sqrtf((float)D), dm, (T*)dkv);
   return dfb_check_launch("gaa_fused_bwd");
 }
 
