@@ -65,5 +65,7 @@ def test_staged_input_prefetch_feeds_the_same_step():
             torch.manual_seed(7)
             run.stage(*batches[i + 1])                       # overlaps the step just launched
         staged.append(loss.item())
-    assert staged == pytest.approx(direct, rel=1e-5, abs=1e-6)      # (the loss sum uses fp32 atomics: last-bit differences)
-    assert len({round(v, 4) for v in direct}) == len(direct)     # the three batches really differ
+    # run-to-run noise of a bf16 step is ~1e-4 on the loss (split-K fp32 atomics in the NMF products feed bf16 roundings);
+    # the three batches differ by > 2e-3 even at the default init (layer scales 1e-6)
+    assert staged == pytest.approx(direct, abs=4e-4)
+    assert min(abs(a - b) for i, a in enumerate(direct) for b in direct[i + 1:]) > 1.2e-3
