@@ -42,7 +42,6 @@ __global__ void __launch_bounds__(NT, 3) dw7_conv_kernel(const __grid_constant__
   const int tid = threadIdx.x, cq = tid % NQ, pg = tid / NQ;
   const int c_base = blockIdx.y * SW, c0 = c_base + cq * 4;
   const int n_tiles = B * tiles_x * tiles_y;
-  const long row_stride = (long)W * C;
   if (tid == 0) {
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -94,7 +93,6 @@ __global__ void __launch_bounds__(NT, 3) dw7_conv_kernel(const __grid_constant__
         }
         const int oy = ty0 + row, ox0 = tx0 + x0;
         bf16* yp = y + (((long)b * H + oy) * W + ox0) * C + c0;
-        (void)row_stride;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
           const uint2 o = pack4(acc[t][0], acc[t][1]);
