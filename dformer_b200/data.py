@@ -60,3 +60,29 @@ class TrainPre:
         lib().train_pre(rgb.data_ptr(), modal_x.data_ptr(), gt.data_ptr(), B, H, W, ptab.data_ptr(), lut_rgb.data_ptr(), lut_modal.data_ptr(), ch, cw,
                         out_rgb.data_ptr(), out_modal.data_ptr(), out_gt.data_ptr(), _s())
         return out_rgb, out_gt, out_modal
+
+
+class ValPre:
+    """utils/dataloader/dataloader.py:112-122 for a device-resident uint8 batch: normalisation (the depth image always with 0.48 / 0.28,
+    as the reference does) and HWC -> CHW; same kernel as TrainPre with the identity geometry."""
+
+    def __init__(self, norm_mean, norm_std, sign: bool = False, config=None):
+        self.config, self.norm_mean, self.norm_std, self.sign = config, norm_mean, norm_std, sign
+        self._luts = {}
+
+    def __call__(self, rgb: torch.Tensor, gt: torch.Tensor, modal_x: torch.Tensor):
+        _chk(rgb, "rgb")
+        assert rgb.dtype == torch.uint8 and modal_x.dtype == torch.uint8 and gt.dtype == torch.uint8 and rgb.dim() == 4 and rgb.shape[-1] == 3
+        B, H, W, _ = rgb.shape
+        dev = rgb.device
+        if dev not in self._luts:
+            self._luts[dev] = (_lut(self.norm_mean, self.norm_std, dev), _lut([0.48] * 3, [0.28] * 3, dev))
+        lut_rgb, lut_modal = self._luts[dev]
+        ptab = torch.tensor([[0, H, W, 0, 0]] * B, dtype=torch.int32).to(dev, non_blocking=True)
+        out_rgb = torch.empty((B, 3, H, W), device=dev, dtype=torch.float32)
+        out_modal = torch.empty((B, 3, H, W), device=dev, dtype=torch.float32)
+        out_gt = torch.empty((B, H, W), device=dev, dtype=torch.int64)
+        rgb, gt, modal_x = rgb.contiguous(), gt.contiguous(), modal_x.contiguous()
+        lib().train_pre(rgb.data_ptr(), modal_x.data_ptr(), gt.data_ptr(), B, H, W, ptab.data_ptr(), lut_rgb.data_ptr(), lut_modal.data_ptr(), H, W,
+                        out_rgb.data_ptr(), out_modal.data_ptr(), out_gt.data_ptr(), _s())
+        return out_rgb, out_gt, out_modal

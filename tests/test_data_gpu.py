@@ -46,3 +46,18 @@ def test_train_pre_full_size_batch_matches_oracle():
         assert o_rgb[b].cpu().equal(torch.from_numpy(np.ascontiguousarray(r)).float()), b
         assert o_modal[b].cpu().equal(torch.from_numpy(np.ascontiguousarray(m)).float()), b
         assert o_gt[b].cpu().equal(torch.from_numpy(np.ascontiguousarray(l)).long()), b
+
+
+def test_val_pre_matches_reference_formula():
+    """ValPre (dataloader.py:112-122): float64 normalisation (depth always with 0.48 / 0.28), HWC -> CHW; labels untouched."""
+    from dformer_b200.data import ValPre
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    rng = np.random.default_rng(5)
+    rgb = rng.integers(0, 256, (2, 37, 53, 3), dtype=np.uint8)
+    modal = rng.integers(0, 256, (2, 37, 53, 3), dtype=np.uint8)
+    gt = rng.integers(0, 41, (2, 37, 53), dtype=np.uint8)
+    o_rgb, o_gt, o_modal = ValPre(mean, std)(torch.from_numpy(rgb).cuda(), torch.from_numpy(gt).cuda(), torch.from_numpy(modal).cuda())
+    norm = lambda im, m, s: ((im.astype(np.float64) / 255.0 - np.asarray(m)) / np.asarray(s)).transpose(0, 3, 1, 2)
+    assert o_rgb.cpu().equal(torch.from_numpy(np.ascontiguousarray(norm(rgb, mean, std))).float())
+    assert o_modal.cpu().equal(torch.from_numpy(np.ascontiguousarray(norm(modal, [0.48] * 3, [0.28] * 3))).float())
+    assert o_gt.cpu().equal(torch.from_numpy(gt).long())
