@@ -586,6 +586,32 @@ extern "C" int dfb200_layernorm_bwd(const void* dy, const void* dy2, int dy_dtyp
   return dfb_check_launch("layernorm_bwd");
 }
 
+// Inference-time BatchNorm folding for conv -> BN pairs: the freshly packed GEMM weight [rows, ld] (compute
+// dtype) is scaled row-wise in place by s = gamma * rsqrt(running_var + eps) and bias_out = (conv_bias - running_mean) * s + beta,
+// so that BN(conv(x)) = x * W' + bias' and the BN kernels drop out of the forward pass.  The fp32 parameters stay untouched.
+template <typename T>
+__global__ void bn_fold_kernel(T* __restrict__ w, int rows, int cols, long ld, const float* __restrict__ conv_bias, const float* __restrict__ rm,
+                               const float* __restrict__ rv, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                               float* __restrict__ bias_out) {
+  pdl_sync();
+  const long n = (long)rows * cols;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const float sc = gamma[r] * rsqrtf(rv[r] + eps);
+    w[(long)r * ld + c] = from_f<T>(to_f(w[(long)r * ld + c]) * sc);
+    if (c == 0) bias_out[r] = ((conv_bias ? conv_bias[r] : 0.f) - rm[r]) * sc + beta[r];
+  }
+}
+
+extern "C" int dfb200_bn_fold(void* w_packed, int dtype, int rows, int cols, long ld, const float* conv_bias, const float* running_mean,
+                              const float* running_var, float eps, const float* gamma, const float* beta, float* bias_out, void* stream) {
+  DFB_REQUIRE(rows > 0 && cols > 0 && ld >= cols && bias_out, "bn_fold: bad arguments");
+  const long n = (long)rows * cols;
+  const int grid = (int)min((n + 255) / 256, 148L * 8);
+  DFB_DISPATCH_DTYPE(dtype, T, { dfb_launch(bn_fold_kernel<T>, grid, 256, 0, ST, (T*)w_packed, rows, cols, ld, conv_bias, running_mean, running_var, eps, gamma, beta, bias_out); });
+  return dfb_check_launch("bn_fold");
+}
+
 extern "C" int dfb200_bn_stats(const void* x, int dtype, int M, int C, double* sum, double* sumsq, void* stream) {
   DFB_REQUIRE(C % 8 == 0, "bn_stats: C %% 8 != 0 (C=%d)", C);
   cudaMemsetAsync(sum, 0, sizeof(double) * C, ST);

@@ -98,6 +98,21 @@ def _bn_fwd(x2d, bn: BNState, out_dtype, act=K.ACT_NONE, residual=None, chan_sca
     return y, ms, count
 
 
+_FOLD_BN = _os.environ.get("DFB200_FOLD_BN", "1") == "1"       # inference: conv -> BN(eval) pairs run as one GEMM
+
+
+def _can_fold(bn: BNState, ctx) -> bool:
+    """eval-mode statistics and no gradient wanted from this call: the BN is a per-channel affine that folds into the conv's GEMM"""
+    return _FOLD_BN and not bn.training and not any(ctx.needs_input_grad)
+
+
+def _lin_bn_folded(x, wb, bn: BNState, T, act=K.ACT_NONE, out_dtype=None):
+    """act(BN_eval(x W^T + b)) as ONE GEMM: the packed weight (re-packed from the fp32 parameters every forward) is scaled in place"""
+    w, b = wb
+    bias = K.bn_fold(w, w.shape[1], b, bn.running_mean, bn.running_var, bn.eps, bn.weight, bn.bias)
+    return K.gemm(x, w, trans_b=True, bias=bias, out_dtype=out_dtype or T, act=act, backend=backend_for(T), K=x.shape[1])
+
+
 def _bn_bwd(dy, x2d, ms, bn: BNState, count, dx_dtype, dgamma, dbeta, act=K.ACT_NONE, residual=None, chan_scale=None, rows_per_sample=1):
     """returns (dx, g) with g = gradient w.r.t. the pre-activation (= gradient of the residual branch)."""
     gbuf, sums = K.bn_bwd_reduce(dy, x2d, ms, bn.weight, bn.bias, residual, act, chan_scale, rows_per_sample)
@@ -122,6 +137,11 @@ class StemFn(torch.autograd.Function):
         H1, W1, H2, W2 = (H + 1) // 2, (W + 1) // 2, ((H + 1) // 2 + 1) // 2, ((W + 1) // 2 + 1) // 2
         pk1, pk2 = st.packed[st.g1], st.packed[st.g2]
         col1 = K.im2col_fwd(inp, (inp.stride(0), inp.stride(2), inp.stride(3), inp.stride(1)), B, H, W, cin, T, pk1[0].shape[1])
+        if _can_fold(st.bn1, ctx) and _can_fold(st.bn2, ctx):          # inference: both BatchNorms ride in their conv's GEMM
+            a1 = _lin_bn_folded(col1, pk1, st.bn1, T, act=K.ACT_GELU)
+            cm = a1.shape[1]
+            col2 = K.im2col_fwd(a1, (H1 * W1 * cm, W1 * cm, cm, 1), B, H1, W1, cm, T, pk2[0].shape[1])
+            return _lin_bn_folded(col2, pk2, st.bn2, T, out_dtype=F32)
         c1 = _lin(col1, pk1, T)
         a1, ms1, n1 = _bn_fwd(c1, st.bn1, T, act=K.ACT_GELU)
         cm = a1.shape[1]
@@ -578,16 +598,25 @@ class HeadFn(torch.autograd.Function):
         K.resize_fwd(o1, B, h1, w1, cat, h1, w1, col0=0)
         K.resize_fwd(o2, B, h2, w2, cat, h1, w1, col0=C1)
         K.resize_fwd(o3, B, h3, w3, cat, h1, w1, col0=C1 + C2)
-        s_pre = _lin(cat, pk("squeeze"), T)
-        s, ms_s, n_s = _bn_fwd(s_pre, st.bn_sq, T, act=K.ACT_RELU)
+        fold = _can_fold(st.bn_sq, ctx) and _can_fold(st.bn_al, ctx) and st.drop_mask is None
+        if fold:
+            s_pre, ms_s, n_s = None, None, 0
+            s = _lin_bn_folded(cat, pk("squeeze"), st.bn_sq, T, act=K.ACT_RELU)
+        else:
+            s_pre = _lin(cat, pk("squeeze"), T)
+            s, ms_s, n_s = _bn_fwd(s_pre, st.bn_sq, T, act=K.ACT_RELU)
         hin = _lin(s, pk("ham_in"), T, act=K.ACT_RELU)
         D = hin.shape[1]
         nmf, nmf_saved = _nmf_fwd(hin.view(B, h1 * w1, D), bases_raw, st.steps, T)
         nmf2d = nmf.view(M, D)
         ho_pre = _lin(nmf2d, pk("ham_out"), T)
         hs, ms_o, n_o = _bn_fwd(ho_pre, st.bn_out, T, act=K.ACT_RELU, residual=s)
-        al_pre = _lin(hs, pk("align"), T)
-        al, ms_a, n_a = _bn_fwd(al_pre, st.bn_al, T, act=K.ACT_RELU, chan_scale=st.drop_mask, rows_per_sample=h1 * w1)
+        if fold:
+            al_pre, ms_a, n_a = None, None, 0
+            al = _lin_bn_folded(hs, pk("align"), st.bn_al, T, act=K.ACT_RELU)
+        else:
+            al_pre = _lin(hs, pk("align"), T)
+            al, ms_a, n_a = _bn_fwd(al_pre, st.bn_al, T, act=K.ACT_RELU, chan_scale=st.drop_mask, rows_per_sample=h1 * w1)
         logits = _lin(al, pk("conv_seg"), T)
         ctx.st = st
         ctx.sv = dict(cat=cat, s_pre=s_pre, ms_s=ms_s, n_s=n_s, s=s, hin=hin, nmf_saved=nmf_saved, nmf=nmf2d, ho_pre=ho_pre, ms_o=ms_o,

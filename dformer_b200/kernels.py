@@ -416,6 +416,15 @@ def bn_bwd_apply(gbuf, x, ms, gamma, sums, count, training, dx_dtype):
     return dx
 
 
+def bn_fold(w_packed, cols, conv_bias, running_mean, running_var, eps, gamma, beta):
+    """Fold an eval-mode BatchNorm into the freshly packed weight of the conv in front of it (in place); returns the folded bias."""
+    rows = w_packed.shape[0]
+    bias = torch.empty(rows, device=w_packed.device, dtype=torch.float32)
+    lib().bn_fold(w_packed.data_ptr(), dt(w_packed), rows, cols, w_packed.stride(0), _p(conv_bias), running_mean.data_ptr(), running_var.data_ptr(),
+                  eps, gamma.data_ptr(), beta.data_ptr(), bias.data_ptr(), _s())
+    return bias
+
+
 def normalize_cols(x):
     B, D, R = x.shape
     out = torch.empty_like(x)

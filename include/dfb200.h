@@ -260,6 +260,11 @@ int dfb200_train_pre(const void* rgb, const void* modal, const void* label, int 
                      const float* lut_rgb, const float* lut_modal, int crop_h, int crop_w, float* out_rgb, float* out_modal,
                      int64_t* out_label, void* stream);
 
+/* ---- inference-time BatchNorm folding for conv -> BN pairs (row N4): scales the packed GEMM weight [rows, ld] (dtype) row-wise in
+ * place by gamma * rsqrt(running_var + eps) and writes bias_out[rows] = (conv_bias - running_mean) * scale + beta. */
+int dfb200_bn_fold(void* w_packed, int dtype, int rows, int cols, long ld, const float* conv_bias, const float* running_mean,
+                   const float* running_var, float eps, const float* gamma, const float* beta, float* bias_out, void* stream);
+
 /* ---- multi-scale + flip evaluation and the mIoU confusion matrix (utils/val_mm.py:257-470, utils/metrics_new.py:6-47) ----
  * resize_nchw_ac:   out[B,C,Ho,Wo] = bilinear(in[B,C,Hi,Wi], align_corners=True), optionally mirrored along W afterwards
  *                   (val_mm.py:366-368,378-380: F.interpolate(..., align_corners=True) then torch.flip(dims=(3,))).

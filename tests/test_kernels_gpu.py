@@ -625,3 +625,25 @@ def test_metrics_match_reference_formulas():
     acc = hist.diag() / hist.sum(1)
     assert m.compute_pixel_acc()[1] == round(acc.mean().item() * 100, 2)
     assert scaled_size(480, 640, 0.75) == (384, 480) and scaled_size(480, 640, 1.25) == (608, 800)
+
+
+# ----------------------------------------------------------------------------- inference-time BatchNorm folding (row N4)
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_bn_fold(dtype):
+    k = K()
+    rows, cols, ld = 48, 27, 32
+    w = torch.zeros(rows, ld, device=DEV, dtype=dtype)
+    w[:, :cols] = rnd(rows, cols, dtype=dtype)
+    w0 = w.clone()
+    cb, rm, rv, g, b = rnd(rows), rnd(rows), torch.rand(rows, device=DEV) + 0.2, 1 + 0.2 * rnd(rows), rnd(rows)
+    bias = k.bn_fold(w, ld, cb, rm, rv, 1e-5, g, b)
+    sc = g * torch.rsqrt(rv + 1e-5)
+    torch.testing.assert_close(w.float(), (w0.float() * sc[:, None]), **tol(dtype))
+    torch.testing.assert_close(bias, (cb - rm) * sc + b, rtol=1e-5, atol=1e-6)
+    # conv -> BN(eval) == one GEMM with the folded weight and bias
+    x = rnd(200, ld, dtype=dtype)
+    ref = ((x.float() @ w0.float().t() + cb) - rm) * sc + b
+    out = k.gemm(x, w, trans_b=True, bias=bias, backend=k.SIMT)
+    torch.testing.assert_close(out.float(), ref, **(dict(rtol=3e-2, atol=8e-2) if dtype == torch.bfloat16 else dict(rtol=1e-4, atol=1e-4)))
+    bias2 = k.bn_fold(w0.clone(), ld, None, rm, rv, 1e-5, g, b)               # conv without bias (the head's ConvModules)
+    torch.testing.assert_close(bias2, -rm * sc + b, rtol=1e-5, atol=1e-6)

@@ -207,3 +207,25 @@ def test_multi_scale_flip_evaluation_matches_the_reference_loop():
     refm.update_hist(hist)
     assert abs(met.compute_iou()[1] - refm.compute_iou()[1]) < 0.05
     assert not m.training
+
+
+def test_eval_bn_folding_is_transparent():
+    """Inference folds the conv -> BN(eval) pairs of the stems and the head into their GEMMs (row N4): same logits as the unfolded path,
+    and the fp32 parameters / running statistics are left untouched."""
+    from dformer_b200 import functions as Fn
+    m, _ = build("DFormer-Tiny", 40, "fp32", 9, train=False)
+    for mod in m.modules():                                  # non-trivial running statistics
+        if isinstance(mod, nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.3)
+            mod.running_var.uniform_(0.5, 2.0)
+    rgb, hha, _, bases = make_inputs(2, 64, 96, 40, seed=9)
+    m.decode_head.injected_bases = bases.cuda()
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    outs = {}
+    for fold in (True, False):
+        Fn._FOLD_BN = fold
+        with torch.no_grad():
+            outs[fold] = m(rgb.cuda(), hha.cuda())
+    Fn._FOLD_BN = True
+    torch.testing.assert_close(outs[True], outs[False], rtol=1e-4, atol=1e-5)
+    assert all(torch.equal(v, m.state_dict()[k]) for k, v in before.items())
