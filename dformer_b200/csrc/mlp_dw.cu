@@ -1,19 +1,20 @@
-// The middle of the DFormer MLP (DFormer.py:62-64) as two HBM-streaming kernels for bf16 channels-last activations:
+// The middle of the DFormer MLP (DFormer.py:62-64) as HBM-streaming kernels for bf16 channels-last activations:
 //
-//   forward   u  = GELU( dw3x3(h) + b + h )                                   reads h, writes u            (2 passes)
-//   backward  dz = du * GELU'( dw3x3(h) + b + h )      (pre-activation recomputed from h, never stored)
-//             dh = dz + dw3x3^T(dz)                                           reads du, h, writes dh       (3 passes)
+//   forward   u  = GELU( dw3x3(h) + b + h )         reads h, writes u (+ gp = GELU'(z) in training)        2 (3) passes
+//   backward  dz = du * gp                          (training default: GELU'(z) kept by the forward pass)
+//             dh = dz + dw3x3^T(dz)                 reads du, gp, h, writes dh                              4 passes
 //             dW[c,ky,kx] += sum_p dz[p,c] h[p+(ky-1,kx-1),c]   db[c] += sum_p dz[p,c]   dfc1_b[c] += sum_p dh[p,c]
+//   (mlp_dw_bwd_kernel: same outputs with GELU'(dw3x3(h) + b + h) recomputed on a one-pixel halo ring instead of read: 3 passes,
+//    but FMA-bound -- kept for callers that did not keep gp.)
 //
-// (the unfused chain -- save z, act_bwd, data-gradient conv, weight-gradient conv, column sum -- moved 10 passes).
+// The unfused chain -- save z, act_bwd, data-gradient conv, weight-gradient conv, column sum -- moved 10 passes.
 //
 // A CTA owns one 64-channel slab and walks TY x TX pixel tiles of it.  Halo tiles are brought in by TMA
 // (cp.async.bulk.tensor.4d over [B, H, W, C]; out-of-image pixels and channels are zero-filled by the copy engine, which
 // is exactly the zero padding of the convolution) and completion is signalled on an mbarrier.  A thread owns one
 // 4-channel group (8-byte shared-memory vectors; 16 threads cover one pixel's 128-byte slab row, conflict-free) and
 // keeps its 9 x 4 filter taps in registers for the whole kernel, the centre tap with the "+ h" folded in.  All FMAs are
-// packed fp32 pairs (FFMA2).  In the backward kernel dz lives only in shared memory (bf16, written in place over the
-// du tile, computed for a one-pixel halo ring so the transposed convolution needs no neighbour exchange).
+// packed fp32 pairs (FFMA2).  dz lives only in shared memory (bf16, written in place over the du tile).
 #include "tile_common.cuh"
 #include "dfb200_internal.h"
 
