@@ -255,15 +255,86 @@ extern "C" int dfb200_resize_fwd(const void* in, int in_dtype, int B, int Hi, in
 #undef L
   return dfb_check_launch("resize_fwd");
 }
+// Block-cooperative adjoint for large up-sampling ratios (the 7x7 attention map -> H x W, the stage-3 feature map -> 60 x 80): one CTA
+// per input pixel.  The separable bilinear weights of its candidate output rows / columns are computed once into shared memory
+// (no per-candidate coordinate arithmetic), thread = (8-channel vector, pixel lane) walks the candidates with one 16-byte load and
+// 8 FMAs each, and the pixel lanes meet in shared memory.
+constexpr int RB_MAXR = 96;          // max candidate rows / columns per input pixel handled by this kernel
+template <typename TO, typename TI>
+__global__ void __launch_bounds__(256) resize_bwd_block_kernel(const TO* __restrict__ dout, long ldo, int col0, int B, int Hi, int Wi, int C, int Ho, int Wo,
+                                                              TI* __restrict__ din, int accumulate) {
+  pdl_sync();
+  __shared__ float wys[RB_MAXR], wxs[RB_MAXR];
+  __shared__ float red[256 * 8];
+  const int nvec = C >> 3;
+  const long pix = blockIdx.x;
+  const int ix = (int)(pix % Wi), iy = (int)((pix / Wi) % Hi), b = (int)(pix / ((long)Wi * Hi));
+  const float ry = (float)Ho / (float)Hi, rx = (float)Wo / (float)Wi;
+  int oy_lo = max(0, (int)floorf((iy - 1) * ry) - 1), oy_hi = min(Ho - 1, (int)ceilf((iy + 2) * ry) + 1);
+  int ox_lo = max(0, (int)floorf((ix - 1) * rx) - 1), ox_hi = min(Wo - 1, (int)ceilf((ix + 2) * rx) + 1);
+  if (iy == 0) oy_lo = 0;
+  if (iy == Hi - 1) oy_hi = Ho - 1;
+  if (ix == 0) ox_lo = 0;
+  if (ix == Wi - 1) ox_hi = Wo - 1;
+  const int ny = oy_hi - oy_lo + 1, nx = ox_hi - ox_lo + 1;
+  for (int i = threadIdx.x; i < ny; i += 256) {
+    const Lerp l = lerp_coord(oy_lo + i, Hi, Ho);
+    wys[i] = (l.i0 == iy ? 1.f - l.w1 : 0.f) + (l.i1 == iy ? l.w1 : 0.f);
+  }
+  for (int i = threadIdx.x; i < nx; i += 256) {
+    const Lerp l = lerp_coord(ox_lo + i, Wi, Wo);
+    wxs[i] = (l.i0 == ix ? 1.f - l.w1 : 0.f) + (l.i1 == ix ? l.w1 : 0.f);
+  }
+  __syncthreads();
+  const int total = ny * nx;
+  for (int v0 = 0; v0 < nvec; v0 += 256) {                     // channel-vector chunks (one for every DFormer width)
+    const int nv = min(256, nvec - v0), lanes = 256 / nv;
+    const int v = threadIdx.x % nv, lane = threadIdx.x / nv;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (lane < lanes) {
+      const TO* base = dout + (long)b * Ho * Wo * ldo + col0 + (v0 + v) * 8;
+      for (int t = lane; t < total; t += lanes) {
+        const int yy = t / nx, xx = t - yy * nx;
+        const float w = wys[yy] * wxs[xx];
+        if (w == 0.f) continue;
+        float g[8];
+        Vec8<TO>::load(base + ((long)(oy_lo + yy) * Wo + ox_lo + xx) * ldo, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, g[j], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = acc[j];
+    __syncthreads();
+    if (lane == 0) {
+      for (int q = 1; q < lanes; ++q)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += red[(q * nv + v) * 8 + j];
+      TI* dst = din + pix * C + (v0 + v) * 8;
+      if (accumulate) {
+        float old[8];
+        Vec8<TI>::load(dst, old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += old[j];
+      }
+      Vec8<TI>::store(dst, acc);
+    }
+    __syncthreads();
+  }
+}
+
 extern "C" int dfb200_resize_bwd(const void* dout, int out_dtype, long ldo, int col0, int B, int Hi, int Wi, int C, int Ho, int Wo, void* din, int in_dtype,
                                  int accumulate, void* stream) {
   DFB_REQUIRE(C % 8 == 0 && ldo % 8 == 0 && col0 % 8 == 0, "resize: C, ldo, col0 must be multiples of 8");
   const long work = (long)B * Hi * Wi * C / 8;
   const bool coop = ((long)Ho * Wo >= 16L * Hi * Wi);              // >= 4x up-sampling per axis: hundreds of candidates per input pixel
   const int g = coop ? (int)min(work / 8 + 1, 148L * 16) : ew_grid(work);
+  // candidate rows / columns per input pixel: 3 * ratio + 4 at most (see the range computation in the kernels)
+  const bool block_ok = (3L * Ho / Hi + 5 <= RB_MAXR) && (3L * Wo / Wi + 5 <= RB_MAXR) && (long)B * Hi * Wi < (1L << 31);
 #define L(TO, TI)                                                                                                                        \
   do {                                                                                                                                   \
-    if (coop) dfb_launch(resize_bwd_warp_kernel<TO, TI>, g, 256, 0, ST, (const TO*)dout, ldo, col0, B, Hi, Wi, C, Ho, Wo, (TI*)din, accumulate); \
+    if (coop && block_ok) dfb_launch(resize_bwd_block_kernel<TO, TI>, (unsigned)((long)B * Hi * Wi), 256, 0, ST, (const TO*)dout, ldo, col0, B, Hi, Wi, C, Ho, Wo, (TI*)din, accumulate); \
+    else if (coop) dfb_launch(resize_bwd_warp_kernel<TO, TI>, g, 256, 0, ST, (const TO*)dout, ldo, col0, B, Hi, Wi, C, Ho, Wo, (TI*)din, accumulate); \
     else dfb_launch(resize_bwd_kernel<TO, TI>, g, 256, 0, ST, (const TO*)dout, ldo, col0, B, Hi, Wi, C, Ho, Wo, (TI*)din, accumulate);           \
   } while (0)
   if (in_dtype == 0 && out_dtype == 0) L(float, float);

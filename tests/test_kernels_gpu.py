@@ -363,6 +363,23 @@ def test_resize(in_dtype, out_dtype, hi, wi, ho, wo):
     torch.testing.assert_close(din.float(), want, **t)
 
 
+@pytest.mark.parametrize("C,hi,wi,ho,wo", [(48, 7, 7, 120, 160), (144, 7, 7, 30, 40), (288, 7, 7, 15, 20), (96, 7, 7, 60, 80), (2056, 2, 2, 9, 11)])
+def test_resize_bwd_block_cooperative(C, hi, wi, ho, wo):
+    """The one-CTA-per-input-pixel adjoint at the attention branch's real widths (vector counts that do not divide the CTA,
+    more vectors than threads) against autograd of F.interpolate (`DFormer.py:131`)."""
+    k = K()
+    B = 2
+    xr = torch.zeros(B, C, hi, wi, device=DEV, requires_grad=True)
+    ref = F.interpolate(xr, (ho, wo), mode="bilinear", align_corners=False)
+    dout = rnd(B * ho * wo, C + 8, dtype=torch.bfloat16)
+    ref.backward(dout.view(B, ho, wo, C + 8)[..., 8:].float().permute(0, 3, 1, 2))
+    want = xr.grad.permute(0, 2, 3, 1).reshape(-1, C)
+    for accumulate in (0, 1):
+        din = torch.ones(B * hi * wi, C, device=DEV, dtype=torch.float32)
+        k.resize_bwd(dout, 8, B, hi, wi, C, ho, wo, din, accumulate=bool(accumulate))
+        torch.testing.assert_close(din, want + accumulate, rtol=1e-4, atol=2e-3)
+
+
 # ----------------------------------------------------------------------------- im2col conv
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_im2col_conv3x3s2(dtype):
