@@ -76,7 +76,9 @@ def synthetic(batch, device, seed):
 
 
 def cfg_for(precision, device):
-    return SimpleNamespace(backbone=VARIANT, decoder="ham", decoder_embed_dim=512, num_classes=NCLS, drop_path_rate=0.15, aux_rate=0.0,
+    # drop_path of the matching local_configs file: 0.15 for Large, 0.1 otherwise
+    return SimpleNamespace(backbone=VARIANT, decoder="ham", decoder_embed_dim=512, num_classes=NCLS,
+                           drop_path_rate=0.15 if VARIANT == "DFormer-Large" else 0.1, aux_rate=0.0,
                            device=device, pretrained_model=None, bn_eps=1e-3, bn_momentum=0.1, background=255, precision=precision)
 
 
@@ -111,7 +113,42 @@ def cpu_reference_run(steps, warmup, batch=1):
     return batch / sec, sec * 1e3, cores, f"{steps} train steps (fwd+loss+bwd, fp32) of {VARIANT} {H}x{W} batch {batch} after {warmup} warm-up"
 
 
+def gpu_eager_port_run(steps, warmup, batch, precision):
+    """Context number asked for by SURVEY.md 8(d): the reference's algorithm as STOCK PyTorch eager ops on the same B200 (the
+    reference has no kernels of its own, so this is what its trainer would launch): the oracle port under autograd,
+    `torch.autocast(bf16)` for the bf16 row, `torch.optim.AdamW` for the update.  The port composes BatchNorm / LayerNorm /
+    bilinear resize from primitive ops, so it issues somewhat more launches than the reference's nn.Modules would."""
+    from oracle import dformer_oracle as O
+    import torch.nn as nn
+    from dformer_b200 import EncoderDecoder
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    m = EncoderDecoder(cfg_for("fp32", "cpu"), norm_layer=nn.BatchNorm2d)
+    P = {k: v.detach().clone().to(dev) for k, v in m.state_dict().items()}
+    train = [P[k].requires_grad_(True) for k, _ in m.named_parameters() if not k.startswith("encoder_backbone.stem_e_fc")]
+    opt = torch.optim.AdamW(train, lr=6e-5, weight_decay=0.01)
+    rgb, hha, label = (t.to(dev) for t in synthetic(batch, "cpu", 0))
+    v = O.VARIANTS[VARIANT]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.reset_peak_memory_stats()
+    for it in range(warmup + steps):
+        if it == warmup:
+            torch.cuda.synchronize()
+            e0.record()
+        bases = O.draw_bases(batch).to(dev, non_blocking=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(precision == "bf16")):
+            loss, _ = O.forward(P, rgb, hha, bases, v["dims"], v["depths"], label=label, training=True)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return batch / (ms * 1e-3), ms, torch.cuda.max_memory_allocated() / 2 ** 30
+
+
 def main():
+    global VARIANT, NCLS, H, W
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -121,16 +158,45 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
+    ap.add_argument("--variant", default=VARIANT, help="other BASELINE.json configs (use with --quick): DFormer-Tiny/Small/Base/Large")
+    ap.add_argument("--size", default=f"{H}x{W}", help="HxW of the synthetic batch (480x480 for the SUNRGBD-shaped config)")
+    ap.add_argument("--classes", type=int, default=NCLS)
+    ap.add_argument("--torch-eager-gpu", action="store_true", help="context line (not a bench arm): the oracle port as stock PyTorch eager "
+                    "ops on cuda:0, bf16-autocast and fp32, same workload")
     ap.add_argument("--quick", action="store_true", help="profiling aid: print only the device-timed ms/step and exit (not a bench line)")
     args = ap.parse_args()
+    custom = (args.variant, args.size, args.classes) != (VARIANT, f"{H}x{W}", NCLS)
+    VARIANT, NCLS = args.variant, args.classes
+    H, W = (int(t) for t in args.size.split("x"))
+    if custom and not (args.quick or args.torch_eager_gpu):
+        ap.error("--variant/--size/--classes select a side configuration: combine them with --quick (ms/step only); the bench line "
+                 "is defined on the headline configuration")
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    if args.torch_eager_gpu:
+        if rank != 0:
+            return
+        rows = {}
+        for prec in ("bf16", "fp32"):
+            try:
+                val, ms, gib = gpu_eager_port_run(args.steps, args.warmup, args.batch, prec)
+                rows[prec] = {"value": val, "unit": "images/s", "ms_per_step": ms, "peak_mem_gib": gib}
+            except Exception as e:  # noqa: BLE001  (e.g. out of memory for the fp32 row at a large batch)
+                rows[prec] = {"value": None, "unit": "images/s", "ms_per_step": None, "error": f"{type(e).__name__}: {str(e)[:200]}"}
+            torch.cuda.empty_cache()
+        print(json.dumps({"impl": "reference-port, stock PyTorch eager on cuda:0", "metric": METRIC, "value": rows["bf16"]["value"],
+                          "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": rows["bf16"]["ms_per_step"],
+                          "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": f"{VARIANT} {H}x{W} {NCLS}cls train step (fwd+loss+bwd+torch.optim.AdamW), batch {args.batch}, "
+                                                 "oracle port under torch.autocast(bf16), eager launches, drop_path 0"},
+                          "bf16_autocast": rows["bf16"], "fp32_torch_defaults": rows["fp32"]}))
+        return
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+        steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))        # ~1.2 s per step on 16 cores: bounded
         val, ms, cores, sample = cpu_reference_run(steps, warmup)
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
                           "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -197,7 +263,8 @@ def main():
     if args.quick:
         sampler.stop_flag = True
         if rank == 0:
-            print(json.dumps({"quick": True, "ms_per_step": ms, "skip": os.environ.get("DFB200_PROFILE_SKIP", "")}))
+            print(json.dumps({"quick": True, "workload": f"{VARIANT} {H}x{W} {NCLS}cls batch {B}/GPU x {world} GPU, {args.precision}",
+                              "ms_per_step": ms, "images_per_s": world * B / (ms * 1e-3), "skip": os.environ.get("DFB200_PROFILE_SKIP", "")}))
         sys.stdout.flush()
         os._exit(0)
     # ---- end-to-end: pinned host inputs -> H2D, step, loss -> D2H, every step.
@@ -366,7 +433,7 @@ def main():
     }
     if n == 1 and not args.no_cpu_baseline:
         try:
-            val, cms, cores, sample = cpu_reference_run(steps=1, warmup=1)
+            val, cms, cores, sample = cpu_reference_run(steps=8, warmup=1)          # ~10 s of CPU work
             out["cpu_baseline"] = {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample, "ms_per_step": cms}
         except Exception as e:  # noqa: BLE001
             out["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": f"failed: {e}"}

@@ -92,3 +92,28 @@ class GraphedTrainStep:
             return self.loss
         self.loss = self._eager()
         return self.loss
+
+
+# ---------------------------------------------------------------------------------------------- checkpoints (row N1)
+def save_checkpoint(path, model, optimizer, epoch, iteration):
+    """`Engine.save_checkpoint` (utils/engine/engine.py:101-129): one `torch.save` of
+    `{"model": state_dict without a DDP "module." prefix, "optimizer": optimizer.state_dict(), "epoch", "iteration"}`.
+    With `optim.FusedAdamW` the optimizer entry is in `torch.optim.AdamW`'s own format and numbering, so the file restores
+    into the reference's trainer and vice versa."""
+    from collections import OrderedDict
+    sd = OrderedDict((k[7:] if k.split(".")[0] == "module" else k, v.detach().cpu()) for k, v in model.state_dict().items())
+    torch.save({"model": sd, "optimizer": optimizer.state_dict(), "epoch": epoch, "iteration": iteration}, path)
+
+
+def restore_checkpoint(path, model, optimizer=None):
+    """`Engine.restore_checkpoint` (utils/engine/engine.py:159-186): loads on the CPU first, restores the model strictly and the
+    optimizer, and returns `(epoch + 1, iteration)` -- the epoch to CONTINUE with, as the reference sets it.  Files whose model
+    keys carry the DDP "module." prefix (the reference's `load_model(..., is_restore=True)` view) are accepted as well."""
+    tmp = torch.load(path, map_location=torch.device("cpu"), weights_only=False)
+    sd = tmp["model"]
+    if sd and all(k.startswith("module.") for k in sd):
+        sd = {k[7:]: v for k, v in sd.items()}
+    model.load_state_dict(sd, strict=True)
+    if optimizer is not None:
+        optimizer.load_state_dict(tmp["optimizer"])
+    return tmp["epoch"] + 1, tmp["iteration"]

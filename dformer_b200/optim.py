@@ -34,15 +34,16 @@ class FusedAdamW:
                     nodecay_ids.update(id(p) for p in (sub.weight, sub.bias) if p is not None)
             wd = torch.zeros_like(flat)
             lrm = torch.zeros_like(flat)
+            decays = torch.zeros_like(flat)
             for s in layout.slots.values():
                 sl = slice(s.offset, s.offset + s.numel)
                 if not s.param.requires_grad:
                     continue
                 if id(s.param) in decay_ids:
-                    wd[sl], lrm[sl] = weight_decay, 1.0
+                    wd[sl], lrm[sl], decays[sl] = weight_decay, 1.0, 1.0
                 elif id(s.param) in nodecay_ids or not reference_groups:
                     lrm[sl] = 1.0
-            self.state.append(dict(mod=mod, m=torch.zeros_like(flat), v=torch.zeros_like(flat), wd=wd, lrm=lrm))
+            self.state.append(dict(mod=mod, m=torch.zeros_like(flat), v=torch.zeros_like(flat), wd=wd, lrm=lrm, decays=decays))
 
     def set_lr(self, lr):
         """Update the learning rate read by (possibly graph-captured) optimizer launches."""
@@ -61,7 +62,7 @@ class FusedAdamW:
         lr = self.lr if lr is None else lr
         dev = self.state[0]["m"].device if self.state else None
         if self._dyn is None and dev is not None:
-            self._dyn = torch.tensor([lr, 0.0], device=dev, dtype=torch.float32)
+            self._dyn = torch.tensor([lr, float(self.step_count - 1)], device=dev, dtype=torch.float32)
         if self._dyn is not None:
             if not torch.cuda.is_current_stream_capturing() and lr != self.lr:
                 self._dyn[0] = lr
@@ -74,6 +75,84 @@ class FusedAdamW:
                 continue
             K.adamw(flat, arena.buf, st["m"], st["v"], lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count,
                     wd_arr=st["wd"], lr_arr=st["lrm"], dyn=self._dyn)
+
+
+    # ------------------------------------------------------------------ checkpoint interchange with the reference
+    def _reference_groups(self):
+        """The two parameter lists `group_weight` hands to `torch.optim.AdamW` (utils/init_func.py:26-70, utils/train.py:207-216),
+        in its module-traversal order: [weights that decay], [biases + BatchNorm affine parameters]."""
+        decay, no_decay = [], []
+        for sub in self.model.modules():
+            if isinstance(sub, (nn.Linear, nn.Conv1d, nn.Conv2d, nn.Conv3d, nn.ConvTranspose2d, nn.ConvTranspose3d)):
+                decay.append(sub.weight)
+                if sub.bias is not None:
+                    no_decay.append(sub.bias)
+            elif isinstance(sub, (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d, nn.GroupNorm, nn.LayerNorm)):
+                no_decay.extend(p for p in (sub.weight, sub.bias) if p is not None)
+        return decay, no_decay
+
+    def _moment_views(self):
+        """id(parameter) -> (exp_avg view, exp_avg_sq view, updated?) inside the flat moment buffers."""
+        views = {}
+        for st in self.state:
+            updated = (st["lrm"] != 0).cpu()
+            for s in st["mod"]._plan.layout.slots.values():
+                sl = slice(s.offset, s.offset + s.numel)
+                views[id(s.param)] = (st["m"][sl].view(s.param.shape), st["v"][sl].view(s.param.shape), bool(updated[s.offset]))
+        return views
+
+    def state_dict(self):
+        """A `torch.optim.AdamW.state_dict()` of the optimizer the reference builds (same parameter numbering, same two groups), so
+        that `Engine.save_checkpoint` / `restore_checkpoint` files (utils/engine/engine.py:101-186) move between the two
+        implementations.  Like torch, only parameters that have been stepped carry state; the never-used `stem_e_fc*` layers
+        (no gradient, `DFormer.py:202-203`) and frozen parameters carry none."""
+        decay, no_decay = self._reference_groups()
+        skeleton = torch.optim.AdamW([dict(params=decay, lr=self.lr), dict(params=no_decay, weight_decay=0.0, lr=self.lr)], lr=self.lr,
+                                     betas=self.betas, eps=self.eps, weight_decay=self.weight_decay).state_dict()
+        views = self._moment_views()
+        state = {}
+        if self.step_count > 0:
+            for idx, p in enumerate(decay + no_decay):
+                mv = views.get(id(p))
+                if mv is not None and mv[2] and p.requires_grad:
+                    state[idx] = {"step": torch.tensor(float(self.step_count)), "exp_avg": mv[0].clone(), "exp_avg_sq": mv[1].clone()}
+        skeleton["state"] = state
+        return skeleton
+
+    def load_state_dict(self, sd):
+        """Inverse of `state_dict()`; also accepts the state of a stock `torch.optim.AdamW` built with the reference's groups."""
+        decay, no_decay = self._reference_groups()
+        params = decay + no_decay
+        saved = [i for g in sd["param_groups"] for i in g["params"]]
+        if len(saved) != len(params):
+            raise ValueError(f"optimizer state has {len(saved)} parameters, the model's reference groups have {len(params)}")
+        views = self._moment_views()
+        for st in self.state:
+            st["m"].zero_()
+            st["v"].zero_()
+        steps = set()
+        for pos, idx in enumerate(saved):
+            e = sd["state"].get(idx)
+            if e is None:
+                continue
+            mv = views.get(id(params[pos]))
+            if mv is None:
+                raise ValueError(f"optimizer state for parameter {idx}, which is not on the hot path")
+            if tuple(e["exp_avg"].shape) != tuple(mv[0].shape):
+                raise ValueError(f"optimizer state {idx}: shape {tuple(e['exp_avg'].shape)} != parameter shape {tuple(mv[0].shape)}")
+            mv[0].copy_(e["exp_avg"])
+            mv[1].copy_(e["exp_avg_sq"])
+            steps.add(int(float(e["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"per-parameter step counts differ ({sorted(steps)}); the fused optimizer keeps one")
+        self.step_count = steps.pop() if steps else 0
+        g0 = sd["param_groups"][0]
+        self.lr, self.betas, self.eps, self.weight_decay = g0["lr"], tuple(g0["betas"]), g0["eps"], g0["weight_decay"]
+        for st in self.state:                       # the per-element decay array follows the restored coefficient
+            st["wd"].copy_(st["decays"] * self.weight_decay)
+        if self._dyn is not None:
+            self._dyn[0] = self.lr
+            self._dyn[1] = float(self.step_count)
 
 
 class WarmUpPolyLR:

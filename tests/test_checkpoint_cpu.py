@@ -1,0 +1,84 @@
+"""Row N1 host logic: the fused optimizer's state dict is `torch.optim.AdamW`'s (reference numbering: `group_weight`,
+utils/init_func.py:26-70) and checkpoints keep the reference's dict format (utils/engine/engine.py:101-186)."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.nn as nn
+
+
+def _model(variant="DFormer-Tiny"):
+    from dformer_b200 import EncoderDecoder
+    cfg = SimpleNamespace(backbone=variant, decoder="ham", decoder_embed_dim=512, num_classes=40, drop_path_rate=0.0, aux_rate=0.0,
+                          device="cpu", pretrained_model=None, bn_eps=1e-3, bn_momentum=0.1, background=255, precision="fp32")
+    return EncoderDecoder(cfg, norm_layer=nn.BatchNorm2d)
+
+
+def _group_weight(module):
+    """The reference rule restated for the test (utils/init_func.py:26-70)."""
+    decay, no_decay = [], []
+    for m in module.modules():
+        if isinstance(m, (nn.Linear, nn.Conv2d)):
+            decay.append(m.weight)
+            if m.bias is not None:
+                no_decay.append(m.bias)
+        elif isinstance(m, (nn.BatchNorm2d, nn.LayerNorm, nn.GroupNorm)):
+            no_decay += [m.weight, m.bias]
+    return [dict(params=decay, lr=1.0), dict(params=no_decay, weight_decay=0.0, lr=1.0)]
+
+
+def test_fused_adamw_state_dict_is_the_reference_optimizers():
+    from dformer_b200.optim import FusedAdamW
+    torch.manual_seed(0)
+    m = _model()
+    opt = FusedAdamW(m, lr=3e-4, weight_decay=0.02)
+    assert opt.state_dict()["state"] == {}                                   # nothing stepped yet, like torch
+    for st in opt.state:
+        st["m"].normal_()
+        st["v"].uniform_()
+    opt.step_count = 7
+    sd = opt.state_dict()
+    groups = _group_weight(m)
+    stock = torch.optim.AdamW(groups, lr=1.0, weight_decay=0.5)
+    assert [g["params"] for g in sd["param_groups"]] == [g["params"] for g in stock.state_dict()["param_groups"]]
+    assert set(sd["param_groups"][0]) == set(stock.state_dict()["param_groups"][0])
+    stock.load_state_dict(sd)
+    assert stock.param_groups[0]["lr"] == 3e-4 and stock.param_groups[0]["weight_decay"] == 0.02 and stock.param_groups[1]["weight_decay"] == 0.0
+    params = groups[0]["params"] + groups[1]["params"]
+    names = {id(p): k for k, p in m.named_parameters()}
+    with_state = {names[id(params[i])] for i in sd["state"]}
+    # every Linear / conv / BatchNorm parameter on the hot path has moments; the unused stem_e_fc layers never get a gradient
+    assert not any("stem_e_fc" in k or "layer_scale" in k or ".norm" in k for k in with_state)
+    assert len(with_state) == len(params) - 4
+    for i, e in sd["state"].items():
+        assert e["exp_avg"].shape == params[i].shape and float(e["step"]) == 7.0
+    # and back: a fresh fused optimizer restored from the stock optimizer's state holds the same moments
+    opt2 = FusedAdamW(_model(), lr=1.0, weight_decay=0.0)
+    opt2.load_state_dict(stock.state_dict())
+    assert (opt2.step_count, opt2.lr, opt2.weight_decay) == (7, 3e-4, 0.02)
+    for a, b in zip(opt.state, opt2.state):
+        live = a["lrm"] != 0
+        assert torch.equal(a["m"] * live, b["m"]) and torch.equal(a["v"] * live, b["v"]) and torch.equal(a["wd"], b["wd"])
+
+
+def test_checkpoint_file_has_the_reference_format(tmp_path):
+    from dformer_b200.engine import restore_checkpoint, save_checkpoint
+    from dformer_b200.optim import FusedAdamW
+    torch.manual_seed(1)
+    m = _model()
+    opt = FusedAdamW(m)
+    path = str(tmp_path / "epoch-9.pt")
+    save_checkpoint(path, nn.ModuleDict({"module": m}), opt, epoch=9, iteration=4321)      # DDP-style "module." prefix is stripped
+    ck = torch.load(path, weights_only=False)
+    assert list(ck) == ["model", "optimizer", "epoch", "iteration"] and (ck["epoch"], ck["iteration"]) == (9, 4321)
+    assert list(ck["model"]) == list(m.state_dict())
+    torch.manual_seed(2)
+    m2 = _model()
+    assert restore_checkpoint(path, m2, FusedAdamW(m2)) == (10, 4321)                       # epoch to continue with (engine.py:178)
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    # the reference's restore view (keys with "module.") is accepted; a foreign optimizer state is refused
+    torch.save({"model": {"module." + k: v for k, v in ck["model"].items()}, "optimizer": ck["optimizer"], "epoch": 0, "iteration": 0}, path)
+    assert restore_checkpoint(path, _model()) == (1, 0)
+    bad = dict(ck["optimizer"], param_groups=[dict(ck["optimizer"]["param_groups"][0], params=[0, 1, 2])])
+    with pytest.raises(ValueError, match="parameters"):
+        FusedAdamW(m2).load_state_dict(bad)

@@ -69,3 +69,70 @@ def test_staged_input_prefetch_feeds_the_same_step():
     # the three batches differ by > 2e-3 even at the default init (layer scales 1e-6)
     assert staged == pytest.approx(direct, abs=4e-4)
     assert min(abs(a - b) for i, a in enumerate(direct) for b in direct[i + 1:]) > 1.2e-3
+
+
+def test_checkpoint_restores_the_trajectory_and_interchanges_with_torch_adamw(tmp_path):
+    """Row N1: `save_checkpoint` / `restore_checkpoint` (utils/engine/engine.py:101-186) with the fused optimizer.  After two
+    training steps the file is restored (a) into a fresh model + FusedAdamW and (b) into a fresh model driven by the optimizer the
+    reference builds -- stock `torch.optim.AdamW` over `group_weight`'s two groups (utils/init_func.py:26-70) -- and all three take
+    a third step on the SAME gradients: identical parameters, with `layer_scale_*` / LayerNorm / `stem_e_fc*` untouched."""
+    from dformer_b200.engine import restore_checkpoint, save_checkpoint
+    from dformer_b200.optim import FusedAdamW
+    rgb, hha = torch.randn(2, 3, 64, 96, device="cuda"), torch.randn(2, 3, 64, 96, device="cuda")
+    lab = torch.randint(0, 40, (2, 64, 96), device="cuda")
+    bases = torch.rand(2, 512, 64, device="cuda")
+
+    def make(seed):
+        m = _build(seed)
+        m.decode_head.injected_bases = bases
+        return m
+
+    def backward(m):
+        loss, _ = m(rgb, hha, lab)
+        loss.backward()
+
+    m = make(0)
+    init = {k: v.detach().clone() for k, v in m.named_parameters()}
+    opt = FusedAdamW(m, lr=1e-3, weight_decay=0.05)
+    for _ in range(2):
+        backward(m)
+        opt.step()
+        opt.zero_grad()
+    path = str(tmp_path / "epoch-4.pt")
+    save_checkpoint(path, m, opt, epoch=4, iteration=2)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck) == {"model", "optimizer", "epoch", "iteration"} and list(ck["model"]) == list(m.state_dict())
+    # (a) fresh model + fused optimizer
+    m2 = make(1)
+    opt2 = FusedAdamW(m2, lr=1.0, weight_decay=0.0)
+    assert restore_checkpoint(path, m2, opt2) == (5, 2)
+    assert (opt2.step_count, opt2.lr, opt2.weight_decay) == (2, 1e-3, 0.05)
+    # (b) fresh model + the reference's stock optimizer
+    m3 = make(2)
+    decay, no_decay = FusedAdamW(m3)._reference_groups()
+    opt3 = torch.optim.AdamW([dict(params=decay, lr=1.0), dict(params=no_decay, weight_decay=0.0, lr=1.0)], lr=1.0, weight_decay=0.3)
+    assert restore_checkpoint(path, m3, opt3) == (5, 2)
+    # third step, same gradients everywhere
+    for mm in (m, m2, m3):
+        backward(mm)
+    torch.cuda.synchronize()
+    for src, dst in zip((m.encoder_backbone, m.decode_head), (m2.encoder_backbone, m2.decode_head)):
+        dst._last_arena.buf.copy_(src._last_arena.buf)                # the fused optimizer reads the gradient arena
+    g1 = {k: p.grad for k, p in m.named_parameters()}
+    for k, p in m3.named_parameters():
+        p.grad = None if g1[k] is None else g1[k].detach().clone()    # the stock optimizer reads p.grad
+    opt.step()
+    opt2.step()
+    opt3.step()
+    torch.cuda.synchronize()
+    p1, p2, p3 = (dict(mm.named_parameters()) for mm in (m, m2, m3))
+    moved = 0
+    for k in p1:
+        torch.testing.assert_close(p2[k], p1[k], rtol=0, atol=0, msg=lambda s, k=k: f"{k}: {s}")
+        torch.testing.assert_close(p3[k], p1[k], rtol=1e-5, atol=1e-6, msg=lambda s, k=k: f"{k}: {s}")
+        frozen = "layer_scale" in k or ".norm" in k or "stem_e_fc" in k
+        if frozen:
+            assert torch.equal(p1[k], init[k]), k                      # the reference's optimizer never sees these
+        else:
+            moved += int(not torch.equal(p1[k], init[k]))
+    assert moved > 300
