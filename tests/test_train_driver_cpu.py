@@ -82,3 +82,39 @@ def test_checkpoint_file_has_the_reference_format(tmp_path):
     bad = dict(ck["optimizer"], param_groups=[dict(ck["optimizer"]["param_groups"][0], params=[0, 1, 2])])
     with pytest.raises(ValueError, match="parameters"):
         FusedAdamW(m2).load_state_dict(bad)
+
+
+# ---------------------------------------------------------------- pinned to the unmodified reference (oracle/make_golden_optim.py)
+def _gold():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "optim.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("variant,ncls", [("DFormer-Tiny", 40), ("DFormer-Small", 40), ("DFormer-Base", 37), ("DFormer-Large", 40)])
+def test_optimizer_groups_are_the_references_group_weight(variant, ncls):
+    """Same parameters, same order (= `torch.optim.AdamW` state numbering) as `group_weight` on the reference model; the fused
+    optimizer's per-element decay / update masks agree with the two groups."""
+    from dformer_b200.optim import FusedAdamW
+    g = _gold()["groups"][variant]
+    m = _model(variant)                       # parameter names / groups do not depend on the class count
+    opt = FusedAdamW(m, weight_decay=0.01)
+    names = {id(p): k for k, p in m.named_parameters()}
+    decay, no_decay = opt._reference_groups()
+    assert [names[id(p)] for p in decay] == g["decay"] and [names[id(p)] for p in no_decay] == g["no_decay"]
+    assert len(names) == g["n_parameters"] and g["no_decay_weight_decay"] == 0.0
+    in_decay, in_no_decay = set(g["decay"]), set(g["no_decay"])
+    for st in opt.state:
+        for s in st["mod"]._plan.layout.slots.values():
+            k = names[id(s.param)]
+            want = (0.01, 1.0) if k in in_decay else (0.0, 1.0) if k in in_no_decay else (0.0, 0.0)      # neither group: never updated
+            assert (float(st["wd"][s.offset]), float(st["lrm"][s.offset])) == pytest.approx(want), k
+
+
+def test_warmup_poly_lr_matches_the_reference_schedule():
+    from dformer_b200.optim import WarmUpPolyLR
+    for case in _gold()["lr"]:
+        pol = WarmUpPolyLR(case["start_lr"], case["lr_power"], case["total_iters"], case["warmup_steps"])
+        for it, want in case["samples"]:
+            assert pol.get_lr(it) == want, (case, it)
