@@ -1,5 +1,5 @@
-"""Stage-by-stage parity dump of the CUDA model against the CPU/GPU oracle (debug aid, GPU box).
-usage: python tools/debug_model.py [variant] [B] [H] [W] [fp32|bf16] [train|eval]"""
+"""Stage-by-stage parity dump of the CUDA model against the CPU/GPU oracle (debug aid, GPU box; lives under tests/ because it executes the oracle).
+usage: python tests/debug_model.py [variant] [B] [H] [W] [fp32|bf16] [train|eval]"""
 import json
 import os
 import sys

@@ -69,3 +69,21 @@ def test_struct_layout_matches_header():
         for part in stmt.split(","):
             names.append(part.replace("*", " ").split()[-1])
     assert names == [f[0] for f in L.GemmArgs._fields_]
+
+
+def test_only_the_checkers_touch_the_oracle_and_nothing_shipped_reads_the_reference_tree():
+    """Task rule: only tests/, `__graft_entry__.smoke()` and bench.py's CPU-baseline / reference legs may import `oracle/`; nothing
+    that runs on the GPU box (package, tools, bench, smoke) may read /root/reference."""
+    import glob
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    product = glob.glob(os.path.join(root, "dformer_b200", "**", "*.py"), recursive=True) + glob.glob(os.path.join(root, "tools", "*.py"))
+    assert len(product) > 15
+    imp = re.compile(r"^\s*(from|import)\s+oracle\b", re.M)
+    for f in product:
+        src = open(f).read()
+        assert not imp.search(src), f"{f} imports the oracle"
+        assert "/root/reference" not in src, f"{f} names the reference tree"
+    for f in ("bench.py", "__graft_entry__.py"):
+        assert "/root/reference" not in open(os.path.join(root, f)).read(), f
