@@ -209,6 +209,65 @@ def test_multi_scale_flip_evaluation_matches_the_reference_loop():
     assert not m.training
 
 
+def test_sliding_window_inference_matches_the_reference_loop():
+    """`evaluation.slide_inference` against `slide_inference` of utils/val_mm.py:257-321 restated with torch ops around the SAME model:
+    overlapping windows with a shifted last row / column (96x160 image, 64x96 crop, stride 2/3), and the small-image branch that
+    resamples the input up to the crop first.  Then the `sliding=True` branch of `evaluate_msf` (:372-375, :387-390) with flip."""
+    import torch.nn.functional as F
+    from types import SimpleNamespace
+
+    from dformer_b200.evaluation import multi_scale_predict, scaled_size, slide_inference
+    ncls = 40
+    m, _ = build("DFormer-Tiny", ncls, "fp32", 6, train=False)
+    B = 2
+    m.decode_head.injected_bases = torch.rand(B, 512, 64, generator=torch.Generator().manual_seed(2)).cuda()
+
+    def reference(imgs, modal_xs, cfg):
+        h_crop, w_crop = cfg.eval_crop_size
+        if h_crop > imgs.shape[-2] or w_crop > imgs.shape[-1]:
+            imgs = F.interpolate(imgs, size=(h_crop, w_crop), mode="bilinear", align_corners=True)
+            modal_xs = F.interpolate(modal_xs, size=(h_crop, w_crop), mode="bilinear", align_corners=True)
+        h_stride, w_stride = int(cfg.eval_stride_rate * h_crop), int(cfg.eval_stride_rate * w_crop)
+        bs, _, h_img, w_img = imgs.shape
+        h_grids = max(h_img - h_crop + h_stride - 1, 0) // h_stride + 1
+        w_grids = max(w_img - w_crop + w_stride - 1, 0) // w_stride + 1
+        preds = imgs.new_zeros((bs, ncls, h_img, w_img))
+        count_mat = imgs.new_zeros((bs, 1, h_img, w_img))
+        n = 0
+        for h_idx in range(h_grids):
+            for w_idx in range(w_grids):
+                y2, x2 = min(h_idx * h_stride + h_crop, h_img), min(w_idx * w_stride + w_crop, w_img)
+                y1, x1 = max(y2 - h_crop, 0), max(x2 - w_crop, 0)
+                with torch.no_grad():
+                    lg = m(imgs[:, :, y1:y2, x1:x2].contiguous(), modal_xs[:, :, y1:y2, x1:x2].contiguous())
+                preds += F.pad(lg, (int(x1), int(preds.shape[3] - x2), int(y1), int(preds.shape[2] - y2)))
+                count_mat[:, :, y1:y2, x1:x2] += 1
+                n += 1
+        assert (count_mat == 0).sum() == 0
+        return preds / count_mat, n
+
+    cfg = SimpleNamespace(eval_crop_size=(64, 96), eval_stride_rate=2 / 3, num_classes=ncls)
+    rgb, hha, _, _ = make_inputs(B, 96, 160, ncls, seed=6)
+    rgb, hha = rgb.cuda(), hha.cuda()
+    ref, n = reference(rgb, hha, cfg)
+    assert n == 4                                                               # 2 x 2 windows, both last ones shifted back
+    torch.testing.assert_close(slide_inference(m, rgb, hha, cfg), ref, rtol=1e-3, atol=1e-4)
+    small_rgb, small_hha = rgb[:, :, :32, :64].contiguous(), hha[:, :, :32, :64].contiguous()
+    ref_small, n = reference(small_rgb, small_hha, cfg)
+    assert n == 1 and ref_small.shape[-2:] == (64, 96)
+    torch.testing.assert_close(slide_inference(m, small_rgb, small_hha, cfg), ref_small, rtol=1e-3, atol=1e-4)
+    # evaluate_msf with sliding=True and flip
+    H, W = 96, 160
+    acc = multi_scale_predict(m, rgb, hha, (1.0,), flip=True, sliding_config=cfg)
+    nh, nw = scaled_size(H, W, 1.0)
+    imgs = [F.interpolate(t, size=(nh, nw), mode="bilinear", align_corners=True) for t in (rgb, hha)]
+    want = F.interpolate(reference(imgs[0], imgs[1], cfg)[0], size=(H, W), mode="bilinear", align_corners=True).softmax(dim=1)
+    imgs = [torch.flip(t, dims=(3,)) for t in imgs]
+    lg = torch.flip(reference(imgs[0], imgs[1], cfg)[0], dims=(3,))
+    want += F.interpolate(lg, size=(H, W), mode="bilinear", align_corners=True).softmax(dim=1)
+    torch.testing.assert_close(acc, want, rtol=1e-3, atol=1e-4)
+
+
 def test_eval_bn_folding_is_transparent():
     """Inference folds the conv -> BN(eval) pairs of the stems and the head into their GEMMs (row N4): same logits as the unfolded path,
     and the fp32 parameters / running statistics are left untouched."""

@@ -118,3 +118,28 @@ def test_warmup_poly_lr_matches_the_reference_schedule():
         pol = WarmUpPolyLR(case["start_lr"], case["lr_power"], case["total_iters"], case["warmup_steps"])
         for it, want in case["samples"]:
             assert pol.get_lr(it) == want, (case, it)
+
+
+# ---------------------------------------------------------------- sliding-window bookkeeping (row N3, utils/val_mm.py:287-318)
+@pytest.mark.parametrize("h_img,w_img,crop,rate", [(480, 640, (480, 640), 2 / 3), (96, 160, (64, 96), 2 / 3), (100, 100, (64, 64), 0.5),
+                                                   (64, 64, (64, 96), 2 / 3), (65, 97, (64, 96), 1.0), (300, 200, (32, 32), 0.75)])
+def test_slide_windows_and_counts_match_the_reference_bookkeeping(h_img, w_img, crop, rate):
+    from dformer_b200.evaluation import slide_counts, slide_windows
+    h_crop, w_crop = crop
+    h_stride, w_stride = int(rate * h_crop), int(rate * w_crop)                  # the reference loop, restated
+    h_grids = max(h_img - h_crop + h_stride - 1, 0) // h_stride + 1
+    w_grids = max(w_img - w_crop + w_stride - 1, 0) // w_stride + 1
+    count = torch.zeros(h_img, w_img)
+    want = []
+    for h_idx in range(h_grids):
+        for w_idx in range(w_grids):
+            y1, x1 = h_idx * h_stride, w_idx * w_stride
+            y2, x2 = min(y1 + h_crop, h_img), min(x1 + w_crop, w_img)
+            y1, x1 = max(y2 - h_crop, 0), max(x2 - w_crop, 0)
+            want.append((y1, y2, x1, x2))
+            count[y1:y2, x1:x2] += 1
+    wins = slide_windows(h_img, w_img, crop, rate)
+    assert wins == want
+    rows, cols = slide_counts(h_img, w_img, wins)
+    assert torch.equal(torch.tensor(rows, dtype=torch.float32)[:, None] * torch.tensor(cols, dtype=torch.float32)[None, :], count)
+    assert count.min() >= 1
