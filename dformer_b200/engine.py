@@ -117,3 +117,80 @@ def restore_checkpoint(path, model, optimizer=None):
     if optimizer is not None:
         optimizer.load_state_dict(tmp["optimizer"])
     return tmp["epoch"] + 1, tmp["iteration"]
+
+
+# ---------------------------------------------------------------------------------------------- training driver (row N1)
+def is_eval(epoch, config):
+    """utils/train.py:60-61."""
+    return epoch > int(config.checkpoint_start_epoch) or epoch == 1 or epoch % 10 == 0
+
+
+class CheckpointKeeper:
+    """`Engine.save_and_link_checkpoint` (utils/engine/engine.py:136-157) without the log-directory symlinks: checkpoints are named
+    `epoch-{epoch}_miou_{miou}.pt`, the five best by metric are kept.  (The reference tries to delete the sixth under a `.pth` name
+    that was never written, so its files pile up; here the file that falls out of the top five is removed.)"""
+
+    def __init__(self, checkpoint_dir, keep=5):
+        self.dir, self.keep, self.state = checkpoint_dir, keep, []
+
+    def path(self, epoch, metric):
+        import os
+        return os.path.join(self.dir, f"epoch-{epoch}_miou_{metric}.pt")
+
+    def save(self, model, optimizer, epoch, iteration, metric):
+        import os
+        os.makedirs(self.dir, exist_ok=True)
+        self.state.append({"epoch": epoch, "metric": metric})
+        self.state.sort(key=lambda x: x["metric"], reverse=True)
+        path = self.path(epoch, metric)
+        save_checkpoint(path, model, optimizer, epoch, iteration)
+        if len(self.state) > self.keep:
+            worst = self.state.pop()
+            try:
+                os.remove(self.path(worst["epoch"], worst["metric"]))
+            except OSError:
+                pass
+        return path
+
+
+def train(runner, optimizer, config, batches, lr_policy, evaluate_fn=None, keeper=None, model=None, start_epoch=1, log=None):
+    """The epoch / iteration loop of utils/train.py:290-470 around a step runner (normally `GraphedTrainStep`).
+
+    * epochs run from `start_epoch` (what `restore_checkpoint` returned) to `config.nepochs` inclusive, `config.niters_per_epoch`
+      iterations each; `batches(epoch)` yields the epoch's `(rgb, modal_x, label)` triples (pinned host or device tensors);
+    * the learning rate follows the reference's order of operations (:352-356): the step runs first, then the rate for iteration
+      `(epoch - 1) * niters + idx` is installed -- so it takes effect one step later and the very first step uses the optimizer's
+      construction-time rate, exactly like the reference;
+    * after the epochs selected by `is_eval` (:60-61) `evaluate_fn(epoch)` returns the mIoU; a new best is checkpointed through
+      `keeper` (:405-416) with the iteration index of the epoch's last step (`engine.update_iteration`, :310).
+    Returns `(best_miou, history)` with one `{"epoch", "loss", "lr"[, "miou"]}` entry per epoch; the loss is read back to the host
+    once per epoch (mean of the per-step device losses), not per step."""
+    import torch as _torch
+    n = int(config.niters_per_epoch)
+    best, history = 0.0, []
+    lr = optimizer.lr if hasattr(optimizer, "lr") else None
+    for epoch in range(start_epoch, int(config.nepochs) + 1):
+        if model is not None:
+            model.train()
+        it = iter(batches(epoch))
+        total = None
+        idx = -1
+        for idx in range(n):
+            rgb, modal_x, label = next(it)
+            loss = runner.step(rgb, modal_x, label)
+            total = loss.detach().clone() if total is None else total + loss.detach()
+            lr = lr_policy.get_lr((epoch - 1) * n + idx)
+            optimizer.set_lr(lr)
+        entry = {"epoch": epoch, "loss": float(total / n) if total is not None else float("nan"), "lr": lr}
+        if evaluate_fn is not None and is_eval(epoch, config):
+            with _torch.no_grad():
+                miou = float(evaluate_fn(epoch))
+            entry["miou"] = miou
+            if miou > best:
+                best = miou
+                if keeper is not None:
+                    keeper.save(model if model is not None else runner.model, optimizer, epoch, idx, miou)
+        history.append(entry)
+        if log is not None:
+            log(entry)
+    return best, history

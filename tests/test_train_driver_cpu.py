@@ -143,3 +143,57 @@ def test_slide_windows_and_counts_match_the_reference_bookkeeping(h_img, w_img, 
     rows, cols = slide_counts(h_img, w_img, wins)
     assert torch.equal(torch.tensor(rows, dtype=torch.float32)[:, None] * torch.tensor(cols, dtype=torch.float32)[None, :], count)
     assert count.min() >= 1
+
+
+# ---------------------------------------------------------------- epoch loop (row N1, utils/train.py:290-470) with fakes
+def test_training_loop_follows_the_reference_order_of_operations(tmp_path):
+    import os
+    from dformer_b200.engine import CheckpointKeeper, is_eval, restore_checkpoint, train
+    from dformer_b200.optim import WarmUpPolyLR
+
+    class Opt:                                       # stands in for FusedAdamW (lr, set_lr, state_dict)
+        def __init__(self):
+            self.lr = 6e-5
+
+        def set_lr(self, lr):
+            self.lr = lr
+
+        def state_dict(self):
+            return {"lr": self.lr}
+
+        def load_state_dict(self, sd):
+            self.lr = sd["lr"]
+
+    class Runner:
+        def __init__(self, opt):
+            self.opt, self.seen, self.model = opt, [], nn.Linear(2, 2)
+
+        def step(self, rgb, modal_x, label):
+            self.seen.append((int(rgb), self.opt.lr))
+            return torch.tensor(float(len(self.seen)))
+
+    cfg = SimpleNamespace(nepochs=23, niters_per_epoch=3, checkpoint_start_epoch=20)
+    pol = WarmUpPolyLR(6e-5, 0.9, cfg.nepochs * cfg.niters_per_epoch, 2 * cfg.niters_per_epoch)
+    opt = Opt()
+    run = Runner(opt)
+    mious = {1: 0.10, 10: 0.30, 20: 0.25, 21: 0.35, 22: 0.40, 23: 0.45}
+    evaluated = []
+
+    def evaluate_fn(epoch):
+        evaluated.append(epoch)
+        return mious[epoch]
+
+    keeper = CheckpointKeeper(str(tmp_path), keep=3)
+    best, hist = train(run, opt, cfg, lambda e: ((torch.tensor(e * 100 + i), None, None) for i in range(10)), pol, evaluate_fn, keeper)
+    assert evaluated == [e for e in range(1, 24) if is_eval(e, cfg)] == [1, 10, 20, 21, 22, 23]
+    assert best == 0.45 and len(hist) == 23 and hist[0]["miou"] == 0.10 and "miou" not in hist[1]
+    # order of operations: the first step runs at the construction-time rate, step k at the rate computed for iteration k - 1
+    assert [b for b, _ in run.seen[:4]] == [100, 101, 102, 200]
+    want = [6e-5] + [pol.get_lr(k) for k in range(len(run.seen) - 1)]
+    assert [lr for _, lr in run.seen] == want
+    assert hist[0]["loss"] == pytest.approx(2.0) and hist[-1]["lr"] == pol.get_lr(23 * 3 - 1)
+    # new bests at epochs 1, 10, 21, 22, 23 (20 was not a best); the three best files remain
+    assert sorted(os.listdir(tmp_path)) == sorted(f"epoch-{e}_miou_{mious[e]}.pt" for e in (21, 22, 23))
+    m2, o2 = nn.Linear(2, 2), Opt()
+    assert restore_checkpoint(keeper.path(23, 0.45), m2, o2) == (24, 2)                 # epoch + 1, index of the last iteration
+    assert all(torch.equal(a, b) for a, b in zip(m2.state_dict().values(), run.model.state_dict().values()))
