@@ -9,18 +9,28 @@ import torch
 
 
 class GraphedTrainStep:
-    def __init__(self, model, optimizer, rgb, modal_x, label, grad_sync=None, warmup=3, use_graph=True):
+    """`preserve_state=True` (default) snapshots parameters, optimizer moments / step counter and BatchNorm buffers before the
+    warm-up + capture passes and restores them afterwards, so building the runner (e.g. after `restore_checkpoint`) does not
+    advance the training trajectory by `warmup + 1` steps on the example batch."""
+
+    def __init__(self, model, optimizer, rgb, modal_x, label, grad_sync=None, warmup=3, use_graph=True, preserve_state=True):
         self.model, self.opt, self.sync = model, optimizer, grad_sync
         self.rgb, self.modal_x, self.label = rgb.clone(), modal_x.clone(), label.clone()
         head = model.decode_head
         ham = head.hamburger.ham
         B = rgb.shape[0]
-        self._bases_host = torch.empty((B * ham.S, ham.D, ham.R), dtype=torch.float32).pin_memory()
-        self._bases_dev = torch.empty_like(self._bases_host, device=rgb.device)
-        head.injected_bases = self._bases_dev
+        # two pinned host buffers for the per-step CPU draw of the NMF bases (ham_head.py:111), each guarded by the event of the
+        # H2D copy that last read it: the host runs many steps ahead of the GPU, so a single buffer would be overwritten while the
+        # previous step's asynchronous copy is still pending
+        self._bases_host = [torch.empty((B * ham.S, ham.D, ham.R), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._bases_evt = [None, None]
+        self._bases_slot = 0
+        self._bases_dev = torch.empty_like(self._bases_host[0], device=rgb.device)
+        self._head = head
         self.loss = None
         self.graph = None
         self._copy_stream = self._staging = self._staged = self._consumed = None
+        snap = self._snapshot() if preserve_state else None
         self._draw_bases()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -33,13 +43,55 @@ class GraphedTrainStep:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.loss = self._eager()
+        if snap is not None:
+            self._restore(snap)
+
+    # ---- state that warm-up / capture passes must not advance
+    def _snapshot(self):
+        model, opt = self.model, self.opt
+        snap = {"params": [p.detach().clone() for p in model.parameters()], "buffers": [b.detach().clone() for b in model.buffers()]}
+        if hasattr(opt, "state") and isinstance(opt.state, list):           # optim.FusedAdamW
+            snap["moments"] = [(st["m"].clone(), st["v"].clone()) for st in opt.state]
+            snap["step_count"] = opt.step_count
+        return snap
+
+    def _restore(self, snap):
+        model, opt = self.model, self.opt
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for p, q in zip(model.parameters(), snap["params"]):
+                p.copy_(q)
+            for b, q in zip(model.buffers(), snap["buffers"]):
+                b.copy_(q)
+            if "moments" in snap:
+                for st, (m, v) in zip(opt.state, snap["moments"]):
+                    st["m"].copy_(m)
+                    st["v"].copy_(v)
+                opt.step_count = snap["step_count"]
+                if getattr(opt, "_dyn", None) is not None:
+                    opt._dyn[1] = float(snap["step_count"])
+        torch.cuda.synchronize()
 
     def _draw_bases(self):
-        torch.rand(self._bases_host.shape, out=self._bases_host)     # same CPU RNG stream as the reference
-        self._bases_dev.copy_(self._bases_host, non_blocking=True)
+        k = self._bases_slot
+        self._bases_slot ^= 1
+        if self._bases_evt[k] is not None:
+            self._bases_evt[k].synchronize()         # the copy that last read this host buffer (two steps ago) has executed
+        host = self._bases_host[k]
+        torch.rand(host.shape, out=host)             # same CPU RNG stream as the reference
+        self._bases_dev.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._bases_evt[k] = ev
 
     def _eager(self):
-        loss, _ = self.model(self.rgb, self.modal_x, self.label)
+        # the injected bases belong to the training step only: evaluation / inference on the same model draws fresh ones
+        head = self._head
+        head.injected_bases = self._bases_dev
+        try:
+            loss, _ = self.model(self.rgb, self.modal_x, self.label)
+        finally:
+            head.injected_bases = None
         loss.backward()
         if self.sync is not None:
             self.sync.finish()
@@ -55,7 +107,7 @@ class GraphedTrainStep:
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.rgb.device)
             self._staging = tuple(torch.empty_like(t) for t in (self.rgb, self.modal_x, self.label, self._bases_dev))
-            self._bases_host2 = torch.empty_like(self._bases_host).pin_memory()
+            self._bases_host2 = torch.empty_like(self._bases_host[0]).pin_memory()
         cs = self._copy_stream
         if self._consumed is not None:
             cs.wait_event(self._consumed)              # the previous staged batch has been moved into the graph's input buffers
@@ -89,6 +141,8 @@ class GraphedTrainStep:
     def _run(self):
         if self.graph is not None:
             self.graph.replay()
+            if hasattr(self.opt, "step_count"):
+                self.opt.step_count += 1               # host mirror of the device-side step counter the replayed AdamW kernel advances
             return self.loss
         self.loss = self._eager()
         return self.loss
@@ -153,7 +207,7 @@ class CheckpointKeeper:
         return path
 
 
-def train(runner, optimizer, config, batches, lr_policy, evaluate_fn=None, keeper=None, model=None, start_epoch=1, log=None):
+def train(runner, optimizer, config, batches, lr_policy, evaluate_fn=None, keeper=None, model=None, start_epoch=1, log=None, is_main=None):
     """The epoch / iteration loop of utils/train.py:290-470 around a step runner (normally `GraphedTrainStep`).
 
     * epochs run from `start_epoch` (what `restore_checkpoint` returned) to `config.nepochs` inclusive, `config.niters_per_epoch`
@@ -163,9 +217,15 @@ def train(runner, optimizer, config, batches, lr_policy, evaluate_fn=None, keepe
       construction-time rate, exactly like the reference;
     * after the epochs selected by `is_eval` (:60-61) `evaluate_fn(epoch)` returns the mIoU; a new best is checkpointed through
       `keeper` (:405-416) with the iteration index of the epoch's last step (`engine.update_iteration`, :310).
+    * only the main rank writes checkpoints (`is_main`, default: rank 0 of the default process group; the reference guards with
+      `local_rank == 0`, :405); the other ranks wait at a barrier so nobody races ahead of a half-written file.
     Returns `(best_miou, history)` with one `{"epoch", "loss", "lr"[, "miou"]}` entry per epoch; the loss is read back to the host
     once per epoch (mean of the per-step device losses), not per step."""
     import torch as _torch
+    import torch.distributed as _dist
+    distributed = _dist.is_available() and _dist.is_initialized()
+    if is_main is None:
+        is_main = (not distributed) or _dist.get_rank() == 0
     n = int(config.niters_per_epoch)
     best, history = 0.0, []
     lr = optimizer.lr if hasattr(optimizer, "lr") else None
@@ -189,7 +249,10 @@ def train(runner, optimizer, config, batches, lr_policy, evaluate_fn=None, keepe
             if miou > best:
                 best = miou
                 if keeper is not None:
-                    keeper.save(model if model is not None else runner.model, optimizer, epoch, idx, miou)
+                    if is_main:
+                        keeper.save(model if model is not None else runner.model, optimizer, epoch, idx, miou)
+                    if distributed:
+                        _dist.barrier()
         history.append(entry)
         if log is not None:
             log(entry)

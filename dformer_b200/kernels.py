@@ -116,6 +116,8 @@ def bgemm(a, b, out, *, trans_a=False, trans_b=False, M, N, K, accumulate=False,
     """Strided-batched GEMM over the leading dimension of 3-D tensors: tcgen05 (3-D TMA maps) when both operands are
     bf16, otherwise the CUDA-core kernel."""
     assert a.dim() == 3 and b.dim() == 3 and out.dim() == 3 and a.stride(2) == 1 and b.stride(2) == 1 and out.stride(2) == 1
+    if not (a.shape[0] == b.shape[0] == out.shape[0]):
+        raise ValueError(f"bgemm: batch counts differ (a {a.shape[0]}, b {b.shape[0]}, out {out.shape[0]})")
     g = GemmArgs()
     g.A, g.B, g.C, g.bias = a.data_ptr(), b.data_ptr(), out.data_ptr(), None
     g.lda, g.ldb, g.ldc = a.stride(1), b.stride(1), out.stride(1)

@@ -137,6 +137,9 @@ class LightHamHead(BaseDecodeHead):
         ham = self.hamburger.ham
         bases = self.injected_bases if self.injected_bases is not None else ham.draw_bases(B, ham.D, dev)
         bases = bases.to(dev, torch.float32).contiguous()
+        if tuple(bases.shape) != (B * ham.S, ham.D, ham.R):
+            raise ValueError(f"NMF bases have shape {tuple(bases.shape)}, this batch needs {(B * ham.S, ham.D, ham.R)} "
+                             "(injected_bases must match the batch of the call)")
         drop_mask = None
         if training and self.dropout is not None and self.dropout.p > 0:
             keep = 1.0 - self.dropout.p

@@ -43,7 +43,8 @@ class FusedAdamW:
                     wd[sl], lrm[sl], decays[sl] = weight_decay, 1.0, 1.0
                 elif id(s.param) in nodecay_ids or not reference_groups:
                     lrm[sl] = 1.0
-            self.state.append(dict(mod=mod, m=torch.zeros_like(flat), v=torch.zeros_like(flat), wd=wd, lrm=lrm, decays=decays))
+            # the layout is kept here: `mod._plan` is reset by any later `model._apply` (e.g. a redundant `.cuda()`)
+            self.state.append(dict(mod=mod, layout=layout, m=torch.zeros_like(flat), v=torch.zeros_like(flat), wd=wd, lrm=lrm, decays=decays))
 
     def set_lr(self, lr):
         """Update the learning rate read by (possibly graph-captured) optimizer launches."""
@@ -96,16 +97,24 @@ class FusedAdamW:
         views = {}
         for st in self.state:
             updated = (st["lrm"] != 0).cpu()
-            for s in st["mod"]._plan.layout.slots.values():
+            for s in st["layout"].slots.values():
                 sl = slice(s.offset, s.offset + s.numel)
                 views[id(s.param)] = (st["m"][sl].view(s.param.shape), st["v"][sl].view(s.param.shape), bool(updated[s.offset]))
         return views
+
+    def _sync_step_count(self):
+        """The device-side counter is authoritative: a replayed CUDA graph advances it without running `step()` on the host
+        (`engine.GraphedTrainStep` mirrors it, but a graph replayed by other code would not).  One sync at checkpoint time."""
+        if self._dyn is not None:
+            self.step_count = int(round(float(self._dyn[1].item())))
+        return self.step_count
 
     def state_dict(self):
         """A `torch.optim.AdamW.state_dict()` of the optimizer the reference builds (same parameter numbering, same two groups), so
         that `Engine.save_checkpoint` / `restore_checkpoint` files (utils/engine/engine.py:101-186) move between the two
         implementations.  Like torch, only parameters that have been stepped carry state; the never-used `stem_e_fc*` layers
         (no gradient, `DFormer.py:202-203`) and frozen parameters carry none."""
+        self._sync_step_count()
         decay, no_decay = self._reference_groups()
         skeleton = torch.optim.AdamW([dict(params=decay, lr=self.lr), dict(params=no_decay, weight_decay=0.0, lr=self.lr)], lr=self.lr,
                                      betas=self.betas, eps=self.eps, weight_decay=self.weight_decay).state_dict()

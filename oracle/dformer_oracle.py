@@ -41,6 +41,30 @@ import torch.nn.functional as F
 Tensor = torch.Tensor
 Params = Dict[str, Tensor]
 
+# ATen-faithful mode.  The primitive restatements below (LayerNorm as mean / var arithmetic, GELU through erf, BatchNorm through
+# mean / var, the 49-window pooling loop, explicit bilinear index math) are what pins the ALGORITHM; but under torch.autocast
+# they round to bf16 after every primitive, which the reference never does: it dispatches the fused ATen ops `F.layer_norm`,
+# `F.gelu`, `F.batch_norm`, `F.adaptive_avg_pool2d`, `F.interpolate`, `F.linear`, `F.cross_entropy`.  Inside
+# `with aten_faithful():` every primitive below calls exactly the op the reference modules call, so that
+# `torch.autocast(bf16)` around `forward` reproduces the reference's AMP rounding points (the bf16 yardstick of the tests and
+# the B200-eager comparator of bench.py).  Both modes are pinned by the same golden vectors (tests/test_oracle_golden.py).
+_ATEN = False
+
+
+class aten_faithful:
+    def __init__(self, on: bool = True):
+        self.on = on
+
+    def __enter__(self):
+        global _ATEN
+        self.prev, _ATEN = _ATEN, self.on
+        return self
+
+    def __exit__(self, *exc):
+        global _ATEN
+        _ATEN = self.prev
+        return False
+
 # models/encoders/DFormer.py:460-497
 VARIANTS = {
     "DFormer-Tiny": dict(dims=(32, 64, 128, 256), depths=(3, 3, 5, 2)),
@@ -55,6 +79,8 @@ for _v in VARIANTS.values():
 # --------------------------------------------------------------------------- norms
 def layer_norm_cl(x: Tensor, w: Tensor, b: Tensor, eps: float = 1e-6) -> Tensor:
     """DFormer.py:37-39 -- LayerNorm over the last (channel) axis of an NHWC tensor."""
+    if _ATEN:
+        return F.layer_norm(x, (x.shape[-1],), w, b, eps)
     mu = x.mean(dim=-1, keepdim=True)
     var = (x - mu).pow(2).mean(dim=-1, keepdim=True)
     return (x - mu) / torch.sqrt(var + eps) * w + b
@@ -67,6 +93,13 @@ def batch_norm_nchw(x: Tensor, P: Params, prefix: str, training: bool, eps: floa
     When ``new_stats`` is a dict the updated running statistics (unbiased var,
     momentum 0.1) are written into it under the reference buffer names."""
     w, b = P[prefix + ".weight"], P[prefix + ".bias"]
+    if _ATEN:
+        rm, rv = P[prefix + ".running_mean"].detach().clone(), P[prefix + ".running_var"].detach().clone()
+        y = F.batch_norm(x, rm, rv, w, b, training, momentum, eps)
+        if training and new_stats is not None:
+            new_stats[prefix + ".running_mean"], new_stats[prefix + ".running_var"] = rm, rv
+            new_stats[prefix + ".num_batches_tracked"] = P[prefix + ".num_batches_tracked"] + 1
+        return y
     if training:
         mean = x.mean(dim=(0, 2, 3))
         var = x.var(dim=(0, 2, 3), unbiased=False)
@@ -84,10 +117,14 @@ def batch_norm_nchw(x: Tensor, P: Params, prefix: str, training: bool, eps: floa
 
 def gelu(x: Tensor) -> Tensor:
     """nn.GELU() default = exact erf form."""
+    if _ATEN:
+        return F.gelu(x)
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
 
 
 def linear(x: Tensor, P: Params, prefix: str) -> Tensor:
+    if _ATEN:
+        return F.linear(x, P[prefix + ".weight"], P[prefix + ".bias"])
     return x @ P[prefix + ".weight"].t() + P[prefix + ".bias"]
 
 
@@ -109,6 +146,8 @@ def mlp(P: Params, prefix: str, x: Tensor) -> Tensor:
 
 def adaptive_avg_pool_7(x_nchw: Tensor) -> Tensor:
     """nn.AdaptiveAvgPool2d((7,7)): window i = [floor(i*In/7), ceil((i+1)*In/7))."""
+    if _ATEN:
+        return F.adaptive_avg_pool2d(x_nchw, (7, 7))
     B, C, H, W = x_nchw.shape
     out = x_nchw.new_zeros(B, C, 7, 7)
     for i in range(7):
@@ -132,6 +171,8 @@ def _bilinear_axis(n_in: int, n_out: int) -> Tuple[Tensor, Tensor, Tensor]:
 
 def bilinear_resize_nchw(x: Tensor, size: Sequence[int]) -> Tensor:
     """F.interpolate(mode='bilinear', align_corners=False) restated with explicit index math."""
+    if _ATEN:
+        return F.interpolate(x, size=(int(size[0]), int(size[1])), mode="bilinear", align_corners=False)
     H, W = x.shape[-2:]
     Ho, Wo = int(size[0]), int(size[1])
     if (H, W) == (Ho, Wo):
@@ -284,6 +325,8 @@ def ham_head(P: Params, outs: Sequence[Tensor], bases_raw: Tensor, training: boo
 def masked_ce(logits: Tensor, label: Tensor, background: int = 255) -> Tensor:
     """builder.py:230 -- CE(reduction='none', ignore_index=255) then mean over label != background."""
     label = label.long()
+    if _ATEN:
+        return F.cross_entropy(logits, label, reduction="none", ignore_index=255)[label != background].mean()
     lse = torch.logsumexp(logits, dim=1)
     valid = label != background
     safe = label.clamp(max=logits.shape[1] - 1)

@@ -34,11 +34,53 @@ def test_graphed_step_matches_eager_step():
         ls = [run.step(rgb, hha, lab).item() for _ in range(4)]
         losses[mode] = ls
         finals[mode] = m.encoder_backbone.stages[2][0].mlp.fc1.weight.detach().clone()
-    # warm-up consumed 1 (eager) vs 1 + capture (graph) optimizer steps; compare the trajectories' shape and sanity
+    # warm-up and capture passes are rolled back (preserve_state), so both runners start from the constructed model and take the
+    # same four steps: equal trajectories up to bf16 run-to-run noise (split-K fp32 atomics)
     assert all(torch.isfinite(torch.tensor(v)).all() for v in losses.values())
-    assert losses["graph"][-1] < losses["graph"][0] + 0.5 and losses["eager"][-1] < losses["eager"][0] + 0.5
-    assert (finals["graph"] - finals["eager"]).abs().max() < 0.05          # same weights up to one extra AdamW step at lr 1e-3
+    assert losses["graph"] == pytest.approx(losses["eager"], abs=2e-2)
+    assert (finals["graph"] - finals["eager"]).abs().max() < 6e-3          # 4 AdamW steps at lr 1e-3 move a weight by <= 4e-3
     assert run.graph is not None
+
+
+def test_graph_replays_advance_the_checkpointed_step_and_eval_draws_fresh_bases(tmp_path):
+    """(a) a checkpoint written after N graph replays must carry step == N (the device counter is authoritative) and
+    restore into an optimizer that continues with bias corrections of step N + 1; (b) building the runner must not advance the
+    model / optimizer state; (c) the runner's injected NMF bases are scoped to its own step, so an evaluation forward with a larger
+    batch on the same model draws its own bases instead of reading past the training buffer."""
+    from dformer_b200.engine import GraphedTrainStep, restore_checkpoint, save_checkpoint
+    from dformer_b200.optim import FusedAdamW
+    rgb, hha = torch.randn(2, 3, 64, 96, device="cuda"), torch.randn(2, 3, 64, 96, device="cuda")
+    lab = torch.randint(0, 40, (2, 64, 96), device="cuda")
+    m = _build(0)
+    w0 = m.encoder_backbone.stages[1][0].mlp.fc1.weight.detach().clone()
+    rm0 = m.decode_head.squeeze.bn.running_mean.detach().clone()
+    opt = FusedAdamW(m, lr=1e-3)
+    run = GraphedTrainStep(m, opt, rgb, hha, lab, warmup=2, use_graph=True)
+    assert torch.equal(m.encoder_backbone.stages[1][0].mlp.fc1.weight, w0) and torch.equal(m.decode_head.squeeze.bn.running_mean, rm0)
+    assert opt.step_count == 0 and float(opt._dyn[1].item()) == 0.0
+    N = 5
+    for _ in range(N):
+        run.step(rgb, hha, lab)
+    torch.cuda.synchronize()
+    assert float(opt._dyn[1].item()) == N
+    path = str(tmp_path / "ck.pt")
+    save_checkpoint(path, m, opt, epoch=1, iteration=N)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    steps = {int(float(e["step"])) for e in ck["optimizer"]["state"].values()}
+    assert steps == {N}
+    m2 = _build(1)
+    opt2 = FusedAdamW(m2, lr=1.0)
+    restore_checkpoint(path, m2, opt2)
+    assert opt2.step_count == N
+    # (c) evaluation on the trained model with a bigger batch than the runner's
+    assert m.decode_head.injected_bases is None
+    m.eval()
+    with torch.no_grad():
+        out = m(torch.randn(3, 3, 64, 96, device="cuda"), torch.randn(3, 3, 64, 96, device="cuda"))
+    assert out.shape == (3, 40, 64, 96) and torch.isfinite(out).all()
+    m.decode_head.injected_bases = torch.rand(2, 512, 64, device="cuda")
+    with pytest.raises(ValueError):
+        m(torch.randn(3, 3, 64, 96, device="cuda"), torch.randn(3, 3, 64, 96, device="cuda"))
 
 
 def test_staged_input_prefetch_feeds_the_same_step():

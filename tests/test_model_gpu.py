@@ -117,55 +117,108 @@ def test_fp32_against_oracle(variant, B, H, W, train):
             assert cos >= 0.999, (k, cos.item())
 
 
-@pytest.mark.parametrize("variant,B,H,W", [("DFormer-Tiny", 2, 96, 128), ("DFormer-Large", 1, 480, 640)])
-def test_bf16_against_oracle(variant, B, H, W):
-    """bf16 path vs the fp32 oracle.  The reference's own bf16-autocast run agrees with its fp32 run on only
-    ~97.7-99 % of argmaxes and 83-90 % of elements at rtol 2e-2 under this stress init, so the gate
-    here is: relative L2 error of the logits <= 2e-2, argmax agreement >= 97 %, gradient cosine >= 0.99."""
-    m, P = build(variant, 40, "bf16", 5, True)
-    rgb, hha, label, bases = make_inputs(B, H, W, 40, seed=5)
-    m.decode_head.injected_bases = bases.cuda()
-    Pd = {k: v.cuda() for k, v in P.items()}
+def _default_init_state(variant, ncls, seed):
+    """the reference's own random init (layer scales 1e-6, `DFormer.py:152`): same-seed construction is bit-identical to the
+    reference's (tests/test_api_cpu.py), so this is the state the reference would train from"""
+    from dformer_b200 import EncoderDecoder
+    cfg = SimpleNamespace(backbone=variant, decoder="ham", decoder_embed_dim=512, num_classes=ncls, drop_path_rate=0.0, aux_rate=0.0,
+                          device="cuda", pretrained_model=None, bn_eps=1e-3, bn_momentum=0.1, background=255, precision="bf16")
+    torch.manual_seed(seed)
+    m = EncoderDecoder(cfg, norm_layer=nn.BatchNorm2d)
+    P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m.cuda().train(True)
+    m.decode_head.dropout = None
+    return m, P
+
+
+def _bf16_parity_figures(variant, B, H, W, init):
+    """ours-bf16, the reference's bf16 (ATen-faithful oracle under torch.autocast: the ops and rounding points the reference's
+    AMP path has) and the fp32 oracle on the same weights / inputs; every figure north_star names, three ways."""
+    if init == "stress":
+        m, P = build(variant, 40, "bf16", 5, True)
+    else:
+        m, P = _default_init_state(variant, 40, 5)
+    rgb, hha, label, bases = (t.cuda() for t in make_inputs(B, H, W, 40, seed=5))
+    m.decode_head.injected_bases = bases
     names = [k for k, p in m.named_parameters() if not k.startswith("encoder_backbone.stem_e_fc")]
-    for k in names:
-        Pd[k].requires_grad_(True)
     v = O.VARIANTS[variant]
-    r = O.forward(Pd, rgb.cuda(), hha.cuda(), bases.cuda(), v["dims"], v["depths"], label=label.cuda(), training=True, return_all=True)
-    loss, out = m(rgb.cuda(), hha.cuda(), label.cuda())
-    err = ((out - r["out"]).norm() / r["out"].norm()).item()
-    # like-for-like yardstick: the oracle itself under torch.autocast(bf16) (= what the reference's AMP path computes)
-    Pn = {k: v.detach() for k, v in Pd.items()}
-    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-        ra = O.forward(Pn, rgb.cuda(), hha.cuda(), bases.cuda(), v["dims"], v["depths"], label=label.cuda(), training=True, return_all=True)
-    err_ref = ((ra["out"].float() - r["out"]).norm() / r["out"].norm()).item()
-    agree_ref = (ra["out"].argmax(1) == r["out"].argmax(1)).float().mean().item()
-    agree = (out.argmax(1) == r["out"].argmax(1)).float().mean().item()
-    print(f"bf16 {variant}: rel-err ours {err:.3e} vs reference-autocast {err_ref:.3e}; argmax ours {agree:.4f} vs reference-autocast {agree_ref:.4f}")
-    assert err <= max(2e-2, 1.25 * err_ref), (err, err_ref)
-    assert agree >= min(0.97, agree_ref - 0.01), (agree, agree_ref)
-    assert abs(loss.item() - r["loss"].item()) <= 2e-2 * abs(r["loss"].item())
+
+    def run_oracle(autocast):
+        Pd = {k: t.cuda().clone().requires_grad_(k in names) for k, t in P.items()}
+        if autocast:
+            with O.aten_faithful(), torch.autocast("cuda", dtype=torch.bfloat16):
+                r = O.forward(Pd, rgb, hha, bases, v["dims"], v["depths"], label=label, training=True, return_all=True)
+        else:
+            r = O.forward(Pd, rgb, hha, bases, v["dims"], v["depths"], label=label, training=True, return_all=True)
+        r["loss"].backward()
+        return r["out"].detach().float(), r["loss"].item(), {k: Pd[k].grad.float() for k in names if Pd[k].grad is not None}
+
+    o32, l32, g32 = run_oracle(False)
+    oref, lref, gref = run_oracle(True)
+    loss, out = m(rgb, hha, label)
     loss.backward()
-    r["loss"].backward()
+    out = out.detach().float()
     named = dict(m.named_parameters())
-    cosines = {k: torch.nn.functional.cosine_similarity(named[k].grad.flatten().float(), Pd[k].grad.flatten(), dim=0).item() for k in names
-               if Pd[k].grad.norm() >= 1e-6}
-    # bf16 gradients of small bias / scale vectors are noisy; gate on the global direction and the distribution
-    ga = torch.cat([named[k].grad.flatten().float() for k in cosines])
-    gb = torch.cat([Pd[k].grad.flatten() for k in cosines])
-    global_cos = torch.nn.functional.cosine_similarity(ga, gb, dim=0).item()
-    vals = sorted(cosines.values())
-    print(f"bf16 {variant}: gradient cosine global {global_cos:.5f}, min {vals[0]:.4f}, 5th pct {vals[len(vals) // 20]:.4f}, median {vals[len(vals) // 2]:.5f}")
-    # like-for-like yardstick for gradients: the oracle under autocast(bf16) vs its own fp32 gradients
-    Pa = {k: v.detach().clone().requires_grad_(k in cosines) for k, v in Pd.items()}
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        la = O.forward(Pa, rgb.cuda(), hha.cuda(), bases.cuda(), v["dims"], v["depths"], label=label.cuda(), training=True, return_all=True)["loss"]
-    la.backward()
-    gr = torch.cat([Pa[k].grad.flatten().float() for k in cosines])
-    ref_cos = torch.nn.functional.cosine_similarity(gr, gb, dim=0).item()
-    print(f"bf16 {variant}: reference-autocast gradient cosine global {ref_cos:.5f}")
-    assert global_cos >= min(0.99, ref_cos - 0.005), (global_cos, ref_cos)
-    assert vals[0] >= 0.90, sorted(cosines.items(), key=lambda kv: kv[1])[:5]
-    assert vals[len(vals) // 20] >= 0.96, vals[len(vals) // 20]
+    gours = {k: named[k].grad.float() for k in g32}
+    live = [k for k in g32 if g32[k].norm() >= 1e-6]
+
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    close = lambda a, b: torch.isclose(a, b, rtol=2e-2, atol=1e-4).float().mean().item()
+    agree = lambda a, b, mask=None: ((a.argmax(1) == b.argmax(1)).float().mean() if mask is None else
+                                    (a.argmax(1) == b.argmax(1))[mask].float().mean()).item()
+    top2 = o32.topk(2, dim=1).values
+    margin = top2[:, 0] - top2[:, 1]
+    # bf16 error band: twice the 99.9th percentile of the REFERENCE's own |bf16 - fp32| logit error (sampled); a pixel whose fp32
+    # top-2 margin exceeds it keeps its argmax under any rounding of that size, so disagreement there is a real defect
+    dref = (oref - o32).abs().flatten()
+    band = 2.0 * torch.quantile(dref[torch.randint(0, dref.numel(), (1 << 20,), device=dref.device)], 0.999).item()
+    safe = margin > band
+    cos = lambda ga, gb: {k: torch.nn.functional.cosine_similarity(ga[k].flatten(), gb[k].flatten(), dim=0).item() for k in live}
+    gcat = lambda g: torch.cat([g[k].flatten() for k in live])
+    gcos = lambda ga, gb: torch.nn.functional.cosine_similarity(gcat(ga), gcat(gb), dim=0).item()
+    c_ours, c_ref = sorted(cos(gours, g32).values()), sorted(cos(gref, g32).values())
+    fig = dict(variant=variant, size=[B, H, W], init=init,
+               rel_l2=dict(ours_vs_fp32=rel(out, o32), ref_bf16_vs_fp32=rel(oref, o32), ours_vs_ref_bf16=rel(out, oref)),
+               close_frac_rtol2e2_atol1e4=dict(ours_vs_fp32=close(out, o32), ref_bf16_vs_fp32=close(oref, o32), ours_vs_ref_bf16=close(out, oref)),
+               argmax=dict(ours_vs_fp32=agree(out, o32), ref_bf16_vs_fp32=agree(oref, o32), ours_vs_ref_bf16=agree(out, oref)),
+               margin_restricted=dict(band=band, pixels_kept=safe.float().mean().item(), ours_vs_fp32=agree(out, o32, safe),
+                                      ref_bf16_vs_fp32=agree(oref, o32, safe)),
+               loss=dict(ours=loss.item(), ref_bf16=lref, fp32=l32),
+               grad_cos_global=dict(ours_vs_fp32=gcos(gours, g32), ref_bf16_vs_fp32=gcos(gref, g32), ours_vs_ref_bf16=gcos(gours, gref)),
+               grad_cos_per_tensor=dict(ours_min=c_ours[0], ours_p5=c_ours[len(c_ours) // 20], ours_median=c_ours[len(c_ours) // 2],
+                                        ref_min=c_ref[0], ref_p5=c_ref[len(c_ref) // 20], ref_median=c_ref[len(c_ref) // 2]))
+    print("bf16-parity " + json.dumps(fig))
+    outdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(outdir):
+        with open(os.path.join(outdir, f"bf16_parity_{variant}_{init}.json"), "w") as f:
+            json.dump(fig, f, indent=1)
+    return fig
+
+
+@pytest.mark.parametrize("variant,B,H,W,init", [("DFormer-Tiny", 2, 96, 128, "stress"), ("DFormer-Large", 1, 480, 640, "stress"),
+                                                 ("DFormer-Large", 1, 480, 640, "default")])
+def test_bf16_parity(variant, B, H, W, init):
+    """north_star: bf16 within rtol 2e-2, argmax >= 99.9 %, gradient cosine >= 0.999 -- of the reference's OWN implementation.
+    The reference's bf16 is its modules under torch.autocast(bf16); the yardstick here is the ATen-faithful oracle under the same
+    autocast (F.layer_norm / F.gelu / F.batch_norm / ... exactly as the reference dispatches them, pinned by the golden vectors),
+    not the primitive restatement whose per-primitive roundings would flatter us.  Gates, every one like-for-like and literal
+    where the reference's own AMP run meets the literal number too (its figures are printed beside ours and recorded in
+    DESIGN.md section 4):
+      * logits: relative L2 error vs fp32 no worse than the reference-bf16's own (10 % slack: two independent bf16 roundings of
+        one computation differ by about that much run to run), or <= 2e-2 outright;
+      * argmax: on pixels whose fp32 top-2 margin exceeds the bf16 error band >= 99.9 % (literal); over all pixels no worse than
+        the reference-bf16's own agreement minus 0.5 points;
+      * gradients: global cosine vs fp32 >= 0.999 or no worse than the reference-bf16's own; per-tensor 5th percentile likewise."""
+    f = _bf16_parity_figures(variant, B, H, W, init)
+    r, a, mr, gc, pt = f["rel_l2"], f["argmax"], f["margin_restricted"], f["grad_cos_global"], f["grad_cos_per_tensor"]
+    assert r["ours_vs_fp32"] <= max(2e-2, 1.10 * r["ref_bf16_vs_fp32"]), r
+    assert r["ours_vs_ref_bf16"] <= 1.5 * max(r["ours_vs_fp32"], r["ref_bf16_vs_fp32"]), r      # independent roundings add in quadrature
+    assert mr["ours_vs_fp32"] >= 0.999, mr
+    assert a["ours_vs_fp32"] >= min(0.999, a["ref_bf16_vs_fp32"] - 0.005), a
+    assert abs(f["loss"]["ours"] - f["loss"]["fp32"]) <= 2e-2 * abs(f["loss"]["fp32"]), f["loss"]
+    assert gc["ours_vs_fp32"] >= min(0.999, gc["ref_bf16_vs_fp32"] - 0.002), gc
+    assert pt["ours_p5"] >= min(0.999, pt["ref_p5"] - 0.02), pt
+    assert pt["ours_min"] >= min(0.90, pt["ref_min"] - 0.05), pt
 
 
 def test_cpu_tensors_are_rejected_loudly():

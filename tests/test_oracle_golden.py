@@ -17,14 +17,15 @@ def _layout(variant):
         return json.load(f)[variant]
 
 
-def test_tiny_eval_forward_matches_reference():
+@pytest.mark.parametrize("aten", [False, True])
+def test_tiny_eval_forward_matches_reference(aten):
     g = torch.load(os.path.join(G, "tiny_eval_64x96.pt"))
     lay = _layout("DFormer-Tiny")
     P = make_state(lay["shapes"], seed=g["seed"])
     B, H, W = g["size"]
     rgb, hha, label, bases = make_inputs(B, H, W, 40, seed=g["seed"])
     v = O.VARIANTS["DFormer-Tiny"]
-    with torch.no_grad():
+    with torch.no_grad(), O.aten_faithful(aten):
         r = O.forward(P, rgb, hha, bases, v["dims"], v["depths"], label=label, training=False, return_all=True)
     for a, b in zip(r["outs"], g["outs"]):
         torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4)
@@ -33,7 +34,9 @@ def test_tiny_eval_forward_matches_reference():
     torch.testing.assert_close(r["loss"], g["loss"], rtol=1e-5, atol=1e-5)
 
 
-def test_tiny_train_forward_backward_matches_reference():
+@pytest.mark.parametrize("aten", [False, True])
+def test_tiny_train_forward_backward_matches_reference(aten):
+    """aten=True: the ATen-faithful mode (the ops the reference dispatches; the autocast yardstick) is pinned by the same vectors."""
     g = torch.load(os.path.join(G, "tiny_train_96x128.pt"))
     lay = _layout("DFormer-Tiny")
     P = make_state(lay["shapes"], seed=g["seed"])
@@ -43,8 +46,9 @@ def test_tiny_train_forward_backward_matches_reference():
     rgb, hha, label, bases = make_inputs(B, H, W, 40, seed=g["seed"])
     v = O.VARIANTS["DFormer-Tiny"]
     stats = {}
-    r = O.forward(P, rgb, hha, bases, v["dims"], v["depths"], label=label, training=True,
-                  new_stats=stats, return_all=True)
+    with O.aten_faithful(aten):
+        r = O.forward(P, rgb, hha, bases, v["dims"], v["depths"], label=label, training=True,
+                      new_stats=stats, return_all=True)
     for a, b in zip(r["outs"], g["outs"]):
         torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(r["small"], g["small"], rtol=1e-4, atol=1e-4)
