@@ -1,4 +1,6 @@
-// Global Awareness Attention core (DFormer.py:122-130) as ONE kernel per direction.
+// Global Awareness Attention core (DFormer.py:122-130) as ONE kernel per direction -- the exact-fp32 (CUDA-core) form.
+// The bf16 configuration runs the same decomposition on the tensor cores (gaa_mma.cu); the C entry points at the end of this
+// file dispatch on the dtype.
 //
 // The 49 pooled query tokens of an image attend over all H*W pixel keys/values, softmax over the pixels:
 //   S = scale * Q K^T  [49, HW]      P = softmax_HW(S)      O = P V  [49, d]             per (image, head)
@@ -406,13 +408,17 @@ int launch_bwd(const float* dout, const float* out, const float* lse, const void
 extern "C" int dfb200_gaa_fused_fwd(const void* m, const void* kv, int dtype, int B, int HW, int heads, int d, float* out, float* lse, float* scratch,
                                     int* counters, void* stream) {
   DFB_REQUIRE(B > 0 && HW > 0 && heads > 0, "gaa_fused_fwd: empty problem");
-  DFB_DISPATCH_DTYPE(dtype, T, { GAA_DISPATCH_D(d, { return launch_fwd<T, D>(m, kv, B, HW, heads, out, lse, scratch, counters, ST); }) });
+  DFB_REQUIRE(dtype == 0 || dtype == 1, "gaa_fused_fwd: bad dtype %d", dtype);
+  if (dtype == 1) return dfb_gaa_mma_fwd(m, kv, B, HW, heads, d, out, lse, scratch, counters, ST);      // bf16: tensor cores (gaa_mma.cu)
+  GAA_DISPATCH_D(d, { return launch_fwd<float, D>(m, kv, B, HW, heads, out, lse, scratch, counters, ST); });
   return DFB_OK;
 }
 
 extern "C" int dfb200_gaa_fused_bwd(const float* dout, const float* out, const float* lse, const void* m, const void* kv, int dtype, int B, int HW,
                                     int heads, int d, float* dm, void* dkv, void* stream) {
   DFB_REQUIRE(B > 0 && HW > 0 && heads > 0, "gaa_fused_bwd: empty problem");
-  DFB_DISPATCH_DTYPE(dtype, T, { GAA_DISPATCH_D(d, { return launch_bwd<T, D>(dout, out, lse, m, kv, B, HW, heads, dm, dkv, ST); }) });
+  DFB_REQUIRE(dtype == 0 || dtype == 1, "gaa_fused_bwd: bad dtype %d", dtype);
+  if (dtype == 1) return dfb_gaa_mma_bwd(dout, out, lse, m, kv, B, HW, heads, d, dm, dkv, ST);           // bf16: tensor cores (gaa_mma.cu)
+  GAA_DISPATCH_D(d, { return launch_bwd<float, D>(dout, out, lse, m, kv, B, HW, heads, dm, dkv, ST); });
   return DFB_OK;
 }

@@ -163,52 +163,7 @@ __device__ __noinline__ void epilogue_generic(const TcParams& p, float* v, int r
         }
         if (p.out_bf16) {
           bf16* dst = reinterpret_cast<bf16*>(p.C) + c_off + (long)row * p.ldc + col0;
-          if (false) {
-            // warp-private transpose through shared memory: lane r holds row r (32 columns); after the swizzled
-            // round trip 4 adjacent lanes write one row's 64 contiguous bytes -> every store instruction covers
-            // 8 fully-written 64-byte row segments instead of 32 scattered 16-byte pieces.
-            uint4* st = reinterpret_cast<uint4*>(epi_stage + (warp - 2) * 4096);
-            __syncwarp();
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              uint4 pk;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[u * 8 + 2 * q], v[u * 8 + 2 * q + 1]);
-              st[lane * 4 + (u ^ ((lane >> 1) & 3))] = pk;
-            }
-            __syncwarp();
-            const int row_base = m_blk * BM + quad * 32;
-            bf16* base = reinterpret_cast<bf16*>(p.C) + c_off + (long)row_base * p.ldc + col0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rr = 8 * i + (lane >> 2), u = lane & 3;
-              uint4 pk = st[rr * 4 + (u ^ ((rr >> 1) & 3))];
-              const long grow = row_base + rr;
-              const int gcol = col0 + u * 8;
-              if (p.epi_mode == 1) {              // dz = du * gelu'(z): the saved pre-activation is read in the coalesced store pattern
-                float f[8], z[8];
-                Vec8<bf16>::unpack(pk, f);
-                Vec8<bf16>::load(reinterpret_cast<const bf16*>(p.aux) + grow * p.ld_aux + gcol, z);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] *= gelu_grad_f(z[j]);
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
-              }
-              *reinterpret_cast<uint4*>(base + (long)rr * p.ldc + u * 8) = pk;
-              if (p.epi_mode == 2) {              // x_new = res + DropPath-scale * layer_scale * f  (fp32 residual stream)
-                float f[8], r8[8], l8[8];
-                Vec8<bf16>::unpack(pk, f);
-                Vec8<float>::load(reinterpret_cast<const float*>(p.aux) + grow * p.ld_aux + gcol, r8);
-                Vec8<float>::load(p.ls + gcol, l8);
-                const float sb = p.scale_b ? __ldg(p.scale_b + grow / p.rows_per_sample) : 1.f;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) r8[j] = fmaf(sb * l8[j], f[j], r8[j]);
-                Vec8<float>::store(reinterpret_cast<float*>(p.out2) + grow * p.ld_out2 + gcol, r8);
-              }
-            }
-          } else if (p.epi_mode != 0) {           // tails of the fused epilogues: per element
+          if (p.epi_mode != 0) {                  // tails of the fused epilogues: per element
             const float sb = (p.epi_mode == 2 && p.scale_b) ? __ldg(p.scale_b + row / p.rows_per_sample) : 1.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -652,10 +607,8 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
     // the un-split (forward / dgrad) shapes are tuned for wave quantisation
     const bool will_split = (g.splitk == 0 && g.out_dtype == 0 && g.act == 0 && p.kb_total >= 16) || g.splitk > 1;
     p.BN = will_split ? pick_bn_padding(g.N) : pick_bn(g.N, p.m_tiles, p.kb_total, g.batch, num_sms, p.b_mn_major);
-    if (const char* e = getenv("DFB200_TC_BN")) {          // tuning aid (tools/gemm_bn_sweep.py): force the tile width
-      const int bn = atoi(e);
-      if (bn >= 16 && bn <= 256 && bn % 16 == 0 && !(p.b_mn_major && bn < 64 && g.N >= 64)) p.BN = bn;
-    }
+    static const int forced_bn = [] { const char* e = getenv("DFB200_TC_BN"); return e ? atoi(e) : 0; }();   // tuning aid (tools/gemm_bn_sweep.py), read once
+    if (forced_bn >= 16 && forced_bn <= 256 && forced_bn % 16 == 0 && !(p.b_mn_major && forced_bn < 64 && g.N >= 64)) p.BN = forced_bn;
   }
   p.n_tiles = dfb_cdiv(g.N, p.BN);
   p.C = g.C; p.ldc = g.ldc; p.bias = g.bias;
