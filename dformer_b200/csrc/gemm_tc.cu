@@ -29,10 +29,8 @@ constexpr int BK = 64;           // 64 bf16 = one 128-byte swizzle row
 constexpr int MAX_STAGES = 8;                     // ring depth is chosen per launch: as deep as shared memory allows for this BN
 constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16 KB
 constexpr int MAX_SMEM = 227 * 1024;
-constexpr int TMEM_COLS = 512;   // 2 accumulator stages x 256 fp32 columns
-constexpr int NUM_THREADS = 320;         // TMA warp + MMA warp + 8 epilogue warps
-constexpr int EPI_STAGE_BYTES = 8 * 4096;         // per-epilogue-warp 32 x 128 B staging tile for coalesced stores
-constexpr int SMEM_BYTES = MAX_SMEM;
+constexpr int SMALL_SMEM = 112 * 1024;            // EPI_WARPS = 4 variant: two CTAs per SM
+constexpr int EPI_WARP_BYTES = 4096;              // per-epilogue-warp [32 rows x 128 B] staging tile of the TMA store
 
 struct TcParams {
   int M, N, K;               // problem (K = reduction length)
@@ -44,7 +42,8 @@ struct TcParams {
   void* C; long ldc;
   const float* bias;
   int out_bf16, act, act_col_start, accumulate;
-  int epi_mode; const void* aux; long ld_aux; void* out2; long ld_out2; const float* ls; const float* scale_b; int rows_per_sample;
+  int acc_stages, acc_stride, tmem_cols;     // accumulator ring in tensor memory: 1 or 2 stages, `acc_stride` columns apart
+  int tma_store;                             // bf16 C written by cp.async.bulk.tensor (tmC valid)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -128,99 +127,98 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, bool mn_major
 __device__ __forceinline__ void sts128(uint32_t saddr, const uint32_t* w) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
 }
-__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
-  uint4 r;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
-  return r;
+// Generic (rarely taken) epilogue: ragged chunks / row tails, fp32 outputs, accumulate, scalar split-K.  Bias and activation
+// have already been applied.  Kept out of line so the hot loop stays small in the instruction cache.
+__device__ __noinline__ void epilogue_generic(const TcParams& p, float* v, int row, int col0, int ncols, long c_off) {
+  const bool full = ncols == 32;
+  if (p.splits > 1) {                       // split-K partial sums: fp32 reductions into a zeroed / accumulating C
+    float* dst = reinterpret_cast<float*>(p.C) + c_off + (long)row * p.ldc + col0;
+    if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) atomicAdd(dst + j, v[j]);
+    }
+    return;
+  }
+  if (p.out_bf16) {
+    bf16* dst = reinterpret_cast<bf16*>(p.C) + c_off + (long)row * p.ldc + col0;
+    if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) Vec8<bf16>::store(dst + j, v + j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
+    }
+  } else {
+    float* dst = reinterpret_cast<float*>(p.C) + c_off + (long)row * p.ldc + col0;
+    const bool vec = full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    if (p.accumulate) {
+      if (vec) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o = *reinterpret_cast<float4*>(dst + j);
+          o.x += v[j]; o.y += v[j + 1]; o.z += v[j + 2]; o.w += v[j + 3];
+          *reinterpret_cast<float4*>(dst + j) = o;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) dst[j] += v[j];
+      }
+    } else if (vec) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) dst[j] = v[j];
+    }
+  }
 }
 
-// Generic (rarely taken) epilogue: ragged chunks / row tails, activations, fp32 outputs, accumulate, scalar split-K.
-// Kept out of line so the hot loop stays small in the instruction cache.
-__device__ __noinline__ void epilogue_generic(const TcParams& p, float* v, int row, int col0, int ncols, long c_off, int m_blk, int quad, int lane,
-                                              int warp, uint8_t* epi_stage, bool rows_all_ok) {
-  const bool full = ncols == 32;
-        if (p.splits > 1) {                       // split-K partial sums: fp32 reductions into a zeroed / accumulating C
-          float* dst = reinterpret_cast<float*>(p.C) + c_off + (long)row * p.ldc + col0;
-          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+// bias (first split only) and activation (columns >= act_col_start) on one 32-column accumulator chunk held in registers
+__device__ __forceinline__ void bias_act(const TcParams& p, float* v, int col0, int ncols, bool add_bias) {
+  if (add_bias) {
+    const float* bp = p.bias + col0;
+    if (ncols == 32 && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
-          } else {
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + j));
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      }
+    } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) atomicAdd(dst + j, v[j]);
-          }
-          return;
-        }
-        if (p.act != 0) {
-          if (p.act == 1) {
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) v[j] += __ldg(bp + j);
+    }
+  }
+  if (p.act == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (col0 + j >= p.act_col_start) ? gelu_f(v[j]) : v[j];
-          } else {
+    for (int j = 0; j < 32; ++j) v[j] = (col0 + j >= p.act_col_start) ? gelu_f(v[j]) : v[j];
+  } else if (p.act == 2) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (col0 + j >= p.act_col_start) ? fmaxf(v[j], 0.f) : v[j];
-          }
-        }
-        if (p.out_bf16) {
-          bf16* dst = reinterpret_cast<bf16*>(p.C) + c_off + (long)row * p.ldc + col0;
-          if (p.epi_mode != 0) {                  // tails of the fused epilogues: per element
-            const float sb = (p.epi_mode == 2 && p.scale_b) ? __ldg(p.scale_b + row / p.rows_per_sample) : 1.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < ncols) {
-                float f = __bfloat162float(__float2bfloat16_rn(v[j]));
-                if (p.epi_mode == 1) {
-                  f *= gelu_grad_f(__bfloat162float(reinterpret_cast<const bf16*>(p.aux)[(long)row * p.ld_aux + col0 + j]));
-                  dst[j] = __float2bfloat16_rn(f);
-                } else {
-                  dst[j] = __float2bfloat16_rn(f);
-                  const float r = reinterpret_cast<const float*>(p.aux)[(long)row * p.ld_aux + col0 + j];
-                  reinterpret_cast<float*>(p.out2)[(long)row * p.ld_out2 + col0 + j] = fmaf(sb * p.ls[col0 + j], f, r);
-                }
-              }
-            }
-          } else if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) Vec8<bf16>::store(dst + j, v + j);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
-          }
-        } else {
-          float* dst = reinterpret_cast<float*>(p.C) + c_off + (long)row * p.ldc + col0;
-          const bool vec = full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-          if (p.accumulate) {
-            if (vec) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 o = *reinterpret_cast<float4*>(dst + j);
-                o.x += v[j]; o.y += v[j + 1]; o.z += v[j + 2]; o.w += v[j + 3];
-                *reinterpret_cast<float4*>(dst + j) = o;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) dst[j] += v[j];
-            }
-          } else if (vec) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) dst[j] = v[j];
-          }
-        }
+    for (int j = 0; j < 32; ++j) v[j] = (col0 + j >= p.act_col_start) ? fmaxf(v[j], 0.f) : v[j];
+  }
 }
 
 // ------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+// EPI_WARPS = 8: one CTA per SM with the whole shared memory (deep ring, 2 x 256 TMEM columns), two epilogue warps per TMEM
+//                lane quadrant (column halves).
+// EPI_WARPS = 4: 192 threads, <= 112 KB shared memory and <= 256 TMEM columns per CTA so that TWO CTAs are resident per SM:
+//                150 tiles of an M = 9600 layer fit in one wave of 296 slots, and GEMMs of different streams (RGB / depth /
+//                weight-gradient) overlap one CTA's load phase with the other's epilogue.
+template <int EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, EPI_WARPS == 4 ? 2 : 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* epi_stage = smem + p.stages * p.stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES);
+  uint8_t* epi_stage = smem + p.stages * p.stage_bytes;                 // EPI_WARPS x [32 rows x 128 B], 1024-byte aligned (128-byte swizzle atom)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_WARPS * EPI_WARP_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
@@ -233,13 +231,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -247,7 +246,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
   // barrier init / tensor-memory allocation above touch no global memory: under programmatic dependent launch they overlap the
-  // tail of the previous kernel of the stream; everything below (TMA loads, bias / aux reads, stores) waits for it
+  // tail of the previous kernel of the stream; everything below (TMA loads, bias reads, stores) waits for it
   pdl_sync();
 
   const int a_boxes = p.a_mn_major ? 2 : 1;                       // MN-major: one [64 k x 64 mn] box per 64 MN elements
@@ -297,7 +296,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb0 = sp * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -313,160 +312,153 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // =============================== epilogue (warps 2..9) ===============================
-    // 8 warps: warp w reads TMEM lane quadrant (w & 3) (hardware rule: a warp may only touch lanes 32*(w%4)..+31)
-    // and the column half ((w - 2) >> 2) of the accumulator, so every SMSP has two epilogue warps in flight.
+    // =============================== epilogue (warps 2 .. 2 + EPI_WARPS) ===============================
+    // warp w reads TMEM lane quadrant (w & 3) (hardware rule: a warp may only touch lanes 32*(w%4)..+31); with 8 warps the two
+    // warps of a quadrant split the tile's columns.
+    constexpr int PARTS = EPI_WARPS / 4;
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int chunks = (p.BN + 31) >> 5;
-    const int c_begin = half == 0 ? 0 : (chunks + 1) >> 1, c_end = half == 0 ? (chunks + 1) >> 1 : chunks;
+    const int part = (warp - 2) >> 2;
+    const uint32_t sbase = smem_u32(epi_stage + (warp - 2) * EPI_WARP_BYTES);
     int acc = 0; uint32_t acc_phase = 0;
+    bool store_pending = false;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.n_tiles, m_blk = (tile / p.n_tiles) % p.m_tiles;
+      const int bz = tile / (tiles_mn * p.splits);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = m_blk * BM + quad * 32 + lane;
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * 256u;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.acc_stride);
       const bool row_ok = row < p.M;
-      const bool rows_all_ok = (m_blk * BM + quad * 32 + 31) < p.M;     // warp-uniform: the whole 32-row slab is inside M
-      const bool first_split = ((tile / tiles_mn) % p.splits) == 0;
-      const long c_off = (long)(tile / (tiles_mn * p.splits)) * p.strideC;
-      for (int ch = c_begin; ch < c_end; ++ch) {
-        const int c0 = ch << 5;
-        uint32_t r[32];
-        __syncwarp();                             // tcgen05.ld is warp-collective: reconverge after the per-row predicated stores
-        tmem_ld32(t_row + (uint32_t)c0, r);
-        tmem_ld_wait();
-        const int col0 = n_blk * p.BN + c0;
-        const int ncols = min(32, min(p.BN - c0, p.N - col0));
-        if (!row_ok || ncols <= 0) continue;
-        float v[32];
+      const bool add_bias = p.bias != nullptr && (p.splits == 1 || ((tile / tiles_mn) % p.splits) == 0);
+      const int tn = min(p.BN, p.N - n_blk * p.BN);                 // valid columns of this tile
+      if (p.tma_store) {
+        // ---- bf16 output through TMA: 64-column boxes, [32 rows x 128 B] staged in the 128-byte swizzle pattern (lane = row writes
+        // its eight 16-byte chunks at chunk ^ (row & 7): conflict-free), one cp.async.bulk.tensor store per box; rows >= M and
+        // columns >= N are clipped by the hardware
+        const int nboxes = (tn + 63) >> 6;
+        const int b_begin = (PARTS == 1 || part == 0) ? 0 : (nboxes + 1) >> 1;
+        const int b_end = PARTS == 1 ? nboxes : (part == 0 ? (nboxes + 1) >> 1 : nboxes);
+        for (int box = b_begin; box < b_end; ++box) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const bool full = ncols == 32;
-        if (p.bias != nullptr && (p.splits == 1 || first_split)) {
-          const float* bp = p.bias + col0;
-          if (full && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          for (int h = 0; h < 2; ++h) {
+            const int c0 = box * 64 + h * 32;
+            uint32_t r[32];
+            __syncwarp();
+            tmem_ld32(t_row + (uint32_t)c0, r);
+            tmem_ld_wait();
+            if (h == 0 && store_pending) {          // the previous box of this warp must have left the staging tile
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              __syncwarp();
             }
-          } else {
+            const int col0 = n_blk * p.BN + c0;
+            const int ncols = min(32, p.N - col0);
+            if (ncols <= 0) continue;
+            float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) v[j] += __ldg(bp + j);
-          }
-        }
-        // ---- hot path 1: bf16 output, complete 32x32 chunk -> swizzled smem transpose -> coalesced 64-byte row segments
-        const bool aligned_c = ((p.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (((c_off + col0) & 7) == 0);
-        if (p.splits == 1 && p.out_bf16 && p.act == 0 && full && rows_all_ok && aligned_c) {
-          const uint32_t sbase = smem_u32(epi_stage + (warp - 2) * 4096);
-          __syncwarp();
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            bias_act(p, v, col0, ncols, add_bias);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint32_t w[4];
+            for (int u = 0; u < 4; ++u) {
+              uint32_t w[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[u * 8 + 2 * q], v[u * 8 + 2 * q + 1]);
-              w[q] = *reinterpret_cast<const uint32_t*>(&h2);
-            }
-            sts128(sbase + (uint32_t)(lane * 4 + (u ^ ((lane >> 1) & 3))) * 16u, w);
-          }
-          __syncwarp();
-          const int row_base = m_blk * BM + quad * 32;
-          bf16* base = reinterpret_cast<bf16*>(p.C) + c_off + (long)row_base * p.ldc + col0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = 8 * i + (lane >> 2), u = lane & 3;
-            uint4 pk = lds128(sbase + (uint32_t)(rr * 4 + (u ^ ((rr >> 1) & 3))) * 16u);
-            const long grow = row_base + rr;
-            const int gcol = col0 + u * 8;
-            if (p.epi_mode == 1) {              // dz = du * gelu'(z): the saved pre-activation is read in the coalesced store pattern
-              float f[8], z[8];
-              Vec8<bf16>::unpack(pk, f);
-              Vec8<bf16>::load(reinterpret_cast<const bf16*>(p.aux) + grow * p.ld_aux + gcol, z);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] *= gelu_grad_f(z[j]);
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
-            }
-            *reinterpret_cast<uint4*>(base + (long)rr * p.ldc + u * 8) = pk;
-            if (p.epi_mode == 2) {              // x_new = res + DropPath-scale * layer_scale * f  (fp32 residual stream)
-              float f[8], r8[8], l8[8];
-              Vec8<bf16>::unpack(pk, f);
-              Vec8<float>::load(reinterpret_cast<const float*>(p.aux) + grow * p.ld_aux + gcol, r8);
-              Vec8<float>::load(p.ls + gcol, l8);
-              const float sb = p.scale_b ? __ldg(p.scale_b + grow / p.rows_per_sample) : 1.f;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) r8[j] = fmaf(sb * l8[j], f[j], r8[j]);
-              Vec8<float>::store(reinterpret_cast<float*>(p.out2) + grow * p.ld_out2 + gcol, r8);
-            }
-          }
-          continue;
-        }
-        // ---- hot path 1b: bf16 output, ragged chunk whose width is a multiple of 8 (BN = 48, 144, 240, ...): every lane
-        // writes whole 16-byte vectors of its own row (full 32-byte sectors, no staging needed for the short tail)
-        if (p.splits == 1 && p.out_bf16 && p.act == 0 && p.epi_mode == 0 && aligned_c && (ncols & 7) == 0) {
-          bf16* dst = reinterpret_cast<bf16*>(p.C) + c_off + (long)row * p.ldc + col0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8)
-            if (j < ncols) Vec8<bf16>::store(dst + j, v + j);
-          continue;
-        }
-        // ---- hot path 2: split-K partial sums -> vector reductions into the fp32 gradient
-        if (p.splits > 1 && (ncols & 3) == 0) {
-          float* dst = reinterpret_cast<float*>(p.C) + c_off + (long)row * p.ldc + col0;
-          if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (j < ncols)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
-            continue;
-          }
-        }
-        // ---- hot path 3: fp32 output without split-K (small wgrads accumulate into the arena; downsample convs write fp32)
-        if (p.splits == 1 && !p.out_bf16 && p.act == 0 && (ncols & 3) == 0) {
-          float* dst = reinterpret_cast<float*>(p.C) + c_off + (long)row * p.ldc + col0;
-          if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j < ncols) {
-                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                if (p.accumulate) {
-                  const float4 old = *reinterpret_cast<const float4*>(dst + j);
-                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                }
-                *reinterpret_cast<float4*>(dst + j) = o;
+              for (int q = 0; q < 4; ++q) {
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[u * 8 + 2 * q], v[u * 8 + 2 * q + 1]);
+                w[q] = *reinterpret_cast<const uint32_t*>(&h2);
               }
+              sts128(sbase + (uint32_t)(lane * 8 + ((h * 4 + u) ^ (lane & 7))) * 16u, w);
             }
-            continue;
           }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                         ::"l"(&tmC), "r"(sbase), "r"(n_blk * p.BN + box * 64), "r"(m_blk * BM + quad * 32), "r"(bz) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          store_pending = true;
         }
-        {
-          float vv[32];                            // address-taken copy: keeps v[] itself in registers for the hot paths
+      } else {
+        const long c_off = (long)bz * p.strideC;
+        const int chunks = (tn + 31) >> 5;
+        const int c_begin = (PARTS == 1 || part == 0) ? 0 : (chunks + 1) >> 1;
+        const int c_end = PARTS == 1 ? chunks : (part == 0 ? (chunks + 1) >> 1 : chunks);
+        for (int ch = c_begin; ch < c_end; ++ch) {
+          const int c0 = ch << 5;
+          uint32_t r[32];
+          __syncwarp();                             // tcgen05.ld is warp-collective: reconverge after the per-row predicated stores
+          tmem_ld32(t_row + (uint32_t)c0, r);
+          tmem_ld_wait();
+          const int col0 = n_blk * p.BN + c0;
+          const int ncols = min(32, tn - c0);
+          if (!row_ok) continue;
+          float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) vv[j] = v[j];
-          epilogue_generic(p, vv, row, col0, ncols, c_off, m_blk, quad, lane, warp, epi_stage, rows_all_ok);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          bias_act(p, v, col0, ncols, add_bias);
+          // ---- split-K partial sums -> vector reductions into the fp32 gradient
+          if (p.splits > 1 && (ncols & 3) == 0) {
+            float* dst = reinterpret_cast<float*>(p.C) + c_off + (long)row * p.ldc + col0;
+            if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (j < ncols)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+              continue;
+            }
+          }
+          // ---- fp32 output without split-K (small wgrads accumulate into the arena; downsample convs write fp32)
+          if (p.splits == 1 && !p.out_bf16 && (ncols & 3) == 0) {
+            float* dst = reinterpret_cast<float*>(p.C) + c_off + (long)row * p.ldc + col0;
+            if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                if (j < ncols) {
+                  float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                  if (p.accumulate) {
+                    const float4 old = *reinterpret_cast<const float4*>(dst + j);
+                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                  }
+                  *reinterpret_cast<float4*>(dst + j) = o;
+                }
+              }
+              continue;
+            }
+          }
+          // ---- bf16 output that cannot go through TMA (unaligned leading dimension / base): whole 16-byte vectors per lane
+          if (p.splits == 1 && p.out_bf16 && (ncols & 7) == 0) {
+            bf16* dst = reinterpret_cast<bf16*>(p.C) + c_off + (long)row * p.ldc + col0;
+            if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8)
+                if (j < ncols) Vec8<bf16>::store(dst + j, v + j);
+              continue;
+            }
+          }
+          {
+            float vv[32];                            // address-taken copy: keeps v[] itself in registers for the hot paths
+#pragma unroll
+            for (int j = 0; j < 32; ++j) vv[j] = v[j];
+            epilogue_generic(p, vv, row, col0, ncols, c_off);
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
     }
+    if (store_pending && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // stores complete before the CTA exits
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
 }
 
@@ -535,33 +527,44 @@ int make_map(CUtensorMap* out, const void* ptr, long inner, long outer, long ld,
 }
 
 // Tile width: minimise the estimated makespan of the static round-robin tile schedule,
-//   waves(BN) * bytes-moved-per-tile(BN)   with  waves = ceil(m_tiles * n_tiles * batch / #SM),
-// instead of only minimising padding: e.g. M = 9600, N = 288 gives 75 x 2 = 150 tiles with BN = 144 (two CTAs run two
-// tiles -> 2 waves of a 144-wide tile) but 225 tiles of width 96 (2 waves of a tile that is 1/3 cheaper).
-int pick_bn_padding(int N) {      // widest tile with the least padding (split-K problems: the reduction split fills the machine)
-  if (N <= 256) return ((N + 15) / 16) * 16;
-  int best = 256; long best_cost = (long)dfb_cdiv(N, 256) * 256;
-  for (int bn = 240; bn >= 64; bn -= 16) {
+//   waves(BN) * bytes-moved-per-tile(BN)   with  waves = ceil(m_tiles * n_tiles * batch / slots),  slots = #SM * CTAs per SM,
+// instead of only minimising padding.  `bn_cap` is the widest tile the variant's shared-memory budget leaves a pipeline for;
+// `step64`: the TMA-store epilogue works on 64-column boxes, so interior tile boundaries must be multiples of 64 (a single
+// tile may have any width that is a multiple of 16: its ragged last box is clipped by the tensor map).
+int pick_bn_padding(int N, int bn_cap) {      // widest tile with the least padding (split-K problems: the reduction split fills the machine)
+  if (N <= bn_cap) return ((N + 15) / 16) * 16;
+  int best = bn_cap; long best_cost = (long)dfb_cdiv(N, bn_cap) * bn_cap;
+  for (int bn = bn_cap - 16; bn >= 64; bn -= 16) {
     const long cost = (long)dfb_cdiv(N, bn) * bn;
     if (cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
 }
 
-int pick_bn(int N, int m_tiles, int kb, int batch, int num_sms, bool b_mn_major) {
-  const int n_max = N <= 256 ? ((N + 15) / 16) * 16 : 256;
-  int best = n_max;
+int pick_bn(int N, int m_tiles, int kb, int batch, int slots, bool b_mn_major, int bn_cap, bool step64) {
+  const int n16 = ((N + 15) / 16) * 16;
+  int best = 0;
   double best_cost = 1e300;
-  for (int bn = n_max; bn >= 32; bn -= 16) {
-    if (b_mn_major && bn < 64 && N >= 64) continue;
+  auto consider = [&](int bn) {
+    if (bn > bn_cap || bn < 16) return;
+    if (b_mn_major && bn < 64 && N >= 64) return;
     const long n_tiles = (N + bn - 1) / bn;
     const long tiles = (long)m_tiles * n_tiles * batch;
-    const long waves = (tiles + num_sms - 1) / num_sms;
+    const long waves = (tiles + slots - 1) / slots;
     const double per_tile = (double)kb * (16384.0 + 128.0 * bn) + 256.0 * bn + 24000.0;
     const double cost = (double)waves * per_tile;
-    if (cost < best_cost * 0.97) { best_cost = cost; best = bn; }     // prefer wider tiles unless clearly (3 %) worse
-  }
+    if (cost < best_cost * 0.97) { best_cost = cost; best = bn; }     // candidates come widest first: prefer wider tiles unless clearly (3 %) worse
+  };
+  if (n16 <= bn_cap) consider(n16);                                    // one tile spanning N
+  for (int bn = bn_cap / (step64 ? 64 : 16) * (step64 ? 64 : 16); bn >= (step64 ? 64 : 32); bn -= (step64 ? 64 : 16)) consider(bn);
+  if (best == 0) best = n16 <= bn_cap ? n16 : (step64 ? 64 : 32);
   return best;
+}
+
+int next_pow2_cols(int c) {
+  int v = 32;
+  while (v < c) v <<= 1;
+  return v;
 }
 
 }  // namespace
@@ -574,25 +577,28 @@ bool dfb_gemm_tc_supported(const dfb200_gemm_args& g) {
   if ((g.lda % 8) || (g.ldb % 8)) return false;
   if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) return false;
   if (g.accumulate && g.out_dtype != 0) return false;
-  if (g.epi_mode != 0) {
-    if (g.out_dtype != 1 || g.batch != 1 || g.splitk > 1 || g.accumulate || g.act != 0 || g.aux == nullptr) return false;
-    if ((g.ld_aux % 8) || (reinterpret_cast<uintptr_t>(g.aux) & 15)) return false;
-    if (g.epi_mode == 2 && (g.out2 == nullptr || g.ls == nullptr || (g.ld_out2 % 8) || g.rows_per_sample <= 0)) return false;
-    if (g.epi_mode < 0 || g.epi_mode > 2) return false;
-  }
+  if (g.epi_mode != 0) return false;           // reserved (the fused gelu'/residual epilogues of round 1 were measured slower and removed)
   return true;
 }
 
 int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
-  DFB_REQUIRE(dfb_gemm_tc_supported(g), "gemm_tc: unsupported arguments (dtype=%d/%d batch=%d lda=%ld ldb=%ld)", g.a_dtype, g.b_dtype, g.batch, g.lda, g.ldb);
+  DFB_REQUIRE(dfb_gemm_tc_supported(g), "gemm_tc: unsupported arguments (dtype=%d/%d batch=%d lda=%ld ldb=%ld epi_mode=%d)", g.a_dtype, g.b_dtype, g.batch,
+              g.lda, g.ldb, g.epi_mode);
   static int num_sms = 0;
   static bool attr_set = false;
+  static int forced_bn = 0, forced_stages = 0, forced_epi = 0;
   if (!attr_set) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { dfb_set_error("gemm_tc smem attr: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
+    // tuning aids (tools/gemm_bn_sweep.py, tools/gemm_replay.py), read once
+    if (const char* v = getenv("DFB200_TC_BN")) forced_bn = atoi(v);
+    if (const char* v = getenv("DFB200_TC_STAGES")) forced_stages = atoi(v);
+    if (const char* v = getenv("DFB200_TC_EPI")) forced_epi = atoi(v);
     attr_set = true;
   }
   TcParams p;
@@ -602,25 +608,37 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   p.kb_total = dfb_cdiv(g.K, BK);
   p.a_mn_major = g.transA ? 1 : 0;   // A stored [K, M]  -> M contiguous
   p.b_mn_major = g.transB ? 0 : 1;   // B stored [K, N]  -> N contiguous
-  {
-    // wgrad-like problems will be split along K; their tile count is multiplied by the split factor later, so only
-    // the un-split (forward / dgrad) shapes are tuned for wave quantisation
-    const bool will_split = (g.splitk == 0 && g.out_dtype == 0 && g.act == 0 && p.kb_total >= 16) || g.splitk > 1;
-    p.BN = will_split ? pick_bn_padding(g.N) : pick_bn(g.N, p.m_tiles, p.kb_total, g.batch, num_sms, p.b_mn_major);
-    static const int forced_bn = [] { const char* e = getenv("DFB200_TC_BN"); return e ? atoi(e) : 0; }();   // tuning aid (tools/gemm_bn_sweep.py), read once
-    if (forced_bn >= 16 && forced_bn <= 256 && forced_bn % 16 == 0 && !(p.b_mn_major && forced_bn < 64 && g.N >= 64)) p.BN = forced_bn;
-  }
-  p.n_tiles = dfb_cdiv(g.N, p.BN);
   p.C = g.C; p.ldc = g.ldc; p.bias = g.bias;
   p.batch = g.batch; p.strideC = g.strideC;
-  p.epi_mode = g.epi_mode; p.aux = g.aux; p.ld_aux = g.ld_aux; p.out2 = g.out2; p.ld_out2 = g.ld_out2;
-  p.ls = g.ls; p.scale_b = g.scale_b; p.rows_per_sample = g.rows_per_sample;
   p.out_bf16 = g.out_dtype == 1; p.act = g.act; p.act_col_start = g.act_col_start; p.accumulate = g.accumulate;
+  // wgrad-like problems are split along K; their tile count is multiplied by the split factor later, so only the un-split
+  // (forward / dgrad) shapes are tuned for wave quantisation
+  const bool will_split = (g.splitk == 0 && g.out_dtype == 0 && g.act == 0 && p.kb_total >= 16) || g.splitk > 1;
+  // bf16 C through TMA: 16-byte aligned base / leading dimension / batch stride
+  const bool can_tma_store = p.out_bf16 && !will_split && (g.ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 &&
+                             (g.batch == 1 || (g.strideC % 8) == 0);
+  // variant: two 192-thread CTAs per SM (EPI_WARPS = 4) when that puts every tile of an un-split problem into ONE wave that the
+  // one-CTA-per-SM variant would need two for (M = 9600 layers: 150 tiles on 148 SMs); everything else runs the deep-ring variant
+  // (measured per shape with tools/gemm_replay.py, profiles/r02_gemm_replay_variants.txt)
+  int epi_warps = 8;
+  if (!will_split) {
+    const int bn8 = pick_bn(g.N, p.m_tiles, p.kb_total, g.batch, num_sms, p.b_mn_major, 256, can_tma_store);
+    const int bn4 = pick_bn(g.N, p.m_tiles, p.kb_total, g.batch, 2 * num_sms, p.b_mn_major, 192, can_tma_store);
+    const long t8 = (long)p.m_tiles * dfb_cdiv(g.N, bn8) * g.batch, t4 = (long)p.m_tiles * dfb_cdiv(g.N, bn4) * g.batch;
+    if (t8 > num_sms && t4 <= 2L * num_sms) epi_warps = 4;
+  }
+  if (forced_epi == 4 || forced_epi == 8) epi_warps = forced_epi;
+  const int ctas_per_sm = epi_warps == 4 ? 2 : 1;
+  const int bn_cap = epi_warps == 4 ? 192 : 256;
+  p.BN = will_split ? pick_bn_padding(g.N, bn_cap) : pick_bn(g.N, p.m_tiles, p.kb_total, g.batch, num_sms * ctas_per_sm, p.b_mn_major, bn_cap, can_tma_store);
+  if (forced_bn >= 16 && forced_bn <= bn_cap && forced_bn % 16 == 0 && !(p.b_mn_major && forced_bn < 64 && g.N >= 64)) p.BN = forced_bn;
+  p.n_tiles = dfb_cdiv(g.N, p.BN);
+  p.tma_store = can_tma_store && ((p.BN % 64) == 0 || p.n_tiles == 1);
   // split-K when the output has too few tiles to fill the machine and the reduction is long (wgrad)
   int splits = 1;
   const long tiles = (long)p.m_tiles * p.n_tiles * g.batch;
   if (g.splitk > 1) splits = g.splitk;
-  else if (g.splitk == 0 && g.out_dtype == 0 && g.act == 0 && g.epi_mode == 0 && tiles * 2 <= num_sms && p.kb_total >= 16)
+  else if (g.splitk == 0 && g.out_dtype == 0 && g.act == 0 && tiles * 2 <= num_sms && p.kb_total >= 16)
     splits = (int)min((long)p.kb_total / 4, (long)(num_sms / tiles));
   if (splits < 1) splits = 1;
   if (splits > 1) DFB_REQUIRE(g.out_dtype == 0 && g.act == 0, "gemm_tc split-K needs fp32 output without activation");
@@ -632,7 +650,7 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
       if (e != cudaSuccess) { dfb_set_error("memset2d: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
     }
   }
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
   int rc;
   const long sA = g.batch > 1 ? g.strideA : (long)g.lda * (g.transA ? g.K : g.M);
   const long sB = g.batch > 1 ? g.strideB : (long)g.ldb * (g.transB ? g.N : g.K);
@@ -642,18 +660,31 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   if (g.transB) rc = make_map(&tmB, g.B, g.K, g.N, g.ldb, 64, p.BN, g.batch, sB);        // stored [N, K]
   else rc = make_map(&tmB, g.B, g.N, g.K, g.ldb, 64, 64, g.batch, sB);                  // stored [K, N]
   if (rc) return rc;
+  if (p.tma_store) {
+    rc = make_map(&tmC, g.C, g.N, g.M, g.ldc, 64, 32, g.batch, g.batch > 1 ? g.strideC : (long)g.ldc * g.M);     // [32 rows x 64 columns] boxes
+    if (rc) return rc;
+  } else {
+    tmC = tmA;                                  // unused by the kernel
+  }
   const long total = tiles * p.splits;
-  const int grid = (int)min((long)num_sms, total);
-  // pipeline depth: no deeper than the k-loop of one tile needs (smaller smem request for the many short-K GEMMs)
-  static int forced_stages = -1;
-  if (forced_stages < 0) { const char* e = getenv("DFB200_TC_STAGES"); forced_stages = e ? atoi(e) : 0; }
+  const int grid = (int)min((long)num_sms * ctas_per_sm, total);
+  // accumulator ring in tensor memory: stages `acc_stride` columns apart (64-column granules: the TMA-store epilogue reads whole boxes)
+  p.acc_stride = ((p.BN + 63) / 64) * 64;
+  const int tmem_budget = epi_warps == 4 ? 256 : 512;
+  p.acc_stages = (2 * p.acc_stride <= tmem_budget && total > grid) ? 2 : 1;     // one tile per CTA needs no second stage
+  p.tmem_cols = next_pow2_cols(p.acc_stages * p.acc_stride);
+  // pipeline depth: as deep as the variant's shared-memory budget allows, but no deeper than the k-blocks this CTA will ever load
   const int b_bytes = p.b_mn_major ? ((p.BN + 63) / 64) * 8192 : ((p.BN * 128 + 1023) / 1024) * 1024;   // 1024-B aligned (swizzle atom)
   p.stage_bytes = A_STAGE_BYTES + b_bytes;
-  const int fixed = EPI_STAGE_BYTES + 1024 + 512;
-  p.stages = (MAX_SMEM - fixed) / p.stage_bytes;
+  const int fixed = epi_warps * EPI_WARP_BYTES + 1024 + 512;
+  p.stages = ((epi_warps == 4 ? SMALL_SMEM : MAX_SMEM) - fixed) / p.stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  const long kb_per_cta = (long)dfb_cdiv(total, grid) * p.kb_per_split;
+  if (p.stages > kb_per_cta) p.stages = (int)kb_per_cta;
   if (forced_stages > 0 && forced_stages < p.stages) p.stages = forced_stages;
+  DFB_REQUIRE(p.stages >= 1, "gemm_tc: tile %d x %d does not fit the shared-memory budget", BM, p.BN);
   const int smem_bytes = p.stages * p.stage_bytes + fixed;
-  dfb_launch(gemm_tc_kernel, grid, NUM_THREADS, smem_bytes, st, tmA, tmB, p);
+  if (epi_warps == 4) dfb_launch(gemm_tc_kernel<4>, grid, 64 + 32 * 4, smem_bytes, st, tmA, tmB, tmC, p);
+  else dfb_launch(gemm_tc_kernel<8>, grid, 64 + 32 * 8, smem_bytes, st, tmA, tmB, tmC, p);
   return dfb_check_launch("gemm_tc");
 }

@@ -18,11 +18,6 @@ from .runtime import GradArena, backend_for
 
 F32 = torch.float32
 import os as _os
-# fused GEMM epilogues exist (gemm_tc.cu epi_mode 1/2) but measured slower on B200 for these wide-N / short-K GEMMs, whose
-# epilogue is already the critical resource (A/B in profiles/r01_ab_fused_epilogues.txt) -> off by default
-_FUSE_RES = _os.environ.get("DFB200_FUSE_RES", "0") == "1"
-_FUSE_RES_MAXM = int(_os.environ.get("DFB200_FUSE_RES_MAXM", "0"))     # ... but always for GEMMs with at most this many rows (latency-bound stages)
-_FUSE_GG = _os.environ.get("DFB200_FUSE_GG", "0") == "1"
 _FUSE_GAA = _os.environ.get("DFB200_FUSE_GAA", "1") == "1"    # one-launch attention core (csrc/gaa_fused.cu); 0 = GEMM + softmax chain
 _SAVE_GP = _os.environ.get("DFB200_MLP_SAVE_GP", "1") == "1"    # fused MLP middle keeps GELU'(z) (bf16) instead of recomputing it in backward
 _FUSE_DW = _os.environ.get("DFB200_FUSE_DW", "1") == "1"      # fused MLP middle (csrc/mlp_dw.cu); 0 = the unfused chain, kept for A/B runs
@@ -38,7 +33,7 @@ def _lin(x, wb, T, act=K.ACT_NONE, act_col_start=0, out=None, out_dtype=None):
 _WGRAD_STREAM = None      # set by BlockFn.backward: weight/bias gradients are leaves of the backward graph
 
 
-def _lin_bwd(dy, x, w, dW, db, T, need_dx=True, dx_out=None, dx_epi=None):
+def _lin_bwd(dy, x, w, dW, db, T, need_dx=True, dx_out=None):
     """dW[N,K] = dy^T x (fp32, into the arena), db = colsum(dy), returns dx = dy @ W.
     The parameter gradients go to the wgrad side stream when one is active (nothing downstream consumes them)."""
     be = backend_for(T)
@@ -58,7 +53,7 @@ def _lin_bwd(dy, x, w, dW, db, T, need_dx=True, dx_out=None, dx_epi=None):
             K.colsum(dy, out=db)
     if not need_dx:
         return None
-    return K.gemm(dy, w, trans_a=False, trans_b=False, out=dx_out, out_dtype=T, backend=be, N=w.shape[1], epi=dx_epi)
+    return K.gemm(dy, w, trans_a=False, trans_b=False, out=dx_out, out_dtype=T, backend=be, N=w.shape[1])
 
 
 def _views(arena: GradArena, prefix: str, names):
@@ -240,13 +235,8 @@ def _mlp_fwd(x, pfx, st, P, sv, scale_b, pre=None):
     else:
         u, z = K.dwconv_fwd(h, P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, add_input=True, act=K.ACT_GELU, save_z=True)
     ls = P["layer_scale_2" if pfx == "mlp." else "layer_scale_2_e"]
-    if T == torch.bfloat16 and (_FUSE_RES or x.shape[0] <= _FUSE_RES_MAXM):      # fc2 + bias + layer-scale/DropPath residual in one tcgen05 epilogue (f kept for the dls gradient)
-        w2, b2 = st.packed[st.key + pfx + "fc2"]
-        out = torch.empty_like(x)
-        f = K.gemm(u, w2, trans_b=True, bias=b2, out_dtype=T, backend=K.TCGEN05, epi=("residual", x, out, ls, scale_b, H * W))
-    else:
-        f = _lin(u, st.packed[st.key + pfx + "fc2"], T)
-        out = K.scale_residual_fwd(x, f, ls, scale_b, H * W)
+    f = _lin(u, st.packed[st.key + pfx + "fc2"], T)
+    out = K.scale_residual_fwd(x, f, ls, scale_b, H * W)
     sv.update({pfx + "x": x, pfx + "mu": mu, pfx + "rs": rs, pfx + "hn": hn, pfx + "h": h, pfx + "u": u, pfx + "f": f, pfx + "z": z})
     return out
 
@@ -266,14 +256,9 @@ def _mlp_bwd(dout, pfx, st, P, sv, scale_b, G):
         dhn = _lin_bwd(dh, sv[pfx + "hn"], st.packed[st.key + pfx + "fc1"][0], G[pfx + "fc1.weight"], None, T)
         return K.layernorm_bwd(dhn, sv[pfx + "x"], P[pfx + "norm.weight"], sv[pfx + "mu"], sv[pfx + "rs"], dout,
                                G[pfx + "norm.weight"], G[pfx + "norm.bias"])
-    if T == torch.bfloat16 and _FUSE_GG:      # dz = (df @ W2) * gelu'(z) in the dgrad GEMM's epilogue
-        dz = _lin_bwd(df, sv[pfx + "u"], w2, G[pfx + "fc2.weight"], G[pfx + "fc2.bias"], T, dx_epi=("gelu_grad", sv[pfx + "z"]))
-        dh = K.dwconv_bwd(dz, sv[pfx + "h"], P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, True, K.ACT_NONE,
-                          G[pfx + "pos.weight"], G[pfx + "pos.bias"], wgrad_stream=_WGRAD_STREAM)
-    else:
-        du = _lin_bwd(df, sv[pfx + "u"], w2, G[pfx + "fc2.weight"], G[pfx + "fc2.bias"], T)
-        dh = K.dwconv_bwd(du, sv[pfx + "h"], P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, True, K.ACT_GELU,
-                          G[pfx + "pos.weight"], G[pfx + "pos.bias"], z=sv[pfx + "z"], wgrad_stream=_WGRAD_STREAM)
+    du = _lin_bwd(df, sv[pfx + "u"], w2, G[pfx + "fc2.weight"], G[pfx + "fc2.bias"], T)
+    dh = K.dwconv_bwd(du, sv[pfx + "h"], P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, True, K.ACT_GELU,
+                      G[pfx + "pos.weight"], G[pfx + "pos.bias"], z=sv[pfx + "z"], wgrad_stream=_WGRAD_STREAM)
     w1 = st.packed[st.key + pfx + "fc1"][0]
     dhn = _lin_bwd(dh, sv[pfx + "hn"], w1, G[pfx + "fc1.weight"], G[pfx + "fc1.bias"], T)
     return K.layernorm_bwd(dhn, sv[pfx + "x"], P[pfx + "norm.weight"], sv[pfx + "mu"], sv[pfx + "rs"], dout,

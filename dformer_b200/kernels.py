@@ -65,8 +65,7 @@ GEMM_SHAPES_ONLY = False  # ... or just to collect the (shape, flops, bytes) cen
 
 
 def gemm(a, b, *, trans_a=False, trans_b=True, bias=None, out=None, out_dtype=None, act=ACT_NONE, act_col_start=0,
-         accumulate=False, backend=AUTO, splitk=0, alpha=0.0, M=None, N=None, K=None, epi=None):
-    # epi = ("gelu_grad", z) | ("residual", res_f32, out2_f32, ls, scale_b, rows_per_sample): fused tcgen05 epilogues
+         accumulate=False, backend=AUTO, splitk=0, alpha=0.0, M=None, N=None, K=None):
     """out[M,N] = act(alpha * op(a) @ op(b) + bias).  a/b are 2-D with unit inner stride (row slices allowed)."""
     _chk(a), _chk(b)
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
@@ -88,13 +87,6 @@ def gemm(a, b, *, trans_a=False, trans_b=True, bias=None, out=None, out_dtype=No
     g.transA, g.transB = int(trans_a), int(trans_b)
     g.a_dtype, g.b_dtype, g.out_dtype = dt(a), dt(b), dt(out)
     g.act, g.act_col_start, g.accumulate, g.backend, g.splitk, g.alpha = act, act_col_start, int(accumulate), backend, splitk, alpha
-    if epi is not None:
-        if epi[0] == "gelu_grad":
-            g.epi_mode, g.aux, g.ld_aux = 1, epi[1].data_ptr(), epi[1].stride(0)
-        else:
-            _, res, out2, ls, scale_b, rps = epi
-            g.epi_mode, g.aux, g.ld_aux, g.out2, g.ld_out2 = 2, res.data_ptr(), res.stride(0), out2.data_ptr(), out2.stride(0)
-            g.ls, g.scale_b, g.rows_per_sample = ls.data_ptr(), _p(scale_b), rps
     if GEMM_PROFILE is not None and GEMM_SHAPES_ONLY:
         tc = backend != SIMT and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
         GEMM_PROFILE.append((None, None, 2.0 * M * N * K, a.element_size() * M * K + b.element_size() * N * K + out.element_size() * M * N, tc,

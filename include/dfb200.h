@@ -55,10 +55,8 @@ typedef struct dfb200_gemm_args {
   int backend;
   int splitk;            /* 0 = auto, 1 = off, >1 = forced number of reduction splits */
   float alpha;           /* scales the product before bias/activation (0 is treated as 1) */
-  /* fused epilogues of the tcgen05 backend (bf16 output):
-   *   epi_mode 1: C = bf16(acc + bias) * gelu'(aux[m,n])              aux: bf16 pre-activation (MLP backward, DFormer.py:64)
-   *   epi_mode 2: C = f = bf16(acc + bias);  out2[m,n] = aux[m,n] + scale_b[m / rows_per_sample] * ls[n] * f
-   *               aux: fp32 residual, out2: fp32 new residual (layer-scale + DropPath residual, DFormer.py:173-179) */
+  /* reserved (must be 0 / NULL): round 1 carried fused gelu'-multiply and layer-scale-residual epilogues here; they were
+   * measured slower than the separate streaming kernels on B200 and removed.  The fields stay so that the struct layout is stable. */
   int epi_mode;
   const void* aux; long ld_aux;
   void* out2; long ld_out2;

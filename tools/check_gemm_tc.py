@@ -59,34 +59,34 @@ def main():
     good = err < 0.05
     ok &= good
     print(f"{'OK ' if good else 'BAD'} wgrad accumulate err={err:.4g}")
-    # fused epilogues
-    for (M, N, K) in [(1000, 768, 96), (300, 96, 768), (4800, 192, 1536)]:
+    # TMA-store epilogue: ragged N / M tails, relu + bias, column slices at 64-column and odd (16-byte aligned) offsets, several n-tiles
+    for (M, N, K, off, width) in [(1000, 720, 288, 0, 720), (333, 432, 576, 64, 512), (4800, 144, 144, 8, 160), (130, 48, 40, 48, 96),
+                                  (9600, 288, 1152, 0, 288), (257, 1152, 288, 128, 1408), (19200, 40, 512, 0, 40)]:
         a = torch.randn(M, K, device=dev).bfloat16()
-        w = (torch.randn(K, N, device=dev) * 0.2).bfloat16()          # dgrad layout: stored [K_red, N]
-        z = torch.randn(M, N, device=dev).bfloat16()
-        out = k.gemm(a, w, trans_a=False, trans_b=False, backend=k.TCGEN05, out_dtype=torch.bfloat16, epi=("gelu_grad", z))
-        du = (a.float() @ w.float()).bfloat16().float()
-        zr = z.float().requires_grad_(True)
-        torch.nn.functional.gelu(zr).sum().backward()
-        ref = du * zr.grad
-        err = (out.float() - ref).abs().max().item()
-        good = err <= 2e-2 * max(1.0, ref.abs().max().item())
-        ok &= good
-        print(f"{'OK ' if good else 'BAD'} epilogue gelu_grad M={M} N={N} K={K} err={err:.4g}")
-        wl = (torch.randn(N, K, device=dev) * 0.2).bfloat16()
+        w = (torch.randn(N, K, device=dev) * 0.2).bfloat16()
         bias = torch.randn(N, device=dev)
-        res = torch.randn(M, N, device=dev)
-        ls = torch.randn(N, device=dev)
-        rps = M // 4 if M % 4 == 0 else M
-        sb = torch.tensor([0.0, 1.25, 1.25, 1.0], device=dev)[: M // rps]
-        out2 = torch.empty(M, N, device=dev)
-        f = k.gemm(a, wl, trans_b=True, bias=bias, backend=k.TCGEN05, out_dtype=torch.bfloat16, epi=("residual", res, out2, ls, sb, rps))
-        fref = (a.float() @ wl.float().t() + bias).bfloat16().float()
-        xref = res + sb.repeat_interleave(rps)[:, None] * ls * fref
-        e1, e2 = (f.float() - fref).abs().max().item(), (out2 - xref).abs().max().item()
-        good = e1 <= 2e-2 * max(1.0, fref.abs().max().item()) and e2 <= 3e-2 * max(1.0, xref.abs().max().item())
+        outbuf = torch.full((M, width), 7.0, device=dev, dtype=torch.bfloat16)
+        k.gemm(a, w, trans_b=True, bias=bias, backend=k.TCGEN05, out=outbuf[:, off:off + N], act=2)
+        ref = torch.relu(a.float() @ w.float().t() + bias)
+        err = (outbuf[:, off:off + N].float() - ref).abs().max().item()
+        untouched = (outbuf[:, :off] == 7).all().item() and (outbuf[:, off + N:] == 7).all().item()
+        good = err <= 2e-2 * max(1.0, ref.abs().max().item()) and untouched
         ok &= good
-        print(f"{'OK ' if good else 'BAD'} epilogue residual M={M} N={N} K={K} err_f={e1:.4g} err_x={e2:.4g}")
+        print(f"{'OK ' if good else 'BAD'} tma-store slice M={M} N={N} K={K} off={off} width={width} err={err:.4g} untouched={untouched}", flush=True)
+    # strided-batched bf16 output (NMF products)
+    for (Bz, M, N, K, ta, tb) in [(3, 4800, 64, 512, False, False), (2, 512, 64, 4800, True, False), (3, 300, 512, 64, False, True)]:
+        a = (torch.randn(Bz, K, M, device=dev) if ta else torch.randn(Bz, M, K, device=dev)).bfloat16()
+        b = (torch.randn(Bz, N, K, device=dev) if tb else torch.randn(Bz, K, N, device=dev)).bfloat16()
+        for od in (torch.bfloat16, torch.float32):
+            out = torch.empty(Bz, M, N, device=dev, dtype=od)
+            k.bgemm(a, b, out, trans_a=ta, trans_b=tb, M=M, N=N, K=K)
+            A = a.float().transpose(1, 2) if ta else a.float()
+            Bm = b.float().transpose(1, 2) if tb else b.float()
+            ref = A @ Bm
+            err = (out.float() - ref).abs().max().item()
+            good = err <= (2e-2 if od == torch.bfloat16 else 2e-3) * max(1.0, ref.abs().max().item())
+            ok &= good
+            print(f"{'OK ' if good else 'BAD'} batched Bz={Bz} M={M} N={N} K={K} ta={int(ta)} tb={int(tb)} out={od} err={err:.4g}", flush=True)
     # timing of a few representative shapes
     for (M, N, K) in [(153600, 768, 96), (153600, 96, 768), (38400, 1536, 192), (38400, 192, 1536), (9600, 1152, 288), (38400, 512, 1056), (8192, 8192, 8192)]:
         a = torch.randn(M, K, device=dev).bfloat16()
