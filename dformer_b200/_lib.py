@@ -77,6 +77,13 @@ SIGNATURES = {
     "dfb200_mu_update_bwd": [P, P, P, P, F, L, P, I, P, L, I, P, I, P],
     "dfb200_cast": [P, I, P, I, L, P],
     "dfb200_cast2d": [P, I, L, P, I, L, L, I, P],
+    "dfb200_sym_cast": [P, I, P, I, I, I, P],
+    "dfb200_peer_alloc": [P],
+    "dfb200_peer_free": [P],
+    "dfb200_peer_export": [P, P],
+    "dfb200_peer_open": [P, P],
+    "dfb200_peer_close": [P],
+    "dfb200_peer_allreduce": [P, P, I, I, P, I, I, P],
     "dfb200_axpy": [P, I, F, P, I, L, P],
     "dfb200_upsample_ce_fwd": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, P],
     "dfb200_upsample_ce_bwd_sep": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, P, I, P],

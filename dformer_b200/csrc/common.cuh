@@ -62,6 +62,26 @@ inline void dfb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface through dfb_check_launch (cudaPeekAtLastError)
 }
 
+// same with a thread-block cluster of `cluster_x` CTAs along x (gridDim.x must be a multiple of it)
+template <typename... KArgs, typename... Args>
+inline void dfb_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = dfb_pdl_enabled() ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f(float v);

@@ -375,6 +375,18 @@ __global__ void cast2d_kernel(const TI* __restrict__ in, long ld_in, TO* __restr
     out[r * ld_out + c] = from_f<TO>(to_f(in[r * ld_in + c]));
   }
 }
+// out[b, i, j] = in[b, i, j] + in[b, j, i] for a batch of small square matrices (NMF backward: the gradient of BtB = B^T B enters
+// both factors, so bases @ (G + G^T) replaces two products)
+template <typename TI, typename TO>
+__global__ void sym_cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, int batch, int R) {
+  pdl_sync();
+  const long n = (long)batch * R * R;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long b = i / (R * R);
+    const int rc = (int)(i - b * R * R), r = rc / R, c = rc - r * R;
+    out[i] = from_f<TO>(to_f(in[i]) + to_f(in[b * R * R + (long)c * R + r]));
+  }
+}
 template <typename TI, typename TO>
 __global__ void axpy_kernel(const TI* __restrict__ x, float alpha, TO* __restrict__ y, long n) {
   pdl_sync();
@@ -561,6 +573,16 @@ extern "C" int dfb200_cast2d(const void* in, int in_dtype, long ld_in, void* out
   else if (in_dtype == 1 && out_dtype == 1) dfb_launch(cast2d_kernel<bf16, bf16>, g, EW_THREADS, 0, ST, (const bf16*)in, ld_in, (bf16*)out, ld_out, rows, cols);
   else { dfb_set_error("cast2d: bad dtypes"); return DFB_ERR_ARG; }
   return dfb_check_launch("cast2d");
+}
+extern "C" int dfb200_sym_cast(const void* in, int in_dtype, void* out, int out_dtype, int batch, int R, void* stream) {
+  const long n = (long)batch * R * R;
+  if (n <= 0) return DFB_OK;
+  const int g = ew_grid(n, 1);
+  if (in_dtype == 0 && out_dtype == 0) dfb_launch(sym_cast_kernel<float, float>, g, EW_THREADS, 0, ST, (const float*)in, (float*)out, batch, R);
+  else if (in_dtype == 0 && out_dtype == 1) dfb_launch(sym_cast_kernel<float, bf16>, g, EW_THREADS, 0, ST, (const float*)in, (bf16*)out, batch, R);
+  else if (in_dtype == 1 && out_dtype == 1) dfb_launch(sym_cast_kernel<bf16, bf16>, g, EW_THREADS, 0, ST, (const bf16*)in, (bf16*)out, batch, R);
+  else { dfb_set_error("sym_cast: bad dtypes"); return DFB_ERR_ARG; }
+  return dfb_check_launch("sym_cast");
 }
 extern "C" int dfb200_axpy(const void* x, int x_dtype, float alpha, void* y, int y_dtype, long n, void* stream) {
   const int g = ew_grid(n, 4);

@@ -9,14 +9,15 @@
 // layout: a warp owns 16 query rows and a whole pixel chunk, so row maxima / sums never leave the warp's quads and the
 // probabilities go from accumulator registers straight into the A operand of the next product.
 //
-//   forward   CTA = 128 pixels of one (image, head), 4 warps x 16 query rows: S -> local max / sum -> P~ (bf16) -> P~ V,
-//             written as an unnormalised partial next to (max, sum); the last CTA of the (image, head) (atomic ticket)
-//             merges the partials flash-decoding style and stores O and the row log-sum-exp.
-//   backward  CTA = 64 pixels: phase 1 (warp = 16 query rows) recomputes P from the saved log-sum-exp, dP = dO V^T,
-//             dS = P o (dP - rowsum(dO o O)); dQ partial = dS K goes out through fp32 atomics; P and dS are parked in
-//             shared memory (bf16); phase 2 (warp = 16 pixels) dV = P^T dO, dK = dS^T Q, complete per pixel.
+//   forward   the CTAs of a thread-block cluster share one (image, head); each walks 128-pixel chunks, 4 warps x 16 query rows:
+//             S -> online max / sum -> P~ (bf16) -> O~ += P~ V; the partials are merged flash-decoding style through distributed
+//             shared memory after one cluster barrier (no HBM scratch, no atomics).
+//   backward  64-pixel chunks: phase 1 (warp = 16 query rows) recomputes P from the saved log-sum-exp, dP = dO V^T,
+//             dS = P o (dP - rowsum(dO o O)), dQ += dS K in registers; P and dS are parked in shared memory (bf16); phase 2
+//             (warp = 16 pixels) dV = P^T dO, dK = dS^T Q, complete per pixel.  dQ is reduced across the cluster through DSMEM.
 // Nothing of size 49 x HW reaches HBM in either direction.
 #include <string.h>
+#include <cooperative_groups.h>
 
 #include "common.cuh"
 #include "dfb200_internal.h"
@@ -115,271 +116,347 @@ __device__ __forceinline__ void mma_regs_by_cols(const uint32_t (*pa)[4], const 
   }
 }
 
+// 8-byte cp.async with zero fill (src_bytes = 0 -> the destination is zeroed, nothing is read)
+__device__ __forceinline__ void cp_async8(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_addr(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// asynchronous copy of `ROWS` pixel rows of one head's K and V slices into a shared-memory buffer pair (real columns only: the
+// zero padding of columns D..DP-1 is written once at kernel start and never overwritten); rows >= nvalid are zero-filled
+template <int D, int ROWS>
+__device__ __forceinline__ void prefetch_kv(const bf16* __restrict__ rows, long pitch, int Cp, int nvalid, bf16* __restrict__ Ks, bf16* __restrict__ Vs) {
+  constexpr int W8 = Geo<D>::W8, PITCH = Geo<D>::PITCH;
+#pragma unroll
+  for (int i = threadIdx.x; i < ROWS * W8; i += NT) {
+    const int r = i / W8, w = i % W8;
+    const bool ok = r < nvalid;
+    const bf16* src = rows + (ok ? (long)r * pitch : 0) + 4 * w;
+    cp_async8(Ks + r * PITCH + 4 * w, src, ok ? 8 : 0);
+    cp_async8(Vs + r * PITCH + 4 * w, src + Cp, ok ? 8 : 0);
+  }
+}
+template <int D, int ROWS>
+__device__ __forceinline__ void zero_pad_cols(bf16* __restrict__ buf) {
+  constexpr int W8 = Geo<D>::W8, WP8 = Geo<D>::WP8, PITCH = Geo<D>::PITCH;
+  if constexpr (WP8 > W8) {
+    for (int i = threadIdx.x; i < ROWS * (WP8 - W8); i += NT) {
+      const int r = i / (WP8 - W8), w = W8 + i % (WP8 - W8);
+      *reinterpret_cast<uint2*>(buf + r * PITCH + 4 * w) = make_uint2(0u, 0u);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ forward
+// grid (nsplit, B * heads), thread-block cluster (nsplit, 1, 1): the CTAs of a cluster share one (image, head); CTA `split` walks the
+// 128-pixel chunks split, split + nsplit, ... with an online softmax (K / V double-buffered through cp.async), parks its partial
+// (O~, max, sum) in its own shared memory, and after one cluster barrier every CTA merges a slice of the 49 rows by reading its
+// peers' partials through distributed shared memory.  No scratch buffer in HBM, no atomics, no tickets.
 template <int D>
 __global__ void __launch_bounds__(NT) gaa_mma_fwd_kernel(const bf16* __restrict__ m, const bf16* __restrict__ kv, int HW, int heads, float scale, int nchunks,
-                                                        float* __restrict__ out, float* __restrict__ lse, float* __restrict__ part, int* __restrict__ counters) {
-  pdl_sync();
-  constexpr int DP = Geo<D>::DP, PITCH = Geo<D>::PITCH, PC = 128, PS = D + 4;
+                                                        float* __restrict__ out, float* __restrict__ lse) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  constexpr int DP = Geo<D>::DP, PITCH = Geo<D>::PITCH, PC = 128;
   extern __shared__ __align__(16) uint8_t smraw[];
   bf16* Qs = reinterpret_cast<bf16*>(smraw);          // [64][PITCH]
-  bf16* Ks = Qs + QR * PITCH;                          // [PC][PITCH]
-  bf16* Vs = Ks + PC * PITCH;                          // [PC][PITCH]
-  float* ms = reinterpret_cast<float*>(Vs + PC * PITCH);   // [64] merge: 1 / total sum
-  float* pm = ms + QR;                                 // [nchunks][49] merge staging (chunk maxima -> weights)
-  float* pl = pm + nchunks * NQ;                       // [nchunks][49] chunk sums
-  __shared__ int s_last;
+  bf16* KV = Qs + QR * PITCH;                          // 2 x (K [PC][PITCH], V [PC][PITCH])
+  float* Op = reinterpret_cast<float*>(KV + 4 * PC * PITCH);   // [64][DP] partial context
+  float* mp = Op + QR * DP;                            // [64] running max
+  float* lp = mp + QR;                                 // [64] running sum
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int bh = blockIdx.y, b = bh / heads, head = bh % heads, c = blockIdx.x;
+  const int bh = blockIdx.y, b = bh / heads, head = bh % heads;
+  const int nsplit = gridDim.x, split = blockIdx.x;
   const int Cp = heads * D;
-  const int nvalid = min(PC, HW - c * PC);
+  const int n_my = (nchunks - split + nsplit - 1) / nsplit;
+  zero_pad_cols<D, 4 * PC>(KV);                        // touches no global memory: overlaps the previous kernel's tail under PDL
+  pdl_sync();
+  const bf16* kvb = kv + (long)b * HW * 2 * Cp + head * D;
+  if (n_my > 0) prefetch_kv<D, PC>(kvb + (long)split * PC * 2 * Cp, 2L * Cp, Cp, min(PC, HW - split * PC), KV, KV + PC * PITCH);
+  cp_async_commit();
   stage_bf16<D, QR>(m + (long)b * NQ * Cp + head * D, Cp, NQ, Qs);
-  {
-    const bf16* rows = kv + ((long)b * HW + (long)c * PC) * 2 * Cp + head * D;
-    stage_bf16<D, PC>(rows, 2L * Cp, nvalid, Ks);
-    stage_bf16<D, PC>(rows + Cp, 2L * Cp, nvalid, Vs);
-  }
-  __syncthreads();
-  // ---- S = Q K^T for this warp's 16 query rows x 128 pixels
-  float s[PC / 8][4];
-#pragma unroll
-  for (int i = 0; i < PC / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-  mma_rows_by_rows<D, PC / 8>(Qs, warp * 16, Ks, s, lane);
-  // ---- local softmax statistics (rows g and g + 8 of the warp's slab; a row lives in the 4 lanes of a quad)
-  float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < PC / 8; ++i) {
-    const int col = i * 8 + 2 * t;
-    s[i][0] = col < nvalid ? s[i][0] * scale : -INFINITY;
-    s[i][1] = col + 1 < nvalid ? s[i][1] * scale : -INFINITY;
-    s[i][2] = col < nvalid ? s[i][2] * scale : -INFINITY;
-    s[i][3] = col + 1 < nvalid ? s[i][3] * scale : -INFINITY;
-    mx0 = fmaxf(mx0, fmaxf(s[i][0], s[i][1]));
-    mx1 = fmaxf(mx1, fmaxf(s[i][2], s[i][3]));
-  }
-  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-  float l0 = 0.f, l1 = 0.f;
-  uint32_t pa[PC / 16][4];           // P~ = exp(S - local max) as A fragments (pixel k-steps of 16)
-#pragma unroll
-  for (int j = 0; j < PC / 16; ++j) {
-    float e[8];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      e[4 * h + 0] = __expf(s[2 * j + h][0] - mx0); e[4 * h + 1] = __expf(s[2 * j + h][1] - mx0);     // exp(-inf) = 0 for the padded tail
-      e[4 * h + 2] = __expf(s[2 * j + h][2] - mx1); e[4 * h + 3] = __expf(s[2 * j + h][3] - mx1);
-    }
-    l0 += e[0] + e[1] + e[4] + e[5];
-    l1 += e[2] + e[3] + e[6] + e[7];
-    pa[j][0] = pack2(e[0], e[1]); pa[j][1] = pack2(e[2], e[3]); pa[j][2] = pack2(e[4], e[5]); pa[j][3] = pack2(e[6], e[7]);
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  // ---- unnormalised partial context O~ = P~ V
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   float o[DP / 8][4];
 #pragma unroll
   for (int i = 0; i < DP / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-  mma_regs_by_cols<D, PC / 16>(pa, Vs, o, lane);
+  for (int it = 0; it < n_my; ++it) {
+    const int c = split + it * nsplit;
+    const int nvalid = min(PC, HW - c * PC);
+    if (it + 1 < n_my) {
+      const int cn = c + nsplit;
+      bf16* nb = KV + ((it + 1) & 1) * 2 * PC * PITCH;
+      prefetch_kv<D, PC>(kvb + (long)cn * PC * 2 * Cp, 2L * Cp, Cp, min(PC, HW - cn * PC), nb, nb + PC * PITCH);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();                               // everything but the newest group (the next chunk) has landed
+    __syncthreads();
+    const bf16* Ks = KV + (it & 1) * 2 * PC * PITCH;
+    const bf16* Vs = Ks + PC * PITCH;
+    // ---- S = Q K^T for this warp's 16 query rows x 128 pixels
+    float s[PC / 8][4];
+#pragma unroll
+    for (int i = 0; i < PC / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+    mma_rows_by_rows<D, PC / 8>(Qs, warp * 16, Ks, s, lane);
+    // ---- online softmax (rows g and g + 8 of the warp's slab; a row lives in the 4 lanes of a quad)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < PC / 8; ++i) {
+      const int col = i * 8 + 2 * t;
+      s[i][0] = col < nvalid ? s[i][0] * scale : -INFINITY;
+      s[i][1] = col + 1 < nvalid ? s[i][1] * scale : -INFINITY;
+      s[i][2] = col < nvalid ? s[i][2] * scale : -INFINITY;
+      s[i][3] = col + 1 < nvalid ? s[i][3] * scale : -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(s[i][0], s[i][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[i][2], s[i][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);       // finite: pixel 0 of every chunk is real
+    const float al0 = __expf(m0 - mn0), al1 = __expf(m1 - mn1);   // exp(-inf) = 0 on the first chunk
+    m0 = mn0; m1 = mn1;
+    float cs0 = 0.f, cs1 = 0.f;
+    uint32_t pa[PC / 16][4];           // P~ = exp(S - running max) as A fragments (pixel k-steps of 16)
+#pragma unroll
+    for (int j = 0; j < PC / 16; ++j) {
+      float e[8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        e[4 * h + 0] = __expf(s[2 * j + h][0] - mn0); e[4 * h + 1] = __expf(s[2 * j + h][1] - mn0);
+        e[4 * h + 2] = __expf(s[2 * j + h][2] - mn1); e[4 * h + 3] = __expf(s[2 * j + h][3] - mn1);
+      }
+      cs0 += e[0] + e[1] + e[4] + e[5];
+      cs1 += e[2] + e[3] + e[6] + e[7];
+      pa[j][0] = pack2(e[0], e[1]); pa[j][1] = pack2(e[2], e[3]); pa[j][2] = pack2(e[4], e[5]); pa[j][3] = pack2(e[6], e[7]);
+    }
+    l0 = fmaf(l0, al0, cs0);           // per-lane partial sums (the quad is reduced once, after the last chunk)
+    l1 = fmaf(l1, al1, cs1);
+#pragma unroll
+    for (int i = 0; i < DP / 8; ++i) { o[i][0] *= al0; o[i][1] *= al0; o[i][2] *= al1; o[i][3] *= al1; }
+    mma_regs_by_cols<D, PC / 16>(pa, Vs, o, lane);
+    __syncthreads();                                   // this buffer is the prefetch target of the next iteration
+  }
+  cp_async_wait<0>();
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   {
     const int r0 = warp * 16 + g, r1 = r0 + 8;
-    float* d0 = part + (((long)bh * nchunks + c) * NQ + r0) * PS;
-    float* d1 = part + (((long)bh * nchunks + c) * NQ + r1) * PS;
 #pragma unroll
     for (int i = 0; i < DP / 8; ++i) {
       const int col = i * 8 + 2 * t;
-      if (col < D) {
-        if (r0 < NQ) *reinterpret_cast<float2*>(d0 + col) = make_float2(o[i][0], o[i][1]);
-        if (r1 < NQ) *reinterpret_cast<float2*>(d1 + col) = make_float2(o[i][2], o[i][3]);
-      }
+      *reinterpret_cast<float2*>(Op + r0 * DP + col) = make_float2(o[i][0], o[i][1]);
+      *reinterpret_cast<float2*>(Op + r1 * DP + col) = make_float2(o[i][2], o[i][3]);
     }
-    if (t == 0) {
-      if (r0 < NQ) *reinterpret_cast<float2*>(d0 + D) = make_float2(mx0, l0);
-      if (r1 < NQ) *reinterpret_cast<float2*>(d1 + D) = make_float2(mx1, l1);
-    }
+    if (t == 0) { mp[r0] = m0; lp[r0] = l0; mp[r1] = m1; lp[r1] = l1; }
   }
-  // ---- the last CTA of this (image, head) merges all partials
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(&counters[bh], 1) == nchunks - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const float* base = part + (long)bh * nchunks * NQ * PS;
-  for (int i = tid; i < nchunks * NQ; i += NT) {
-    const float2 ml = __ldcg(reinterpret_cast<const float2*>(base + (long)i * PS + D));
-    pm[i] = ml.x;
-    pl[i] = ml.y;
-  }
-  __syncthreads();
-  for (int r = warp; r < NQ; r += NT / 32) {
+  cluster.sync();
+  // ---- merge: this CTA finishes rows split, split + nsplit, ... (thread = one output element)
+  const int rows_mine = (NQ - split + nsplit - 1) / nsplit;
+  for (int idx = tid; idx < rows_mine * D; idx += NT) {
+    const int r = split + (idx / D) * nsplit, j = idx % D;
     float M = -INFINITY;
-    for (int cc = lane; cc < nchunks; cc += 32) M = fmaxf(M, pm[cc * NQ + r]);
-    M = warp_max(M);
-    float L = 0.f;
-    for (int cc = lane; cc < nchunks; cc += 32) {
-      const float w = __expf(pm[cc * NQ + r] - M);
-      L = fmaf(pl[cc * NQ + r], w, L);
-      pm[cc * NQ + r] = w;
+    for (int pr = 0; pr < nsplit; ++pr) M = fmaxf(M, cluster.map_shared_rank(mp, pr)[r]);
+    float L = 0.f, acc = 0.f;
+    for (int pr = 0; pr < nsplit; ++pr) {
+      const float w = __expf(cluster.map_shared_rank(mp, pr)[r] - M);     // a CTA that saw no chunk carries max = -inf -> weight 0
+      L = fmaf(cluster.map_shared_rank(lp, pr)[r], w, L);
+      acc = fmaf(cluster.map_shared_rank(Op, pr)[r * DP + j], w, acc);
     }
-    L = warp_sum(L);
-    if (lane == 0) { ms[r] = 1.0f / L; lse[(long)bh * NQ + r] = M + __logf(L); }
+    out[((long)b * NQ + r) * Cp + head * D + j] = acc / L;
+    if (j == 0) lse[(long)bh * NQ + r] = M + __logf(L);
   }
-  __syncthreads();
-  constexpr int D4 = D / 4;
-  for (int idx = tid; idx < NQ * D4; idx += NT) {
-    const int r = idx / D4, j = (idx % D4) * 4;
-    const float* src = base + (long)r * PS + j;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int cc = 0; cc < nchunks; ++cc) {
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (long)cc * NQ * PS));
-      const float w = pm[cc * NQ + r];
-      acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
-    }
-    const float inv = ms[r];
-    *reinterpret_cast<float4*>(out + ((long)b * NQ + r) * Cp + head * D + j) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-  }
-  if (tid == 0) counters[bh] = 0;                        // self-resetting ticket: the buffer is reusable by the next launch
+  cluster.sync();                                      // peers may still be reading this CTA's partial
 }
 
 // ------------------------------------------------------------------------------------------------ backward
+// Same cluster layout; a CTA walks 64-pixel chunks.  dQ partials stay in registers across the chunks and are reduced across the
+// cluster through distributed shared memory (plain stores to dm: no memset, no atomics).
 template <int D>
 __global__ void __launch_bounds__(NT) gaa_mma_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ lse,
-                                                        const bf16* __restrict__ m, const bf16* __restrict__ kv, int HW, int heads, float scale,
+                                                        const bf16* __restrict__ m, const bf16* __restrict__ kv, int HW, int heads, float scale, int nchunks,
                                                         float* __restrict__ dm, bf16* __restrict__ dkv) {
-  pdl_sync();
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   constexpr int DP = Geo<D>::DP, PITCH = Geo<D>::PITCH, PC = 64, PP = PC + 8;
   extern __shared__ __align__(16) uint8_t smraw[];
   bf16* Qs = reinterpret_cast<bf16*>(smraw);          // [64][PITCH]
   bf16* dOs = Qs + QR * PITCH;                         // [64][PITCH]
-  bf16* Ks = dOs + QR * PITCH;                         // [PC][PITCH]
-  bf16* Vs = Ks + PC * PITCH;                          // [PC][PITCH]
-  bf16* Ps = Vs + PC * PITCH;                          // [64][PP]  probabilities, query-major
+  bf16* KV = dOs + QR * PITCH;                         // 2 x (K [PC][PITCH], V [PC][PITCH])
+  bf16* Ps = KV + 4 * PC * PITCH;                      // [64][PP]  probabilities, query-major
   bf16* dSs = Ps + QR * PP;                            // [64][PP]
   float* lses = reinterpret_cast<float*>(dSs + QR * PP);   // [64]
   float* Dr = lses + QR;                               // [64] rowsum(dO o O) = rowsum(dP o P)
+  float* dqp = Dr + QR;                                // [64][DP] this CTA's dQ partial (read by the cluster)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int bh = blockIdx.y, b = bh / heads, head = bh % heads, c = blockIdx.x;
+  const int bh = blockIdx.y, b = bh / heads, head = bh % heads;
+  const int nsplit = gridDim.x, split = blockIdx.x;
   const int Cp = heads * D;
-  const int nvalid = min(PC, HW - c * PC);
+  const int n_my = (nchunks - split + nsplit - 1) / nsplit;
   const long qoff = (long)b * NQ * Cp + head * D;
+  zero_pad_cols<D, 4 * PC>(KV);
+  pdl_sync();
+  const bf16* kvb = kv + (long)b * HW * 2 * Cp + head * D;
+  if (n_my > 0) prefetch_kv<D, PC>(kvb + (long)split * PC * 2 * Cp, 2L * Cp, Cp, min(PC, HW - split * PC), KV, KV + PC * PITCH);
+  cp_async_commit();
   stage_bf16<D, QR>(m + qoff, Cp, NQ, Qs);
   stage_f32<D, QR>(dout + qoff, Cp, NQ, dOs);
-  {
-    const bf16* rows = kv + ((long)b * HW + (long)c * PC) * 2 * Cp + head * D;
-    stage_bf16<D, PC>(rows, 2L * Cp, nvalid, Ks);
-    stage_bf16<D, PC>(rows + Cp, 2L * Cp, nvalid, Vs);
-  }
   if (tid < QR) lses[tid] = tid < NQ ? lse[(long)bh * NQ + tid] : 0.f;
-  for (int r = warp; r < QR; r += NT / 32) {             // Dr from the fp32 sources (one warp per row)
+  {                                                      // Dr from the fp32 sources: a thread pair per row, all loads independent
+    const int r = tid >> 1, hf = tid & 1;
     float sdo = 0.f;
-    if (r < NQ)
-      for (int j = lane; j < D; j += 32) sdo = fmaf(dout[qoff + (long)r * Cp + j], out[qoff + (long)r * Cp + j], sdo);
-    sdo = warp_sum(sdo);
-    if (lane == 0) Dr[r] = sdo;
-  }
-  __syncthreads();
-  // ---- phase 1: this warp's 16 query rows x 64 pixels
-  {
-    float s[PC / 8][4], dp[PC / 8][4];
+    if (r < NQ) {
+      const float4* a4 = reinterpret_cast<const float4*>(dout + qoff + (long)r * Cp + hf * (D / 2));
+      const float4* b4 = reinterpret_cast<const float4*>(out + qoff + (long)r * Cp + hf * (D / 2));
+      if constexpr ((D / 2) % 4 == 0) {
 #pragma unroll
-    for (int i = 0; i < PC / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f; }
-    mma_rows_by_rows<D, PC / 8>(Qs, warp * 16, Ks, s, lane);
-    mma_rows_by_rows<D, PC / 8>(dOs, warp * 16, Vs, dp, lane);
-    const int r0 = warp * 16 + g, r1 = r0 + 8;
-    const float ls0 = lses[r0], ls1 = lses[r1], dr0 = Dr[r0], dr1 = Dr[r1];
-    const bool ok0 = r0 < NQ, ok1 = r1 < NQ;
-    uint32_t da[PC / 16][4];         // dS as A fragments for dQ = dS K
-#pragma unroll
-    for (int i = 0; i < PC / 8; ++i) {
-      const int col = i * 8 + 2 * t;
-      const bool c0 = col < nvalid, c1 = col + 1 < nvalid;
-      const float p00 = (ok0 && c0) ? __expf(fmaf(s[i][0], scale, -ls0)) : 0.f, p01 = (ok0 && c1) ? __expf(fmaf(s[i][1], scale, -ls0)) : 0.f;
-      const float p10 = (ok1 && c0) ? __expf(fmaf(s[i][2], scale, -ls1)) : 0.f, p11 = (ok1 && c1) ? __expf(fmaf(s[i][3], scale, -ls1)) : 0.f;
-      const float d00 = p00 * (dp[i][0] - dr0), d01 = p01 * (dp[i][1] - dr0), d10 = p10 * (dp[i][2] - dr1), d11 = p11 * (dp[i][3] - dr1);
-      const uint32_t pk0 = pack2(p00, p01), pk1 = pack2(p10, p11), dk0 = pack2(d00, d01), dk1 = pack2(d10, d11);
-      *reinterpret_cast<uint32_t*>(Ps + r0 * PP + col) = pk0;
-      *reinterpret_cast<uint32_t*>(Ps + r1 * PP + col) = pk1;
-      *reinterpret_cast<uint32_t*>(dSs + r0 * PP + col) = dk0;
-      *reinterpret_cast<uint32_t*>(dSs + r1 * PP + col) = dk1;
-      da[i >> 1][(i & 1) * 2 + 0] = dk0;
-      da[i >> 1][(i & 1) * 2 + 1] = dk1;
-    }
-    float dq[DP / 8][4];
-#pragma unroll
-    for (int i = 0; i < DP / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
-    mma_regs_by_cols<D, PC / 16>(da, Ks, dq, lane);
-#pragma unroll
-    for (int i = 0; i < DP / 8; ++i) {
-      const int col = i * 8 + 2 * t;
-      if (col < D) {
-        if (ok0) { atomicAdd(dm + qoff + (long)r0 * Cp + col, dq[i][0] * scale); atomicAdd(dm + qoff + (long)r0 * Cp + col + 1, dq[i][1] * scale); }
-        if (ok1) { atomicAdd(dm + qoff + (long)r1 * Cp + col, dq[i][2] * scale); atomicAdd(dm + qoff + (long)r1 * Cp + col + 1, dq[i][3] * scale); }
-      }
-    }
-  }
-  __syncthreads();
-  // ---- phase 2: this warp's 16 pixels: dV = P^T dO, dK = scale * dS^T Q   (reduction over the 64 query rows)
-  {
-    float dv[DP / 8][4], dk[DP / 8][4];
-#pragma unroll
-    for (int i = 0; i < DP / 8; ++i) { dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; }
-    const int m0 = warp * 16;
-    const int i4 = lane >> 3;
-#pragma unroll
-    for (int kq = 0; kq < QR / 16; ++kq) {
-      uint32_t ap[4], as[4];         // A[m = pixel][k = query] fragments, transposed out of the query-major tiles
-      const int qrow = kq * 16 + (lane & 7) + (i4 >> 1) * 8, pcol = m0 + (i4 & 1) * 8;
-      ldsm_x4_t(smem_addr(Ps + qrow * PP + pcol), ap[0], ap[1], ap[2], ap[3]);
-      ldsm_x4_t(smem_addr(dSs + qrow * PP + pcol), as[0], as[1], as[2], as[3]);
-#pragma unroll
-      for (int np = 0; np < DP / 16; ++np) {
-        uint32_t b0, b1, b2, b3;
-        const int brow = kq * 16 + (lane & 7) + (i4 & 1) * 8, bcol = np * 16 + (i4 >> 1) * 8;
-        ldsm_x4_t(smem_addr(dOs + brow * PITCH + bcol), b0, b1, b2, b3);
-        mma16816(dv[2 * np], ap, b0, b1);
-        mma16816(dv[2 * np + 1], ap, b2, b3);
-        ldsm_x4_t(smem_addr(Qs + brow * PITCH + bcol), b0, b1, b2, b3);
-        mma16816(dk[2 * np], as, b0, b1);
-        mma16816(dk[2 * np + 1], as, b2, b3);
-      }
-    }
-    const int p0 = m0 + g, p1 = p0 + 8;
-    bf16* row0 = dkv + ((long)b * HW + (long)c * PC + p0) * 2 * Cp + head * D;
-    bf16* row1 = dkv + ((long)b * HW + (long)c * PC + p1) * 2 * Cp + head * D;
-#pragma unroll
-    for (int i = 0; i < DP / 8; ++i) {
-      const int col = i * 8 + 2 * t;
-      if (col < D) {
-        if (p0 < nvalid) {
-          *reinterpret_cast<uint32_t*>(row0 + col) = pack2(dk[i][0] * scale, dk[i][1] * scale);
-          *reinterpret_cast<uint32_t*>(row0 + Cp + col) = pack2(dv[i][0], dv[i][1]);
+        for (int j = 0; j < D / 8; ++j) {
+          const float4 a = a4[j], c4 = b4[j];
+          sdo = fmaf(a.x, c4.x, fmaf(a.y, c4.y, fmaf(a.z, c4.z, fmaf(a.w, c4.w, sdo))));
         }
-        if (p1 < nvalid) {
-          *reinterpret_cast<uint32_t*>(row1 + col) = pack2(dk[i][2] * scale, dk[i][3] * scale);
-          *reinterpret_cast<uint32_t*>(row1 + Cp + col) = pack2(dv[i][2], dv[i][3]);
+      } else {                                           // D = 36: half rows of 18 floats (8-byte aligned)
+        const float2* a2 = reinterpret_cast<const float2*>(a4);
+        const float2* b2 = reinterpret_cast<const float2*>(b4);
+#pragma unroll
+        for (int j = 0; j < D / 4; ++j) {
+          const float2 a = a2[j], c2 = b2[j];
+          sdo = fmaf(a.x, c2.x, fmaf(a.y, c2.y, sdo));
         }
       }
     }
+    sdo += __shfl_xor_sync(0xffffffffu, sdo, 1);
+    if (hf == 0) Dr[r] = sdo;
   }
+  float dq[DP / 8][4];
+#pragma unroll
+  for (int i = 0; i < DP / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+  const int r0 = warp * 16 + g, r1 = r0 + 8;
+  const bool ok0 = r0 < NQ, ok1 = r1 < NQ;
+  for (int it = 0; it < n_my; ++it) {
+    const int c = split + it * nsplit;
+    const int nvalid = min(PC, HW - c * PC);
+    if (it + 1 < n_my) {
+      const int cn = c + nsplit;
+      bf16* nb = KV + ((it + 1) & 1) * 2 * PC * PITCH;
+      prefetch_kv<D, PC>(kvb + (long)cn * PC * 2 * Cp, 2L * Cp, Cp, min(PC, HW - cn * PC), nb, nb + PC * PITCH);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();                                   // K / V of this chunk (and, first time round, Q / dO / lse / Dr) are visible
+    const bf16* Ks = KV + (it & 1) * 2 * PC * PITCH;
+    const bf16* Vs = Ks + PC * PITCH;
+    // ---- phase 1: this warp's 16 query rows x 64 pixels
+    {
+      float s[PC / 8][4], dp[PC / 8][4];
+#pragma unroll
+      for (int i = 0; i < PC / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f; }
+      mma_rows_by_rows<D, PC / 8>(Qs, warp * 16, Ks, s, lane);
+      mma_rows_by_rows<D, PC / 8>(dOs, warp * 16, Vs, dp, lane);
+      const float ls0 = lses[r0], ls1 = lses[r1], dr0 = Dr[r0], dr1 = Dr[r1];
+      uint32_t da[PC / 16][4];         // dS as A fragments for dQ = dS K
+#pragma unroll
+      for (int i = 0; i < PC / 8; ++i) {
+        const int col = i * 8 + 2 * t;
+        const bool c0 = col < nvalid, c1 = col + 1 < nvalid;
+        const float p00 = (ok0 && c0) ? __expf(fmaf(s[i][0], scale, -ls0)) : 0.f, p01 = (ok0 && c1) ? __expf(fmaf(s[i][1], scale, -ls0)) : 0.f;
+        const float p10 = (ok1 && c0) ? __expf(fmaf(s[i][2], scale, -ls1)) : 0.f, p11 = (ok1 && c1) ? __expf(fmaf(s[i][3], scale, -ls1)) : 0.f;
+        const float d00 = p00 * (dp[i][0] - dr0), d01 = p01 * (dp[i][1] - dr0), d10 = p10 * (dp[i][2] - dr1), d11 = p11 * (dp[i][3] - dr1);
+        const uint32_t pk0 = pack2(p00, p01), pk1 = pack2(p10, p11), dk0 = pack2(d00, d01), dk1 = pack2(d10, d11);
+        *reinterpret_cast<uint32_t*>(Ps + r0 * PP + col) = pk0;
+        *reinterpret_cast<uint32_t*>(Ps + r1 * PP + col) = pk1;
+        *reinterpret_cast<uint32_t*>(dSs + r0 * PP + col) = dk0;
+        *reinterpret_cast<uint32_t*>(dSs + r1 * PP + col) = dk1;
+        da[i >> 1][(i & 1) * 2 + 0] = dk0;
+        da[i >> 1][(i & 1) * 2 + 1] = dk1;
+      }
+      mma_regs_by_cols<D, PC / 16>(da, Ks, dq, lane);
+    }
+    __syncthreads();
+    // ---- phase 2: this warp's 16 pixels: dV = P^T dO, dK = scale * dS^T Q   (reduction over the 64 query rows)
+    {
+      float dv[DP / 8][4], dk[DP / 8][4];
+#pragma unroll
+      for (int i = 0; i < DP / 8; ++i) { dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; }
+      const int m0 = warp * 16;
+      const int i4 = lane >> 3;
+#pragma unroll
+      for (int kq = 0; kq < QR / 16; ++kq) {
+        uint32_t ap[4], as[4];         // A[m = pixel][k = query] fragments, transposed out of the query-major tiles
+        const int qrow = kq * 16 + (lane & 7) + (i4 >> 1) * 8, pcol = m0 + (i4 & 1) * 8;
+        ldsm_x4_t(smem_addr(Ps + qrow * PP + pcol), ap[0], ap[1], ap[2], ap[3]);
+        ldsm_x4_t(smem_addr(dSs + qrow * PP + pcol), as[0], as[1], as[2], as[3]);
+#pragma unroll
+        for (int np = 0; np < DP / 16; ++np) {
+          uint32_t b0, b1, b2, b3;
+          const int brow = kq * 16 + (lane & 7) + (i4 & 1) * 8, bcol = np * 16 + (i4 >> 1) * 8;
+          ldsm_x4_t(smem_addr(dOs + brow * PITCH + bcol), b0, b1, b2, b3);
+          mma16816(dv[2 * np], ap, b0, b1);
+          mma16816(dv[2 * np + 1], ap, b2, b3);
+          ldsm_x4_t(smem_addr(Qs + brow * PITCH + bcol), b0, b1, b2, b3);
+          mma16816(dk[2 * np], as, b0, b1);
+          mma16816(dk[2 * np + 1], as, b2, b3);
+        }
+      }
+      const int p0 = m0 + g, p1 = p0 + 8;
+      bf16* row0 = dkv + ((long)b * HW + (long)c * PC + p0) * 2 * Cp + head * D;
+      bf16* row1 = dkv + ((long)b * HW + (long)c * PC + p1) * 2 * Cp + head * D;
+#pragma unroll
+      for (int i = 0; i < DP / 8; ++i) {
+        const int col = i * 8 + 2 * t;
+        if (col < D) {
+          if (p0 < nvalid) {
+            *reinterpret_cast<uint32_t*>(row0 + col) = pack2(dk[i][0] * scale, dk[i][1] * scale);
+            *reinterpret_cast<uint32_t*>(row0 + Cp + col) = pack2(dv[i][0], dv[i][1]);
+          }
+          if (p1 < nvalid) {
+            *reinterpret_cast<uint32_t*>(row1 + col) = pack2(dk[i][2] * scale, dk[i][3] * scale);
+            *reinterpret_cast<uint32_t*>(row1 + Cp + col) = pack2(dv[i][2], dv[i][3]);
+          }
+        }
+      }
+    }
+    __syncthreads();                                   // P / dS tiles and this K / V buffer are free again
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < DP / 8; ++i) {
+    const int col = i * 8 + 2 * t;
+    *reinterpret_cast<float2*>(dqp + r0 * DP + col) = make_float2(dq[i][0] * scale, dq[i][1] * scale);
+    *reinterpret_cast<float2*>(dqp + r1 * DP + col) = make_float2(dq[i][2] * scale, dq[i][3] * scale);
+  }
+  cluster.sync();
+  const int rows_mine = (NQ - split + nsplit - 1) / nsplit;
+  for (int idx = tid; idx < rows_mine * D; idx += NT) {
+    const int r = split + (idx / D) * nsplit, j = idx % D;
+    float acc = 0.f;
+    for (int pr = 0; pr < nsplit; ++pr) acc += cluster.map_shared_rank(dqp, pr)[r * DP + j];
+    dm[qoff + (long)r * Cp + j] = acc;
+  }
+  cluster.sync();
 }
 
-template <int D> constexpr int fwd_smem_fixed() { return (QR + 2 * 128) * Geo<D>::PITCH * 2 + QR * 4; }
-template <int D> constexpr int bwd_smem() { return (2 * QR + 2 * 64) * Geo<D>::PITCH * 2 + 2 * QR * (64 + 8) * 2 + 2 * QR * 4; }
+template <int D> constexpr int fwd_smem() { return (QR + 4 * 128) * Geo<D>::PITCH * 2 + (QR * Geo<D>::DP + 2 * QR) * 4; }
+template <int D> constexpr int bwd_smem() { return (2 * QR + 4 * 64) * Geo<D>::PITCH * 2 + 2 * QR * (64 + 8) * 2 + (2 * QR + QR * Geo<D>::DP) * 4; }
+
+// CTAs per (image, head): enough to put about two CTAs on every SM, at most one per chunk, at most the portable cluster size
+inline int pick_nsplit(int nchunks, int bh) {
+  int ns = (2 * 148 + bh - 1) / bh;
+  if (ns > 8) ns = 8;
+  if (ns > nchunks) ns = nchunks;
+  return ns < 1 ? 1 : ns;
+}
 
 template <int D>
-int launch_fwd(const void* m, const void* kv, int B, int HW, int heads, float* out, float* lse, float* part, int* counters, cudaStream_t st) {
+int launch_fwd(const void* m, const void* kv, int B, int HW, int heads, float* out, float* lse, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gaa_mma_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gaa_mma_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<D>());
     if (e != cudaSuccess) { dfb_set_error("gaa_mma_fwd smem attr: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
     attr = true;
   }
   const int nchunks = dfb_cdiv(HW, 128);
-  const int smem = fwd_smem_fixed<D>() + 2 * nchunks * NQ * 4;            // + merge staging of the (max, sum) pairs
-  if (smem > 200 * 1024) { dfb_set_error("gaa_mma_fwd: HW=%d too large for the one-launch merge", HW); return DFB_ERR_UNSUPPORTED; }
-  dim3 grid(nchunks, B * heads);
-  dfb_launch(gaa_mma_fwd_kernel<D>, grid, NT, smem, st, (const bf16*)m, (const bf16*)kv, HW, heads, 1.0f / sqrtf((float)D), nchunks, out, lse, part, counters);
+  const int nsplit = pick_nsplit(nchunks, B * heads);
+  dim3 grid(nsplit, B * heads);
+  dfb_launch_cluster(gaa_mma_fwd_kernel<D>, grid, NT, fwd_smem<D>(), st, nsplit, (const bf16*)m, (const bf16*)kv, HW, heads, 1.0f / sqrtf((float)D), nchunks, out, lse);
   return dfb_check_launch("gaa_mma_fwd");
 }
 
@@ -392,10 +469,11 @@ int launch_bwd(const float* dout, const float* out, const float* lse, const void
     if (e != cudaSuccess) { dfb_set_error("gaa_mma_bwd smem attr: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
     attr = true;
   }
-  cudaMemsetAsync(dm, 0, sizeof(float) * (size_t)B * NQ * heads * D, st);
-  dim3 grid(dfb_cdiv(HW, 64), B * heads);
-  dfb_launch(gaa_mma_bwd_kernel<D>, grid, NT, bwd_smem<D>(), st, dout, out, lse, (const bf16*)m, (const bf16*)kv, HW, heads, 1.0f / sqrtf((float)D), dm,
-             (bf16*)dkv);
+  const int nchunks = dfb_cdiv(HW, 64);
+  const int nsplit = pick_nsplit(nchunks, B * heads);
+  dim3 grid(nsplit, B * heads);
+  dfb_launch_cluster(gaa_mma_bwd_kernel<D>, grid, NT, bwd_smem<D>(), st, nsplit, dout, out, lse, (const bf16*)m, (const bf16*)kv, HW, heads,
+                     1.0f / sqrtf((float)D), nchunks, dm, (bf16*)dkv);
   return dfb_check_launch("gaa_mma_bwd");
 }
 
@@ -411,7 +489,7 @@ int launch_bwd(const float* dout, const float* out, const float* lse, const void
   }
 
 int dfb_gaa_mma_fwd(const void* m, const void* kv, int B, int HW, int heads, int d, float* out, float* lse, float* scratch, int* counters, cudaStream_t st) {
-  GAA_MMA_DISPATCH_D(d, { return launch_fwd<D>(m, kv, B, HW, heads, out, lse, scratch, counters, st); });
+  GAA_MMA_DISPATCH_D(d, { return launch_fwd<D>(m, kv, B, HW, heads, out, lse, st); });
   return DFB_OK;
 }
 

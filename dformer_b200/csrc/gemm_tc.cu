@@ -644,7 +644,10 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   if (splits > 1) DFB_REQUIRE(g.out_dtype == 0 && g.act == 0, "gemm_tc split-K needs fp32 output without activation");
   p.kb_per_split = dfb_cdiv(p.kb_total, splits);
   p.splits = dfb_cdiv(p.kb_total, p.kb_per_split);
-  if (p.splits > 1 && !g.accumulate) {
+  if (p.splits > 1 && !g.accumulate && g.ldc == g.N && (g.batch == 1 || g.strideC == (long)g.M * g.N)) {      // contiguous C: one memset node
+    cudaError_t e = cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)g.batch * g.M * g.N, st);
+    if (e != cudaSuccess) { dfb_set_error("memset: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
+  } else if (p.splits > 1 && !g.accumulate) {
     for (int b = 0; b < g.batch; ++b) {
       cudaError_t e = cudaMemset2DAsync((float*)g.C + (long)b * g.strideC, g.ldc * sizeof(float), 0, (size_t)g.N * sizeof(float), g.M, st);
       if (e != cudaSuccess) { dfb_set_error("memset2d: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }

@@ -14,6 +14,7 @@ import torch
 import torch.distributed as dist
 
 from . import kernels as K
+from .parallel import small_all_reduce_
 from .runtime import GradArena, backend_for
 
 F32 = torch.float32
@@ -81,7 +82,7 @@ def _bn_fwd(x2d, bn: BNState, out_dtype, act=K.ACT_NONE, residual=None, chan_sca
         count = float(M)
         if bn.sync:                                             # SyncBatchNorm: one all-reduce of (sum, sumsq); equal shards per rank
             grp = bn.sync_group if bn.sync_group is not True else None
-            dist.all_reduce(st, group=grp)
+            small_all_reduce_(st, grp)                          # NVLink peer-memory kernel on one box (parallel.PeerExchange), else NCCL / gloo
             count = float(M) * dist.get_world_size(grp)
         ms = K.bn_finalize(st, count, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
         if bn.nbt is not None:
@@ -114,7 +115,7 @@ def _bn_bwd(dy, x2d, ms, bn: BNState, count, dx_dtype, dgamma, dbeta, act=K.ACT_
     K.axpy(sums[0], 1.0, dbeta)                                 # local parameter gradients (DP averages them later)
     K.axpy(sums[1], 1.0, dgamma)
     if bn.sync:
-        dist.all_reduce(sums, group=bn.sync_group if bn.sync_group is not True else None)
+        small_all_reduce_(sums, bn.sync_group if bn.sync_group is not True else None)
     dx = K.bn_bwd_apply(gbuf, x2d, ms, bn.weight, sums, count, bn.training, dx_dtype)
     return dx, gbuf
 
@@ -450,17 +451,36 @@ class BlockFn(torch.autograd.Function):
 
 
 # ============================================================================================ NMF2D
-def _nmf_fwd(x, bases_raw, steps, T):
+def _nmf_fwd(x, bases_raw, steps, T, side=None):
     """ham_head.py:60-100,109-145 on channels-last x [B, N, D] (compute dtype); bases_raw [B, D, R] fp32.
 
     The factor state (coef, bases) and every multiplicative update stay fp32; in bf16 mode the batched matrix
-    products run on the tcgen05 GEMM with bf16 copies of the factors (what the reference's autocast bmm does)."""
+    products run on the tcgen05 GEMM with bf16 copies of the factors (what the reference's autocast bmm does).
+    `side`: a second stream for the small Gram products (B^T B, C^T C), which only depend on one factor: the chain is
+    latency-bound (5-8 us launches on a few SMs), so every launch taken off the critical path is time saved."""
     B, N, D = x.shape
     R = bases_raw.shape[2]
     dev = x.device
     f = lambda *s: torch.empty(s, device=dev, dtype=F32)
     lo = (lambda t: t) if T == F32 else (lambda t: K.cast(t, torch.bfloat16))
     sk = max(1, N // 512)
+    main = torch.cuda.current_stream()
+
+    def on_side(fn):
+        """run fn() on the side stream after everything enqueued so far; returns (result, event to wait for)"""
+        if side is None:
+            return fn(), None
+        K.fork(side)
+        with torch.cuda.stream(side):
+            r = fn()
+            ev = K.signal(side)
+        K.share(main, *(r if isinstance(r, tuple) else (r,)))
+        return r, ev
+
+    def wait(ev):
+        if ev is not None:
+            main.wait_event(ev)
+
     bases, _ = K.normalize_cols(bases_raw)
     bases_l = lo(bases)
     S = K.bgemm(x, bases_l, f(B, N, R), M=N, N=R, K=D)
@@ -471,16 +491,18 @@ def _nmf_fwd(x, bases_raw, steps, T):
     lo_out = lambda *s: torch.empty(s, device=dev, dtype=T)     # short-K products land directly in the compute dtype (no split-K, no cast)
 
     def coef_update(coef, coef_l, bases, bases_l):
+        btb_l, ev = on_side(lambda: K.bgemm(bases_l, bases_l, lo_out(B, R, R), trans_a=True, M=R, N=R, K=D))
         num = K.bgemm(x, bases_l, f(B, N, R), M=N, N=R, K=D)
-        btb_l = K.bgemm(bases_l, bases_l, lo_out(B, R, R), trans_a=True, M=R, N=R, K=D)
+        wait(ev)
         den = K.bgemm(coef_l, btb_l, f(B, N, R), M=N, N=R, K=R)
         coef_n, coef_nl = K.mu_update(coef, num, den, lo_dtype=T)          # fp32 state + compute-dtype operand from one launch
         return coef_n, coef_nl, (coef, coef_l, num, den, bases_l, btb_l)
 
     for _ in range(steps):
         coef_n, coef_nl, rec_c = coef_update(coef, coef_l, bases, bases_l)
+        ctc_l, ev = on_side(lambda: lo(K.bgemm(coef_nl, coef_nl, f(B, R, R), trans_a=True, M=R, N=R, K=N, splitk=sk)))
         num2 = K.bgemm(x, coef_nl, f(B, D, R), trans_a=True, M=D, N=R, K=N, splitk=sk)
-        ctc_l = lo(K.bgemm(coef_nl, coef_nl, f(B, R, R), trans_a=True, M=R, N=R, K=N, splitk=sk))
+        wait(ev)
         den2 = K.bgemm(bases_l, ctc_l, f(B, D, R), M=D, N=R, K=R)
         bases_n, bases_nl = K.mu_update(bases, num2, den2, lo_dtype=T)
         tape.append((rec_c, (bases, bases_l, num2, den2, coef_nl, ctc_l)))
@@ -491,23 +513,39 @@ def _nmf_fwd(x, bases_raw, steps, T):
     return out, (tape, rec_f, coef_fl, bases_l)
 
 
-def _nmf_bwd(dout, x, saved, T):
+def _nmf_bwd(dout, x, saved, T, side=None):
     """Back-propagation through every multiplicative update (the reference does not detach them, ham_head.py:45,119).
 
     The gradient w.r.t. x is a sum of 2*steps + 2 rank-R products (one per use of x in a numerator, plus the initial
     softmax).  Their factors are gathered side by side along the reduction dimension -- A_cat [B, N, slots*R],
     B_cat [B, D, slots*R] -- and contracted by ONE GEMM with K = slots*R that writes dx once, instead of `slots`
-    read-modify-write passes over an fp32 [B, N, D] accumulator."""
+    read-modify-write passes over an fp32 [B, N, D] accumulator.
+    The gradient of a Gram matrix G = F^T F enters F twice (F dG + F dG^T): the two products are one product with the
+    symmetrised dG; the Gram-gradient products run on `side` next to the long x^T (.) / x (.) products."""
     tape, rec_f, coef_fl, bases_Tl = saved
     B, N, D = x.shape
     R = coef_fl.shape[2]
     dev = x.device
     f = lambda *s: torch.empty(s, device=dev, dtype=F32)
-    lo = (lambda t: t) if T == F32 else (lambda t: K.cast(t, torch.bfloat16))
     slots = 2 * len(tape) + 2
     a_cat = torch.empty((B, N, slots * R), device=dev, dtype=T)
     b_cat = torch.empty((B, D, slots * R), device=dev, dtype=T)
     slot = [0]
+    main = torch.cuda.current_stream()
+
+    def on_side(fn):
+        if side is None:
+            return fn(), None
+        K.fork(side)
+        with torch.cuda.stream(side):
+            r = fn()
+            ev = K.signal(side)
+        K.share(main, r)
+        return r, ev
+
+    def wait(ev):
+        if ev is not None:
+            main.wait_event(ev)
 
     def push(a_src, b_src):
         """register one product  dx += a[B,N,R] @ b[B,D,R]^T : returns the two column slices of the concatenated operands; a source
@@ -531,11 +569,12 @@ def _nmf_bwd(dout, x, saved, T):
         dco = f(B, N, R)
         dnum_l, _ = push(None, bases_l)                                                     # num = x @ bases
         dden_l = K.mu_update_bwd(dcoef_new, coef, num, den, dco, False, dnum_l, T)
+        # BtB = bases^T bases: d(BtB) = coef^T dden, symmetrised, on the side stream
+        dbtb_s, ev = on_side(lambda: K.sym_cast(K.bgemm(coef_l, dden_l, f(B, R, R), trans_a=True, M=R, N=R, K=N, splitk=sk), T))
         K.bgemm(x, dnum_l, dbases, trans_a=True, M=D, N=R, K=N, accumulate=True, splitk=sk)
         K.bgemm(dden_l, btb_l, dco, M=N, N=R, K=R, accumulate=True)                         # den = coef @ BtB (BtB symmetric)
-        dbtb_l = lo(K.bgemm(coef_l, dden_l, f(B, R, R), trans_a=True, M=R, N=R, K=N, splitk=sk))
-        K.bgemm(bases_l, dbtb_l, dbases, M=D, N=R, K=R, accumulate=True)                    # BtB = bases^T bases
-        K.bgemm(bases_l, dbtb_l, dbases, trans_b=True, M=D, N=R, K=R, accumulate=True)
+        wait(ev)
+        K.bgemm(bases_l, dbtb_s, dbases, M=D, N=R, K=R, accumulate=True)
         return dco
 
     def bases_update_bwd(dbases_new, rec, dcoef):
@@ -543,11 +582,12 @@ def _nmf_bwd(dout, x, saved, T):
         dba = f(B, D, R)
         _, dnum2_l = push(coef_l, None)                                                     # num2 = x^T @ coef
         dden2_l = K.mu_update_bwd(dbases_new, bases, num2, den2, dba, False, dnum2_l, T)
+        # CtC = coef^T coef: d(CtC) = bases^T dden2, symmetrised, on the side stream
+        dctc_s, ev = on_side(lambda: K.sym_cast(K.bgemm(bases_l, dden2_l, f(B, R, R), trans_a=True, M=R, N=R, K=D), T))
         K.bgemm(x, dnum2_l, dcoef, M=N, N=R, K=D, accumulate=True)
         K.bgemm(dden2_l, ctc_l, dba, M=D, N=R, K=R, accumulate=True)                        # den2 = bases @ CtC
-        dctc_l = K.bgemm(bases_l, dden2_l, torch.empty((B, R, R), device=dev, dtype=T), trans_a=True, M=R, N=R, K=D)
-        K.bgemm(coef_l, dctc_l, dcoef, M=N, N=R, K=R, accumulate=True)                      # CtC = coef^T coef
-        K.bgemm(coef_l, dctc_l, dcoef, trans_b=True, M=N, N=R, K=R, accumulate=True)
+        wait(ev)
+        K.bgemm(coef_l, dctc_s, dcoef, M=N, N=R, K=R, accumulate=True)
         return dba
 
     dcoef = coef_update_bwd(dcoef, rec_f, dbases)
@@ -592,7 +632,7 @@ class HeadFn(torch.autograd.Function):
             s, ms_s, n_s = _bn_fwd(s_pre, st.bn_sq, T, act=K.ACT_RELU)
         hin = _lin(s, pk("ham_in"), T, act=K.ACT_RELU)
         D = hin.shape[1]
-        nmf, nmf_saved = _nmf_fwd(hin.view(B, h1 * w1, D), bases_raw, st.steps, T)
+        nmf, nmf_saved = _nmf_fwd(hin.view(B, h1 * w1, D), bases_raw, st.steps, T, side=getattr(st, "side", None))
         nmf2d = nmf.view(M, D)
         ho_pre = _lin(nmf2d, pk("ham_out"), T)
         hs, ms_o, n_o = _bn_fwd(ho_pre, st.bn_out, T, act=K.ACT_RELU, residual=s)
@@ -637,7 +677,7 @@ class HeadFn(torch.autograd.Function):
                                   G["hamburger.ham_out.bn.bias"], act=K.ACT_RELU, residual=sv["s"])
         dnmf = _lin_bwd(dho_pre, sv["nmf"], pk("ham_out")[0], G["hamburger.ham_out.conv.weight"].view(pk("ham_out")[0].shape), None, T)
         hin = sv["hin"]
-        dhin = _nmf_bwd(dnmf.view(B, h1 * w1, D), hin.view(B, h1 * w1, D), sv["nmf_saved"], T).view(M, D)
+        dhin = _nmf_bwd(dnmf.view(B, h1 * w1, D), hin.view(B, h1 * w1, D), sv["nmf_saved"], T, side=getattr(st, "side", None)).view(M, D)
         dhin_pre = K.act_bwd(dhin, hin, K.ACT_RELU)
         ds = _lin_bwd(dhin_pre, sv["s"], pk("ham_in")[0], G["hamburger.ham_in.conv.weight"].view(pk("ham_in")[0].shape),
                       G["hamburger.ham_in.conv.bias"], T)

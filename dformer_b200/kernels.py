@@ -321,6 +321,9 @@ def gaa_fused_fwd(m, kv, B, HW, heads, d):
     dev = m.device
     out = torch.empty((B * 49, heads * d), device=dev, dtype=torch.float32)
     lse = torch.empty((B * heads * 49,), device=dev, dtype=torch.float32)
+    if m.dtype == torch.bfloat16:                     # tensor-core kernel: partials are merged inside a thread-block cluster (no scratch, no tickets)
+        lib().gaa_fused_fwd(m.data_ptr(), kv.data_ptr(), dt(m), B, HW, heads, d, out.data_ptr(), lse.data_ptr(), None, None, _s())
+        return out, lse
     scratch = torch.empty((B * heads * ((HW + 127) // 128) * 49 * (d + 4),), device=dev, dtype=torch.float32)
     key = (dev, torch.cuda.current_stream().cuda_stream)
     cnt = _GAA_COUNTERS.get(key)                      # self-resetting tickets: one persistent zeroed buffer per (device, stream)
@@ -463,6 +466,15 @@ def mu_update_bwd(dout, a, num, den, da, accumulate_da, dnum_out, dden_dtype, ep
 def cast(x, dtype):
     out = torch.empty(x.shape, device=x.device, dtype=dtype)
     lib().cast(x.data_ptr(), dt(x), out.data_ptr(), dt(out), x.numel(), _s())
+    return out
+
+
+def sym_cast(x, dtype):
+    """x [B, R, R] -> x + x^T (per matrix) in `dtype`"""
+    B, R, R2 = x.shape
+    assert R == R2 and x.is_contiguous()
+    out = torch.empty((B, R, R), device=x.device, dtype=dtype)
+    lib().sym_cast(x.data_ptr(), dt(x), out.data_ptr(), dt(out), B, R, _s())
     return out
 
 

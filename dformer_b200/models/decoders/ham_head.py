@@ -148,7 +148,10 @@ class LightHamHead(BaseDecodeHead):
         ws = getattr(self, "_wstream", None)
         if ws is None or ws.device != dev:
             ws = self._wstream = torch.cuda.Stream(device=dev)
-        st = SimpleNamespace(dtype=T, packed=packed, arena=arena, prefix="", tag="head", names=self.PARAMS, B=B, sizes=sizes, wstream=ws,
+        sd = getattr(self, "_side_stream", None)
+        if sd is None or sd.device != dev:
+            sd = self._side_stream = torch.cuda.Stream(device=dev)
+        st = SimpleNamespace(dtype=T, packed=packed, arena=arena, prefix="", tag="head", names=self.PARAMS, B=B, sizes=sizes, wstream=ws, side=sd,
                              steps=ham.train_steps if training else ham.eval_steps, drop_mask=drop_mask,
                              bn_sq=Fn.BNState(self.squeeze.bn, "squeeze.bn", training, sync),
                              bn_out=Fn.BNState(self.hamburger.ham_out.bn, "hamburger.ham_out.bn", training, sync),

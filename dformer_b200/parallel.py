@@ -66,3 +66,83 @@ class GradSync:
         self.pending.clear()
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
+
+
+class PeerExchange:
+    """Small-message all-reduce over NVLink peer memory (csrc/peer.cu) for the SyncBatchNorm statistics.
+
+    One exchange buffer per rank, mapped by every peer of the box through CUDA IPC; `all_reduce_(t)` sums a small fp32 / fp64
+    tensor in place with one single-CTA kernel on the current stream (graph-capturable).  Built lazily per process group by
+    `peer_exchange(group)`; unavailable (-> NCCL all-reduce) when the ranks are not all CUDA ranks of one host."""
+
+    def __init__(self, group=None):
+        import ctypes
+        import socket
+
+        from ._lib import lib
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.ok = False
+        self._ptrs = []
+        L = lib()
+        mine = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        err = ""
+        try:
+            L.peer_alloc(ctypes.byref(mine))
+            L.peer_export(mine, handle)
+        except RuntimeError as e:                                  # e.g. IPC not permitted in this container
+            err = str(e)
+        info = (socket.gethostname(), torch.cuda.current_device(), bytes(handle), err)
+        infos = [None] * self.world
+        dist.all_gather_object(infos, info, group=group)
+        same_host = all(i[0] == infos[0][0] for i in infos) and len({i[1] for i in infos}) == self.world
+        good = same_host and not any(i[3] for i in infos) and self.world <= 16
+        bases = []
+        if good:
+            try:
+                for r, (_, _, h, _) in enumerate(infos):
+                    if r == self.rank:
+                        bases.append(mine.value)
+                    else:
+                        p = ctypes.c_void_p()
+                        L.peer_open((ctypes.c_ubyte * 64).from_buffer_copy(h), ctypes.byref(p))
+                        self._ptrs.append(p)
+                        bases.append(p.value)
+            except RuntimeError:
+                good = False
+        flag = torch.tensor([1 if good else 0], device="cuda", dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)          # everybody or nobody (also orders set-up before first use)
+        self._mine = mine
+        if int(flag.item()) == 1:
+            self.table = torch.tensor(bases, device="cuda", dtype=torch.int64)
+            self.ok = True
+
+    def all_reduce_(self, t):
+        from ._lib import lib
+        assert t.is_cuda and t.is_contiguous() and t.dtype in (torch.float32, torch.float64)
+        lib().peer_allreduce(t.data_ptr(), t.data_ptr(), 0 if t.dtype == torch.float32 else 2, t.numel(), self.table.data_ptr(), self.rank, self.world,
+                             torch.cuda.current_stream().cuda_stream)
+        return t
+
+
+_PEER = {}
+
+
+def peer_exchange(group=None):
+    """The PeerExchange of a process group (None when it cannot be used: CPU / gloo ranks, several hosts, IPC refused)."""
+    key = id(group) if group is not None else None
+    if key not in _PEER:
+        usable = torch.cuda.is_available() and dist.get_backend(group) == "nccl" and dist.get_world_size(group) > 1
+        ex = PeerExchange(group) if usable else None
+        _PEER[key] = ex if (ex is not None and ex.ok) else None
+    return _PEER[key]
+
+
+def small_all_reduce_(t, group=None):
+    """In-place sum of a small statistics tensor across the group: peer-memory kernel on one NVLink box, else the backend's all_reduce."""
+    ex = peer_exchange(group)
+    if ex is not None and t.numel() * t.element_size() <= 16 * 1024:
+        return ex.all_reduce_(t)
+    dist.all_reduce(t, group=group)
+    return t

@@ -160,7 +160,9 @@ int dfb200_gaa_bwd(const float* dout, const void* m, const void* kv, const float
 /* Fused form of the same attention core (one launch per direction, nothing of size 49 x HW in HBM; head dim d in
  * {16, 32, 36, 48}).  forward: out [B*49, heads*d] fp32, lse [B*heads*49] (row log-sum-exp kept for backward);
  * scratch: B*heads*ceil(HW/128)*49*(d+4) floats of partials; counters: B*heads ints, zero before the first call
- * (self-resetting).  backward: recomputes the probabilities from (m, kv, lse); dm is zero-filled by the launcher. */
+ * (self-resetting).  backward: recomputes the probabilities from (m, kv, lse); dm is zero-filled by the launcher.
+ * dtype bf16 runs on the tensor cores (mma.sync) with thread-block clusters: partials are merged through distributed shared
+ * memory, so `scratch` and `counters` are unused there and may be NULL. */
 int dfb200_gaa_fused_fwd(const void* m, const void* kv, int dtype, int B, int HW, int heads, int d, float* out, float* lse,
                          float* scratch, int* counters, void* stream);
 int dfb200_gaa_fused_bwd(const float* dout, const float* out, const float* lse, const void* m, const void* kv, int dtype,
@@ -218,6 +220,9 @@ int dfb200_mu_update_bwd(const float* dout, const float* a, const float* num, co
                          void* stream);
 int dfb200_cast(const void* in, int in_dtype, void* out, int out_dtype, long n, void* stream);
 /* strided 2-D convert/copy: out[r*ld_out + c] = in[r*ld_in + c], r < rows, c < cols (column slices of concatenated operands) */
+/* out[b,i,j] = in[b,i,j] + in[b,j,i] for `batch` contiguous R x R matrices (ham_head.py:122-141 backward: d(B^T B) enters both
+ * factors, so one product with the symmetrised gradient replaces two). in fp32/bf16, out fp32/bf16 (not bf16 -> fp32). */
+int dfb200_sym_cast(const void* in, int in_dtype, void* out, int out_dtype, int batch, int R, void* stream);
 int dfb200_cast2d(const void* in, int in_dtype, long ld_in, void* out, int out_dtype, long ld_out, long rows, int cols,
                   void* stream);
 int dfb200_axpy(const void* x, int x_dtype, float alpha, void* y, int y_dtype, long n, void* stream); /* y += alpha*x */
@@ -283,6 +288,22 @@ int dfb200_adamw(float* p, const float* g, float* m, float* v, long n, float lr,
                  so a captured CUDA graph follows the schedule */, void* stream);
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches evidence) */
 long dfb200_launch_count(void);
+
+/* ---- SyncBatchNorm statistics exchange over NVLink peer memory (torch SyncBatchNorm of utils/train.py:182-194) ------------
+ * Small-message all-reduce among the ranks of ONE box (one process per GPU).  Every rank allocates an exchange buffer
+ * (dfb200_peer_alloc: one cudaMalloc of ~0.5 MB, zero-filled), exports it as a 64-byte CUDA IPC handle, opens the
+ * handles of its peers (the caller ships the handles between processes, e.g. torch.distributed.all_gather_object) and
+ * uploads the table of `world` base pointers -- entry `rank` = its own buffer -- to device memory.
+ * dfb200_peer_allreduce: out[i] = sum over ranks of in[i] (n elements, dtype 0 = float32, 2 = float64, at most 16 KB),
+ * summed in rank order (bitwise identical on every rank); one single-CTA kernel, asynchronous on `stream`, graph-capturable
+ * (the call sequence number lives in the buffer and is advanced on the device).  Every rank must issue the same sequence
+ * of calls; a rank that waits ~20 s for a peer traps (launch failure) instead of hanging. */
+int dfb200_peer_alloc(void** ptr);
+int dfb200_peer_free(void* ptr);
+int dfb200_peer_export(void* ptr, unsigned char* handle64);
+int dfb200_peer_open(const unsigned char* handle64, void** ptr);
+int dfb200_peer_close(void* ptr);
+int dfb200_peer_allreduce(const void* in, void* out, int dtype, int n, void* const* bases_dev, int rank, int world, void* stream);
 
 #ifdef __cplusplus
 }

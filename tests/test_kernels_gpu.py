@@ -667,3 +667,13 @@ def test_bn_fold(dtype):
     torch.testing.assert_close(out.float(), ref, **(dict(rtol=3e-2, atol=8e-2) if dtype == torch.bfloat16 else dict(rtol=1e-4, atol=1e-4)))
     bias2 = k.bn_fold(w0.clone(), ld, None, rm, rv, 1e-5, g, b)               # conv without bias (the head's ConvModules)
     torch.testing.assert_close(bias2, -rm * sc + b, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("in_dtype,out_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16)])
+def test_sym_cast(in_dtype, out_dtype):
+    """x + x^T per matrix (the symmetrised Gram-matrix gradient of the NMF backward, ham_head.py:122-141)"""
+    k = K()
+    x = rnd(5, 64, 64, dtype=in_dtype)
+    out = k.sym_cast(x, out_dtype)
+    ref = (x.float() + x.float().transpose(1, 2)).to(out_dtype)
+    torch.testing.assert_close(out, ref, rtol=0, atol=0)
