@@ -10,6 +10,19 @@ import torch
 import torch.distributed as dist
 
 
+import weakref
+
+_GRAD_SYNCS = weakref.WeakSet()
+_PEER_CHAIN = {"event": None, "capturing": False}     # completion event of the most recent peer-memory exchange of this step
+
+
+def _last_peer_event():
+    ev = _PEER_CHAIN["event"]
+    if ev is not None and _PEER_CHAIN["capturing"] != (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()):
+        ev = _PEER_CHAIN["event"] = None              # recorded inside / outside a graph capture that is over: nothing to order against
+    return ev
+
+
 class GradSync:
     def __init__(self, model, bucket_mb=25.0, group=None):
         self.model, self.group = model, group
@@ -19,6 +32,8 @@ class GradSync:
         self.pending = {}        # id(arena) -> [arena, lo, hi, events] contiguous finished-but-unsent range
         self.handles = []
         self.launched = 0
+        self.inflight = False    # an all-reduce has been launched on self.stream since the last join (see small_all_reduce_)
+        _GRAD_SYNCS.add(self)
         for m in model.modules():
             if hasattr(m, "grad_hook") and hasattr(m, "_build_plan"):
                 m.grad_hook = self._on_range_done
@@ -29,6 +44,10 @@ class GradSync:
             self.stream.wait_stream(torch.cuda.current_stream())
             for ev in events:                       # gradients written on the wgrad side stream
                 self.stream.wait_event(ev)
+            pe = _last_peer_event()
+            if pe is not None:                      # collectives of the step form ONE total order on every rank (see small_all_reduce_)
+                self.stream.wait_event(pe)
+            self.inflight = True
             with torch.cuda.stream(self.stream):
                 dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group)
             buf.record_stream(self.stream)
@@ -66,6 +85,8 @@ class GradSync:
         self.pending.clear()
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
+        self.inflight = False
+        _PEER_CHAIN["event"] = None
 
 
 class PeerExchange:
@@ -133,7 +154,9 @@ def peer_exchange(group=None):
     """The PeerExchange of a process group (None when it cannot be used: CPU / gloo ranks, several hosts, IPC refused)."""
     key = id(group) if group is not None else None
     if key not in _PEER:
-        usable = torch.cuda.is_available() and dist.get_backend(group) == "nccl" and dist.get_world_size(group) > 1
+        import os
+        usable = (torch.cuda.is_available() and dist.get_backend(group) == "nccl" and dist.get_world_size(group) > 1
+                  and os.environ.get("DFB200_PEER_EXCHANGE", "1") != "0")        # 0: measure against NCCL's all-reduce (bench A/B only)
         ex = PeerExchange(group) if usable else None
         _PEER[key] = ex if (ex is not None and ex.ok) else None
     return _PEER[key]
@@ -143,6 +166,24 @@ def small_all_reduce_(t, group=None):
     """In-place sum of a small statistics tensor across the group: peer-memory kernel on one NVLink box, else the backend's all_reduce."""
     ex = peer_exchange(group)
     if ex is not None and t.numel() * t.element_size() <= 16 * 1024:
-        return ex.all_reduce_(t)
+        # The exchange kernel spins on its peers.  Two kernels that wait on other ranks must never be co-scheduled in different
+        # orders on different ranks (rank 0 inside collective A waiting for rank 1, rank 1 inside collective B waiting for rank 0,
+        # each blocking the other's launch queue), so every collective of a step -- these exchanges on the RGB and depth streams
+        # and the NCCL gradient all-reduces on the communication stream -- is chained into one total order, identical on all
+        # ranks because they run the same program: an exchange starts after the previous exchange and after any gradient
+        # all-reduce launched before it; an all-reduce starts after the last exchange (GradSync._fire).
+        cur = torch.cuda.current_stream()
+        for gs in list(_GRAD_SYNCS):
+            if gs.inflight and gs.stream is not None:
+                cur.wait_stream(gs.stream)
+                gs.inflight = False
+        pe = _last_peer_event()
+        if pe is not None:
+            cur.wait_event(pe)
+        ex.all_reduce_(t)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        _PEER_CHAIN["event"], _PEER_CHAIN["capturing"] = ev, torch.cuda.is_current_stream_capturing()
+        return t
     dist.all_reduce(t, group=group)
     return t
