@@ -551,27 +551,15 @@ int launch_conv(const T* x, const T* dy, const float* w, const float* b, int B, 
 
 #define ST reinterpret_cast<cudaStream_t>(stream)
 
-static bool dw7_tma() {      // DFB200_DW7_TMA=0 selects the older cp.async kernels of this file (A/B runs)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DFB200_DW7_TMA"); v = e ? atoi(e) : 1; }
-  return v != 0;
-}
-
 extern "C" int dfb200_dwconv_fwd(const void* x, int dtype, const float* weight, const float* bias, int B, int H, int W, int C, int k, int add_input,
                                  int act, void* y, void* z_out, void* stream) {
   DFB_REQUIRE(C % 8 == 0, "dwconv: C %% 8 != 0 (C=%d)", C);
   DFB_REQUIRE(k == 3 || k == 7, "dwconv: k must be 3 or 7");
-  if (k == 7 && dtype == 1 && !add_input && act == 0 && z_out == nullptr && dw7_tma()) return dfb_dw7_conv(x, weight, bias, B, H, W, C, 0, y, ST);
+  if (k == 7 && dtype == 1 && !add_input && act == 0 && z_out == nullptr) return dfb_dw7_conv(x, weight, bias, B, H, W, C, 0, y, ST);
   DFB_DISPATCH_DTYPE(dtype, T, {
     if (k == 3) return launch_conv<T, 3, 0>((const T*)x, nullptr, weight, bias, B, H, W, C, add_input, act, (T*)y, (T*)z_out, ST);
     return launch_conv<T, 7, 0>((const T*)x, nullptr, weight, bias, B, H, W, C, add_input, act, (T*)y, (T*)z_out, ST);
   });
-}
-
-static bool wgrad7_db() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DFB200_WGRAD7_DB"); v = e ? atoi(e) : 1; }
-  return v != 0;
 }
 
 extern "C" int dfb200_dwconv_bwd(const void* dy, const void* x, const void* z, int dtype, const float* weight, const float* bias, int B, int H, int W,
@@ -579,7 +567,7 @@ extern "C" int dfb200_dwconv_bwd(const void* dy, const void* x, const void* z, i
   DFB_REQUIRE(C % 8 == 0, "dwconv: C %% 8 != 0 (C=%d)", C);
   DFB_REQUIRE(k == 3 || k == 7, "dwconv: k must be 3 or 7");
   DFB_REQUIRE(act == 0 || dz_buf != nullptr, "dwconv_bwd: dz_buf required when act != 0");
-  if (k == 7 && dtype == 1 && !add_input && act == 0 && dw7_tma()) {
+  if (k == 7 && dtype == 1 && !add_input && act == 0) {
     if (dx) {
       const int rc = dfb_dw7_conv(dy, weight, nullptr, B, H, W, C, 1, dx, ST);
       if (rc) return rc;
@@ -613,8 +601,7 @@ extern "C" int dfb200_dwconv_bwd(const void* dy, const void* x, const void* z, i
     if (dweight) {
       if constexpr (sizeof(T) == 2) {
         if (k == 3) return launch_wgrad_tiled<3, false>((const bf16*)dz, (const bf16*)x, B, H, W, C, dweight, dbias, ST);
-        return wgrad7_db() ? launch_wgrad_tiled<7, true>((const bf16*)dz, (const bf16*)x, B, H, W, C, dweight, dbias, ST)
-                           : launch_wgrad_tiled<7, false>((const bf16*)dz, (const bf16*)x, B, H, W, C, dweight, dbias, ST);
+        return launch_wgrad_tiled<7, true>((const bf16*)dz, (const bf16*)x, B, H, W, C, dweight, dbias, ST);
       }
       if (k == 3) dfb_launch(dwconv_wgrad_kernel<T, 3>, wgrid, 256, 0, ST, dz, (const T*)x, B, H, W, C, dweight, dbias, ppb);
       else dfb_launch(dwconv_wgrad_kernel<T, 7>, wgrid, 256, 0, ST, dz, (const T*)x, B, H, W, C, dweight, dbias, ppb);

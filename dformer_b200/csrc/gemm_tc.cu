@@ -596,7 +596,7 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { dfb_set_error("gemm_tc smem attr: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
     // tuning aids (tools/gemm_bn_sweep.py, tools/gemm_replay.py), read once
-    if (const char* v = getenv("DFB200_TC_BN")) forced_bn = atoi(v);
+    if (const char* v = getenv("DFB200_TC_BN")) forced_bn = atoi(v);      // whole-process overrides for tools/gemm_replay.py runs
     if (const char* v = getenv("DFB200_TC_STAGES")) forced_stages = atoi(v);
     if (const char* v = getenv("DFB200_TC_EPI")) forced_epi = atoi(v);
     attr_set = true;

@@ -19,9 +19,6 @@ from .runtime import GradArena, backend_for
 
 F32 = torch.float32
 import os as _os
-_FUSE_GAA = _os.environ.get("DFB200_FUSE_GAA", "1") == "1"    # one-launch attention core (csrc/gaa_fused.cu); 0 = GEMM + softmax chain
-_SAVE_GP = _os.environ.get("DFB200_MLP_SAVE_GP", "1") == "1"    # fused MLP middle keeps GELU'(z) (bf16) instead of recomputing it in backward
-_FUSE_DW = _os.environ.get("DFB200_FUSE_DW", "1") == "1"      # fused MLP middle (csrc/mlp_dw.cu); 0 = the unfused chain, kept for A/B runs
 
 
 # ============================================================================================ helpers
@@ -228,8 +225,8 @@ def _mlp_fwd(x, pfx, st, P, sv, scale_b, pre=None):
     else:
         hn, mu, rs = K.layernorm_fwd(x, P[pfx + "norm.weight"], P[pfx + "norm.bias"], 1e-6, T)
     h = _lin(hn, st.packed[st.key + pfx + "fc1"], T)
-    if T == torch.bfloat16 and _FUSE_DW:       # TMA-fed fused kernel; the pre-activation is recomputed in the fused backward
-        if _SAVE_GP and sv.get("_bwd", True):
+    if T == torch.bfloat16:                    # TMA-fed fused kernel (csrc/mlp_dw.cu); training keeps GELU'(z) (bf16) for a streaming backward
+        if sv.get("_bwd", True):
             u, z = K.mlp_dw_fwd(h, P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, save_gp=True)      # z slot holds GELU'(z)
         else:
             u, z = K.mlp_dw_fwd(h, P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W), None
@@ -247,7 +244,7 @@ def _mlp_bwd(dout, pfx, st, P, sv, scale_b, G):
     T = st.dtype
     B, H, W = st.B, st.H, st.W
     lsn = "layer_scale_2" if pfx == "mlp." else "layer_scale_2_e"
-    fused = T == torch.bfloat16 and _FUSE_DW
+    fused = T == torch.bfloat16
     df = K.scale_residual_bwd(dout, sv[pfx + "f"], P[lsn], scale_b, H * W, G[lsn], dy_colsum=G[pfx + "fc2.bias"] if fused else None)
     w2 = st.packed[st.key + pfx + "fc2"][0]
     if fused:                                 # GELU' . dw3x3^T . weight/bias gradients . fc1 bias gradient: one kernel, dz stays on chip
@@ -313,7 +310,7 @@ class BlockFn(torch.autograd.Function):
             with torch.cuda.stream(side2):
                 kv = _lin(l, pk("attn.kv"), T)
                 dh_ = Ce // st.heads
-                if _FUSE_GAA and dh_ in K.GAA_FUSED_DIMS:           # one launch; keeps only the row log-sum-exp
+                if dh_ in K.GAA_FUSED_DIMS:                         # one launch (tensor cores in bf16); keeps only the row log-sum-exp
                     o7, lse7 = K.gaa_fused_fwd(m, kv, B, HW, st.heads, dh_)
                     probs = None
                 else:
