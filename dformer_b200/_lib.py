@@ -59,6 +59,7 @@ SIGNATURES = {
     "dfb200_gaa_bwd": [P, P, P, P, I, I, I, I, I, P, P, P, P],
     "dfb200_gaa_fused_fwd": [P, P, I, I, I, I, I, P, P, P, P, P],
     "dfb200_gaa_fused_bwd": [P, P, P, P, P, I, I, I, I, I, P, P, P],
+    "dfb200_gaa_fused_bwd_ex": [P, P, P, P, P, I, I, I, I, P, P, P, P, P, P],
     "dfb200_resize_fwd": [P, I, I, I, I, I, P, I, I, I, L, I, P],
     "dfb200_resize_bwd": [P, I, L, I, I, I, I, I, I, I, P, I, I, P],
     "dfb200_im2col3x3s2_fwd": [P, I, L, L, L, L, I, I, I, I, P, I, I, P],

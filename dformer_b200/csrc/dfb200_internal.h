@@ -13,4 +13,4 @@ int dfb_dw7_wgrad(const void* dz, const void* x, int B, int H, int W, int C, flo
 // tensor-core (mma.sync bf16) Global Awareness Attention core (gaa_mma.cu); same buffers as dfb200_gaa_fused_fwd / _bwd
 int dfb_gaa_mma_fwd(const void* m, const void* kv, int B, int HW, int heads, int d, float* out, float* lse, float* scratch, int* counters, cudaStream_t st);
 int dfb_gaa_mma_bwd(const float* dout, const float* out, const float* lse, const void* m, const void* kv, int B, int HW, int heads, int d, float* dm,
-                    void* dkv, cudaStream_t st);
+                    void* dkv, float* dkv_colsum, float* dm_colsum, void* dm_lo, cudaStream_t st);

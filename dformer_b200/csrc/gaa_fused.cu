@@ -418,7 +418,16 @@ extern "C" int dfb200_gaa_fused_bwd(const float* dout, const float* out, const f
                                     int heads, int d, float* dm, void* dkv, void* stream) {
   DFB_REQUIRE(B > 0 && HW > 0 && heads > 0, "gaa_fused_bwd: empty problem");
   DFB_REQUIRE(dtype == 0 || dtype == 1, "gaa_fused_bwd: bad dtype %d", dtype);
-  if (dtype == 1) return dfb_gaa_mma_bwd(dout, out, lse, m, kv, B, HW, heads, d, dm, dkv, ST);           // bf16: tensor cores (gaa_mma.cu)
+  if (dtype == 1) return dfb_gaa_mma_bwd(dout, out, lse, m, kv, B, HW, heads, d, dm, dkv, nullptr, nullptr, nullptr, ST);      // bf16: tensor cores (gaa_mma.cu)
   GAA_DISPATCH_D(d, { return launch_bwd<float, D>(dout, out, lse, m, kv, B, HW, heads, dm, dkv, ST); });
   return DFB_OK;
+}
+
+// bf16 only: the backward pass that also emits what the two projections around the attention core need next --
+// dkv_colsum[2*heads*d] += column sums of dkv (bias gradient of `kv`, DFormer.py:121), dm_colsum[heads*d] += column sums of dm
+// (bias gradient of `short_cut_linear`, DFormer.py:108), dm_lo = dm rounded to bf16 (operand of that layer's gradient GEMMs).
+extern "C" int dfb200_gaa_fused_bwd_ex(const float* dout, const float* out, const float* lse, const void* m, const void* kv, int B, int HW, int heads,
+                                       int d, float* dm, void* dkv, float* dkv_colsum, float* dm_colsum, void* dm_lo, void* stream) {
+  DFB_REQUIRE(B > 0 && HW > 0 && heads > 0, "gaa_fused_bwd_ex: empty problem");
+  return dfb_gaa_mma_bwd(dout, out, lse, m, kv, B, HW, heads, d, dm, dkv, dkv_colsum, dm_colsum, dm_lo, ST);
 }

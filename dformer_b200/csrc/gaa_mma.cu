@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(NT) gaa_mma_fwd_kernel(const bf16* __restrict_
 template <int D>
 __global__ void __launch_bounds__(NT) gaa_mma_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ lse,
                                                         const bf16* __restrict__ m, const bf16* __restrict__ kv, int HW, int heads, float scale, int nchunks,
-                                                        float* __restrict__ dm, bf16* __restrict__ dkv) {
+                                                        float* __restrict__ dm, bf16* __restrict__ dkv, float* __restrict__ dkv_colsum,
+                                                        float* __restrict__ dm_colsum, bf16* __restrict__ dm_lo) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   constexpr int DP = Geo<D>::DP, PITCH = Geo<D>::PITCH, PC = 64, PP = PC + 8;
@@ -287,6 +288,7 @@ __global__ void __launch_bounds__(NT) gaa_mma_bwd_kernel(const float* __restrict
   float* lses = reinterpret_cast<float*>(dSs + QR * PP);   // [64]
   float* Dr = lses + QR;                               // [64] rowsum(dO o O) = rowsum(dP o P)
   float* dqp = Dr + QR;                                // [64][DP] this CTA's dQ partial (read by the cluster)
+  float* csw = dqp + QR * DP;                          // [4 warps][2][DP] column sums of dK / dV, then [DP] column sums of dQ
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int bh = blockIdx.y, b = bh / heads, head = bh % heads;
   const int nsplit = gridDim.x, split = blockIdx.x;
@@ -331,6 +333,9 @@ __global__ void __launch_bounds__(NT) gaa_mma_bwd_kernel(const float* __restrict
   for (int i = 0; i < DP / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
   const int r0 = warp * 16 + g, r1 = r0 + 8;
   const bool ok0 = r0 < NQ, ok1 = r1 < NQ;
+  float csk[DP / 8][2], csv[DP / 8][2];               // per-thread column sums of dK / dV over this CTA's pixels (bias gradient of the kv projection)
+#pragma unroll
+  for (int i = 0; i < DP / 8; ++i) csk[i][0] = csk[i][1] = csv[i][0] = csv[i][1] = 0.f;
   for (int it = 0; it < n_my; ++it) {
     const int c = split + it * nsplit;
     const int nvalid = min(PC, HW - c * PC);
@@ -396,6 +401,11 @@ __global__ void __launch_bounds__(NT) gaa_mma_bwd_kernel(const float* __restrict
           mma16816(dk[2 * np + 1], as, b2, b3);
         }
       }
+#pragma unroll
+      for (int i = 0; i < DP / 8; ++i) {               // padded pixels carry P = dS = 0, so no masking is needed
+        csk[i][0] += dk[i][0] + dk[i][2]; csk[i][1] += dk[i][1] + dk[i][3];
+        csv[i][0] += dv[i][0] + dv[i][2]; csv[i][1] += dv[i][1] + dv[i][3];
+      }
       const int p0 = m0 + g, p1 = p0 + 8;
       bf16* row0 = dkv + ((long)b * HW + (long)c * PC + p0) * 2 * Cp + head * D;
       bf16* row1 = dkv + ((long)b * HW + (long)c * PC + p1) * 2 * Cp + head * D;
@@ -423,19 +433,47 @@ __global__ void __launch_bounds__(NT) gaa_mma_bwd_kernel(const float* __restrict
     *reinterpret_cast<float2*>(dqp + r0 * DP + col) = make_float2(dq[i][0] * scale, dq[i][1] * scale);
     *reinterpret_cast<float2*>(dqp + r1 * DP + col) = make_float2(dq[i][2] * scale, dq[i][3] * scale);
   }
+  if (dkv_colsum != nullptr) {                         // column sums of this CTA's dK / dV rows: reduce the 8 row groups of a warp, then the 4 warps
+#pragma unroll
+    for (int i = 0; i < DP / 8; ++i) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float a = csk[i][e], v = csv[i][e];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); v += __shfl_xor_sync(0xffffffffu, v, o); }
+        if (g == 0) { csw[(warp * 2 + 0) * DP + i * 8 + 2 * t + e] = a * scale; csw[(warp * 2 + 1) * DP + i * 8 + 2 * t + e] = v; }
+      }
+    }
+  }
   cluster.sync();
+  if (dkv_colsum != nullptr) {
+    for (int idx = tid; idx < 2 * D; idx += NT) {
+      const int which = idx / D, j = idx % D;
+      const float v = csw[(0 * 2 + which) * DP + j] + csw[(1 * 2 + which) * DP + j] + csw[(2 * 2 + which) * DP + j] + csw[(3 * 2 + which) * DP + j];
+      atomicAdd(dkv_colsum + which * Cp + head * D + j, v);
+    }
+  }
+  __syncthreads();
+  if (tid < DP) csw[tid] = 0.f;                        // reused: column sums of this CTA's dQ rows
+  __syncthreads();
   const int rows_mine = (NQ - split + nsplit - 1) / nsplit;
   for (int idx = tid; idx < rows_mine * D; idx += NT) {
     const int r = split + (idx / D) * nsplit, j = idx % D;
     float acc = 0.f;
     for (int pr = 0; pr < nsplit; ++pr) acc += cluster.map_shared_rank(dqp, pr)[r * DP + j];
     dm[qoff + (long)r * Cp + j] = acc;
+    if (dm_lo != nullptr) dm_lo[qoff + (long)r * Cp + j] = __float2bfloat16_rn(acc);
+    if (dm_colsum != nullptr) atomicAdd(&csw[j], acc);
+  }
+  if (dm_colsum != nullptr) {
+    __syncthreads();
+    if (tid < D) atomicAdd(dm_colsum + head * D + tid, csw[tid]);
   }
   cluster.sync();
 }
 
 template <int D> constexpr int fwd_smem() { return (QR + 4 * 128) * Geo<D>::PITCH * 2 + (QR * Geo<D>::DP + 2 * QR) * 4; }
-template <int D> constexpr int bwd_smem() { return (2 * QR + 4 * 64) * Geo<D>::PITCH * 2 + 2 * QR * (64 + 8) * 2 + (2 * QR + QR * Geo<D>::DP) * 4; }
+template <int D> constexpr int bwd_smem() { return (2 * QR + 4 * 64) * Geo<D>::PITCH * 2 + 2 * QR * (64 + 8) * 2 + (2 * QR + QR * Geo<D>::DP + 8 * Geo<D>::DP) * 4; }
 
 // CTAs per (image, head): enough to put about two CTAs on every SM, at most one per chunk, at most the portable cluster size
 inline int pick_nsplit(int nchunks, int bh) {
@@ -462,7 +500,7 @@ int launch_fwd(const void* m, const void* kv, int B, int HW, int heads, float* o
 
 template <int D>
 int launch_bwd(const float* dout, const float* out, const float* lse, const void* m, const void* kv, int B, int HW, int heads, float* dm, void* dkv,
-               cudaStream_t st) {
+               float* dkv_colsum, float* dm_colsum, void* dm_lo, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(gaa_mma_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem<D>());
@@ -473,7 +511,7 @@ int launch_bwd(const float* dout, const float* out, const float* lse, const void
   const int nsplit = pick_nsplit(nchunks, B * heads);
   dim3 grid(nsplit, B * heads);
   dfb_launch_cluster(gaa_mma_bwd_kernel<D>, grid, NT, bwd_smem<D>(), st, nsplit, dout, out, lse, (const bf16*)m, (const bf16*)kv, HW, heads,
-                     1.0f / sqrtf((float)D), nchunks, dm, (bf16*)dkv);
+                     1.0f / sqrtf((float)D), nchunks, dm, (bf16*)dkv, dkv_colsum, dm_colsum, (bf16*)dm_lo);
   return dfb_check_launch("gaa_mma_bwd");
 }
 
@@ -494,7 +532,7 @@ int dfb_gaa_mma_fwd(const void* m, const void* kv, int B, int HW, int heads, int
 }
 
 int dfb_gaa_mma_bwd(const float* dout, const float* out, const float* lse, const void* m, const void* kv, int B, int HW, int heads, int d, float* dm,
-                    void* dkv, cudaStream_t st) {
-  GAA_MMA_DISPATCH_D(d, { return launch_bwd<D>(dout, out, lse, m, kv, B, HW, heads, dm, dkv, st); });
+                    void* dkv, float* dkv_colsum, float* dm_colsum, void* dm_lo, cudaStream_t st) {
+  GAA_MMA_DISPATCH_D(d, { return launch_bwd<D>(dout, out, lse, m, kv, B, HW, heads, dm, dkv, dkv_colsum, dm_colsum, dm_lo, st); });
   return DFB_OK;
 }

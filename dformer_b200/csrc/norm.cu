@@ -294,6 +294,138 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const T* __restrict__ d
   }
 }
 
+// raw (unconverted) 8-element vectors: lets the loads of the NEXT row stay in flight while the current row is reduced
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> {
+  uint4 v;
+  __device__ __forceinline__ void load(const bf16* p) { v = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void get(float* f) const { Vec8<bf16>::unpack(v, f); }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) { a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4); }
+  __device__ __forceinline__ void get(float* f) const { f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w; }
+};
+
+template <typename T, int L>
+__global__ void __launch_bounds__(256, 2) ln_bwd_vec_pf_kernel(const T* __restrict__ dy, const T* __restrict__ dy2, const float* __restrict__ x,
+                                                         const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                         int M, int C, const float* dx_in, float* dx, float* __restrict__ dgamma,
+                                                         float* __restrict__ dbeta) {
+  pdl_sync();
+  extern __shared__ float sm[];   // [8 warps][2][C] per-warp partial column sums
+  constexpr int RPW = 32 / L, VPL = 1;
+  const int lane = threadIdx.x & 31, sub = lane % L, rsel = lane / L;
+  const int nvec = C >> 3;
+  const int groups_per_block = (blockDim.x >> 5) * RPW;
+  float gm[VPL][8], pg[VPL][8], pb[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = sub + i * L;
+    if (v < nvec) Vec8<float>::load(gamma + v * 8, gm[i]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { pg[i][j] = 0.f; pb[i][j] = 0.f; }
+  }
+  const float invC = 1.f / (float)C;
+  // Software pipeline (one-vector-per-lane shapes, C <= 256: the register budget allows it): the loads of the next row of this warp
+  // are issued before the current row is reduced, doubling the bytes in flight of a kernel that runs at 16 warps per SM.
+  constexpr bool PF = (VPL == 1);
+  Raw8<T> nd[VPL], nd2[VPL];
+  Raw8<float> nx[VPL], ni[VPL];
+  float nmu = 0.f, nrs = 0.f;
+  const long stride = (long)gridDim.x * groups_per_block;
+  auto fetch = [&](long row0) {
+    const long row = row0 + rsel;
+    const bool valid = row < M;
+    nmu = valid ? mean[row] : 0.f;
+    nrs = valid ? rstd[row] : 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vv = sub + i * L;
+      if (vv < nvec && valid) {
+        nd[i].load(dy + row * C + vv * 8);
+        if (dy2) nd2[i].load(dy2 + row * C + vv * 8);
+        nx[i].load(x + row * C + vv * 8);
+        if (dx_in) ni[i].load(dx_in + row * C + vv * 8);
+      }
+    }
+  };
+  long row0 = (long)blockIdx.x * groups_per_block + (threadIdx.x >> 5) * RPW;
+  if (PF && row0 < M) fetch(row0);
+  for (; row0 < M; row0 += stride) {
+    const long row = row0 + rsel;
+    const bool valid = row < M;                     // warp-uniform trip count; masked rows contribute zeros
+    if (!PF) fetch(row0);
+    const float mu = nmu, rs = nrs;
+    float xh[VPL][8], g[VPL][8], o[VPL][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vv = sub + i * L;
+      if (vv < nvec && valid) {
+        float d[8], xv[8];
+        nd[i].get(d);
+        if (dy2) {                                  // fused gradient fan-in (was a separate axpy pass): sum rounded to T like that pass did
+          float d2[8];
+          nd2[i].get(d2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] = to_f(from_f<T>(d[j] + d2[j]));
+        }
+        nx[i].get(xv);
+        if (dx_in) ni[i].get(o[i]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[i][j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (xv[j] - mu) * rs;
+          g[i][j] = d[j] * gm[i][j];
+          pg[i][j] = fmaf(d[j], xh[i][j], pg[i][j]);
+          pb[i][j] += d[j];
+          s1 += g[i][j];
+          s2 = fmaf(g[i][j], xh[i][j], s2);
+        }
+      }
+    }
+    if (PF && row0 + stride < M) fetch(row0 + stride);          // next row's loads fly during the reductions and the store below
+    s1 = group_sum<L>(s1) * invC;
+    s2 = group_sum<L>(s2) * invC;
+    if (!valid) continue;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vv = sub + i * L;
+      if (vv < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[i][j] += rs * (g[i][j] - s1 - xh[i][j] * s2);
+        Vec8<float>::store(dx + row * C + vv * 8, o[i]);
+      }
+    }
+  }
+  // column sums: lanes of a warp that own the same channels (different rows) meet through shuffles, every warp stores its
+  // partial row to its own shared-memory slab (no atomics), then one thread per channel adds the 8 slabs and issues the
+  // single global atomic of this CTA for that channel
+  float* slab = sm + (threadIdx.x >> 5) * 2 * C;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vv = sub + i * L;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = pg[i][j], b = pb[i][j];
+#pragma unroll
+      for (int o = L; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+      if (rsel == 0 && vv < nvec) { slab[vv * 8 + j] = a; slab[C + vv * 8 + j] = b; }
+    }
+  }
+  __syncthreads();
+  const int nwarp = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    float v = 0.f;
+    for (int w = 0; w < nwarp; ++w) v += sm[w * 2 * C + c];
+    atomicAdd((c < C ? dgamma : dbeta - C) + c, v);
+  }
+}
+
 #define LN_DISPATCH_VEC(C, ...)                                                            \
   do {                                                                                     \
     const int nvec_ = (C) >> 3;                                                            \
@@ -567,6 +699,7 @@ extern "C" int dfb200_scale_residual_layernorm_fwd(const float* res, const void*
   return ln_fwd_launch(res, gamma, beta, eps, M, C, y, dtype, mean, rstd, rp, ST);
 }
 
+#define LN_BWD_ARGS grid, 256, 16 * C * sizeof(float), ST, (const T*)dy, (const T*)dy2, x, gamma, mean, rstd, M, C, dx_in, dx, dgamma, dbeta
 extern "C" int dfb200_layernorm_bwd(const void* dy, const void* dy2, int dy_dtype, const float* x, const float* gamma, const float* mean, const float* rstd, int M, int C,
                                     const float* dx_in, float* dx, float* dgamma, float* dbeta, void* stream) {
   DFB_REQUIRE(C >= 1 && C <= 32 * LN_MAX_PER_LANE, "layernorm: C=%d out of range", C);
@@ -576,7 +709,14 @@ extern "C" int dfb200_layernorm_bwd(const void* dy, const void* dy2, int dy_dtyp
   const int grid = min(dfb_cdiv(M, 32), 148 * 8);
   if (C % 8 == 0 && C <= 704 /* 8 per-warp slabs of 2*C floats in 48 KB */ && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dy2) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dx_in)) & 15) == 0) {
     DFB_DISPATCH_DTYPE(dy_dtype, T, {
-      LN_DISPATCH_VEC(C, { dfb_launch(ln_bwd_vec_kernel<T, L, VPL>, grid, 256, 16 * C * sizeof(float), ST, (const T*)dy, (const T*)dy2, x, gamma, mean, rstd, M, C, dx_in, dx, dgamma, dbeta); });
+      const int nvec = C >> 3;
+      if (nvec <= 8) dfb_launch(ln_bwd_vec_pf_kernel<T, 8>, LN_BWD_ARGS);              // one vector per lane: software-pipelined rows
+      else if (nvec <= 16) dfb_launch(ln_bwd_vec_pf_kernel<T, 16>, LN_BWD_ARGS);
+      else if (nvec <= 32) dfb_launch(ln_bwd_vec_pf_kernel<T, 32>, LN_BWD_ARGS);
+      else if (nvec <= 64) dfb_launch(ln_bwd_vec_kernel<T, 32, 2>, LN_BWD_ARGS);
+      else if (nvec <= 96) dfb_launch(ln_bwd_vec_kernel<T, 32, 3>, LN_BWD_ARGS);
+      else dfb_launch(ln_bwd_vec_kernel<T, 32, 4>, LN_BWD_ARGS);
+
     });
     return dfb_check_launch("layernorm_bwd_vec");
   }

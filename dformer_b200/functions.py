@@ -407,15 +407,22 @@ class BlockFn(torch.autograd.Function):
             with torch.cuda.stream(side2):
                 do7 = torch.empty((B * 49, Ce), device=dev, dtype=F32)
                 K.resize_bwd(dy, C, B, 7, 7, Ce, H, W, do7)
-                if sv["probs"] is None:
-                    dm, dkv = K.gaa_fused_bwd(do7, sv["o7"], sv["lse7"], sv["m"], sv["kv"], B, HW, st.heads, Ce // st.heads)
+                bias_done = False
+                if sv["probs"] is None and T == torch.bfloat16:      # tensor-core kernel: also emits both bias gradients and dm in bf16
+                    dmT, dkv = K.gaa_fused_bwd_ex(do7, sv["o7"], sv["lse7"], sv["m"], sv["kv"], B, HW, st.heads, Ce // st.heads,
+                                                  G["attn.kv.bias"], G["attn.short_cut_linear.bias"])
+                    bias_done = True
                 else:
-                    dm, dkv = K.gaa_bwd(do7, sv["m"], sv["kv"], sv["probs"], B, HW, st.heads, Ce // st.heads)
-                dl_kv = _lin_bwd(dkv, sv["l"], pk("attn.kv")[0], G["attn.kv.weight"], G["attn.kv.bias"], T)
+                    if sv["probs"] is None:
+                        dm, dkv = K.gaa_fused_bwd(do7, sv["o7"], sv["lse7"], sv["m"], sv["kv"], B, HW, st.heads, Ce // st.heads)
+                    else:
+                        dm, dkv = K.gaa_bwd(do7, sv["m"], sv["kv"], sv["probs"], B, HW, st.heads, Ce // st.heads)
+                    dmT = dm if T == F32 else K.cast(dm, T)
+                dl_kv = _lin_bwd(dkv, sv["l"], pk("attn.kv")[0], G["attn.kv.weight"], None if bias_done else G["attn.kv.bias"], T)
                 ev_dlkv = K.signal(side2)                 # the main stream needs dl_kv early (GELU' of l); the pooled-query
-                dmT = dm if T == F32 else K.cast(dm, T)   # gradients below are only consumed by the final LayerNorm backward
+                # gradients below are only consumed by the final LayerNorm backward
                 dpooled = _lin_bwd(dmT, sv["pooled"], pk("attn.short_cut_linear")[0], G["attn.short_cut_linear.weight"],
-                                   G["attn.short_cut_linear.bias"], T)
+                                   None if bias_done else G["attn.short_cut_linear.bias"], T)
                 dxn_pool, den_pool = K.pool7_bwd(dpooled, C, Ce, B, H, W)
             K.share(main, dxn_pool, den_pool, dl_kv)
         # ---- RGB path: a = a(dw7(l))

@@ -341,6 +341,18 @@ def gaa_fused_bwd(dout, out, lse, m, kv, B, HW, heads, d):
     return dm, dkv
 
 
+def gaa_fused_bwd_ex(dout, out, lse, m, kv, B, HW, heads, d, dkv_colsum, dm_colsum):
+    """bf16 tensor-core backward that also accumulates the bias gradients of the kv / short_cut_linear projections and returns
+    dm already in bf16: (dm_lo, dkv)."""
+    assert m.dtype == torch.bfloat16
+    dm = torch.empty((B * 49, heads * d), device=m.device, dtype=torch.float32)
+    dm_lo = torch.empty((B * 49, heads * d), device=m.device, dtype=torch.bfloat16)
+    dkv = torch.empty_like(kv)
+    lib().gaa_fused_bwd_ex(dout.data_ptr(), out.data_ptr(), lse.data_ptr(), m.data_ptr(), kv.data_ptr(), B, HW, heads, d, dm.data_ptr(),
+                           dkv.data_ptr(), _p(dkv_colsum), _p(dm_colsum), dm_lo.data_ptr(), _s())
+    return dm_lo, dkv
+
+
 def resize_fwd(inp, B, Hi, Wi, out, Ho, Wo, col0=0):
     C = inp.shape[-1]
     lib().resize_fwd(inp.data_ptr(), dt(inp), B, Hi, Wi, C, out.data_ptr(), dt(out), Ho, Wo, out.stride(0), col0, _s())

@@ -167,6 +167,11 @@ int dfb200_gaa_fused_fwd(const void* m, const void* kv, int dtype, int B, int HW
                          float* scratch, int* counters, void* stream);
 int dfb200_gaa_fused_bwd(const float* dout, const float* out, const float* lse, const void* m, const void* kv, int dtype,
                          int B, int HW, int heads, int d, float* dm, void* dkv, void* stream);
+/* bf16 only: the same backward pass, also emitting (each optional, NULL = skip) dkv_colsum[2*heads*d] += column sums of dkv (bias
+ * gradient of `kv`, DFormer.py:121), dm_colsum[heads*d] += column sums of dm (bias gradient of `short_cut_linear`, :108) and
+ * dm_lo = dm in bf16 (the operand of that layer's gradient GEMMs): three launches less per Block. */
+int dfb200_gaa_fused_bwd_ex(const float* dout, const float* out, const float* lse, const void* m, const void* kv, int B, int HW,
+                            int heads, int d, float* dm, void* dkv, float* dkv_colsum, float* dm_colsum, void* dm_lo, void* stream);
 /* bilinear (align_corners=False) resize of a channels-last map into a column slice of a wider buffer:
  * out[b, y, x, col0 + c] = interp(in[b, :, :, c]).  Used for 7x7 -> HxW (DFormer.py:131), the head's
  * resize+concat (ham_head.py:226-233) with fp32 inputs. */

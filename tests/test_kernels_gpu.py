@@ -343,6 +343,13 @@ def test_gaa(dtype, HW, heads, d):
         dm2, dkv2 = k.gaa_fused_bwd(dout, out2, lse, m, kv, B, HW, heads, d)
         torch.testing.assert_close(dm2, mr.grad, **(t if dtype == torch.bfloat16 else tf))
         torch.testing.assert_close(dkv2.float(), kvr.grad, **t)
+        if dtype == torch.bfloat16:           # the variant that also emits the two bias gradients (accumulating) and dm in bf16
+            cs_kv, cs_m = torch.ones(2 * Cp, device=DEV), torch.ones(Cp, device=DEV)
+            dm3, dkv3 = k.gaa_fused_bwd_ex(dout, out2, lse, m, kv, B, HW, heads, d, cs_kv, cs_m)
+            torch.testing.assert_close(dkv3.float(), dkv2.float(), rtol=0, atol=0)
+            torch.testing.assert_close(dm3.float(), dm2, rtol=1e-2, atol=1e-2)
+            torch.testing.assert_close(cs_kv - 1, kvr.grad.sum(0), rtol=3e-2, atol=6e-2 * max(1.0, (B * HW) ** 0.5 / 8))
+            torch.testing.assert_close(cs_m - 1, mr.grad.sum(0), rtol=3e-2, atol=5e-2)
 
 
 @pytest.mark.parametrize("in_dtype,out_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16)])
