@@ -12,6 +12,8 @@ import torch.distributed as dist
 
 import weakref
 
+import os as _os
+_SKIP_AR = _os.environ.get("DFB200_PROFILE_SKIP_AR", "0") == "1"      # profiling only: drop the gradient all-reduces (wrong results) to see their cost
 _GRAD_SYNCS = weakref.WeakSet()
 _PEER_CHAIN = {"event": None, "capturing": False}     # completion event of the most recent peer-memory exchange of this step
 
@@ -49,7 +51,8 @@ class GradSync:
                 self.stream.wait_event(pe)
             self.inflight = True
             with torch.cuda.stream(self.stream):
-                dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group)
+                if not _SKIP_AR:
+                    dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group)
             buf.record_stream(self.stream)
         else:                       # gloo (CPU tests): no AVG op, no streams
             dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
