@@ -584,13 +584,13 @@ bool dfb_gemm_tc_supported(const dfb200_gemm_args& g) {
 int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   DFB_REQUIRE(dfb_gemm_tc_supported(g), "gemm_tc: unsupported arguments (dtype=%d/%d batch=%d lda=%ld ldb=%ld epi_mode=%d)", g.a_dtype, g.b_dtype, g.batch,
               g.lda, g.ldb, g.epi_mode);
-  static int num_sms = 0;
+  static int num_sms_all = 0, sms_main = 0, sms_split = 0;
   static bool attr_set = false;
   static int forced_bn = 0, forced_stages = 0, forced_epi = 0;
   if (!attr_set) {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&num_sms_all, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -599,6 +599,15 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
     if (const char* v = getenv("DFB200_TC_BN")) forced_bn = atoi(v);      // whole-process overrides for tools/gemm_replay.py runs
     if (const char* v = getenv("DFB200_TC_STAGES")) forced_stages = atoi(v);
     if (const char* v = getenv("DFB200_TC_EPI")) forced_epi = atoi(v);
+    // Persistent grids deliberately do NOT cover the whole chip.  The training step runs four streams (RGB chain, depth chain,
+    // attention branch, weight gradients): a GEMM whose CTAs sit on every SM keeps the other streams' kernels waiting for its
+    // whole duration (and a one-wave kernel that cannot place all its CTAs runs a second wave).  Measured on the DFormer-L step
+    // (profiles/r02_sm_budget_sweep.txt): forward / dgrad GEMMs on 5/6 of the SMs and the split-K weight-gradient GEMMs (off the
+    // critical path) on half of them: 22.9 -> 22.1 ms/step, although the same GEMMs timed alone get 9 % slower.
+    sms_main = num_sms_all - num_sms_all / 6;
+    sms_split = (num_sms_all * 49) / 100;
+    if (const char* v = getenv("DFB200_TC_SM_RESERVE")) { const int r = atoi(v); if (r > 0 && r < num_sms_all) sms_main = sms_split = num_sms_all - r; }
+    if (const char* v = getenv("DFB200_TC_SM_SPLIT")) { const int r = atoi(v); if (r > 0 && r <= num_sms_all) sms_split = r; }
     attr_set = true;
   }
   TcParams p;
@@ -614,6 +623,7 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   // wgrad-like problems are split along K; their tile count is multiplied by the split factor later, so only the un-split
   // (forward / dgrad) shapes are tuned for wave quantisation
   const bool will_split = (g.splitk == 0 && g.out_dtype == 0 && g.act == 0 && p.kb_total >= 16) || g.splitk > 1;
+  const int num_sms = will_split ? sms_split : sms_main;
   // bf16 C through TMA: 16-byte aligned base / leading dimension / batch stride
   const bool can_tma_store = p.out_bf16 && !will_split && (g.ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 &&
                              (g.batch == 1 || (g.strideC % 8) == 0);
