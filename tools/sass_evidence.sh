@@ -1,7 +1,7 @@
 #!/bin/bash
 # Counts the Blackwell-specific SASS mnemonics per kernel of libdformer_b200.so (no GPU needed): UTC*MMA = tcgen05.mma,
-# LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG/UBLKCP = TMA, FFMA2 = packed fp32 FMA, HMMA = legacy mma.sync (expected: none).
-#   tools/sass_evidence.sh > profiles/r01_sass_mnemonics.txt
+# LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG/UBLKCP = TMA, FFMA2 = packed fp32 FMA, HMMA = warp-level mma.sync (only the 49-row attention core, gaa_mma.cu: see its header for why not tcgen05).
+#   tools/sass_evidence.sh > profiles/r02_sass_mnemonics.txt
 LIB=${1:-dformer_b200/libdformer_b200.so}
 echo "cuobjdump -sass $LIB  (sm_100a; built by 'make'; $(nvcc --version | tail -1))"
 cuobjdump -sass "$LIB" | awk '
