@@ -284,19 +284,33 @@ __global__ void __launch_bounds__(EW_THREADS) scale_residual_bwd_kernel(const fl
 }
 
 // ------------------------------------------------------------------ NMF helpers
-__global__ void normalize_cols_kernel(const float* __restrict__ in, int D, int R, float* __restrict__ out, float* __restrict__ norms) {
+__global__ void __launch_bounds__(256) normalize_cols_kernel(const float* __restrict__ in, int D, int R, float* __restrict__ out, float* __restrict__ norms) {
   pdl_sync();
-  // one block per image b; thread r handles column r of the [D,R] matrix: out = in / max(||col||_2, 1e-12)
+  // one block per image b: out = in / max(||col||_2, 1e-12) per column of the [D, R] matrix.  Thread t owns column t % R and every
+  // (256 / R)-th row (coalesced along R); the per-column partial sums meet in shared memory.
+  extern __shared__ float nsm[];                       // [blockDim.x] partials, then [R] inverse norms
   const int b = blockIdx.x;
   const float* src = in + (long)b * D * R;
   float* dst = out + (long)b * D * R;
-  for (int r = threadIdx.x; r < R; r += blockDim.x) {
-    float s = 0.f;
-    for (int d = 0; d < D; ++d) { const float v = src[(long)d * R + r]; s = fmaf(v, v, s); }
-    const float nrm = fmaxf(sqrtf(s), 1e-12f);
-    if (norms) norms[b * R + r] = nrm;
-    const float inv = 1.f / nrm;
-    for (int d = 0; d < D; ++d) dst[(long)d * R + r] = src[(long)d * R + r] * inv;
+  const int t = threadIdx.x, nth = blockDim.x;
+  const int rl = nth / R;                              // row lanes (>= 1: the launcher guarantees R <= blockDim.x)
+  const int col = t % R, lane_r = t / R;
+  float s = 0.f;
+  if (lane_r < rl)
+    for (int d = lane_r; d < D; d += rl) { const float v = src[(long)d * R + col]; s = fmaf(v, v, s); }
+  nsm[t] = s;
+  __syncthreads();
+  if (t < R) {
+    float tot = 0.f;
+    for (int q = 0; q < rl; ++q) tot += nsm[q * R + t];
+    const float nrm = fmaxf(sqrtf(tot), 1e-12f);
+    if (norms) norms[b * R + t] = nrm;
+    nsm[nth + t] = 1.f / nrm;
+  }
+  __syncthreads();
+  if (lane_r < rl) {
+    const float inv = nsm[nth + col];
+    for (int d = lane_r; d < D; d += rl) dst[(long)d * R + col] = src[(long)d * R + col] * inv;
   }
 }
 
@@ -528,7 +542,8 @@ extern "C" int dfb200_scale_residual_bwd(const float* dout, const void* y, long 
 }
 
 extern "C" int dfb200_normalize_cols(const float* in, int B, int D, int R, float* out, float* norms, void* stream) {
-  dfb_launch(normalize_cols_kernel, B, 64, 0, ST, in, D, R, out, norms);
+  DFB_REQUIRE(R >= 1 && R <= 256, "normalize_cols: R=%d out of range (1..256)", R);
+  dfb_launch(normalize_cols_kernel, B, 256, (256 + R) * sizeof(float), ST, in, D, R, out, norms);
   return dfb_check_launch("normalize_cols");
 }
 extern "C" int dfb200_softmax_rows(const float* in, int rows, int cols, float* out, void* stream) {

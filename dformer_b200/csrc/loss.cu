@@ -246,6 +246,94 @@ __global__ void __launch_bounds__(256) upsample_ce_bwd_rows_fused_kernel(const T
       if (c0 + j < ncls) { tA[o + j] = a[j] - bb[j]; tB[o + j] = bb[j]; }
   }
 }
+// ---- training forward (loss + per-pixel log-sum-exp only, nothing hi-res materialised), same row grouping as the recompute
+// backward above: thread = (b, source row ly0, hi-res column ox) walks the <= MAXR hi-res rows whose bilinear source row is ly0.
+// The two horizontally interpolated low-res rows are built once per class and shared by those rows (one lerp + one exp per
+// hi-res logit instead of four strided loads + three lerps), 16-byte loads over the classes when ncls % 8 == 0, and one common
+// shift max_c max(top_c, bot_c) >= every interpolated logit of the group replaces the online-softmax rescaling.
+template <typename T, int MAXR, bool VEC>
+__global__ void __launch_bounds__(256) upsample_ce_fwd_rows_kernel(const T* __restrict__ small, int B, int h, int w, int ncls, int H, int W,
+                                                                   const int64_t* __restrict__ label, int ignore, float* __restrict__ lse_out,
+                                                                   float* loss_acc) {
+  pdl_sync();
+  __shared__ float red[32];
+  float loss = 0.f, cnt = 0.f;
+  const long n = (long)B * h * W;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % W), ly0 = (int)((i / W) % h), b = (int)(i / ((long)W * h));
+    const Lerp lx = lerp_coord(ox, w, W);
+    const int i1 = min(ly0 + 1, h - 1);
+    const T* r00 = small + (((long)b * h + ly0) * w + lx.i0) * ncls;
+    const T* r01 = small + (((long)b * h + ly0) * w + lx.i1) * ncls;
+    const T* r10 = small + (((long)b * h + i1) * w + lx.i0) * ncls;
+    const T* r11 = small + (((long)b * h + i1) * w + lx.i1) * ncls;
+    const int o_lo = first_row_of(ly0, h, H), nr = min(first_row_of(ly0 + 1, h, H) - o_lo, MAXR);
+    const float wx = lx.w1, ux = 1.f - lx.w1;
+    auto rows8 = [&](int c0, float* top, float* bot) {          // horizontally interpolated logits of classes c0 .. c0 + 7
+      float a[8], bq[8], c[8], d[8];
+      if (VEC) {
+        Vec8<T>::load(r00 + c0, a); Vec8<T>::load(r01 + c0, bq); Vec8<T>::load(r10 + c0, c); Vec8<T>::load(r11 + c0, d);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool ok = c0 + j < ncls;
+          a[j] = ok ? to_f(r00[c0 + j]) : -INFINITY; bq[j] = ok ? to_f(r01[c0 + j]) : -INFINITY;
+          c[j] = ok ? to_f(r10[c0 + j]) : -INFINITY; d[j] = ok ? to_f(r11[c0 + j]) : -INFINITY;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { top[j] = ux * a[j] + wx * bq[j]; bot[j] = ux * c[j] + wx * d[j]; }
+    };
+    float M = -INFINITY;
+    for (int c0 = 0; c0 < ncls; c0 += 8) {
+      float top[8], bot[8];
+      rows8(c0, top, bot);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (VEC || c0 + j < ncls) M = fmaxf(M, fmaxf(top[j], bot[j]));
+    }
+    float wy[MAXR], sum[MAXR], pk[MAXR];
+    int lab[MAXR];
+#pragma unroll
+    for (int k = 0; k < MAXR; ++k) {
+      sum[k] = 0.f; pk[k] = 0.f; wy[k] = 0.f; lab[k] = -1;
+      if (k < nr) {
+        wy[k] = lerp_coord(o_lo + k, h, H).w1;
+        const long lb = label[((long)b * H + o_lo + k) * W + ox];
+        lab[k] = (lb != (long)ignore && lb >= 0 && lb < ncls) ? (int)lb : -1;
+      }
+    }
+    for (int c0 = 0; c0 < ncls; c0 += 8) {
+      float top[8], bot[8];
+      rows8(c0, top, bot);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (VEC || c0 + j < ncls) {
+#pragma unroll
+          for (int k = 0; k < MAXR; ++k) {
+            const float v = (1.f - wy[k]) * top[j] + wy[k] * bot[j];
+            sum[k] += __expf(v - M);
+            if (c0 + j == lab[k]) pk[k] = v;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < MAXR; ++k) {
+      if (k < nr) {
+        const float lse = M + __logf(sum[k]);
+        lse_out[((long)b * H + o_lo + k) * W + ox] = lse;
+        if (lab[k] >= 0) { loss += lse - pk[k]; cnt += 1.f; }
+      }
+    }
+  }
+  if (loss_acc) {
+    loss = block_sum(loss, red);
+    cnt = block_sum(cnt, red);
+    if (threadIdx.x == 0) { atomicAdd(loss_acc, loss); atomicAdd(loss_acc + 1, cnt); }
+  }
+}
+
 // Pass 2 (columns): ds[b,ly,lx,c] = scale * sum_ox wx(lx,ox) * (tA[ly] + tB[ly-1] (+ tB[h-1] on the last row))[ox, c]
 template <typename TD>
 __global__ void __launch_bounds__(256) upsample_ce_bwd_cols_fused_kernel(const float* __restrict__ tA, const float* __restrict__ tB, int B, int h, int w,
@@ -286,6 +374,20 @@ __global__ void __launch_bounds__(256) upsample_ce_bwd_cols_fused_kernel(const f
 extern "C" int dfb200_upsample_ce_fwd(const void* logits_small, int dtype, int B, int h, int w, int ncls, int H, int W, const int64_t* label, int ignore,
                                       float* out_nchw, float* lse, float* loss_acc, void* up_lowp, void* stream) {
   const long n = (long)B * H * W;
+  // training forward (only the loss and the per-pixel log-sum-exp are wanted): the row-grouped kernel; a source row feeds at most
+  // ceil(1.5 * H / h) hi-res rows (the first group also takes the rows whose source coordinate clamps to 0)
+  constexpr int MAXR = 12;
+  if (out_nchw == nullptr && up_lowp == nullptr && lse != nullptr && label != nullptr && H >= h && (3L * H + 2 * h - 1) / (2L * h) <= MAXR) {
+    const long n1 = (long)B * h * W;
+    long g1 = (n1 + 255) / 256;
+    if (g1 < 1) g1 = 1;
+    const bool vec = (ncls % 8) == 0 && (reinterpret_cast<uintptr_t>(logits_small) & 15) == 0;
+    DFB_DISPATCH_DTYPE(dtype, T, {
+      if (vec) dfb_launch(upsample_ce_fwd_rows_kernel<T, MAXR, true>, (unsigned)g1, 256, 0, ST, (const T*)logits_small, B, h, w, ncls, H, W, label, ignore, lse, loss_acc);
+      else dfb_launch(upsample_ce_fwd_rows_kernel<T, MAXR, false>, (unsigned)g1, 256, 0, ST, (const T*)logits_small, B, h, w, ncls, H, W, label, ignore, lse, loss_acc);
+    });
+    return dfb_check_launch("upsample_ce_fwd_rows");
+  }
   long g = (n + 255) / 256;
   if (g > 148L * 16) g = 148L * 16;
   if (g < 1) g = 1;

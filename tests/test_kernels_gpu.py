@@ -549,6 +549,11 @@ def test_upsample_ce(dtype, ncls):
     ds2 = k.upsample_ce_bwd_sep(up, dtype, B, h, w, ncls, H, W, label, 255, lse2, acc2, dl)
     t2 = dict(rtol=5e-2, atol=2e-5) if dtype == torch.bfloat16 else dict(rtol=1e-3, atol=1e-7)
     torch.testing.assert_close(ds2.view(B, h, w, ncls).float(), sr.grad.permute(0, 2, 3, 1), **t2)
+    # training forward (loss + per-pixel log-sum-exp only): the row-grouped kernel (16-byte class vectors when ncls % 8 == 0)
+    _, lse4, acc4, loss4, _ = k.upsample_ce_fwd(small.view(-1, ncls), B, h, w, ncls, H, W, label, 255, want_out=False)
+    torch.testing.assert_close(loss4, ref_loss, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(lse4, lse, rtol=1e-4, atol=1e-4)          # lse: the per-pixel kernel's, checked through the loss above
+    torch.testing.assert_close(acc4[1], acc[1])
     # recompute form (what training uses): nothing but lse kept by the forward pass
     ds3 = k.upsample_ce_bwd_fused(small.view(-1, ncls), B, h, w, ncls, H, W, label, 255, lse, acc, dl)
     torch.testing.assert_close(ds3.view(B, h, w, ncls).float(), sr.grad.permute(0, 2, 3, 1), **t)
