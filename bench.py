@@ -383,6 +383,10 @@ def gemm_census_roofline(runner, dev, K):
         for i in range(nsets):
             launch(i)
         per = _time_replays(launch, reps, cap_stream)
+        K.gemm_sm_budget(148, 148)                          # the same launches with grids over the whole chip (the kernel alone)
+        launch(0)
+        tot["ms_full_chip"] = tot.get("ms_full_chip", 0.0) + _time_replays(launch, reps, cap_stream) * 1e3 * cnt
+        K.gemm_sm_budget(0, 0)
         tot["ms"] += per * 1e3 * cnt
         tot["fl"] += fl * cnt
         tot["by"] += by * cnt
@@ -652,6 +656,11 @@ def main():
                      "achieved": achieved_gbs, "peak": hbm, "unit": "GB/s", "frac": achieved_gbs / hbm, "traffic": traffic,
                      "traffic_source": traffic_src,
                      "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)",
+                     "grid_policy": "persistent grids cover 124 SMs (forward / dgrad) and 72 SMs (split-K weight gradients) of 148: fastest "
+                                    "inside the four-stream step (profiles/r02_sm_budget_sweep.txt); `full_chip` = the same launches with grids "
+                                    "over all 148 SMs, i.e. the kernel running alone",
+                     "full_chip": {"achieved": tc_by / (tot["ms_full_chip"] * 1e-3) / 1e9, "frac": tc_by / (tot["ms_full_chip"] * 1e-3) / 1e9 / hbm,
+                                   "kernel_ms_per_step": tot["ms_full_chip"]} if tot.get("ms_full_chip") else None,
                      "algorithmic_bytes_per_launch": tc_by / max(tc_n, 1), "launches_per_step": tc_n,
                      "avg_launch_us": tc_ms * 1e3 / max(tc_n, 1), "kernel_ms_per_step": tc_ms, "kernel_share_of_step": tc_ms / ms,
                      "timing": "per distinct launch configuration of the step: CUDA events around a captured graph of back-to-back launches "

@@ -37,6 +37,7 @@ P, I, L, F, D = c_void_p, c_int, c_long, c_float, c_double
 # name -> argument ctypes (all return int unless noted)
 SIGNATURES = {
     "dfb200_gemm": [ctypes.POINTER(GemmArgs), P],
+    "dfb200_gemm_sm_budget": [I, I],
     "dfb200_colsum": [P, I, L, I, I, P, I, P],
     "dfb200_pack_params": [P, I, I, I, P],
     "dfb200_unpack_conv_grad": [P, I, I, I, P, P],
@@ -68,7 +69,7 @@ SIGNATURES = {
     "dfb200_bn_finalize": [P, P, D, F, F, I, P, P, P, P, P],
     "dfb200_bn_eval_stats": [P, P, F, I, P, P, P],
     "dfb200_bn_apply": [P, I, P, P, P, P, P, I, P, I, I, I, P, I, P],
-    "dfb200_bn_bwd_reduce": [P, I, P, I, P, P, P, P, P, I, P, I, I, I, P, P, P, P],
+    "dfb200_bn_bwd_reduce": [P, I, P, I, P, P, P, P, P, I, P, I, I, I, P, P, P, P, P, P],
     "dfb200_bn_bwd_apply": [P, I, P, I, P, P, P, P, P, F, I, I, I, P, I, P],
     "dfb200_bn_fold": [P, I, I, I, L, P, P, P, F, P, P, P, P],
     "dfb200_normalize_cols": [P, I, I, I, P, P, P],

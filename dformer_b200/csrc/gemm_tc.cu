@@ -569,6 +569,15 @@ int next_pow2_cols(int c) {
 
 }  // namespace
 
+// SM budgets of the persistent grids: [0] forward / dgrad, [1] split-K (weight gradients).  g_sms_budget = 0 -> the measured defaults.
+static int g_sms_default[2] = {0, 0};
+static int g_sms_budget[2] = {0, 0};
+extern "C" int dfb200_gemm_sm_budget(int main_sms, int split_sms) {
+  g_sms_budget[0] = main_sms > 0 ? main_sms : 0;
+  g_sms_budget[1] = split_sms > 0 ? split_sms : 0;
+  return DFB_OK;
+}
+
 bool dfb_gemm_tc_supported(const dfb200_gemm_args& g) {
   if (g.a_dtype != 1 || g.b_dtype != 1 || g.batch < 1 || g.batch_inner > 1) return false;
   if (g.batch > 1 && ((g.strideA % 8) || (g.strideB % 8) || g.bias != nullptr)) return false;
@@ -584,7 +593,7 @@ bool dfb_gemm_tc_supported(const dfb200_gemm_args& g) {
 int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   DFB_REQUIRE(dfb_gemm_tc_supported(g), "gemm_tc: unsupported arguments (dtype=%d/%d batch=%d lda=%ld ldb=%ld epi_mode=%d)", g.a_dtype, g.b_dtype, g.batch,
               g.lda, g.ldb, g.epi_mode);
-  static int num_sms_all = 0, sms_main = 0, sms_split = 0;
+  static int num_sms_all = 0;
   static bool attr_set = false;
   static int forced_bn = 0, forced_stages = 0, forced_epi = 0;
   if (!attr_set) {
@@ -604,10 +613,10 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
     // whole duration (and a one-wave kernel that cannot place all its CTAs runs a second wave).  Measured on the DFormer-L step
     // (profiles/r02_sm_budget_sweep.txt): forward / dgrad GEMMs on 5/6 of the SMs and the split-K weight-gradient GEMMs (off the
     // critical path) on half of them: 22.9 -> 22.1 ms/step, although the same GEMMs timed alone get 9 % slower.
-    sms_main = num_sms_all - num_sms_all / 6;
-    sms_split = (num_sms_all * 49) / 100;
-    if (const char* v = getenv("DFB200_TC_SM_RESERVE")) { const int r = atoi(v); if (r > 0 && r < num_sms_all) sms_main = sms_split = num_sms_all - r; }
-    if (const char* v = getenv("DFB200_TC_SM_SPLIT")) { const int r = atoi(v); if (r > 0 && r <= num_sms_all) sms_split = r; }
+    g_sms_default[0] = num_sms_all - num_sms_all / 6;
+    g_sms_default[1] = (num_sms_all * 49) / 100;
+    if (const char* v = getenv("DFB200_TC_SM_RESERVE")) { const int r = atoi(v); if (r > 0 && r < num_sms_all) g_sms_default[0] = g_sms_default[1] = num_sms_all - r; }
+    if (const char* v = getenv("DFB200_TC_SM_SPLIT")) { const int r = atoi(v); if (r > 0 && r <= num_sms_all) g_sms_default[1] = r; }
     attr_set = true;
   }
   TcParams p;
@@ -623,7 +632,8 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   // wgrad-like problems are split along K; their tile count is multiplied by the split factor later, so only the un-split
   // (forward / dgrad) shapes are tuned for wave quantisation
   const bool will_split = (g.splitk == 0 && g.out_dtype == 0 && g.act == 0 && p.kb_total >= 16) || g.splitk > 1;
-  const int num_sms = will_split ? sms_split : sms_main;
+  const int budget = g_sms_budget[will_split ? 1 : 0];
+  const int num_sms = (budget > 0 && budget <= num_sms_all) ? budget : g_sms_default[will_split ? 1 : 0];
   // bf16 C through TMA: 16-byte aligned base / leading dimension / batch stride
   const bool can_tma_store = p.out_bf16 && !will_split && (g.ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 &&
                              (g.batch == 1 || (g.strideC % 8) == 0);

@@ -560,7 +560,7 @@ template <typename TX, typename TY>
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ mean,
                                                                    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                    const TY* __restrict__ residual, int act, const float* __restrict__ chan_scale, int rows_per_sample,
-                                                                   int M, int C, TY* __restrict__ gbuf, float* sum_g, float* sum_gx, int rows_per_block) {
+                                                                   int M, int C, TY* __restrict__ gbuf, float* sum_g, float* sum_gx, float* dbeta, float* dgamma, int rows_per_block) {
   pdl_sync();
   __shared__ float s1[BN_THREADS * 8];
   __shared__ float s2[BN_THREADS * 8];
@@ -608,6 +608,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const TY* __r
     for (int q = 0; q < rl_count; ++q) { d1 += s1[(q * nvec + v) * 8 + j]; d2 += s2[(q * nvec + v) * 8 + j]; }
     atomicAdd(sum_g + (v0 + v) * 8 + j, d1);
     atomicAdd(sum_gx + (v0 + v) * 8 + j, d2);
+    if (dbeta) atomicAdd(dbeta + (v0 + v) * 8 + j, d1);        // the local parameter gradients are these very sums (before any cross-rank reduction)
+    if (dgamma) atomicAdd(dgamma + (v0 + v) * 8 + j, d2);
   }
 }
 
@@ -793,11 +795,11 @@ extern "C" int dfb200_bn_apply(const void* x, int x_dtype, const float* mean, co
 
 extern "C" int dfb200_bn_bwd_reduce(const void* dy, int y_dtype, const void* x, int x_dtype, const float* mean, const float* invstd, const float* gamma,
                                     const float* beta, const void* residual, int act, const float* chan_scale, int rows_per_sample, int M, int C,
-                                    void* gbuf, float* sum_g, float* sum_gx, void* stream) {
+                                    void* gbuf, float* sum_g, float* sum_gx, float* dbeta, float* dgamma, void* stream) {
   DFB_REQUIRE(C % 8 == 0, "bn_bwd_reduce: C %% 8 != 0 (C=%d)", C);
   const int rpb = rows_per_block(M);
   dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(C / 8, BN_THREADS));
-#define L(TX, TY) dfb_launch(bn_bwd_reduce_kernel<TX, TY>, grid, BN_THREADS, 0, ST, (const TY*)dy, (const TX*)x, mean, invstd, gamma, beta, (const TY*)residual, act, chan_scale, rows_per_sample, M, C, (TY*)gbuf, sum_g, sum_gx, rpb)
+#define L(TX, TY) dfb_launch(bn_bwd_reduce_kernel<TX, TY>, grid, BN_THREADS, 0, ST, (const TY*)dy, (const TX*)x, mean, invstd, gamma, beta, (const TY*)residual, act, chan_scale, rows_per_sample, M, C, (TY*)gbuf, sum_g, sum_gx, dbeta, dgamma, rpb)
   if (x_dtype == 0 && y_dtype == 0) L(float, float);
   else if (x_dtype == 0 && y_dtype == 1) L(float, bf16);
   else if (x_dtype == 1 && y_dtype == 1) L(bf16, bf16);

@@ -108,9 +108,8 @@ def _lin_bn_folded(x, wb, bn: BNState, T, act=K.ACT_NONE, out_dtype=None):
 
 def _bn_bwd(dy, x2d, ms, bn: BNState, count, dx_dtype, dgamma, dbeta, act=K.ACT_NONE, residual=None, chan_scale=None, rows_per_sample=1):
     """returns (dx, g) with g = gradient w.r.t. the pre-activation (= gradient of the residual branch)."""
-    gbuf, sums = K.bn_bwd_reduce(dy, x2d, ms, bn.weight, bn.bias, residual, act, chan_scale, rows_per_sample)
-    K.axpy(sums[0], 1.0, dbeta)                                 # local parameter gradients (DP averages them later)
-    K.axpy(sums[1], 1.0, dgamma)
+    # local parameter gradients (DP averages them later) come out of the same pass as the two sums
+    gbuf, sums = K.bn_bwd_reduce(dy, x2d, ms, bn.weight, bn.bias, residual, act, chan_scale, rows_per_sample, dbeta=dbeta, dgamma=dgamma)
     if bn.sync:
         small_all_reduce_(sums, bn.sync_group if bn.sync_group is not True else None)
     dx = K.bn_bwd_apply(gbuf, x2d, ms, bn.weight, sums, count, bn.training, dx_dtype)

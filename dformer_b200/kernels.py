@@ -104,6 +104,11 @@ def gemm(a, b, *, trans_a=False, trans_b=True, bias=None, out=None, out_dtype=No
     return out
 
 
+def gemm_sm_budget(main_sms=0, split_sms=0):
+    """SMs the persistent GEMM grids may cover (0 = the in-step defaults; 148 = whole chip, for stand-alone timing)."""
+    lib().gemm_sm_budget(main_sms, split_sms)
+
+
 def bgemm(a, b, out, *, trans_a=False, trans_b=False, M, N, K, accumulate=False, alpha=0.0, splitk=1, backend=AUTO):
     """Strided-batched GEMM over the leading dimension of 3-D tensors: tcgen05 (3-D TMA maps) when both operands are
     bf16, otherwise the CUDA-core kernel."""
@@ -408,12 +413,13 @@ def bn_apply(x, ms, gamma, beta, out_dtype, residual=None, act=ACT_NONE, chan_sc
     return y
 
 
-def bn_bwd_reduce(dy, x, ms, gamma, beta, residual, act, chan_scale, rows_per_sample):
+def bn_bwd_reduce(dy, x, ms, gamma, beta, residual, act, chan_scale, rows_per_sample, dbeta=None, dgamma=None):
+    """dbeta / dgamma (optional): accumulate the local parameter gradients (= the two sums) in the same pass"""
     M, C = x.shape
     gbuf = torch.empty_like(dy)
     sums = torch.zeros((2, C), device=x.device, dtype=torch.float32)
     lib().bn_bwd_reduce(dy.data_ptr(), dt(dy), x.data_ptr(), dt(x), ms[0].data_ptr(), ms[1].data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                        _p(residual), act, _p(chan_scale), rows_per_sample, M, C, gbuf.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), _s())
+                        _p(residual), act, _p(chan_scale), rows_per_sample, M, C, gbuf.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), _p(dbeta), _p(dgamma), _s())
     return gbuf, sums
 
 

@@ -63,6 +63,10 @@ typedef struct dfb200_gemm_args {
   const float* ls; const float* scale_b; int rows_per_sample;
 } dfb200_gemm_args;
 int dfb200_gemm(const dfb200_gemm_args* args, void* stream);
+/* SMs the persistent tcgen05 GEMM grids may cover: `main_sms` for forward / dgrad problems, `split_sms` for split-K (weight-gradient)
+ * problems; 0 = the defaults (5/6 and 49 % of the chip, measured best inside the four-stream training step); the SM count = the whole
+ * chip (best for a GEMM running alone).  Process-wide, takes effect for the following launches. */
+int dfb200_gemm_sm_budget(int main_sms, int split_sms);
 
 /* column sums: out[n] (+)= sum_m X[m,n]  (bias gradients).  X is [M,N] with leading dimension ldx. */
 int dfb200_colsum(const void* X, int dtype, long ldx, int M, int N, float* out, int accumulate, void* stream);
@@ -207,7 +211,8 @@ int dfb200_bn_apply(const void* x, int x_dtype, const float* mean, const float* 
  *   dx = gamma*invstd*( g - sum_g/n - xhat*sum_gx/n )   (training)  or gamma*invstd*g (eval)          */
 int dfb200_bn_bwd_reduce(const void* dy, int y_dtype, const void* x, int x_dtype, const float* mean, const float* invstd,
                          const float* gamma, const float* beta, const void* residual, int act, const float* chan_scale,
-                         int rows_per_sample, int M, int C, void* gbuf, float* sum_g, float* sum_gx, void* stream);
+                         int rows_per_sample, int M, int C, void* gbuf, float* sum_g, float* sum_gx,
+                         float* dbeta /* optional: += sum_g (the bias gradient) */, float* dgamma /* optional: += sum_gx */, void* stream);
 int dfb200_bn_bwd_apply(const void* gbuf, int y_dtype, const void* x, int x_dtype, const float* mean, const float* invstd,
                         const float* gamma, const float* sum_g, const float* sum_gx, float count, int training, int M,
                         int C, void* dx, int dx_dtype, void* stream);
