@@ -12,60 +12,83 @@ namespace {
 __device__ __forceinline__ int win_start(int i, int n) { return (i * n) / 7; }
 __device__ __forceinline__ int win_end(int i, int n) { return ((i + 1) * n + 6) / 7; }
 
+// one CTA per (image, pooled cell): thread = (8-channel vector, pixel lane); the pixel lanes' partial sums meet in shared memory.
+// (One thread per output vector walked up to H/7 x W/7 pixels serially with 14 k threads in flight: latency-bound.)
 template <typename T>
-__global__ void pool7_fwd_kernel(const T* __restrict__ xn, int C1, const T* __restrict__ en, int C2, int B, int H, int W, T* __restrict__ out) {
+__global__ void __launch_bounds__(256) pool7_fwd_kernel(const T* __restrict__ xn, int C1, const T* __restrict__ en, int C2, int B, int H, int W,
+                                                        T* __restrict__ out) {
   pdl_sync();
+  extern __shared__ float psm[];                        // [lanes][nvec * 8]
   const int Ct = C1 + C2, nvec = Ct >> 3;
-  const long n = (long)B * 49 * nvec;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % nvec) * 8;
-    const int cell = (int)((i / nvec) % 49);
-    const int b = (int)(i / ((long)nvec * 49));
-    const int py = cell / 7, px = cell % 7;
-    const int y0 = win_start(py, H), y1 = win_end(py, H), x0 = win_start(px, W), x1 = win_end(px, W);
+  const int cell = blockIdx.x % 49, b = blockIdx.x / 49;
+  const int py = cell / 7, px = cell % 7;
+  const int y0 = win_start(py, H), y1 = win_end(py, H), x0 = win_start(px, W), x1 = win_end(px, W);
+  const int ww = x1 - x0, npix = (y1 - y0) * ww;
+  const int lanes = max(1, min((int)blockDim.x / nvec, npix));
+  const int t = threadIdx.x, v = t % nvec, lane = t / nvec;
+  if (lane < lanes && t < lanes * nvec) {
+    const int c = v * 8;
     const T* src; int Cs, cc;
     if (c < C1) { src = xn; Cs = C1; cc = c; } else { src = en; Cs = C2; cc = c - C1; }
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int y = y0; y < y1; ++y)
-      for (int x = x0; x < x1; ++x) {
-        float v[8];
-        Vec8<T>::load(src + (((long)b * H + y) * W + x) * Cs + cc, v);
+    for (int p = lane; p < npix; p += lanes) {
+      const int y = y0 + p / ww, x = x0 + p % ww;
+      float vv[8];
+      Vec8<T>::load(src + (((long)b * H + y) * W + x) * Cs + cc, vv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += v[j];
-      }
-    const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
+      for (int j = 0; j < 8; ++j) acc[j] += vv[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) psm[(lane * nvec + v) * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  for (int i = t; i < nvec; i += blockDim.x) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int l = 0; l < lanes; ++l)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += psm[(l * nvec + i) * 8 + j];
+    const float inv = 1.f / (float)npix;
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] *= inv;
-    Vec8<T>::store(out + ((long)b * 49 + cell) * Ct + c, acc);
+    Vec8<T>::store(out + ((long)b * 49 + cell) * Ct + i * 8, acc);
   }
 }
 
-// gather form: each pixel belongs to <= 2 x 2 (overlapping) windows
+// gather form: for maps of >= 7 rows / columns the cells that can contain coordinate v are floor(7 v / n) - 1 .. + 1
 template <typename T>
-__global__ void pool7_bwd_kernel(const T* __restrict__ dout, int C1, int C2, int B, int H, int W, T* __restrict__ dxn, T* __restrict__ den) {
+__global__ void __launch_bounds__(256) pool7_bwd_kernel(const T* __restrict__ dout, int C1, int C2, int B, int H, int W, T* __restrict__ dxn,
+                                                        T* __restrict__ den) {
   pdl_sync();
+  // one CTA per image row (b, y): the (at most three) pooled rows that contain y and their 1 / window-height are CTA constants,
+  // all index arithmetic is 32-bit
   const int Ct = C1 + C2, nvec = Ct >> 3;
-  const long n = (long)B * H * W * nvec;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % nvec) * 8;
-    const long pix = i / nvec;
-    const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long)W * H));
+  const int y = blockIdx.x % H, b = blockIdx.x / H;
+  const int pyc = (y * 7) / H;
+  // maps with fewer than 7 rows / columns repeat pixels over more than three cells: scan all seven there
+  const int py_lo = H >= 7 ? max(0, pyc - 1) : 0, py_hi = H >= 7 ? min(6, pyc + 1) : 6;
+  const T* drow = dout + (long)b * 49 * Ct;
+  const long rowbase = ((long)b * H + y) * W;
+  const int n = W * nvec;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int x = i / nvec, c = (i - x * nvec) * 8;
+    const int pxc = (x * 7) / W;
+    const int px_lo = W >= 7 ? max(0, pxc - 1) : 0, px_hi = W >= 7 ? min(6, pxc + 1) : 6;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int py = 0; py < 7; ++py) {
+    for (int py = py_lo; py <= py_hi; ++py) {
       const int y0 = win_start(py, H), y1 = win_end(py, H);
       if (y < y0 || y >= y1) continue;
-      for (int px = 0; px < 7; ++px) {
+      for (int px = px_lo; px <= px_hi; ++px) {
         const int x0 = win_start(px, W), x1 = win_end(px, W);
         if (x < x0 || x >= x1) continue;
         float v[8];
-        Vec8<T>::load(dout + ((long)b * 49 + py * 7 + px) * Ct + c, v);
+        Vec8<T>::load(drow + (py * 7 + px) * Ct + c, v);
         const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], inv, acc[j]);
       }
     }
-    if (c < C1) Vec8<T>::store(dxn + pix * C1 + c, acc);
-    else Vec8<T>::store(den + pix * C2 + (c - C1), acc);
+    if (c < C1) Vec8<T>::store(dxn + (rowbase + x) * C1 + c, acc);
+    else Vec8<T>::store(den + (rowbase + x) * C2 + (c - C1), acc);
   }
 }
 
@@ -230,14 +253,17 @@ __global__ void softmax_bwd_inplace_kernel(float* __restrict__ dP, const float* 
 extern "C" int dfb200_pool7_fwd(const void* xn, int C1, const void* en, int C2, int dtype, int B, int H, int W, void* out, void* stream) {
   DFB_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0, "pool7: channels must be multiples of 8");
   DFB_DISPATCH_DTYPE(dtype, T, {
-    dfb_launch(pool7_fwd_kernel<T>, ew_grid((long)B * 49 * (C1 + C2) / 8), 256, 0, ST, (const T*)xn, C1, (const T*)en, C2, B, H, W, (T*)out);
+    const int nvec = (C1 + C2) / 8;
+    DFB_REQUIRE(nvec <= 256, "pool7_fwd: %d channels exceed one CTA (2048)", C1 + C2);
+    const int lanes = 256 / nvec;
+    dfb_launch(pool7_fwd_kernel<T>, B * 49, 256, (size_t)lanes * nvec * 8 * sizeof(float), ST, (const T*)xn, C1, (const T*)en, C2, B, H, W, (T*)out);
   });
   return dfb_check_launch("pool7_fwd");
 }
 extern "C" int dfb200_pool7_bwd(const void* dout, int C1, int C2, int dtype, int B, int H, int W, void* dxn, void* den, void* stream) {
   DFB_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0, "pool7: channels must be multiples of 8");
   DFB_DISPATCH_DTYPE(dtype, T, {
-    dfb_launch(pool7_bwd_kernel<T>, ew_grid((long)B * H * W * (C1 + C2) / 8), 256, 0, ST, (const T*)dout, C1, C2, B, H, W, (T*)dxn, (T*)den);
+    dfb_launch(pool7_bwd_kernel<T>, B * H, 256, 0, ST, (const T*)dout, C1, C2, B, H, W, (T*)dxn, (T*)den);
   });
   return dfb_check_launch("pool7_bwd");
 }
