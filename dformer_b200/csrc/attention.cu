@@ -56,24 +56,19 @@ __global__ void __launch_bounds__(256) pool7_fwd_kernel(const T* __restrict__ xn
 
 // gather form: for maps of >= 7 rows / columns the cells that can contain coordinate v are floor(7 v / n) - 1 .. + 1
 template <typename T>
-__global__ void __launch_bounds__(256) pool7_bwd_kernel(const T* __restrict__ dout, int C1, int C2, int B, int H, int W, T* __restrict__ dxn,
-                                                        T* __restrict__ den) {
+__global__ void pool7_bwd_kernel(const T* __restrict__ dout, int C1, int C2, int B, int H, int W, T* __restrict__ dxn, T* __restrict__ den) {
   pdl_sync();
-  // one CTA per image row (b, y): the (at most three) pooled rows that contain y and their 1 / window-height are CTA constants,
-  // all index arithmetic is 32-bit
   const int Ct = C1 + C2, nvec = Ct >> 3;
-  const int y = blockIdx.x % H, b = blockIdx.x / H;
-  const int pyc = (y * 7) / H;
-  // maps with fewer than 7 rows / columns repeat pixels over more than three cells: scan all seven there
-  const int py_lo = H >= 7 ? max(0, pyc - 1) : 0, py_hi = H >= 7 ? min(6, pyc + 1) : 6;
-  const T* drow = dout + (long)b * 49 * Ct;
-  const long rowbase = ((long)b * H + y) * W;
-  const int n = W * nvec;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int x = i / nvec, c = (i - x * nvec) * 8;
-    const int pxc = (x * 7) / W;
-    const int px_lo = W >= 7 ? max(0, pxc - 1) : 0, px_hi = W >= 7 ? min(6, pxc + 1) : 6;
+  const unsigned n = (unsigned)B * H * W * nvec;           // 32-bit index arithmetic (the launcher checks the range)
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int c = (int)(i % nvec) * 8;
+    const unsigned pix = i / nvec;
+    const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((unsigned)W * H));
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int pyc = (y * 7) / H, pxc = (x * 7) / W;
+    // maps with fewer than 7 rows / columns repeat pixels over more than three cells: scan all seven there
+    const int py_lo = H >= 7 ? max(0, pyc - 1) : 0, py_hi = H >= 7 ? min(6, pyc + 1) : 6;
+    const int px_lo = W >= 7 ? max(0, pxc - 1) : 0, px_hi = W >= 7 ? min(6, pxc + 1) : 6;
     for (int py = py_lo; py <= py_hi; ++py) {
       const int y0 = win_start(py, H), y1 = win_end(py, H);
       if (y < y0 || y >= y1) continue;
@@ -81,14 +76,14 @@ __global__ void __launch_bounds__(256) pool7_bwd_kernel(const T* __restrict__ do
         const int x0 = win_start(px, W), x1 = win_end(px, W);
         if (x < x0 || x >= x1) continue;
         float v[8];
-        Vec8<T>::load(drow + (py * 7 + px) * Ct + c, v);
+        Vec8<T>::load(dout + ((long)b * 49 + py * 7 + px) * Ct + c, v);
         const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], inv, acc[j]);
       }
     }
-    if (c < C1) Vec8<T>::store(dxn + (rowbase + x) * C1 + c, acc);
-    else Vec8<T>::store(den + (rowbase + x) * C2 + (c - C1), acc);
+    if (c < C1) Vec8<T>::store(dxn + (long)pix * C1 + c, acc);
+    else Vec8<T>::store(den + (long)pix * C2 + (c - C1), acc);
   }
 }
 
@@ -106,15 +101,15 @@ __device__ __forceinline__ Lerp lerp_coord(int o, int n_in, int n_out) {
   return l;
 }
 
-template <typename TI, typename TO>
+template <typename TI, typename TO, typename IT>          // IT: 32-bit index arithmetic whenever the element count allows it
 __global__ void resize_fwd_kernel(const TI* __restrict__ in, int B, int Hi, int Wi, int C, TO* __restrict__ out, int Ho, int Wo, long ldo, int col0) {
   pdl_sync();
   const int nvec = C >> 3;
-  const long n = (long)B * Ho * Wo * nvec;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+  const IT n = (IT)B * Ho * Wo * nvec;
+  for (IT i = blockIdx.x * (IT)blockDim.x + threadIdx.x; i < n; i += (IT)gridDim.x * blockDim.x) {
     const int c = (int)(i % nvec) * 8;
-    const long pix = i / nvec;
-    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long)Wo * Ho));
+    const IT pix = i / nvec;
+    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((IT)Wo * Ho));
     const Lerp ly = lerp_coord(oy, Hi, Ho), lx = lerp_coord(ox, Wi, Wo);
     const TI* base = in + (long)b * Hi * Wi * C + c;
     float v00[8], v01[8], v10[8], v11[8], o[8];
@@ -128,7 +123,7 @@ __global__ void resize_fwd_kernel(const TI* __restrict__ in, int B, int Hi, int 
       const float bot = (1.f - lx.w1) * v10[j] + lx.w1 * v11[j];
       o[j] = (1.f - ly.w1) * top + ly.w1 * bot;
     }
-    Vec8<TO>::store(out + pix * ldo + col0 + c, o);
+    Vec8<TO>::store(out + (long)pix * ldo + col0 + c, o);
   }
 }
 
@@ -263,7 +258,8 @@ extern "C" int dfb200_pool7_fwd(const void* xn, int C1, const void* en, int C2, 
 extern "C" int dfb200_pool7_bwd(const void* dout, int C1, int C2, int dtype, int B, int H, int W, void* dxn, void* den, void* stream) {
   DFB_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0, "pool7: channels must be multiples of 8");
   DFB_DISPATCH_DTYPE(dtype, T, {
-    dfb_launch(pool7_bwd_kernel<T>, B * H, 256, 0, ST, (const T*)dout, C1, C2, B, H, W, (T*)dxn, (T*)den);
+    DFB_REQUIRE((long)B * H * W * (C1 + C2) / 8 < (1L << 31), "pool7_bwd: problem too large for 32-bit indexing");
+    dfb_launch(pool7_bwd_kernel<T>, ew_grid((long)B * H * W * (C1 + C2) / 8), 256, 0, ST, (const T*)dout, C1, C2, B, H, W, (T*)dxn, (T*)den);
   });
   return dfb_check_launch("pool7_bwd");
 }
@@ -271,8 +267,10 @@ extern "C" int dfb200_pool7_bwd(const void* dout, int C1, int C2, int dtype, int
 extern "C" int dfb200_resize_fwd(const void* in, int in_dtype, int B, int Hi, int Wi, int C, void* out, int out_dtype, int Ho, int Wo, long ldo, int col0,
                                  void* stream) {
   DFB_REQUIRE(C % 8 == 0 && ldo % 8 == 0 && col0 % 8 == 0, "resize: C, ldo, col0 must be multiples of 8");
-  const int g = ew_grid((long)B * Ho * Wo * C / 8);
-#define L(TI, TO) dfb_launch(resize_fwd_kernel<TI, TO>, g, 256, 0, ST, (const TI*)in, B, Hi, Wi, C, (TO*)out, Ho, Wo, ldo, col0)
+  const long nfw = (long)B * Ho * Wo * C / 8;
+  const int g = ew_grid(nfw);
+#define L(TI, TO) do { if (nfw < (1L << 30)) dfb_launch(resize_fwd_kernel<TI, TO, unsigned>, g, 256, 0, ST, (const TI*)in, B, Hi, Wi, C, (TO*)out, Ho, Wo, ldo, col0); \
+                       else dfb_launch(resize_fwd_kernel<TI, TO, long>, g, 256, 0, ST, (const TI*)in, B, Hi, Wi, C, (TO*)out, Ho, Wo, ldo, col0); } while (0)
   if (in_dtype == 0 && out_dtype == 0) L(float, float);
   else if (in_dtype == 0 && out_dtype == 1) L(float, bf16);
   else if (in_dtype == 1 && out_dtype == 1) L(bf16, bf16);
