@@ -484,6 +484,22 @@ def _nmf_fwd(x, bases_raw, steps, T, side=None):
         if ev is not None:
             main.wait_event(ev)
 
+    # split-K products accumulate with fp32 reductions into zeroed outputs: ONE zero-filled pool per call (one memset node) instead of
+    # one memset in front of every such GEMM of the latency-bound chain
+    zpool = torch.zeros(max(1, steps) * (B * D * R + B * R * R), device=dev, dtype=F32) if sk > 1 else None
+    zoff = [0]
+
+    def fz(*shape):
+        if zpool is None:
+            return f(*shape)
+        n = 1
+        for d in shape:
+            n *= d
+        v = zpool[zoff[0]:zoff[0] + n].view(*shape)
+        zoff[0] += n
+        return v
+
+    acc_z = zpool is not None                                   # accumulate into the pre-zeroed view (no memset launched by the GEMM)
     bases, _ = K.normalize_cols(bases_raw)
     bases_l = lo(bases)
     S = K.bgemm(x, bases_l, f(B, N, R), M=N, N=R, K=D)
@@ -503,8 +519,9 @@ def _nmf_fwd(x, bases_raw, steps, T, side=None):
 
     for _ in range(steps):
         coef_n, coef_nl, rec_c = coef_update(coef, coef_l, bases, bases_l)
-        ctc_l, ev = on_side(lambda: lo(K.bgemm(coef_nl, coef_nl, f(B, R, R), trans_a=True, M=R, N=R, K=N, splitk=sk)))
-        num2 = K.bgemm(x, coef_nl, f(B, D, R), trans_a=True, M=D, N=R, K=N, splitk=sk)
+        ctc_buf, num2_buf = fz(B, R, R), fz(B, D, R)
+        ctc_l, ev = on_side(lambda: lo(K.bgemm(coef_nl, coef_nl, ctc_buf, trans_a=True, M=R, N=R, K=N, splitk=sk, accumulate=acc_z)))
+        num2 = K.bgemm(x, coef_nl, num2_buf, trans_a=True, M=D, N=R, K=N, splitk=sk, accumulate=acc_z)
         wait(ev)
         den2 = K.bgemm(bases_l, ctc_l, f(B, D, R), M=D, N=R, K=R)
         bases_n, bases_nl = K.mu_update(bases, num2, den2, lo_dtype=T)
@@ -563,9 +580,24 @@ def _nmf_bwd(dout, x, saved, T, side=None):
         return av, bv
 
     sk = max(1, N // 512)
+    # one zero-filled pool for the split-K outputs of the chain (see _nmf_fwd)
+    zpool = torch.zeros(B * D * R + (len(tape) + 1) * B * R * R, device=dev, dtype=F32) if sk > 1 else None
+    zoff = [0]
+
+    def fz(*shape):
+        if zpool is None:
+            return f(*shape)
+        n = 1
+        for d in shape:
+            n *= d
+        v = zpool[zoff[0]:zoff[0] + n].view(*shape)
+        zoff[0] += n
+        return v
+
+    acc_z = zpool is not None
     # out = coef_f @ bases^T
     dcoef = K.bgemm(dout, bases_Tl, f(B, N, R), M=N, N=R, K=D)
-    dbases = K.bgemm(dout, coef_fl, f(B, D, R), trans_a=True, M=D, N=R, K=N, splitk=sk)
+    dbases = K.bgemm(dout, coef_fl, fz(B, D, R), trans_a=True, M=D, N=R, K=N, splitk=sk, accumulate=acc_z)
 
     def coef_update_bwd(dcoef_new, rec, dbases):
         coef, coef_l, num, den, bases_l, btb_l = rec
@@ -573,7 +605,8 @@ def _nmf_bwd(dout, x, saved, T, side=None):
         dnum_l, _ = push(None, bases_l)                                                     # num = x @ bases
         dden_l = K.mu_update_bwd(dcoef_new, coef, num, den, dco, False, dnum_l, T)
         # BtB = bases^T bases: d(BtB) = coef^T dden, symmetrised, on the side stream
-        dbtb_s, ev = on_side(lambda: K.sym_cast(K.bgemm(coef_l, dden_l, f(B, R, R), trans_a=True, M=R, N=R, K=N, splitk=sk), T))
+        dbtb_buf = fz(B, R, R)
+        dbtb_s, ev = on_side(lambda: K.sym_cast(K.bgemm(coef_l, dden_l, dbtb_buf, trans_a=True, M=R, N=R, K=N, splitk=sk, accumulate=acc_z), T))
         K.bgemm(x, dnum_l, dbases, trans_a=True, M=D, N=R, K=N, accumulate=True, splitk=sk)
         K.bgemm(dden_l, btb_l, dco, M=N, N=R, K=R, accumulate=True)                         # den = coef @ BtB (BtB symmetric)
         wait(ev)
