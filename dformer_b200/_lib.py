@@ -69,7 +69,7 @@ SIGNATURES = {
     "dfb200_bn_finalize": [P, P, D, F, F, I, P, P, P, P, P],
     "dfb200_bn_eval_stats": [P, P, F, I, P, P, P],
     "dfb200_bn_apply": [P, I, P, P, P, P, P, I, P, I, I, I, P, I, P],
-    "dfb200_bn_bwd_reduce": [P, I, P, I, P, P, P, P, P, I, P, I, I, I, P, P, P, P, P, P],
+    "dfb200_bn_bwd_reduce": [P, P, I, P, I, P, P, P, P, P, I, P, I, I, I, P, P, P, P, P, P],
     "dfb200_bn_bwd_apply": [P, I, P, I, P, P, P, P, P, F, I, I, I, P, I, P],
     "dfb200_bn_fold": [P, I, I, I, L, P, P, P, F, P, P, P, P],
     "dfb200_normalize_cols": [P, I, I, I, P, P, P],

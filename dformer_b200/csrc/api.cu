@@ -44,6 +44,6 @@ extern "C" int dfb200_gemm(const dfb200_gemm_args* a, void* stream) {
   if (a->M <= 0 || a->N <= 0) return DFB_OK;
   if (a->backend == DFB200_BACKEND_TCGEN05) return dfb_gemm_tc(*a, st);
   if (a->backend == DFB200_BACKEND_AUTO && dfb_gemm_tc_supported(*a)) return dfb_gemm_tc(*a, st);
-  if (a->epi_mode != 0) { dfb_set_error("gemm: epi_mode %d is reserved (must be 0)", a->epi_mode); return DFB_ERR_UNSUPPORTED; }
+  if (a->epi_mode != 0) { dfb_set_error("gemm: fused epilogue %d needs the tcgen05 backend (bf16 operands and output, aligned C / aux / out2)", a->epi_mode); return DFB_ERR_UNSUPPORTED; }
   return dfb_gemm_simt(*a, st);
 }

@@ -89,7 +89,16 @@ __global__ void pack_params_kernel(const dfb200_pack_entry* __restrict__ table, 
   pdl_sync();
   const dfb200_pack_entry e = table[blockIdx.y];
   T* dst = reinterpret_cast<T*>(e.dst);
-  if (e.kind == 0) {
+  if (e.kind == 0 && e.cols == e.dst_ld && (((long)e.rows * e.cols) & 7) == 0 &&
+      ((reinterpret_cast<uintptr_t>(e.src) | reinterpret_cast<uintptr_t>(e.dst)) & 15) == 0) {
+    // unpadded rows: a flat cast, eight elements per thread and iteration (two 16-byte loads, one or two 16-byte stores)
+    const unsigned nv = (unsigned)(((long)e.rows * e.cols) >> 3);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) {
+      float v[8];
+      Vec8<float>::load(e.src + (size_t)i * 8, v);
+      Vec8<T>::store(dst + (size_t)i * 8, v);
+    }
+  } else if (e.kind == 0) {
     const long n = (long)e.rows * e.cols;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
       const int r = (int)(i / e.cols), c = (int)(i % e.cols);
@@ -457,7 +466,7 @@ extern "C" int dfb200_colsum(const void* X, int dtype, long ldx, int M, int N, f
 extern "C" int dfb200_pack_params(const dfb200_pack_entry* table_dev, int n_entries, int max_elems, int dst_dtype, void* stream) {
   if (n_entries <= 0) return DFB_OK;
   DFB_REQUIRE(n_entries <= 65535, "pack_params: too many entries (%d)", n_entries);
-  int gx = dfb_cdiv(max_elems, EW_THREADS * 4);
+  int gx = dfb_cdiv(max_elems, EW_THREADS * 16);
   if (gx < 1) gx = 1;
   if (gx > 64) gx = 64;
   dim3 grid(gx, n_entries);

@@ -44,6 +44,9 @@ struct TcParams {
   int out_bf16, act, act_col_start, accumulate;
   int acc_stages, acc_stride, tmem_cols;     // accumulator ring in tensor memory: 1 or 2 stages, `acc_stride` columns apart
   int tma_store;                             // bf16 C written by cp.async.bulk.tensor (tmC valid)
+  // fused epilogue (TMA-store path only), see dfb200.h:
+  //   1 "gate": C = (acc + bias) * aux (bf16 [M, N], leading dimension ld_aux); second output (optional) = acc + bias
+  int epi_mode, has_out2;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -124,6 +127,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, bool mn_major
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
 }
 
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void sts128(uint32_t saddr, const uint32_t* w) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
 }
@@ -181,28 +189,47 @@ __device__ __noinline__ void epilogue_generic(const TcParams& p, float* v, int r
   }
 }
 
-// bias (first split only) and activation (columns >= act_col_start) on one 32-column accumulator chunk held in registers
-__device__ __forceinline__ void bias_act(const TcParams& p, float* v, int col0, int ncols, bool add_bias) {
-  if (add_bias) {
-    const float* bp = p.bias + col0;
-    if (ncols == 32 && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
+// bias (first split only) on one 32-column accumulator chunk held in registers
+__device__ __forceinline__ void add_bias_chunk(const TcParams& p, float* v, int col0, int ncols) {
+  const float* bp = p.bias + col0;
+  if (ncols == 32 && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + j));
-        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) v[j] += __ldg(bp + j);
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + j));
+      v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
     }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols) v[j] += __ldg(bp + j);
   }
+}
+// activation on the columns >= act_col_start
+__device__ __forceinline__ void act_chunk(const TcParams& p, float* v, int col0) {
   if (p.act == 1) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = (col0 + j >= p.act_col_start) ? gelu_f(v[j]) : v[j];
   } else if (p.act == 2) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = (col0 + j >= p.act_col_start) ? fmaxf(v[j], 0.f) : v[j];
+  }
+}
+__device__ __forceinline__ void bias_act(const TcParams& p, float* v, int col0, int ncols, bool add_bias) {
+  if (add_bias) add_bias_chunk(p, v, col0, ncols);
+  act_chunk(p, v, col0);
+}
+// 32 fp32 values of row `lane` -> bf16 -> half `h` of the warp's [32 rows x 128 B] staging tile in the 128-byte swizzle pattern
+// (the row's eight 16-byte chunks land at chunk ^ (row & 7): conflict-free, and what the TMA store expects)
+__device__ __forceinline__ void stage_half(uint32_t sbase, int lane, int h, const float* v) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[u * 8 + 2 * q], v[u * 8 + 2 * q + 1]);
+      w[q] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    sts128(sbase + (uint32_t)(lane * 8 + ((h * 4 + u) ^ (lane & 7))) * 16u, w);
   }
 }
 
@@ -214,15 +241,19 @@ __device__ __forceinline__ void bias_act(const TcParams& p, float* v, int col0, 
 //                weight-gradient) overlap one CTA's load phase with the other's epilogue.
 template <int EPI_WARPS>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, EPI_WARPS == 4 ? 2 : 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmE, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_stage = smem + p.stages * p.stage_bytes;                 // EPI_WARPS x [32 rows x 128 B], 1024-byte aligned (128-byte swizzle atom)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_WARPS * EPI_WARP_BYTES);
+  uint8_t* epi_stage2 = epi_stage + EPI_WARPS * EPI_WARP_BYTES;         // second output's staging tiles (present when has_out2)
+  uint8_t* epi_aux = epi_stage2 + (p.has_out2 ? EPI_WARPS * EPI_WARP_BYTES : 0);     // gate tiles (present in gate mode), TMA-loaded per box
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_aux + (p.epi_mode == 1 ? EPI_WARPS * EPI_WARP_BYTES : 0));
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* aux_bar = tmem_empty + 2;           // [EPI_WARPS]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(aux_bar + EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_mn = p.m_tiles * p.n_tiles;
@@ -232,6 +263,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    if (p.has_out2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
+    if (p.epi_mode == 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmE) : "memory");
+    for (int s = 0; s < EPI_WARPS; ++s) mbar_init(&aux_bar[s], 1);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -261,6 +295,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n_blk = tile % p.n_tiles, m_blk = (tile / p.n_tiles) % p.m_tiles;
         const int sp = (tile / tiles_mn) % p.splits, bz = tile / (tiles_mn * p.splits);
         const int kb0 = sp * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int ncol0 = n_blk * p.BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * p.stage_bytes;
@@ -272,9 +307,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_3d(&tmA, &full_bar[stage], sa, kb * BK, m_blk * BM, bz);
           }
           if (p.b_mn_major) {
-            for (int i = 0; i < b_boxes; ++i) tma_load_3d(&tmB, &full_bar[stage], sb + i * 8192, n_blk * p.BN + i * 64, kb * BK, bz);
+            for (int i = 0; i < b_boxes; ++i) tma_load_3d(&tmB, &full_bar[stage], sb + i * 8192, ncol0 + i * 64, kb * BK, bz);
           } else {
-            tma_load_3d(&tmB, &full_bar[stage], sb, kb * BK, n_blk * p.BN, bz);
+            tma_load_3d(&tmB, &full_bar[stage], sb, kb * BK, ncol0, bz);
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -323,18 +358,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quad = warp & 3;
     const int part = (warp - 2) >> 2;
     const uint32_t sbase = smem_u32(epi_stage + (warp - 2) * EPI_WARP_BYTES);
+    const uint32_t sbase2 = smem_u32(epi_stage2 + (warp - 2) * EPI_WARP_BYTES);
+    const uint32_t sbase_aux = smem_u32(epi_aux + (warp - 2) * EPI_WARP_BYTES);
+    uint64_t* my_aux_bar = &aux_bar[warp - 2];
+    uint32_t aux_phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     bool store_pending = false;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.n_tiles, m_blk = (tile / p.n_tiles) % p.m_tiles;
       const int bz = tile / (tiles_mn * p.splits);
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       const int row = m_blk * BM + quad * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.acc_stride);
       const bool row_ok = row < p.M;
       const bool add_bias = p.bias != nullptr && (p.splits == 1 || ((tile / tiles_mn) % p.splits) == 0);
-      const int tn = min(p.BN, p.N - n_blk * p.BN);                 // valid columns of this tile
+      const int ncol0 = n_blk * p.BN;
+      const int tn = min(p.BN, p.N - ncol0);                        // valid columns of this tile
       if (p.tma_store) {
         // ---- bf16 output through TMA: 64-column boxes, [32 rows x 128 B] staged in the 128-byte swizzle pattern (lane = row writes
         // its eight 16-byte chunks at chunk ^ (row & 7): conflict-free), one cp.async.bulk.tensor store per box; rows >= M and
@@ -342,7 +380,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int nboxes = (tn + 63) >> 6;
         const int b_begin = (PARTS == 1 || part == 0) ? 0 : (nboxes + 1) >> 1;
         const int b_end = PARTS == 1 ? nboxes : (part == 0 ? (nboxes + 1) >> 1 : nboxes);
+        // gate: the [32 rows x 64 columns] gate tile of a box is TMA-loaded into this warp's aux buffer (same swizzled layout as the
+        // staging tile).  It does not depend on the accumulator: the first box's load is issued before waiting for the MMAs of the
+        // tile, the next box's as soon as the current one has been consumed.
+        auto load_gate = [&](int box) {
+          if (p.epi_mode == 1 && box < b_end && lane == 0) {
+            mbar_expect_tx(my_aux_bar, EPI_WARP_BYTES);
+            tma_load_3d(&tmE, my_aux_bar, epi_aux + (warp - 2) * EPI_WARP_BYTES, ncol0 + box * 64, m_blk * BM + quad * 32, bz);
+          }
+        };
+        load_gate(b_begin);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
         for (int box = b_begin; box < b_end; ++box) {
+          const int cb = ncol0 + box * 64;                            // first global column of this box
+          const bool sec = p.has_out2 != 0;                           // gate mode keeps acc + bias as a second output
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int c0 = box * 64 + h * 32;
@@ -350,38 +402,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             tmem_ld32(t_row + (uint32_t)c0, r);
             tmem_ld_wait();
-            if (h == 0 && store_pending) {          // the previous box of this warp must have left the staging tile
+            if (h == 0 && store_pending) {          // the previous box of this warp must have left the staging tile(s)
               if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
               __syncwarp();
             }
-            const int col0 = n_blk * p.BN + c0;
+            const int col0 = ncol0 + c0;
             const int ncols = min(32, p.N - col0);
             if (ncols <= 0) continue;
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             bias_act(p, v, col0, ncols, add_bias);
+            if (p.epi_mode == 1) {
+              // ---- gate: second output keeps acc + bias (needed by the backward pass), C = (acc + bias) * aux
+              if (sec) stage_half(sbase2, lane, h, v);
+              if (h == 0) { mbar_wait(my_aux_bar, aux_phase); aux_phase ^= 1; }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              uint32_t w[4];
+              for (int u = 0; u < 4; ++u) {          // out-of-range rows / columns were zero-filled by the load and are clipped by the store
+                float g8[8];
+                Vec8<bf16>::unpack(lds128(sbase_aux + (uint32_t)(lane * 8 + ((h * 4 + u) ^ (lane & 7))) * 16u), g8);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[u * 8 + 2 * q], v[u * 8 + 2 * q + 1]);
-                w[q] = *reinterpret_cast<const uint32_t*>(&h2);
+                for (int j = 0; j < 8; ++j) v[u * 8 + j] *= g8[j];
               }
-              sts128(sbase + (uint32_t)(lane * 8 + ((h * 4 + u) ^ (lane & 7))) * 16u, w);
             }
+            stage_half(sbase, lane, h, v);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
+          load_gate(box + 1);
           if (lane == 0) {
             asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                         ::"l"(&tmC), "r"(sbase), "r"(n_blk * p.BN + box * 64), "r"(m_blk * BM + quad * 32), "r"(bz) : "memory");
+                         ::"l"(&tmC), "r"(sbase), "r"(cb), "r"(m_blk * BM + quad * 32), "r"(bz) : "memory");
+            if (sec)
+              asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                           ::"l"(&tmD), "r"(sbase2), "r"(cb), "r"(m_blk * BM + quad * 32), "r"(bz) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           store_pending = true;
         }
       } else {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
         const long c_off = (long)bz * p.strideC;
         const int chunks = (tn + 31) >> 5;
         const int c_begin = (PARTS == 1 || part == 0) ? 0 : (chunks + 1) >> 1;
@@ -392,7 +453,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();                             // tcgen05.ld is warp-collective: reconverge after the per-row predicated stores
           tmem_ld32(t_row + (uint32_t)c0, r);
           tmem_ld_wait();
-          const int col0 = n_blk * p.BN + c0;
+          const int col0 = ncol0 + c0;
           const int ncols = min(32, tn - c0);
           if (!row_ok) continue;
           float v[32];
@@ -586,7 +647,13 @@ bool dfb_gemm_tc_supported(const dfb200_gemm_args& g) {
   if ((g.lda % 8) || (g.ldb % 8)) return false;
   if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) return false;
   if (g.accumulate && g.out_dtype != 0) return false;
-  if (g.epi_mode != 0) return false;           // reserved (the fused gelu'/residual epilogues of round 1 were measured slower and removed)
+  if (g.epi_mode != 0) {                       // fused "gate" epilogue: bf16 output through the TMA-store path only
+    if (g.epi_mode != 1) return false;
+    if (g.batch != 1 || g.out_dtype != 1 || g.accumulate || g.splitk > 1) return false;
+    if ((g.ldc % 8) || (reinterpret_cast<uintptr_t>(g.C) & 15)) return false;
+    if (g.out2 && ((g.ld_out2 % 8) || (reinterpret_cast<uintptr_t>(g.out2) & 15))) return false;
+    if (!g.aux || (g.ld_aux % 8) || (reinterpret_cast<uintptr_t>(g.aux) & 15) || (g.N % 8)) return false;
+  }
   return true;
 }
 
@@ -629,6 +696,7 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   p.C = g.C; p.ldc = g.ldc; p.bias = g.bias;
   p.batch = g.batch; p.strideC = g.strideC;
   p.out_bf16 = g.out_dtype == 1; p.act = g.act; p.act_col_start = g.act_col_start; p.accumulate = g.accumulate;
+  p.epi_mode = g.epi_mode; p.has_out2 = (g.epi_mode != 0 && g.out2) ? 1 : 0;
   // wgrad-like problems are split along K; their tile count is multiplied by the split factor later, so only the un-split
   // (forward / dgrad) shapes are tuned for wave quantisation
   const bool will_split = (g.splitk == 0 && g.out_dtype == 0 && g.act == 0 && p.kb_total >= 16) || g.splitk > 1;
@@ -673,7 +741,8 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
       if (e != cudaSuccess) { dfb_set_error("memset2d: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
     }
   }
-  CUtensorMap tmA, tmB, tmC;
+  DFB_REQUIRE(p.epi_mode == 0 || p.tma_store, "gemm_tc: fused epilogue %d needs the TMA-store path (BN %d, N %d)", p.epi_mode, p.BN, g.N);
+  CUtensorMap tmA, tmB, tmC, tmD, tmE;
   int rc;
   const long sA = g.batch > 1 ? g.strideA : (long)g.lda * (g.transA ? g.K : g.M);
   const long sB = g.batch > 1 ? g.strideB : (long)g.ldb * (g.transB ? g.N : g.K);
@@ -689,6 +758,18 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   } else {
     tmC = tmA;                                  // unused by the kernel
   }
+  if (p.has_out2) {
+    rc = make_map(&tmD, g.out2, g.N, g.M, g.ld_out2, 64, 32, 1, (long)g.ld_out2 * g.M);
+    if (rc) return rc;
+  } else {
+    tmD = tmA;                                  // unused by the kernel
+  }
+  if (p.epi_mode == 1) {
+    rc = make_map(&tmE, g.aux, g.N, g.M, g.ld_aux, 64, 32, 1, (long)g.ld_aux * g.M);
+    if (rc) return rc;
+  } else {
+    tmE = tmA;                                  // unused by the kernel
+  }
   const long total = tiles * p.splits;
   const int grid = (int)min((long)num_sms * ctas_per_sm, total);
   // accumulator ring in tensor memory: stages `acc_stride` columns apart (64-column granules: the TMA-store epilogue reads whole boxes)
@@ -699,7 +780,7 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   // pipeline depth: as deep as the variant's shared-memory budget allows, but no deeper than the k-blocks this CTA will ever load
   const int b_bytes = p.b_mn_major ? ((p.BN + 63) / 64) * 8192 : ((p.BN * 128 + 1023) / 1024) * 1024;   // 1024-B aligned (swizzle atom)
   p.stage_bytes = A_STAGE_BYTES + b_bytes;
-  const int fixed = epi_warps * EPI_WARP_BYTES + 1024 + 512;
+  const int fixed = epi_warps * EPI_WARP_BYTES * (1 + (p.has_out2 ? 1 : 0) + (p.epi_mode == 1 ? 1 : 0)) + 1024 + 512;
   p.stages = ((epi_warps == 4 ? SMALL_SMEM : MAX_SMEM) - fixed) / p.stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   const long kb_per_cta = (long)dfb_cdiv(total, grid) * p.kb_per_split;
@@ -707,7 +788,7 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   if (forced_stages > 0 && forced_stages < p.stages) p.stages = forced_stages;
   DFB_REQUIRE(p.stages >= 1, "gemm_tc: tile %d x %d does not fit the shared-memory budget", BM, p.BN);
   const int smem_bytes = p.stages * p.stage_bytes + fixed;
-  if (epi_warps == 4) dfb_launch(gemm_tc_kernel<4>, grid, 64 + 32 * 4, smem_bytes, st, tmA, tmB, tmC, p);
-  else dfb_launch(gemm_tc_kernel<8>, grid, 64 + 32 * 8, smem_bytes, st, tmA, tmB, tmC, p);
+  if (epi_warps == 4) dfb_launch(gemm_tc_kernel<4>, grid, 64 + 32 * 4, smem_bytes, st, tmA, tmB, tmC, tmD, tmE, p);
+  else dfb_launch(gemm_tc_kernel<8>, grid, 64 + 32 * 8, smem_bytes, st, tmA, tmB, tmC, tmD, tmE, p);
   return dfb_check_launch("gemm_tc");
 }

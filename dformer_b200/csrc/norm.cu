@@ -469,9 +469,21 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T* __restric
   const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
   if (t < active) {
     const int cv = t % nvec, rl = t / nvec;
-    for (int r = r0 + rl; r < r1; r += rl_count) {
+    const T* xp = x + (v0 + cv) * 8;
+    int r = r0 + rl;
+    // four rows in flight per thread: the loop is a dependent chain of DRAM latencies otherwise (one 16-byte load per ~0.8 us)
+    for (; r + 3 * rl_count < r1; r += 4 * rl_count) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) Vec8<T>::load(xp + (long)(r + u * rl_count) * C, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a1[j] += v[u][j]; a2[j] = fmaf(v[u][j], v[u][j], a2[j]); }
+    }
+    for (; r < r1; r += rl_count) {
       float v[8];
-      Vec8<T>::load(x + (long)r * C + (v0 + cv) * 8, v);
+      Vec8<T>::load(xp + (long)r * C, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { a1[j] += v[j]; a2[j] = fmaf(v[j], v[j], a2[j]); }
     }
@@ -538,11 +550,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const TX* __restri
     sh[j] = fmaf(-mean[c + j], sc[j], beta[c + j]);
   }
   const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
-  for (int r = r0 + rl; r < r1; r += rl_count) {
+  auto finish = [&](int r, float* v, const float* res) {
     const long off = (long)r * C + c;
-    float v[8], res[8];
-    Vec8<TX>::load(x + off, v);
-    if (residual) Vec8<TY>::load(residual + off, res);
     const float* cs = chan_scale ? chan_scale + (long)(r / rows_per_sample) * C + c : nullptr;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -553,11 +562,27 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const TX* __restri
       v[j] = z;
     }
     Vec8<TY>::store(y + off, v);
+  };
+  int r = r0 + rl;
+  for (; r + rl_count < r1; r += 2 * rl_count) {          // two rows in flight per thread
+    const long offa = (long)r * C + c, offb = (long)(r + rl_count) * C + c;
+    float va[8], vb[8], ra[8], rb[8];
+    Vec8<TX>::load(x + offa, va);
+    Vec8<TX>::load(x + offb, vb);
+    if (residual) { Vec8<TY>::load(residual + offa, ra); Vec8<TY>::load(residual + offb, rb); }
+    finish(r, va, ra);
+    finish(r + rl_count, vb, rb);
+  }
+  if (r < r1) {
+    float v[8], res[8];
+    Vec8<TX>::load(x + (long)r * C + c, v);
+    if (residual) Vec8<TY>::load(residual + (long)r * C + c, res);
+    finish(r, v, res);
   }
 }
 
 template <typename TX, typename TY>
-__global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ mean,
+__global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_reduce_kernel(const TY* __restrict__ dy, const TY* __restrict__ dy2, const TX* __restrict__ x, const float* __restrict__ mean,
                                                                    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                    const TY* __restrict__ residual, int act, const float* __restrict__ chan_scale, int rows_per_sample,
                                                                    int M, int C, TY* __restrict__ gbuf, float* sum_g, float* sum_gx, float* dbeta, float* dgamma, int rows_per_block) {
@@ -576,16 +601,13 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const TY* __r
     float mu[8], is[8], ga[8], be[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { mu[j] = mean[c + j]; is[j] = invstd[c + j]; ga[j] = gamma[c + j]; be[j] = beta[c + j]; }
-    for (int r = r0 + rl; r < r1; r += rl_count) {
+    auto finish = [&](int r, const float* xv, float* g, const float* g2, const float* res) {
       const long off = (long)r * C + c;
-      float xv[8], g[8], res[8];
-      Vec8<TX>::load(x + off, xv);
-      Vec8<TY>::load(dy + off, g);
-      if (residual) Vec8<TY>::load(residual + off, res);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float xh = (xv[j] - mu[j]) * is[j];
         float gj = g[j];
+        if (dy2) gj += g2[j];                                   // gradient fan-in (residual branch): summed here instead of in an axpy pass
         if (chan_scale) gj *= chan_scale[(r / rows_per_sample) * C + c + j];
         if (act) {
           float z = xh * ga[j] + be[j];
@@ -597,6 +619,28 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const TY* __r
         a2[j] = fmaf(gj, xh, a2[j]);
       }
       Vec8<TY>::store(gbuf + off, g);
+    };
+    int r = r0 + rl;
+    for (; r + rl_count < r1; r += 2 * rl_count) {        // two rows in flight per thread
+      const long offa = (long)r * C + c, offb = (long)(r + rl_count) * C + c;
+      float xa[8], xb[8], ga_[8], gb_[8], ha[8], hb[8], ra[8], rb[8];
+      Vec8<TX>::load(x + offa, xa);
+      Vec8<TY>::load(dy + offa, ga_);
+      Vec8<TX>::load(x + offb, xb);
+      Vec8<TY>::load(dy + offb, gb_);
+      if (dy2) { Vec8<TY>::load(dy2 + offa, ha); Vec8<TY>::load(dy2 + offb, hb); }
+      if (residual) { Vec8<TY>::load(residual + offa, ra); Vec8<TY>::load(residual + offb, rb); }
+      finish(r, xa, ga_, ha, ra);
+      finish(r + rl_count, xb, gb_, hb, rb);
+    }
+    if (r < r1) {
+      const long off = (long)r * C + c;
+      float xv[8], g[8], h2[8], res[8];
+      Vec8<TX>::load(x + off, xv);
+      Vec8<TY>::load(dy + off, g);
+      if (dy2) Vec8<TY>::load(dy2 + off, h2);
+      if (residual) Vec8<TY>::load(residual + off, res);
+      finish(r, xv, g, h2, res);
     }
   }
 #pragma unroll
@@ -643,7 +687,20 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const TY* __re
     }
   }
   const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
-  for (int r = r0 + rl; r < r1; r += rl_count) {
+  int r = r0 + rl;
+  for (; r + rl_count < r1; r += 2 * rl_count) {          // two rows in flight per thread
+    const long offa = (long)r * C + c, offb = (long)(r + rl_count) * C + c;
+    float ga_[8], gb_[8], xa[8], xb[8];
+    Vec8<TY>::load(gbuf + offa, ga_);
+    Vec8<TX>::load(x + offa, xa);
+    Vec8<TY>::load(gbuf + offb, gb_);
+    Vec8<TX>::load(x + offb, xb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ga_[j] = fmaf(p[j], ga_[j], fmaf(q[j], xa[j], rr[j])); gb_[j] = fmaf(p[j], gb_[j], fmaf(q[j], xb[j], rr[j])); }
+    Vec8<TD>::store(dx + offa, ga_);
+    Vec8<TD>::store(dx + offb, gb_);
+  }
+  if (r < r1) {
     const long off = (long)r * C + c;
     float g[8], xv[8];
     Vec8<TY>::load(gbuf + off, g);
@@ -663,7 +720,6 @@ inline int bn_stream_rows(int M, int C) {
   return rpb;
 }
 
-inline int rows_per_block(int M) { int r = dfb_cdiv(M, 148 * 4); return r < 32 ? 32 : r; }
 
 }  // namespace
 
@@ -793,13 +849,17 @@ extern "C" int dfb200_bn_apply(const void* x, int x_dtype, const float* mean, co
   return dfb_check_launch("bn_apply");
 }
 
-extern "C" int dfb200_bn_bwd_reduce(const void* dy, int y_dtype, const void* x, int x_dtype, const float* mean, const float* invstd, const float* gamma,
-                                    const float* beta, const void* residual, int act, const float* chan_scale, int rows_per_sample, int M, int C,
-                                    void* gbuf, float* sum_g, float* sum_gx, float* dbeta, float* dgamma, void* stream) {
+extern "C" int dfb200_bn_bwd_reduce(const void* dy, const void* dy2, int y_dtype, const void* x, int x_dtype, const float* mean, const float* invstd,
+                                    const float* gamma, const float* beta, const void* residual, int act, const float* chan_scale, int rows_per_sample,
+                                    int M, int C, void* gbuf, float* sum_g, float* sum_gx, float* dbeta, float* dgamma, void* stream) {
   DFB_REQUIRE(C % 8 == 0, "bn_bwd_reduce: C %% 8 != 0 (C=%d)", C);
-  const int rpb = rows_per_block(M);
-  dim3 grid(dfb_cdiv(M, rpb), dfb_cdiv(C / 8, BN_THREADS));
-#define L(TX, TY) dfb_launch(bn_bwd_reduce_kernel<TX, TY>, grid, BN_THREADS, 0, ST, (const TY*)dy, (const TX*)x, mean, invstd, gamma, beta, (const TY*)residual, act, chan_scale, rows_per_sample, M, C, (TY*)gbuf, sum_g, sum_gx, dbeta, dgamma, rpb)
+  // the kernel keeps ~100 registers per thread (per-channel constants + two rows in flight): two CTAs per SM, so the grid is ONE wave
+  // of 2 x 148 CTAs (a second, partial wave of this latency-sensitive kernel cost as much as the first)
+  const int ygrid = dfb_cdiv(C / 8, BN_THREADS);
+  int rpb = dfb_cdiv(M, max(1, (148 * 2) / ygrid));
+  if (rpb < 32) rpb = 32;
+  dim3 grid(dfb_cdiv(M, rpb), ygrid);
+#define L(TX, TY) dfb_launch(bn_bwd_reduce_kernel<TX, TY>, grid, BN_THREADS, 0, ST, (const TY*)dy, (const TY*)dy2, (const TX*)x, mean, invstd, gamma, beta, (const TY*)residual, act, chan_scale, rows_per_sample, M, C, (TY*)gbuf, sum_g, sum_gx, dbeta, dgamma, rpb)
   if (x_dtype == 0 && y_dtype == 0) L(float, float);
   else if (x_dtype == 0 && y_dtype == 1) L(float, bf16);
   else if (x_dtype == 1 && y_dtype == 1) L(bf16, bf16);

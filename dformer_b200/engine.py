@@ -5,7 +5,11 @@ Streams and graphs instead of a tracing compiler: the step is ordinary eager cod
 C-ABI kernel launches on the current stream); `torch.cuda.graph` records it.  Inputs live in static device buffers
 that `step()` refreshes with asynchronous H2D copies; the NMF bases keep the reference's CPU `torch.rand` draw
 (ham_head.py:111), staged through pinned memory outside the graph."""
+import os
+
 import torch
+
+_SKIP_BASES = os.environ.get("DFB200_PROFILE_SKIP_BASES", "0") == "1"
 
 
 class GraphedTrainStep:
@@ -73,6 +77,8 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
 
     def _draw_bases(self):
+        if _SKIP_BASES and self.graph is not None:       # diagnostic only (cost of the per-step host draw + H2D copy in front of the graph)
+            return
         k = self._bases_slot
         self._bases_slot ^= 1
         if self._bases_evt[k] is not None:

@@ -22,10 +22,11 @@ import os as _os
 
 
 # ============================================================================================ helpers
-def _lin(x, wb, T, act=K.ACT_NONE, act_col_start=0, out=None, out_dtype=None):
+def _lin(x, wb, T, act=K.ACT_NONE, act_col_start=0, out=None, out_dtype=None, **epi):
+    """epi: the fused gate epilogue of the tcgen05 GEMM (gate= / out2=, kernels.gemm)"""
     w, b = wb
     return K.gemm(x, w, trans_b=True, bias=b, out=out, out_dtype=out_dtype or T, act=act, act_col_start=act_col_start,
-                  backend=backend_for(T), K=x.shape[1])
+                  backend=backend_for(T), K=x.shape[1], **epi)
 
 
 _WGRAD_STREAM = None      # set by BlockFn.backward: weight/bias gradients are leaves of the backward graph
@@ -106,10 +107,10 @@ def _lin_bn_folded(x, wb, bn: BNState, T, act=K.ACT_NONE, out_dtype=None):
     return K.gemm(x, w, trans_b=True, bias=bias, out_dtype=out_dtype or T, act=act, backend=backend_for(T), K=x.shape[1])
 
 
-def _bn_bwd(dy, x2d, ms, bn: BNState, count, dx_dtype, dgamma, dbeta, act=K.ACT_NONE, residual=None, chan_scale=None, rows_per_sample=1):
-    """returns (dx, g) with g = gradient w.r.t. the pre-activation (= gradient of the residual branch)."""
+def _bn_bwd(dy, x2d, ms, bn: BNState, count, dx_dtype, dgamma, dbeta, act=K.ACT_NONE, residual=None, chan_scale=None, rows_per_sample=1, dy2=None):
+    """returns (dx, g) with g = gradient w.r.t. the pre-activation (= gradient of the residual branch); dy2: second incoming gradient."""
     # local parameter gradients (DP averages them later) come out of the same pass as the two sums
-    gbuf, sums = K.bn_bwd_reduce(dy, x2d, ms, bn.weight, bn.bias, residual, act, chan_scale, rows_per_sample, dbeta=dbeta, dgamma=dgamma)
+    gbuf, sums = K.bn_bwd_reduce(dy, x2d, ms, bn.weight, bn.bias, residual, act, chan_scale, rows_per_sample, dbeta=dbeta, dgamma=dgamma, dy2=dy2)
     if bn.sync:
         small_all_reduce_(sums, bn.sync_group if bn.sync_group is not True else None)
     dx = K.bn_bwd_apply(gbuf, x2d, ms, bn.weight, sums, count, bn.training, dx_dtype)
@@ -129,6 +130,8 @@ class StemFn(torch.autograd.Function):
         H1, W1, H2, W2 = (H + 1) // 2, (W + 1) // 2, ((H + 1) // 2 + 1) // 2, ((W + 1) // 2 + 1) // 2
         pk1, pk2 = st.packed[st.g1], st.packed[st.g2]
         col1 = K.im2col_fwd(inp, (inp.stride(0), inp.stride(2), inp.stride(3), inp.stride(1)), B, H, W, cin, T, pk1[0].shape[1])
+        if getattr(st, "ev_pack", None) is not None:
+            torch.cuda.current_stream().wait_event(st.ev_pack)          # the packed weights (side stream) are first needed here
         if _can_fold(st.bn1, ctx) and _can_fold(st.bn2, ctx):          # inference: both BatchNorms ride in their conv's GEMM
             a1 = _lin_bn_folded(col1, pk1, st.bn1, T, act=K.ACT_GELU)
             cm = a1.shape[1]
@@ -281,6 +284,12 @@ class BlockFn(torch.autograd.Function):
         sv = {"_bwd": any(ctx.needs_input_grad)}          # inference: nothing is kept for a backward pass
         side = st.side
         main = torch.cuda.current_stream()
+        # bf16: the gating products q * a / cut * e (:134-135) are epilogues of the GEMMs that produce a / e (csrc/gemm_tc.cu "gate"):
+        # they land directly in their column slices of the concat buffer y (:137-140)
+        fuse = T == torch.bfloat16
+        keep = sv["_bwd"]
+        ycols = 2 * C if win else C + Ce
+        y = torch.empty((M, ycols), device=x.device, dtype=T)
         # ---- depth gate path on the side stream
         K.fork(side)
         with torch.cuda.stream(side):
@@ -288,9 +297,9 @@ class BlockFn(torch.autograd.Function):
             ev_en = K.signal(side)
             ef = _lin(en, pk("attn.e_fore"), T)
             ec = K.dwconv_fwd(ef, P["attn.e_conv.weight"], P["attn.e_conv.bias"], B, H, W, 7)
-            e = _lin(ec, pk("attn.e_back"), T)
-            ev_e = K.signal(side)
-        K.share(main, en, mu2, rs2, ef, ec, e)
+            if not fuse:
+                e = _lin(ec, pk("attn.e_back"), T)
+                ev_e = K.signal(side)
         # ---- RGB path
         xn, mu1, rs1 = K.layernorm_fwd(x, P["attn.norm.weight"], P["attn.norm.bias"], 1e-6, T)
         if win:                                                       # global-awareness branch on a second side stream:
@@ -300,10 +309,17 @@ class BlockFn(torch.autograd.Function):
                 side2.wait_event(ev_en)
                 pooled = K.pool7_fwd(xn, en, B, H, W)
                 m = _lin(pooled, pk("attn.short_cut_linear"), T)
-        qcl = _lin(xn, pk("attn.qcl"), T)                                         # [M, 2.5C] = q | cut | z_l
-        l = K.act_fwd(qcl[:, C + Ce:], K.ACT_GELU)
-        ycols = 2 * C if win else C + Ce
-        y = torch.empty((M, ycols), device=x.device, dtype=T)
+        qcl = _lin(xn, pk("attn.qcl"), T)                                         # [M, 2.5C] = z_l | q | cut
+        l = K.act_fwd(qcl[:, :C], K.ACT_GELU)
+        if fuse:
+            ev_qcl = K.signal()
+            with torch.cuda.stream(side):                             # e_back needs `cut` as its gate
+                side.wait_event(ev_qcl)
+                e = torch.empty((M, Ce), device=x.device, dtype=T) if keep else None
+                _lin(ec, pk("attn.e_back"), T, out=y[:, ycols - Ce:], gate=qcl[:, 2 * C:], out2=e)
+                ev_e = K.signal(side)
+            K.share(side, y, qcl)
+        K.share(main, en, mu2, rs2, ef, ec, e)
         if win:
             K.fork(side2)
             with torch.cuda.stream(side2):
@@ -317,14 +333,20 @@ class BlockFn(torch.autograd.Function):
                     lse7 = None
                 K.resize_fwd(o7, B, 7, 7, y, H, W, col0=C)
             K.share(main, kv, pooled, m, probs, o7, lse7)
+            K.share(side2, y, l)
             sv.update(kv=kv, pooled=pooled, m=m, probs=probs, o7=o7, lse7=lse7)
         cv = K.dwconv_fwd(l, P["attn.conv.weight"], P["attn.conv.bias"], B, H, W, 7)
-        a = _lin(cv, pk("attn.a"), T)
-        K.mul_fwd(qcl[:, :C], a, y[:, :C])
+        if fuse:
+            a = torch.empty((M, C), device=x.device, dtype=T) if keep else None
+            _lin(cv, pk("attn.a"), T, out=y[:, :C], gate=qcl[:, C:2 * C], out2=a)
+        else:
+            a = _lin(cv, pk("attn.a"), T)
+            K.mul_fwd(qcl[:, C:2 * C], a, y[:, :C])
         if win:
             K.join(side2)
         main.wait_event(ev_e)
-        K.mul_fwd(qcl[:, C:C + Ce], e, y[:, ycols - Ce:])
+        if not fuse:
+            K.mul_fwd(qcl[:, 2 * C:], e, y[:, ycols - Ce:])
         pp = _lin(y, pk("attn.pp"), T)                                            # [M, C (+Ce)] = proj | proj_e
         sv.update(x=x, x_e=x_e, mu1=mu1, rs1=rs1, mu2=mu2, rs2=rs2, xn=xn, en=en, qcl=qcl, l=l, cv=cv, a=a, y=y, ef=ef, ec=ec, e=e, pp=pp)
         # ---- MLPs: depth stream on the side stream, RGB stream on the main stream
@@ -390,7 +412,7 @@ class BlockFn(torch.autograd.Function):
         da = torch.empty((M, C), device=dev, dtype=T)
         de = torch.empty((M, Ce), device=dev, dtype=T)
         # the element-wise gradient kernels below also emit the bias gradients of q | q_cut | l, a and e_back (column sums of what they write)
-        K.mul_bwd(dy[:, ycols - Ce:], qcl[:, C:C + Ce], sv["e"], dqcl[:, C:C + Ce], de, G["attn.q_cut.bias"], G["attn.e_back.bias"])
+        K.mul_bwd(dy[:, ycols - Ce:], qcl[:, 2 * C:], sv["e"], dqcl[:, 2 * C:], de, G["attn.q_cut.bias"], G["attn.e_back.bias"])
         # ---- depth gate path e = e_back(dw7(e_fore(en))) on the side stream
         K.fork(side)
         with torch.cuda.stream(side):
@@ -425,15 +447,15 @@ class BlockFn(torch.autograd.Function):
                 dxn_pool, den_pool = K.pool7_bwd(dpooled, C, Ce, B, H, W)
             K.share(main, dxn_pool, den_pool, dl_kv)
         # ---- RGB path: a = a(dw7(l))
-        K.mul_bwd(dy[:, :C], qcl[:, :C], sv["a"], dqcl[:, :C], da, G["attn.q.bias"], G["attn.a.bias"])
+        K.mul_bwd(dy[:, :C], qcl[:, C:2 * C], sv["a"], dqcl[:, C:2 * C], da, G["attn.q.bias"], G["attn.a.bias"])
         dcv = _lin_bwd(da, sv["cv"], pk("attn.a")[0], G["attn.a.weight"], None, T)
         dl = K.dwconv_bwd(dcv, sv["l"], P["attn.conv.weight"], P["attn.conv.bias"], B, H, W, 7, False, K.ACT_NONE,
                           G["attn.conv.weight"], G["attn.conv.bias"], wgrad_stream=_WGRAD_STREAM)
         if win:
             main.wait_event(ev_dlkv)
-        K.act_bwd(dl, qcl[:, C + Ce:], K.ACT_GELU, out=dqcl[:, C + Ce:], dout2=dl_kv, colsum=G["attn.l.bias"])      # kv branch's gradient of l joins here
+        K.act_bwd(dl, qcl[:, :C], K.ACT_GELU, out=dqcl[:, :C], dout2=dl_kv, colsum=G["attn.l.bias"])      # kv branch's gradient of l joins here
         qclw = pk("attn.qcl")[0]
-        dWq = ar.span(st.prefix + "attn.q.weight", st.prefix + "attn.l.weight", qclw.shape)
+        dWq = ar.span(st.prefix + "attn.l.weight", st.prefix + "attn.q_cut.weight", qclw.shape)
         dxn = _lin_bwd(dqcl, sv["xn"], qclw, dWq, None, T)
         # the pooled-query branch's gradient joins inside the LayerNorm backward kernels (dy2)
         if win:
@@ -717,8 +739,9 @@ class HeadFn(torch.autograd.Function):
         dhin_pre = K.act_bwd(dhin, hin, K.ACT_RELU)
         ds = _lin_bwd(dhin_pre, sv["s"], pk("ham_in")[0], G["hamburger.ham_in.conv.weight"].view(pk("ham_in")[0].shape),
                       G["hamburger.ham_in.conv.bias"], T)
-        K.axpy(ds_res, 1.0, ds)
-        ds_pre, _ = _bn_bwd(ds, sv["s_pre"], sv["ms_s"], st.bn_sq, sv["n_s"], T, G["squeeze.bn.weight"], G["squeeze.bn.bias"], act=K.ACT_RELU)
+        # s feeds ham_in and the residual of ham_out: the two gradients are summed inside the BatchNorm backward
+        ds_pre, _ = _bn_bwd(ds, sv["s_pre"], sv["ms_s"], st.bn_sq, sv["n_s"], T, G["squeeze.bn.weight"], G["squeeze.bn.bias"], act=K.ACT_RELU,
+                            dy2=ds_res)
         dcat = _lin_bwd(ds_pre, sv["cat"], pk("squeeze")[0], G["squeeze.conv.weight"].view(pk("squeeze")[0].shape), None, T)
         do1 = torch.empty((M, C1), device=dev, dtype=F32)
         do2 = torch.empty((B * h2 * w2, C2), device=dev, dtype=F32)

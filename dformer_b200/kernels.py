@@ -65,8 +65,9 @@ GEMM_SHAPES_ONLY = False  # ... or just to collect the (shape, flops, bytes) cen
 
 
 def gemm(a, b, *, trans_a=False, trans_b=True, bias=None, out=None, out_dtype=None, act=ACT_NONE, act_col_start=0,
-         accumulate=False, backend=AUTO, splitk=0, alpha=0.0, M=None, N=None, K=None):
-    """out[M,N] = act(alpha * op(a) @ op(b) + bias).  a/b are 2-D with unit inner stride (row slices allowed)."""
+         accumulate=False, backend=AUTO, splitk=0, alpha=0.0, M=None, N=None, K=None, gate=None, out2=None):
+    """out[M,N] = act(alpha * op(a) @ op(b) + bias).  a/b are 2-D with unit inner stride (row slices allowed).
+    Fused epilogue (tcgen05 backend, bf16): `gate` [M,N] -> out = (a @ b + bias) * gate, `out2` (optional) = a @ b + bias."""
     _chk(a), _chk(b)
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
     if M is None:
@@ -87,6 +88,14 @@ def gemm(a, b, *, trans_a=False, trans_b=True, bias=None, out=None, out_dtype=No
     g.transA, g.transB = int(trans_a), int(trans_b)
     g.a_dtype, g.b_dtype, g.out_dtype = dt(a), dt(b), dt(out)
     g.act, g.act_col_start, g.accumulate, g.backend, g.splitk, g.alpha = act, act_col_start, int(accumulate), backend, splitk, alpha
+    if gate is not None:
+        _chk(gate)
+        assert gate.shape == (M, N) and gate.stride(1) == 1 and gate.dtype == out.dtype
+        g.epi_mode, g.aux, g.ld_aux = 1, gate.data_ptr(), gate.stride(0)
+        if out2 is not None:
+            _chk(out2)
+            assert out2.shape == (M, N) and out2.stride(1) == 1 and out2.dtype == out.dtype
+            g.out2, g.ld_out2 = out2.data_ptr(), out2.stride(0)
     if GEMM_PROFILE is not None and GEMM_SHAPES_ONLY:
         tc = backend != SIMT and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
         GEMM_PROFILE.append((None, None, 2.0 * M * N * K, a.element_size() * M * K + b.element_size() * N * K + out.element_size() * M * N, tc,
@@ -413,12 +422,14 @@ def bn_apply(x, ms, gamma, beta, out_dtype, residual=None, act=ACT_NONE, chan_sc
     return y
 
 
-def bn_bwd_reduce(dy, x, ms, gamma, beta, residual, act, chan_scale, rows_per_sample, dbeta=None, dgamma=None):
-    """dbeta / dgamma (optional): accumulate the local parameter gradients (= the two sums) in the same pass"""
+def bn_bwd_reduce(dy, x, ms, gamma, beta, residual, act, chan_scale, rows_per_sample, dbeta=None, dgamma=None, dy2=None):
+    """dbeta / dgamma (optional): accumulate the local parameter gradients (= the two sums) in the same pass;
+    dy2 (optional): a second incoming gradient, summed with dy in the same pass"""
+    assert dy2 is None or (dy2.shape == dy.shape and dy2.dtype == dy.dtype and dy2.is_contiguous())
     M, C = x.shape
     gbuf = torch.empty_like(dy)
     sums = torch.zeros((2, C), device=x.device, dtype=torch.float32)
-    lib().bn_bwd_reduce(dy.data_ptr(), dt(dy), x.data_ptr(), dt(x), ms[0].data_ptr(), ms[1].data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+    lib().bn_bwd_reduce(dy.data_ptr(), _p(dy2), dt(dy), x.data_ptr(), dt(x), ms[0].data_ptr(), ms[1].data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                         _p(residual), act, _p(chan_scale), rows_per_sample, M, C, gbuf.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), _p(dbeta), _p(dgamma), _s())
     return gbuf, sums
 

@@ -109,7 +109,7 @@ class Block(nn.Module):
 
     # parameter order inside the gradient arena: members of one fused GEMM are adjacent
     def param_names(self):
-        a = ["attn.q.weight", "attn.q_cut.weight", "attn.l.weight", "attn.q.bias", "attn.q_cut.bias", "attn.l.bias",
+        a = ["attn.l.weight", "attn.q.weight", "attn.q_cut.weight", "attn.l.bias", "attn.q.bias", "attn.q_cut.bias",
              "attn.a.weight", "attn.a.bias"]
         if self.window != 0:
             a += ["attn.kv.weight", "attn.kv.bias", "attn.short_cut_linear.weight", "attn.short_cut_linear.bias"]
@@ -127,7 +127,7 @@ class Block(nn.Module):
         return a
 
     def gemm_groups(self):
-        g = [("attn.qcl", ["attn.q", "attn.q_cut", "attn.l"]), ("attn.a", ["attn.a"])]
+        g = [("attn.qcl", ["attn.l", "attn.q", "attn.q_cut"]), ("attn.a", ["attn.a"])]
         if self.window != 0:
             g += [("attn.kv", ["attn.kv"]), ("attn.short_cut_linear", ["attn.short_cut_linear"])]
         g += [("attn.e_fore", ["attn.e_fore"]), ("attn.e_back", ["attn.e_back"]),
@@ -250,7 +250,14 @@ class DFormer(nn.Module):
         x, x_e = x.float(), x_e.float()
         plan = self._plan or self._build_plan()
         dev = x.device
-        packed = plan.packer.pack(dev, T)
+        if self._side_stream is None or self._side_stream[0].device != dev:
+            self._side_stream = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
+        side, side2, wstream = self._side_stream
+        # compute-dtype copies of the GEMM weights: on a side stream, under the stems' im2col gathers (which need no weights)
+        Fn.K.fork(side2)
+        with torch.cuda.stream(side2):
+            packed = plan.packer.pack(dev, T)
+            ev_pack = Fn.K.signal(side2)
         arena = GradArena(plan.layout, dev, self.grad_hook)
         self._last_arena = arena
         named = plan.named
@@ -266,14 +273,10 @@ class DFormer(nn.Module):
                 keep = plan.dp_keep = (1.0 - torch.tensor(rates, dtype=torch.float32).view(-1, 1, 1)).to(dev)
             dp = torch.floor(keep + torch.rand(n_blocks, 4, B, device=dev)) / keep      # DropPath: mask / keep_prob per sample
 
-        if self._side_stream is None or self._side_stream[0].device != dev:
-            self._side_stream = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
-        side, side2, wstream = self._side_stream
-
         def stem(inp, sfx, cin):
             p = f"downsample_layers{sfx}.0."
             seq = self.downsample_layers[0] if sfx == "" else self.downsample_layers_e[0]
-            st = SimpleNamespace(dtype=T, cin=cin, packed=packed, g1=p + "c1", g2=p + "c2", arena=arena, prefix=p, tag=p, wstream=wstream,
+            st = SimpleNamespace(dtype=T, cin=cin, packed=packed, ev_pack=ev_pack, g1=p + "c1", g2=p + "c2", arena=arena, prefix=p, tag=p, wstream=wstream,
                                  bn1=Fn.BNState(seq[1], p + "1", training, False), bn2=Fn.BNState(seq[4], p + "4", training, False))
             names = ("0.weight", "0.bias", "1.weight", "1.bias", "3.weight", "3.bias", "4.weight", "4.bias")
             return Fn.StemFn.apply(inp, st, *[named[p + n] for n in names])

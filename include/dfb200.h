@@ -55,8 +55,14 @@ typedef struct dfb200_gemm_args {
   int backend;
   int splitk;            /* 0 = auto, 1 = off, >1 = forced number of reduction splits */
   float alpha;           /* scales the product before bias/activation (0 is treated as 1) */
-  /* reserved (must be 0 / NULL): round 1 carried fused gelu'-multiply and layer-scale-residual epilogues here; they were
-   * measured slower than the separate streaming kernels on B200 and removed.  The fields stay so that the struct layout is stable. */
+  /* Fused epilogue of the tcgen05 backend (bf16 C through the TMA-store path, batch 1; any other configuration is rejected):
+   *   epi_mode 1 "gate": C = (A.B + bias) * aux   (aux: bf16 [M, N], leading dimension ld_aux; DFormer.py:134-135 `q * a`,
+   *                      `cutted_x * x_e` computed where the second factor is produced and written straight into a column slice of
+   *                      the concat buffer, :137-140); out2 (optional, bf16 [M, N], ld_out2) receives A.B + bias, which the backward
+   *                      pass needs.
+   * `ls`, `scale_b`, `rows_per_sample` are reserved (NULL / 0).  Measured and removed: a layer-scale-residual epilogue and a
+   * gelu'-multiply epilogue (round 1), a "dual activation" epilogue emitting GELU(l) beside l (round 2, +0.3 ms/step: eight
+   * epilogue warps evaluate erf slower than a full-occupancy streaming kernel). */
   int epi_mode;
   const void* aux; long ld_aux;
   void* out2; long ld_out2;
@@ -206,10 +212,11 @@ int dfb200_bn_eval_stats(const float* running_mean, const float* running_var, fl
 int dfb200_bn_apply(const void* x, int x_dtype, const float* mean, const float* invstd, const float* gamma,
                     const float* beta, const void* residual, int act, const float* chan_scale, int rows_per_sample,
                     int M, int C, void* y, int y_dtype, void* stream);
-/* backward, pass 1: g = dy [* chan_scale] * act'(.) ; writes g (dtype of y) into gbuf, accumulates
- * sum_g[c], sum_gx[c] = sum g*xhat (zero-init by caller).  pass 2 (bn_bwd_apply):
+/* backward, pass 1: g = (dy [+ dy2]) [* chan_scale] * act'(.) ; writes g (dtype of y) into gbuf, accumulates
+ * sum_g[c], sum_gx[c] = sum g*xhat (zero-init by caller).  dy2 (optional, same dtype / shape as dy) is a second incoming
+ * gradient (fan-in of a residual branch) summed in the same pass.  pass 2 (bn_bwd_apply):
  *   dx = gamma*invstd*( g - sum_g/n - xhat*sum_gx/n )   (training)  or gamma*invstd*g (eval)          */
-int dfb200_bn_bwd_reduce(const void* dy, int y_dtype, const void* x, int x_dtype, const float* mean, const float* invstd,
+int dfb200_bn_bwd_reduce(const void* dy, const void* dy2, int y_dtype, const void* x, int x_dtype, const float* mean, const float* invstd,
                          const float* gamma, const float* beta, const void* residual, int act, const float* chan_scale,
                          int rows_per_sample, int M, int C, void* gbuf, float* sum_g, float* sum_gx,
                          float* dbeta /* optional: += sum_g (the bias gradient) */, float* dgamma /* optional: += sum_gx */, void* stream);

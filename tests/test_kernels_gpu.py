@@ -441,9 +441,10 @@ def test_im2col_conv3x3s2(dtype):
 # ----------------------------------------------------------------------------- BatchNorm
 @pytest.mark.parametrize("x_dtype,y_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16)])
 @pytest.mark.parametrize("act,use_res", [(0, False), (1, False), (2, False), (2, True)])
-def test_batchnorm_train(x_dtype, y_dtype, act, use_res):
+@pytest.mark.parametrize("M,C", [(2400, 48), (4099, 512), (37, 2056)])
+def test_batchnorm_train(x_dtype, y_dtype, act, use_res, M, C):
     k = K()
-    M, C, B = 2400, 48, 2
+    B = 1 if M % 2 else 2
     x = (rnd(M, C) * 1.5 + 0.7).to(x_dtype)
     gamma, beta = 1 + 0.1 * rnd(C), 0.1 * rnd(C)
     rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
@@ -463,8 +464,9 @@ def test_batchnorm_train(x_dtype, y_dtype, act, use_res):
     torch.testing.assert_close(rm, rm2, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(rv, rv2, rtol=1e-4, atol=1e-5)
     dy = rnd(M, C, dtype=y_dtype)
-    ref.backward(dy.float())
-    gbuf, sums = k.bn_bwd_reduce(dy, x, ms, gamma, beta, res, act, None, M // B)
+    dy_b = rnd(M, C, dtype=y_dtype) if use_res else None             # second incoming gradient, summed inside the kernel
+    ref.backward(dy.float() + (dy_b.float() if use_res else 0))
+    gbuf, sums = k.bn_bwd_reduce(dy, x, ms, gamma, beta, res, act, None, M // B, dy2=dy_b)
     dx = k.bn_bwd_apply(gbuf, x, ms, gamma, sums, M, True, x_dtype)
     t = dict(rtol=3e-2, atol=3e-2) if torch.bfloat16 in (x_dtype, y_dtype) else dict(rtol=1e-3, atol=1e-4)
     torch.testing.assert_close(dx.float(), xr.grad, **t)

@@ -73,6 +73,25 @@ def main():
         good = err <= 2e-2 * max(1.0, ref.abs().max().item()) and untouched
         ok &= good
         print(f"{'OK ' if good else 'BAD'} tma-store slice M={M} N={N} K={K} off={off} width={width} err={err:.4g} untouched={untouched}", flush=True)
+    # fused "gate" epilogue (q * a, cut * e written into column slices of the concat buffer; optional un-gated second output)
+    for (M, N, K, ycols, off, keep) in [(1000, 96, 96, 144, 0, True), (1000, 48, 48, 144, 96, True), (4800, 192, 192, 384, 0, False),
+                                        (1200, 144, 144, 576, 432, True), (300, 288, 288, 1152, 864, False), (130, 40, 72, 200, 160, True)]:
+        a = torch.randn(M, K, device=dev).bfloat16()
+        w = (torch.randn(N, K, device=dev) * 0.2).bfloat16()
+        bias = torch.randn(N, device=dev)
+        qbuf = torch.randn(M, 3 * N + 8, device=dev).bfloat16()
+        gate = qbuf[:, N:2 * N] if N % 8 == 0 else qbuf[:, :N]
+        y = torch.full((M, ycols), 7.0, device=dev, dtype=torch.bfloat16)
+        plain = torch.full((M, N + 8), 7.0, device=dev, dtype=torch.bfloat16) if keep else None
+        k.gemm(a, w, trans_b=True, bias=bias, backend=k.TCGEN05, out=y[:, off:off + N], gate=gate, out2=plain[:, :N] if keep else None)
+        ref = a.float() @ w.float().t() + bias
+        refy = ref * gate.float()
+        e1 = (y[:, off:off + N].float() - refy).abs().max().item()
+        e2 = (plain[:, :N].float() - ref).abs().max().item() if keep else 0.0
+        untouched = (y[:, :off] == 7).all().item() and (y[:, off + N:] == 7).all().item() and (not keep or (plain[:, N:] == 7).all().item())
+        good = e1 <= 2e-2 * max(1.0, refy.abs().max().item()) and e2 <= 2e-2 * max(1.0, ref.abs().max().item()) and untouched
+        ok &= good
+        print(f"{'OK ' if good else 'BAD'} gate M={M} N={N} K={K} off={off} keep={keep} err={e1:.4g} err_plain={e2:.4g} untouched={untouched}", flush=True)
     # strided-batched bf16 output (NMF products)
     for (Bz, M, N, K, ta, tb) in [(3, 4800, 64, 512, False, False), (2, 512, 64, 4800, True, False), (3, 300, 512, 64, False, True)]:
         a = (torch.randn(Bz, K, M, device=dev) if ta else torch.randn(Bz, M, K, device=dev)).bfloat16()

@@ -1,6 +1,6 @@
 """Device time of single kernels at the DFormer-L batch-8 stage shapes: each launcher is captured `reps` times back to back in a
 CUDA graph and the replay is timed with CUDA events (no host launch overhead in the figure).
-usage: python tools/ktime.py [family ...]   families: gaa ln dw7 mlp_dw elem pool"""
+usage: python tools/ktime.py [family ...]   families: gaa ln dw7 mlp_dw elem pool bn gate"""
 import os
 import sys
 
@@ -118,6 +118,44 @@ def fam_pool():
         t3 = gtime(lambda: K.resize_fwd(o7, B, 7, 7, y, H, W, col0=C))
         t4 = gtime(lambda: K.resize_bwd(y, C, B, 7, 7, Ce, H, W, do7))
         print(f"pool/resize [{B},{H},{W}] C={C}: pool7 fwd {t1:.1f} bwd {t2:.1f}  resize fwd {t3:.1f} bwd {t4:.1f} us", flush=True)
+
+
+def fam_bn():
+    """BatchNorm streaming kernels at the head (M = 38400, C = 512), stem (M = 614400 / 153600) and downsample shapes"""
+    for (M, C, xdt) in [(38400, 512, torch.bfloat16), (614400, 48, torch.bfloat16), (153600, 96, torch.bfloat16), (153600, 96, torch.float32),
+                        (38400, 192, torch.float32), (9600, 288, torch.float32)]:
+        x = torch.randn(M, C, device=DEV).to(xdt)
+        dy, res = rb(M, C), rb(M, C)
+        g, b = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+        rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+        st = K.bn_stats(x)
+        ms = K.bn_finalize(st, M, 1e-5, 0.1, rm, rv)
+        gbuf, sums = K.bn_bwd_reduce(dy, x, ms, g, b, res, K.ACT_RELU, None, M // B)
+        t1 = gtime(lambda: K.bn_stats(x))
+        t2 = gtime(lambda: K.bn_apply(x, ms, g, b, torch.bfloat16, residual=res, act=K.ACT_RELU))
+        t3 = gtime(lambda: K.bn_bwd_reduce(dy, x, ms, g, b, res, K.ACT_RELU, None, M // B))
+        t3b = gtime(lambda: K.bn_bwd_reduce(dy, x, ms, g, b, None, K.ACT_NONE, None, M // B))
+        t4 = gtime(lambda: K.bn_bwd_apply(gbuf, x, ms, g, sums, M, True, torch.bfloat16))
+        es = x.element_size()
+        n = M * C
+        print(f"bn M={M} C={C} x={'bf16' if es == 2 else 'fp32'}: stats {t1:.1f} us ({n * es / t1 / 1e3:.0f} GB/s)  apply+res+relu {t2:.1f} ({n * (es + 4) / t2 / 1e3:.0f})  "
+              f"bwd_reduce+res+relu {t3:.1f} ({n * (es + 6) / t3 / 1e3:.0f})  bwd_reduce plain {t3b:.1f} ({n * (es + 4) / t3b / 1e3:.0f})  "
+              f"bwd_apply {t4:.1f} ({n * (es + 4) / t4 / 1e3:.0f}) [incl. the small memset / alloc of each call]", flush=True)
+
+
+def fam_gate():
+    """the gating GEMMs (a, e_back) with the fused gate epilogue vs GEMM + mul_fwd"""
+    for H, W, C, _, _ in STAGES:
+        M = B * H * W
+        for n in (C, C // 2):
+            x, w, bias = rb(M, n), rb(n, n), torch.randn(n, device=DEV)
+            q, y, a = rb(M, 5 * C // 2), rb(M, 2 * C), rb(M, n)
+            gate = q[:, C:C + n]
+            t1 = gtime(lambda: K.gemm(x, w, trans_b=True, bias=bias, out=y[:, :n], gate=gate, out2=a))
+            t1b = gtime(lambda: K.gemm(x, w, trans_b=True, bias=bias, out=y[:, :n], gate=gate))
+            t2 = gtime(lambda: K.gemm(x, w, trans_b=True, bias=bias, out=a))
+            t3 = gtime(lambda: K.mul_fwd(gate, a, y[:, :n]))
+            print(f"gate M={M} N=K={n}: fused (keeps a) {t1:.1f} us  fused (inference) {t1b:.1f}  |  gemm {t2:.1f} + mul {t3:.1f} = {t2 + t3:.1f} us", flush=True)
 
 
 if __name__ == "__main__":

@@ -44,6 +44,11 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 # timeline analysis: busy union, idle gaps, concurrency
 iv = sorted((ev.time_range.start, ev.time_range.end, ev.name) for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA)
 t0, t1 = iv[0][0], max(e for _, e, _ in iv)
+if os.environ.get("DFB200_TIMELINE_CSV"):            # chronological kernel list (start us, duration us, stream, name) for offline analysis
+    with open(os.environ["DFB200_TIMELINE_CSV"], "w") as fh:
+        for ev in sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start):
+            nm = ev.name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0][:70]
+            fh.write(f"{ev.time_range.start - t0:.2f},{ev.time_range.end - ev.time_range.start:.2f},{getattr(ev, 'device_resource_id', -1)},{nm}\n")
 busy, cur_s, cur_e = 0.0, iv[0][0], iv[0][1]
 gaps = []
 for s_, e_, n_ in iv[1:]:
