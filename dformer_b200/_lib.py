@@ -90,6 +90,8 @@ SIGNATURES = {
     "dfb200_upsample_ce_fwd": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, P],
     "dfb200_upsample_ce_bwd_sep": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, P, I, P],
     "dfb200_ce_finalize": [P, P, P],
+    "dfb200_upsample_ce_train": [P, I, I, I, I, I, I, I, P, I, P, P, P, P],
+    "dfb200_ce_grad_finalize": [P, L, P, P, P, I, P],
     "dfb200_upsample_ce_bwd_fused": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, P, I, P],
     "dfb200_upsample_ce_bwd": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, I, P],
     "dfb200_train_pre": [P, P, P, I, I, I, P, P, P, I, I, P, P, P, P],

@@ -334,6 +334,165 @@ __global__ void __launch_bounds__(256) upsample_ce_fwd_rows_kernel(const T* __re
   }
 }
 
+
+// ---- training step in ONE pass: loss + per-pixel log-sum-exp AND the (unscaled) gradient w.r.t. the low-res logits.
+// CTA = (image, source row ly0, segment of CE_SEG hi-res columns); thread = one hi-res column, walking the <= MAXR hi-res rows whose
+// bilinear source row is ly0 (same row grouping as upsample_ce_fwd_rows_kernel: the two horizontally interpolated low-res rows are
+// shared by those rows).  Three sweeps over the classes: (1) common shift, (2) sum of exponentials -> lse, loss, (3) per chunk of 8
+// classes g = softmax - onehot, split between source rows ly0 / ly0 + 1 (weights 1 - wy / wy) and -- through shared-memory
+// reductions -- between the two source columns of the thread's hi-res column; the segment's partial sums are added to the fp32
+// gradient with one atomic per (low-res pixel, class).  Nothing hi-res is written besides lse (optional); the gradient is scaled by
+// dloss / #valid later (ce_grad_finalize_kernel), so this kernel needs neither.  Replaces forward + rows adjoint + columns adjoint
+// (three launches, 200 MB of fp32 partials through HBM).
+constexpr int CE_SEG = 128;
+template <typename T, int MAXR, bool VEC>
+__global__ void __launch_bounds__(CE_SEG) upsample_ce_train_kernel(const T* __restrict__ small, int B, int h, int w, int ncls, int H, int W,
+                                                                   const int64_t* __restrict__ label, int ignore, float* __restrict__ lse_out,
+                                                                   float* loss_acc, float* __restrict__ dgrad) {
+  pdl_sync();
+  __shared__ float red[32];
+  __shared__ float tAs[CE_SEG][9], tBs[CE_SEG][9];  // per hi-res column of the segment: shares of source rows ly0 / ly0 + 1, 8 classes (+1: bank skew)
+  __shared__ int s_i0[CE_SEG], s_i1[CE_SEG];        // horizontal source columns / weight of every hi-res column of the segment
+  __shared__ float s_w1[CE_SEG];
+  const int nseg = (W + CE_SEG - 1) / CE_SEG;
+  const int seg = blockIdx.x % nseg, ly0 = (blockIdx.x / nseg) % h, b = blockIdx.x / (nseg * h);
+  const int s0 = seg * CE_SEG, s1 = min(W, s0 + CE_SEG);
+  const int ox = s0 + threadIdx.x;
+  const bool col_ok = ox < s1;
+  const Lerp lx = lerp_coord(col_ok ? ox : s1 - 1, w, W);
+  const int lx_min = lerp_coord(s0, w, W).i0;
+  const int nlx = lerp_coord(s1 - 1, w, W).i1 - lx_min + 1;      // <= CE_SEG + 2 because W >= w
+  const int i1 = min(ly0 + 1, h - 1);
+  const T* r00 = small + (((long)b * h + ly0) * w + lx.i0) * ncls;
+  const T* r01 = small + (((long)b * h + ly0) * w + lx.i1) * ncls;
+  const T* r10 = small + (((long)b * h + i1) * w + lx.i0) * ncls;
+  const T* r11 = small + (((long)b * h + i1) * w + lx.i1) * ncls;
+  const int o_lo = first_row_of(ly0, h, H);
+  const int nr = col_ok ? min(first_row_of(ly0 + 1, h, H) - o_lo, MAXR) : 0;
+  const float wx = lx.w1, ux = 1.f - lx.w1;
+  s_i0[threadIdx.x] = col_ok ? lx.i0 : -1;
+  s_i1[threadIdx.x] = col_ok ? lx.i1 : -1;
+  s_w1[threadIdx.x] = wx;
+  auto rows8 = [&](int c0, float* top, float* bot) {          // horizontally interpolated logits of classes c0 .. c0 + 7
+    float a[8], bq[8], c[8], d[8];
+    if (VEC) {
+      Vec8<T>::load(r00 + c0, a); Vec8<T>::load(r01 + c0, bq); Vec8<T>::load(r10 + c0, c); Vec8<T>::load(r11 + c0, d);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = c0 + j < ncls;
+        a[j] = ok ? to_f(r00[c0 + j]) : -INFINITY; bq[j] = ok ? to_f(r01[c0 + j]) : -INFINITY;
+        c[j] = ok ? to_f(r10[c0 + j]) : -INFINITY; d[j] = ok ? to_f(r11[c0 + j]) : -INFINITY;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { top[j] = ux * a[j] + wx * bq[j]; bot[j] = ux * c[j] + wx * d[j]; }
+  };
+  // ---- sweep 1: one shift >= every interpolated logit of the group
+  float M = -INFINITY;
+  for (int c0 = 0; c0 < ncls; c0 += 8) {
+    float top[8], bot[8];
+    rows8(c0, top, bot);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (VEC || c0 + j < ncls) M = fmaxf(M, fmaxf(top[j], bot[j]));
+  }
+  float wy[MAXR], sum[MAXR], pk[MAXR];
+  int lab[MAXR];
+#pragma unroll
+  for (int k = 0; k < MAXR; ++k) {
+    sum[k] = 0.f; pk[k] = 0.f; wy[k] = 0.f; lab[k] = -1;
+    if (k < nr) {
+      wy[k] = lerp_coord(o_lo + k, h, H).w1;
+      const long lb = label[((long)b * H + o_lo + k) * W + ox];
+      lab[k] = (lb != (long)ignore && lb >= 0 && lb < ncls) ? (int)lb : -1;
+    }
+  }
+  // ---- sweep 2: sums of exponentials, picked logits
+  for (int c0 = 0; c0 < ncls; c0 += 8) {
+    float top[8], bot[8];
+    rows8(c0, top, bot);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (VEC || c0 + j < ncls) {
+#pragma unroll
+        for (int k = 0; k < MAXR; ++k) {
+          const float v = (1.f - wy[k]) * top[j] + wy[k] * bot[j];
+          sum[k] += __expf(v - M);
+          if (c0 + j == lab[k]) pk[k] = v;
+        }
+      }
+    }
+  }
+  float loss = 0.f, cnt = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXR; ++k) {
+    if (k < nr) {
+      const float lse = M + __logf(sum[k]);
+      if (lse_out) lse_out[((long)b * H + o_lo + k) * W + ox] = lse;
+      if (lab[k] >= 0) { loss += lse - pk[k]; cnt += 1.f; }
+    }
+    sum[k] = (k < nr && lab[k] >= 0) ? 1.f / sum[k] : 0.f;      // from here on: 1 / sum for the valid pixels, 0 (no gradient) otherwise
+  }
+  loss = block_sum(loss, red);
+  cnt = block_sum(cnt, red);
+  if (threadIdx.x == 0) { atomicAdd(loss_acc, loss); atomicAdd(loss_acc + 1, cnt); }
+  // ---- sweep 3: gradient, one chunk of 8 classes at a time
+  const float rx = (float)W / (float)w;
+  for (int c0 = 0; c0 < ncls; c0 += 8) {
+    float top[8], bot[8], ga[8], gb[8];
+    rows8(c0, top, bot);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ga[j] = 0.f; gb[j] = 0.f;
+      if (VEC || c0 + j < ncls) {
+#pragma unroll
+        for (int k = 0; k < MAXR; ++k) {
+          const float v = (1.f - wy[k]) * top[j] + wy[k] * bot[j];
+          float g = __expf(v - M) * sum[k];
+          if (c0 + j == lab[k]) g -= 1.f;
+          ga[j] += g;
+          gb[j] = fmaf(wy[k], g, gb[j]);
+        }
+      }
+    }
+    __syncthreads();                                            // the previous chunk's shares have been consumed
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { tAs[threadIdx.x][j] = ga[j] - gb[j]; tBs[threadIdx.x][j] = gb[j]; }
+    __syncthreads();
+    // gather form of the horizontal adjoint: one thread per (low-res column, class) sums the shares of the hi-res columns of this
+    // segment whose source columns include it
+    for (int i = threadIdx.x; i < nlx * 8; i += CE_SEG) {
+      const int q = i >> 3, j = i & 7, lxq = lx_min + q;
+      if (c0 + j >= ncls) continue;
+      int t_lo = max(s0, (int)floorf((lxq - 1) * rx) - 1) - s0, t_hi = min(s1 - 1, (int)ceilf((lxq + 2) * rx) + 1) - s0;
+      if (lxq == 0) t_lo = 0;
+      if (lxq == w - 1) t_hi = s1 - 1 - s0;
+      float va = 0.f, vb = 0.f;
+      for (int t = t_lo; t <= t_hi; ++t) {
+        const float w1 = s_w1[t];
+        const float wgt = (s_i0[t] == lxq ? 1.f - w1 : 0.f) + (s_i1[t] == lxq ? w1 : 0.f);
+        va = fmaf(wgt, tAs[t][j], va);
+        vb = fmaf(wgt, tBs[t][j], vb);
+      }
+      if (i1 == ly0) {
+        atomicAdd(dgrad + (((long)b * h + ly0) * w + lxq) * ncls + c0 + j, va + vb);
+      } else {
+        atomicAdd(dgrad + (((long)b * h + ly0) * w + lxq) * ncls + c0 + j, va);
+        atomicAdd(dgrad + (((long)b * h + i1) * w + lxq) * ncls + c0 + j, vb);
+      }
+    }
+  }
+}
+
+template <typename TD>
+__global__ void ce_grad_finalize_kernel(const float* __restrict__ g, long n, const float* __restrict__ loss_acc, const float* __restrict__ dloss,
+                                        TD* __restrict__ out) {
+  pdl_sync();
+  const float gscale = dloss[0] / loss_acc[1];
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) out[i] = from_f<TD>(g[i] * gscale);
+}
+
 // Pass 2 (columns): ds[b,ly,lx,c] = scale * sum_ox wx(lx,ox) * (tA[ly] + tB[ly-1] (+ tB[h-1] on the last row))[ox, c]
 template <typename TD>
 __global__ void __launch_bounds__(256) upsample_ce_bwd_cols_fused_kernel(const float* __restrict__ tA, const float* __restrict__ tB, int B, int h, int w,
@@ -395,6 +554,33 @@ extern "C" int dfb200_upsample_ce_fwd(const void* logits_small, int dtype, int B
     dfb_launch(upsample_ce_fwd_kernel<T>, (int)g, 256, 0, ST, (const T*)logits_small, B, h, w, ncls, H, W, label, ignore, out_nchw, lse, loss_acc, (T*)up_lowp);
   });
   return dfb_check_launch("upsample_ce_fwd");
+}
+
+// One-pass training form: loss_acc += (sum of NLL, #valid), dgrad (fp32 [B*h*w, ncls], zero-initialised by the caller) += the gradient of
+// the SUM of NLL w.r.t. the low-res logits; dfb200_ce_grad_finalize scales it by dloss / #valid.  Returns DFB_ERR_UNSUPPORTED for geometries
+// the row-grouped kernel does not cover (down-sampling, more than 12 hi-res rows per source row): use fwd + bwd_fused there.
+extern "C" int dfb200_upsample_ce_train(const void* logits_small, int dtype, int B, int h, int w, int ncls, int H, int W, const int64_t* label, int ignore,
+                                        float* lse, float* loss_acc, float* dgrad, void* stream) {
+  constexpr int MAXR = 12;
+  if (!(label && loss_acc && dgrad && H >= h && W >= w && (3L * H + 2 * h - 1) / (2L * h) <= MAXR)) {
+    dfb_set_error("upsample_ce_train: unsupported geometry (%dx%d -> %dx%d)", h, w, H, W);
+    return DFB_ERR_UNSUPPORTED;
+  }
+  const long grid = (long)B * h * ((W + CE_SEG - 1) / CE_SEG);
+  const bool vec = (ncls % 8) == 0 && (reinterpret_cast<uintptr_t>(logits_small) & 15) == 0;
+  DFB_DISPATCH_DTYPE(dtype, T, {
+    if (vec) dfb_launch(upsample_ce_train_kernel<T, MAXR, true>, (unsigned)grid, CE_SEG, 0, ST, (const T*)logits_small, B, h, w, ncls, H, W, label, ignore, lse, loss_acc, dgrad);
+    else dfb_launch(upsample_ce_train_kernel<T, MAXR, false>, (unsigned)grid, CE_SEG, 0, ST, (const T*)logits_small, B, h, w, ncls, H, W, label, ignore, lse, loss_acc, dgrad);
+  });
+  return dfb_check_launch("upsample_ce_train");
+}
+
+extern "C" int dfb200_ce_grad_finalize(const float* dgrad, long n, const float* loss_acc, const float* dloss, void* out, int out_dtype, void* stream) {
+  long g = (n + 255) / 256;
+  if (g > 148L * 8) g = 148L * 8;
+  if (g < 1) g = 1;
+  DFB_DISPATCH_DTYPE(out_dtype, TD, { dfb_launch(ce_grad_finalize_kernel<TD>, (int)g, 256, 0, ST, dgrad, n, loss_acc, dloss, (TD*)out); });
+  return dfb_check_launch("ce_grad_finalize");
 }
 
 extern "C" int dfb200_ce_finalize(const float* loss_acc, float* loss, void* stream) {

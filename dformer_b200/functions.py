@@ -765,8 +765,16 @@ class UpsampleCEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, small, label, meta):
         B, h, w, ncls, H, W, ignore, want_out = meta
-        out, lse, acc, loss, _ = K.upsample_ce_fwd(small, B, h, w, ncls, H, W, label, ignore, want_out=want_out, want_loss=label is not None)
         ctx.meta = meta
+        ctx.one_pass = (label is not None and not want_out and ctx.needs_input_grad[0] and K.upsample_ce_train_supported(h, w, H, W))
+        if ctx.one_pass:          # training without the hi-res logits: loss and (unscaled) gradient from ONE launch, nothing hi-res kept
+            loss, acc, dgrad = K.upsample_ce_train(small, B, h, w, ncls, H, W, label, ignore)
+            ctx.save_for_backward(dgrad, acc)
+            ctx.small_dtype = small.dtype
+            out = torch.empty(0, device=small.device)
+            ctx.mark_non_differentiable(out)
+            return loss, out
+        out, lse, acc, loss, _ = K.upsample_ce_fwd(small, B, h, w, ncls, H, W, label, ignore, want_out=want_out, want_loss=label is not None)
         if label is not None:
             ctx.save_for_backward(small, label, lse, acc)
         if out is None:
@@ -779,8 +787,11 @@ class UpsampleCEFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss, _dout):
         B, h, w, ncls, H, W, ignore, _ = ctx.meta
-        small, label, lse, acc = ctx.saved_tensors
         dl = dloss.contiguous().float()
+        if ctx.one_pass:
+            dgrad, acc = ctx.saved_tensors
+            return K.ce_grad_finalize(dgrad, acc, dl, ctx.small_dtype), None, None
+        small, label, lse, acc = ctx.saved_tensors
         ds = K.upsample_ce_bwd_fused(small, B, h, w, ncls, H, W, label, ignore, lse, acc, dl)
         return ds, None, None
 

@@ -541,6 +541,29 @@ def upsample_ce_fwd(small, B, h, w, ncls, H, W, label, ignore, want_out=True, wa
     return out, lse, acc, loss, up
 
 
+def upsample_ce_train_supported(h, w, H, W):
+    """geometries the one-pass training kernel covers (dfb200_upsample_ce_train)"""
+    return H >= h and W >= w and (3 * H + 2 * h - 1) // (2 * h) <= 12
+
+
+def upsample_ce_train(small, B, h, w, ncls, H, W, label, ignore):
+    """loss and the UNSCALED gradient w.r.t. the low-res logits in one launch: returns (loss, acc, dgrad fp32 [B*h*w, ncls])"""
+    dev = small.device
+    acc = torch.zeros(2, device=dev, dtype=torch.float32)
+    dgrad = torch.zeros((B * h * w, ncls), device=dev, dtype=torch.float32)
+    lib().upsample_ce_train(small.data_ptr(), dt(small), B, h, w, ncls, H, W, label.data_ptr(), ignore, None, acc.data_ptr(), dgrad.data_ptr(), _s())
+    loss = torch.empty((), device=dev, dtype=torch.float32)
+    lib().ce_finalize(acc.data_ptr(), loss.data_ptr(), _s())
+    return loss, acc, dgrad
+
+
+def ce_grad_finalize(dgrad, acc, dloss, out_dtype):
+    """gradient of the masked-mean loss: dgrad * dloss / #valid, in out_dtype"""
+    out = torch.empty(dgrad.shape, device=dgrad.device, dtype=out_dtype)
+    lib().ce_grad_finalize(dgrad.data_ptr(), dgrad.numel(), acc.data_ptr(), dloss.data_ptr(), out.data_ptr(), dt(out), _s())
+    return out
+
+
 def upsample_ce_bwd_sep(up, small_dtype, B, h, w, ncls, H, W, label, ignore, lse, acc, dloss):
     dsmall = torch.empty((B * h * w, ncls), device=up.device, dtype=small_dtype)
     scratch = torch.empty((B, ncls, h, W), device=up.device, dtype=torch.float32)

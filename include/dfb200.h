@@ -254,6 +254,13 @@ int dfb200_upsample_ce_fwd(const void* logits_small, int dtype, int B, int h, in
                            void* up_lowp /* optional [B,ncls,H,W] copy of the up-sampled logits in `dtype` (kept for backward) */,
                            void* stream);
 int dfb200_ce_finalize(const float* loss_acc, float* loss, void* stream);
+/* Training step in one pass (builder.py:203,230 forward AND backward): loss_acc[0..1] += (sum of NLL, number of valid pixels), lse (optional)
+ * = per-pixel log-sum-exp, dgrad (fp32 [B*h*w, ncls], zero-initialised by the caller) += d(sum of NLL)/d(logits_small); nothing hi-res
+ * is materialised.  dfb200_ce_grad_finalize turns it into the gradient of the mean: out = dgrad * dloss / loss_acc[1] (dtype of choice).
+ * Returns DFB_ERR_UNSUPPORTED for down-sampling geometries or more than 12 hi-res rows per source row (use fwd + bwd_fused there). */
+int dfb200_upsample_ce_train(const void* logits_small, int dtype, int B, int h, int w, int ncls, int H, int W, const int64_t* label,
+                             int ignore, float* lse, float* loss_acc, float* dgrad, void* stream);
+int dfb200_ce_grad_finalize(const float* dgrad, long n, const float* loss_acc, const float* dloss, void* out, int out_dtype, void* stream);
 /* dlogits_small [B,h,w,ncls] = resize^T( (softmax(up) - onehot) * dloss / valid )  (gather form, deterministic) */
 /* Separable (rows, then columns) form of the same adjoint, fed by the up-sampled logits `up` [B,ncls,H,W] (dtype up_dtype)
  * that the forward kernel can emit: each hi-res probability is evaluated once instead of once per overlapping footprint.

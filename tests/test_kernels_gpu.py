@@ -579,6 +579,43 @@ def test_upsample_ce_bwd_fused_general_scales(h, w, H, W):
     torch.testing.assert_close(ds.view(B, h, w, ncls), sr.grad.permute(0, 2, 3, 1), rtol=1e-3, atol=1e-6)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("ncls,h,w,H,W", [(40, 12, 16, 96, 128), (37, 12, 16, 96, 128), (40, 60, 80, 480, 640), (13, 7, 9, 30, 40), (13, 5, 6, 5, 6),
+                                          (13, 1, 3, 8, 9), (13, 15, 20, 33, 47), (8, 6, 8, 6, 300), (40, 3, 40, 24, 320)])
+def test_upsample_ce_one_pass_training_kernel(dtype, ncls, h, w, H, W):
+    """loss + gradient of the masked-mean CE through the x8 (or any up-sampling) bilinear resize from ONE launch (what training uses):
+    several column segments per row, ragged last segment, 16-byte and scalar class loads, ignore labels, identity / fractional scales."""
+    k = K()
+    B = 2
+    assert k.upsample_ce_train_supported(h, w, H, W)
+    small = rnd(B, h, w, ncls, dtype=dtype)
+    label = torch.randint(0, ncls, (B, H, W), device=DEV)
+    label[torch.rand(B, H, W, device=DEV) < 0.15] = 255
+    loss, acc, dgrad = k.upsample_ce_train(small.view(-1, ncls), B, h, w, ncls, H, W, label, 255)
+    sr = small.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    up = F.interpolate(sr, (H, W), mode="bilinear", align_corners=False)
+    ref_loss = F.cross_entropy(up, label, reduction="none", ignore_index=255)[label != 255].mean()
+    torch.testing.assert_close(loss, ref_loss, rtol=1e-4, atol=1e-5)
+    assert acc[1].item() == (label != 255).sum().item()
+    (ref_loss * 3.0).backward()
+    ds = k.ce_grad_finalize(dgrad, acc, torch.full((), 3.0, device=DEV), dtype)
+    t = dict(rtol=2e-2, atol=2e-5) if dtype == torch.bfloat16 else dict(rtol=1e-3, atol=1e-6)
+    torch.testing.assert_close(ds.view(B, h, w, ncls).float(), sr.grad.permute(0, 2, 3, 1), **t)
+    # agrees with the three-launch path it replaces
+    _, lse, acc2, loss2, _ = k.upsample_ce_fwd(small.view(-1, ncls), B, h, w, ncls, H, W, label, 255, want_out=False)
+    ds2 = k.upsample_ce_bwd_fused(small.view(-1, ncls), B, h, w, ncls, H, W, label, 255, lse, acc2, torch.full((), 3.0, device=DEV))
+    torch.testing.assert_close(loss, loss2, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(ds.float(), ds2.float(), **t)
+
+
+def test_upsample_ce_one_pass_rejects_downsampling():
+    k = K()
+    assert not k.upsample_ce_train_supported(16, 16, 8, 8)
+    small = rnd(1, 16, 16, 8)
+    with pytest.raises(RuntimeError, match="unsupported geometry"):
+        k.upsample_ce_train(small.view(-1, 8), 1, 16, 16, 8, 8, 8, torch.zeros(1, 8, 8, dtype=torch.long, device=DEV), 255)
+
+
 def test_adamw_matches_torch():
     k = K()
     p = rnd(1000)

@@ -1,6 +1,6 @@
 """Device time of single kernels at the DFormer-L batch-8 stage shapes: each launcher is captured `reps` times back to back in a
 CUDA graph and the replay is timed with CUDA events (no host launch overhead in the figure).
-usage: python tools/ktime.py [family ...]   families: gaa ln dw7 mlp_dw elem pool bn gate"""
+usage: python tools/ktime.py [family ...]   families: gaa ln dw7 mlp_dw elem pool bn gate loss"""
 import os
 import sys
 
@@ -141,6 +141,21 @@ def fam_bn():
         print(f"bn M={M} C={C} x={'bf16' if es == 2 else 'fp32'}: stats {t1:.1f} us ({n * es / t1 / 1e3:.0f} GB/s)  apply+res+relu {t2:.1f} ({n * (es + 4) / t2 / 1e3:.0f})  "
               f"bwd_reduce+res+relu {t3:.1f} ({n * (es + 6) / t3 / 1e3:.0f})  bwd_reduce plain {t3b:.1f} ({n * (es + 4) / t3b / 1e3:.0f})  "
               f"bwd_apply {t4:.1f} ({n * (es + 4) / t4 / 1e3:.0f}) [incl. the small memset / alloc of each call]", flush=True)
+
+
+def fam_loss():
+    """x8 upsample + CE at the bench shape: three-launch path (forward, rows adjoint, columns adjoint) vs the one-pass training kernel"""
+    Bq, h, w, ncls, H, W = 8, 60, 80, 40, 480, 640
+    small = rb(Bq * h * w, ncls)
+    label = torch.randint(0, ncls, (Bq, H, W), device=DEV)
+    label[torch.rand(Bq, H, W, device=DEV) < 0.05] = 255
+    one = torch.ones((), device=DEV)
+    _, lse, acc, _, _ = K.upsample_ce_fwd(small, Bq, h, w, ncls, H, W, label, 255, want_out=False)
+    t1 = gtime(lambda: K.upsample_ce_fwd(small, Bq, h, w, ncls, H, W, label, 255, want_out=False))
+    t2 = gtime(lambda: K.upsample_ce_bwd_fused(small, Bq, h, w, ncls, H, W, label, 255, lse, acc, one))
+    t3 = gtime(lambda: K.upsample_ce_train(small, Bq, h, w, ncls, H, W, label, 255))
+    print(f"loss [{Bq},{ncls},{h}x{w} -> {H}x{W}]: forward {t1:.1f} us + adjoint (rows + columns) {t2:.1f} us = {t1 + t2:.1f} us  |  one-pass training kernel {t3:.1f} us "
+          f"(each incl. its small fills)", flush=True)
 
 
 def fam_gate():
