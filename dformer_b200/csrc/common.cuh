@@ -218,6 +218,11 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float2* v) {
 // 8-wide vector load/store of activations as floats (16B for bf16, 32B for fp32).
 template <typename T> struct Vec8;
 template <> struct Vec8<float> {
+  struct raw_t { float4 a, b; };                                  // the loaded-but-not-yet-used form (software-pipelined loops)
+  static __device__ __forceinline__ raw_t load_raw(const float* p) { raw_t r; r.a = *reinterpret_cast<const float4*>(p); r.b = *reinterpret_cast<const float4*>(p + 4); return r; }
+  static __device__ __forceinline__ void unpack(const raw_t& r, float* v) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+  }
   static __device__ __forceinline__ void load(const float* p, float* v) {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -228,6 +233,8 @@ template <> struct Vec8<float> {
   }
 };
 template <> struct Vec8<bf16> {
+  typedef uint4 raw_t;
+  static __device__ __forceinline__ raw_t load_raw(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
   // bf16 -> fp32 is a 16-bit shift: one SHL / one LOP per value instead of the cvt sequence __bfloat1622float2 emits
   static __device__ __forceinline__ void unpack(const uint4& u, float* v) {
     v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);

@@ -581,10 +581,14 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const TX* __restri
   }
 }
 
-template <typename TX, typename TY>
+// ACT: 0 none, 1 GELU, 2 ReLU (compile time).  EXTRA = false: no residual / second gradient / channel scale (the encoder's BatchNorms):
+// those operands are not even tested.  The row loop is software-pipelined: the loads of the next pair of rows are issued before the
+// current pair is processed (ncu of the plain loop: 46 % of the warp samples sat on the first use of the freshly loaded row, 16 warps
+// per SM cannot hide a DRAM round trip plus ~400 issue slots of arithmetic behind each other).
+template <typename TX, typename TY, int ACT, bool EXTRA>
 __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_reduce_kernel(const TY* __restrict__ dy, const TY* __restrict__ dy2, const TX* __restrict__ x, const float* __restrict__ mean,
                                                                    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                   const TY* __restrict__ residual, int act, const float* __restrict__ chan_scale, int rows_per_sample,
+                                                                   const TY* __restrict__ residual, const float* __restrict__ chan_scale, int rows_per_sample,
                                                                    int M, int C, TY* __restrict__ gbuf, float* sum_g, float* sum_gx, float* dbeta, float* dgamma, int rows_per_block) {
   pdl_sync();
   __shared__ float s1[BN_THREADS * 8];
@@ -600,19 +604,39 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_reduce_kernel(const TY* 
     const int cv = t % nvec, rl = t / nvec, c = (v0 + cv) * 8;
     float mu[8], is[8], ga[8], be[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { mu[j] = mean[c + j]; is[j] = invstd[c + j]; ga[j] = gamma[c + j]; be[j] = beta[c + j]; }
-    auto finish = [&](int r, const float* xv, float* g, const float* g2, const float* res) {
+    for (int j = 0; j < 8; ++j) { mu[j] = mean[c + j]; is[j] = invstd[c + j]; ga[j] = ACT ? gamma[c + j] : 0.f; be[j] = ACT ? beta[c + j] : 0.f; }
+    typedef typename Vec8<TX>::raw_t RX;
+    typedef typename Vec8<TY>::raw_t RY;
+    struct Row { RX x; RY g, g2, res; };
+    const bool has2 = EXTRA && dy2 != nullptr, hasr = EXTRA && residual != nullptr, hascs = EXTRA && chan_scale != nullptr;
+    auto fetch = [&](int r, Row& w) {
+      if (r < r1) {
+        const long off = (long)r * C + c;
+        w.x = Vec8<TX>::load_raw(x + off);
+        w.g = Vec8<TY>::load_raw(dy + off);
+        if (has2) w.g2 = Vec8<TY>::load_raw(dy2 + off);
+        if (hasr) w.res = Vec8<TY>::load_raw(residual + off);
+      }
+    };
+    auto finish = [&](int r, const Row& w) {
+      if (r >= r1) return;
       const long off = (long)r * C + c;
+      float xv[8], g[8], g2[8], res[8];
+      Vec8<TX>::unpack(w.x, xv);
+      Vec8<TY>::unpack(w.g, g);
+      if (has2) Vec8<TY>::unpack(w.g2, g2);
+      if (hasr) Vec8<TY>::unpack(w.res, res);
+      const float* cs = hascs ? chan_scale + (long)(r / rows_per_sample) * C + c : nullptr;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float xh = (xv[j] - mu[j]) * is[j];
         float gj = g[j];
-        if (dy2) gj += g2[j];                                   // gradient fan-in (residual branch): summed here instead of in an axpy pass
-        if (chan_scale) gj *= chan_scale[(r / rows_per_sample) * C + c + j];
-        if (act) {
-          float z = xh * ga[j] + be[j];
-          if (residual) z += res[j];
-          gj *= act_bwd(z, act);
+        if (has2) gj += g2[j];                                  // gradient fan-in (residual branch): summed here instead of in an axpy pass
+        if (hascs) gj *= cs[j];
+        if (ACT) {
+          float z = fmaf(xh, ga[j], be[j]);
+          if (hasr) z += res[j];
+          gj *= act_bwd(z, ACT);
         }
         g[j] = gj;
         a1[j] += gj;
@@ -620,27 +644,19 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_reduce_kernel(const TY* 
       }
       Vec8<TY>::store(gbuf + off, g);
     };
+    constexpr int NR = EXTRA ? 1 : 2;                           // rows per pipeline stage (the four-operand form has no registers for pairs)
+    const int step = NR * rl_count;
     int r = r0 + rl;
-    for (; r + rl_count < r1; r += 2 * rl_count) {        // two rows in flight per thread
-      const long offa = (long)r * C + c, offb = (long)(r + rl_count) * C + c;
-      float xa[8], xb[8], ga_[8], gb_[8], ha[8], hb[8], ra[8], rb[8];
-      Vec8<TX>::load(x + offa, xa);
-      Vec8<TY>::load(dy + offa, ga_);
-      Vec8<TX>::load(x + offb, xb);
-      Vec8<TY>::load(dy + offb, gb_);
-      if (dy2) { Vec8<TY>::load(dy2 + offa, ha); Vec8<TY>::load(dy2 + offb, hb); }
-      if (residual) { Vec8<TY>::load(residual + offa, ra); Vec8<TY>::load(residual + offb, rb); }
-      finish(r, xa, ga_, ha, ra);
-      finish(r + rl_count, xb, gb_, hb, rb);
-    }
-    if (r < r1) {
-      const long off = (long)r * C + c;
-      float xv[8], g[8], h2[8], res[8];
-      Vec8<TX>::load(x + off, xv);
-      Vec8<TY>::load(dy + off, g);
-      if (dy2) Vec8<TY>::load(dy2 + off, h2);
-      if (residual) Vec8<TY>::load(residual + off, res);
-      finish(r, xv, g, h2, res);
+    Row cur[NR], nxt[NR];
+#pragma unroll
+    for (int u = 0; u < NR; ++u) fetch(r + u * rl_count, cur[u]);
+    for (; r < r1; r += step) {
+#pragma unroll
+      for (int u = 0; u < NR; ++u) fetch(r + step + u * rl_count, nxt[u]);      // next stage in flight while this one is processed
+#pragma unroll
+      for (int u = 0; u < NR; ++u) finish(r + u * rl_count, cur[u]);
+#pragma unroll
+      for (int u = 0; u < NR; ++u) cur[u] = nxt[u];
     }
   }
 #pragma unroll
@@ -859,13 +875,19 @@ extern "C" int dfb200_bn_bwd_reduce(const void* dy, const void* dy2, int y_dtype
   int rpb = dfb_cdiv(M, max(1, (148 * 2) / ygrid));
   if (rpb < 32) rpb = 32;
   dim3 grid(dfb_cdiv(M, rpb), ygrid);
-#define L(TX, TY) dfb_launch(bn_bwd_reduce_kernel<TX, TY>, grid, BN_THREADS, 0, ST, (const TY*)dy, (const TY*)dy2, (const TX*)x, mean, invstd, gamma, beta, (const TY*)residual, act, chan_scale, rows_per_sample, M, C, (TY*)gbuf, sum_g, sum_gx, dbeta, dgamma, rpb)
+  DFB_REQUIRE(act >= 0 && act <= 2, "bn_bwd_reduce: bad activation %d", act);
+  const bool extra = dy2 != nullptr || residual != nullptr || chan_scale != nullptr;
+#define L3(TX, TY, A, E) dfb_launch(bn_bwd_reduce_kernel<TX, TY, A, E>, grid, BN_THREADS, 0, ST, (const TY*)dy, (const TY*)dy2, (const TX*)x, mean, invstd, gamma, beta, (const TY*)residual, chan_scale, rows_per_sample, M, C, (TY*)gbuf, sum_g, sum_gx, dbeta, dgamma, rpb)
+#define L2(TX, TY, A) do { if (extra) L3(TX, TY, A, true); else L3(TX, TY, A, false); } while (0)
+#define L(TX, TY) do { if (act == 0) L2(TX, TY, 0); else if (act == 1) L2(TX, TY, 1); else L2(TX, TY, 2); } while (0)
   if (x_dtype == 0 && y_dtype == 0) L(float, float);
   else if (x_dtype == 0 && y_dtype == 1) L(float, bf16);
   else if (x_dtype == 1 && y_dtype == 1) L(bf16, bf16);
   else if (x_dtype == 1 && y_dtype == 0) L(bf16, float);
   else { dfb_set_error("bn_bwd_reduce: bad dtypes"); return DFB_ERR_ARG; }
 #undef L
+#undef L2
+#undef L3
   return dfb_check_launch("bn_bwd_reduce");
 }
 
