@@ -39,7 +39,8 @@ static inline int dfb_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 // the tcgen05 GEMM, the barrier / tensor-memory prologue).  Inside a captured CUDA graph the same-stream kernel->kernel edges
 // become programmatic edges.  Measured on the DFormer-L step: 28.72 -> 28.44 ms.  An early griddepcontrol.launch_dependents at
 // kernel entry (-DDFB_PDL_EARLY_TRIGGER) was measured SLOWER (29.42 ms): the waiting CTAs of the next kernel take SM slots
-// from the kernels of the three other streams of the step.
+// from the kernels of the three other streams of the step.  Round 2 repeated it restricted to grids of <= 296 CTAs (the launch-latency-bound
+// kernels): training 21.66 -> 22.22 ms, batch-1 inference unchanged (2.506 ms), batch 8 7.74 -> 7.88 ms.  Not kept.
 __device__ __forceinline__ void pdl_sync() {
 #ifdef DFB_PDL_EARLY_TRIGGER
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

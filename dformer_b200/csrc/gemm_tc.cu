@@ -31,6 +31,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16 KB
 constexpr int MAX_SMEM = 227 * 1024;
 constexpr int SMALL_SMEM = 112 * 1024;            // EPI_WARPS = 4 variant: two CTAs per SM
 constexpr int EPI_WARP_BYTES = 4096;              // per-epilogue-warp [32 rows x 128 B] staging tile of the TMA store
+constexpr int EPI_BIAS_FLOATS = 256;              // per-epilogue-warp bias slice (<= 4 boxes of 64 columns per warp and tile)
 
 struct TcParams {
   int M, N, K;               // problem (K = reduction length)
@@ -248,7 +249,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* epi_stage = smem + p.stages * p.stage_bytes;                 // EPI_WARPS x [32 rows x 128 B], 1024-byte aligned (128-byte swizzle atom)
   uint8_t* epi_stage2 = epi_stage + EPI_WARPS * EPI_WARP_BYTES;         // second output's staging tiles (present when has_out2)
   uint8_t* epi_aux = epi_stage2 + (p.has_out2 ? EPI_WARPS * EPI_WARP_BYTES : 0);     // gate tiles (present in gate mode), TMA-loaded per box
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_aux + (p.epi_mode == 1 ? EPI_WARPS * EPI_WARP_BYTES : 0));
+  float* epi_bias = reinterpret_cast<float*>(epi_aux + (p.epi_mode == 1 ? EPI_WARPS * EPI_WARP_BYTES : 0));   // per warp: the bias of its boxes
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_bias + EPI_WARPS * EPI_BIAS_FLOATS);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
@@ -361,6 +363,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t sbase2 = smem_u32(epi_stage2 + (warp - 2) * EPI_WARP_BYTES);
     const uint32_t sbase_aux = smem_u32(epi_aux + (warp - 2) * EPI_WARP_BYTES);
     uint64_t* my_aux_bar = &aux_bar[warp - 2];
+    float* bias_w = epi_bias + (warp - 2) * EPI_BIAS_FLOATS;
     uint32_t aux_phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     bool store_pending = false;
@@ -390,6 +393,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         };
         load_gate(b_begin);
+        // bias of this warp's boxes -> shared memory while the MMAs of the tile are still running: an L2 round trip between
+        // "accumulator ready" and the first store is the critical path of every one-tile-per-CTA launch (the small-M layers)
+        if (add_bias) {
+          const int c_lo = ncol0 + b_begin * 64;
+          for (int i = lane; i < (b_end - b_begin) * 64; i += 32) bias_w[i] = (c_lo + i < p.N) ? __ldg(p.bias + c_lo + i) : 0.f;
+          __syncwarp();
+        }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         for (int box = b_begin; box < b_end; ++box) {
@@ -412,7 +422,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            bias_act(p, v, col0, ncols, add_bias);
+            if (add_bias) {
+              const float4* bq = reinterpret_cast<const float4*>(bias_w + (box - b_begin) * 64 + h * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = bq[j];
+                v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+              }
+            }
+            act_chunk(p, v, col0);
             if (p.epi_mode == 1) {
               // ---- gate: second output keeps acc + bias (needed by the backward pass), C = (acc + bias) * aux
               if (sec) stage_half(sbase2, lane, h, v);
@@ -512,7 +530,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
     }
-    if (store_pending && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // stores complete before the CTA exits
+    // the staging tiles must outlive the bulk stores' reads of them, nothing more: completion of the grid (what the next kernel's
+    // griddepcontrol.wait / stream order waits for) covers the writes themselves
+    if (store_pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -780,7 +800,7 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   // pipeline depth: as deep as the variant's shared-memory budget allows, but no deeper than the k-blocks this CTA will ever load
   const int b_bytes = p.b_mn_major ? ((p.BN + 63) / 64) * 8192 : ((p.BN * 128 + 1023) / 1024) * 1024;   // 1024-B aligned (swizzle atom)
   p.stage_bytes = A_STAGE_BYTES + b_bytes;
-  const int fixed = epi_warps * EPI_WARP_BYTES * (1 + (p.has_out2 ? 1 : 0) + (p.epi_mode == 1 ? 1 : 0)) + 1024 + 512;
+  const int fixed = epi_warps * EPI_WARP_BYTES * (1 + (p.has_out2 ? 1 : 0) + (p.epi_mode == 1 ? 1 : 0)) + epi_warps * EPI_BIAS_FLOATS * 4 + 1024 + 512;
   p.stages = ((epi_warps == 4 ? SMALL_SMEM : MAX_SMEM) - fixed) / p.stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   const long kb_per_cta = (long)dfb_cdiv(total, grid) * p.kb_per_split;
