@@ -48,6 +48,7 @@ struct TcParams {
   // fused epilogue (TMA-store path only), see dfb200.h:
   //   1 "gate": C = (acc + bias) * aux (bf16 [M, N], leading dimension ld_aux); second output (optional) = acc + bias
   int epi_mode, has_out2;
+  int bias_smem;                             // the epilogue warps stage their bias slices in shared memory (when that costs no pipeline stage)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -250,7 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* epi_stage2 = epi_stage + EPI_WARPS * EPI_WARP_BYTES;         // second output's staging tiles (present when has_out2)
   uint8_t* epi_aux = epi_stage2 + (p.has_out2 ? EPI_WARPS * EPI_WARP_BYTES : 0);     // gate tiles (present in gate mode), TMA-loaded per box
   float* epi_bias = reinterpret_cast<float*>(epi_aux + (p.epi_mode == 1 ? EPI_WARPS * EPI_WARP_BYTES : 0));   // per warp: the bias of its boxes
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_bias + EPI_WARPS * EPI_BIAS_FLOATS);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_bias + (p.bias_smem ? EPI_WARPS * EPI_BIAS_FLOATS : 0));
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
@@ -395,7 +396,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         load_gate(b_begin);
         // bias of this warp's boxes -> shared memory while the MMAs of the tile are still running: an L2 round trip between
         // "accumulator ready" and the first store is the critical path of every one-tile-per-CTA launch (the small-M layers)
-        if (add_bias) {
+        if (add_bias && p.bias_smem) {
           const int c_lo = ncol0 + b_begin * 64;
           for (int i = lane; i < (b_end - b_begin) * 64; i += 32) bias_w[i] = (c_lo + i < p.N) ? __ldg(p.bias + c_lo + i) : 0.f;
           __syncwarp();
@@ -422,13 +423,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (add_bias) {
+            if (add_bias && p.bias_smem) {
               const float4* bq = reinterpret_cast<const float4*>(bias_w + (box - b_begin) * 64 + h * 32);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 b4 = bq[j];
                 v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
               }
+            } else if (add_bias) {
+              add_bias_chunk(p, v, col0, ncols);
             }
             act_chunk(p, v, col0);
             if (p.epi_mode == 1) {
@@ -800,10 +803,18 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   // pipeline depth: as deep as the variant's shared-memory budget allows, but no deeper than the k-blocks this CTA will ever load
   const int b_bytes = p.b_mn_major ? ((p.BN + 63) / 64) * 8192 : ((p.BN * 128 + 1023) / 1024) * 1024;   // 1024-B aligned (swizzle atom)
   p.stage_bytes = A_STAGE_BYTES + b_bytes;
-  const int fixed = epi_warps * EPI_WARP_BYTES * (1 + (p.has_out2 ? 1 : 0) + (p.epi_mode == 1 ? 1 : 0)) + epi_warps * EPI_BIAS_FLOATS * 4 + 1024 + 512;
-  p.stages = ((epi_warps == 4 ? SMALL_SMEM : MAX_SMEM) - fixed) / p.stage_bytes;
-  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  const int fixed0 = epi_warps * EPI_WARP_BYTES * (1 + (p.has_out2 ? 1 : 0) + (p.epi_mode == 1 ? 1 : 0)) + 1024 + 512;
+  const int budget_smem = epi_warps == 4 ? SMALL_SMEM : MAX_SMEM;
   const long kb_per_cta = (long)dfb_cdiv(total, grid) * p.kb_per_split;
+  // bias slices in shared memory (fetched before the accumulator is ready): only where the 4 / 8 KB do not cost this launch a pipeline
+  // stage it would use (the deep-K, many-tile GEMMs hide the bias fetch behind the next tile's main loop anyway)
+  const int bias_bytes = epi_warps * EPI_BIAS_FLOATS * 4;
+  const long st_without = min((long)min((budget_smem - fixed0) / p.stage_bytes, MAX_STAGES), kb_per_cta);
+  const long st_with = min((long)min((budget_smem - fixed0 - bias_bytes) / p.stage_bytes, MAX_STAGES), kb_per_cta);
+  p.bias_smem = (p.tma_store && p.bias != nullptr && st_with >= 1 && st_with == st_without) ? 1 : 0;
+  const int fixed = fixed0 + (p.bias_smem ? bias_bytes : 0);
+  p.stages = (budget_smem - fixed) / p.stage_bytes;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   if (p.stages > kb_per_cta) p.stages = (int)kb_per_cta;
   if (forced_stages > 0 && forced_stages < p.stages) p.stages = forced_stages;
   DFB_REQUIRE(p.stages >= 1, "gemm_tc: tile %d x %d does not fit the shared-memory budget", BM, p.BN);
