@@ -241,7 +241,9 @@ __device__ __forceinline__ void stage_half(uint32_t sbase, int lane, int h, cons
 // EPI_WARPS = 4: 192 threads, <= 112 KB shared memory and <= 256 TMEM columns per CTA so that TWO CTAs are resident per SM:
 //                150 tiles of an M = 9600 layer fit in one wave of 296 slots, and GEMMs of different streams (RGB / depth /
 //                weight-gradient) overlap one CTA's load phase with the other's epilogue.
-template <int EPI_WARPS>
+// GATE / BIAS_SMEM are compile-time: carried as run-time branches inside the epilogue loop they cost the plain store-bound GEMMs
+// 16 - 20 % (fc1-type (153600, 768, 96): 61.6 -> 74.7 us) -- the hot loop of the common case must contain nothing but its own work.
+template <int EPI_WARPS, bool GATE, bool BIAS_SMEM>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, EPI_WARPS == 4 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmE, const TcParams p) {
@@ -249,9 +251,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_stage = smem + p.stages * p.stage_bytes;                 // EPI_WARPS x [32 rows x 128 B], 1024-byte aligned (128-byte swizzle atom)
   uint8_t* epi_stage2 = epi_stage + EPI_WARPS * EPI_WARP_BYTES;         // second output's staging tiles (present when has_out2)
-  uint8_t* epi_aux = epi_stage2 + (p.has_out2 ? EPI_WARPS * EPI_WARP_BYTES : 0);     // gate tiles (present in gate mode), TMA-loaded per box
-  float* epi_bias = reinterpret_cast<float*>(epi_aux + (p.epi_mode == 1 ? EPI_WARPS * EPI_WARP_BYTES : 0));   // per warp: the bias of its boxes
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_bias + (p.bias_smem ? EPI_WARPS * EPI_BIAS_FLOATS : 0));
+  const bool has_out2 = GATE && p.has_out2 != 0;
+  uint8_t* epi_aux = epi_stage2 + (has_out2 ? EPI_WARPS * EPI_WARP_BYTES : 0);       // gate tiles (present in gate mode), TMA-loaded per box
+  float* epi_bias = reinterpret_cast<float*>(epi_aux + (GATE ? EPI_WARPS * EPI_WARP_BYTES : 0));   // per warp: the bias of its boxes
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_bias + (BIAS_SMEM ? EPI_WARPS * EPI_BIAS_FLOATS : 0));
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
@@ -266,8 +269,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
-    if (p.has_out2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
-    if (p.epi_mode == 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmE) : "memory");
+    if (has_out2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
+    if (GATE) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmE) : "memory");
     for (int s = 0; s < EPI_WARPS; ++s) mbar_init(&aux_bar[s], 1);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
@@ -388,7 +391,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // staging tile).  It does not depend on the accumulator: the first box's load is issued before waiting for the MMAs of the
         // tile, the next box's as soon as the current one has been consumed.
         auto load_gate = [&](int box) {
-          if (p.epi_mode == 1 && box < b_end && lane == 0) {
+          if (GATE && box < b_end && lane == 0) {
             mbar_expect_tx(my_aux_bar, EPI_WARP_BYTES);
             tma_load_3d(&tmE, my_aux_bar, epi_aux + (warp - 2) * EPI_WARP_BYTES, ncol0 + box * 64, m_blk * BM + quad * 32, bz);
           }
@@ -396,7 +399,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         load_gate(b_begin);
         // bias of this warp's boxes -> shared memory while the MMAs of the tile are still running: an L2 round trip between
         // "accumulator ready" and the first store is the critical path of every one-tile-per-CTA launch (the small-M layers)
-        if (add_bias && p.bias_smem) {
+        if (BIAS_SMEM && add_bias) {
           const int c_lo = ncol0 + b_begin * 64;
           for (int i = lane; i < (b_end - b_begin) * 64; i += 32) bias_w[i] = (c_lo + i < p.N) ? __ldg(p.bias + c_lo + i) : 0.f;
           __syncwarp();
@@ -405,7 +408,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         for (int box = b_begin; box < b_end; ++box) {
           const int cb = ncol0 + box * 64;                            // first global column of this box
-          const bool sec = p.has_out2 != 0;                           // gate mode keeps acc + bias as a second output
+          const bool sec = has_out2;                                  // gate mode keeps acc + bias as a second output
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int c0 = box * 64 + h * 32;
@@ -423,7 +426,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (add_bias && p.bias_smem) {
+            if (BIAS_SMEM && add_bias) {
               const float4* bq = reinterpret_cast<const float4*>(bias_w + (box - b_begin) * 64 + h * 32);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -434,7 +437,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               add_bias_chunk(p, v, col0, ncols);
             }
             act_chunk(p, v, col0);
-            if (p.epi_mode == 1) {
+            if (GATE) {
               // ---- gate: second output keeps acc + bias (needed by the backward pass), C = (acc + bias) * aux
               if (sec) stage_half(sbase2, lane, h, v);
               if (h == 0) { mbar_wait(my_aux_bar, aux_phase); aux_phase ^= 1; }
@@ -690,9 +693,13 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms_all, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t e = cudaSuccess;
+#define TC_ATTR(G, S)                                                                                                                       \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<8, G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);           \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<4, G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM);         \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<4, G, S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    TC_ATTR(false, false) TC_ATTR(false, true) TC_ATTR(true, false) TC_ATTR(true, true)
+#undef TC_ATTR
     if (e != cudaSuccess) { dfb_set_error("gemm_tc smem attr: %s", cudaGetErrorString(e)); return DFB_ERR_CUDA; }
     // tuning aids (tools/gemm_bn_sweep.py, tools/gemm_replay.py), read once
     if (const char* v = getenv("DFB200_TC_BN")) forced_bn = atoi(v);      // whole-process overrides for tools/gemm_replay.py runs
@@ -819,7 +826,16 @@ int dfb_gemm_tc(const dfb200_gemm_args& g, cudaStream_t st) {
   if (forced_stages > 0 && forced_stages < p.stages) p.stages = forced_stages;
   DFB_REQUIRE(p.stages >= 1, "gemm_tc: tile %d x %d does not fit the shared-memory budget", BM, p.BN);
   const int smem_bytes = p.stages * p.stage_bytes + fixed;
-  if (epi_warps == 4) dfb_launch(gemm_tc_kernel<4>, grid, 64 + 32 * 4, smem_bytes, st, tmA, tmB, tmC, tmD, tmE, p);
-  else dfb_launch(gemm_tc_kernel<8>, grid, 64 + 32 * 8, smem_bytes, st, tmA, tmB, tmC, tmD, tmE, p);
+  const bool gate = p.epi_mode == 1, bsm = p.bias_smem != 0;
+#define TC_LAUNCH(G, S)                                                                                                   \
+  do {                                                                                                                    \
+    if (epi_warps == 4) dfb_launch(gemm_tc_kernel<4, G, S>, grid, 64 + 32 * 4, smem_bytes, st, tmA, tmB, tmC, tmD, tmE, p);  \
+    else dfb_launch(gemm_tc_kernel<8, G, S>, grid, 64 + 32 * 8, smem_bytes, st, tmA, tmB, tmC, tmD, tmE, p);                 \
+  } while (0)
+  if (gate && bsm) TC_LAUNCH(true, true);
+  else if (gate) TC_LAUNCH(true, false);
+  else if (bsm) TC_LAUNCH(false, true);
+  else TC_LAUNCH(false, false);
+#undef TC_LAUNCH
   return dfb_check_launch("gemm_tc");
 }

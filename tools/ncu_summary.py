@@ -35,6 +35,15 @@ def main():
         keys = list(data)
         first = next(i for i, k in enumerate(keys) if "pack_params" in data[k]["k"])
         data = collections.OrderedDict((k, data[k]) for k in keys[first:])
+    if "--gemm-traffic" in sys.argv:         # per-launch DRAM traffic of the tcgen05 GEMM family -> JSON read by bench.py (roofline.traffic)
+        import json
+        i = sys.argv.index("--gemm-traffic")
+        out, src = sys.argv[i + 1], sys.argv[i + 2]
+        del sys.argv[i:i + 3]
+        g = [d for d in data.values() if "gemm_tc_kernel" in d["k"]]
+        json.dump({"dram_bytes_per_launch": sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in g) / len(g),
+                   "launches": len(g), "avg_us_cold_serialised": sum(d.get("gpu__time_duration.sum", 0) for d in g) / len(g), "source": src},
+                  open(out, "w"), indent=1)
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
     agg = collections.defaultdict(lambda: [0.0, 0, 0.0, 0.0])
     for d in data.values():
