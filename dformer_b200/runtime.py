@@ -108,7 +108,7 @@ class GradArena:
 # --------------------------------------------------------------------------------------------- packing
 @dataclass
 class GemmGroup:
-    """Row-concatenation of nn.Linear / conv weights that feed ONE GEMM (e.g. q|q_cut|l)."""
+    """Row-concatenation of nn.Linear / conv weights that feed ONE GEMM (e.g. l|q|q_cut)."""
     name: str
     weights: List[str]                  # parameter names in concat order
     biases: List[Optional[str]]
