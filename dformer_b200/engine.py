@@ -9,6 +9,8 @@ import os
 
 import torch
 
+from .runtime import bump_weights_epoch
+
 _SKIP_BASES = os.environ.get("DFB200_PROFILE_SKIP_BASES", "0") == "1"
 
 
@@ -147,6 +149,7 @@ class GraphedTrainStep:
     def _run(self):
         if self.graph is not None:
             self.graph.replay()
+            bump_weights_epoch()                       # replayed AdamW: cached inference copies of the weights (runtime.ParamPacker) are stale
             if hasattr(self.opt, "step_count"):
                 self.opt.step_count += 1               # host mirror of the device-side step counter the replayed AdamW kernel advances
             return self.loss

@@ -95,15 +95,33 @@ def _bn_fwd(x2d, bn: BNState, out_dtype, act=K.ACT_NONE, residual=None, chan_sca
 _FOLD_BN = _os.environ.get("DFB200_FOLD_BN", "1") == "1"       # inference: conv -> BN(eval) pairs run as one GEMM
 
 
-def _can_fold(bn: BNState, ctx) -> bool:
+def _wants_grad(ctx, st) -> bool:
+    """Will this call ever be differentiated?  `ctx.needs_input_grad` alone is not the answer: autograd fills it from the inputs'
+    `requires_grad` flags even under `torch.no_grad()` (parameters always require grad), i.e. it is True in plain inference; and
+    inside Function.forward the grad mode is always off.  The module that applies the Function records the caller's grad mode in
+    `st.grad` (absent = assume a backward pass may follow)."""
+    return bool(getattr(st, "grad", True)) and any(ctx.needs_input_grad)
+
+
+def _can_fold(bn: BNState, ctx, st) -> bool:
     """eval-mode statistics and no gradient wanted from this call: the BN is a per-channel affine that folds into the conv's GEMM"""
-    return _FOLD_BN and not bn.training and not any(ctx.needs_input_grad)
+    return _FOLD_BN and not bn.training and not _wants_grad(ctx, st)
 
 
-def _lin_bn_folded(x, wb, bn: BNState, T, act=K.ACT_NONE, out_dtype=None):
-    """act(BN_eval(x W^T + b)) as ONE GEMM: the packed weight (re-packed from the fp32 parameters every forward) is scaled in place"""
+def _lin_bn_folded(x, wb, bn: BNState, T, act=K.ACT_NONE, out_dtype=None, cache=None):
+    """act(BN_eval(x W^T + b)) as ONE GEMM: the packed weight is scaled in place.  `cache` (frozen inference, ParamPacker.fold_cache):
+    the fold of this layer is applied once per repack and its bias kept, keyed by the BatchNorm tensors' versions."""
     w, b = wb
-    bias = K.bn_fold(w, w.shape[1], b, bn.running_mean, bn.running_var, bn.eps, bn.weight, bn.bias)
+    key = (w.data_ptr(), bn.running_mean._version, bn.running_var._version, bn.weight._version, bn.bias._version)
+    if cache is not None and bn.prefix in cache and cache[bn.prefix][0] == key:
+        bias = cache[bn.prefix][1]
+    else:
+        if cache is not None and bn.prefix in cache:
+            raise RuntimeError("dformer_b200: BatchNorm buffers of %s changed under a frozen, already folded weight copy; call "
+                               "dformer_b200.runtime.bump_weights_epoch() after editing buffers in place" % bn.prefix)
+        bias = K.bn_fold(w, w.shape[1], b, bn.running_mean, bn.running_var, bn.eps, bn.weight, bn.bias)
+        if cache is not None:
+            cache[bn.prefix] = (key, bias)
     return K.gemm(x, w, trans_b=True, bias=bias, out_dtype=out_dtype or T, act=act, backend=backend_for(T), K=x.shape[1])
 
 
@@ -132,11 +150,12 @@ class StemFn(torch.autograd.Function):
         col1 = K.im2col_fwd(inp, (inp.stride(0), inp.stride(2), inp.stride(3), inp.stride(1)), B, H, W, cin, T, pk1[0].shape[1])
         if getattr(st, "ev_pack", None) is not None:
             torch.cuda.current_stream().wait_event(st.ev_pack)          # the packed weights (side stream) are first needed here
-        if _can_fold(st.bn1, ctx) and _can_fold(st.bn2, ctx):          # inference: both BatchNorms ride in their conv's GEMM
-            a1 = _lin_bn_folded(col1, pk1, st.bn1, T, act=K.ACT_GELU)
+        if _can_fold(st.bn1, ctx, st) and _can_fold(st.bn2, ctx, st):          # inference: both BatchNorms ride in their conv's GEMM
+            fc = getattr(st, "fold_cache", None)
+            a1 = _lin_bn_folded(col1, pk1, st.bn1, T, act=K.ACT_GELU, cache=fc)
             cm = a1.shape[1]
             col2 = K.im2col_fwd(a1, (H1 * W1 * cm, W1 * cm, cm, 1), B, H1, W1, cm, T, pk2[0].shape[1])
-            return _lin_bn_folded(col2, pk2, st.bn2, T, out_dtype=F32)
+            return _lin_bn_folded(col2, pk2, st.bn2, T, out_dtype=F32, cache=fc)
         c1 = _lin(col1, pk1, T)
         a1, ms1, n1 = _bn_fwd(c1, st.bn1, T, act=K.ACT_GELU)
         cm = a1.shape[1]
@@ -281,7 +300,7 @@ class BlockFn(torch.autograd.Function):
         Ce, M, HW = C // 2, x.shape[0], st.H * st.W
         win, dd = st.window != 0, st.drop_depth
         pk = lambda n: st.packed[st.key + n]
-        sv = {"_bwd": any(ctx.needs_input_grad)}          # inference: nothing is kept for a backward pass
+        sv = {"_bwd": _wants_grad(ctx, st)}               # inference: nothing is kept for a backward pass
         side = st.side
         main = torch.cuda.current_stream()
         # bf16: the gating products q * a / cut * e (:134-135) are epilogues of the GEMMs that produce a / e (csrc/gemm_tc.cu "gate"):
@@ -681,10 +700,10 @@ class HeadFn(torch.autograd.Function):
         K.resize_fwd(o1, B, h1, w1, cat, h1, w1, col0=0)
         K.resize_fwd(o2, B, h2, w2, cat, h1, w1, col0=C1)
         K.resize_fwd(o3, B, h3, w3, cat, h1, w1, col0=C1 + C2)
-        fold = _can_fold(st.bn_sq, ctx) and _can_fold(st.bn_al, ctx) and st.drop_mask is None
+        fold = _can_fold(st.bn_sq, ctx, st) and _can_fold(st.bn_al, ctx, st) and st.drop_mask is None
         if fold:
             s_pre, ms_s, n_s = None, None, 0
-            s = _lin_bn_folded(cat, pk("squeeze"), st.bn_sq, T, act=K.ACT_RELU)
+            s = _lin_bn_folded(cat, pk("squeeze"), st.bn_sq, T, act=K.ACT_RELU, cache=getattr(st, "fold_cache", None))
         else:
             s_pre = _lin(cat, pk("squeeze"), T)
             s, ms_s, n_s = _bn_fwd(s_pre, st.bn_sq, T, act=K.ACT_RELU)
@@ -696,7 +715,7 @@ class HeadFn(torch.autograd.Function):
         hs, ms_o, n_o = _bn_fwd(ho_pre, st.bn_out, T, act=K.ACT_RELU, residual=s)
         if fold:
             al_pre, ms_a, n_a = None, None, 0
-            al = _lin_bn_folded(hs, pk("align"), st.bn_al, T, act=K.ACT_RELU)
+            al = _lin_bn_folded(hs, pk("align"), st.bn_al, T, act=K.ACT_RELU, cache=getattr(st, "fold_cache", None))
         else:
             al_pre = _lin(hs, pk("align"), T)
             al, ms_a, n_a = _bn_fwd(al_pre, st.bn_al, T, act=K.ACT_RELU, chan_scale=st.drop_mask, rows_per_sample=h1 * w1)
@@ -764,9 +783,10 @@ class UpsampleCEFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, small, label, meta):
-        B, h, w, ncls, H, W, ignore, want_out = meta
-        ctx.meta = meta
-        ctx.one_pass = (label is not None and not want_out and ctx.needs_input_grad[0] and K.upsample_ce_train_supported(h, w, H, W))
+        B, h, w, ncls, H, W, ignore, want_out = meta[:8]
+        grad = meta[8] if len(meta) > 8 else True            # the caller's grad mode (inside forward it is always off)
+        ctx.meta = meta[:8]
+        ctx.one_pass = (label is not None and not want_out and grad and ctx.needs_input_grad[0] and K.upsample_ce_train_supported(h, w, H, W))
         if ctx.one_pass:          # training without the hi-res logits: loss and (unscaled) gradient from ONE launch, nothing hi-res kept
             loss, acc, dgrad = K.upsample_ce_train(small, B, h, w, ncls, H, W, label, ignore)
             ctx.save_for_backward(dgrad, acc)

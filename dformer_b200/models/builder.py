@@ -78,7 +78,7 @@ class EncoderDecoder(nn.Module):
             return None, Fn.UpsampleFn.apply(s2d, (B, h, w, ncls, H, W))
         lab = label.long().contiguous()
         want_out = getattr(self.cfg, "return_logits", True)
-        loss, out = Fn.UpsampleCEFn.apply(s2d, lab, (B, h, w, ncls, H, W, self._ignore_index(), want_out))
+        loss, out = Fn.UpsampleCEFn.apply(s2d, lab, (B, h, w, ncls, H, W, self._ignore_index(), want_out, torch.is_grad_enabled()))
         return loss, (out if want_out else None)
 
     def encode_decode(self, rgb, modal_x):

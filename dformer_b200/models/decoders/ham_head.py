@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 from ... import functions as Fn
-from ...runtime import GradArena, ParamLayout, ParamPacker, flatten_parameters, is_flat, require_cuda, resolve_dtype
+from ...runtime import GradArena, ParamLayout, ParamPacker, bump_weights_epoch, flatten_parameters, is_flat, require_cuda, resolve_dtype
 from .decode_head import BaseDecodeHead
 
 
@@ -130,7 +130,14 @@ class LightHamHead(BaseDecodeHead):
         flat = [l.permute(0, 2, 3, 1).reshape(-1, l.shape[1]).float().contiguous() for l in lv]   # channels-last views (no copy for our encoder)
         plan = self._plan or self._build_plan()
         dev = flat[0].device
-        packed = plan.packer.pack(dev, T)
+        grad_mode = torch.is_grad_enabled()               # recorded for the Functions: inside Function.forward it is always off
+        # inference (eval mode, no gradients, folding on): the packed copies and the BatchNorm folds applied to them are reused
+        frozen = (not self.training) and (not grad_mode) and Fn._FOLD_BN
+        bn_modes = tuple(m.training for m in self.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm))
+        if not frozen:
+            bump_weights_epoch()
+        packed = plan.packer.pack(dev, T, frozen=frozen, token=bn_modes)
+        fold_cache = plan.packer.fold_cache(dev, T) if frozen else None
         arena = GradArena(plan.layout, dev, self.grad_hook)
         self._last_arena = arena
         training = self.training
@@ -151,7 +158,7 @@ class LightHamHead(BaseDecodeHead):
         sd = getattr(self, "_side_stream", None)
         if sd is None or sd.device != dev:
             sd = self._side_stream = torch.cuda.Stream(device=dev)
-        st = SimpleNamespace(dtype=T, packed=packed, arena=arena, prefix="", tag="head", names=self.PARAMS, B=B, sizes=sizes, wstream=ws, side=sd,
+        st = SimpleNamespace(grad=grad_mode, dtype=T, packed=packed, fold_cache=fold_cache, arena=arena, prefix="", tag="head", names=self.PARAMS, B=B, sizes=sizes, wstream=ws, side=sd,
                              steps=ham.train_steps if training else ham.eval_steps, drop_mask=drop_mask,
                              bn_sq=Fn.BNState(self.squeeze.bn, "squeeze.bn", training, sync),
                              bn_out=Fn.BNState(self.hamburger.ham_out.bn, "hamburger.ham_out.bn", training, sync),

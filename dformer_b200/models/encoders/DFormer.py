@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from ... import functions as Fn
-from ...runtime import GradArena, ParamLayout, ParamPacker, flatten_parameters, is_flat, require_cuda, resolve_dtype
+from ...runtime import GradArena, ParamLayout, ParamPacker, bump_weights_epoch, flatten_parameters, is_flat, require_cuda, resolve_dtype
 
 
 def _norm_layer(norm_cfg, channels):
@@ -254,10 +254,17 @@ class DFormer(nn.Module):
             self._side_stream = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
         side, side2, wstream = self._side_stream
         # compute-dtype copies of the GEMM weights: on a side stream, under the stems' im2col gathers (which need no weights)
+        grad_mode = torch.is_grad_enabled()               # recorded for the Functions: inside Function.forward it is always off
+        # inference (eval mode, no gradients, folding on): the packed copies and the BatchNorm folds applied to them are reused
+        frozen = (not self.training) and (not grad_mode) and Fn._FOLD_BN
+        bn_modes = tuple(m.training for m in self.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm))
+        if not frozen:
+            bump_weights_epoch()
         Fn.K.fork(side2)
         with torch.cuda.stream(side2):
-            packed = plan.packer.pack(dev, T)
+            packed = plan.packer.pack(dev, T, frozen=frozen, token=bn_modes)
             ev_pack = Fn.K.signal(side2)
+        fold_cache = plan.packer.fold_cache(dev, T) if frozen else None
         arena = GradArena(plan.layout, dev, self.grad_hook)
         self._last_arena = arena
         named = plan.named
@@ -276,7 +283,8 @@ class DFormer(nn.Module):
         def stem(inp, sfx, cin):
             p = f"downsample_layers{sfx}.0."
             seq = self.downsample_layers[0] if sfx == "" else self.downsample_layers_e[0]
-            st = SimpleNamespace(dtype=T, cin=cin, packed=packed, ev_pack=ev_pack, g1=p + "c1", g2=p + "c2", arena=arena, prefix=p, tag=p, wstream=wstream,
+            st = SimpleNamespace(grad=grad_mode, dtype=T, cin=cin, packed=packed, ev_pack=ev_pack, fold_cache=fold_cache, g1=p + "c1", g2=p + "c2", arena=arena, prefix=p, tag=p,
+                                 wstream=wstream,
                                  bn1=Fn.BNState(seq[1], p + "1", training, False), bn2=Fn.BNState(seq[4], p + "4", training, False))
             names = ("0.weight", "0.bias", "1.weight", "1.bias", "3.weight", "3.bias", "4.weight", "4.bias")
             return Fn.StemFn.apply(inp, st, *[named[p + n] for n in names])
@@ -284,7 +292,7 @@ class DFormer(nn.Module):
         def down(xx, sfx, i, h, w):
             p = f"downsample_layers{sfx}.{i}."
             seq = self.downsample_layers[i] if sfx == "" else self.downsample_layers_e[i]
-            st = SimpleNamespace(dtype=T, packed=packed, g=p + "c", arena=arena, prefix=p, tag=p, B=B, H=h, W=w,
+            st = SimpleNamespace(grad=grad_mode, dtype=T, packed=packed, g=p + "c", arena=arena, prefix=p, tag=p, B=B, H=h, W=w,
                                  bn=Fn.BNState(seq[0], p + "0", training, True if sync else False))
             return Fn.DownsampleFn.apply(xx, st, *[named[p + n] for n in ("0.weight", "0.bias", "1.weight", "1.bias")])
 
@@ -307,7 +315,7 @@ class DFormer(nn.Module):
             for j, blk in enumerate(self.stages[i]):
                 p = f"stages.{i}.{j}."
                 names = blk.param_names()
-                st = SimpleNamespace(dtype=T, packed=packed, key=p, arena=arena, prefix=p, tag=p, names=names, B=B, H=h, W=w,
+                st = SimpleNamespace(grad=grad_mode, dtype=T, packed=packed, key=p, arena=arena, prefix=p, tag=p, names=names, B=B, H=h, W=w,
                                      C=self.dims[i], heads=blk.num_head, window=blk.window, drop_depth=blk.drop_depth, side=side, side2=side2, wstream=wstream,
                                      dp=(tuple(dp[bi, k] if rates[bi] > 0 else None for k in range(4)) if dp is not None else (None,) * 4))
                 x, x_e = Fn.BlockFn.apply(x, x_e, st, *[named[p + n] for n in names])

@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 
 from . import kernels as K
+from .runtime import bump_weights_epoch
 
 
 def _flat_modules(model):
@@ -59,6 +60,7 @@ class FusedAdamW:
     @torch.no_grad()
     def step(self, lr=None):
         """Uses the gradient arenas written by the last backward pass (p.grad views alias them)."""
+        bump_weights_epoch()                          # the kernel below rewrites parameters without touching autograd's version counters
         self.step_count += 1
         lr = self.lr if lr is None else lr
         dev = self.state[0]["m"].device if self.state else None

@@ -221,6 +221,62 @@ def test_bf16_parity(variant, B, H, W, init):
     assert pt["ours_min"] >= min(0.90, pt["ref_min"] - 0.05), pt
 
 
+def test_frozen_inference_reuses_packed_weights_and_notices_every_kind_of_update():
+    """eval mode + no_grad: the packed GEMM operands and the BatchNorm folds are made once and reused (no pack_params / bn_fold launches
+    in later forwards); in-place parameter edits (autograd version counters), the fused optimizer and graph replays (weights epoch)
+    and a training-mode forward all invalidate them."""
+    from dformer_b200 import kernels as K
+    from dformer_b200._lib import lib
+    from dformer_b200.optim import FusedAdamW
+    from dformer_b200.runtime import bump_weights_epoch
+    m, _ = build("DFormer-Tiny", 40, "bf16", 9, train=False)
+    for mod in m.modules():
+        if isinstance(mod, nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.3)
+            mod.running_var.uniform_(0.5, 2.0)
+    rgb, hha, label, bases = (t.cuda() for t in make_inputs(2, 64, 96, 40, seed=9))
+    m.decode_head.injected_bases = bases
+
+    def infer():
+        n0 = lib().launch_count()
+        with torch.no_grad():
+            o = m(rgb, hha)
+        return o.float().clone(), lib().launch_count() - n0
+
+    # "same" / "different" by relative L2 distance: two runs of the same forward agree to rounding only (the split-K reductions of
+    # the few-tile GEMMs add their partial sums with fp32 atomics in arrival order, one bf16 ulp downstream)
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    o1, n1 = infer()
+    o2, n2 = infer()
+    assert rel(o2, o1) < 5e-3 and n2 <= n1 - 10, (rel(o2, o1), n1, n2)       # 2 + 2 packing launches and 6 folds less
+    fresh = lambda: (bump_weights_epoch(), infer())[1][0]
+    # (a) in-place edits of parameters: autograd's version counters
+    with torch.no_grad():
+        m.encoder_backbone.stages[0][0].attn.q.weight.mul_(3.0)
+        m.decode_head.conv_seg.weight.mul_(1.5)
+    o3, n3 = infer()
+    assert rel(o3, o1) > 0.1 and n3 == n1, (rel(o3, o1), n3, n1)
+    assert rel(o3, fresh()) < 5e-3
+    # (b) a training step with the fused optimizer (parameters rewritten by a kernel), then inference again
+    m.train()
+    m.decode_head.dropout = None
+    opt = FusedAdamW(m, lr=1e-2)
+    loss, _ = m(rgb, hha, label.clamp(max=39))
+    loss.backward()
+    opt.step()
+    opt.zero_grad()
+    m.eval()
+    o4, _ = infer()
+    assert rel(o4, o3) > 0.1, rel(o4, o3)
+    assert rel(o4, fresh()) < 5e-3
+    # (c) BatchNorm statistics replaced through load_state_dict
+    sd = {k: (v * 1.5 if k.endswith("running_var") else v) for k, v in m.state_dict().items()}
+    m.load_state_dict(sd)
+    o5, _ = infer()
+    assert rel(o5, o4) > 0.05, rel(o5, o4)
+    assert rel(o5, fresh()) < 5e-3
+
+
 def test_cpu_tensors_are_rejected_loudly():
     m, _ = build("DFormer-Tiny", 40, "fp32", 1, False)
     with pytest.raises(RuntimeError, match="no CPU"):
