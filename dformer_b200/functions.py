@@ -255,7 +255,14 @@ def _mlp_fwd(x, pfx, st, P, sv, scale_b, pre=None):
         u, z = K.dwconv_fwd(h, P[pfx + "pos.weight"], P[pfx + "pos.bias"], B, H, W, 3, add_input=True, act=K.ACT_GELU, save_z=True)
     ls = P["layer_scale_2" if pfx == "mlp." else "layer_scale_2_e"]
     f = _lin(u, st.packed[st.key + pfx + "fc2"], T)
-    out = K.scale_residual_fwd(x, f, ls, scale_b, H * W)
+    carry = getattr(st, "carry", None)
+    if carry is not None:
+        # not the last Block of its stage: the residual x + dp * ls * f (:176/:179) is applied by the NEXT Block's first LayerNorm
+        # kernel (`_carried_layernorm`), which writes it into the buffer returned here -- one pass over x less per stream and Block
+        out = torch.empty_like(x)
+        carry[pfx] = (x, f, ls, scale_b, out)
+    else:
+        out = K.scale_residual_fwd(x, f, ls, scale_b, H * W)
     sv.update({pfx + "x": x, pfx + "mu": mu, pfx + "rs": rs, pfx + "hn": hn, pfx + "h": h, pfx + "u": u, pfx + "f": f, pfx + "z": z})
     return out
 
@@ -282,6 +289,18 @@ def _mlp_bwd(dout, pfx, st, P, sv, scale_b, G):
     dhn = _lin_bwd(dh, sv[pfx + "hn"], w1, G[pfx + "fc1.weight"], G[pfx + "fc1.bias"], T)
     return K.layernorm_bwd(dhn, sv[pfx + "x"], P[pfx + "norm.weight"], sv[pfx + "mu"], sv[pfx + "rs"], dout,
                            G[pfx + "norm.weight"], G[pfx + "norm.bias"])
+
+
+def _carried_layernorm(x, pfx, st, gamma, beta):
+    """First LayerNorm of a Block (DFormer.py:104-105).  When the previous Block of the stage left its MLP residual pending
+    (`_mlp_fwd`), x is that Block's still unwritten output buffer: the residual is formed, stored into x and normalised in one pass."""
+    pend = st.pending.pop(pfx, None) if getattr(st, "pending", None) is not None else None
+    if pend is None:
+        return K.layernorm_fwd(x, gamma, beta, 1e-6, st.dtype)
+    res, f, ls, scale_b, out = pend
+    assert out.data_ptr() == x.data_ptr() and out.shape == x.shape, "pending residual does not belong to this Block's input"
+    _, xn, mu, rs = K.scale_residual_layernorm_fwd(res, f, ls, scale_b, st.H * st.W, gamma, beta, 1e-6, out=out)
+    return xn, mu, rs
 
 
 class BlockFn(torch.autograd.Function):
@@ -312,7 +331,7 @@ class BlockFn(torch.autograd.Function):
         # ---- depth gate path on the side stream
         K.fork(side)
         with torch.cuda.stream(side):
-            en, mu2, rs2 = K.layernorm_fwd(x_e, P["attn.norm_e.weight"], P["attn.norm_e.bias"], 1e-6, T)
+            en, mu2, rs2 = _carried_layernorm(x_e, "mlp_e2.", st, P["attn.norm_e.weight"], P["attn.norm_e.bias"])
             ev_en = K.signal(side)
             ef = _lin(en, pk("attn.e_fore"), T)
             ec = K.dwconv_fwd(ef, P["attn.e_conv.weight"], P["attn.e_conv.bias"], B, H, W, 7)
@@ -320,7 +339,7 @@ class BlockFn(torch.autograd.Function):
                 e = _lin(ec, pk("attn.e_back"), T)
                 ev_e = K.signal(side)
         # ---- RGB path
-        xn, mu1, rs1 = K.layernorm_fwd(x, P["attn.norm.weight"], P["attn.norm.bias"], 1e-6, T)
+        xn, mu1, rs1 = _carried_layernorm(x, "mlp.", st, P["attn.norm.weight"], P["attn.norm.bias"])
         if win:                                                       # global-awareness branch on a second side stream:
             side2 = st.side2                                          # the pooled queries only need the two LayerNorm outputs, so they
             K.fork(side2)                                             # are computed while the main stream runs the q|cut|l GEMM
@@ -495,7 +514,14 @@ class BlockFn(torch.autograd.Function):
 
 
 # ============================================================================================ NMF2D
-def _nmf_fwd(x, bases_raw, steps, T, side=None):
+def nmf_prepare(bases_raw, T):
+    """`F.normalize(bases, dim=1)` of the freshly drawn bases (ham_head.py:111-115) + their compute-dtype copy.  Depends on nothing the
+    network computes, so the head issues it on its side stream under the resize / squeeze kernels (LightHamHead.forward)."""
+    bases, _ = K.normalize_cols(bases_raw)
+    return bases, (bases if T == F32 else K.cast(bases, torch.bfloat16))
+
+
+def _nmf_fwd(x, bases_raw, steps, T, side=None, prepared=None):
     """ham_head.py:60-100,109-145 on channels-last x [B, N, D] (compute dtype); bases_raw [B, D, R] fp32.
 
     The factor state (coef, bases) and every multiplicative update stay fp32; in bf16 mode the batched matrix
@@ -541,8 +567,7 @@ def _nmf_fwd(x, bases_raw, steps, T, side=None):
         return v
 
     acc_z = zpool is not None                                   # accumulate into the pre-zeroed view (no memset launched by the GEMM)
-    bases, _ = K.normalize_cols(bases_raw)
-    bases_l = lo(bases)
+    bases, bases_l = prepared if prepared is not None else nmf_prepare(bases_raw, T)
     S = K.bgemm(x, bases_l, f(B, N, R), M=N, N=R, K=D)
     coef = K.softmax_rows(S)
     coef_l = lo(coef)
@@ -700,6 +725,8 @@ class HeadFn(torch.autograd.Function):
         K.resize_fwd(o1, B, h1, w1, cat, h1, w1, col0=0)
         K.resize_fwd(o2, B, h2, w2, cat, h1, w1, col0=C1)
         K.resize_fwd(o3, B, h3, w3, cat, h1, w1, col0=C1 + C2)
+        if getattr(st, "ev_prologue", None) is not None:         # weight packing / Dropout2d mask / normalised bases from the side stream
+            torch.cuda.current_stream().wait_event(st.ev_prologue)
         fold = _can_fold(st.bn_sq, ctx, st) and _can_fold(st.bn_al, ctx, st) and st.drop_mask is None
         if fold:
             s_pre, ms_s, n_s = None, None, 0
@@ -709,7 +736,8 @@ class HeadFn(torch.autograd.Function):
             s, ms_s, n_s = _bn_fwd(s_pre, st.bn_sq, T, act=K.ACT_RELU)
         hin = _lin(s, pk("ham_in"), T, act=K.ACT_RELU)
         D = hin.shape[1]
-        nmf, nmf_saved = _nmf_fwd(hin.view(B, h1 * w1, D), bases_raw, st.steps, T, side=getattr(st, "side", None))
+        nmf, nmf_saved = _nmf_fwd(hin.view(B, h1 * w1, D), bases_raw, st.steps, T, side=getattr(st, "side", None),
+                                  prepared=getattr(st, "bases_prepared", None))
         nmf2d = nmf.view(M, D)
         ho_pre = _lin(nmf2d, pk("ham_out"), T)
         hs, ms_o, n_o = _bn_fwd(ho_pre, st.bn_out, T, act=K.ACT_RELU, residual=s)

@@ -177,10 +177,15 @@ def layernorm_fwd(x, gamma, beta, eps, out_dtype):
     return y, mean, rstd
 
 
-def scale_residual_layernorm_fwd(res, branch, ls, scale_b, rows_per_sample, gamma, beta, eps):
-    """x1 = res + scale_b * ls * branch (fp32) and LN(x1) in branch.dtype in one pass: returns (x1, y, mean, rstd)."""
+def scale_residual_layernorm_fwd(res, branch, ls, scale_b, rows_per_sample, gamma, beta, eps, out=None):
+    """x1 = res + scale_b * ls * branch (fp32) and LN(x1) in branch.dtype in one pass: returns (x1, y, mean, rstd).
+    `out` (optional, fp32 [M, C] contiguous) receives x1 instead of a fresh tensor."""
     M, C = res.shape
-    x1 = torch.empty_like(res)
+    if out is None:
+        x1 = torch.empty_like(res)
+    else:
+        assert out.shape == res.shape and out.dtype == res.dtype and out.is_contiguous() and out.device == res.device
+        x1 = out
     y = torch.empty((M, C), device=res.device, dtype=branch.dtype)
     mean = torch.empty(M, device=res.device, dtype=torch.float32)
     rstd = torch.empty(M, device=res.device, dtype=torch.float32)

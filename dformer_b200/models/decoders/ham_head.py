@@ -136,21 +136,10 @@ class LightHamHead(BaseDecodeHead):
         bn_modes = tuple(m.training for m in self.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm))
         if not frozen:
             bump_weights_epoch()
-        packed = plan.packer.pack(dev, T, frozen=frozen, token=bn_modes)
-        fold_cache = plan.packer.fold_cache(dev, T) if frozen else None
         arena = GradArena(plan.layout, dev, self.grad_hook)
         self._last_arena = arena
         training = self.training
         ham = self.hamburger.ham
-        bases = self.injected_bases if self.injected_bases is not None else ham.draw_bases(B, ham.D, dev)
-        bases = bases.to(dev, torch.float32).contiguous()
-        if tuple(bases.shape) != (B * ham.S, ham.D, ham.R):
-            raise ValueError(f"NMF bases have shape {tuple(bases.shape)}, this batch needs {(B * ham.S, ham.D, ham.R)} "
-                             "(injected_bases must match the batch of the call)")
-        drop_mask = None
-        if training and self.dropout is not None and self.dropout.p > 0:
-            keep = 1.0 - self.dropout.p
-            drop_mask = (torch.rand(B, self.channels, device=dev) < keep).float() / keep             # Dropout2d: whole channels per sample
         sync = True if (self.sync_bn and training) else False
         ws = getattr(self, "_wstream", None)
         if ws is None or ws.device != dev:
@@ -158,7 +147,28 @@ class LightHamHead(BaseDecodeHead):
         sd = getattr(self, "_side_stream", None)
         if sd is None or sd.device != dev:
             sd = self._side_stream = torch.cuda.Stream(device=dev)
-        st = SimpleNamespace(grad=grad_mode, dtype=T, packed=packed, fold_cache=fold_cache, arena=arena, prefix="", tag="head", names=self.PARAMS, B=B, sizes=sizes, wstream=ws, side=sd,
+        # Prologue on the side stream, under the head's resize kernels: nothing here depends on the encoder's output -- the compute-dtype
+        # copies of the GEMM weights, the Dropout2d channel mask and the normalised NMF bases.  HeadFn waits for `ev_prologue`
+        # in front of its first GEMM.
+        main = torch.cuda.current_stream()
+        Fn.K.fork(sd)
+        with torch.cuda.stream(sd):
+            packed = plan.packer.pack(dev, T, frozen=frozen, token=bn_modes)
+            bases = self.injected_bases if self.injected_bases is not None else ham.draw_bases(B, ham.D, dev)
+            bases = bases.to(dev, torch.float32).contiguous()
+            if tuple(bases.shape) != (B * ham.S, ham.D, ham.R):
+                raise ValueError(f"NMF bases have shape {tuple(bases.shape)}, this batch needs {(B * ham.S, ham.D, ham.R)} "
+                                 "(injected_bases must match the batch of the call)")
+            bases.record_stream(sd)                         # injected bases usually live on the caller's stream
+            bases_prepared = Fn.nmf_prepare(bases, T)
+            drop_mask = None
+            if training and self.dropout is not None and self.dropout.p > 0:
+                keep = 1.0 - self.dropout.p
+                drop_mask = (torch.rand(B, self.channels, device=dev) < keep).float() / keep         # Dropout2d: whole channels per sample
+            ev_prologue = Fn.K.signal(sd)
+        Fn.K.share(main, bases, drop_mask, *bases_prepared)
+        fold_cache = plan.packer.fold_cache(dev, T) if frozen else None
+        st = SimpleNamespace(ev_prologue=ev_prologue, bases_prepared=bases_prepared, grad=grad_mode, dtype=T, packed=packed, fold_cache=fold_cache, arena=arena, prefix="", tag="head", names=self.PARAMS, B=B, sizes=sizes, wstream=ws, side=sd,
                              steps=ham.train_steps if training else ham.eval_steps, drop_mask=drop_mask,
                              bn_sq=Fn.BNState(self.squeeze.bn, "squeeze.bn", training, sync),
                              bn_out=Fn.BNState(self.hamburger.ham_out.bn, "hamburger.ham_out.bn", training, sync),

@@ -312,14 +312,20 @@ class DFormer(nn.Module):
             else:
                 h, w = (h + 1) // 2, (w + 1) // 2
             Fn.K.join(side)
+            # MLP residuals left pending by a Block for the next Block's first LayerNorm kernel (functions._mlp_fwd / _carried_layernorm);
+            # the last Block of a stage materialises its outputs (they are the stage output and the downsample input)
+            handover = {}
+            n_blk = len(self.stages[i])
             for j, blk in enumerate(self.stages[i]):
                 p = f"stages.{i}.{j}."
                 names = blk.param_names()
                 st = SimpleNamespace(grad=grad_mode, dtype=T, packed=packed, key=p, arena=arena, prefix=p, tag=p, names=names, B=B, H=h, W=w,
                                      C=self.dims[i], heads=blk.num_head, window=blk.window, drop_depth=blk.drop_depth, side=side, side2=side2, wstream=wstream,
-                                     dp=(tuple(dp[bi, k] if rates[bi] > 0 else None for k in range(4)) if dp is not None else (None,) * 4))
+                                     dp=(tuple(dp[bi, k] if rates[bi] > 0 else None for k in range(4)) if dp is not None else (None,) * 4),
+                                     pending=handover, carry=handover if j + 1 < n_blk else None)
                 x, x_e = Fn.BlockFn.apply(x, x_e, st, *[named[p + n] for n in names])
                 bi += 1
+            assert not handover, "a Block left a residual pending at the end of its stage"
             outs.append(x.view(B, h, w, self.dims[i]).permute(0, 3, 1, 2))
         return outs, None
 

@@ -48,7 +48,7 @@ agg = defaultdict(lambda: [0.0, 0])
 rows = []
 for ev in evs:
     nm = ev.name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0][:70]
-    rows.append((ev.time_range.start - t0, ev.time_range.end - ev.time_range.start, nm))
+    rows.append((ev.time_range.start - t0, ev.time_range.end - ev.time_range.start, nm, getattr(ev, "device_resource_id", -1)))
     agg[nm][0] += ev.time_range.end - ev.time_range.start
     agg[nm][1] += 1
 print(f"{len(rows)} kernels, span {rows[-1][0] + rows[-1][1]:.1f} us, sum of durations {sum(r[1] for r in rows):.1f} us")
@@ -56,5 +56,5 @@ for nm, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:25]:
     print(f"{t:9.1f} us  x{n:<4d} {nm}")
 if len(sys.argv) > 2:
     with open(sys.argv[2], "w") as fh:
-        for s_, d_, nm in rows:
-            fh.write(f"{s_:.2f},{d_:.2f},{nm}\n")
+        for s_, d_, nm, sid in rows:
+            fh.write(f"{s_:.2f},{d_:.2f},{sid},{nm}\n")
