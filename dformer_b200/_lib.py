@@ -86,6 +86,11 @@ SIGNATURES = {
     "dfb200_peer_open": [P, P],
     "dfb200_peer_close": [P],
     "dfb200_peer_allreduce": [P, P, I, I, P, I, I, P],
+    "dfb200_nccl_version": [P],
+    "dfb200_nccl_unique_id": [P],
+    "dfb200_nccl_comm_init": [P, I, I, P],
+    "dfb200_nccl_all_reduce": [P, P, L, I, I, P],
+    "dfb200_nccl_comm_destroy": [P],
     "dfb200_axpy": [P, I, F, P, I, L, P],
     "dfb200_upsample_ce_fwd": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, P],
     "dfb200_upsample_ce_bwd_sep": [P, I, I, I, I, I, I, I, P, I, P, P, P, P, P, I, P],

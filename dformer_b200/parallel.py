@@ -190,3 +190,56 @@ def small_all_reduce_(t, group=None):
         return t
     dist.all_reduce(t, group=group)
     return t
+
+
+class NativeNccl:
+    """Host mirror of the `dfb200_nccl_*` C-ABI wrappers (include/dfb200.h): an NCCL communicator created WITHOUT torch.distributed,
+    for hosts that drive libdformer_b200.so directly.  The Python product path above keeps torch.distributed's NCCL backend; this
+    class exists so that the wrappers are exercised (tests/test_nccl_abi*.py) and documents the call sequence a C/C++ host follows:
+
+        id = NativeNccl.unique_id()            # rank 0; ship the 128 bytes to the other ranks out of band
+        comm = NativeNccl(id, nranks, rank)    # collective; the current CUDA device is this rank's GPU
+        comm.all_reduce_(arena_slice, average=True, stream=comm_stream)     # per finished gradient bucket
+    """
+
+    _DT = {torch.float32: 0, torch.bfloat16: 1, torch.float64: 2}
+
+    @staticmethod
+    def version():
+        import ctypes
+
+        from ._lib import lib
+        v = ctypes.c_int(0)
+        lib().nccl_version(ctypes.byref(v))
+        return v.value
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import ctypes
+
+        from ._lib import lib
+        buf = (ctypes.c_ubyte * 128)()
+        lib().nccl_unique_id(buf)
+        return bytes(buf)
+
+    def __init__(self, unique_id: bytes, nranks: int, rank: int):
+        import ctypes
+
+        from ._lib import lib
+        assert len(unique_id) == 128
+        self._comm = ctypes.c_void_p()
+        self.nranks, self.rank = nranks, rank
+        lib().nccl_comm_init((ctypes.c_ubyte * 128).from_buffer_copy(unique_id), nranks, rank, ctypes.byref(self._comm))
+
+    def all_reduce_(self, t, average=True, stream=None):
+        from ._lib import lib
+        assert t.is_cuda and t.is_contiguous() and t.dtype in self._DT
+        st = stream if stream is not None else torch.cuda.current_stream(t.device)
+        lib().nccl_all_reduce(self._comm, t.data_ptr(), t.numel(), self._DT[t.dtype], 1 if average else 0, st.cuda_stream)
+        return t
+
+    def destroy(self):
+        from ._lib import lib
+        if self._comm is not None and self._comm.value:
+            lib().nccl_comm_destroy(self._comm)
+        self._comm = None

@@ -329,6 +329,21 @@ int dfb200_peer_open(const unsigned char* handle64, void** ptr);
 int dfb200_peer_close(void* ptr);
 int dfb200_peer_allreduce(const void* in, void* out, int dtype, int n, void* const* bases_dev, int rank, int world, void* stream);
 
+/* ---- NCCL thin wrappers: the gradient all-reduce of DistributedDataParallel (utils/train.py:238-243) ------
+ * For hosts that do not bring torch.distributed (the Python mirror uses torch.distributed's NCCL backend, dformer_b200/parallel.py).
+ * libnccl is resolved at run time: $DFB200_NCCL_LIB, else "libnccl.so.2" (inside a PyTorch process: the already loaded
+ * torch-bundled library), else "libnccl.so"; every call returns -3 with a message when it cannot be found.
+ *   dfb200_nccl_unique_id: rank 0 fills 128 bytes (ncclUniqueId) and ships them to the other ranks out of band;
+ *   dfb200_nccl_comm_init: collective over the `nranks` processes (one per GPU; the calling thread's current device is the rank's GPU);
+ *   dfb200_nccl_all_reduce: in place on `buf` (count elements, dtype 0 = float32, 1 = bfloat16, 2 = float64), sum or -- `average`
+ *                           != 0 -- mean over the ranks (ncclAvg, what DDP applies to gradients), asynchronous on `stream`:
+ *                           call it per finished bucket of the flat gradient arena on a communication stream. */
+int dfb200_nccl_version(int* version);
+int dfb200_nccl_unique_id(void* id128);
+int dfb200_nccl_comm_init(const void* id128, int nranks, int rank, void** comm);
+int dfb200_nccl_all_reduce(void* comm, void* buf, long count, int dtype, int average, void* stream);
+int dfb200_nccl_comm_destroy(void* comm);
+
 #ifdef __cplusplus
 }
 #endif
